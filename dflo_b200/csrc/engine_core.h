@@ -1,0 +1,909 @@
+// Orchestration of the explicit RK stage, independent of where the kernels execute.
+// Engine<Backend> owns the device buffers and issues the kernels of kernels.cuh through the
+// backend: CudaBackend (engine_cuda.cu, the product: CUDA streams, graphs, NCCL) or the CPU
+// emulation backend of tests/emu (test infrastructure only; it is never part of the shipped
+// library).  Mirrors ConservationLaw<dim>::iterate_explicit and compute_time_step
+// (reference src/claw.cc:444-511, 725-772).
+#pragma once
+
+#include "../../include/dflo_b200.h"
+#include "expr.h"
+#include "kernels.cuh"
+#include "partition.h"
+#include "tables.h"
+#include "tables_pack.h"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace dflo
+{
+   //---------------------------------------------------------------------------------------------
+   // small thread-per-item kernels (thread(args, global_thread_index))
+   //---------------------------------------------------------------------------------------------
+   struct CellAverageKernel
+   {
+      typedef AvgArgs Args;
+      static DFLO_DEV void thread (const Args &A, int j) { cell_average_thread (A, j); }
+   };
+
+   // Gather between the reference DoF layout (global cell order, optional deal.II dof map) and the
+   // engine's local cell order.
+   struct LayoutArgs
+   {
+      double *local;             // [n_cells_local][D]
+      double *ext;               // staging copy of the caller's vector
+      const int *l2g;            // local -> global cell
+      const uint32_t *dof_map;   // optional
+      int64_t ext_offset;        // ext[0] corresponds to reference position ext_offset (no dof_map)
+      int n_cells, D, to_local;
+   };
+   struct LayoutKernel
+   {
+      typedef LayoutArgs Args;
+      static DFLO_DEV void thread (const Args &A, int j)
+      {
+         if (j >= A.n_cells * A.D) return;
+         const int l = j / A.D, i = j % A.D;
+         const int64_t ref = (int64_t) A.l2g[l] * A.D + i;
+         const int64_t e = A.dof_map ? (int64_t) A.dof_map[ref] : ref - A.ext_offset;
+         if (A.to_local)
+            A.local[j] = A.ext[e];
+         else
+            A.ext[e] = A.local[j];
+      }
+   };
+
+   // rows of 4 (cell averages) or 1 (flags) between local and global cell order
+   struct RowGatherArgs
+   {
+      const double *src;
+      double *dst;
+      const int *idx; // dst row r <- src row idx[r]
+      int n_rows, width;
+   };
+   struct RowGatherKernel
+   {
+      typedef RowGatherArgs Args;
+      static DFLO_DEV void thread (const Args &A, int j)
+      {
+         if (j >= A.n_rows * A.width) return;
+         const int r = j / A.width, c = j % A.width;
+         A.dst[j] = A.src[(size_t) A.idx[r] * A.width + c];
+      }
+   };
+
+   // boundary values g(x,t) at the face quadrature points from the compiled expressions
+   struct BcEvalArgs
+   {
+      double *bc_g;              // [n_bfaces][nqf][4]
+      const int *bf_cell, *bf_face, *bf_id;
+      const double *geom;
+      const double *gx;          // Gauss nodes [nqf]
+      const ExprInstr *code;     // all programs back to back
+      const int *prog_start;     // [10*4 + 1] offsets; empty program => keep the stored value
+      const double *time;        // [0] t, [1] dt
+      int n_bfaces, nqf;
+      int use_t_plus_dt;
+   };
+   struct BcEvalKernel
+   {
+      typedef BcEvalArgs Args;
+      static DFLO_DEV void thread (const Args &A, int j)
+      {
+         if (j >= A.n_bfaces * A.nqf) return;
+         const int bf = j / A.nqf, q = j % A.nqf;
+         const int cell = A.bf_cell[bf], f = A.bf_face[bf], id = A.bf_id[bf];
+         const double *g = A.geom + (size_t) cell * 4;
+         const double s = A.gx[q];
+         const double x = g[0] + (f == 0 ? 0.0 : f == 1 ? 1.0 : s) * g[2];
+         const double y = g[1] + (f == 2 ? 0.0 : f == 3 ? 1.0 : s) * g[3];
+         const double t = A.time[0] + (A.use_t_plus_dt ? A.time[1] : 0.0);
+         for (int c = 0; c < 4; ++c)
+         {
+            const int p0 = A.prog_start[id * 4 + c], p1 = A.prog_start[id * 4 + c + 1];
+            if (p1 > p0) A.bc_g[(size_t) j * 4 + c] = expr_eval (A.code + p0, p1 - p0, x, y, t);
+         }
+      }
+   };
+
+   // time scalars on the device: [0] t, [1] dt, [2] dt accumulator (min over cells), [3] final time
+   struct DtArgs
+   {
+      const double *avg;
+      const double *geom;
+      double *time;
+      int n_cells, degree;
+      double cfl;
+   };
+   struct DtKernel // phase kernel: per-cell dt, block minimum, one atomic per block
+   {
+      typedef DtArgs Args;
+      static constexpr int THREADS = 256;
+      static constexpr int NPHASE = 3;
+      static constexpr int SMEM_DOUBLES = THREADS;
+      static int grid (int n) { return (n + THREADS - 1) / THREADS; }
+      static DFLO_DEV void phase (int p, const Args &A, double *sm, int tid, int bid)
+      {
+         const int cell = bid * THREADS + tid;
+         if (p == 0)
+            sm[tid] = cell < A.n_cells ? cell_time_step (A.avg + (size_t) cell * 4, A.geom + (size_t) cell * 4, A.cfl, A.degree) : 1.0e20;
+         else if (p == 1)
+         {
+            if (tid < 16)
+            {
+               double m = sm[tid];
+               for (int i = tid + 16; i < THREADS; i += 16) m = std_min (m, sm[i]);
+               sm[tid] = m;
+            }
+         }
+         else if (tid == 0)
+         {
+            double m = sm[0];
+            for (int i = 1; i < 16; ++i) m = std_min (m, sm[i]);
+#if defined(__CUDA_ARCH__)
+            // positive doubles order like their bit patterns
+            atomicMin ((unsigned long long *) (A.time + 2), (unsigned long long) __double_as_longlong (m));
+#else
+            if (m < A.time[2]) A.time[2] = m;
+#endif
+         }
+      }
+   };
+   struct DtFinalizeArgs
+   {
+      double *time;
+      double time_step;
+   };
+   struct DtFinalizeKernel // claw.cc:468-476
+   {
+      typedef DtFinalizeArgs Args;
+      static DFLO_DEV void thread (const Args &A, int j)
+      {
+         if (j != 0) return;
+         double dt = A.time[2];
+         if (dt > 0 && A.time_step > 0) dt = std_min (dt, A.time_step);
+         if (A.time[0] + dt > A.time[3]) dt = A.time[3] - A.time[0];
+         A.time[1] = dt;
+         A.time[2] = 1.0e20;
+      }
+   };
+   struct AdvanceTimeKernel // claw.cc:1072
+   {
+      typedef DtFinalizeArgs Args;
+      static DFLO_DEV void thread (const Args &A, int j)
+      {
+         if (j == 0) A.time[0] += A.time[1];
+      }
+   };
+
+   struct SumSqArgs
+   {
+      const double *v;
+      double *out;
+      int64_t n;
+   };
+   struct SumSqKernel // right_hand_side.l2_norm()^2, claw.cc:749
+   {
+      typedef SumSqArgs Args;
+      static constexpr int THREADS = 256;
+      static constexpr int NPHASE = 3;
+      static constexpr int SMEM_DOUBLES = THREADS;
+      static int grid (int64_t n) { int64_t g = (n + THREADS * 8 - 1) / (THREADS * 8); return (int) (g < 1 ? 1 : g > 1184 ? 1184 : g); }
+      static DFLO_DEV void phase (int p, const Args &A, double *sm, int tid, int bid)
+      {
+         if (p == 0)
+         {
+            double s = 0.0;
+            const int64_t stride = (int64_t) grid (A.n) * THREADS;
+            for (int64_t i = (int64_t) bid * THREADS + tid; i < A.n; i += stride) s += A.v[i] * A.v[i];
+            sm[tid] = s;
+         }
+         else if (p == 1)
+         {
+            if (tid < 16)
+            {
+               double s = sm[tid];
+               for (int i = tid + 16; i < THREADS; i += 16) s += sm[i];
+               sm[tid] = s;
+            }
+         }
+         else if (tid == 0)
+         {
+            double s = 0.0;
+            for (int i = 0; i < 16; ++i) s += sm[i];
+#if defined(__CUDA_ARCH__)
+            atomicAdd (A.out, s);
+#else
+            *A.out += s;
+#endif
+         }
+      }
+   };
+
+   struct PackArgs
+   {
+      const double *src;
+      double *dst;
+      const int *cells;
+      int n_cells, width;
+   };
+   struct PackKernel // halo pack: dst[r][:] = src[cells[r]][:]
+   {
+      typedef PackArgs Args;
+      static DFLO_DEV void thread (const Args &A, int j)
+      {
+         if (j >= A.n_cells * A.width) return;
+         const int r = j / A.width, c = j % A.width;
+         A.dst[j] = A.src[(size_t) A.cells[r] * A.width + c];
+      }
+   };
+
+   //---------------------------------------------------------------------------------------------
+   // compile-time dispatch over (basis, degree, flux)
+   //---------------------------------------------------------------------------------------------
+   template <class BK, int BASIS, int N1>
+   struct StageDispatch
+   {
+      static void run (BK &bk, int flux, const StageArgs &a)
+      {
+         switch (flux)
+         {
+            case FLUX_LXF: bk.template launch<StageKernel<BASIS, N1, FLUX_LXF>> (StageKernel<BASIS, N1, FLUX_LXF>::grid (a.n_compute), a); break;
+            case FLUX_SW: bk.template launch<StageKernel<BASIS, N1, FLUX_SW>> (StageKernel<BASIS, N1, FLUX_SW>::grid (a.n_compute), a); break;
+            case FLUX_KFVS: bk.template launch<StageKernel<BASIS, N1, FLUX_KFVS>> (StageKernel<BASIS, N1, FLUX_KFVS>::grid (a.n_compute), a); break;
+            case FLUX_ROE: bk.template launch<StageKernel<BASIS, N1, FLUX_ROE>> (StageKernel<BASIS, N1, FLUX_ROE>::grid (a.n_compute), a); break;
+            default: bk.template launch<StageKernel<BASIS, N1, FLUX_HLLC>> (StageKernel<BASIS, N1, FLUX_HLLC>::grid (a.n_compute), a); break;
+         }
+      }
+   };
+
+   template <class BK>
+   void launch_stage (BK &bk, int basis, int n1, int flux, const StageArgs &a)
+   {
+      if (n1 == 1) // degree 0: Q0 == P0
+         StageDispatch<BK, BASIS_QK, 1>::run (bk, flux, a);
+      else if (basis == BASIS_QK)
+      {
+         if (n1 == 2) StageDispatch<BK, BASIS_QK, 2>::run (bk, flux, a);
+         else if (n1 == 3) StageDispatch<BK, BASIS_QK, 3>::run (bk, flux, a);
+         else if (n1 == 4) StageDispatch<BK, BASIS_QK, 4>::run (bk, flux, a);
+         else StageDispatch<BK, BASIS_QK, 5>::run (bk, flux, a);
+      }
+      else
+      {
+         if (n1 == 2) StageDispatch<BK, BASIS_PK, 2>::run (bk, flux, a);
+         else if (n1 == 3) StageDispatch<BK, BASIS_PK, 3>::run (bk, flux, a);
+         else StageDispatch<BK, BASIS_PK, 4>::run (bk, flux, a);
+      }
+   }
+
+   template <class BK>
+   void launch_limiter (BK &bk, int basis, int n1, const LimiterArgs &a)
+   {
+      if (n1 == 1) return;
+#define DFLO_LIM(B, N) bk.template launch<LimiterKernel<B, N>> (LimiterKernel<B, N>::grid (a.n_compute), a)
+      if (basis == BASIS_QK)
+      {
+         if (n1 == 2) DFLO_LIM (BASIS_QK, 2);
+         else if (n1 == 3) DFLO_LIM (BASIS_QK, 3);
+         else if (n1 == 4) DFLO_LIM (BASIS_QK, 4);
+         else DFLO_LIM (BASIS_QK, 5);
+      }
+      else
+      {
+         if (n1 == 2) DFLO_LIM (BASIS_PK, 2);
+         else if (n1 == 3) DFLO_LIM (BASIS_PK, 3);
+         else DFLO_LIM (BASIS_PK, 4);
+      }
+#undef DFLO_LIM
+   }
+
+   //---------------------------------------------------------------------------------------------
+   // The engine
+   //---------------------------------------------------------------------------------------------
+   template <class BK>
+   class Engine
+   {
+   public:
+      BK bk;
+      dflo_params prm;
+      FeTables tab;
+      LocalMesh lm;
+      std::string error;
+      int n_rk;
+      double ark[3];
+
+      // device state
+      double *U[3] = {nullptr, nullptr, nullptr};
+      double *AVG[3] = {nullptr, nullptr, nullptr};
+      int cur = 0, old = 0;
+      double *rhs = nullptr;
+      double *d_time = nullptr;       // t, dt, dt accumulator, final time
+      double *d_scratch = nullptr;    // [1] reductions
+      int *d_nbr = nullptr;
+      unsigned char *d_fflags = nullptr;
+      double *d_geom = nullptr, *d_bc_g = nullptr, *d_stage_tab = nullptr, *d_lim_tab = nullptr, *d_gw = nullptr, *d_gx = nullptr;
+      int *d_bkind = nullptr, *d_bf_cell = nullptr, *d_bf_face = nullptr, *d_bf_id = nullptr, *d_l2g = nullptr, *d_flags = nullptr;
+      unsigned int *d_err = nullptr;
+      ExprInstr *d_code = nullptr;
+      int *d_prog_start = nullptr;
+      double *d_ext = nullptr;        // staging for set/get_solution
+      size_t ext_capacity = 0;
+      uint32_t *d_dofmap = nullptr;
+      size_t dofmap_capacity = 0;
+      // halo
+      std::vector<int *> d_send_cells[2];
+      std::vector<double *> d_send_u[2], d_send_avg[2];
+      // boundary expressions
+      std::vector<ExprInstr> programs[DFLO_MAX_BOUNDARIES][4];
+      bool have_programs = false, programs_time_dependent = false;
+      int n_global_bfaces = 0;
+
+      int D () const { return tab.D; }
+      bool tvb () const { return prm.limiter_type == DFLO_LIMITER_TVB && tab.k > 0; }
+      bool pos () const { return prm.pos_lim && tab.k > 0; }
+
+      int init (const dflo_flat_mesh &mesh, const dflo_params &p, int rank, int world)
+      {
+         prm = p;
+         if (p.basis != DFLO_BASIS_QK && p.basis != DFLO_BASIS_PK) return fail (DFLO_E_INVALID, "unknown basis");
+         if (!build_tables (p.basis, p.degree, tab)) return fail (DFLO_E_UNSUPPORTED, "degree out of range (Qk 0..4, Pk 0..3)");
+         if (p.flux_type < 0 || p.flux_type > 4) return fail (DFLO_E_INVALID, "unknown flux");
+         if (mesh.n_cells <= 0) return fail (DFLO_E_INVALID, "empty mesh");
+         for (int b = 0; b < mesh.n_boundary_faces; ++b)
+            if (mesh.bface_id[b] < 0 || mesh.bface_id[b] >= DFLO_MAX_BOUNDARIES) return fail (DFLO_E_INVALID, "boundary id out of range");
+         // claw.cc:141-159
+         if (tab.k == 0) { n_rk = 1; ark[0] = 0.0; }
+         else if (tab.k == 1) { n_rk = 2; ark[0] = 0.0; ark[1] = 0.5; }
+         else { n_rk = 3; ark[0] = 0.0; ark[1] = 3.0 / 4.0; ark[2] = 1.0 / 3.0; }
+         const int layers = tvb () ? 2 : 1;
+         std::string e;
+         if (!build_local_mesh (mesh, rank, world, layers, lm, e)) return fail (DFLO_E_INVALID, e);
+         n_global_bfaces = mesh.n_boundary_faces;
+
+         const size_t nd = (size_t) lm.n_local * D ();
+         for (int i = 0; i < 3; ++i)
+         {
+            U[i] = bk.template alloc<double> (nd);
+            AVG[i] = bk.template alloc<double> ((size_t) lm.n_local * 4);
+            bk.zero (U[i], nd * sizeof (double));
+            bk.zero (AVG[i], (size_t) lm.n_local * 4 * sizeof (double));
+         }
+         d_time = bk.template alloc<double> (4);
+         const double t0[4] = {0.0, 0.0, 1.0e20, 1.0e20};
+         bk.h2d (d_time, t0, sizeof (t0));
+         d_scratch = bk.template alloc<double> (4);
+         d_nbr = upload (lm.nbr);
+         d_fflags = upload (lm.fflags);
+         d_geom = upload (lm.geom);
+         d_l2g = upload (lm.l2g);
+         std::vector<int> kinds (std::max<size_t> (1, lm.bf_id.size ()), 0);
+         for (size_t b = 0; b < lm.bf_id.size (); ++b) kinds[b] = prm.bc_kind[lm.bf_id[b]];
+         d_bkind = upload (kinds);
+         d_bf_cell = upload (pad1 (lm.bf_cell));
+         d_bf_face = upload (pad1 (lm.bf_face));
+         d_bf_id = upload (pad1 (lm.bf_id));
+         const size_t ng = std::max<size_t> (1, lm.bf_id.size ()) * tab.n1 * 4;
+         d_bc_g = bk.template alloc<double> (ng);
+         bk.zero (d_bc_g, ng * sizeof (double));
+         d_stage_tab = upload (pack_stage_tables (tab));
+         d_lim_tab = upload (pack_limiter_tables (tab));
+         d_gw = upload (std::vector<double> (tab.gw, tab.gw + tab.n1));
+         d_gx = upload (std::vector<double> (tab.gx, tab.gx + tab.n1));
+         d_flags = bk.template alloc<int> (lm.n_local);
+         bk.zero (d_flags, lm.n_local * sizeof (int));
+         d_err = bk.template alloc<unsigned int> (1);
+         bk.zero (d_err, sizeof (unsigned int));
+         d_prog_start = bk.template alloc<int> (DFLO_MAX_BOUNDARIES * 4 + 1);
+         for (auto &pr : lm.peers)
+            for (int k = 0; k < 2; ++k)
+            {
+               d_send_cells[k].push_back (upload (pad1 (pr.send_cells[k])));
+               d_send_u[k].push_back (bk.template alloc<double> (std::max<size_t> (1, pr.send_cells[k].size ()) * D ()));
+               d_send_avg[k].push_back (bk.template alloc<double> (std::max<size_t> (1, pr.send_cells[k].size ()) * 4));
+            }
+         return bk.check (error);
+      }
+
+      void release ()
+      {
+         bk.sync ();
+         bk.drop_graphs ();
+         for (int i = 0; i < 3; ++i)
+         {
+            bk.free (U[i]);
+            bk.free (AVG[i]);
+         }
+         void *ptrs[] = {rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
+                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_ext, d_dofmap};
+         for (void *p : ptrs) bk.free (p);
+         for (int k = 0; k < 2; ++k)
+         {
+            for (auto p : d_send_cells[k]) bk.free (p);
+            for (auto p : d_send_u[k]) bk.free (p);
+            for (auto p : d_send_avg[k]) bk.free (p);
+         }
+      }
+
+      //------------------------------------------------------------------------------------------
+      int set_solution (const double *u, const uint32_t *dof_map, size_t n)
+      {
+         if (n != (size_t) lm.n_global * D ()) return fail (DFLO_E_INVALID, "set_solution: wrong vector length");
+         bk.halo_wait ();
+         int rc = stage_external (u, dof_map, n, true);
+         if (rc) return rc;
+         layout (U[cur], dof_map != nullptr, true);
+         compute_cell_average (cur, lm.n_owned);
+         exchange_halo (cur);
+         old = cur;
+         bk.drop_graphs ();
+         return bk.check (error);
+      }
+
+      int get_solution (double *u, const uint32_t *dof_map, size_t n) { return get_vector (U[cur], u, dof_map, n); }
+
+      int get_rhs (double *r, const uint32_t *dof_map, size_t n)
+      {
+         if (!rhs) return fail (DFLO_E_INVALID, "get_rhs before assemble_rhs");
+         return get_vector (rhs, r, dof_map, n);
+      }
+
+      int get_cell_average (double *avg)
+      {
+         bk.halo_wait ();
+         bk.sync ();
+         std::vector<double> loc ((size_t) lm.n_owned * 4);
+         bk.d2h (loc.data (), AVG[cur], loc.size () * sizeof (double));
+         for (int l = 0; l < lm.n_owned; ++l)
+            for (int c = 0; c < 4; ++c) avg[(size_t) lm.l2g[l] * 4 + c] = loc[(size_t) l * 4 + c];
+         return bk.check (error);
+      }
+
+      int get_limited_flags (int32_t *flags)
+      {
+         bk.sync ();
+         std::vector<int> loc (lm.n_owned);
+         bk.d2h (loc.data (), d_flags, loc.size () * sizeof (int));
+         for (int l = 0; l < lm.n_owned; ++l) flags[lm.l2g[l]] = loc[l];
+         return bk.check (error);
+      }
+
+      int commit_step ()
+      {
+         old = cur;
+         return DFLO_OK;
+      }
+
+      //------------------------------------------------------------------------------------------
+      int set_boundary_values (const double *g)
+      {
+         const int nqf = tab.n1;
+         std::vector<double> loc (std::max<size_t> (1, lm.bf_global.size ()) * nqf * 4, 0.0);
+         for (size_t b = 0; b < lm.bf_global.size (); ++b)
+            std::memcpy (&loc[b * nqf * 4], g + (size_t) lm.bf_global[b] * nqf * 4, sizeof (double) * nqf * 4);
+         bk.h2d (d_bc_g, loc.data (), loc.size () * sizeof (double));
+         return bk.check (error);
+      }
+
+      int set_boundary_expression (int id, int comp, const char *text)
+      {
+         if (id < 0 || id >= DFLO_MAX_BOUNDARIES || comp < 0 || comp > 3) return fail (DFLO_E_INVALID, "boundary id/component out of range");
+         ExprCompiler cc;
+         std::string e;
+         std::vector<ExprInstr> code;
+         bool uses_t = false;
+         if (!cc.compile (text, code, e, &uses_t)) return fail (DFLO_E_EXPR, e);
+         programs[id][comp] = code;
+         // flatten all programs
+         std::vector<ExprInstr> all;
+         std::vector<int> start (DFLO_MAX_BOUNDARIES * 4 + 1, 0);
+         for (int b = 0; b < DFLO_MAX_BOUNDARIES; ++b)
+            for (int c = 0; c < 4; ++c)
+            {
+               start[b * 4 + c] = all.size ();
+               all.insert (all.end (), programs[b][c].begin (), programs[b][c].end ());
+            }
+         start[DFLO_MAX_BOUNDARIES * 4] = all.size ();
+         bk.sync ();
+         bk.free (d_code);
+         d_code = bk.template alloc<ExprInstr> (std::max<size_t> (1, all.size ()));
+         bk.h2d (d_code, all.data (), all.size () * sizeof (ExprInstr));
+         bk.h2d (d_prog_start, start.data (), start.size () * sizeof (int));
+         have_programs = true;
+         programs_time_dependent = programs_time_dependent || uses_t;
+         bk.drop_graphs ();
+         eval_boundary (false); // values at the current time
+         return bk.check (error);
+      }
+
+      //------------------------------------------------------------------------------------------
+      // assemble_system, assemble_explicit.cc:433-452
+      int assemble_rhs (double t_bc)
+      {
+         bk.halo_wait ();
+         if (!rhs)
+         {
+            rhs = bk.template alloc<double> ((size_t) lm.n_local * D ());
+            bk.zero (rhs, (size_t) lm.n_local * D () * sizeof (double));
+         }
+         set_time (0, t_bc);
+         eval_boundary (false);
+         StageArgs a = stage_args (0, MODE_RHS);
+         a.out = rhs;
+         a.n_compute = lm.n_owned;
+         launch_stage (bk, tab.basis, tab.n1, prm.flux_type, a);
+         return bk.check (error);
+      }
+
+      // one pass of the rk loop body, claw.cc:747-766, with host-supplied dt and BC time
+      int rk_stage (int rk, double t_bc, double dt, double *res_norm)
+      {
+         if (rk < 0 || rk >= n_rk) return fail (DFLO_E_INVALID, "rk out of range");
+         bk.halo_wait ();
+         if (res_norm)
+         {
+            int rc = assemble_rhs (t_bc);
+            if (rc) return rc;
+            const double z = 0.0;
+            bk.h2d (d_scratch, &z, sizeof (double));
+            SumSqArgs s;
+            s.v = rhs;
+            s.out = d_scratch;
+            s.n = (int64_t) lm.n_owned * D ();
+            bk.template launch<SumSqKernel> (SumSqKernel::grid (s.n), s);
+            bk.allreduce_sum (d_scratch, 1);
+            double ss = 0.0;
+            bk.sync ();
+            bk.d2h (&ss, d_scratch, sizeof (double));
+            *res_norm = sqrt (ss);
+         }
+         const double td[2] = {t_bc, dt};
+         bk.h2d (d_time, td, sizeof (td));
+         eval_boundary (false);
+         enqueue_stage (rk);
+         return bk.check (error);
+      }
+
+      // claw.cc:997-1003: limit the initial condition (TVB only)
+      int limit_initial_condition ()
+      {
+         bk.halo_wait ();
+         if (tvb ())
+         {
+            LimiterArgs a = limiter_args (cur);
+            a.pos_lim = 0;
+            launch_limiter (bk, tab.basis, tab.n1, a);
+            exchange_halo (cur);
+         }
+         old = cur;
+         return bk.check (error);
+      }
+
+      // compute_time_step, claw.cc:444-511 (global time step)
+      int compute_dt (double elapsed, double final_time, double *dt)
+      {
+         bk.halo_wait ();
+         const double t0[4] = {elapsed, 0.0, 1.0e20, final_time};
+         bk.h2d (d_time, t0, sizeof (t0));
+         enqueue_dt ();
+         bk.sync ();
+         double t[2];
+         bk.d2h (t, d_time, sizeof (t));
+         *dt = t[1];
+         return bk.check (error);
+      }
+
+      // n whole steps on the device, claw.cc:1026-1110
+      int advance (int n_steps, double final_time, double *elapsed, double *last_dt)
+      {
+         bk.halo_wait ();
+         const double t0[4] = {*elapsed, 0.0, 1.0e20, final_time};
+         bk.h2d (d_time, t0, sizeof (t0));
+         bk.timer_start ();
+         for (int s = 0; s < n_steps; ++s)
+         {
+            // at the start of a step old == cur, so the buffer rotation of the whole step is
+            // a function of cur alone: one CUDA graph per starting buffer
+            int cur_after = 0;
+            if (bk.graph_launch (cur, &cur_after))
+            {
+               cur = cur_after;
+               old = cur;
+            }
+            else
+            {
+               const int key = cur;
+               const bool capturing = bk.capture_begin ();
+               enqueue_step ();
+               if (capturing) bk.capture_end_and_launch (key, cur);
+            }
+         }
+         bk.timer_stop ();
+         bk.sync ();
+         double t[2];
+         bk.d2h (t, d_time, sizeof (t));
+         *elapsed = t[0];
+         if (last_dt) *last_dt = t[1];
+         int rc = bk.check (error);
+         if (rc) return rc;
+         return poll_error ();
+      }
+
+      int poll_error ()
+      {
+         bk.sync ();
+         unsigned int e = 0;
+         bk.d2h (&e, d_err, sizeof (e));
+         if (e & ERR_NEGATIVE_STATE) return fail (DFLO_E_NEGATIVE_STATE, "Fatal: Negative states");
+         if (e & ERR_POSLIM_ROOT) return fail (DFLO_E_POSLIM_ROOT, "Problem in positivity limiter");
+         return bk.check (error);
+      }
+
+   private:
+      int fail (int code, const std::string &msg)
+      {
+         error = msg;
+         return code;
+      }
+
+      template <class T>
+      static std::vector<T> pad1 (const std::vector<T> &v)
+      {
+         std::vector<T> r = v;
+         if (r.empty ()) r.push_back (T ());
+         return r;
+      }
+
+      template <class T>
+      T *upload (const std::vector<T> &v)
+      {
+         T *d = bk.template alloc<T> (std::max<size_t> (1, v.size ()));
+         if (!v.empty ()) bk.h2d (d, v.data (), v.size () * sizeof (T));
+         return d;
+      }
+
+      void set_time (int slot, double v) { bk.h2d (d_time + slot, &v, sizeof (double)); }
+
+      int free_buffer () const
+      {
+         for (int i = 0; i < 3; ++i)
+            if (i != cur && i != old) return i;
+         return 0;
+      }
+
+      StageArgs stage_args (int rk, int mode)
+      {
+         StageArgs a;
+         a.u = U[cur];
+         a.u_old = U[old];
+         a.out = nullptr;
+         a.avg = AVG[cur];
+         a.avg_out = nullptr;
+         a.nbr = d_nbr;
+         a.fflags = d_fflags;
+         a.geom = d_geom;
+         a.bc_g = d_bc_g;
+         a.bkind = d_bkind;
+         a.tab = d_stage_tab;
+         a.time = d_time;
+         a.dt_cell = nullptr;
+         a.n_compute = lm.n_compute;
+         a.mode = mode;
+         a.compat_mpi = prm.compat == DFLO_COMPAT_MPI;
+         a.ark = ark[rk];
+         a.gravity = prm.gravity;
+         return a;
+      }
+
+      LimiterArgs limiter_args (int buf)
+      {
+         LimiterArgs a;
+         a.u = U[buf];
+         a.avg = AVG[buf];
+         a.nbr = d_nbr;
+         a.fflags = d_fflags;
+         a.geom = d_geom;
+         a.tab = d_lim_tab;
+         a.flags_out = d_flags;
+         a.err = d_err;
+         a.n_compute = lm.n_owned;
+         a.tvb = tvb ();
+         a.char_lim = prm.char_lim;
+         a.pos_lim = pos ();
+         a.cam = prm.conserve_angular_momentum;
+         a.M = prm.M;
+         a.beta = prm.beta;
+         return a;
+      }
+
+      void compute_cell_average (int buf, int n_cells)
+      {
+         AvgArgs a;
+         a.u = U[buf];
+         a.avg = AVG[buf];
+         a.gw = d_gw;
+         a.n_cells = n_cells;
+         a.basis = tab.basis;
+         a.n1 = tab.n1;
+         a.ns = tab.ns;
+         bk.template launch1d<CellAverageKernel> (n_cells * 4, a);
+      }
+
+      void eval_boundary (bool t_plus_dt)
+      {
+         if (!have_programs || lm.bf_id.empty ()) return;
+         BcEvalArgs a;
+         a.bc_g = d_bc_g;
+         a.bf_cell = d_bf_cell;
+         a.bf_face = d_bf_face;
+         a.bf_id = d_bf_id;
+         a.geom = d_geom;
+         a.gx = d_gx;
+         a.code = d_code;
+         a.prog_start = d_prog_start;
+         a.time = d_time;
+         a.n_bfaces = lm.bf_id.size ();
+         a.nqf = tab.n1;
+         a.use_t_plus_dt = t_plus_dt;
+         bk.template launch1d<BcEvalKernel> (a.n_bfaces * a.nqf, a);
+      }
+
+      void enqueue_dt ()
+      {
+         DtArgs a;
+         a.avg = AVG[cur];
+         a.geom = d_geom;
+         a.time = d_time;
+         a.n_cells = lm.n_owned;
+         a.degree = tab.k;
+         a.cfl = prm.cfl;
+         bk.template launch<DtKernel> (DtKernel::grid (a.n_cells), a);
+         bk.allreduce_min_dt (d_time + 2);
+         DtFinalizeArgs f;
+         f.time = d_time;
+         f.time_step = prm.time_step;
+         bk.template launch1d<DtFinalizeKernel> (1, f);
+      }
+
+      // stage kernel + limiters + halo for rk, reading d_time for dt
+      void enqueue_stage (int rk)
+      {
+         const int out = free_buffer ();
+         StageArgs a = stage_args (rk, MODE_STAGE);
+         a.out = U[out];
+         a.avg_out = AVG[out];
+         launch_stage (bk, tab.basis, tab.n1, prm.flux_type, a);
+         if (tvb () || pos ())
+         {
+            LimiterArgs l = limiter_args (out);
+            launch_limiter (bk, tab.basis, tab.n1, l);
+         }
+         cur = out;
+         exchange_halo (cur);
+      }
+
+      void enqueue_step ()
+      {
+         enqueue_dt ();
+         for (int rk = 0; rk < n_rk; ++rk)
+         {
+            // bc time: t for rk 0, t+dt afterwards (src/claw.cc:736-745); always t in src_mpi
+            if (programs_time_dependent) eval_boundary (rk > 0 && prm.compat == DFLO_COMPAT_SRC);
+            enqueue_stage (rk);
+         }
+         DtFinalizeArgs f;
+         f.time = d_time;
+         f.time_step = prm.time_step;
+         bk.template launch1d<AdvanceTimeKernel> (1, f);
+         old = cur;
+      }
+
+      void exchange_halo (int buf)
+      {
+         if (lm.peers.empty ()) return;
+         for (size_t p = 0; p < lm.peers.size (); ++p)
+            for (int k = 0; k < 2; ++k)
+            {
+               const int n = lm.peers[p].send_cells[k].size ();
+               if (!n) continue;
+               PackArgs a;
+               a.src = U[buf];
+               a.dst = d_send_u[k][p];
+               a.cells = d_send_cells[k][p];
+               a.n_cells = n;
+               a.width = D ();
+               bk.template launch1d<PackKernel> (n * D (), a);
+               a.src = AVG[buf];
+               a.dst = d_send_avg[k][p];
+               a.width = 4;
+               bk.template launch1d<PackKernel> (n * 4, a);
+            }
+         bk.halo_begin ();
+         for (size_t p = 0; p < lm.peers.size (); ++p)
+            for (int k = 0; k < 2; ++k)
+            {
+               const HaloPeer &pr = lm.peers[p];
+               const int ns = pr.send_cells[k].size ();
+               if (ns)
+               {
+                  bk.halo_send (pr.rank, d_send_u[k][p], (size_t) ns * D ());
+                  bk.halo_send (pr.rank, d_send_avg[k][p], (size_t) ns * 4);
+               }
+               if (pr.recv_count[k])
+               {
+                  bk.halo_recv (pr.rank, U[buf] + (size_t) pr.recv_start[k] * D (), (size_t) pr.recv_count[k] * D ());
+                  bk.halo_recv (pr.rank, AVG[buf] + (size_t) pr.recv_start[k] * 4, (size_t) pr.recv_count[k] * 4);
+               }
+            }
+         bk.halo_end ();
+      }
+
+      // caller vector -> device staging
+      int stage_external (const double *u, const uint32_t *dof_map, size_t n, bool to_device)
+      {
+         const size_t need = dof_map ? n : (size_t) lm.n_owned * D ();
+         if (ext_capacity < need)
+         {
+            bk.sync ();
+            bk.free (d_ext);
+            d_ext = bk.template alloc<double> (need);
+            ext_capacity = need;
+         }
+         if (dof_map)
+         {
+            if (dofmap_capacity < n)
+            {
+               bk.sync ();
+               bk.free (d_dofmap);
+               d_dofmap = bk.template alloc<uint32_t> (n);
+               dofmap_capacity = n;
+            }
+            bk.h2d (d_dofmap, dof_map, n * sizeof (uint32_t));
+         }
+         if (to_device)
+         {
+            if (dof_map)
+               bk.h2d (d_ext, u, n * sizeof (double));
+            else
+               bk.h2d (d_ext, u + (size_t) lm.begin * D (), need * sizeof (double));
+         }
+         return DFLO_OK;
+      }
+
+      void layout (double *local, bool with_map, bool to_local)
+      {
+         LayoutArgs a;
+         a.local = local;
+         a.ext = d_ext;
+         a.l2g = d_l2g;
+         a.dof_map = with_map ? d_dofmap : nullptr;
+         a.ext_offset = (int64_t) lm.begin * D ();
+         a.n_cells = lm.n_owned;
+         a.D = D ();
+         a.to_local = to_local;
+         bk.template launch1d<LayoutKernel> (lm.n_owned * D (), a);
+      }
+
+      int get_vector (const double *local, double *u, const uint32_t *dof_map, size_t n)
+      {
+         if (n != (size_t) lm.n_global * D ()) return fail (DFLO_E_INVALID, "get: wrong vector length");
+         bk.halo_wait ();
+         int rc = stage_external (nullptr, dof_map, n, false);
+         if (rc) return rc;
+         if (dof_map)
+         {
+            // other ranks' entries must survive: start from the caller's content
+            bk.h2d (d_ext, u, n * sizeof (double));
+         }
+         layout (const_cast<double *> (local), dof_map != nullptr, false);
+         bk.sync ();
+         if (dof_map)
+            bk.d2h (u, d_ext, n * sizeof (double));
+         else
+            bk.d2h (u + (size_t) lm.begin * D (), d_ext, (size_t) lm.n_owned * D () * sizeof (double));
+         return bk.check (error);
+      }
+   };
+}

@@ -1,0 +1,420 @@
+#include "mesh.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <sstream>
+#include <unordered_map>
+
+namespace dflo
+{
+   dflo_flat_mesh FlatMesh::view () const
+   {
+      dflo_flat_mesh m;
+      m.n_cells = n_cells ();
+      m.cell_origin = origin.data ();
+      m.cell_size = size.data ();
+      m.neighbor = neighbor.data ();
+      m.face_flags = face_flags.data ();
+      m.n_boundary_faces = n_bfaces ();
+      m.bface_cell = bface_cell.data ();
+      m.bface_face = bface_face.data ();
+      m.bface_id = bface_id.data ();
+      return m;
+   }
+
+   namespace
+   {
+      // local vertex pairs of the faces left, right, bottom, top (deal.II faces 0..3)
+      const int FV[4][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}};
+
+      inline uint64_t edge_key (int a, int b)
+      {
+         const uint64_t lo = a < b ? a : b, hi = a < b ? b : a;
+         return (hi << 32) | lo;
+      }
+   }
+
+   bool flatten (const PrimitiveMesh &pm, const int bc_kind[DFLO_MAX_BOUNDARIES],
+                 const int periodic_pair[DFLO_MAX_BOUNDARIES], FlatMesh &out, std::string &err)
+   {
+      const int nc = pm.n_cells ();
+      out = FlatMesh ();
+      out.origin.resize (2 * (size_t) nc);
+      out.size.resize (2 * (size_t) nc);
+      out.neighbor.assign (4 * (size_t) nc, -1);
+      out.face_flags.assign (4 * (size_t) nc, 0);
+
+      struct Side { int cell, face; };
+      std::unordered_map<uint64_t, std::pair<Side, Side>> edges;
+      edges.reserve (2 * (size_t) nc + 16);
+      const double *V = pm.vertices.data ();
+      for (int c = 0; c < nc; ++c)
+      {
+         const int *v = &pm.cells[4 * (size_t) c];
+         const double x0 = V[2 * v[0]], y0 = V[2 * v[0] + 1];
+         const double hx = V[2 * v[1]] - x0, hy = V[2 * v[2] + 1] - y0;
+         const double tol = 1e-12 * (std::fabs (hx) + std::fabs (hy));
+         if (!(hx > 0 && hy > 0) || std::fabs (V[2 * v[1] + 1] - y0) > tol || std::fabs (V[2 * v[2]] - x0) > tol
+             || std::fabs (V[2 * v[3]] - (x0 + hx)) > tol || std::fabs (V[2 * v[3] + 1] - (y0 + hy)) > tol)
+         {
+            err = "cell " + std::to_string (c) + " is not an axis-aligned rectangle with lexicographic vertices (mapping = cartesian)";
+            return false;
+         }
+         out.origin[2 * (size_t) c] = x0;
+         out.origin[2 * (size_t) c + 1] = y0;
+         out.size[2 * (size_t) c] = hx;
+         out.size[2 * (size_t) c + 1] = hy;
+         for (int f = 0; f < 4; ++f)
+         {
+            const uint64_t k = edge_key (v[FV[f][0]], v[FV[f][1]]);
+            auto it = edges.find (k);
+            if (it == edges.end ())
+               edges.emplace (k, std::make_pair (Side{c, f}, Side{-1, -1}));
+            else if (it->second.second.cell < 0)
+               it->second.second = Side{c, f};
+            else
+            {
+               err = "face shared by more than two cells";
+               return false;
+            }
+         }
+      }
+      std::unordered_map<uint64_t, int> line_id;
+      for (int b = 0; b < pm.n_blines (); ++b) line_id[edge_key (pm.blines[2 * b], pm.blines[2 * b + 1])] = pm.bline_id[b];
+
+      // boundary id of every (cell,face) that has no vertex-sharing neighbour; -1 elsewhere
+      std::vector<int> bid (4 * (size_t) nc, -1);
+      for (auto &kv : edges)
+      {
+         const Side a = kv.second.first, b = kv.second.second;
+         if (b.cell >= 0)
+         {
+            if ((a.face ^ 1) != b.face)
+            {
+               err = "neighbouring cells are not equally oriented (mapping = cartesian)";
+               return false;
+            }
+            out.neighbor[4 * (size_t) a.cell + a.face] = b.cell;
+            out.neighbor[4 * (size_t) b.cell + b.face] = a.cell;
+            // MeshWorker::loop integrates an interior face once, from the smaller cell
+            out.face_flags[4 * (size_t) a.cell + a.face] = a.cell < b.cell ? DFLO_FACE_OWNER : 0;
+            out.face_flags[4 * (size_t) b.cell + b.face] = b.cell < a.cell ? DFLO_FACE_OWNER : 0;
+         }
+         else
+         {
+            auto it = line_id.find (kv.first);
+            const int id = it == line_id.end () ? 0 : it->second; // unlisted faces get id 0
+            if (id < 0 || id >= DFLO_MAX_BOUNDARIES)
+            {
+               err = "boundary id " + std::to_string (id) + " out of range";
+               return false;
+            }
+            bid[4 * (size_t) a.cell + a.face] = id;
+         }
+      }
+
+      // periodic partners: same tangential coordinate, opposite face, partner id
+      std::map<int, std::vector<Side>> by_id;
+      for (int c = 0; c < nc; ++c)
+         for (int f = 0; f < 4; ++f)
+         {
+            const int id = bid[4 * (size_t) c + f];
+            if (id >= 0 && bc_kind[id] == DFLO_BC_PERIODIC) by_id[id].push_back (Side{c, f});
+         }
+      auto tangential = [&] (const Side &s) {
+         return s.face < 2 ? out.origin[2 * (size_t) s.cell + 1] + 0.5 * out.size[2 * (size_t) s.cell + 1]
+                           : out.origin[2 * (size_t) s.cell] + 0.5 * out.size[2 * (size_t) s.cell];
+      };
+      for (auto &kv : by_id)
+      {
+         const int partner = periodic_pair[kv.first];
+         if (partner < 0 || partner >= DFLO_MAX_BOUNDARIES || !by_id.count (partner))
+         {
+            err = "periodic boundary " + std::to_string (kv.first) + " has no partner boundary";
+            return false;
+         }
+         std::vector<Side> cand = by_id[partner];
+         std::sort (cand.begin (), cand.end (), [&] (const Side &a, const Side &b) { return tangential (a) < tangential (b); });
+         for (const Side &s : kv.second)
+         {
+            const double t = tangential (s);
+            const double tol = 1e-9 * (out.size[2 * (size_t) s.cell] + out.size[2 * (size_t) s.cell + 1]);
+            auto lo = std::lower_bound (cand.begin (), cand.end (), t - tol, [&] (const Side &a, double val) { return tangential (a) < val; });
+            int found = -1;
+            for (auto it = lo; it != cand.end () && tangential (*it) <= t + tol; ++it)
+               if (it->face == (s.face ^ 1)) found = it->cell;
+            if (found < 0)
+            {
+               err = "periodic face without partner";
+               return false;
+            }
+            out.neighbor[4 * (size_t) s.cell + s.face] = found;
+            out.face_flags[4 * (size_t) s.cell + s.face] = DFLO_FACE_PERIODIC;
+         }
+      }
+
+      // genuine boundary faces ordered by (cell, face)
+      for (int c = 0; c < nc; ++c)
+         for (int f = 0; f < 4; ++f)
+            if (out.neighbor[4 * (size_t) c + f] < 0)
+            {
+               out.neighbor[4 * (size_t) c + f] = -1 - (int) out.bface_cell.size ();
+               out.bface_cell.push_back (c);
+               out.bface_face.push_back (f);
+               out.bface_id.push_back (bid[4 * (size_t) c + f]);
+            }
+      return true;
+   }
+
+   namespace
+   {
+      // Union of lattice-aligned blocks sharing one vertex lattice; boundary ids assigned to the
+      // outer edges by a classifier on the edge mid point.
+      struct LatticeBuilder
+      {
+         double X0, Y0, dx, dy;
+         std::map<std::pair<int, int>, int> vid;
+         PrimitiveMesh pm;
+
+         int vertex (int i, int j)
+         {
+            auto key = std::make_pair (i, j);
+            auto it = vid.find (key);
+            if (it != vid.end ()) return it->second;
+            const int id = pm.n_vertices ();
+            pm.vertices.push_back (X0 + i * dx);
+            pm.vertices.push_back (Y0 + j * dy);
+            vid[key] = id;
+            return id;
+         }
+
+         void block (int i0, int j0, int ni, int nj)
+         {
+            for (int j = 0; j < nj; ++j)
+               for (int i = 0; i < ni; ++i)
+               {
+                  pm.cells.push_back (vertex (i0 + i, j0 + j));
+                  pm.cells.push_back (vertex (i0 + i + 1, j0 + j));
+                  pm.cells.push_back (vertex (i0 + i, j0 + j + 1));
+                  pm.cells.push_back (vertex (i0 + i + 1, j0 + j + 1));
+               }
+         }
+
+         // classify(xm, ym, face) -> boundary id
+         void boundary (const std::function<int (double, double, int)> &classify)
+         {
+            std::unordered_map<uint64_t, std::pair<int, int>> cnt; // edge -> (count, cell*4+face)
+            const int nc = pm.n_cells ();
+            for (int c = 0; c < nc; ++c)
+               for (int f = 0; f < 4; ++f)
+               {
+                  auto &e = cnt[edge_key (pm.cells[4 * c + FV[f][0]], pm.cells[4 * c + FV[f][1]])];
+                  e.first++;
+                  e.second = 4 * c + f;
+               }
+            std::vector<int> outer;
+            for (auto &kv : cnt)
+               if (kv.second.first == 1) outer.push_back (kv.second.second);
+            std::sort (outer.begin (), outer.end ());
+            for (int cf : outer)
+            {
+               const int c = cf / 4, f = cf % 4;
+               const int a = pm.cells[4 * c + FV[f][0]], b = pm.cells[4 * c + FV[f][1]];
+               const double xm = 0.5 * (pm.vertices[2 * a] + pm.vertices[2 * b]);
+               const double ym = 0.5 * (pm.vertices[2 * a + 1] + pm.vertices[2 * b + 1]);
+               pm.blines.push_back (a);
+               pm.blines.push_back (b);
+               pm.bline_id.push_back (classify (xm, ym, f));
+            }
+         }
+      };
+   }
+
+   PrimitiveMesh make_rectangle (int nx, int ny, double x0, double x1, double y0, double y1, const int ids[4])
+   {
+      LatticeBuilder lb;
+      lb.X0 = x0;
+      lb.Y0 = y0;
+      lb.dx = (x1 - x0) / nx;
+      lb.dy = (y1 - y0) / ny;
+      lb.block (0, 0, nx, ny);
+      lb.boundary ([&] (double, double, int f) { return ids[f]; });
+      return lb.pm;
+   }
+
+   // examples/isentropic_vortex/grid.geo: [-5,5]^2; Physical Line 1 bottom, 2 right, 3 top, 4 left
+   PrimitiveMesh make_isentropic_vortex_grid (int n)
+   {
+      const int ids[4] = {4, 2, 1, 3};
+      return make_rectangle (n, n, -5.0, 5.0, -5.0, 5.0, ids);
+   }
+
+   // examples/sod_shock_tube/tube.geo: [0,1] x [0, ny*dx]; Physical Line 0 walls, 1 outlet (right),
+   // 2 inlet (left)
+   PrimitiveMesh make_sod_tube (int nx, int ny)
+   {
+      const double dx = 1.0 / nx;
+      const int ids[4] = {2, 1, 0, 0};
+      return make_rectangle (nx, ny, 0.0, 1.0, 0.0, dx * ny, ids);
+   }
+
+   // examples/double_mach_reflection/grid.geo with ny-1 := ny_cells: two transfinite blocks that
+   // meet at x0 = 1/6 so that the wall start is a mesh line; ids: 0 bottom x<x0, 1 bottom x>x0
+   // (the reflecting wall), 2 right, 3 top, 4 left
+   PrimitiveMesh make_double_mach_grid (int ny_cells)
+   {
+      const double Lx = 4.0, Ly = 1.0, xs = 1.0 / 6.0;
+      const double dy = Ly / ny_cells;
+      const int n1 = (int) std::ceil (xs / dy - 1e-12);
+      const int n2 = (int) std::ceil ((Lx - xs) / dy - 1e-12);
+      LatticeBuilder lb;
+      lb.X0 = xs - n1 * dy;
+      lb.Y0 = 0.0;
+      lb.dx = dy;
+      lb.dy = dy;
+      lb.block (0, 0, n1, ny_cells);
+      lb.block (n1, 0, n2, ny_cells);
+      const double xsplit = xs;
+      lb.boundary ([&] (double xm, double, int f) {
+         if (f == 0) return 4;
+         if (f == 1) return 2;
+         if (f == 3) return 3;
+         return xm < xsplit ? 0 : 1;
+      });
+      return lb.pm;
+   }
+
+   // examples/forward_step/step.geo: three transfinite blocks of an L-shaped channel
+   // [0,3]x[0,1] with a step of height 0.2 starting at x = 0.6; ids: 1 inflow (left), 2 walls,
+   // 3 outlet (right)
+   PrimitiveMesh make_forward_step_grid (double cl)
+   {
+      const int n1 = (int) std::lround (0.6 / cl), n2 = (int) std::lround (0.2 / cl), n3 = (int) std::lround (0.8 / cl),
+                n4 = (int) std::lround (2.4 / cl);
+      LatticeBuilder lb;
+      lb.X0 = 0.0;
+      lb.Y0 = 0.0;
+      lb.dx = cl;
+      lb.dy = cl;
+      lb.block (0, 0, n1, n2);       // surface 1
+      lb.block (0, n2, n1, n3);      // surface 2
+      lb.block (n1, n2, n4, n3);     // surface 3
+      const double xr = cl * (n1 + n4);
+      lb.boundary ([&] (double xm, double, int f) {
+         if (f == 0 && xm < 0.5 * cl) return 1;
+         if (f == 1 && xm > xr - 0.5 * cl) return 3;
+         return 2;
+      });
+      return lb.pm;
+   }
+
+   bool write_gmsh2 (const std::string &path, const PrimitiveMesh &pm)
+   {
+      FILE *fp = std::fopen (path.c_str (), "w");
+      if (!fp) return false;
+      std::fprintf (fp, "$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n", pm.n_vertices ());
+      for (int v = 0; v < pm.n_vertices (); ++v)
+         std::fprintf (fp, "%d %.17g %.17g 0\n", v + 1, pm.vertices[2 * v], pm.vertices[2 * v + 1]);
+      std::fprintf (fp, "$EndNodes\n$Elements\n%d\n", pm.n_blines () + pm.n_cells ());
+      int e = 1;
+      for (int b = 0; b < pm.n_blines (); ++b, ++e)
+         std::fprintf (fp, "%d 1 2 %d %d %d %d\n", e, pm.bline_id[b], pm.bline_id[b], pm.blines[2 * b] + 1, pm.blines[2 * b + 1] + 1);
+      for (int c = 0; c < pm.n_cells (); ++c, ++e) // gmsh quads are counter-clockwise
+         std::fprintf (fp, "%d 3 2 100 1 %d %d %d %d\n", e, pm.cells[4 * c] + 1, pm.cells[4 * c + 1] + 1, pm.cells[4 * c + 3] + 1,
+                       pm.cells[4 * c + 2] + 1);
+      std::fprintf (fp, "$EndElements\n");
+      std::fclose (fp);
+      return true;
+   }
+
+   bool read_gmsh2 (const std::string &path, PrimitiveMesh &pm, std::string &err)
+   {
+      std::ifstream in (path.c_str ());
+      if (!in)
+      {
+         err = "cannot open " + path;
+         return false;
+      }
+      pm = PrimitiveMesh ();
+      std::string line;
+      std::map<int, int> node_index;
+      while (std::getline (in, line))
+      {
+         if (line.compare (0, 6, "$Nodes") == 0)
+         {
+            int n;
+            in >> n;
+            for (int i = 0; i < n; ++i)
+            {
+               int id;
+               double x, y, z;
+               in >> id >> x >> y >> z;
+               node_index[id] = i;
+               pm.vertices.push_back (x);
+               pm.vertices.push_back (y);
+            }
+         }
+         else if (line.compare (0, 9, "$Elements") == 0)
+         {
+            int n;
+            in >> n;
+            for (int i = 0; i < n; ++i)
+            {
+               int id, type, ntags;
+               in >> id >> type >> ntags;
+               std::vector<int> tags (ntags);
+               for (int t = 0; t < ntags; ++t) in >> tags[t];
+               const int nn = type == 1 ? 2 : type == 3 ? 4 : type == 15 ? 1 : -1;
+               if (nn < 0)
+               {
+                  err = "unsupported gmsh element type " + std::to_string (type);
+                  return false;
+               }
+               int nd[4];
+               for (int k = 0; k < nn; ++k)
+               {
+                  in >> nd[k];
+                  nd[k] = node_index[nd[k]];
+               }
+               if (type == 1)
+               {
+                  pm.blines.push_back (nd[0]);
+                  pm.blines.push_back (nd[1]);
+                  pm.bline_id.push_back (ntags > 0 ? tags[0] : 0); // boundary_id = physical tag
+               }
+               else if (type == 3)
+               {
+                  // counter-clockwise (or clockwise) ring -> lexicographic with v0 = lower-left
+                  int r = 0;
+                  for (int k = 1; k < 4; ++k)
+                  {
+                     const double dxk = pm.vertices[2 * nd[k]] - pm.vertices[2 * nd[r]];
+                     const double dyk = pm.vertices[2 * nd[k] + 1] - pm.vertices[2 * nd[r] + 1];
+                     if (dxk + dyk < 0) r = k;
+                  }
+                  int ring[4];
+                  for (int k = 0; k < 4; ++k) ring[k] = nd[(r + k) % 4];
+                  // ring[1] must be the +x neighbour; if it is the +y neighbour the ring is clockwise
+                  const double dy1 = pm.vertices[2 * ring[1] + 1] - pm.vertices[2 * ring[0] + 1];
+                  const double dx1 = pm.vertices[2 * ring[1]] - pm.vertices[2 * ring[0]];
+                  if (std::fabs (dy1) > std::fabs (dx1)) std::swap (ring[1], ring[3]);
+                  pm.cells.push_back (ring[0]);
+                  pm.cells.push_back (ring[1]);
+                  pm.cells.push_back (ring[3]);
+                  pm.cells.push_back (ring[2]);
+               }
+            }
+         }
+      }
+      if (pm.n_cells () == 0)
+      {
+         err = "no quadrilateral cells in " + path;
+         return false;
+      }
+      return true;
+   }
+}

@@ -1,0 +1,58 @@
+// Host-side mesh handling of the standalone driver: what dflo gets from gmsh + deal.II's
+// GridIn::read_msh / Triangulation (reference src/claw.cc:956-967) and flattens once in
+// setup_system (src/claw.cc:270-386).
+#pragma once
+
+#include "../../../include/dflo_b200.h"
+
+#include <string>
+#include <vector>
+
+namespace dflo
+{
+   // gmsh-like primitive mesh: vertices, quads in deal.II lexicographic vertex order
+   // (v0=(0,0) v1=(1,0) v2=(0,1) v3=(1,1)), boundary lines with physical ids.
+   struct PrimitiveMesh
+   {
+      std::vector<double> vertices;  // [nv][2]
+      std::vector<int> cells;        // [nc][4]
+      std::vector<int> blines;       // [nb][2]
+      std::vector<int> bline_id;     // [nb]
+      int n_vertices () const { return vertices.size () / 2; }
+      int n_cells () const { return cells.size () / 4; }
+      int n_blines () const { return bline_id.size (); }
+   };
+
+   // Owning storage behind a dflo_flat_mesh view.
+   struct FlatMesh
+   {
+      std::vector<double> origin, size;
+      std::vector<int32_t> neighbor;
+      std::vector<uint8_t> face_flags;
+      std::vector<int32_t> bface_cell, bface_face, bface_id;
+      dflo_flat_mesh view () const;
+      int n_cells () const { return origin.size () / 2; }
+      int n_bfaces () const { return bface_cell.size (); }
+   };
+
+   // Derive neighbours, MeshWorker face ownership, periodic partners and the boundary-face list.
+   // bc_kind[id] == DFLO_BC_PERIODIC marks periodic ids, periodic_pair[id] their partner id.
+   // Returns false (and sets err) for cells that are not axis-aligned rectangles in lexicographic
+   // orientation (MappingCartesian), non-manifold faces or unmatched periodic faces.
+   bool flatten (const PrimitiveMesh &pm, const int bc_kind[DFLO_MAX_BOUNDARIES],
+                 const int periodic_pair[DFLO_MAX_BOUNDARIES], FlatMesh &out, std::string &err);
+
+   // structured nx x ny block of [x0,x1]x[y0,y1], cells x fastest; ids of (left,right,bottom,top)
+   PrimitiveMesh make_rectangle (int nx, int ny, double x0, double x1, double y0, double y1, const int ids[4]);
+
+   // The four BASELINE geometries, reproducing the transfinite blocks of the reference's .geo
+   // files (no gmsh in this image).  Cells are emitted block by block like gmsh does.
+   PrimitiveMesh make_isentropic_vortex_grid (int n_cells_per_side);          // examples/isentropic_vortex/grid.geo
+   PrimitiveMesh make_sod_tube (int nx_cells, int ny_cells);                  // examples/sod_shock_tube/tube.geo
+   PrimitiveMesh make_double_mach_grid (int ny_cells);                        // examples/double_mach_reflection/grid.geo
+   PrimitiveMesh make_forward_step_grid (double cl);                          // examples/forward_step/step.geo
+
+   // gmsh ASCII format 2 (what GridIn::read_msh reads)
+   bool read_gmsh2 (const std::string &path, PrimitiveMesh &pm, std::string &err);
+   bool write_gmsh2 (const std::string &path, const PrimitiveMesh &pm);
+}

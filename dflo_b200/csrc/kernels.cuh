@@ -1,0 +1,819 @@
+// Kernels of the explicit RK stage, written as "phase" functions: phase(p, args, smem, tid, bid)
+// is the work of one thread between two block barriers.  launch.cuh turns a kernel class into a
+// __global__ function (phases unrolled, __syncthreads between them); tests/emu runs the very
+// same phase code thread by thread on the CPU so index arithmetic is checked against the oracle
+// before GPU time is spent.  No state lives in registers across phases: everything a later
+// phase needs is in shared memory.
+//
+// Layout: DoFs are kept in the reference's order, u[cell*D + comp*NS + node], so
+// a block of CPB consecutive cells is one contiguous run of CPB*D doubles that is moved
+// HBM <-> shared memory with fully coalesced flat copies.  A group of G = (k+1)^2 threads works
+// on one cell: one thread per Gauss point (volume flux), per face point (Riemann flux, 4(k+1)
+// per cell, looped) and per DoF (residual + RK combine).
+//
+// Cell-centric faces: every cell evaluates the numerical flux of all four of its faces, so the
+// residual, M^-1, the RK combine and the cell average are produced in one pass with no atomics
+// and rhs never touches HBM.  For an interior face both adjacent cells evaluate the SAME
+// function call the reference makes once (plus side = the cell MeshWorker::loop visits the face
+// from, reference src/assemble_explicit.cc:440-451), so both obtain bit-identical fluxes and
+// the scheme stays conservative to round-off exactly like the reference's single evaluation.
+#pragma once
+
+#include "euler.cuh"
+#include "tables.h"
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DFLO_DEV __device__ __forceinline__
+#else
+#define DFLO_DEV inline
+#endif
+
+namespace dflo
+{
+   enum { FACE_OWNER = 1, FACE_PERIODIC = 2, FACE_FLIP = 4 };
+   enum { MODE_STAGE = 0, MODE_RHS = 1 };
+   enum { ERR_NEGATIVE_STATE = 1, ERR_POSLIM_ROOT = 2 };
+
+   constexpr int cells_per_block (int G) { return G >= 128 ? 1 : 128 / G; }
+   constexpr int n_scalar (int basis, int n1) { return basis == BASIS_QK ? n1 * n1 : n1 * (n1 + 1) / 2; }
+   constexpr int n_gll (int n1) { return ((n1 - 1) + 3) % 2 == 0 ? ((n1 - 1) + 3) / 2 : ((n1 - 1) + 4) / 2; }
+
+   // flat table layouts (built by pack_stage_tables / pack_limiter_tables in tables_pack.h)
+   constexpr int stage_table_size (int basis, int n1)
+   {
+      return basis == BASIS_QK ? n1 * n1 + 3 * n1 : 3 * n1 * n1 * n_scalar (basis, n1) + 4 * n1 * n_scalar (basis, n1) + n1;
+   }
+   constexpr int limiter_table_size (int basis, int n1)
+   {
+      return basis == BASIS_QK ? 3 * n1 + n_gll (n1) * n1 : 2 * n_gll (n1) * n1 * n_scalar (basis, n1);
+   }
+
+   struct StageArgs
+   {
+      const double *u;        // current_solution   [n_local][D]
+      const double *u_old;    // old_solution
+      double *out;            // MODE_STAGE: updated solution (a different buffer than u); MODE_RHS: right_hand_side
+      const double *avg;      // cell_average of u   [n_local][4]
+      double *avg_out;        // cell_average of the updated solution
+      const int *nbr;         // [n_local][4]
+      const unsigned char *fflags;
+      const double *geom;     // [n_local][4] x0, y0, hx, hy
+      const double *bc_g;     // [n_bfaces][n_q_face][4]
+      const int *bkind;       // [n_bfaces]
+      const double *tab;      // flat stage tables
+      const double *time;     // device scalars: [0] elapsed time, [1] dt
+      const double *dt_cell;  // optional per-cell dt (local time stepping), else nullptr
+      int n_compute;
+      int mode;
+      int compat_mpi;
+      double ark;
+      double gravity;
+   };
+
+   template <int BASIS, int N1, int FLUX>
+   struct StageKernel
+   {
+      typedef StageArgs Args;
+      static constexpr int NQ = N1 * N1;
+      static constexpr int G = NQ;
+      static constexpr int NS = n_scalar (BASIS, N1);
+      static constexpr int D = 4 * NS;
+      static constexpr int CPB = cells_per_block (G);
+      static constexpr int THREADS = CPB * G;
+      static constexpr int NPHASE = 4;
+      static constexpr int TAB = stage_table_size (BASIS, N1);
+      // shared memory carve-up (in doubles)
+      static constexpr int O_U = TAB;
+      static constexpr int O_F = O_U + CPB * D;
+      static constexpr int O_H = O_F + CPB * 8 * NQ;
+      static constexpr int O_W = O_H + CPB * 16 * N1;
+      static constexpr int SMEM_DOUBLES = O_W + (BASIS == BASIS_PK ? CPB * 4 * NQ : 0);
+
+      static int grid (int n_compute) { return (n_compute + CPB - 1) / CPB; }
+
+      // table accessors ------------------------------------------------------------------------
+      // Qk: dw[N1*N1] e0[N1] e1[N1] gw[N1]
+      // Pk: phi[NQ*NS] dphix[NQ*NS] dphiy[NQ*NS] phiface[4*N1*NS] gw[N1]
+      static DFLO_DEV const double *t_dw (const double *tb) { return tb; }
+      static DFLO_DEV const double *t_e (const double *tb, int side) { return tb + N1 * N1 + side * N1; }
+      static DFLO_DEV const double *t_gw (const double *tb)
+      {
+         return BASIS == BASIS_QK ? tb + N1 * N1 + 2 * N1 : tb + 3 * NQ * NS + 4 * N1 * NS;
+      }
+      static DFLO_DEV const double *t_phi (const double *tb) { return tb; }
+      static DFLO_DEV const double *t_dphix (const double *tb) { return tb + NQ * NS; }
+      static DFLO_DEV const double *t_dphiy (const double *tb) { return tb + 2 * NQ * NS; }
+      static DFLO_DEV const double *t_phiface (const double *tb) { return tb + 3 * NQ * NS; }
+
+      // Trace of one cell (ucell = its D DoFs, shared or global memory) at point q of its face f.
+      // The same fma chain is used for a cell's own trace and for its neighbour's, so the two
+      // cells sharing a face feed bit-identical states into the Riemann solver.
+      static DFLO_DEV void trace (const double *tb, const double *ucell, int f, int q, double W[4])
+      {
+         if (BASIS == BASIS_QK)
+         {
+            const double *e = t_e (tb, f & 1);
+            const int base = (f < 2) ? N1 * q : q;
+            const int stride = (f < 2) ? 1 : N1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+               double s = 0.0;
+#pragma unroll
+               for (int a = 0; a < N1; ++a) s = fma (e[a], ucell[c * NS + base + a * stride], s);
+               W[c] = s;
+            }
+         }
+         else
+         {
+            const double *pf = t_phiface (tb) + (f * N1 + q) * NS;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+               double s = 0.0;
+#pragma unroll
+               for (int m = 0; m < NS; ++m) s = fma (pf[m], ucell[c * NS + m], s);
+               W[c] = s;
+            }
+         }
+      }
+
+      static DFLO_DEV void phase (int p, const Args &A, double *sm, int tid, int bid)
+      {
+         const int c0 = bid * CPB;
+         const int ncb = (A.n_compute - c0 < CPB) ? A.n_compute - c0 : CPB;
+         double *tb = sm;
+         double *su = sm + O_U;
+         double *sF = sm + O_F;
+         double *sH = sm + O_H;
+         double *sW = sm + O_W;
+         const int slot = tid / G, lq = tid % G;
+         const bool active = slot < ncb;
+         const int cell = c0 + slot;
+
+         if (p == 0)
+         {
+            // tables and this block's DoFs: flat, coalesced
+            for (int i = tid; i < TAB; i += THREADS) tb[i] = A.tab[i];
+            const double *src = A.u + (size_t) c0 * D;
+            for (int i = tid; i < ncb * D; i += THREADS) su[i] = src[i];
+         }
+         else if (p == 1)
+         {
+            if (!active) return;
+            const double *uc = su + slot * D;
+            // ---- volume: Cartesian fluxes at Gauss point lq (assemble_explicit.cc:57-79) ----
+            {
+               double W[4], Fx[4], Fy[4];
+               if (BASIS == BASIS_QK)
+               {
+                  // collocation: the interpolation loop 65-75 is the identity
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) W[c] = uc[c * NS + lq];
+               }
+               else
+               {
+                  const double *ph = t_phi (tb) + lq * NS;
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                  {
+                     double s = 0.0;
+#pragma unroll
+                     for (int m = 0; m < NS; ++m) s = fma (ph[m], uc[c * NS + m], s);
+                     W[c] = s;
+                     sW[(slot * 4 + c) * NQ + lq] = s;
+                  }
+               }
+               flux_matrix (W, Fx, Fy);
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  sF[(slot * 8 + c) * NQ + lq] = Fx[c];
+                  sF[(slot * 8 + 4 + c) * NQ + lq] = Fy[c];
+               }
+            }
+            // ---- faces: numerical flux along this cell's outward normal at the 4(k+1) face
+            //      points (assemble_explicit.cc:176-206, 303-341; periodic: src_mpi 186-260) ----
+            double Ao[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Ao[c] = A.avg[(size_t) cell * 4 + c];
+            for (int idx = lq; idx < 4 * N1; idx += G)
+            {
+               const int f = idx / N1, q = idx % N1;
+               const double nx = (f == 0) ? -1.0 : (f == 1) ? 1.0 : 0.0;
+               const double ny = (f == 2) ? -1.0 : (f == 3) ? 1.0 : 0.0;
+               double Wo[4], Wn[4], An[4], H[4];
+               trace (tb, uc, f, q, Wo);
+               const int nb = A.nbr[(size_t) cell * 4 + f];
+               const int fl = A.fflags[(size_t) cell * 4 + f];
+               bool plus = true; // this cell is the "plus" side of the flux call
+               if (nb >= 0)
+               {
+                  const int qn = (fl & FACE_FLIP) ? N1 - 1 - q : q;
+                  trace (tb, A.u + (size_t) nb * D, f ^ 1, qn, Wn);
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) An[c] = A.avg[(size_t) nb * 4 + c];
+                  plus = (fl & (FACE_OWNER | FACE_PERIODIC)) != 0;
+               }
+               else
+               {
+                  const int bf = -1 - nb;
+                  const int kind = A.bkind[bf];
+                  double g[4];
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) g[c] = A.bc_g[((size_t) bf * N1 + q) * 4 + c];
+                  compute_wminus (kind, nx, ny, Wo, g, Wn);
+                  if (A.compat_mpi) // src_mpi/assemble_explicit.cc:296-321
+                     compute_wminus (kind, nx, ny, Ao, g, An);
+                  else // src/assemble_explicit.cc:203-204: own average on both sides
+                  {
+#pragma unroll
+                     for (int c = 0; c < 4; ++c) An[c] = Ao[c];
+                  }
+               }
+               double L[4], R[4], AL[4], AR[4];
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  L[c] = plus ? Wo[c] : Wn[c];
+                  R[c] = plus ? Wn[c] : Wo[c];
+                  AL[c] = plus ? Ao[c] : An[c];
+                  AR[c] = plus ? An[c] : Ao[c];
+               }
+               const double sg = plus ? 1.0 : -1.0;
+               numerical_flux<FLUX> (sg * nx, sg * ny, L, R, AL, AR, H);
+#pragma unroll
+               for (int c = 0; c < 4; ++c) sH[((slot * 4 + f) * N1 + q) * 4 + c] = sg * H[c];
+            }
+         }
+         else if (p == 2)
+         {
+            if (!active || lq >= NS) return;
+            const double hx = A.geom[(size_t) cell * 4 + 2], hy = A.geom[(size_t) cell * 4 + 3];
+            const double *gw = t_gw (tb);
+            const double dt = A.dt_cell ? A.dt_cell[cell] : A.time[1];
+            double *uc = su + slot * D;
+            const double *H = sH + slot * 16 * N1;
+            double r[4];
+            double invm;
+            if (BASIS == BASIS_QK)
+            {
+               // rhs_i = sum_q F.grad(phi_i) JxW - sum_faces sum_q H phi_i JxW  (85-115, 209-244,
+               // 344-382) with phi_i the Lagrange function of Gauss node (a,b)
+               const int a = lq % N1, b = lq / N1;
+               const double *dw = t_dw (tb);
+               const double *e0 = t_e (tb, 0), *e1 = t_e (tb, 1);
+               const double wa = gw[a], wb = gw[b];
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  double sx = 0.0, sy = 0.0;
+#pragma unroll
+                  for (int ap = 0; ap < N1; ++ap) sx = fma (sF[(slot * 8 + c) * NQ + ap + N1 * b], dw[ap * N1 + a], sx);
+#pragma unroll
+                  for (int bp = 0; bp < N1; ++bp) sy = fma (sF[(slot * 8 + 4 + c) * NQ + a + N1 * bp], dw[bp * N1 + b], sy);
+                  const double fx = H[((1 * N1) + b) * 4 + c] * e1[a] + H[((0 * N1) + b) * 4 + c] * e0[a];
+                  const double fy = H[((3 * N1) + a) * 4 + c] * e1[b] + H[((2 * N1) + a) * 4 + c] * e0[b];
+                  r[c] = hy * wb * (sx - fx) + hx * wa * (sy - fy);
+               }
+               if (A.gravity != 0.0)
+               {
+                  double W[4], Gv[4];
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) W[c] = uc[c * NS + lq];
+                  forcing (W, Gv);
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) r[c] += A.gravity * Gv[c] * (wa * wb * hx * hy);
+               }
+               invm = 1.0 / (wa * wb * hx * hy); // claw.cc:228-258 on a Cartesian cell
+            }
+            else
+            {
+               const int m = lq;
+               const double *dpx = t_dphix (tb), *dpy = t_dphiy (tb), *pf = t_phiface (tb), *ph = t_phi (tb);
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  double s = 0.0;
+                  for (int q = 0; q < NQ; ++q)
+                  {
+                     const double w2 = gw[q % N1] * gw[q / N1];
+                     s += w2 * (sF[(slot * 8 + c) * NQ + q] * dpx[q * NS + m] * hy + sF[(slot * 8 + 4 + c) * NQ + q] * dpy[q * NS + m] * hx);
+                  }
+                  for (int f = 0; f < 4; ++f)
+                  {
+                     const double len = (f < 2) ? hy : hx;
+                     for (int q = 0; q < N1; ++q) s -= gw[q] * len * H[((f * N1) + q) * 4 + c] * pf[(f * N1 + q) * NS + m];
+                  }
+                  r[c] = s;
+               }
+               if (A.gravity != 0.0)
+               {
+                  for (int q = 0; q < NQ; ++q)
+                  {
+                     double W[4], Gv[4];
+#pragma unroll
+                     for (int c = 0; c < 4; ++c) W[c] = sW[(slot * 4 + c) * NQ + q];
+                     forcing (W, Gv);
+                     const double w = gw[q % N1] * gw[q / N1] * hx * hy * ph[q * NS + m];
+#pragma unroll
+                     for (int c = 0; c < 4; ++c) r[c] += A.gravity * Gv[c] * w;
+                  }
+               }
+               invm = 1.0 / (hx * hy); // orthonormal modes
+            }
+            if (A.mode == MODE_RHS)
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c) uc[c * NS + lq] = r[c];
+            }
+            else
+            {
+               // solve() + RK combine: claw.cc:694-713, 757-760
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  const double un = uc[c * NS + lq] + dt * r[c] * invm;
+                  if (A.ark != 0.0)
+                  {
+                     const double uo = A.u_old[(size_t) cell * D + c * NS + lq];
+                     uc[c * NS + lq] = (1.0 - A.ark) * un + A.ark * uo;
+                  }
+                  else
+                     uc[c * NS + lq] = un;
+               }
+            }
+         }
+         else // p == 3
+         {
+            double *dst = A.out + (size_t) c0 * D;
+            for (int i = tid; i < ncb * D; i += THREADS) dst[i] = su[i];
+            if (A.mode == MODE_STAGE)
+            {
+               // compute_cell_average of the updated solution, claw.cc:562-597
+               const double *gw = t_gw (tb);
+               for (int j = tid; j < ncb * 4; j += THREADS)
+               {
+                  const int s = j / 4, c = j % 4;
+                  double v;
+                  if (BASIS == BASIS_QK)
+                  {
+                     v = 0.0;
+                     for (int b = 0; b < N1; ++b)
+                        for (int a = 0; a < N1; ++a) v += gw[a] * gw[b] * su[s * D + c * NS + a + N1 * b];
+                  }
+                  else
+                     v = su[s * D + c * NS];
+                  A.avg_out[(size_t) (c0 + s) * 4 + c] = v;
+               }
+            }
+         }
+      }
+   };
+
+   //---------------------------------------------------------------------------------------------
+   // Cell averages of a solution vector (claw.cc:562-597), used after set_solution
+   //---------------------------------------------------------------------------------------------
+   struct AvgArgs
+   {
+      const double *u;
+      double *avg;
+      const double *gw; // [N1] device
+      int n_cells, basis, n1, ns;
+   };
+
+   DFLO_DEV void cell_average_thread (const AvgArgs &A, int j)
+   {
+      if (j >= A.n_cells * 4) return;
+      const int cell = j / 4, c = j % 4;
+      const double *uc = A.u + (size_t) cell * 4 * A.ns + c * A.ns;
+      double v;
+      if (A.basis == BASIS_QK)
+      {
+         v = 0.0;
+         for (int b = 0; b < A.n1; ++b)
+            for (int a = 0; a < A.n1; ++a) v += A.gw[a] * A.gw[b] * uc[a + A.n1 * b];
+      }
+      else
+         v = uc[0];
+      A.avg[j] = v;
+   }
+
+   //---------------------------------------------------------------------------------------------
+   // TVB limiter (limiter.cc:224-516) fused with the positivity limiter (positivity.cc:16-208),
+   // in place on the freshly updated solution.  Reads only the cell's own DoFs and the cell
+   // averages of the cell and its four face neighbours, so cells are independent exactly as in
+   // the reference's serial loops.
+   //---------------------------------------------------------------------------------------------
+   struct LimiterArgs
+   {
+      double *u;              // in place
+      const double *avg;
+      const int *nbr;
+      const unsigned char *fflags;
+      const double *geom;
+      const double *tab;      // flat limiter tables
+      int *flags_out;         // [n_local] bit0 TVB rewrote, bit1 theta1<1, bit2 theta2<1
+      unsigned int *err;      // device error word
+      int n_compute;
+      int tvb, char_lim, pos_lim, cam;
+      double M, beta;
+   };
+
+   template <int BASIS, int N1>
+   struct LimiterKernel
+   {
+      typedef LimiterArgs Args;
+      static constexpr int NQ = N1 * N1;
+      static constexpr int G = NQ;
+      static constexpr int NS = n_scalar (BASIS, N1);
+      static constexpr int D = 4 * NS;
+      static constexpr int CPB = cells_per_block (G);
+      static constexpr int THREADS = CPB * G;
+      static constexpr int NPHASE = 11;
+      static constexpr int NGLL = n_gll (N1);
+      static constexpr int NPOS = NGLL * N1;
+      static constexpr int TAB = limiter_table_size (BASIS, N1);
+      static constexpr int O_U = TAB;
+      static constexpr int O_D = O_U + CPB * D;        // slopes Dx[4], Dy[4] per cell
+      static constexpr int O_N = O_D + CPB * 8;        // limited slopes
+      static constexpr int O_P = O_N + CPB * 8;        // point values / theta candidates [2*NPOS]
+      static constexpr int O_T = O_P + CPB * 2 * NPOS; // theta1, theta2
+      static constexpr int O_FLAG = O_T + CPB * 2;     // per-cell flags (stored as doubles) + block flag
+      static constexpr int SMEM_DOUBLES = O_FLAG + CPB + 1;
+
+      static int grid (int n_compute) { return (n_compute + CPB - 1) / CPB; }
+
+      // Qk tables: gw[N1] gx[N1] gdiff[N1] gl_interp[NGLL*N1];  Pk: phipos[2][NPOS][NS]
+      static DFLO_DEV const double *t_gw (const double *tb) { return tb; }
+      static DFLO_DEV const double *t_gx (const double *tb) { return tb + N1; }
+      static DFLO_DEV const double *t_gdiff (const double *tb) { return tb + 2 * N1; }
+      static DFLO_DEV const double *t_gli (const double *tb) { return tb + 3 * N1; }
+      static DFLO_DEV const double *t_phipos (const double *tb) { return tb; }
+
+      // value of component c at positivity point pt of set (0: GLL x Gauss, 1: Gauss x GLL)
+      static DFLO_DEV double point_value (const double *tb, const double *uc, int set, int pt, int c)
+      {
+         double s = 0.0;
+         if (BASIS == BASIS_QK)
+         {
+            const double *gli = t_gli (tb);
+            if (set == 0)
+            {
+               const int j = pt % NGLL, b = pt / NGLL;
+#pragma unroll
+               for (int a = 0; a < N1; ++a) s = fma (gli[j * N1 + a], uc[c * NS + a + N1 * b], s);
+            }
+            else
+            {
+               const int a = pt % N1, j = pt / N1;
+#pragma unroll
+               for (int b = 0; b < N1; ++b) s = fma (gli[j * N1 + b], uc[c * NS + a + N1 * b], s);
+            }
+         }
+         else
+         {
+            const double *pp = t_phipos (tb) + (set * NPOS + pt) * NS;
+#pragma unroll
+            for (int m = 0; m < NS; ++m) s = fma (pp[m], uc[c * NS + m], s);
+         }
+         return s;
+      }
+
+      static DFLO_DEV void phase (int p, const Args &A, double *sm, int tid, int bid)
+      {
+         const int c0 = bid * CPB;
+         const int ncb = (A.n_compute - c0 < CPB) ? A.n_compute - c0 : CPB;
+         double *tb = sm;
+         double *su = sm + O_U;
+         double *sD = sm + O_D;
+         double *sN = sm + O_N;
+         double *sP = sm + O_P;
+         double *sT = sm + O_T;
+         double *sFlag = sm + O_FLAG;
+         const int slot = tid / G, lq = tid % G;
+         const bool active = slot < ncb;
+         const int cell = c0 + slot;
+         const double eps = 1.0e-13;
+         if (N1 == 1) return; // degree 0: both limiters return at once (limiter.cc:227, positivity.cc:19)
+
+         if (p == 0)
+         {
+            for (int i = tid; i < TAB; i += THREADS) tb[i] = A.tab[i];
+            const double *src = A.u + (size_t) c0 * D;
+            for (int i = tid; i < ncb * D; i += THREADS) su[i] = src[i];
+            for (int i = tid; i < CPB + 1; i += THREADS) sFlag[i] = 0.0;
+         }
+         else if (p == 1)
+         {
+            // mean slopes of the cell, limiter.cc:268-281 (Qk) / 412-420 (Pk)
+            if (!active || !A.tvb) return;
+            const double *uc = su + slot * D;
+            for (int r = lq; r < 8; r += G)
+            {
+               const int c = r % 4, dir = r / 4;
+               double s = 0.0;
+               if (BASIS == BASIS_QK)
+               {
+                  const double *gw = t_gw (tb), *gd = t_gdiff (tb);
+                  for (int b = 0; b < N1; ++b)
+                     for (int a = 0; a < N1; ++a)
+                        s += (dir == 0 ? gd[a] * gw[b] : gw[a] * gd[b]) * uc[c * NS + a + N1 * b];
+               }
+               else
+                  s = uc[c * NS + (dir == 0 ? 1 : N1)] * 1.7320508075688772; // sqrt(3); base index 1 / k+1
+               sD[slot * 8 + r] = s;
+            }
+         }
+         else if (p == 2)
+         {
+            // one thread per cell, packed into the first lanes: differences of means,
+            // characteristic projection, minmod (limiter.cc:283-345 / 425-486)
+            if (!A.tvb || tid >= ncb) return;
+            const int s = tid, cl = c0 + tid;
+            const double hx = A.geom[(size_t) cl * 4 + 2], hy = A.geom[(size_t) cl * 4 + 3];
+            const double dx = sqrt (hx * hx + hy * hy) / 1.4142135623730951; // diameter / sqrt(dim)
+            const double Mdx2 = A.M * dx * dx;
+            const double beta = (BASIS == BASIS_QK) ? A.beta : 0.5 * A.beta;
+            double av[4], Dx[4], Dy[4], dbx[4], dfx[4], dby[4], dfy[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+               av[c] = A.avg[(size_t) cl * 4 + c];
+               if (BASIS == BASIS_QK)
+               {
+                  // Dx = dx * mean(d/dx), mean gradient on the unit cell divided by hx
+                  Dx[c] = dx * (sD[s * 8 + c] / hx);
+                  Dy[c] = dx * (sD[s * 8 + 4 + c] / hy);
+               }
+               else
+               {
+                  Dx[c] = sD[s * 8 + c];
+                  Dy[c] = sD[s * 8 + 4 + c];
+               }
+               dbx[c] = dfx[c] = Dx[c];
+               dby[c] = dfy[c] = Dy[c];
+            }
+            const double ang_mom = Dx[1] - Dy[0];
+            // lcell/rcell/bcell/tcell (claw.cc:357-379); periodic partners count as neighbours
+            // (src_mpi/claw.cc:417-465)
+            for (int f = 0; f < 4; ++f)
+            {
+               const int nb = A.nbr[(size_t) cl * 4 + f];
+               if (nb < 0) continue;
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  const double an = A.avg[(size_t) nb * 4 + c];
+                  if (f == 0) dbx[c] = av[c] - an;
+                  if (f == 1) dfx[c] = an - av[c];
+                  if (f == 2) dby[c] = av[c] - an;
+                  if (f == 3) dfy[c] = an - av[c];
+               }
+            }
+            EigenMatrices em;
+            if (A.char_lim)
+            {
+               compute_eigen_matrix (av, em);
+               transform_to_char (em.Lx, dbx);
+               transform_to_char (em.Lx, dfx);
+               transform_to_char (em.Ly, dby);
+               transform_to_char (em.Ly, dfy);
+               transform_to_char (em.Lx, Dx);
+               transform_to_char (em.Ly, Dy);
+            }
+            double Dxn[4], Dyn[4], change_x = 0.0, change_y = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+               Dxn[c] = minmod (Dx[c], beta * dbx[c], beta * dfx[c], Mdx2);
+               Dyn[c] = minmod (Dy[c], beta * dby[c], beta * dfy[c], Mdx2);
+               change_x += fabs (Dxn[c] - Dx[c]);
+               change_y += fabs (Dyn[c] - Dy[c]);
+            }
+            change_x /= 4;
+            change_y /= 4;
+            if (change_x + change_y > 1.0e-10)
+            {
+               if (BASIS == BASIS_QK)
+               {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                  {
+                     Dxn[c] /= dx;
+                     Dyn[c] /= dx;
+                  }
+               }
+               if (A.char_lim)
+               {
+                  transform_to_con (em.Rx, Dxn);
+                  transform_to_con (em.Ry, Dyn);
+               }
+               if (BASIS == BASIS_PK && A.cam) // limiter.cc:496-500
+               {
+                  Dyn[0] = 0.5 * (Dyn[0] - (ang_mom - Dxn[1]));
+                  Dxn[1] = ang_mom + Dyn[0];
+               }
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  sN[s * 8 + c] = Dxn[c];
+                  sN[s * 8 + 4 + c] = Dyn[c];
+               }
+               sFlag[s] = 1.0;
+               sFlag[CPB] = 1.0; // benign race: every writer stores the same value
+            }
+         }
+         else if (p == 3)
+         {
+            // rewrite the cell as mean + limited linear part (limiter.cc:356-366 / 501-511)
+            if (!active || !A.tvb || lq >= NS || sFlag[slot] == 0.0) return;
+            double *uc = su + slot * D;
+            if (BASIS == BASIS_QK)
+            {
+               const double *gx = t_gx (tb);
+               const int a = lq % N1, b = lq / N1;
+               const double x0 = A.geom[(size_t) cell * 4 + 0], y0 = A.geom[(size_t) cell * 4 + 1];
+               const double hx = A.geom[(size_t) cell * 4 + 2], hy = A.geom[(size_t) cell * 4 + 3];
+               const double dr0 = (x0 + gx[a] * hx) - (x0 + 0.5 * hx);
+               const double dr1 = (y0 + gx[b] * hy) - (y0 + 0.5 * hy);
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+                  uc[c * NS + lq] = A.avg[(size_t) cell * 4 + c] + dr0 * sN[slot * 8 + c] + dr1 * sN[slot * 8 + 4 + c];
+            }
+            else
+            {
+               const int m = lq;
+               if (m == 0) return;
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  double v = 0.0;
+                  if (m == 1) v = sN[slot * 8 + c] / 1.7320508075688772;
+                  if (m == N1) v = sN[slot * 8 + 4 + c] / 1.7320508075688772;
+                  uc[c * NS + m] = v;
+               }
+            }
+         }
+         else if (p == 4)
+         {
+            // positivity, density at the GLL x Gauss point sets (positivity.cc:68-78)
+            if (!active || !A.pos_lim) return;
+            const double *uc = su + slot * D;
+            if (lq == 0)
+            {
+               double av[4];
+#pragma unroll
+               for (int c = 0; c < 4; ++c) av[c] = A.avg[(size_t) cell * 4 + c];
+               if (std_min (av[RHO], pressure (av)) < eps) // positivity.cc:26-39
+               {
+#if defined(__CUDA_ARCH__)
+                  atomicOr (A.err, (unsigned int) ERR_NEGATIVE_STATE);
+#else
+                  *A.err |= ERR_NEGATIVE_STATE;
+#endif
+               }
+            }
+            for (int idx = lq; idx < 2 * NPOS; idx += G)
+               sP[slot * 2 * NPOS + idx] = point_value (tb, uc, idx / NPOS, idx % NPOS, RHO);
+         }
+         else if (p == 5)
+         {
+            if (!A.pos_lim || tid >= ncb) return;
+            const int s = tid, cl = c0 + tid;
+            double rho_min = 1.0e20;
+            for (int i = 0; i < 2 * NPOS; ++i) rho_min = std_min (rho_min, sP[s * 2 * NPOS + i]);
+            const double density_average = A.avg[(size_t) cl * 4 + RHO];
+            const double rat = fabs (density_average - eps) / (fabs (density_average - rho_min) + 1.0e-13);
+            const double theta1 = std_min (rat, 1.0);
+            sT[s * 2] = theta1;
+            if (theta1 < 1.0)
+            {
+               sFlag[s] += 2.0;
+               sFlag[CPB] = 1.0;
+            }
+         }
+         else if (p == 6)
+         {
+            // scale density about its mean (positivity.cc:85-110)
+            if (!active || !A.pos_lim || lq >= NS) return;
+            const double theta1 = sT[slot * 2];
+            if (!(theta1 < 1.0)) return;
+            double *uc = su + slot * D;
+            if (BASIS == BASIS_QK)
+               uc[RHO * NS + lq] = theta1 * uc[RHO * NS + lq] + (1.0 - theta1) * A.avg[(size_t) cell * 4 + RHO];
+            else if (lq > 0)
+               uc[RHO * NS + lq] *= theta1;
+         }
+         else if (p == 7)
+         {
+            // pressure at every point; where negative, the admissible fraction t towards the
+            // mean (positivity.cc:134-179)
+            if (!active || !A.pos_lim) return;
+            const double *uc = su + slot * D;
+            double av[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) av[c] = A.avg[(size_t) cell * 4 + c];
+            for (int idx = lq; idx < 2 * NPOS; idx += G)
+            {
+               const int set = idx / NPOS, pt = idx % NPOS;
+               const double mx = point_value (tb, uc, set, pt, 0);
+               const double my = point_value (tb, uc, set, pt, 1);
+               const double rho = point_value (tb, uc, set, pt, RHO);
+               const double E = point_value (tb, uc, set, pt, ENE);
+               const double pre = GM1 * (E - 0.5 * (mx * mx + my * my) / rho);
+               double t = 1.0;
+               if (pre < eps)
+               {
+                  const double drho = rho - av[RHO];
+                  const double dm0 = mx - av[0], dm1 = my - av[1];
+                  const double dE = E - av[ENE];
+                  const double a1 = 2.0 * drho * dE - (dm0 * dm0 + dm1 * dm1);
+                  double b1 = 2.0 * drho * (av[ENE] - eps / GM1) + 2.0 * av[RHO] * dE - 2.0 * (av[0] * dm0 + av[1] * dm1);
+                  double c1 = 2.0 * av[RHO] * av[ENE] - (av[0] * av[0] + av[1] * av[1]) - 2.0 * eps * av[RHO] / GM1;
+                  b1 /= a1;
+                  c1 /= a1;
+                  const double Dd = sqrt (fabs (b1 * b1 - 4.0 * c1));
+                  const double t1 = 0.5 * (-b1 - Dd), t2 = 0.5 * (-b1 + Dd);
+                  if (t1 > -1.0e-12 && t1 < 1.0 + 1.0e-12)
+                     t = t1;
+                  else if (t2 > -1.0e-12 && t2 < 1.0 + 1.0e-12)
+                     t = t2;
+                  else
+                  {
+                     t = 0.0;
+#if defined(__CUDA_ARCH__)
+                     atomicOr (A.err, (unsigned int) ERR_POSLIM_ROOT);
+#else
+                     *A.err |= ERR_POSLIM_ROOT;
+#endif
+                  }
+                  t = std_min (1.0, t);
+                  t = std_max (0.0, t);
+                  if (fabs (1.0 - t) < 1.0e-14) t = 0.0;
+               }
+               sP[slot * 2 * NPOS + idx] = t;
+            }
+         }
+         else if (p == 8)
+         {
+            if (!A.pos_lim || tid >= ncb) return;
+            const int s = tid;
+            double theta2 = 1.0;
+            for (int i = 0; i < 2 * NPOS; ++i) theta2 = std_min (theta2, sP[s * 2 * NPOS + i]);
+            sT[s * 2 + 1] = theta2;
+            if (theta2 < 1.0)
+            {
+               sFlag[s] += 4.0;
+               sFlag[CPB] = 1.0;
+            }
+         }
+         else if (p == 9)
+         {
+            // scale all components about the mean (positivity.cc:182-206), then write back the
+            // block only if some cell in it changed
+            if (active && A.pos_lim && lq < NS)
+            {
+               const double theta2 = sT[slot * 2 + 1];
+               if (theta2 < 1.0)
+               {
+                  double *uc = su + slot * D;
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                  {
+                     if (BASIS == BASIS_QK)
+                        uc[c * NS + lq] = theta2 * uc[c * NS + lq] + (1.0 - theta2) * A.avg[(size_t) cell * 4 + c];
+                     else if (lq > 0)
+                        uc[c * NS + lq] *= theta2;
+                  }
+               }
+            }
+            if (active && lq == 0 && A.flags_out) A.flags_out[cell] = (int) sFlag[slot];
+         }
+         else // p == 10: write the block back only if some cell in it changed
+         {
+            if (sFlag[CPB] == 0.0) return;
+            double *dst = A.u + (size_t) c0 * D;
+            for (int i = tid; i < ncb * D; i += THREADS) dst[i] = su[i];
+         }
+      }
+   };
+
+   //---------------------------------------------------------------------------------------------
+   // compute_time_step_cartesian, claw.cc:484-511: per-cell dt from the cell averages
+   //---------------------------------------------------------------------------------------------
+   DFLO_DEV double cell_time_step (const double *avg, const double *geom, double cfl, int degree)
+   {
+      const double hx = geom[2], hy = geom[3];
+      const double h = sqrt (hx * hx + hy * hy) / 1.4142135623730951;
+      const double sonic = sound_speed (avg);
+      const double density = avg[RHO];
+      double max_eigenvalue = 0.0;
+      max_eigenvalue += (sonic + fabs (avg[0] / density)) / h;
+      max_eigenvalue += (sonic + fabs (avg[1] / density)) / h;
+      return cfl / max_eigenvalue / (2.0 * degree + 1.0);
+   }
+}

@@ -705,11 +705,10 @@ namespace
       const double Mdx2 = o.prm.M * dx * dx;
       const double *avg = &o.cell_average[c * NC];
       double dbx[NC], dfx[NC], dby[NC], dfy[NC];
-      // lcell/rcell/bcell/tcell (claw.cc:336-380) = neighbours through faces 0/1/2/3 that
-      // share vertices with this cell; a periodic partner is NOT found by cell->neighbor()
-      const std::vector<char> &shared = o.shared;
-      const bool has[4] = {(bool) shared[4 * c + 0], (bool) shared[4 * c + 1], (bool) shared[4 * c + 2],
-                           (bool) shared[4 * c + 3]};
+      // lcell/rcell/bcell/tcell (claw.cc:336-380) = neighbours through faces 0/1/2/3; periodic
+      // partners count as neighbours too (the only tree with periodic faces resolves them
+      // through the periodic map, src_mpi/claw.cc:417-465)
+      const bool has[4] = {cl.nbr[0] >= 0, cl.nbr[1] >= 0, cl.nbr[2] >= 0, cl.nbr[3] >= 0};
       for (int i = 0; i < NC; ++i)
       {
          dbx[i] = w.Dx[i];

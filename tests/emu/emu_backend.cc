@@ -1,0 +1,158 @@
+// TEST INFRASTRUCTURE ONLY -- never part of the shipped library, never loaded by dflo_b200.
+//
+// CPU emulation backend for Engine<Backend> (dflo_b200/csrc/engine_core.h): runs the very same
+// kernel phase code as the CUDA build, block by block and thread by thread, so that index
+// arithmetic, buffer rotation, limiter logic and the halo lists can be checked against the
+// oracle in the CPU-only test tier before GPU time is spent.  Exposes the ABI of
+// include/dflo_b200.h under the prefix dflo_emu_.  Halo exchange between emulated ranks is
+// done by the test (in-process or over torch.distributed/gloo) through dflo_emu_halo_*.
+#include "../../dflo_b200/csrc/abi_impl.h"
+
+#include <cstdlib>
+#include <map>
+#include <vector>
+
+namespace
+{
+   struct EmuBackend
+   {
+      int64_t launches = 0;
+      int rank = 0, world = 1;
+      // halo mailboxes: outgoing[peer] = concatenated payload in send order, incoming likewise
+      struct Pending { double *dst; size_t count; };
+      std::map<int, std::vector<double>> outbox;
+      std::map<int, std::vector<Pending>> recv_plan;
+      bool halo_pending = false;
+
+      int open (int, int r, int w, const void *, std::string &)
+      {
+         rank = r;
+         world = w;
+         return DFLO_OK;
+      }
+      void close () {}
+      template <class T> T *alloc (size_t n) { return static_cast<T *> (std::calloc (n ? n : 1, sizeof (T))); }
+      void free (void *p) { std::free (p); }
+      void h2d (void *d, const void *h, size_t b) { std::memcpy (d, h, b); }
+      void d2h (void *h, const void *d, size_t b) { std::memcpy (h, d, b); }
+      void zero (void *d, size_t b) { std::memset (d, 0, b); }
+      void sync () {}
+      int check (std::string &) { return DFLO_OK; }
+      void *stream_handle () const { return nullptr; }
+      void drop_graphs () {}
+      bool graph_launch (int, int *) { return false; }
+      bool capture_begin () { return false; }
+      void capture_end_and_launch (int, int) {}
+      void timer_start () {}
+      void timer_stop () {}
+      float timer_ms () { return 0.0f; }
+      void allreduce_min_dt (double *) {} // single-rank advance only in emulation
+      void allreduce_sum (double *, int) {}
+
+      template <class K> void launch (int grid, const typename K::Args &a)
+      {
+         ++launches;
+         std::vector<double> smem (K::SMEM_DOUBLES);
+         for (int b = 0; b < grid; ++b)
+            for (int p = 0; p < K::NPHASE; ++p)
+               for (int t = 0; t < K::THREADS; ++t) K::phase (p, a, smem.data (), t, b);
+      }
+      template <class K> void launch1d (int n, const typename K::Args &a)
+      {
+         ++launches;
+         for (int j = 0; j < n; ++j) K::thread (a, j);
+      }
+
+      // halo: sends are copied into the outbox; receives are recorded and completed by the test
+      void halo_begin ()
+      {
+         outbox.clear ();
+         recv_plan.clear ();
+      }
+      void halo_send (int peer, const double *buf, size_t count)
+      {
+         std::vector<double> &o = outbox[peer];
+         o.insert (o.end (), buf, buf + count);
+      }
+      void halo_recv (int peer, double *dst, size_t count) { recv_plan[peer].push_back (Pending{dst, count}); }
+      void halo_end () { halo_pending = !recv_plan.empty () || !outbox.empty (); }
+      void halo_wait () {}
+   };
+}
+
+DFLO_DEFINE_ABI (dflo_emu_, EmuBackend, dflo_emu_ctx)
+
+extern "C" {
+// number of doubles this rank sends to / expects from `peer` in the pending exchange
+size_t dflo_emu_halo_send_count (dflo_emu_ctx *c, int peer) { return c->eng.bk.outbox.count (peer) ? c->eng.bk.outbox[peer].size () : 0; }
+size_t dflo_emu_halo_recv_count (dflo_emu_ctx *c, int peer)
+{
+   size_t n = 0;
+   if (c->eng.bk.recv_plan.count (peer))
+      for (auto &p : c->eng.bk.recv_plan[peer]) n += p.count;
+   return n;
+}
+void dflo_emu_halo_get_send (dflo_emu_ctx *c, int peer, double *out)
+{
+   const std::vector<double> &o = c->eng.bk.outbox[peer];
+   std::memcpy (out, o.data (), o.size () * sizeof (double));
+}
+void dflo_emu_halo_put_recv (dflo_emu_ctx *c, int peer, const double *in)
+{
+   size_t off = 0;
+   for (auto &p : c->eng.bk.recv_plan[peer])
+   {
+      std::memcpy (p.dst, in + off, p.count * sizeof (double));
+      off += p.count;
+   }
+   c->eng.bk.recv_plan.erase (peer);
+}
+int dflo_emu_n_peers (dflo_emu_ctx *c) { return c->eng.lm.peers.size (); }
+int dflo_emu_peer_rank (dflo_emu_ctx *c, int i) { return c->eng.lm.peers[i].rank; }
+int dflo_emu_n_local (dflo_emu_ctx *c) { return c->eng.lm.n_local; }
+int dflo_emu_n_compute (dflo_emu_ctx *c) { return c->eng.lm.n_compute; }
+}
+
+// point-wise device physics (dflo_b200/csrc/euler.cuh) exposed for unit tests against the oracle
+extern "C" {
+void dflo_emu_numerical_flux (int flux, const double n[2], const double Wp[4], const double Wm[4], const double Ap[4],
+                              const double Am[4], double H[4])
+{
+   switch (flux)
+   {
+      case 0: dflo::numerical_flux<0> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
+      case 1: dflo::numerical_flux<1> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
+      case 2: dflo::numerical_flux<2> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
+      case 3: dflo::numerical_flux<3> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
+      default: dflo::numerical_flux<4> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
+   }
+}
+void dflo_emu_flux_matrix (const double W[4], double F[8])
+{
+   double Fx[4], Fy[4];
+   dflo::flux_matrix (W, Fx, Fy);
+   for (int c = 0; c < 4; ++c)
+   {
+      F[2 * c] = Fx[c];
+      F[2 * c + 1] = Fy[c];
+   }
+}
+void dflo_emu_wminus (int kind, const double n[2], const double Wp[4], const double g[4], double Wm[4])
+{
+   dflo::compute_wminus (kind, n[0], n[1], Wp, g, Wm);
+}
+void dflo_emu_eigen (const double W[4], double Rx[16], double Lx[16], double Ry[16], double Ly[16])
+{
+   dflo::EigenMatrices m;
+   dflo::compute_eigen_matrix (W, m);
+   for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j)
+      {
+         Rx[4 * i + j] = m.Rx[i][j];
+         Lx[4 * i + j] = m.Lx[i][j];
+         Ry[4 * i + j] = m.Ry[i][j];
+         Ly[4 * i + j] = m.Ly[i][j];
+      }
+}
+double dflo_emu_minmod (double a, double b, double c, double Mdx2) { return dflo::minmod (a, b, c, Mdx2); }
+}
