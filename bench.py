@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- million DoF-updates/s of the explicit RK stage (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                     CPU reference arm (oracle on host cores)
+
+One "step" = one full time step of the hot path (compute_time_step + n_rk RK stages: residual,
+M^-1, RK combine, cell average, configured limiters) over the whole mesh; one DoF-update = one
+scalar unknown advanced through one RK stage.  Workload at N = 1: BASELINE.json configs[1]
+(isentropic vortex, Q3, 256x256 Cartesian cells, periodic, Roe flux, SSP-RK3).  For N > 1 the
+per-GPU work is kept (weak scaling): the periodic box is extended to 256N x 256 cells and sharded
+by cell id, one NCCL halo exchange per stage.
+
+Timing: `value` = device-resident throughput: every step is one dflo_b200_advance() call (CUDA
+graph replay) timed with CUDA events on the ctx stream; L2 (126 MB) is flushed before every timed
+step by rewriting a 256 MB buffer (the 3 x 32 MiB state of this workload would otherwise sit in
+L2 across steps); the per-step event times are summed, max over ranks.  `e2e` = the same step
+through the C ABI with HOST buffers: set_solution (pinned host -> device) + advance + get_solution
+(device -> pinned host) inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "million DoF-updates/sec (explicit RK stage)"
+UNIT = "MDoF-updates/s"
+PERIODIC = {1: ("periodic", 3), 3: ("periodic", 1), 2: ("periodic", 4), 4: ("periodic", 2)}
+WORKLOADS = {
+    # name: (description, basis, degree, flux, cells per side per GPU)
+    "cfg2": ("isentropic_vortex, Q3, 256x256 Cartesian, Roe flux, explicit RK3, periodic", "Qk", 3, "roe", 256),
+    "cfg1": ("isentropic_vortex, Q1, 32x32 Cartesian, LxF flux, explicit RK2, periodic", "Qk", 1, "lxf", 32),
+}
+
+
+def isentropic_vortex(x, y):
+    """src_mpi/ic.cc:44-61: vortex advected with M_inf = 0.5 along x (exact solution)."""
+    g, beta = 1.4, 5.0
+    a1 = 0.5 * beta / np.pi
+    a2 = 0.5 * (g - 1.0) * a1 * a1
+    r2 = x * x + y * y
+    rho = (1.0 - a2 * np.exp(1.0 - r2)) ** (1.0 / (g - 1.0))
+    vx = 0.5 - a1 * y * np.exp(0.5 * (1.0 - r2))
+    vy = a1 * x * np.exp(0.5 * (1.0 - r2))
+    pre = rho ** g / g
+    return np.stack([rho * vx, rho * vy, rho, pre / (g - 1.0) + 0.5 * rho * (vx * vx + vy * vy)], axis=-1)
+
+
+def gauss01(n):
+    x, w = np.polynomial.legendre.leggauss(n)
+    return 0.5 * (x + 1.0), 0.5 * w
+
+
+def initial_dofs(nx, ny, x0, x1, y0, y1, k):
+    """Qk interpolation of the vortex at the Gauss nodes, reference DoF layout [cell][comp][node]."""
+    gx, _ = gauss01(k + 1)
+    hx, hy = (x1 - x0) / nx, (y1 - y0) / ny
+    xs = x0 + hx * (np.arange(nx)[:, None] + gx[None, :])          # [nx][a]
+    ys = y0 + hy * (np.arange(ny)[:, None] + gx[None, :])          # [ny][b]
+    X = np.broadcast_to(xs[None, :, None, :], (ny, nx, k + 1, k + 1))   # [j][i][b][a]
+    Y = np.broadcast_to(ys[:, None, :, None], (ny, nx, k + 1, k + 1))
+    f = isentropic_vortex(X, Y)                                     # [j][i][b][a][c]
+    u = np.transpose(f, (0, 1, 4, 2, 3)).reshape(ny * nx, 4, (k + 1) ** 2)
+    return np.ascontiguousarray(u).reshape(-1)
+
+
+def sample_clocks(stop, out):
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i",
+                              os.environ.get("LOCAL_RANK", "0"), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+    except Exception:
+        return
+    while not stop.is_set():
+        line = p.stdout.readline()
+        if not line:
+            break
+        out.append(line.strip())
+    p.terminate()
+
+
+def clocks_summary(lines):
+    sm, mx, reasons = [], 0, set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in lines:
+        f = [s.strip() for s in ln.split(",")]
+        try:
+            sm.append(float(f[0]))
+            mx = max(mx, float(f[1]))
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        except Exception:
+            continue
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline(workload, budget_s=15.0, threads=None):
+    """The oracle (kind 'port': restated assembly; physics = the reference's own equation.h object
+    code when oracle/_ref was built) timed on this box's host cores on a bounded sample."""
+    from oracle import oracle as O
+    desc, basis, k, flux, _ = WORKLOADS[workload]
+    threads = threads or os.cpu_count() or 1
+    variant = "refphys" if os.path.exists(O.lib_path("refphys")) else "restated"
+    if variant == "restated":
+        O.build()
+
+    def make(n):
+        p = O.make_params(basis=basis, degree=k, flux=flux, bc=PERIODIC, cfl=0.9, n_threads=threads)
+        o = O.Oracle(*O.rect_mesh(n, n, -5, 5, -5, 5), p, variant=variant)
+        xq = o.cell_qpoints()
+        o.set_initial_condition(isentropic_vortex(xq[..., 0], xq[..., 1]))
+        o.compute_cell_average()
+        return o
+    n = 32
+    o = make(n)
+    t0 = time.perf_counter()
+    o.run_steps(1)
+    t1 = time.perf_counter() - t0
+    per_cell = t1 / (n * n)
+    # size the sample: ~budget_s of CPU work in a handful of steps
+    n = int(min(256, max(32, np.sqrt(budget_s / 4.0 / per_cell))))
+    o = make(n)
+    steps = max(1, int(budget_s / (per_cell * n * n)))
+    t0 = time.perf_counter()
+    o.run_steps(steps)
+    dt = time.perf_counter() - t0
+    updates = n * n * o.D * o.n_rk * steps
+    return {"value": updates / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "physics": O.load(variant).phys_impl_name().decode(),
+            "sample": "%d steps of %s on a %dx%d sample mesh, %.1f s wall" % (steps, desc.split(",")[0] + " " + basis[0] + str(k)
+                                                                              + " " + flux, n, n, dt),
+            "sample_cells": n * n, "sample_steps": steps, "wall_s": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc = WORKLOADS[args.workload][0]
+    from oracle import oracle as O
+    _, basis, k, flux, _ = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    variant = "refphys" if os.path.exists(O.lib_path("refphys")) else "restated"
+    if variant == "restated":
+        O.build()
+    # each "step" = one time step on a bounded sample mesh sized for ~1 s
+    n = 32
+    p = O.make_params(basis=basis, degree=k, flux=flux, bc=PERIODIC, cfl=0.9, n_threads=threads)
+
+    def make(n):
+        o = O.Oracle(*O.rect_mesh(n, n, -5, 5, -5, 5), p, variant=variant)
+        xq = o.cell_qpoints()
+        o.set_initial_condition(isentropic_vortex(xq[..., 0], xq[..., 1]))
+        o.compute_cell_average()
+        return o
+    o = make(n)
+    t0 = time.perf_counter()
+    o.run_steps(1)
+    per_cell = (time.perf_counter() - t0) / (n * n)
+    total = max(1, args.steps + args.warmup)
+    n = int(min(256, max(32, np.sqrt(min(2.0, 150.0 / total) / per_cell))))
+    o = make(n)
+    o.run_steps(args.warmup)
+    t0 = time.perf_counter()
+    o.run_steps(args.steps)
+    dt = time.perf_counter() - t0
+    updates = n * n * o.D * o.n_rk * args.steps
+    val = updates / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "sample": "%dx%d cells of the same case per step (bounded CPU sample)" % (n, n),
+                   "host_threads": threads},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "physics": O.load(variant).phys_impl_name().decode(),
+                         "sample": "%d steps on %dx%d cells, OpenMP workers + serial copier (WorkStream-like)" % (args.steps, n, n)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "dflo itself needs deal.II (absent): this arm times the CPU restatement of its explicit path "
+                "(oracle/), physics from the reference's own equation.h when oracle/_ref is present",
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from dflo_b200 import abi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        L = abi.load_library()
+        idbuf = (abi.ctypes.c_char * 128)()
+        if rank == 0:
+            assert L.dflo_b200_nccl_unique_id(idbuf) == 0
+        t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        nccl_id = bytes(t.cpu().tolist())
+
+    desc, basis, k, flux, npg = WORKLOADS[args.workload]
+    nx, ny = npg * world, npg
+    x0, x1, y0, y1 = -5.0 * world, 5.0 * world, -5.0, 5.0
+    params, pair = abi.make_params(basis=basis, degree=k, flux=flux, bc=PERIODIC, cfl=0.9, compat="mpi")
+    mesh = abi.Mesh("rectangle", [nx, ny, x0, x1, y0, y1, 4, 2, 1, 3])
+    flat = mesh.flatten(params, pair)
+    eng = abi.Engine(flat, params, device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
+    D, n_rk = eng.D, eng.n_rk
+    n_dof = nx * ny * D
+    u_host = torch.empty(n_dof, dtype=torch.float64, pin_memory=True)
+    u_host.numpy()[:] = initial_dofs(nx, ny, x0, x1, y0, y1, k)
+    u_np = u_host.numpy()
+    eng.set_solution(u_np)
+
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_step(t):
+        if flush is not None:
+            flush.zero_()
+            torch.cuda.synchronize()
+        t, _ = eng.advance(1, elapsed=t)
+        return t, eng.last_advance_ms()
+
+    t = 0.0
+    for _ in range(args.warmup):
+        t, _ = timed_step(t)
+    clk_lines, stop = [], threading.Event()
+    th = threading.Thread(target=sample_clocks, args=(stop, clk_lines), daemon=True)
+    if rank == 0:
+        th.start()
+    barrier()
+    launches0 = eng.launch_count()
+    wall0 = time.perf_counter()
+    ms_total = 0.0
+    for _ in range(args.steps):
+        t, ms = timed_step(t)
+        ms_total += ms
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = eng.launch_count() - launches0
+    # back-to-back (no flush, one advance call, one graph launch per step): launch-overhead view
+    barrier()
+    tb, _ = eng.advance(args.steps, elapsed=t)
+    ms_b2b = eng.last_advance_ms()
+    stop.set()
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e_steps = max(3, min(args.steps, 20))
+    barrier()
+    e0 = time.perf_counter()
+    te = tb
+    for _ in range(e2e_steps):
+        eng.set_solution(u_np)
+        te, _ = eng.advance(1, elapsed=te)
+        eng.get_solution(out=u_np)
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    owned_dof = eng.cell_range()[1] * D - eng.cell_range()[0] * D
+
+    # ---- kernel-only timing of the dominant (stage) kernel for the roofline ----
+    k_ms = eng.time_stage_kernel(rk=1, reps=20, flush_bytes=0 if args.no_flush else 256 * 1024 * 1024)
+    k_ms_warm = eng.time_stage_kernel(rk=1, reps=20, flush_bytes=0)
+    eng.poll_error()
+
+    vals = torch.tensor([ms_total, ms_b2b, e2e_s, k_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_total, ms_b2b, e2e_s, k_ms = [float(v) for v in vals.cpu()]
+
+    if rank == 0:
+        updates_per_step = n_dof * n_rk
+        value = updates_per_step * args.steps / (ms_total * 1e-3) / 1e6
+        peak, peak_src = measured_peak_hbm()
+        bytes_per_update = 24.0 + 32.0 / D   # read u, read u_old, write u (+ cell mean)
+        alg_bytes_launch = (n_dof // world) * bytes_per_update
+        achieved = alg_bytes_launch / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "cells": nx * ny, "dofs": n_dof, "rk_stages": n_rk,
+                       "parallelism": "cells sharded by id over %d GPU(s), 1 NCCL halo exchange per stage" % world,
+                       "l2": "flushed before every timed step (256 MB rewrite)" if flush is not None else "not flushed",
+                       "timing": "CUDA events on the ctx stream around each step's graph launch, summed, max over ranks"},
+            "value_back_to_back_no_flush": updates_per_step * args.steps / (ms_b2b * 1e-3) / 1e6,
+            "wall_s_timed_region": wall,
+            "e2e": {"value": updates_per_step * e2e_steps / e2e_s / 1e6, "unit": UNIT,
+                    "h2d_bytes_per_step": int(owned_dof * 8), "d2h_bytes_per_step": int(owned_dof * 8),
+                    "steps": e2e_steps, "what": "set_solution(pinned host) + advance(1 step) + get_solution(pinned host) per step"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "StageKernel<%s,%d,%s>" % (basis, k + 1, flux),
+                         "kernel_ms": k_ms, "kernel_ms_l2_warm": k_ms_warm,
+                         "algorithmic_bytes_per_launch": alg_bytes_launch,
+                         "bytes_per_dof_update": bytes_per_update, "peak_source": peak_src},
+            "clocks": clocks_summary(clk_lines),
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload)
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -164,6 +164,7 @@ def _declare_engine(L, prefix):
     f("stream").argtypes = [vp]
     f("synchronize").argtypes = [vp]
     f("last_advance_ms").argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    f("time_stage_kernel").argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_float)]
 
 
 def _dp(a):
@@ -371,6 +372,11 @@ class Engine:
 
     def synchronize(self):
         self._check(self._f("synchronize")(self.h))
+
+    def time_stage_kernel(self, rk=1, reps=20, flush_bytes=0):
+        ms = ctypes.c_float(0.0)
+        self._check(self._f("time_stage_kernel")(self.h, rk, reps, flush_bytes, ctypes.byref(ms)))
+        return ms.value
 
     def last_advance_ms(self):
         ms = ctypes.c_float(0.0)

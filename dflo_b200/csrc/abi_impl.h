@@ -125,6 +125,10 @@
       c->eng.bk.sync ();                                                                                                 \
       return c->eng.bk.check (c->eng.error);                                                                             \
    }                                                                                                                     \
+   int DFLO_ABI_CAT (PREFIX, time_stage_kernel) (CTX *c, int rk, int reps, size_t flush_bytes, float *ms)                \
+   {                                                                                                                     \
+      return (c && ms) ? c->eng.time_stage_kernel (rk, reps, flush_bytes, ms) : DFLO_E_INVALID;                          \
+   }                                                                                                                     \
    int DFLO_ABI_CAT (PREFIX, last_advance_ms) (CTX *c, float *ms)                                                        \
    {                                                                                                                     \
       if (!c || !ms) return DFLO_E_INVALID;                                                                              \

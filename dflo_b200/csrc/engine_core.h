@@ -183,6 +183,7 @@ namespace dflo
       const double *v;
       double *out;
       int64_t n;
+      int nblocks;
    };
    struct SumSqKernel // right_hand_side.l2_norm()^2, claw.cc:749
    {
@@ -196,7 +197,7 @@ namespace dflo
          if (p == 0)
          {
             double s = 0.0;
-            const int64_t stride = (int64_t) grid (A.n) * THREADS;
+            const int64_t stride = (int64_t) A.nblocks * THREADS;
             for (int64_t i = (int64_t) bid * THREADS + tid; i < A.n; i += stride) s += A.v[i] * A.v[i];
             sm[tid] = s;
          }
@@ -552,7 +553,8 @@ namespace dflo
             s.v = rhs;
             s.out = d_scratch;
             s.n = (int64_t) lm.n_owned * D ();
-            bk.template launch<SumSqKernel> (SumSqKernel::grid (s.n), s);
+            s.nblocks = SumSqKernel::grid (s.n);
+            bk.template launch<SumSqKernel> (s.nblocks, s);
             bk.allreduce_sum (d_scratch, 1);
             double ss = 0.0;
             bk.sync ();
@@ -629,6 +631,33 @@ namespace dflo
          int rc = bk.check (error);
          if (rc) return rc;
          return poll_error ();
+      }
+
+      // Instrumentation: average device time of the stage kernel of RK stage rk alone, timed
+      // with events on the ctx stream, L2 flushed (a scratch buffer larger than L2 is rewritten)
+      // before every repetition.  The solution state is not modified.
+      int time_stage_kernel (int rk, int reps, size_t flush_bytes, float *avg_ms)
+      {
+         if (rk < 0 || rk >= n_rk || reps < 1) return fail (DFLO_E_INVALID, "time_stage_kernel: bad arguments");
+         bk.halo_wait ();
+         void *scratch = flush_bytes ? bk.template alloc<char> (flush_bytes) : nullptr;
+         const int out = free_buffer ();
+         StageArgs a = stage_args (rk, MODE_STAGE);
+         a.out = U[out];
+         a.avg_out = AVG[out];
+         double total = 0.0;
+         for (int r = 0; r < reps; ++r)
+         {
+            if (scratch) bk.zero (scratch, flush_bytes);
+            bk.timer_start ();
+            launch_stage (bk, tab.basis, tab.n1, prm.flux_type, a);
+            bk.timer_stop ();
+            total += bk.timer_ms ();
+         }
+         bk.sync ();
+         bk.free (scratch);
+         *avg_ms = (float) (total / reps);
+         return bk.check (error);
       }
 
       int poll_error ()

@@ -1,0 +1,267 @@
+// The product: CUDA backend of Engine<> for sm_100a and the extern "C" entry points of
+// include/dflo_b200.h.  One CUDA stream per ctx; whole time steps are captured once into a CUDA
+// graph (one per starting solution buffer) and replayed, so a step costs one graph launch and no
+// host round trip; the halo exchange of a sharded ctx is one NCCL group of send/recv pairs per
+// RK stage on the same stream.  There is no CPU fallback: without a CUDA device create() returns
+// DFLO_E_NO_DEVICE.
+#include "abi_impl.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+
+namespace
+{
+   template <class K>
+   __global__ void __launch_bounds__ (K::THREADS) phase_kernel (const typename K::Args a)
+   {
+      extern __shared__ double dflo_smem[];
+#pragma unroll
+      for (int p = 0; p < K::NPHASE; ++p)
+      {
+         K::phase (p, a, dflo_smem, threadIdx.x, blockIdx.x);
+         if (p + 1 < K::NPHASE) __syncthreads ();
+      }
+   }
+
+   template <class K>
+   __global__ void __launch_bounds__ (256) thread_kernel (const typename K::Args a, int n)
+   {
+      const int j = blockIdx.x * 256 + threadIdx.x;
+      if (j < n) K::thread (a, j);
+   }
+
+   struct CudaBackend
+   {
+      cudaStream_t stream = nullptr;
+      cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+      int device = 0, rank = 0, world = 1;
+      int64_t launches = 0;
+      cudaError_t first_error = cudaSuccess;
+      ncclResult_t first_nccl_error = ncclSuccess;
+      ncclComm_t comm = nullptr;
+      bool use_graphs = true;
+      bool capturing = false;
+      struct Graph
+      {
+         cudaGraphExec_t exec;
+         int cur_after;
+         int64_t launches_per_replay;
+      };
+      std::map<int, Graph> graphs;
+      int64_t launches_at_capture = 0;
+
+      void note (cudaError_t e)
+      {
+         if (e != cudaSuccess && first_error == cudaSuccess) first_error = e;
+      }
+      void note (ncclResult_t e)
+      {
+         if (e != ncclSuccess && first_nccl_error == ncclSuccess) first_nccl_error = e;
+      }
+
+      int open (int dev, int r, int w, const void *nccl_id, std::string &err)
+      {
+         int count = 0;
+         if (cudaGetDeviceCount (&count) != cudaSuccess || count == 0)
+         {
+            (void) cudaGetLastError ();
+            err = "no CUDA device visible; dflo_b200 has no CPU fallback";
+            return DFLO_E_NO_DEVICE;
+         }
+         if (dev < 0 || dev >= count)
+         {
+            err = "device index out of range";
+            return DFLO_E_INVALID;
+         }
+         device = dev;
+         rank = r;
+         world = w;
+         note (cudaSetDevice (device));
+         note (cudaStreamCreateWithFlags (&stream, cudaStreamNonBlocking));
+         note (cudaEventCreate (&ev0));
+         note (cudaEventCreate (&ev1));
+         const char *g = std::getenv ("DFLO_B200_GRAPHS");
+         use_graphs = g ? (std::atoi (g) != 0) : true;
+         if (world > 1)
+         {
+            if (!nccl_id)
+            {
+               err = "sharded context needs an NCCL unique id";
+               return DFLO_E_INVALID;
+            }
+            ncclUniqueId id;
+            std::memcpy (&id, nccl_id, sizeof (id));
+            const ncclResult_t rc = ncclCommInitRank (&comm, world, id, rank);
+            if (rc != ncclSuccess)
+            {
+               err = std::string ("ncclCommInitRank: ") + ncclGetErrorString (rc);
+               return DFLO_E_NCCL;
+            }
+         }
+         return check (err);
+      }
+
+      void close ()
+      {
+         if (comm) ncclCommDestroy (comm);
+         comm = nullptr;
+         if (ev0) cudaEventDestroy (ev0);
+         if (ev1) cudaEventDestroy (ev1);
+         if (stream) cudaStreamDestroy (stream);
+         stream = nullptr;
+         ev0 = ev1 = nullptr;
+      }
+
+      template <class T> T *alloc (size_t n)
+      {
+         void *p = nullptr;
+         note (cudaMalloc (&p, (n ? n : 1) * sizeof (T)));
+         return static_cast<T *> (p);
+      }
+      void free (void *p)
+      {
+         if (p) note (cudaFree (p));
+      }
+      void h2d (void *d, const void *h, size_t b)
+      {
+         if (b) note (cudaMemcpyAsync (d, h, b, cudaMemcpyHostToDevice, stream));
+      }
+      void d2h (void *h, const void *d, size_t b)
+      {
+         if (!b) return;
+         note (cudaMemcpyAsync (h, d, b, cudaMemcpyDeviceToHost, stream));
+         note (cudaStreamSynchronize (stream));
+      }
+      void zero (void *d, size_t b) { note (cudaMemsetAsync (d, 0, b, stream)); }
+      void sync () { note (cudaStreamSynchronize (stream)); }
+      void *stream_handle () const { return (void *) stream; }
+
+      int check (std::string &err)
+      {
+         note (cudaPeekAtLastError ());
+         if (first_error != cudaSuccess)
+         {
+            err = std::string ("CUDA: ") + cudaGetErrorString (first_error);
+            return DFLO_E_CUDA;
+         }
+         if (first_nccl_error != ncclSuccess)
+         {
+            err = std::string ("NCCL: ") + ncclGetErrorString (first_nccl_error);
+            return DFLO_E_NCCL;
+         }
+         return DFLO_OK;
+      }
+
+      template <class K> void launch (int grid, const typename K::Args &a)
+      {
+         if (grid <= 0) return;
+         ++launches;
+         phase_kernel<K><<<grid, K::THREADS, K::SMEM_DOUBLES * sizeof (double), stream>>> (a);
+         note (cudaPeekAtLastError ());
+      }
+      template <class K> void launch1d (int n, const typename K::Args &a)
+      {
+         if (n <= 0) return;
+         ++launches;
+         thread_kernel<K><<<(n + 255) / 256, 256, 0, stream>>> (a, n);
+         note (cudaPeekAtLastError ());
+      }
+
+      // ---- CUDA graphs: one instantiated graph of a whole time step per starting buffer ----
+      void drop_graphs ()
+      {
+         for (auto &kv : graphs) cudaGraphExecDestroy (kv.second.exec);
+         graphs.clear ();
+      }
+      bool graph_launch (int key, int *cur_after)
+      {
+         auto it = graphs.find (key);
+         if (it == graphs.end ()) return false;
+         note (cudaGraphLaunch (it->second.exec, stream));
+         launches += it->second.launches_per_replay;
+         *cur_after = it->second.cur_after;
+         return true;
+      }
+      bool capture_begin ()
+      {
+         if (!use_graphs || world > 1) return false; // sharded steps run eagerly (NCCL on the stream)
+         if (cudaStreamBeginCapture (stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+         {
+            (void) cudaGetLastError ();
+            return false;
+         }
+         capturing = true;
+         launches_at_capture = launches;
+         return true;
+      }
+      void capture_end_and_launch (int key, int cur_after)
+      {
+         cudaGraph_t g = nullptr;
+         capturing = false;
+         note (cudaStreamEndCapture (stream, &g));
+         if (!g) return;
+         Graph entry;
+         entry.cur_after = cur_after;
+         entry.launches_per_replay = launches - launches_at_capture;
+         const cudaError_t rc = cudaGraphInstantiate (&entry.exec, g, 0);
+         cudaGraphDestroy (g);
+         note (rc);
+         if (rc != cudaSuccess) return;
+         graphs[key] = entry;
+         note (cudaGraphLaunch (entry.exec, stream)); // capture recorded the step, now run it
+      }
+
+      void timer_start () { note (cudaEventRecord (ev0, stream)); }
+      void timer_stop () { note (cudaEventRecord (ev1, stream)); }
+      float timer_ms ()
+      {
+         float ms = 0.0f;
+         note (cudaEventSynchronize (ev1));
+         note (cudaEventElapsedTime (&ms, ev0, ev1));
+         return ms;
+      }
+
+      // ---- NCCL: halo as one group of send/recv pairs, dt/residual as tiny all-reduces ----
+      void halo_begin ()
+      {
+         if (comm) note (ncclGroupStart ());
+      }
+      void halo_send (int peer, const double *buf, size_t count)
+      {
+         if (comm) note (ncclSend (buf, count, ncclDouble, peer, comm, stream));
+      }
+      void halo_recv (int peer, double *buf, size_t count)
+      {
+         if (comm) note (ncclRecv (buf, count, ncclDouble, peer, comm, stream));
+      }
+      void halo_end ()
+      {
+         if (comm) note (ncclGroupEnd ());
+      }
+      void halo_wait () {}
+      void allreduce_min_dt (double *p)
+      {
+         if (comm) note (ncclAllReduce (p, p, 1, ncclDouble, ncclMin, comm, stream));
+      }
+      void allreduce_sum (double *p, int n)
+      {
+         if (comm) note (ncclAllReduce (p, p, n, ncclDouble, ncclSum, comm, stream));
+      }
+   };
+}
+
+DFLO_DEFINE_ABI (dflo_b200_, CudaBackend, dflo_ctx)
+
+extern "C" int dflo_b200_nccl_unique_id (void *out128)
+{
+   if (!out128) return DFLO_E_INVALID;
+   ncclUniqueId id;
+   if (ncclGetUniqueId (&id) != ncclSuccess) return DFLO_E_NCCL;
+   static_assert (sizeof (id) == 128, "ncclUniqueId is 128 bytes");
+   std::memcpy (out128, &id, sizeof (id));
+   return DFLO_OK;
+}

@@ -104,7 +104,6 @@ namespace dflo
    }
 }
 
-#ifndef __CUDA_ARCH__
 #include <cctype>
 #include <cstdlib>
 #include <string>
@@ -373,4 +372,3 @@ namespace dflo
       }
    };
 }
-#endif

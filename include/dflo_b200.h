@@ -172,6 +172,10 @@ int64_t dflo_b200_launch_count (const dflo_ctx *ctx);
 /* CUDA stream the ctx launches on (cudaStream_t as void*), for event timing by the caller */
 void *dflo_b200_stream (const dflo_ctx *ctx);
 int dflo_b200_synchronize (dflo_ctx *ctx);
+/* average device time (ms) of the stage kernel of RK stage rk alone over `reps` launches, CUDA
+ * events on the ctx stream, with flush_bytes of scratch rewritten before each launch to evict L2
+ * (0 = no flush); the solution state is left untouched */
+int dflo_b200_time_stage_kernel (dflo_ctx *ctx, int rk, int reps, size_t flush_bytes, float *avg_ms);
 /* device-resident time of the last dflo_b200_advance call, measured with CUDA events on the ctx stream */
 int dflo_b200_last_advance_ms (dflo_ctx *ctx, float *ms);
 

@@ -1,0 +1,229 @@
+"""Shared test scaffolding: builds the same case for the CPU oracle and for the engine (the CUDA
+library through its C ABI, or the CPU emulation build of the same kernel code in the no-GPU tier),
+feeds both identical inputs and compares."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from dflo_b200 import abi  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_LIB = os.path.join(EMU_DIR, "_build", "libdflo_emu.so")
+
+PERIODIC_BOX = {1: ("periodic", 3), 3: ("periodic", 1), 2: ("periodic", 4), 4: ("periodic", 2)}
+SOD_BC = {0: "slip", 1: "outflow", 2: "inflow"}
+DMR_BC = {0: "outflow", 1: "slip", 2: "outflow", 3: "inflow", 4: "inflow"}
+STEP_BC = {1: "inflow", 2: "slip", 3: "outflow"}
+
+_emu = None
+
+
+def build_emu():
+    """g++ build of tests/emu (the product's kernel phase code on a CPU emulation backend)."""
+    src = [os.path.join(EMU_DIR, "emu_backend.cc")] + [os.path.join(ROOT, "dflo_b200", "csrc", f)
+                                                       for f in ("tables.cc", "host/mesh.cc", "host/host_abi.cc")]
+    deps = src + [os.path.join(ROOT, "dflo_b200", "csrc", f) for f in
+                  ("kernels.cuh", "euler.cuh", "engine_core.h", "abi_impl.h", "partition.h", "expr.h", "tables.h",
+                   "tables_pack.h")]
+    if os.path.exists(EMU_LIB) and all(os.path.getmtime(EMU_LIB) >= os.path.getmtime(d) for d in deps):
+        return EMU_LIB
+    os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas"] + src
+                   + ["-o", EMU_LIB], check=True)
+    return EMU_LIB
+
+
+def emu_lib():
+    global _emu
+    if _emu is None:
+        L = ctypes.CDLL(build_emu())
+        abi._declare_host(L)
+        abi._declare_engine(L, "dflo_emu_")
+        L.dflo_emu_halo_send_count.restype = ctypes.c_size_t
+        L.dflo_emu_halo_recv_count.restype = ctypes.c_size_t
+        for n in ("halo_send_count", "halo_recv_count"):
+            getattr(L, "dflo_emu_" + n).argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.dflo_emu_halo_get_send.argtypes = [ctypes.c_void_p, ctypes.c_int, abi.c_double_p]
+        L.dflo_emu_halo_put_recv.argtypes = [ctypes.c_void_p, ctypes.c_int, abi.c_double_p]
+        for n in ("n_peers", "n_local", "n_compute"):
+            getattr(L, "dflo_emu_" + n).argtypes = [ctypes.c_void_p]
+        L.dflo_emu_peer_rank.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.dflo_emu_minmod.restype = ctypes.c_double
+        L.dflo_emu_minmod.argtypes = [ctypes.c_double] * 4
+        _emu = L
+    return _emu
+
+
+def gpu_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+# ---------------------------------------------------------------------------------------------
+# initial conditions (numpy; evaluated once and fed to both sides)
+# ---------------------------------------------------------------------------------------------
+def ic_vortex(x, y):
+    return O.isentropic_vortex(x, y, compat="mpi")
+
+
+def ic_sod(x, y):
+    rho = np.where(x <= 0.5, 1.0, 0.125)
+    E = np.where(x <= 0.5, 2.5, 0.25)
+    return np.stack([0 * x, 0 * x, rho, E], axis=-1)
+
+
+def ic_dmr(x, y):
+    s = x < 1.0 / 6.0 + y / np.sqrt(3.0)
+    return np.stack([57.1576766498 * s, -33.0 * s, 8.0 * s + 1.4 * (~s), 563.5 * s + 2.5 * (~s)], axis=-1)
+
+
+def ic_step(x, y):
+    return np.stack([4.2 + 0 * x, 0 * x, 1.4 + 0 * x, 8.8 + 0 * x], axis=-1)
+
+
+def ic_smooth(x, y):
+    return np.stack([1.0 + 0.1 * np.sin(3 * x), 0.2 * np.cos(2 * y), 1.4 + 0.1 * x, 8.8 + y], axis=-1)
+
+
+def ic_pulse(x, y):
+    r2 = (x - 0.45) ** 2 + (y - 0.05) ** 2
+    rho = 0.05 + np.exp(-r2 / 0.004)
+    p = 0.02 + 20 * np.exp(-r2 / 0.004)
+    return np.stack([0 * x, 0 * x, rho, p / 0.4], axis=-1)
+
+
+def ic_blast(x, y):
+    r2 = (x - 0.45) ** 2 + (y - 0.05) ** 2
+    p = np.where(r2 < 0.01, 500.0, 0.01)
+    return np.stack([0 * x, 0 * x, 1.0 + 0 * x, p / 0.4], axis=-1)
+
+
+class Case:
+    """One configuration built twice: oracle (CPU restatement) and engine (C ABI)."""
+
+    def __init__(self, mesh, bc, ic, backend="emu", oracle_variant="restated", world=1, **prm):
+        self.prm_kw = dict(prm)
+        self.lib = emu_lib() if backend == "emu" else abi.load_library()
+        self.prefix = "dflo_emu_" if backend == "emu" else "dflo_b200_"
+        self.backend = backend
+        self.params, self.pair = abi.make_params(bc=bc, **prm)
+        self.mesh = abi.Mesh(mesh[0], mesh[1], lib=self.lib)
+        self.flat = self.mesh.flatten(self.params, self.pair)
+        v, c, bl, bi = self.mesh.primitive()
+        okw = {k: v_ for k, v_ in prm.items() if k != "time_step"}
+        self.oracle = O.Oracle(v, c, bl, bi, O.make_params(bc=bc, **okw), variant=oracle_variant)
+        xq = self.oracle.cell_qpoints()
+        self.oracle.set_initial_condition(ic(xq[..., 0], xq[..., 1]))
+        self.oracle.compute_cell_average()
+        self.u0 = self.oracle.solution().copy()
+        self.world = world
+        if world == 1:
+            self.engines = [abi.Engine(self.flat, self.params, lib=self.lib, prefix=self.prefix)]
+        else:
+            assert backend == "emu"
+            self.engines = [abi.Engine(self.flat, self.params, rank=r, world=world, nccl_id=b"\0" * 128, lib=self.lib,
+                                       prefix=self.prefix) for r in range(world)]
+        for e in self.engines:
+            e.set_solution(self.u0)
+        self.exchange()
+        self.engine = self.engines[0]
+        self.g = None
+        self.t = 0.0
+
+    # emulated halo exchange between in-process ranks
+    def exchange(self):
+        if self.world == 1:
+            return
+        L = self.lib
+        for e in self.engines:
+            for i in range(L.dflo_emu_n_peers(e.h)):
+                p = L.dflo_emu_peer_rank(e.h, i)
+                n = L.dflo_emu_halo_send_count(e.h, p)
+                if n == 0:
+                    continue
+                buf = np.zeros(n)
+                L.dflo_emu_halo_get_send(e.h, p, buf.ctypes.data_as(abi.c_double_p))
+                dst = self.engines[p]
+                assert L.dflo_emu_halo_recv_count(dst.h, e.rank) == n
+                L.dflo_emu_halo_put_recv(dst.h, e.rank, buf.ctypes.data_as(abi.c_double_p))
+
+    def set_boundary(self, values=(57.1576766498, -33.0, 8.0, 563.5), wiggle=0.0):
+        o = self.oracle
+        if o.n_bfaces == 0:
+            return
+        _, _, _, xqb = o.bfaces()
+        g = np.zeros((o.n_bfaces, o.nqf, 4))
+        g[...] = np.asarray(values)
+        g[..., 2] += wiggle * np.sin(xqb[..., 0])
+        self.g = g
+        o.set_bc_values(g)
+        for e in self.engines:
+            e.set_boundary_values(g)
+
+    def solution(self):
+        u = np.zeros(self.oracle.n_cells * self.oracle.D)
+        for e in self.engines:
+            e.get_solution(out=u)
+        return u
+
+    def rhs_pair(self):
+        r_o = self.oracle.assemble()
+        r_e = np.zeros_like(r_o)
+        for e in self.engines:
+            e.assemble_rhs(self.t)
+        for e in self.engines:
+            D = e.D
+            b, en = e.cell_range()
+            r_e[b * D:en * D] = e.get_rhs()[b * D:en * D]
+        return r_o, r_e
+
+    def limit_initial(self):
+        self.oracle.apply_limiter()
+        self.oracle.commit_step()
+        for e in self.engines:
+            e.limit_initial_condition()
+        self.exchange()
+
+    def step(self):
+        """One full time step on both sides with the oracle's dt; returns (#cells whose limiter
+        decision differs summed over the stages, dt_oracle, dt_engine)."""
+        o = self.oracle
+        dt_o = o.compute_dt(self.t)
+        dt_e = min(e.compute_dt(self.t) for e in self.engines)
+        flagdiff = 0
+        for rk in range(o.n_rk):
+            err, _ = o.rk_stage(rk, dt_o)
+            assert err == 0, "oracle limiter error %d" % err
+            for e in self.engines:
+                e.rk_stage(rk, self.t, dt_o)
+            self.exchange()
+            fo = o.limited_flags()
+            fe = np.zeros_like(fo)
+            for e in self.engines:
+                b, en = e.cell_range()
+                fe[b:en] = e.limited_flags()[b:en]
+            flagdiff += int(np.count_nonzero(fo != fe))
+        o.commit_step()
+        for e in self.engines:
+            e.commit_step()
+        self.t += dt_o
+        return flagdiff, dt_o, dt_e
+
+    def rel_err(self):
+        uo = self.oracle.solution()
+        return np.abs(uo - self.solution()).max() / max(1.0, np.abs(uo).max())
+
+    def close(self):
+        for e in self.engines:
+            e.close()
