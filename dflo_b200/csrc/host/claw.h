@@ -1,0 +1,56 @@
+// Host-side mirror of dflo's ConservationLaw<2> driver (reference src/claw.h:57-365) for the
+// explicit path: same member names and the same control flow as src/claw.cc, with the body of
+// the RK loop (assemble_system .. apply_positivity_limiter) delegated to the B200 engine through
+// the C ABI of include/dflo_b200.h -- exactly the calls INTEGRATION.md asks a dflo maintainer to
+// add behind `#ifdef DFLO_WITH_B200`.
+#pragma once
+
+#include "../../../include/dflo_b200.h"
+#include "../tables.h"
+#include "mesh.h"
+#include "parameters.h"
+
+#include <string>
+#include <vector>
+
+namespace dflo
+{
+   class ConservationLaw
+   {
+   public:
+      // input_filename: input.prm; mesh_override: "<generator> <args...>" or empty (then "mesh file"
+      // is read as gmsh v2, relative to the .prm); overrides: extra parameter text applied last
+      ConservationLaw (const std::string &input_filename, const std::string &mesh_override, const std::string &overrides,
+                       int compat);
+      ~ConservationLaw ();
+
+      bool ok () const { return error.empty (); }
+      std::string error;
+
+      // setup_system + set_initial_condition + initial limiting (src/claw.cc:981-1003)
+      int setup_system (int device, int rank, int world, const void *nccl_unique_id);
+      // the time loop (src/claw.cc:1026-1110), at most max_steps steps (<0: until final time)
+      int run (int max_steps, bool verbose);
+
+      void set_initial_condition (std::vector<double> &u) const;   // src/ic.cc:104-182
+      int get_solution (std::vector<double> &u);
+      int output_results (const std::string &path);                // src/output.cc (VTU)
+
+      Parameters::AllParameters parameters;
+      dflo_params engine_params;
+      PrimitiveMesh pm;
+      FlatMesh flat;
+      dflo_flat_mesh flat_view;
+      FeTables tab;
+      dflo_ctx *ctx = nullptr;
+      int compat;
+      double elapsed_time = 0.0, global_dt = 0.0;
+      int time_iter = 0;
+      int n_dofs () const { return flat.n_cells () * tab.D; }
+
+   private:
+      void initial_value (double x, double y, double w[4]) const;
+      int compute_time_step ();
+      int iterate_explicit (double &res_norm0, double &res_norm, bool want_norm);
+   };
+}

@@ -3,18 +3,12 @@
 #include "../expr.h"
 #include "host_error.h"
 #include "mesh.h"
+#include "mesh_handle.h"
 
 #include <cstring>
 #include <string>
 #include <vector>
 
-struct dflo_mesh
-{
-   dflo::PrimitiveMesh pm;
-   dflo::FlatMesh flat;
-   dflo_flat_mesh view;
-   bool flattened = false;
-};
 
 namespace dflo
 {
