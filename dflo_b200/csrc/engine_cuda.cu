@@ -7,7 +7,8 @@
 #include "abi_impl.h"
 
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h> // types only: the library is bound at run time, see NcclApi
 
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +16,63 @@
 
 namespace
 {
+   // NCCL is bound with dlopen when the first sharded ctx is created, not at link time: a host
+   // process that already carries an NCCL (torch.distributed ships its own libnccl.so.2, newer
+   // than the system one) must keep exactly one copy, and a single-GPU host needs none at all.
+   struct NcclApi
+   {
+      void *handle = nullptr;
+      decltype (&ncclGetUniqueId) GetUniqueId = nullptr;
+      decltype (&ncclCommInitRank) CommInitRank = nullptr;
+      decltype (&ncclCommDestroy) CommDestroy = nullptr;
+      decltype (&ncclGetErrorString) GetErrorString = nullptr;
+      decltype (&ncclGroupStart) GroupStart = nullptr;
+      decltype (&ncclGroupEnd) GroupEnd = nullptr;
+      decltype (&ncclSend) Send = nullptr;
+      decltype (&ncclRecv) Recv = nullptr;
+      decltype (&ncclAllReduce) AllReduce = nullptr;
+      std::string error;
+
+      bool load ()
+      {
+         if (handle) return true;
+         const char *env = std::getenv ("DFLO_B200_NCCL_LIB");
+         if (env) handle = dlopen (env, RTLD_NOW | RTLD_GLOBAL);
+         if (!handle) handle = dlopen ("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD); // the copy the host process already has
+         if (!handle) handle = dlopen ("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+         if (!handle) handle = dlopen ("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+         if (!handle)
+         {
+            error = std::string ("cannot load libnccl.so.2: ") + dlerror ();
+            return false;
+         }
+#define DFLO_NCCL_SYM(name)                                                          \
+   name = reinterpret_cast<decltype (name)> (dlsym (handle, "nccl" #name));           \
+   if (!name)                                                                        \
+   {                                                                                 \
+      error = "libnccl lacks nccl" #name;                                            \
+      handle = nullptr;                                                              \
+      return false;                                                                  \
+   }
+         DFLO_NCCL_SYM (GetUniqueId)
+         DFLO_NCCL_SYM (CommInitRank)
+         DFLO_NCCL_SYM (CommDestroy)
+         DFLO_NCCL_SYM (GetErrorString)
+         DFLO_NCCL_SYM (GroupStart)
+         DFLO_NCCL_SYM (GroupEnd)
+         DFLO_NCCL_SYM (Send)
+         DFLO_NCCL_SYM (Recv)
+         DFLO_NCCL_SYM (AllReduce)
+#undef DFLO_NCCL_SYM
+         return true;
+      }
+   };
+   NcclApi &nccl ()
+   {
+      static NcclApi api;
+      return api;
+   }
+
    template <class K>
    __global__ void __launch_bounds__ (K::THREADS) phase_kernel (const typename K::Args a)
    {
@@ -93,12 +151,17 @@ namespace
                err = "sharded context needs an NCCL unique id";
                return DFLO_E_INVALID;
             }
+            if (!nccl ().load ())
+            {
+               err = nccl ().error;
+               return DFLO_E_NCCL;
+            }
             ncclUniqueId id;
             std::memcpy (&id, nccl_id, sizeof (id));
-            const ncclResult_t rc = ncclCommInitRank (&comm, world, id, rank);
+            const ncclResult_t rc = nccl ().CommInitRank (&comm, world, id, rank);
             if (rc != ncclSuccess)
             {
-               err = std::string ("ncclCommInitRank: ") + ncclGetErrorString (rc);
+               err = std::string ("ncclCommInitRank: ") + nccl ().GetErrorString (rc);
                return DFLO_E_NCCL;
             }
          }
@@ -107,7 +170,7 @@ namespace
 
       void close ()
       {
-         if (comm) ncclCommDestroy (comm);
+         if (comm) nccl ().CommDestroy (comm);
          comm = nullptr;
          if (ev0) cudaEventDestroy (ev0);
          if (ev1) cudaEventDestroy (ev1);
@@ -150,7 +213,7 @@ namespace
          }
          if (first_nccl_error != ncclSuccess)
          {
-            err = std::string ("NCCL: ") + ncclGetErrorString (first_nccl_error);
+            err = std::string ("NCCL: ") + nccl ().GetErrorString (first_nccl_error);
             return DFLO_E_NCCL;
          }
          return DFLO_OK;
@@ -228,28 +291,28 @@ namespace
       // ---- NCCL: halo as one group of send/recv pairs, dt/residual as tiny all-reduces ----
       void halo_begin ()
       {
-         if (comm) note (ncclGroupStart ());
+         if (comm) note (nccl ().GroupStart ());
       }
       void halo_send (int peer, const double *buf, size_t count)
       {
-         if (comm) note (ncclSend (buf, count, ncclDouble, peer, comm, stream));
+         if (comm) note (nccl ().Send (buf, count, ncclDouble, peer, comm, stream));
       }
       void halo_recv (int peer, double *buf, size_t count)
       {
-         if (comm) note (ncclRecv (buf, count, ncclDouble, peer, comm, stream));
+         if (comm) note (nccl ().Recv (buf, count, ncclDouble, peer, comm, stream));
       }
       void halo_end ()
       {
-         if (comm) note (ncclGroupEnd ());
+         if (comm) note (nccl ().GroupEnd ());
       }
       void halo_wait () {}
       void allreduce_min_dt (double *p)
       {
-         if (comm) note (ncclAllReduce (p, p, 1, ncclDouble, ncclMin, comm, stream));
+         if (comm) note (nccl ().AllReduce (p, p, 1, ncclDouble, ncclMin, comm, stream));
       }
       void allreduce_sum (double *p, int n)
       {
-         if (comm) note (ncclAllReduce (p, p, n, ncclDouble, ncclSum, comm, stream));
+         if (comm) note (nccl ().AllReduce (p, p, n, ncclDouble, ncclSum, comm, stream));
       }
    };
 }
@@ -260,7 +323,7 @@ extern "C" int dflo_b200_nccl_unique_id (void *out128)
 {
    if (!out128) return DFLO_E_INVALID;
    ncclUniqueId id;
-   if (ncclGetUniqueId (&id) != ncclSuccess) return DFLO_E_NCCL;
+   if (!nccl ().load () || nccl ().GetUniqueId (&id) != ncclSuccess) return DFLO_E_NCCL;
    static_assert (sizeof (id) == 128, "ncclUniqueId is 128 bytes");
    std::memcpy (out128, &id, sizeof (id));
    return DFLO_OK;

@@ -1,0 +1,187 @@
+"""CPU tier: the product's kernel phase code and engine orchestration (dflo_b200/csrc/kernels.cuh,
+engine_core.h, partition.h), compiled for the host by tests/emu and run thread by thread, against
+the CPU oracle.  Same cases and tolerances as the GPU tier (tests/test_gpu_parity.py); this tier
+exists so index arithmetic, buffer rotation, limiter logic and halo lists are proven before GPU
+time is spent.  It never stands in for the CUDA library: the GPU tier calls libdflo_b200.so only."""
+import numpy as np
+import pytest
+
+from cases import ALL_FLUXES, BASELINE_SMALL, BASES, TOL_RHS, TOL_STEP_SHOCK, TOL_STEP_SMOOTH
+from helpers import (DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, Case, ic_dmr, ic_pulse, ic_smooth, ic_sod, ic_step, ic_vortex)
+
+
+def _rhs_ok(c):
+    r_o, r_e = c.rhs_pair()
+    assert np.abs(r_o - r_e).max() <= TOL_RHS * max(1.0, np.abs(r_o).max()) * np.sqrt(c.oracle.D)
+    return r_o
+
+
+@pytest.mark.parametrize("flux", ALL_FLUXES)
+@pytest.mark.parametrize("basis,k", BASES)
+def test_rhs_and_step_periodic(basis, k, flux):
+    c = Case(("isentropic_vortex", [6]), PERIODIC_BOX, ic_vortex, basis=basis, degree=k, flux=flux, cfl=0.5)
+    _rhs_ok(c)
+    _, dt_o, dt_e = c.step()
+    assert abs(dt_o - dt_e) <= 1e-12 * dt_o
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+@pytest.mark.parametrize("compat", ["src", "mpi"])
+@pytest.mark.parametrize("basis,k,flux", [("Qk", 2, "lxf"), ("Pk", 2, "lxf"), ("Qk", 1, "roe")])
+def test_all_boundary_kinds_multiblock_gravity(basis, k, flux, compat):
+    """inflow / slip / pressure / farfield on the 3-block L-shaped forward-step mesh (non-lexicographic
+    cell order), gravity source on; LxF exercises the src-vs-src_mpi boundary-average fork."""
+    bc = {1: "inflow", 2: "slip", 3: "pressure", 0: "farfield"}
+    c = Case(("forward_step", [0.2]), bc, ic_smooth, basis=basis, degree=k, flux=flux, cfl=0.5, compat=compat, gravity=0.7)
+    c.set_boundary(values=(0.5, 0.1, 1.2, 3.0), wiggle=0.1)
+    _rhs_ok(c)
+    c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+@pytest.mark.parametrize("basis,k", [("Pk", 1), ("Pk", 2), ("Qk", 1), ("Qk", 2), ("Qk", 3)])
+def test_sod_tvb_positivity(basis, k):
+    c = Case(("sod_tube", [20, 3]), SOD_BC, ic_sod, basis=basis, degree=k, flux="hllc", limiter="TVB", char_lim=True,
+             pos_lim=True, M=0.0, beta=2.0, cfl=0.5)
+    c.set_boundary(values=(0.0, 0.0, 1.0, 2.5))
+    c.limit_initial()
+    flips = sum(c.step()[0] for _ in range(2))
+    assert c.rel_err() <= TOL_STEP_SHOCK and flips == 0
+    assert np.count_nonzero(c.oracle.limited_flags()) > 0
+    c.close()
+
+
+@pytest.mark.parametrize("basis,k", [("Pk", 2), ("Qk", 2)])
+def test_positivity_only(basis, k):
+    c = Case(("sod_tube", [20, 4]), SOD_BC, ic_pulse, basis=basis, degree=k, flux="lxf", pos_lim=True, cfl=0.15)
+    c.set_boundary(values=(0.0, 0.0, 0.05, 0.05))
+    flips = sum(c.step()[0] for _ in range(4))
+    assert c.rel_err() <= TOL_STEP_SHOCK and flips == 0
+    c.close()
+
+
+@pytest.mark.parametrize("char_lim", [False, True])
+def test_tvb_component_vs_characteristic_and_pk_angular_momentum(char_lim):
+    c = Case(("sod_tube", [16, 3]), SOD_BC, ic_sod, basis="Pk", degree=2, flux="roe", limiter="TVB", char_lim=char_lim,
+             conserve_angular_momentum=True, M=0.0, beta=1.5, cfl=0.4)
+    c.set_boundary(values=(0.0, 0.0, 1.0, 2.5))
+    c.limit_initial()
+    flips = sum(c.step()[0] for _ in range(2))
+    assert c.rel_err() <= TOL_STEP_SHOCK and flips == 0
+    c.close()
+
+
+@pytest.mark.parametrize("name,mesh,bc,ic,prm,nsteps", BASELINE_SMALL, ids=[b[0] for b in BASELINE_SMALL])
+def test_baseline_configs_small(name, mesh, bc, ic, prm, nsteps):
+    """The five BASELINE.json configurations at sizes the emulation finishes in seconds."""
+    small = {"cfg1": ("isentropic_vortex", [8]), "cfg2": ("isentropic_vortex", [5]), "cfg3": ("sod_tube", [24, 3]),
+             "cfg4": ("double_mach", [6]), "cfg5": ("forward_step", [0.2])}[name[:4]]
+    c = Case(small, bc, ic, **prm)
+    if "dmr" in name:
+        c.set_boundary(values=(57.1576766498, -33.0, 8.0, 563.5))
+    elif "step" in name:
+        c.set_boundary(values=(4.2, 0.0, 1.4, 8.8))
+    elif "sod" in name:
+        c.set_boundary(values=(0.0, 0.0, 1.0, 2.5))
+    shocked = prm.get("limiter", "none") != "none"
+    if shocked:
+        c.limit_initial()
+    _rhs_ok(c)
+    flips = sum(c.step()[0] for _ in range(2))
+    assert c.rel_err() <= (TOL_STEP_SHOCK if shocked else TOL_STEP_SMOOTH)
+    if "kfvs" not in name:
+        assert flips == 0
+    c.close()
+
+
+# ---- invariants of the path: hold for the oracle AND the engine ----------------
+@pytest.mark.parametrize("basis,k,flux", [("Qk", 2, "roe"), ("Pk", 2, "hllc"), ("Qk", 1, "lxf"), ("Qk", 3, "kfvs")])
+def test_free_stream_preservation(basis, k, flux):
+    """uniform state, periodic box: rhs == 0 to round-off on both sides"""
+    ic = lambda x, y: np.stack([0.3 + 0 * x, -0.2 + 0 * x, 1.1 + 0 * x, 2.7 + 0 * x], axis=-1)
+    c = Case(("isentropic_vortex", [5]), PERIODIC_BOX, ic, basis=basis, degree=k, flux=flux)
+    r_o, r_e = c.rhs_pair()
+    # KFVS: the A&S erf makes H(W,W,n) != F(W).n at 1e-7, identically on every face, so the
+    # volume and surface terms do not cancel pointwise -- but they do in the cell integral
+    tol = 1e-6 if flux == "kfvs" else 1e-12
+    assert np.abs(r_o).max() < tol and np.abs(r_e).max() < tol
+    c.close()
+
+
+@pytest.mark.parametrize("basis,k", [("Qk", 2), ("Pk", 2)])
+def test_conservation_periodic(basis, k):
+    """sum over cells of the rhs tested against phi = 1 vanishes on a periodic mesh: every interior
+    flux enters twice with opposite sign (bit-identical evaluations on both sides)."""
+    c = Case(("isentropic_vortex", [6]), PERIODIC_BOX, ic_vortex, basis=basis, degree=k, flux="roe")
+    r_o, r_e = c.rhs_pair()
+    D, ns = c.oracle.D, c.oracle.D // 4
+    for r in (r_o, r_e):
+        R = r.reshape(-1, 4, ns)
+        if basis == "Qk":
+            tot = R.sum(axis=(0, 2))           # sum_i rhs_i = rhs tested against sum_i phi_i = 1
+        else:
+            tot = R[:, :, 0].sum(axis=0)       # phi_0 = 1 on the unit cell
+        assert np.abs(tot).max() < 1e-12 * max(1.0, np.abs(r).max())
+    c.close()
+
+
+def test_limiter_preserves_cell_means_and_flags_match():
+    c = Case(("sod_tube", [20, 3]), SOD_BC, ic_sod, basis="Qk", degree=2, flux="hllc", limiter="TVB", char_lim=True,
+             pos_lim=True, M=0.0, beta=2.0, cfl=0.5)
+    c.set_boundary(values=(0.0, 0.0, 1.0, 2.5))
+    before = c.engine.cell_average().copy()
+    c.limit_initial()
+    u = c.solution().reshape(-1, 4, 9)
+    gx, gw = c.oracle.tables()
+    w2 = np.outer(gw, gw).reshape(-1)
+    means = (u * w2).sum(axis=2)
+    assert np.abs(means - before).max() < 1e-13
+    c.close()
+
+
+def test_tvb_large_M_leaves_smooth_data_untouched():
+    c = Case(("isentropic_vortex", [6]), PERIODIC_BOX, ic_vortex, basis="Qk", degree=2, flux="roe", limiter="TVB",
+             char_lim=True, M=1.0e6, beta=1.0)
+    u0 = c.solution().copy()
+    c.limit_initial()
+    assert np.array_equal(u0, c.solution())
+    assert np.count_nonzero(c.engine.limited_flags()) == 0
+    c.close()
+
+
+# ---- sharded engine: N in-process ranks with an emulated halo exchange ------------------------
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", ["vortex_Q2_roe", "sod_P2_tvb_pos", "step_Q1_tvb"])
+def test_sharded_matches_single(case, world):
+    if case == "vortex_Q2_roe":
+        args = (("isentropic_vortex", [6]), PERIODIC_BOX, ic_vortex)
+        prm = dict(basis="Qk", degree=2, flux="roe", cfl=0.5)
+        bval = None
+    elif case == "sod_P2_tvb_pos":
+        args = (("sod_tube", [18, 3]), SOD_BC, ic_sod)
+        prm = dict(basis="Pk", degree=2, flux="hllc", limiter="TVB", char_lim=True, pos_lim=True, M=0.0, beta=2.0, cfl=0.5)
+        bval = (0.0, 0.0, 1.0, 2.5)
+    else:
+        args = (("forward_step", [0.2]), STEP_BC, ic_step)
+        prm = dict(basis="Qk", degree=1, flux="lxf", limiter="TVB", char_lim=True, M=0.0, beta=2.0, cfl=0.5)
+        bval = (4.2, 0.0, 1.4, 8.8)
+    one = Case(*args, **prm)
+    many = Case(*args, world=world, **prm)
+    for c in (one, many):
+        if bval:
+            c.set_boundary(values=bval)
+        if "limiter" in prm:
+            c.limit_initial()
+    r1 = one.rhs_pair()[1]
+    rn = many.rhs_pair()[1]
+    assert np.array_equal(r1, rn)
+    for _ in range(2):
+        one.step()
+        many.step()
+    # sharding must not change a single bit: same kernels, same inputs, ghost cells updated redundantly
+    assert np.array_equal(one.solution(), many.solution())
+    assert many.rel_err() <= TOL_STEP_SHOCK
+    one.close()
+    many.close()

@@ -1,0 +1,335 @@
+"""CPU tier: host front end (input.prm parser, expression VM, mesh generators / gmsh reader,
+flattening, partitioner) and the C-ABI surface of libdflo_b200.so.  No GPU compute calls."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dflo_b200 import abi
+from helpers import PERIODIC_BOX, SOD_BC, STEP_BC, emu_lib
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRM_DIR = os.path.join(ROOT, "tests", "golden", "prm")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return abi.load_library()
+
+
+def _claw_api(L):
+    L.dflo_claw_create.restype = ctypes.c_void_p
+    L.dflo_claw_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    L.dflo_claw_destroy.argtypes = [ctypes.c_void_p]
+    L.dflo_claw_params.restype = ctypes.POINTER(abi.Params)
+    L.dflo_claw_params.argtypes = [ctypes.c_void_p]
+    L.dflo_claw_periodic_pairs.restype = ctypes.POINTER(ctypes.c_int)
+    L.dflo_claw_periodic_pairs.argtypes = [ctypes.c_void_p]
+    L.dflo_claw_n_dofs.argtypes = [ctypes.c_void_p]
+    L.dflo_claw_final_time.restype = ctypes.c_double
+    L.dflo_claw_final_time.argtypes = [ctypes.c_void_p]
+    L.dflo_claw_boundary_expression.restype = ctypes.c_char_p
+    L.dflo_claw_boundary_expression.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    L.dflo_claw_initial_condition.argtypes = [ctypes.c_void_p, abi.c_double_p, ctypes.c_size_t]
+    L.dflo_claw_setup.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.dflo_claw_mesh.restype = ctypes.c_void_p
+    L.dflo_claw_mesh.argtypes = [ctypes.c_void_p]
+    return L
+
+
+# ---------------------------------------------------------------------------------------------
+# C-ABI surface
+# ---------------------------------------------------------------------------------------------
+def _declared_symbols(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dflo_(?:b200|mesh|expr|claw|host)_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.mark.parametrize("header", ["dflo_b200.h", "dflo_host.h"])
+def test_library_exports_every_declared_symbol(lib, header):
+    names = _declared_symbols(header)
+    assert len(names) >= (25 if header == "dflo_b200.h" else 20)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_abi_version_and_strerror(lib):
+    lib.dflo_b200_abi_version.restype = ctypes.c_int
+    assert lib.dflo_b200_abi_version() == 1
+    assert lib.dflo_b200_strerror(0) == b"ok"
+    assert b"Negative states" in lib.dflo_b200_strerror(abi.E_NEGATIVE_STATE)       # positivity.cc:33-37
+    assert b"positivity limiter" in lib.dflo_b200_strerror(abi.E_POSLIM_ROOT)       # positivity.cc:160-169
+
+
+def test_params_struct_layout_matches_header():
+    """ctypes mirror == the C struct of include/dflo_b200.h (checked against a compiled sizeof)."""
+    import subprocess
+    import tempfile
+    src = '#include "dflo_b200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu\\n",' \
+          'sizeof(dflo_params),offsetof(dflo_params,M),offsetof(dflo_params,bc_kind),sizeof(dflo_flat_mesh));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(x) for x in out] == [ctypes.sizeof(abi.Params), abi.Params.M.offset, abi.Params.bc_kind.offset,
+                                     ctypes.sizeof(abi.FlatMesh)]
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    """On a box with no CUDA device the product refuses to run (DFLO_E_NO_DEVICE); with a device
+    this test only checks that creation works and the kernels are counted."""
+    import torch
+    params, pair = abi.make_params(bc=PERIODIC_BOX, basis="Qk", degree=1)
+    mesh = abi.Mesh("isentropic_vortex", [4], lib=lib)
+    flat = mesh.flatten(params, pair)
+    if torch.cuda.is_available():
+        e = abi.Engine(flat, params)
+        e.close()
+    else:
+        with pytest.raises(abi.DfloError) as ei:
+            abi.Engine(flat, params)
+        assert ei.value.code == abi.E_NO_DEVICE
+        assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under dflo_b200/ may import, include or link it."""
+    bad = []
+    for path in glob.glob(os.path.join(ROOT, "dflo_b200", "**", "*"), recursive=True):
+        if os.path.isdir(path) or path.endswith((".so", ".o")) or "/_obj/" in path or os.path.basename(path) == "dflo_b200":
+            continue
+        try:
+            text = open(path, errors="ignore").read()
+        except Exception:
+            continue
+        if re.search(r"(from|import)\s+oracle|oracle/|liboracle|phys_restated|dflo_oracle", text):
+            bad.append(path)
+    assert not bad, bad
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", abi.LIB_PATH], capture_output=True, text=True).stdout
+    # cudart is linked statically; NCCL is bound with dlopen only when a sharded ctx is created
+    assert "oracle" not in needed and "nccl" not in needed
+
+
+# ---------------------------------------------------------------------------------------------
+# input.prm
+# ---------------------------------------------------------------------------------------------
+EXPECT = {
+    "cfg1": dict(basis=0, degree=1, flux=abi.FLUX["lxf"], limiter=0, pos=0, cfl=0.9, n_periodic=4),
+    "cfg2": dict(basis=0, degree=3, flux=abi.FLUX["roe"], limiter=0, pos=0, cfl=0.9, n_periodic=4),
+    "cfg3": dict(basis=1, degree=2, flux=abi.FLUX["hllc"], limiter=1, pos=1, cfl=0.9, n_periodic=0, M=0.0, beta=2.0),
+    "cfg4": dict(basis=0, degree=2, flux=abi.FLUX["hllc"], limiter=1, pos=0, cfl=0.9, n_periodic=0, M=100.0, beta=1.0),
+    "cfg5": dict(basis=0, degree=3, flux=abi.FLUX["kfvs"], limiter=1, pos=1, cfl=0.5, n_periodic=0, M=0.0, beta=2.0),
+}
+MESH_FOR = {"cfg1": "isentropic_vortex 8", "cfg2": "isentropic_vortex 8", "cfg3": "sod_tube 20 2", "cfg4": "double_mach 4",
+            "cfg5": "forward_step 0.2"}
+
+
+@pytest.mark.parametrize("prm", sorted(f for f in os.listdir(PRM_DIR) if f.endswith(".prm")))
+def test_prm_baseline_fixtures(lib, prm):
+    L = _claw_api(lib)
+    key = prm[:4]
+    h = L.dflo_claw_create(os.path.join(PRM_DIR, prm).encode(), MESH_FOR[key].encode(), None, abi.COMPAT["mpi"])
+    assert h, L.dflo_host_last_error()
+    p = L.dflo_claw_params(h).contents
+    e = EXPECT[key]
+    assert (p.basis, p.degree, p.flux_type, p.limiter_type, p.pos_lim) == (e["basis"], e["degree"], e["flux"], e["limiter"], e["pos"])
+    assert p.cfl == e["cfl"]
+    if "M" in e:
+        assert (p.M, p.beta) == (e["M"], e["beta"]) and p.char_lim == 1
+    pairs = [L.dflo_claw_periodic_pairs(h)[i] for i in range(10)]
+    assert sum(1 for x in pairs if x >= 0) == e["n_periodic"]
+    if key == "cfg4":
+        assert p.bc_kind[3] == abi.BC["inflow"] and p.bc_kind[1] == abi.BC["slip"]
+        ex = L.dflo_claw_boundary_expression(h, 3, 2).decode()
+        x = np.array([0.1, 1.0, 2.0])
+        got = abi.expr_eval(ex, x, 0 * x + 1.0, t=0.01, lib=lib)
+        xs = 1.0 / 6.0 + (1 + 20 * 0.01) / np.sqrt(3.0)
+        assert np.array_equal(got, np.where(x < xs, 8.0, 1.4))
+    # host-side initial condition in the reference DoF layout
+    n = L.dflo_claw_n_dofs(h)
+    u = np.zeros(n)
+    assert L.dflo_claw_initial_condition(h, u.ctypes.data_as(abi.c_double_p), n) == 0
+    assert np.all(np.isfinite(u))
+    D = 4 * ((e["degree"] + 1) ** 2 if e["basis"] == 0 else (e["degree"] + 1) * (e["degree"] + 2) // 2)
+    rho = u.reshape(-1, 4, D // 4)[:, 2, :]
+    assert rho[:, 0].min() > 0.0          # Qk: nodal densities; Pk: mode 0 = mean density
+    L.dflo_claw_destroy(h)
+
+
+def test_prm_rejects_undeclared_keys_and_bad_combinations(lib, tmp_path):
+    L = _claw_api(lib)
+    base = open(os.path.join(PRM_DIR, "cfg3_sod_P2_hllc_tvb_pos.prm")).read()
+    cases = {
+        "undeclared": base + "\nset no such key = 1\n",                                     # ParameterHandler: error
+        "tvb_needs_cartesian": base.replace("set mapping   = cartesian", "set mapping   = q1"),   # parameters.cc:536-541
+        "bad_flux": base.replace("set flux = hllc", "set flux = hllx"),
+    }
+    for name, text in cases.items():
+        p = tmp_path / (name + ".prm")
+        p.write_text(text)
+        h = L.dflo_claw_create(str(p).encode(), b"sod_tube 10 2", None, 0)
+        assert not h, name
+        assert L.dflo_host_last_error()
+    # src/ does not know periodic boundaries (SURVEY 8a forks): compat=src rejects them, compat=mpi accepts
+    vort = os.path.join(PRM_DIR, "cfg1_isentropic_vortex_Q1_lxf.prm").encode()
+    h = L.dflo_claw_create(vort, b"isentropic_vortex 4", None, abi.COMPAT["mpi"])
+    assert h
+    L.dflo_claw_destroy(h)
+
+
+def test_prm_parses_the_reference_examples(lib):
+    """Every explicit-path example deck the reference ships parses (when /root/reference is here)."""
+    L = _claw_api(lib)
+    decks = {"isentropic_vortex": "isentropic_vortex 4", "sod_shock_tube": "sod_tube 10 2",
+             "double_mach_reflection": "double_mach 4", "forward_step": "forward_step 0.2"}
+    if not os.path.isdir("/root/reference/examples"):
+        pytest.skip("reference tree not present on this box")
+    for ex, mesh in decks.items():
+        h = L.dflo_claw_create(("/root/reference/examples/%s/input.prm" % ex).encode(), mesh.encode(), None, abi.COMPAT["mpi"])
+        assert h, (ex, L.dflo_host_last_error())
+        L.dflo_claw_destroy(h)
+
+
+# ---------------------------------------------------------------------------------------------
+# expressions (deal.II FunctionParser / muparser subset)
+# ---------------------------------------------------------------------------------------------
+def test_expression_vm(lib):
+    x = np.linspace(-2.0, 3.0, 41)
+    y = np.linspace(0.5, 1.5, 41)
+    t = 0.3
+    pi = np.pi
+    cases = {
+        "1.0 + 2*x - y/4": 1.0 + 2 * x - y / 4,
+        "x^2 + y^3": x ** 2 + y ** 3,
+        "-x^2": -(x ** 2),
+        "2^3^2": 512.0 + 0 * x,
+        "sin(_pi*x)*cos(y) + exp(-t)": np.sin(pi * x) * np.cos(y) + np.exp(-t),
+        "sqrt(abs(x)) * (x >= 0) + (x < 0)*3": np.sqrt(np.abs(x)) * (x >= 0) + (x < 0) * 3,
+        "(x<=0.5) + 0.125*(x>0.5)": (x <= 0.5) + 0.125 * (x > 0.5),
+        "57.1576766498*(x<1.0/6.0+(1+20*t)/sqrt(3)) + 0.0": 57.1576766498 * (x < 1.0 / 6.0 + (1 + 20 * t) / np.sqrt(3.0)),
+        "1e-3*x + 2.5E2": 1e-3 * x + 250.0,
+        "(x > 0) && (y < 1) || (x == -2)": ((x > 0) & (y < 1)) | (x == -2),
+        "log(y) + tan(y/2)": np.log(y) + np.tan(y / 2),
+    }
+    for ex, want in cases.items():
+        got = abi.expr_eval(ex, x, y, t, lib=lib)
+        assert np.allclose(got, np.asarray(want, dtype=float), rtol=1e-15, atol=1e-15), ex
+    for bad in ["1 +", "foo(x)", "(x", "x y", ""]:
+        with pytest.raises(abi.DfloError):
+            abi.expr_eval(bad, x, y, t, lib=lib)
+
+
+# ---------------------------------------------------------------------------------------------
+# meshes, flattening, partitioning
+# ---------------------------------------------------------------------------------------------
+MESHES = [("isentropic_vortex", [6], PERIODIC_BOX), ("sod_tube", [12, 3], SOD_BC), ("double_mach", [4], {1: "slip", 3: "inflow", 4: "inflow"}),
+          ("forward_step", [0.2], STEP_BC), ("rectangle", [5, 3, 0.0, 2.0, -1.0, 1.0, 4, 2, 1, 3], PERIODIC_BOX)]
+
+
+@pytest.mark.parametrize("kind,args,bc", MESHES, ids=[m[0] for m in MESHES])
+def test_flatten_matches_oracle_topology(lib, kind, args, bc):
+    """the product's flattening (neighbour lists, boundary faces, face ownership, periodic partners)
+    against the oracle's independent derivation from the same primitive mesh"""
+    params, pair = abi.make_params(bc=bc)
+    m = abi.Mesh(kind, args, lib=lib)
+    m.flatten(params, pair)
+    fa = m.flat_arrays()
+    v, c, bl, bi = m.primitive()
+    o = O.Oracle(v, c, bl, bi, O.make_params(bc=bc))
+    assert np.array_equal(fa["neighbor"], o.neighbors())
+    oc, of, oid, _ = o.bfaces()
+    assert np.array_equal(fa["bface_cell"], oc) and np.array_equal(fa["bface_face"], of) and np.array_equal(fa["bface_id"], oid)
+    nb, fl = fa["neighbor"], fa["face_flags"]
+    n = len(nb)
+    for cell in range(n):
+        for f in range(4):
+            j = nb[cell, f]
+            if j < 0:
+                assert fl[cell, f] == 0
+                continue
+            assert nb[j, f ^ 1] == cell                        # symmetric
+            if fl[cell, f] & abi.FACE_PERIODIC:
+                assert fl[j, f ^ 1] & abi.FACE_PERIODIC        # both sides integrate (src_mpi 186-260)
+            else:                                              # MeshWorker: exactly one side owns the face
+                assert bool(fl[cell, f] & abi.FACE_OWNER) != bool(fl[j, f ^ 1] & abi.FACE_OWNER)
+                assert bool(fl[cell, f] & abi.FACE_OWNER) == (cell < j)
+    assert np.all(fa["size"] > 0)
+
+
+def test_generators_reproduce_the_geo_files(lib):
+    """cell counts / extents / boundary ids of the transfinite .geo files"""
+    m = abi.Mesh("isentropic_vortex", [32], lib=lib)
+    v, c, bl, bi = m.primitive()
+    assert len(c) == 1024 and v.min() == -5.0 and v.max() == 5.0 and sorted(set(bi)) == [1, 2, 3, 4]
+    m = abi.Mesh("sod_tube", [100, 10], lib=lib)
+    v, c, bl, bi = m.primitive()
+    assert len(c) == 1000 and v[:, 0].max() == 1.0 and abs(v[:, 1].max() - 0.1) < 1e-15 and sorted(set(bi)) == [0, 1, 2]
+    m = abi.Mesh("double_mach", [16], lib=lib)
+    v, c, bl, bi = m.primitive()
+    # grid.geo: n1 = ceil(x0/dy) = 3, n2 = ceil((4-x0)/dy) = 62 columns of squares around x0 = 1/6
+    assert len(c) == 65 * 16 and abs(v[:, 0].max() - (1 / 6 + 62 / 16)) < 1e-14 and v[:, 1].max() == 1.0
+    assert abs(v[:, 0].min() - (1 / 6 - 3 / 16)) < 1e-14 and sorted(set(bi)) == [0, 1, 2, 3, 4]
+    m = abi.Mesh("forward_step", [0.1], lib=lib)
+    v, c, bl, bi = m.primitive()
+    # 3 blocks: [0,0.6]x[0,0.2], [0,0.6]x[0.2,1], [0.6,3]x[0.2,1]
+    assert len(c) == 6 * 2 + 6 * 8 + 24 * 8
+    assert v[:, 0].max() == 3.0 and v[:, 1].max() == 1.0 and sorted(set(bi)) == [1, 2, 3]
+
+
+def test_gmsh_v2_round_trip(lib, tmp_path):
+    m = abi.Mesh("forward_step", [0.2], lib=lib)
+    path = str(tmp_path / "step.msh")
+    m.write_gmsh(path)
+    text = open(path).read()
+    assert text.startswith("$MeshFormat\n2.") and "$Elements" in text
+    r = abi.Mesh(gmsh_path=path, lib=lib)
+    a, b = m.primitive(), r.primitive()
+    assert np.array_equal(a[0], b[0])
+    # same cells up to the reader's CCW -> lexicographic conversion; same boundary ids
+    assert np.array_equal(np.sort(a[1], axis=1), np.sort(b[1], axis=1))
+    assert np.array_equal(np.sort(a[2], axis=1), np.sort(b[2], axis=1)) and np.array_equal(a[3], b[3])
+    params, pair = abi.make_params(bc=STEP_BC)
+    m.flatten(params, pair)
+    r.flatten(params, pair)
+    fa, fb = m.flat_arrays(), r.flat_arrays()
+    for k in fa:
+        assert np.array_equal(fa[k], fb[k]), k
+    with pytest.raises(abi.DfloError):
+        abi.Mesh(gmsh_path=str(tmp_path / "missing.msh"), lib=lib)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("layers_case", ["none", "tvb"])
+def test_partition_ranges_and_halo_symmetry(world, layers_case):
+    """contiguous cell-id ranges cover the mesh; what rank a sends to b is what b expects from a"""
+    L = emu_lib()
+    prm = dict(basis="Qk", degree=1, flux="lxf")
+    if layers_case == "tvb":
+        prm.update(limiter="TVB", M=0.0, beta=1.0)
+    params, pair = abi.make_params(bc=STEP_BC, **prm)
+    m = abi.Mesh("forward_step", [0.1], lib=L)
+    flat = m.flatten(params, pair)
+    engines = [abi.Engine(flat, params, rank=r, world=world, nccl_id=b"\0" * 128, lib=L, prefix="dflo_emu_") for r in range(world)]
+    ranges = [e.cell_range() for e in engines]
+    assert ranges[0][0] == 0 and ranges[-1][1] == m.n_cells
+    assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+    sizes = [b - a for a, b in ranges]
+    assert max(sizes) - min(sizes) <= 1
+    u = np.arange(m.n_cells * engines[0].D, dtype=np.float64)
+    for e in engines:
+        e.set_solution(u)          # triggers the first halo exchange
+    for e in engines:
+        for i in range(L.dflo_emu_n_peers(e.h)):
+            p = L.dflo_emu_peer_rank(e.h, i)
+            assert L.dflo_emu_halo_send_count(e.h, p) == L.dflo_emu_halo_recv_count(engines[p].h, e.rank)
+            assert L.dflo_emu_halo_send_count(e.h, p) > 0
+        # ghost layers: 1 without limiter, 2 with TVB (SURVEY 8e option 2)
+        assert L.dflo_emu_n_local(e.h) > e.cell_range()[1] - e.cell_range()[0]
+    for e in engines:
+        e.close()
