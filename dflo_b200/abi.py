@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdflo_b200.so")
+# DFLO_B200_LIB: developer override to compare differently tuned builds of the same library
+LIB_PATH = os.environ.get("DFLO_B200_LIB") or os.path.join(_HERE, "csrc", "libdflo_b200.so")
 
 MAX_BOUNDARIES = 10
 FLUX = {"lxf": 0, "sw": 1, "kfvs": 2, "roe": 3, "hllc": 4}

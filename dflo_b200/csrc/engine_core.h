@@ -121,6 +121,7 @@ namespace dflo
    {
       typedef DtArgs Args;
       static constexpr int THREADS = 256;
+      static constexpr int MIN_BLOCKS = 1;
       static constexpr int NPHASE = 3;
       static constexpr int SMEM_DOUBLES = THREADS;
       static int grid (int n) { return (n + THREADS - 1) / THREADS; }
@@ -189,6 +190,7 @@ namespace dflo
    {
       typedef SumSqArgs Args;
       static constexpr int THREADS = 256;
+      static constexpr int MIN_BLOCKS = 1;
       static constexpr int NPHASE = 3;
       static constexpr int SMEM_DOUBLES = THREADS;
       static int grid (int64_t n) { int64_t g = (n + THREADS * 8 - 1) / (THREADS * 8); return (int) (g < 1 ? 1 : g > 1184 ? 1184 : g); }
@@ -247,36 +249,36 @@ namespace dflo
    template <class BK, int BASIS, int N1>
    struct StageDispatch
    {
-      static void run (BK &bk, int flux, const StageArgs &a)
+      static void run (BK &bk, int flux, int n_tiles, const StageArgs &a)
       {
          switch (flux)
          {
-            case FLUX_LXF: bk.template launch<StageKernel<BASIS, N1, FLUX_LXF>> (StageKernel<BASIS, N1, FLUX_LXF>::grid (a.n_compute), a); break;
-            case FLUX_SW: bk.template launch<StageKernel<BASIS, N1, FLUX_SW>> (StageKernel<BASIS, N1, FLUX_SW>::grid (a.n_compute), a); break;
-            case FLUX_KFVS: bk.template launch<StageKernel<BASIS, N1, FLUX_KFVS>> (StageKernel<BASIS, N1, FLUX_KFVS>::grid (a.n_compute), a); break;
-            case FLUX_ROE: bk.template launch<StageKernel<BASIS, N1, FLUX_ROE>> (StageKernel<BASIS, N1, FLUX_ROE>::grid (a.n_compute), a); break;
-            default: bk.template launch<StageKernel<BASIS, N1, FLUX_HLLC>> (StageKernel<BASIS, N1, FLUX_HLLC>::grid (a.n_compute), a); break;
+            case FLUX_LXF: bk.template launch<StageKernel<BASIS, N1, FLUX_LXF>> (n_tiles, a); break;
+            case FLUX_SW: bk.template launch<StageKernel<BASIS, N1, FLUX_SW>> (n_tiles, a); break;
+            case FLUX_KFVS: bk.template launch<StageKernel<BASIS, N1, FLUX_KFVS>> (n_tiles, a); break;
+            case FLUX_ROE: bk.template launch<StageKernel<BASIS, N1, FLUX_ROE>> (n_tiles, a); break;
+            default: bk.template launch<StageKernel<BASIS, N1, FLUX_HLLC>> (n_tiles, a); break;
          }
       }
    };
 
    template <class BK>
-   void launch_stage (BK &bk, int basis, int n1, int flux, const StageArgs &a)
+   void launch_stage (BK &bk, int basis, int n1, int flux, int n_tiles, const StageArgs &a)
    {
       if (n1 == 1) // degree 0: Q0 == P0
-         StageDispatch<BK, BASIS_QK, 1>::run (bk, flux, a);
+         StageDispatch<BK, BASIS_QK, 1>::run (bk, flux, n_tiles, a);
       else if (basis == BASIS_QK)
       {
-         if (n1 == 2) StageDispatch<BK, BASIS_QK, 2>::run (bk, flux, a);
-         else if (n1 == 3) StageDispatch<BK, BASIS_QK, 3>::run (bk, flux, a);
-         else if (n1 == 4) StageDispatch<BK, BASIS_QK, 4>::run (bk, flux, a);
-         else StageDispatch<BK, BASIS_QK, 5>::run (bk, flux, a);
+         if (n1 == 2) StageDispatch<BK, BASIS_QK, 2>::run (bk, flux, n_tiles, a);
+         else if (n1 == 3) StageDispatch<BK, BASIS_QK, 3>::run (bk, flux, n_tiles, a);
+         else if (n1 == 4) StageDispatch<BK, BASIS_QK, 4>::run (bk, flux, n_tiles, a);
+         else StageDispatch<BK, BASIS_QK, 5>::run (bk, flux, n_tiles, a);
       }
       else
       {
-         if (n1 == 2) StageDispatch<BK, BASIS_PK, 2>::run (bk, flux, a);
-         else if (n1 == 3) StageDispatch<BK, BASIS_PK, 3>::run (bk, flux, a);
-         else StageDispatch<BK, BASIS_PK, 4>::run (bk, flux, a);
+         if (n1 == 2) StageDispatch<BK, BASIS_PK, 2>::run (bk, flux, n_tiles, a);
+         else if (n1 == 3) StageDispatch<BK, BASIS_PK, 3>::run (bk, flux, n_tiles, a);
+         else StageDispatch<BK, BASIS_PK, 4>::run (bk, flux, n_tiles, a);
       }
    }
 
@@ -323,7 +325,8 @@ namespace dflo
       double *rhs = nullptr;
       double *d_time = nullptr;       // t, dt, dt accumulator, final time
       double *d_scratch = nullptr;    // [1] reductions
-      int *d_nbr = nullptr;
+      int *d_nbr = nullptr, *d_tile_start = nullptr, *d_halo_start = nullptr, *d_halo_cells = nullptr, *d_job_start = nullptr;
+      FaceJob *d_jobs = nullptr;
       unsigned char *d_fflags = nullptr;
       double *d_geom = nullptr, *d_bc_g = nullptr, *d_stage_tab = nullptr, *d_lim_tab = nullptr, *d_gw = nullptr, *d_gx = nullptr;
       int *d_bkind = nullptr, *d_bf_cell = nullptr, *d_bf_face = nullptr, *d_bf_id = nullptr, *d_l2g = nullptr, *d_flags = nullptr;
@@ -361,7 +364,7 @@ namespace dflo
          else { n_rk = 3; ark[0] = 0.0; ark[1] = 3.0 / 4.0; ark[2] = 1.0 / 3.0; }
          const int layers = tvb () ? 2 : 1;
          std::string e;
-         if (!build_local_mesh (mesh, rank, world, layers, lm, e)) return fail (DFLO_E_INVALID, e);
+         if (!build_local_mesh (mesh, rank, world, layers, tile_nx (tab.n1), tile_ny (tab.n1), lm, e)) return fail (DFLO_E_INVALID, e);
          n_global_bfaces = mesh.n_boundary_faces;
 
          const size_t nd = (size_t) lm.n_local * D ();
@@ -377,6 +380,11 @@ namespace dflo
          bk.h2d (d_time, t0, sizeof (t0));
          d_scratch = bk.template alloc<double> (4);
          d_nbr = upload (lm.nbr);
+         d_tile_start = upload (lm.tile_start);
+         d_halo_start = upload (lm.halo_start);
+         d_halo_cells = upload (pad1 (lm.halo_cells));
+         d_job_start = upload (lm.job_start);
+         d_jobs = upload_aligned_jobs ();
          d_fflags = upload (lm.fflags);
          d_geom = upload (lm.geom);
          d_l2g = upload (lm.l2g);
@@ -418,7 +426,8 @@ namespace dflo
             bk.free (AVG[i]);
          }
          void *ptrs[] = {rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
-                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_ext, d_dofmap};
+                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_ext, d_dofmap, d_tile_start, d_halo_start, d_halo_cells,
+                         d_job_start, d_jobs};
          for (void *p : ptrs) bk.free (p);
          for (int k = 0; k < 2; ++k)
          {
@@ -533,8 +542,7 @@ namespace dflo
          eval_boundary (false);
          StageArgs a = stage_args (0, MODE_RHS);
          a.out = rhs;
-         a.n_compute = lm.n_owned;
-         launch_stage (bk, tab.basis, tab.n1, prm.flux_type, a);
+         launch_stage (bk, tab.basis, tab.n1, prm.flux_type, lm.n_tiles_owned, a);
          return bk.check (error);
       }
 
@@ -650,7 +658,7 @@ namespace dflo
          {
             if (scratch) bk.zero (scratch, flush_bytes);
             bk.timer_start ();
-            launch_stage (bk, tab.basis, tab.n1, prm.flux_type, a);
+            launch_stage (bk, tab.basis, tab.n1, prm.flux_type, lm.n_tiles, a);
             bk.timer_stop ();
             total += bk.timer_ms ();
          }
@@ -685,6 +693,15 @@ namespace dflo
          return r;
       }
 
+      FaceJob *upload_aligned_jobs ()
+      {
+         static_assert (sizeof (FaceJob) == 4 * sizeof (int), "FaceJob is 4 ints");
+         const size_t n = std::max<size_t> (1, lm.jobs.size () / 4);
+         FaceJob *d = bk.template alloc<FaceJob> (n);
+         if (!lm.jobs.empty ()) bk.h2d (d, lm.jobs.data (), lm.jobs.size () * sizeof (int));
+         return d;
+      }
+
       template <class T>
       T *upload (const std::vector<T> &v)
       {
@@ -710,15 +727,17 @@ namespace dflo
          a.out = nullptr;
          a.avg = AVG[cur];
          a.avg_out = nullptr;
-         a.nbr = d_nbr;
-         a.fflags = d_fflags;
+         a.tile_start = d_tile_start;
+         a.halo_start = d_halo_start;
+         a.halo_cells = d_halo_cells;
+         a.job_start = d_job_start;
+         a.jobs = d_jobs;
          a.geom = d_geom;
          a.bc_g = d_bc_g;
          a.bkind = d_bkind;
          a.tab = d_stage_tab;
          a.time = d_time;
          a.dt_cell = nullptr;
-         a.n_compute = lm.n_compute;
          a.mode = mode;
          a.compat_mpi = prm.compat == DFLO_COMPAT_MPI;
          a.ark = ark[rk];
@@ -803,7 +822,7 @@ namespace dflo
          StageArgs a = stage_args (rk, MODE_STAGE);
          a.out = U[out];
          a.avg_out = AVG[out];
-         launch_stage (bk, tab.basis, tab.n1, prm.flux_type, a);
+         launch_stage (bk, tab.basis, tab.n1, prm.flux_type, lm.n_tiles, a);
          if (tvb () || pos ())
          {
             LimiterArgs l = limiter_args (out);

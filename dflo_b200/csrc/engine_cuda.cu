@@ -74,9 +74,9 @@ namespace
    }
 
    template <class K>
-   __global__ void __launch_bounds__ (K::THREADS) phase_kernel (const typename K::Args a)
+   __global__ void __launch_bounds__ (K::THREADS, K::MIN_BLOCKS) phase_kernel (const typename K::Args a)
    {
-      extern __shared__ double dflo_smem[];
+      extern __shared__ __align__ (16) double dflo_smem[];
 #pragma unroll
       for (int p = 0; p < K::NPHASE; ++p)
       {
@@ -222,8 +222,14 @@ namespace
       template <class K> void launch (int grid, const typename K::Args &a)
       {
          if (grid <= 0) return;
+         constexpr size_t smem = K::SMEM_DOUBLES * sizeof (double);
+         if (smem > 48 * 1024) // opt in to large dynamic shared memory once per kernel
+         {
+            static const cudaError_t rc = cudaFuncSetAttribute (phase_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            note (rc);
+         }
          ++launches;
-         phase_kernel<K><<<grid, K::THREADS, K::SMEM_DOUBLES * sizeof (double), stream>>> (a);
+         phase_kernel<K><<<grid, K::THREADS, smem, stream>>> (a);
          note (cudaPeekAtLastError ());
       }
       template <class K> void launch1d (int n, const typename K::Args &a)

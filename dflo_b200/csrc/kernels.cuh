@@ -33,13 +33,18 @@
 
 namespace dflo
 {
-   enum { FACE_OWNER = 1, FACE_PERIODIC = 2, FACE_FLIP = 4 };
+   enum { FACE_OWNER = 1, FACE_PERIODIC = 2, FACE_FLIP = 4, JOB_SHARED = 8 };
    enum { MODE_STAGE = 0, MODE_RHS = 1 };
    enum { ERR_NEGATIVE_STATE = 1, ERR_POSLIM_ROOT = 2 };
 
    constexpr int cells_per_block (int G) { return G >= 128 ? 1 : 128 / G; }
    constexpr int n_scalar (int basis, int n1) { return basis == BASIS_QK ? n1 * n1 : n1 * (n1 + 1) / 2; }
    constexpr int n_gll (int n1) { return ((n1 - 1) + 3) % 2 == 0 ? ((n1 - 1) + 3) / 2 : ((n1 - 1) + 4) / 2; }
+
+   // Tile shape of the stage kernel per degree: tx x ty cells, (k+1)^2 threads per cell, 256 threads
+   // per block (the host renumbers cells tile-major with the same numbers, partition.h).
+   constexpr int tile_nx (int n1) { return n1 == 1 ? 16 : n1 == 2 ? 8 : n1 == 3 ? 7 : n1 == 4 ? 4 : 5; }
+   constexpr int tile_ny (int n1) { return n1 == 1 ? 16 : n1 == 2 ? 8 : n1 == 3 ? 4 : n1 == 4 ? 4 : 2; }
 
    // flat table layouts (built by pack_stage_tables / pack_limiter_tables in tables_pack.h)
    constexpr int stage_table_size (int basis, int n1)
@@ -51,6 +56,16 @@ namespace dflo
       return basis == BASIS_QK ? 3 * n1 + n_gll (n1) * n1 : 2 * n_gll (n1) * n1 * n_scalar (basis, n1);
    }
 
+   // One unique face of a tile (built by build_tile_jobs, partition.h)
+   struct alignas (16) FaceJob
+   {
+      int a;       // slot of the visiting cell in the tile * 4 + its local face number
+      int nb;      // neighbour: local cell id, or -1 - local boundary face
+      int slot_b;  // where the neighbour's DoFs sit in shared memory (tile slot, or tile_cells + halo
+                   // slot), or -1: read them from global memory
+      int flags;   // FACE_* | JOB_SHARED
+   };
+
    struct StageArgs
    {
       const double *u;        // current_solution   [n_local][D]
@@ -58,20 +73,61 @@ namespace dflo
       double *out;            // MODE_STAGE: updated solution (a different buffer than u); MODE_RHS: right_hand_side
       const double *avg;      // cell_average of u   [n_local][4]
       double *avg_out;        // cell_average of the updated solution
-      const int *nbr;         // [n_local][4]
-      const unsigned char *fflags;
+      const int *tile_start;  // [n_tiles+1]
+      const int *halo_start;  // [n_tiles+1]
+      const int *halo_cells;
+      const int *job_start;   // [n_tiles+1]
+      const FaceJob *jobs;
       const double *geom;     // [n_local][4] x0, y0, hx, hy
       const double *bc_g;     // [n_bfaces][n_q_face][4]
       const int *bkind;       // [n_bfaces]
       const double *tab;      // flat stage tables
       const double *time;     // device scalars: [0] elapsed time, [1] dt
       const double *dt_cell;  // optional per-cell dt (local time stepping), else nullptr
-      int n_compute;
       int mode;
       int compat_mpi;
       double ark;
       double gravity;
    };
+
+#if defined(__CUDA_ARCH__)
+   // ---- sm_100a asynchronous bulk copies (TMA unit, 1-D): global -> shared completing on an
+   //      mbarrier, shared -> global as a bulk group ----
+   __device__ __forceinline__ unsigned smem_addr (const void *p) { return (unsigned) __cvta_generic_to_shared (p); }
+   __device__ __forceinline__ void mbar_init (void *bar, unsigned count)
+   {
+      asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr (bar)), "r"(count) : "memory");
+      asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __device__ __forceinline__ void mbar_expect_tx (void *bar, unsigned bytes)
+   {
+      asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr (bar)), "r"(bytes) : "memory");
+   }
+   __device__ __forceinline__ void mbar_wait (void *bar, unsigned parity)
+   {
+      asm volatile ("{\n"
+                    ".reg .pred p;\n"
+                    "WAIT_%=:\n"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                    "@p bra DONE_%=;\n"
+                    "bra WAIT_%=;\n"
+                    "DONE_%=:\n"
+                    "}" ::"r"(smem_addr (bar)), "r"(parity) : "memory");
+   }
+   __device__ __forceinline__ void bulk_g2s (void *dst, const void *src, unsigned bytes, void *bar)
+   {
+      asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr (dst)),
+                    "l"(src), "r"(bytes), "r"(smem_addr (bar))
+                    : "memory");
+   }
+   __device__ __forceinline__ void bulk_s2g (void *dst, const void *src, unsigned bytes)
+   {
+      asm volatile ("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr (src)), "r"(bytes) : "memory");
+      asm volatile ("cp.async.bulk.commit_group;" ::: "memory");
+   }
+   __device__ __forceinline__ void bulk_s2g_wait () { asm volatile ("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+   __device__ __forceinline__ void fence_async_smem () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
    template <int BASIS, int N1, int FLUX>
    struct StageKernel
@@ -81,18 +137,22 @@ namespace dflo
       static constexpr int G = NQ;
       static constexpr int NS = n_scalar (BASIS, N1);
       static constexpr int D = 4 * NS;
-      static constexpr int CPB = cells_per_block (G);
-      static constexpr int THREADS = CPB * G;
+      static constexpr int TC = tile_nx (N1) * tile_ny (N1);        // cells per tile
+      static constexpr int NH = 2 * (tile_nx (N1) + tile_ny (N1));  // staged halo cells per tile
+      static constexpr int THREADS = (TC * G + 31) / 32 * 32;
+#ifndef DFLO_STAGE_MIN_BLOCKS
+#define DFLO_STAGE_MIN_BLOCKS 3
+#endif
+      static constexpr int MIN_BLOCKS = DFLO_STAGE_MIN_BLOCKS; // resident blocks per SM the register budget is held to
       static constexpr int NPHASE = 4;
       static constexpr int TAB = stage_table_size (BASIS, N1);
-      // shared memory carve-up (in doubles)
-      static constexpr int O_U = TAB;
-      static constexpr int O_F = O_U + CPB * D;
-      static constexpr int O_H = O_F + CPB * 8 * NQ;
-      static constexpr int O_W = O_H + CPB * 16 * N1;
-      static constexpr int SMEM_DOUBLES = O_W + (BASIS == BASIS_PK ? CPB * 4 * NQ : 0);
-
-      static int grid (int n_compute) { return (n_compute + CPB - 1) / CPB; }
+      // shared memory carve-up (in doubles); every bulk-copy destination is 16-byte aligned
+      static constexpr int O_TAB = 2;                                // [0,2): the mbarrier
+      static constexpr int O_U = O_TAB + (TAB + 1) / 2 * 2;
+      static constexpr int O_F = O_U + (TC + NH) * D;
+      static constexpr int O_H = O_F + TC * 8 * NQ;
+      static constexpr int O_W = O_H + TC * 16 * N1;
+      static constexpr int SMEM_DOUBLES = O_W + (BASIS == BASIS_PK ? TC * 4 * NQ : 0);
 
       // table accessors ------------------------------------------------------------------------
       // Qk: dw[N1*N1] e0[N1] e1[N1] gw[N1]
@@ -109,8 +169,8 @@ namespace dflo
       static DFLO_DEV const double *t_phiface (const double *tb) { return tb + 3 * NQ * NS; }
 
       // Trace of one cell (ucell = its D DoFs, shared or global memory) at point q of its face f.
-      // The same fma chain is used for a cell's own trace and for its neighbour's, so the two
-      // cells sharing a face feed bit-identical states into the Riemann solver.
+      // The same fma chain is used for a cell's own trace and for its neighbour's, so whichever
+      // block evaluates a face feeds bit-identical states into the Riemann solver.
       static DFLO_DEV void trace (const double *tb, const double *ucell, int f, int q, double W[4])
       {
          if (BASIS == BASIS_QK)
@@ -143,9 +203,9 @@ namespace dflo
 
       static DFLO_DEV void phase (int p, const Args &A, double *sm, int tid, int bid)
       {
-         const int c0 = bid * CPB;
-         const int ncb = (A.n_compute - c0 < CPB) ? A.n_compute - c0 : CPB;
-         double *tb = sm;
+         const int c0 = A.tile_start[bid];
+         const int ncb = A.tile_start[bid + 1] - c0;
+         double *tb = sm + O_TAB;
          double *su = sm + O_U;
          double *sF = sm + O_F;
          double *sH = sm + O_H;
@@ -156,17 +216,35 @@ namespace dflo
 
          if (p == 0)
          {
-            // tables and this block's DoFs: flat, coalesced
+            // stage the tile (one contiguous run of ncb*D doubles) and its halo cells in shared
+            // memory, plus the tables
+            const int h0 = A.halo_start[bid];
+            const int nh = A.halo_start[bid + 1] - h0;
+#if defined(__CUDA_ARCH__)
+            if (tid == 0)
+            {
+               mbar_init (sm, 1);
+               mbar_expect_tx (sm, (unsigned) ((ncb + nh) * D * sizeof (double)));
+            }
+            __syncthreads ();
+            if (tid == 0) bulk_g2s (su, A.u + (size_t) c0 * D, (unsigned) (ncb * D * sizeof (double)), sm);
+            for (int h = tid - 1; h >= 0 && h < nh; h += THREADS)
+               bulk_g2s (su + (TC + h) * D, A.u + (size_t) A.halo_cells[h0 + h] * D, (unsigned) (D * sizeof (double)), sm);
             for (int i = tid; i < TAB; i += THREADS) tb[i] = A.tab[i];
+            mbar_wait (sm, 0);
+#else
             const double *src = A.u + (size_t) c0 * D;
             for (int i = tid; i < ncb * D; i += THREADS) su[i] = src[i];
+            for (int i = tid; i < nh * D; i += THREADS) su[TC * D + i] = A.u[(size_t) A.halo_cells[h0 + i / D] * D + i % D];
+            for (int i = tid; i < TAB; i += THREADS) tb[i] = A.tab[i];
+#endif
          }
          else if (p == 1)
          {
-            if (!active) return;
-            const double *uc = su + slot * D;
             // ---- volume: Cartesian fluxes at Gauss point lq (assemble_explicit.cc:57-79) ----
+            if (active)
             {
+               const double *uc = su + slot * D;
                double W[4], Fx[4], Fy[4];
                if (BASIS == BASIS_QK)
                {
@@ -195,25 +273,31 @@ namespace dflo
                   sF[(slot * 8 + 4 + c) * NQ + lq] = Fy[c];
                }
             }
-            // ---- faces: numerical flux along this cell's outward normal at the 4(k+1) face
-            //      points (assemble_explicit.cc:176-206, 303-341; periodic: src_mpi 186-260) ----
-            double Ao[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) Ao[c] = A.avg[(size_t) cell * 4 + c];
-            for (int idx = lq; idx < 4 * N1; idx += G)
+            // ---- faces: one numerical flux per UNIQUE face point of the tile, along the visiting
+            //      cell's outward normal (assemble_explicit.cc:176-206, 303-341; periodic: src_mpi
+            //      186-260); a face shared by two cells of the tile serves both ----
+            const int j0 = A.job_start[bid];
+            const int nj = (A.job_start[bid + 1] - j0) * N1;
+            for (int idx = tid; idx < nj; idx += THREADS)
             {
-               const int f = idx / N1, q = idx % N1;
+               const FaceJob job = A.jobs[j0 + idx / N1];
+               const int q = idx % N1;
+               const int sa = job.a >> 2, f = job.a & 3;
+               const int nb = job.nb, fl = job.flags;
                const double nx = (f == 0) ? -1.0 : (f == 1) ? 1.0 : 0.0;
                const double ny = (f == 2) ? -1.0 : (f == 3) ? 1.0 : 0.0;
-               double Wo[4], Wn[4], An[4], H[4];
-               trace (tb, uc, f, q, Wo);
-               const int nb = A.nbr[(size_t) cell * 4 + f];
-               const int fl = A.fflags[(size_t) cell * 4 + f];
-               bool plus = true; // this cell is the "plus" side of the flux call
+               double Wo[4], Wn[4], Ao[4], An[4], H[4];
+               trace (tb, su + sa * D, f, q, Wo);
+#pragma unroll
+               for (int c = 0; c < 4; ++c) Ao[c] = A.avg[(size_t) (c0 + sa) * 4 + c];
+               bool plus = true; // the visiting cell is the "plus" side of the flux call
                if (nb >= 0)
                {
                   const int qn = (fl & FACE_FLIP) ? N1 - 1 - q : q;
-                  trace (tb, A.u + (size_t) nb * D, f ^ 1, qn, Wn);
+                  if (job.slot_b >= 0)
+                     trace (tb, su + job.slot_b * D, f ^ 1, qn, Wn);
+                  else
+                     trace (tb, A.u + (size_t) nb * D, f ^ 1, qn, Wn);
 #pragma unroll
                   for (int c = 0; c < 4; ++c) An[c] = A.avg[(size_t) nb * 4 + c];
                   plus = (fl & (FACE_OWNER | FACE_PERIODIC)) != 0;
@@ -246,7 +330,12 @@ namespace dflo
                const double sg = plus ? 1.0 : -1.0;
                numerical_flux<FLUX> (sg * nx, sg * ny, L, R, AL, AR, H);
 #pragma unroll
-               for (int c = 0; c < 4; ++c) sH[((slot * 4 + f) * N1 + q) * 4 + c] = sg * H[c];
+               for (int c = 0; c < 4; ++c) sH[((sa * 4 + f) * N1 + q) * 4 + c] = sg * H[c];
+               if (fl & JOB_SHARED) // the neighbour's outward normal is -n
+               {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) sH[((job.slot_b * 4 + (f ^ 1)) * N1 + q) * 4 + c] = -(sg * H[c]);
+               }
             }
          }
          else if (p == 2)
@@ -257,6 +346,12 @@ namespace dflo
             const double dt = A.dt_cell ? A.dt_cell[cell] : A.time[1];
             double *uc = su + slot * D;
             const double *H = sH + slot * 16 * N1;
+            double uo[4] = {0.0, 0.0, 0.0, 0.0};
+            if (A.mode == MODE_STAGE && A.ark != 0.0)
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c) uo[c] = A.u_old[(size_t) cell * D + c * NS + lq];
+            }
             double r[4];
             double invm;
             if (BASIS == BASIS_QK)
@@ -338,19 +433,24 @@ namespace dflo
                {
                   const double un = uc[c * NS + lq] + dt * r[c] * invm;
                   if (A.ark != 0.0)
-                  {
-                     const double uo = A.u_old[(size_t) cell * D + c * NS + lq];
-                     uc[c * NS + lq] = (1.0 - A.ark) * un + A.ark * uo;
-                  }
+                     uc[c * NS + lq] = (1.0 - A.ark) * un + A.ark * uo[c];
                   else
                      uc[c * NS + lq] = un;
                }
             }
+#if defined(__CUDA_ARCH__)
+            fence_async_smem (); // make this thread's shared-memory writes visible to the bulk-copy engine
+#endif
          }
          else // p == 3
          {
             double *dst = A.out + (size_t) c0 * D;
+#if defined(__CUDA_ARCH__)
+            // the tile goes back as one bulk copy shared -> global
+            if (tid == 0) bulk_s2g (dst, su, (unsigned) (ncb * D * sizeof (double)));
+#else
             for (int i = tid; i < ncb * D; i += THREADS) dst[i] = su[i];
+#endif
             if (A.mode == MODE_STAGE)
             {
                // compute_cell_average of the updated solution, claw.cc:562-597
@@ -370,6 +470,9 @@ namespace dflo
                   A.avg_out[(size_t) (c0 + s) * 4 + c] = v;
                }
             }
+#if defined(__CUDA_ARCH__)
+            if (tid == 0) bulk_s2g_wait (); // shared memory must outlive the copy
+#endif
          }
       }
    };
@@ -433,6 +536,7 @@ namespace dflo
       static constexpr int D = 4 * NS;
       static constexpr int CPB = cells_per_block (G);
       static constexpr int THREADS = CPB * G;
+      static constexpr int MIN_BLOCKS = 1;
       static constexpr int NPHASE = 11;
       static constexpr int NGLL = n_gll (N1);
       static constexpr int NPOS = NGLL * N1;

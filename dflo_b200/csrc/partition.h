@@ -6,14 +6,27 @@
 //   layers = 2: lets the stage kernel redundantly update the first ghost layer so that the TVB
 //               limiter of owned cells sees its neighbours' post-update means without a second
 //               exchange: still ONE halo exchange per RK stage.
-// Local cell order: owned (global order) | ghost layer 1 grouped by owner rank | ghost layer 2
-// grouped by owner rank, each group in global order, so every peer's data lands in at most two
-// contiguous ranges and needs no unpack kernel.
+// Local cell order: owned (tile-major, see below) | ghost layer 1 grouped by owner rank | ghost
+// layer 2 grouped by owner rank, each ghost group in global order, so every peer's data lands in
+// at most two contiguous ranges and needs no unpack kernel.
+//
+// Tiles.  The stage kernel works on one TILE of cells per thread block: a run of consecutive local
+// cells whose DoFs are one contiguous block of memory (one bulk async copy into shared memory).
+// Owned cells are therefore renumbered tile-major: on a uniform Cartesian lattice (every mesh the
+// reference's TVB/Pk paths accept, reference src/parameters.cc:536-550) tiles are tx x ty patches
+// of the lattice; otherwise they are grown greedily through the face-neighbour graph.  For every
+// tile the host flattens, once, (a) the list of distinct cells outside the tile that touch it
+// (its halo, staged next to the tile in shared memory) and (b) the list of UNIQUE faces: an
+// interior face whose two cells sit in the same tile appears once, from the cell that
+// MeshWorker::loop visits it from (reference src/assemble_explicit.cc:440-451), so its Riemann
+// problem is solved once per tile instead of once per adjacent cell.  Correctness never depends
+// on how cells were grouped, only the amount of sharing does.
 #pragma once
 
 #include "../../include/dflo_b200.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -41,7 +54,18 @@ namespace dflo
       std::vector<int> bf_global, bf_id; // local boundary faces (of the computed cells) -> global bface, boundary id
       std::vector<int> bf_cell, bf_face; // local cell, face
       std::vector<HaloPeer> peers;
+
+      // tiles of the computed cells [0, n_compute): owned tiles first, then ghost-layer-1 tiles
+      int tile_cells = 0, tile_halo_max = 0;
+      int n_tiles = 0, n_tiles_owned = 0;
+      std::vector<int> tile_start;   // [n_tiles+1] first local cell of each tile
+      std::vector<int> halo_start;   // [n_tiles+1] into halo_cells
+      std::vector<int> halo_cells;   // local cell ids staged after the tile's own cells
+      std::vector<int> job_start;    // [n_tiles+1] into jobs (in units of jobs)
+      std::vector<int> jobs;         // 4 ints per unique face, see FaceJob in kernels.cuh
    };
+
+   constexpr int JOB_SHARED_FLAG = 8; // job flag beside DFLO_FACE_* (kernels.cuh JOB_SHARED): the flux also serves the neighbour slot
 
    inline void partition_range (int n, int world, int r, int &b, int &e)
    {
@@ -92,7 +116,132 @@ namespace dflo
       std::sort (g2.begin (), g2.end ());
    }
 
-   inline bool build_local_mesh (const dflo_flat_mesh &m, int rank, int world, int layers, LocalMesh &L, std::string &err)
+   // Tile-major order of the owned cells [b, e): returns the global cell ids in their new local
+   // order and the tile boundaries (prefix offsets into that order).
+   inline void order_owned_cells (const dflo_flat_mesh &m, int b, int e, int tx, int ty, std::vector<int> &order,
+                                  std::vector<int> &tile_start)
+   {
+      const int n = e - b, tc = tx * ty;
+      order.clear ();
+      tile_start.assign (1, 0);
+      // uniform lattice?
+      const double hx = m.cell_size[0], hy = m.cell_size[1];
+      double xmin = m.cell_origin[0], ymin = m.cell_origin[1];
+      bool uniform = hx > 0 && hy > 0;
+      for (int c = 0; c < m.n_cells && uniform; ++c)
+      {
+         uniform = std::fabs (m.cell_size[2 * (size_t) c] - hx) <= 1e-9 * hx && std::fabs (m.cell_size[2 * (size_t) c + 1] - hy) <= 1e-9 * hy;
+         xmin = std::min (xmin, m.cell_origin[2 * (size_t) c]);
+         ymin = std::min (ymin, m.cell_origin[2 * (size_t) c + 1]);
+      }
+      if (uniform && tc > 1)
+      {
+         struct Key { int64_t tile; int iy, ix, cell; };
+         std::vector<Key> keys (n);
+         for (int i = 0; i < n; ++i)
+         {
+            const int c = b + i;
+            const int ix = (int) std::llround ((m.cell_origin[2 * (size_t) c] - xmin) / hx);
+            const int iy = (int) std::llround ((m.cell_origin[2 * (size_t) c + 1] - ymin) / hy);
+            keys[i] = Key{((int64_t) (iy / ty) << 32) | (int64_t) (ix / tx), iy, ix, c};
+         }
+         std::sort (keys.begin (), keys.end (), [] (const Key &p, const Key &q) {
+            if (p.tile != q.tile) return p.tile < q.tile;
+            if (p.iy != q.iy) return p.iy < q.iy;
+            if (p.ix != q.ix) return p.ix < q.ix;
+            return p.cell < q.cell;
+         });
+         for (int i = 0; i < n; ++i)
+         {
+            // a new tile starts at every new lattice patch, and whenever a patch overflows (two
+            // cells on one lattice site: overlapping blocks of a malformed mesh)
+            if (i > 0 && (keys[i].tile != keys[i - 1].tile || i - tile_start.back () >= tc)) tile_start.push_back (i);
+            order.push_back (keys[i].cell);
+         }
+         tile_start.push_back (n);
+         return;
+      }
+      // general meshes: grow tiles breadth-first through the face-neighbour graph
+      std::vector<char> taken (n, 0);
+      std::vector<int> queue;
+      for (int seed = 0; seed < n; ++seed)
+      {
+         if (taken[seed]) continue;
+         queue.assign (1, seed);
+         taken[seed] = 1;
+         const int first = (int) order.size ();
+         for (size_t head = 0; head < queue.size (); ++head)
+         {
+            const int c = b + queue[head];
+            order.push_back (c);
+            for (int f = 0; f < 4 && (int) queue.size () < tc; ++f)
+            {
+               const int nb = m.neighbor[4 * (size_t) c + f];
+               if (nb >= b && nb < e && !taken[nb - b])
+               {
+                  taken[nb - b] = 1;
+                  queue.push_back (nb - b);
+               }
+            }
+         }
+         tile_start.push_back (first + (int) queue.size ());
+      }
+   }
+
+   // Unique-face job lists and tile halos (needs L.nbr / L.fflags / L.tile_start filled in)
+   inline void build_tile_jobs (LocalMesh &L)
+   {
+      L.n_tiles = (int) L.tile_start.size () - 1;
+      L.halo_start.assign (1, 0);
+      L.job_start.assign (1, 0);
+      L.halo_cells.clear ();
+      L.jobs.clear ();
+      std::vector<int> halo_slot (L.n_local, -1);
+      for (int t = 0; t < L.n_tiles; ++t)
+      {
+         const int c0 = L.tile_start[t], c1 = L.tile_start[t + 1];
+         const size_t h0 = L.halo_cells.size ();
+         for (int cell = c0; cell < c1; ++cell)
+            for (int f = 0; f < 4; ++f)
+            {
+               const int nb = L.nbr[4 * (size_t) cell + f];
+               const int fl = L.fflags[4 * (size_t) cell + f];
+               int slot_b = -1, flags = fl;
+               if (nb >= 0)
+               {
+                  const bool inside = nb >= c0 && nb < c1;
+                  if (inside && !(fl & DFLO_FACE_PERIODIC))
+                  {
+                     if (!(fl & DFLO_FACE_OWNER)) continue; // the owner's job covers this side too
+                     slot_b = nb - c0;
+                     flags |= JOB_SHARED_FLAG;
+                  }
+                  else if (inside)
+                     slot_b = nb - c0; // periodic partner in the same tile: both sides integrate
+                  else
+                  {
+                     if (halo_slot[nb] < 0 && (int) (L.halo_cells.size () - h0) < L.tile_halo_max)
+                     {
+                        halo_slot[nb] = (int) (L.halo_cells.size () - h0);
+                        L.halo_cells.push_back (nb);
+                     }
+                     // beyond the staged halo capacity the kernel gathers from global memory
+                     slot_b = halo_slot[nb] >= 0 ? L.tile_cells + halo_slot[nb] : -1;
+                  }
+               }
+               L.jobs.push_back ((cell - c0) * 4 + f);
+               L.jobs.push_back (nb);
+               L.jobs.push_back (slot_b);
+               L.jobs.push_back (flags);
+            }
+         for (size_t h = h0; h < L.halo_cells.size (); ++h) halo_slot[L.halo_cells[h]] = -1;
+         L.halo_start.push_back ((int) L.halo_cells.size ());
+         L.job_start.push_back ((int) (L.jobs.size () / 4));
+      }
+   }
+
+   inline bool build_local_mesh (const dflo_flat_mesh &m, int rank, int world, int layers, int tile_x, int tile_y,
+                                 LocalMesh &L, std::string &err)
    {
       if (world < 1 || rank < 0 || rank >= world || m.n_cells < world)
       {
@@ -113,12 +262,24 @@ namespace dflo
       L.n_local = L.n_owned + L.n_ghost1 + L.n_ghost2;
       L.n_compute = L.n_owned + (L.layers >= 2 ? L.n_ghost1 : 0);
       L.l2g.resize (L.n_local);
-      for (int i = 0; i < L.n_owned; ++i) L.l2g[i] = L.begin + i;
+      L.tile_cells = tile_x * tile_y;
+      L.tile_halo_max = 2 * (tile_x + tile_y);
+      std::vector<int> order;
+      order_owned_cells (m, L.begin, L.end, tile_x, tile_y, order, L.tile_start);
+      L.n_tiles_owned = (int) L.tile_start.size () - 1;
+      std::vector<int> owned_g2l (L.n_owned);
+      for (int i = 0; i < L.n_owned; ++i)
+      {
+         L.l2g[i] = order[i];
+         owned_g2l[order[i] - L.begin] = i;
+      }
+      // ghost-layer-1 cells that are updated redundantly: tiles of consecutive cells
+      for (int c = L.n_owned; c < L.n_compute; c += L.tile_cells) L.tile_start.push_back (std::min (c + L.tile_cells, L.n_compute));
       for (int i = 0; i < L.n_ghost1; ++i) L.l2g[L.n_owned + i] = g1[i];
       for (int i = 0; i < L.n_ghost2; ++i) L.l2g[L.n_owned + L.n_ghost1 + i] = g2[i];
       // global -> local lookup for the cells we hold
       auto g2l = [&] (int g) -> int {
-         if (g >= L.begin && g < L.end) return g - L.begin;
+         if (g >= L.begin && g < L.end) return owned_g2l[g - L.begin];
          auto it = std::lower_bound (g1.begin (), g1.end (), g);
          if (it != g1.end () && *it == g) return L.n_owned + (int) (it - g1.begin ());
          it = std::lower_bound (g2.begin (), g2.end (), g);
@@ -161,6 +322,7 @@ namespace dflo
                L.nbr[4 * (size_t) l + f] = l; // never evaluated
          }
       }
+      build_tile_jobs (L);
       if (world == 1) return true;
 
       // Halo lists.  What we receive: our ghosts, grouped by owner.  What we send to peer p: the
@@ -188,9 +350,9 @@ namespace dflo
          std::vector<int> pg1, pg2;
          ghost_layers (m, world, p, layers, pg1, pg2);
          for (int g : pg1)
-            if (g >= L.begin && g < L.end) peers[p].send_cells[0].push_back (g - L.begin);
+            if (g >= L.begin && g < L.end) peers[p].send_cells[0].push_back (owned_g2l[g - L.begin]);
          for (int g : pg2)
-            if (g >= L.begin && g < L.end) peers[p].send_cells[1].push_back (g - L.begin);
+            if (g >= L.begin && g < L.end) peers[p].send_cells[1].push_back (owned_g2l[g - L.begin]);
       }
       for (int p = 0; p < world; ++p)
          if (p != rank
