@@ -325,8 +325,9 @@ namespace dflo
       double *rhs = nullptr;
       double *d_time = nullptr;       // t, dt, dt accumulator, final time
       double *d_scratch = nullptr;    // [1] reductions
-      int *d_nbr = nullptr, *d_tile_start = nullptr, *d_halo_start = nullptr, *d_halo_cells = nullptr, *d_job_start = nullptr;
+      int *d_nbr = nullptr, *d_halo_cells = nullptr;
       FaceJob *d_jobs = nullptr;
+      TileDesc *d_tiles = nullptr;
       unsigned char *d_fflags = nullptr;
       double *d_geom = nullptr, *d_bc_g = nullptr, *d_stage_tab = nullptr, *d_lim_tab = nullptr, *d_gw = nullptr, *d_gx = nullptr;
       int *d_bkind = nullptr, *d_bf_cell = nullptr, *d_bf_face = nullptr, *d_bf_id = nullptr, *d_l2g = nullptr, *d_flags = nullptr;
@@ -380,11 +381,22 @@ namespace dflo
          bk.h2d (d_time, t0, sizeof (t0));
          d_scratch = bk.template alloc<double> (4);
          d_nbr = upload (lm.nbr);
-         d_tile_start = upload (lm.tile_start);
-         d_halo_start = upload (lm.halo_start);
          d_halo_cells = upload (pad1 (lm.halo_cells));
-         d_job_start = upload (lm.job_start);
          d_jobs = upload_aligned_jobs ();
+         {
+            std::vector<TileDesc> td (std::max (1, lm.n_tiles));
+            for (int t = 0; t < lm.n_tiles; ++t)
+            {
+               td[t].c0 = lm.tile_start[t];
+               td[t].ncb = lm.tile_start[t + 1] - lm.tile_start[t];
+               td[t].h0 = lm.halo_start[t];
+               td[t].nh = lm.halo_start[t + 1] - lm.halo_start[t];
+               td[t].j0 = lm.job_start[t];
+               td[t].nj = lm.job_start[t + 1] - lm.job_start[t];
+               td[t].pad0 = td[t].pad1 = 0;
+            }
+            d_tiles = upload (td);
+         }
          d_fflags = upload (lm.fflags);
          d_geom = upload (lm.geom);
          d_l2g = upload (lm.l2g);
@@ -426,8 +438,7 @@ namespace dflo
             bk.free (AVG[i]);
          }
          void *ptrs[] = {rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
-                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_ext, d_dofmap, d_tile_start, d_halo_start, d_halo_cells,
-                         d_job_start, d_jobs};
+                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles};
          for (void *p : ptrs) bk.free (p);
          for (int k = 0; k < 2; ++k)
          {
@@ -727,10 +738,8 @@ namespace dflo
          a.out = nullptr;
          a.avg = AVG[cur];
          a.avg_out = nullptr;
-         a.tile_start = d_tile_start;
-         a.halo_start = d_halo_start;
+         a.tiles = d_tiles;
          a.halo_cells = d_halo_cells;
-         a.job_start = d_job_start;
          a.jobs = d_jobs;
          a.geom = d_geom;
          a.bc_g = d_bc_g;

@@ -33,6 +33,52 @@ namespace dflo
    // std::max / std::min with the C++ library's exact semantics ((a<b)?b:a and (b<a)?b:a).  They
    // differ from fmax/fmin when an argument is NaN, and the reference's branches on wave speeds
    // computed from non-physical traces (negative density at an unlimited shock) depend on that.
+   // Reciprocal, reciprocal square root and square root for the flux kernels.  On the device: the
+   // 20-bit hardware seed (MUFU.RCP64H / MUFU.RSQ64H) refined by two Newton steps in fma
+   // arithmetic -- within 1-2 ulp of the correctly rounded result for normal arguments, with none
+   // of the range checks and slow-path subroutine calls of the IEEE-rounded `1.0/x` / `sqrt(x)`
+   // sequences (the flux arguments are densities, sound speeds and their sums; a negative or NaN
+   // argument still yields the negative / NaN result the branches of the callers expect).  On the
+   // host (tests/emu) the exact operations are used.
+   DFLO_HD double fast_rcp (double x)
+   {
+#if defined(__CUDA_ARCH__)
+      double r;
+      asm ("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+      double e = fma (-x, r, 1.0);
+      r = fma (r, e, r);
+      e = fma (-x, r, 1.0);
+      return fma (r, e, r);
+#else
+      return 1.0 / x;
+#endif
+   }
+   DFLO_HD double fast_rsqrt (double x)
+   {
+#if defined(__CUDA_ARCH__)
+      double y;
+      asm ("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+      const double hx = 0.5 * x;
+      double e = fma (-hx * y, y, 0.5);  // (1 - x y^2)/2
+      y = fma (y, e, y);
+      e = fma (-hx * y, y, 0.5);
+      return fma (y, e, y);
+#else
+      return 1.0 / sqrt (x);
+#endif
+   }
+   DFLO_HD double fast_sqrt (double x)
+   {
+#if defined(__CUDA_ARCH__)
+      if (x == 0.0) return 0.0;
+      const double y = fast_rsqrt (x);
+      const double s = x * y;
+      return fma (fma (-s, s, x), 0.5 * y, s); // one correction step on the square root itself
+#else
+      return sqrt (x);
+#endif
+   }
+
    DFLO_HD double std_max (double a, double b) { return (a < b) ? b : a; }
    DFLO_HD double std_min (double a, double b) { return (b < a) ? b : a; }
 
@@ -48,7 +94,7 @@ namespace dflo
    // equation.h:158-193: Cartesian flux components Fx[c], Fy[c]
    DFLO_HD void flux_matrix (const double W[4], double Fx[4], double Fy[4])
    {
-      const double r = 1.0 / W[RHO];
+      const double r = fast_rcp (W[RHO]);
       const double u = W[0] * r, v = W[1] * r;
       const double p = GM1 * (W[ENE] - 0.5 * (W[0] * u + W[1] * v));
       Fx[0] = W[0] * u + p;
@@ -73,16 +119,16 @@ namespace dflo
    // |v.n| + c of a cell average, equation.h:119-137
    DFLO_HD double max_eigenvalue_normal (const double A[4], double nx, double ny)
    {
-      const double r = 1.0 / A[RHO];
+      const double r = fast_rcp (A[RHO]);
       const double p = GM1 * (A[ENE] - 0.5 * (A[0] * A[0] + A[1] * A[1]) * r);
-      return fabs ((A[0] * nx + A[1] * ny) * r) + sqrt (GAMMA * p * r);
+      return fabs ((A[0] * nx + A[1] * ny) * r) + fast_sqrt (GAMMA * p * r);
    }
 
    // equation.h:324-377
    DFLO_HD void lxf_flux (double nx, double ny, const double Wp[4], const double Wm[4], const double Ap[4],
                           const double Am[4], double H[4])
    {
-      const double rp = 1.0 / Wp[RHO], rm = 1.0 / Wm[RHO];
+      const double rp = fast_rcp (Wp[RHO]), rm = fast_rcp (Wm[RHO]);
       const double vnp = (Wp[0] * nx + Wp[1] * ny) * rp;
       const double vnm = (Wm[0] * nx + Wm[1] * ny) * rm;
       const double pp = GM1 * (Wp[ENE] - 0.5 * (Wp[0] * Wp[0] + Wp[1] * Wp[1]) * rp);
@@ -98,13 +144,13 @@ namespace dflo
    // equation.h:382-464
    DFLO_HD void steger_warming_flux (double nx, double ny, const double Wp[4], const double Wm[4], double H[4])
    {
-      const double rp = 1.0 / Wp[RHO], rm = 1.0 / Wm[RHO];
+      const double rp = fast_rcp (Wp[RHO]), rm = fast_rcp (Wm[RHO]);
       const double up = Wp[0] * rp, vp = Wp[1] * rp, um = Wm[0] * rm, vm = Wm[1] * rm;
       const double vnp = up * nx + vp * ny, vnm = um * nx + vm * ny;
       const double q2p = up * up + vp * vp, q2m = um * um + vm * vm;
       const double pp = GM1 * (Wp[ENE] - 0.5 * Wp[RHO] * q2p);
       const double pm = GM1 * (Wm[ENE] - 0.5 * Wm[RHO] * q2m);
-      const double cp = sqrt (GAMMA * pp * rp), cm = sqrt (GAMMA * pm * rm);
+      const double cp = fast_sqrt (GAMMA * pp * rp), cm = fast_sqrt (GAMMA * pm * rm);
 
       const double l1p = std_max (vnp, 0.0), l2p = std_max (vnp + cp, 0.0), l3p = std_max (vnp - cp, 0.0);
       const double ap = 2.0 * GM1 * l1p + l2p + l3p;
@@ -124,9 +170,9 @@ namespace dflo
    // equation.h:469-556
    DFLO_HD void roe_flux (double nx, double ny, const double Wl[4], const double Wr[4], double H[4])
    {
-      const double sl = sqrt (Wl[RHO]), sr = sqrt (Wr[RHO]);
-      const double fl = sl / (sl + sr), fr = 1.0 - fl;
-      const double rl = 1.0 / Wl[RHO], rr = 1.0 / Wr[RHO];
+      const double sl = fast_sqrt (Wl[RHO]), sr = fast_sqrt (Wr[RHO]);
+      const double fl = sl * fast_rcp (sl + sr), fr = 1.0 - fl;
+      const double rl = fast_rcp (Wl[RHO]), rr = fast_rcp (Wr[RHO]);
       const double ul = Wl[0] * rl, vl = Wl[1] * rl, ur = Wr[0] * rr, vr = Wr[1] * rr;
       const double v2l = ul * ul + vl * vl, v2r = ur * ur + vr * vr;
       const double vnl = ul * nx + vl * ny, vnr = ur * nx + vr * ny;
@@ -141,8 +187,8 @@ namespace dflo
       const double dens = sl * sr;
       const double h = hl * fl + hr * fr;
       const double c2 = GM1 * (h - 0.5 * v2);
-      const double c = sqrt (c2);
-      const double ic2 = 1.0 / c2;
+      const double c = fast_sqrt (c2);
+      const double ic2 = fast_rcp (c2);
       const double drho = Wr[RHO] - Wl[RHO], dp = pr - pl, dvn = vnr - vnl;
 
       const double a1 = (dp - dens * c * dvn) * (0.5 * ic2);
@@ -152,8 +198,9 @@ namespace dflo
       double l1 = fabs (vn - c), l3 = fabs (vn + c);
       const double l2 = fabs (vn);
       const double delta = 0.1 * c; // Harten fix on the acoustic waves only (528-531)
-      if (l1 < delta) l1 = 0.5 * (l1 * l1 / delta + delta);
-      if (l3 < delta) l3 = 0.5 * (l3 * l3 / delta + delta);
+      const double idelta = fast_rcp (delta);
+      if (l1 < delta) l1 = 0.5 * (l1 * l1 * idelta + delta);
+      if (l3 < delta) l3 = 0.5 * (l3 * l3 * idelta + delta);
 
       const double w1 = l1 * a1, w2 = l2 * a2, w3 = l3 * a3, w4 = l2 * dens;
       const double Drho = w1 + w2 + w3;
@@ -170,9 +217,9 @@ namespace dflo
    // equation.h:563-681 (HLLC after SU2 v2.0.2)
    DFLO_HD void hllc_flux (double nx, double ny, const double Wl[4], const double Wr[4], double H[4])
    {
-      const double sql = sqrt (Wl[RHO]), sqr = sqrt (Wr[RHO]);
-      const double fl = sql / (sql + sqr), fr = 1.0 - fl;
-      const double rl = 1.0 / Wl[RHO], rr = 1.0 / Wr[RHO];
+      const double sql = fast_sqrt (Wl[RHO]), sqr = fast_sqrt (Wr[RHO]);
+      const double fl = sql * fast_rcp (sql + sqr), fr = 1.0 - fl;
+      const double rl = fast_rcp (Wl[RHO]), rr = fast_rcp (Wr[RHO]);
       const double ul = Wl[0] * rl, vl = Wl[1] * rl, ur = Wr[0] * rr, vr = Wr[1] * rr;
       const double v2l = ul * ul + vl * vl, v2r = ur * ur + vr * vr;
       const double vnl = ul * nx + vl * ny, vnr = ur * nx + vr * ny;
@@ -181,13 +228,13 @@ namespace dflo
       const double pl = GM1 * (Wl[ENE] - 0.5 * Wl[RHO] * v2l);
       const double pr = GM1 * (Wr[ENE] - 0.5 * Wr[RHO] * v2r);
       const double hl = (Wl[ENE] + pl) * rl, hr = (Wr[ENE] + pr) * rr;
-      const double cl = sqrt (GAMMA * pl * rl), cr = sqrt (GAMMA * pr * rr);
+      const double cl = fast_sqrt (GAMMA * pl * rl), cr = fast_sqrt (GAMMA * pr * rr);
       const double h = hl * fl + hr * fr;
-      const double c = sqrt (GM1 * (h - 0.5 * v2));
+      const double c = fast_sqrt (GM1 * (h - 0.5 * v2));
       const double s_l = std_min (vn - c, vnl - cl);
       const double s_r = std_max (vn + c, vnr + cr);
       const double ml = Wl[RHO] * (s_l - vnl), mr = Wr[RHO] * (s_r - vnr);
-      const double s_m = (pl - pr - ml * vnl + mr * vnr) / (mr - ml);
+      const double s_m = (pl - pr - ml * vnl + mr * vnr) * fast_rcp (mr - ml);
       const double ps = Wr[RHO] * (vnr - s_r) * (vnr - s_m) + pr;
 
       if (s_m >= 0.0)
@@ -201,7 +248,7 @@ namespace dflo
          }
          else
          {
-            const double inv = 1.0 / (s_l - s_m);
+            const double inv = fast_rcp (s_l - s_m);
             const double smu = s_l - vnl;
             const double dps = ps - pl;
             H[RHO] = Wl[RHO] * smu * inv * s_m;
@@ -214,7 +261,7 @@ namespace dflo
       {
          if (s_r >= 0.0)
          {
-            const double inv = 1.0 / (s_r - s_m);
+            const double inv = fast_rcp (s_r - s_m);
             const double smu = s_r - vnr;
             const double dps = ps - pr;
             H[RHO] = Wr[RHO] * smu * inv * s_m;
@@ -235,22 +282,22 @@ namespace dflo
    // equation.h:714-751 with ERF of 686-709 (Abramowitz-Stegun 7.1.26, NOT libm erf)
    DFLO_HD void kinetic_split_flux (double sign, double nx, double ny, const double W[4], double H[4])
    {
-      const double r = 1.0 / W[RHO];
+      const double r = fast_rcp (W[RHO]);
       const double vn = (W[0] * nx + W[1] * ny) * r;
       const double p = GM1 * (W[ENE] - 0.5 * (W[0] * W[0] + W[1] * W[1]) * r);
-      const double beta = 0.5 * W[RHO] / p;
-      const double sb = sqrt (beta);
+      const double beta = 0.5 * W[RHO] * fast_rcp (p);
+      const double sb = fast_sqrt (beta);
       const double s = vn * sb;
       const double ex = exp (-s * s);
       // ERF(s)
       const double x = fabs (s);
-      const double t = 1.0 / (1.0 + 0.3275911 * x);
+      const double t = fast_rcp (1.0 + 0.3275911 * x);
       const double y = 1.0
                        - (((((1.061405429 * t + -1.453152027) * t) + 1.421413741) * t + -0.284496736) * t + 0.254829592)
                             * t * ex;
       const double erf_s = (s < 0) ? -y : y;
       const double A = 0.5 * (1.0 + sign * erf_s);
-      const double B = 0.5 * sign * ex / (1.7724538509055160273 * sb); // sqrt(pi*beta)
+      const double B = 0.5 * sign * ex * fast_rcp (1.7724538509055160273 * sb); // sqrt(pi*beta)
       const double uf = vn * A + B;
       H[0] = p * nx * A + W[0] * uf;
       H[1] = p * ny * A + W[1] * uf;

@@ -66,6 +66,13 @@ namespace dflo
       int flags;   // FACE_* | JOB_SHARED
    };
 
+   // One tile of the stage kernel: cells [c0, c0+ncb), its staged halo cells halo_cells[h0 .. h0+nh)
+   // and its unique faces jobs[j0 .. j0+nj)
+   struct alignas (32) TileDesc
+   {
+      int c0, ncb, h0, nh, j0, nj, pad0, pad1;
+   };
+
    struct StageArgs
    {
       const double *u;        // current_solution   [n_local][D]
@@ -73,10 +80,8 @@ namespace dflo
       double *out;            // MODE_STAGE: updated solution (a different buffer than u); MODE_RHS: right_hand_side
       const double *avg;      // cell_average of u   [n_local][4]
       double *avg_out;        // cell_average of the updated solution
-      const int *tile_start;  // [n_tiles+1]
-      const int *halo_start;  // [n_tiles+1]
+      const TileDesc *tiles;  // [n_tiles]
       const int *halo_cells;
-      const int *job_start;   // [n_tiles+1]
       const FaceJob *jobs;
       const double *geom;     // [n_local][4] x0, y0, hx, hy
       const double *bc_g;     // [n_bfaces][n_q_face][4]
@@ -141,7 +146,7 @@ namespace dflo
       static constexpr int NH = 2 * (tile_nx (N1) + tile_ny (N1));  // staged halo cells per tile
       static constexpr int THREADS = (TC * G + 31) / 32 * 32;
 #ifndef DFLO_STAGE_MIN_BLOCKS
-#define DFLO_STAGE_MIN_BLOCKS 3
+#define DFLO_STAGE_MIN_BLOCKS 4
 #endif
       static constexpr int MIN_BLOCKS = DFLO_STAGE_MIN_BLOCKS; // resident blocks per SM the register budget is held to
       static constexpr int NPHASE = 4;
@@ -152,7 +157,12 @@ namespace dflo
       static constexpr int O_F = O_U + (TC + NH) * D;
       static constexpr int O_H = O_F + TC * 8 * NQ;
       static constexpr int O_W = O_H + TC * 16 * N1;
-      static constexpr int SMEM_DOUBLES = O_W + (BASIS == BASIS_PK ? TC * 4 * NQ : 0);
+      static constexpr int O_UOLD = O_W + (BASIS == BASIS_PK ? TC * 4 * NQ : 0);   // old_solution of the tile
+      static constexpr int O_GEOM = O_UOLD + TC * D;                             // x0 y0 hx hy per tile cell
+      static constexpr int O_AVG = O_GEOM + TC * 4;                              // cell averages, tile + halo (LxF only)
+      static constexpr int O_JOBS = O_AVG + (FLUX == FLUX_LXF ? (TC + NH) * 4 : 0);
+      static constexpr int O_DT = O_JOBS + TC * 4 * 2;                           // FaceJob = 2 doubles
+      static constexpr int SMEM_DOUBLES = O_DT + 2;
 
       // table accessors ------------------------------------------------------------------------
       // Qk: dw[N1*N1] e0[N1] e1[N1] gw[N1]
@@ -203,39 +213,70 @@ namespace dflo
 
       static DFLO_DEV void phase (int p, const Args &A, double *sm, int tid, int bid)
       {
-         const int c0 = A.tile_start[bid];
-         const int ncb = A.tile_start[bid + 1] - c0;
+         const TileDesc td = A.tiles[bid];
+         const int c0 = td.c0, ncb = td.ncb;
          double *tb = sm + O_TAB;
          double *su = sm + O_U;
          double *sF = sm + O_F;
          double *sH = sm + O_H;
          double *sW = sm + O_W;
+         double *sUold = sm + O_UOLD;
+         double *sGeom = sm + O_GEOM;
+         double *sAvg = sm + O_AVG;
+         FaceJob *sJobs = reinterpret_cast<FaceJob *> (sm + O_JOBS);
          const int slot = tid / G, lq = tid % G;
          const bool active = slot < ncb;
          const int cell = c0 + slot;
+         const bool need_old = A.mode == MODE_STAGE && A.ark != 0.0;
 
          if (p == 0)
          {
-            // stage the tile (one contiguous run of ncb*D doubles) and its halo cells in shared
-            // memory, plus the tables
-            const int h0 = A.halo_start[bid];
-            const int nh = A.halo_start[bid + 1] - h0;
+            // Stage EVERYTHING this tile reads from global memory in shared memory, as bulk async
+            // copies completing on one mbarrier: the tile's DoFs (one contiguous run), its halo
+            // cells, old_solution of the tile, geometry, the unique-face list and (LxF) the cell
+            // averages.  Later phases touch global memory only to write.
+            const int h0 = td.h0, nh = td.nh, nj = td.nj;
+            const unsigned cell_bytes = (unsigned) (D * sizeof (double));
 #if defined(__CUDA_ARCH__)
             if (tid == 0)
             {
+               unsigned bytes = (unsigned) (ncb + nh) * cell_bytes + (unsigned) ncb * 32u + (unsigned) nj * 16u;
+               if (need_old) bytes += (unsigned) ncb * cell_bytes;
+               if (FLUX == FLUX_LXF) bytes += (unsigned) (ncb + nh) * 32u;
                mbar_init (sm, 1);
-               mbar_expect_tx (sm, (unsigned) ((ncb + nh) * D * sizeof (double)));
+               mbar_expect_tx (sm, bytes);
             }
             __syncthreads ();
-            if (tid == 0) bulk_g2s (su, A.u + (size_t) c0 * D, (unsigned) (ncb * D * sizeof (double)), sm);
-            for (int h = tid - 1; h >= 0 && h < nh; h += THREADS)
-               bulk_g2s (su + (TC + h) * D, A.u + (size_t) A.halo_cells[h0 + h] * D, (unsigned) (D * sizeof (double)), sm);
+            if (tid == 0)
+            {
+               bulk_g2s (su, A.u + (size_t) c0 * D, (unsigned) ncb * cell_bytes, sm);
+               if (need_old) bulk_g2s (sUold, A.u_old + (size_t) c0 * D, (unsigned) ncb * cell_bytes, sm);
+               bulk_g2s (sGeom, A.geom + (size_t) c0 * 4, (unsigned) ncb * 32u, sm);
+               if (nj) bulk_g2s (sJobs, A.jobs + td.j0, (unsigned) nj * 16u, sm);
+               if (FLUX == FLUX_LXF) bulk_g2s (sAvg, A.avg + (size_t) c0 * 4, (unsigned) ncb * 32u, sm);
+            }
+            else if (tid <= nh)
+            {
+               const int hc = A.halo_cells[h0 + tid - 1];
+               bulk_g2s (su + (TC + tid - 1) * D, A.u + (size_t) hc * D, cell_bytes, sm);
+               if (FLUX == FLUX_LXF) bulk_g2s (sAvg + (TC + tid - 1) * 4, A.avg + (size_t) hc * 4, 32u, sm);
+            }
+            if (tid == THREADS - 1) sm[O_DT] = A.time[1];
             for (int i = tid; i < TAB; i += THREADS) tb[i] = A.tab[i];
             mbar_wait (sm, 0);
 #else
-            const double *src = A.u + (size_t) c0 * D;
-            for (int i = tid; i < ncb * D; i += THREADS) su[i] = src[i];
+            for (int i = tid; i < ncb * D; i += THREADS) su[i] = A.u[(size_t) c0 * D + i];
             for (int i = tid; i < nh * D; i += THREADS) su[TC * D + i] = A.u[(size_t) A.halo_cells[h0 + i / D] * D + i % D];
+            if (need_old)
+               for (int i = tid; i < ncb * D; i += THREADS) sUold[i] = A.u_old[(size_t) c0 * D + i];
+            for (int i = tid; i < ncb * 4; i += THREADS) sGeom[i] = A.geom[(size_t) c0 * 4 + i];
+            for (int i = tid; i < nj; i += THREADS) sJobs[i] = A.jobs[td.j0 + i];
+            if (FLUX == FLUX_LXF)
+            {
+               for (int i = tid; i < ncb * 4; i += THREADS) sAvg[i] = A.avg[(size_t) c0 * 4 + i];
+               for (int i = tid; i < nh * 4; i += THREADS) sAvg[TC * 4 + i] = A.avg[(size_t) A.halo_cells[h0 + i / 4] * 4 + i % 4];
+            }
+            if (tid == THREADS - 1) sm[O_DT] = A.time[1];
             for (int i = tid; i < TAB; i += THREADS) tb[i] = A.tab[i];
 #endif
          }
@@ -276,11 +317,10 @@ namespace dflo
             // ---- faces: one numerical flux per UNIQUE face point of the tile, along the visiting
             //      cell's outward normal (assemble_explicit.cc:176-206, 303-341; periodic: src_mpi
             //      186-260); a face shared by two cells of the tile serves both ----
-            const int j0 = A.job_start[bid];
-            const int nj = (A.job_start[bid + 1] - j0) * N1;
-            for (int idx = tid; idx < nj; idx += THREADS)
+            const int njq = td.nj * N1;
+            for (int idx = tid; idx < njq; idx += THREADS)
             {
-               const FaceJob job = A.jobs[j0 + idx / N1];
+               const FaceJob job = sJobs[idx / N1];
                const int q = idx % N1;
                const int sa = job.a >> 2, f = job.a & 3;
                const int nb = job.nb, fl = job.flags;
@@ -288,8 +328,11 @@ namespace dflo
                const double ny = (f == 2) ? -1.0 : (f == 3) ? 1.0 : 0.0;
                double Wo[4], Wn[4], Ao[4], An[4], H[4];
                trace (tb, su + sa * D, f, q, Wo);
+               if (FLUX == FLUX_LXF) // the only flux that reads the cell averages (equation.h:357-359)
+               {
 #pragma unroll
-               for (int c = 0; c < 4; ++c) Ao[c] = A.avg[(size_t) (c0 + sa) * 4 + c];
+                  for (int c = 0; c < 4; ++c) Ao[c] = sAvg[sa * 4 + c];
+               }
                bool plus = true; // the visiting cell is the "plus" side of the flux call
                if (nb >= 0)
                {
@@ -298,8 +341,11 @@ namespace dflo
                      trace (tb, su + job.slot_b * D, f ^ 1, qn, Wn);
                   else
                      trace (tb, A.u + (size_t) nb * D, f ^ 1, qn, Wn);
+                  if (FLUX == FLUX_LXF)
+                  {
 #pragma unroll
-                  for (int c = 0; c < 4; ++c) An[c] = A.avg[(size_t) nb * 4 + c];
+                     for (int c = 0; c < 4; ++c) An[c] = job.slot_b >= 0 ? sAvg[job.slot_b * 4 + c] : A.avg[(size_t) nb * 4 + c];
+                  }
                   plus = (fl & (FACE_OWNER | FACE_PERIODIC)) != 0;
                }
                else
@@ -310,12 +356,15 @@ namespace dflo
 #pragma unroll
                   for (int c = 0; c < 4; ++c) g[c] = A.bc_g[((size_t) bf * N1 + q) * 4 + c];
                   compute_wminus (kind, nx, ny, Wo, g, Wn);
-                  if (A.compat_mpi) // src_mpi/assemble_explicit.cc:296-321
-                     compute_wminus (kind, nx, ny, Ao, g, An);
-                  else // src/assemble_explicit.cc:203-204: own average on both sides
+                  if (FLUX == FLUX_LXF)
                   {
+                     if (A.compat_mpi) // src_mpi/assemble_explicit.cc:296-321
+                        compute_wminus (kind, nx, ny, Ao, g, An);
+                     else // src/assemble_explicit.cc:203-204: own average on both sides
+                     {
 #pragma unroll
-                     for (int c = 0; c < 4; ++c) An[c] = Ao[c];
+                        for (int c = 0; c < 4; ++c) An[c] = Ao[c];
+                     }
                   }
                }
                double L[4], R[4], AL[4], AR[4];
@@ -341,17 +390,11 @@ namespace dflo
          else if (p == 2)
          {
             if (!active || lq >= NS) return;
-            const double hx = A.geom[(size_t) cell * 4 + 2], hy = A.geom[(size_t) cell * 4 + 3];
+            const double hx = sGeom[slot * 4 + 2], hy = sGeom[slot * 4 + 3];
             const double *gw = t_gw (tb);
-            const double dt = A.dt_cell ? A.dt_cell[cell] : A.time[1];
+            const double dt = A.dt_cell ? A.dt_cell[cell] : sm[O_DT];
             double *uc = su + slot * D;
             const double *H = sH + slot * 16 * N1;
-            double uo[4] = {0.0, 0.0, 0.0, 0.0};
-            if (A.mode == MODE_STAGE && A.ark != 0.0)
-            {
-#pragma unroll
-               for (int c = 0; c < 4; ++c) uo[c] = A.u_old[(size_t) cell * D + c * NS + lq];
-            }
             double r[4];
             double invm;
             if (BASIS == BASIS_QK)
@@ -433,7 +476,7 @@ namespace dflo
                {
                   const double un = uc[c * NS + lq] + dt * r[c] * invm;
                   if (A.ark != 0.0)
-                     uc[c * NS + lq] = (1.0 - A.ark) * un + A.ark * uo[c];
+                     uc[c * NS + lq] = (1.0 - A.ark) * un + A.ark * sUold[slot * D + c * NS + lq];
                   else
                      uc[c * NS + lq] = un;
                }

@@ -12,8 +12,9 @@ __global__ void __launch_bounds__ (K::THREADS, K::MIN_BLOCKS) probe_kernel (cons
       if (p + 1 < K::NPHASE) __syncthreads ();
    }
 }
-#ifndef PROBE_LIST
-#define PROBE_LIST X(0,4,3) X(0,3,4) X(1,3,4) X(0,2,0) X(0,4,2)
-#endif
 #define X(B,N,F) template __global__ void probe_kernel<dflo::StageKernel<B,N,F>>(const dflo::StageArgs);
-PROBE_LIST
+#ifdef PB   // -DPB=0 -DPN=4 -DPF=3: basis, k+1, flux
+X(PB, PN, PF)
+#else
+X(0,4,3) X(0,3,4) X(1,3,4) X(0,2,0) X(0,4,2)
+#endif
