@@ -253,11 +253,11 @@ namespace dflo
       {
          switch (flux)
          {
-            case FLUX_LXF: bk.template launch<StageKernel<BASIS, N1, FLUX_LXF>> (n_tiles, a); break;
-            case FLUX_SW: bk.template launch<StageKernel<BASIS, N1, FLUX_SW>> (n_tiles, a); break;
-            case FLUX_KFVS: bk.template launch<StageKernel<BASIS, N1, FLUX_KFVS>> (n_tiles, a); break;
-            case FLUX_ROE: bk.template launch<StageKernel<BASIS, N1, FLUX_ROE>> (n_tiles, a); break;
-            default: bk.template launch<StageKernel<BASIS, N1, FLUX_HLLC>> (n_tiles, a); break;
+            case FLUX_LXF: bk.template launch_stage<StageKernel<BASIS, N1, FLUX_LXF>> (n_tiles, a); break;
+            case FLUX_SW: bk.template launch_stage<StageKernel<BASIS, N1, FLUX_SW>> (n_tiles, a); break;
+            case FLUX_KFVS: bk.template launch_stage<StageKernel<BASIS, N1, FLUX_KFVS>> (n_tiles, a); break;
+            case FLUX_ROE: bk.template launch_stage<StageKernel<BASIS, N1, FLUX_ROE>> (n_tiles, a); break;
+            default: bk.template launch_stage<StageKernel<BASIS, N1, FLUX_HLLC>> (n_tiles, a); break;
          }
       }
    };

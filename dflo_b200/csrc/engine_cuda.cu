@@ -102,6 +102,8 @@ namespace
       ncclResult_t first_nccl_error = ncclSuccess;
       ncclComm_t comm = nullptr;
       bool use_graphs = true;
+      bool persistent = true;
+      int n_sm = 148;
       bool capturing = false;
       struct Graph
       {
@@ -142,6 +144,9 @@ namespace
          note (cudaStreamCreateWithFlags (&stream, cudaStreamNonBlocking));
          note (cudaEventCreate (&ev0));
          note (cudaEventCreate (&ev1));
+         note (cudaDeviceGetAttribute (&n_sm, cudaDevAttrMultiProcessorCount, device));
+         const char *ps = std::getenv ("DFLO_B200_PERSISTENT");
+         persistent = ps ? (std::atoi (ps) != 0) : true;
          const char *g = std::getenv ("DFLO_B200_GRAPHS");
          use_graphs = g ? (std::atoi (g) != 0) : true;
          if (world > 1)
@@ -230,6 +235,30 @@ namespace
          }
          ++launches;
          phase_kernel<K><<<grid, K::THREADS, smem, stream>>> (a);
+         note (cudaPeekAtLastError ());
+      }
+      // The stage kernel.  Default: the pipelined persistent form (one producer warp streaming tiles
+      // through two shared-memory stages); DFLO_B200_PERSISTENT=0 selects the one-tile-per-block form.
+      template <class K> void launch_stage (int n_tiles, const typename K::Args &a)
+      {
+         if (n_tiles <= 0) return;
+         if (!persistent)
+         {
+            launch<K> (n_tiles, a);
+            return;
+         }
+         constexpr size_t smem = K::PERSIST_SMEM_DOUBLES * sizeof (double);
+         static int blocks_per_sm = -1;
+         if (blocks_per_sm < 0)
+         {
+            note (cudaFuncSetAttribute (dflo::stage_persistent_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            int n = 0;
+            note (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&n, dflo::stage_persistent_kernel<K>, K::THREADS + 32, smem));
+            blocks_per_sm = n > 0 ? n : 1;
+         }
+         const int grid = std::min (n_tiles, n_sm * blocks_per_sm);
+         ++launches;
+         dflo::stage_persistent_kernel<K><<<grid, K::THREADS + 32, smem, stream>>> (a, n_tiles);
          note (cudaPeekAtLastError ());
       }
       template <class K> void launch1d (int n, const typename K::Args &a)

@@ -95,7 +95,7 @@ namespace dflo
       double gravity;
    };
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
    // ---- sm_100a asynchronous bulk copies (TMA unit, 1-D): global -> shared completing on an
    //      mbarrier, shared -> global as a bulk group ----
    __device__ __forceinline__ unsigned smem_addr (const void *p) { return (unsigned) __cvta_generic_to_shared (p); }
@@ -132,6 +132,12 @@ namespace dflo
    }
    __device__ __forceinline__ void bulk_s2g_wait () { asm volatile ("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
    __device__ __forceinline__ void fence_async_smem () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
+   __device__ __forceinline__ void mbar_arrive (void *bar)
+   {
+      asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr (bar)) : "memory");
+   }
+   template <int ID, int COUNT>
+   __device__ __forceinline__ void named_barrier () { asm volatile ("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
 #endif
 
    template <int BASIS, int N1, int FLUX>
@@ -150,6 +156,7 @@ namespace dflo
 #endif
       static constexpr int MIN_BLOCKS = DFLO_STAGE_MIN_BLOCKS; // resident blocks per SM the register budget is held to
       static constexpr int NPHASE = 4;
+      static constexpr int FLUX_ID = FLUX;
       static constexpr int TAB = stage_table_size (BASIS, N1);
       // shared memory carve-up (in doubles); every bulk-copy destination is 16-byte aligned
       static constexpr int O_TAB = 2;                                // [0,2): the mbarrier
@@ -163,6 +170,22 @@ namespace dflo
       static constexpr int O_JOBS = O_AVG + (FLUX == FLUX_LXF ? (TC + NH) * 4 : 0);
       static constexpr int O_DT = O_JOBS + TC * 4 * 2;                           // FaceJob = 2 doubles
       static constexpr int SMEM_DOUBLES = O_DT + 2;
+      // pipelined (persistent) form: barriers | tables | work arrays | old_solution | dt | 2 input stages
+      static constexpr int PERSIST_BLOCKS = 3;                       // resident blocks per SM aimed at
+      static constexpr int P_TAB = 8;                                // [0,8): six mbarriers
+      static constexpr int P_F = P_TAB + (TAB + 1) / 2 * 2;
+      static constexpr int P_H = P_F + TC * 8 * NQ;
+      static constexpr int P_W = P_H + TC * 16 * N1;
+      static constexpr int P_UOLD = P_W + (BASIS == BASIS_PK ? TC * 4 * NQ : 0);
+      static constexpr int P_DT = P_UOLD + TC * D;
+      static constexpr int P_STAGE = P_DT + 2;
+      static constexpr int S_U = 0;                                  // offsets inside one input stage
+      static constexpr int S_GEOM = S_U + (TC + NH) * D;
+      static constexpr int S_AVG = S_GEOM + TC * 4;
+      static constexpr int S_JOBS = S_AVG + (FLUX == FLUX_LXF ? (TC + NH) * 4 : 0);
+      static constexpr int S_TD = S_JOBS + TC * 4 * 2;
+      static constexpr int STAGE_DOUBLES = S_TD + 4;
+      static constexpr int PERSIST_SMEM_DOUBLES = P_STAGE + 2 * STAGE_DOUBLES;
 
       // table accessors ------------------------------------------------------------------------
       // Qk: dw[N1*N1] e0[N1] e1[N1] gw[N1]
@@ -211,19 +234,29 @@ namespace dflo
          }
       }
 
+      // where the pieces of one tile live in shared memory
+      struct Views
+      {
+         double *tb, *su, *sF, *sH, *sW, *sUold, *sGeom, *sAvg, *sDt;
+         FaceJob *sJobs;
+      };
+
+      // one-tile-per-block form (generic phase_kernel, and the CPU emulation of tests/emu)
       static DFLO_DEV void phase (int p, const Args &A, double *sm, int tid, int bid)
       {
-         const TileDesc td = A.tiles[bid];
+         const Views v = {sm + O_TAB, sm + O_U, sm + O_F, sm + O_H, sm + O_W, sm + O_UOLD, sm + O_GEOM, sm + O_AVG, sm + O_DT,
+                          reinterpret_cast<FaceJob *> (sm + O_JOBS)};
+         work (p, A, A.tiles[bid], v, sm, tid, false);
+      }
+
+      // p = 0: stage the tile (one-tile-per-block form only); 1: volume + face fluxes; 2: residual,
+      // M^-1, RK combine; 3: write back + cell averages.  `persistent`: called from the pipelined
+      // kernel below (inputs already staged by its producer warp, plain stores on the way out).
+      static DFLO_DEV void work (int p, const Args &A, const TileDesc &td, const Views &v, double *sm, int tid, bool persistent)
+      {
          const int c0 = td.c0, ncb = td.ncb;
-         double *tb = sm + O_TAB;
-         double *su = sm + O_U;
-         double *sF = sm + O_F;
-         double *sH = sm + O_H;
-         double *sW = sm + O_W;
-         double *sUold = sm + O_UOLD;
-         double *sGeom = sm + O_GEOM;
-         double *sAvg = sm + O_AVG;
-         FaceJob *sJobs = reinterpret_cast<FaceJob *> (sm + O_JOBS);
+         double *tb = v.tb, *su = v.su, *sF = v.sF, *sH = v.sH, *sW = v.sW, *sUold = v.sUold, *sGeom = v.sGeom, *sAvg = v.sAvg;
+         FaceJob *sJobs = v.sJobs;
          const int slot = tid / G, lq = tid % G;
          const bool active = slot < ncb;
          const int cell = c0 + slot;
@@ -261,7 +294,7 @@ namespace dflo
                bulk_g2s (su + (TC + tid - 1) * D, A.u + (size_t) hc * D, cell_bytes, sm);
                if (FLUX == FLUX_LXF) bulk_g2s (sAvg + (TC + tid - 1) * 4, A.avg + (size_t) hc * 4, 32u, sm);
             }
-            if (tid == THREADS - 1) sm[O_DT] = A.time[1];
+            if (tid == THREADS - 1) v.sDt[0] = A.time[1];
             for (int i = tid; i < TAB; i += THREADS) tb[i] = A.tab[i];
             mbar_wait (sm, 0);
 #else
@@ -276,7 +309,7 @@ namespace dflo
                for (int i = tid; i < ncb * 4; i += THREADS) sAvg[i] = A.avg[(size_t) c0 * 4 + i];
                for (int i = tid; i < nh * 4; i += THREADS) sAvg[TC * 4 + i] = A.avg[(size_t) A.halo_cells[h0 + i / 4] * 4 + i % 4];
             }
-            if (tid == THREADS - 1) sm[O_DT] = A.time[1];
+            if (tid == THREADS - 1) v.sDt[0] = A.time[1];
             for (int i = tid; i < TAB; i += THREADS) tb[i] = A.tab[i];
 #endif
          }
@@ -392,7 +425,7 @@ namespace dflo
             if (!active || lq >= NS) return;
             const double hx = sGeom[slot * 4 + 2], hy = sGeom[slot * 4 + 3];
             const double *gw = t_gw (tb);
-            const double dt = A.dt_cell ? A.dt_cell[cell] : sm[O_DT];
+            const double dt = A.dt_cell ? A.dt_cell[cell] : v.sDt[0];
             double *uc = su + slot * D;
             const double *H = sH + slot * 16 * N1;
             double r[4];
@@ -482,15 +515,21 @@ namespace dflo
                }
             }
 #if defined(__CUDA_ARCH__)
-            fence_async_smem (); // make this thread's shared-memory writes visible to the bulk-copy engine
+            if (!persistent) fence_async_smem (); // make this thread's shared-memory writes visible to the bulk-copy engine
 #endif
          }
          else // p == 3
          {
             double *dst = A.out + (size_t) c0 * D;
 #if defined(__CUDA_ARCH__)
-            // the tile goes back as one bulk copy shared -> global
-            if (tid == 0) bulk_s2g (dst, su, (unsigned) (ncb * D * sizeof (double)));
+            if (persistent) // fire-and-forget 16-byte stores: the stage buffer is free as soon as they are issued
+            {
+               const double2 *s2 = reinterpret_cast<const double2 *> (su);
+               double2 *d2 = reinterpret_cast<double2 *> (dst);
+               for (int i = tid; i < ncb * D / 2; i += THREADS) d2[i] = s2[i];
+            }
+            else if (tid == 0) // the tile goes back as one bulk copy shared -> global
+               bulk_s2g (dst, su, (unsigned) (ncb * D * sizeof (double)));
 #else
             for (int i = tid; i < ncb * D; i += THREADS) dst[i] = su[i];
 #endif
@@ -514,11 +553,106 @@ namespace dflo
                }
             }
 #if defined(__CUDA_ARCH__)
-            if (tid == 0) bulk_s2g_wait (); // shared memory must outlive the copy
+            if (!persistent && tid == 0) bulk_s2g_wait (); // shared memory must outlive the copy
 #endif
          }
       }
    };
+
+#if defined(__CUDACC__)
+   // Pipelined form of the stage kernel: one persistent block per SM slot walks over the tiles
+   // t = blockIdx.x, blockIdx.x + gridDim.x, ...  K::THREADS consumer threads run phases 1-3 of
+   // StageKernel::work on the tile in input stage (it & 1) while ONE producer warp, two tiles
+   // ahead, streams the next tiles' inputs into the other stage with bulk async copies (TMA):
+   //   full[s]   producer -> consumers   stage s holds tile it (expect_tx byte count)
+   //   empty[s]  consumers -> producer   all consumer threads are done with stage s
+   //   full_old / empty_old              the same hand-shake for old_solution of the tile
+   // so no consumer ever waits on a global-memory load; consumers synchronise among themselves
+   // with a named barrier that the producer warp does not take part in.
+   template <class K>
+   __global__ void __launch_bounds__ (K::THREADS + 32, K::PERSIST_BLOCKS) stage_persistent_kernel (const StageArgs A, int n_tiles)
+   {
+      extern __shared__ __align__ (16) double sm[];
+      const int tid = threadIdx.x;
+      unsigned long long *bars = reinterpret_cast<unsigned long long *> (sm); // full0 full1 empty0 empty1 full_old empty_old
+      const bool need_old = A.mode == MODE_STAGE && A.ark != 0.0;
+      constexpr unsigned cell_bytes = (unsigned) (K::D * sizeof (double));
+      if (tid == 0)
+      {
+         mbar_init (&bars[0], 1);
+         mbar_init (&bars[1], 1);
+         mbar_init (&bars[2], K::THREADS);
+         mbar_init (&bars[3], K::THREADS);
+         mbar_init (&bars[4], 1);
+         mbar_init (&bars[5], 1);
+         sm[K::P_DT] = A.time[1];
+      }
+      for (int i = tid; i < K::TAB; i += K::THREADS + 32) sm[K::P_TAB + i] = A.tab[i];
+      __syncthreads ();
+
+      if (tid >= K::THREADS)
+      {
+         // ---------------- producer warp ----------------
+         const int lane = tid - K::THREADS;
+         int it = 0;
+         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it)
+         {
+            const int s = it & 1;
+            double *st = sm + K::P_STAGE + s * K::STAGE_DOUBLES;
+            if (it >= 2) mbar_wait (&bars[2 + s], ((it >> 1) - 1) & 1);
+            const TileDesc td = A.tiles[t];
+            if (lane == 0)
+            {
+               unsigned bytes = (unsigned) (td.ncb + td.nh) * cell_bytes + (unsigned) td.ncb * 32u + (unsigned) td.nj * 16u + 32u;
+               if (K::FLUX_ID == FLUX_LXF) bytes += (unsigned) (td.ncb + td.nh) * 32u;
+               mbar_expect_tx (&bars[s], bytes);
+               bulk_g2s (st + K::S_U, A.u + (size_t) td.c0 * K::D, (unsigned) td.ncb * cell_bytes, &bars[s]);
+               bulk_g2s (st + K::S_GEOM, A.geom + (size_t) td.c0 * 4, (unsigned) td.ncb * 32u, &bars[s]);
+               if (td.nj) bulk_g2s (st + K::S_JOBS, A.jobs + td.j0, (unsigned) td.nj * 16u, &bars[s]);
+               bulk_g2s (st + K::S_TD, A.tiles + t, 32u, &bars[s]);
+               if (K::FLUX_ID == FLUX_LXF) bulk_g2s (st + K::S_AVG, A.avg + (size_t) td.c0 * 4, (unsigned) td.ncb * 32u, &bars[s]);
+            }
+            __syncwarp ();
+            for (int h = lane; h < td.nh; h += 32)
+            {
+               const int hc = A.halo_cells[td.h0 + h];
+               bulk_g2s (st + K::S_U + (K::TC + h) * K::D, A.u + (size_t) hc * K::D, cell_bytes, &bars[s]);
+               if (K::FLUX_ID == FLUX_LXF) bulk_g2s (st + K::S_AVG + (K::TC + h) * 4, A.avg + (size_t) hc * 4, 32u, &bars[s]);
+            }
+            if (need_old)
+            {
+               if (it >= 1) mbar_wait (&bars[5], (it - 1) & 1);
+               if (lane == 0)
+               {
+                  mbar_expect_tx (&bars[4], (unsigned) td.ncb * cell_bytes);
+                  bulk_g2s (sm + K::P_UOLD, A.u_old + (size_t) td.c0 * K::D, (unsigned) td.ncb * cell_bytes, &bars[4]);
+               }
+            }
+         }
+         return;
+      }
+
+      // ---------------- consumers ----------------
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it)
+      {
+         const int s = it & 1;
+         double *st = sm + K::P_STAGE + s * K::STAGE_DOUBLES;
+         const typename K::Views v = {sm + K::P_TAB, st + K::S_U, sm + K::P_F, sm + K::P_H, sm + K::P_W, sm + K::P_UOLD, st + K::S_GEOM,
+                                      st + K::S_AVG, sm + K::P_DT, reinterpret_cast<FaceJob *> (st + K::S_JOBS)};
+         mbar_wait (&bars[s], (it >> 1) & 1);
+         const TileDesc td = *reinterpret_cast<const TileDesc *> (st + K::S_TD);
+         K::work (1, A, td, v, nullptr, tid, true);
+         named_barrier<1, K::THREADS> ();
+         if (need_old) mbar_wait (&bars[4], it & 1);
+         K::work (2, A, td, v, nullptr, tid, true);
+         named_barrier<1, K::THREADS> ();
+         if (need_old && tid == 0) mbar_arrive (&bars[5]);
+         K::work (3, A, td, v, nullptr, tid, true);
+         mbar_arrive (&bars[2 + s]);
+      }
+   }
+#endif
 
    //---------------------------------------------------------------------------------------------
    // Cell averages of a solution vector (claw.cc:562-597), used after set_solution

@@ -57,6 +57,9 @@ namespace
             for (int p = 0; p < K::NPHASE; ++p)
                for (int t = 0; t < K::THREADS; ++t) K::phase (p, a, smem.data (), t, b);
       }
+      // the stage kernel: one tile per emulated block (the CUDA build pipelines tiles through a
+      // persistent kernel; the per-tile phase code is the same)
+      template <class K> void launch_stage (int n_tiles, const typename K::Args &a) { launch<K> (n_tiles, a); }
       template <class K> void launch1d (int n, const typename K::Args &a)
       {
          ++launches;
