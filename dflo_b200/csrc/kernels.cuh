@@ -119,6 +119,18 @@ namespace dflo
                     "DONE_%=:\n"
                     "}" ::"r"(smem_addr (bar)), "r"(parity) : "memory");
    }
+   // same, for a warp that has nothing else to do: let the hardware park it (suspend-time hint)
+   __device__ __forceinline__ void mbar_wait_parked (void *bar, unsigned parity)
+   {
+      asm volatile ("{\n"
+                    ".reg .pred p;\n"
+                    "WAIT_%=:\n"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+                    "@p bra DONE_%=;\n"
+                    "bra WAIT_%=;\n"
+                    "DONE_%=:\n"
+                    "}" ::"r"(smem_addr (bar)), "r"(parity), "r"(20000u) : "memory");
+   }
    __device__ __forceinline__ void bulk_g2s (void *dst, const void *src, unsigned bytes, void *bar)
    {
       asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr (dst)),
@@ -155,7 +167,7 @@ namespace dflo
 #define DFLO_STAGE_MIN_BLOCKS 4
 #endif
       static constexpr int MIN_BLOCKS = DFLO_STAGE_MIN_BLOCKS; // resident blocks per SM the register budget is held to
-      static constexpr int NPHASE = 4;
+      static constexpr int NPHASE = 6;
       static constexpr int FLUX_ID = FLUX;
       static constexpr int TAB = stage_table_size (BASIS, N1);
       // shared memory carve-up (in doubles); every bulk-copy destination is 16-byte aligned
@@ -249,8 +261,8 @@ namespace dflo
          work (p, A, A.tiles[bid], v, sm, tid, false);
       }
 
-      // p = 0: stage the tile (one-tile-per-block form only); 1: volume + face fluxes; 2: residual,
-      // M^-1, RK combine; 3: write back + cell averages.  `persistent`: called from the pipelined
+      // p = 0: stage the tile (one-tile-per-block form only); 1: volume fluxes + own traces; 2: face
+      // fluxes; 3: residual, M^-1, RK combine; 4: write back + row sums; 5: cell averages.  `persistent`: called from the pipelined
       // kernel below (inputs already staged by its producer warp, plain stores on the way out).
       static DFLO_DEV void work (int p, const Args &A, const TileDesc &td, const Views &v, double *sm, int tid, bool persistent)
       {
@@ -347,9 +359,28 @@ namespace dflo
                   sF[(slot * 8 + 4 + c) * NQ + lq] = Fy[c];
                }
             }
+            // ---- traces of the cell on its own four faces, one (face, point) per thread: each
+            //      half-warp reads one cell, which is free of shared-memory bank conflicts.  They
+            //      are parked in the slots the fluxes will overwrite (sH). ----
+            if (active)
+            {
+               const double *uc = su + slot * D;
+               for (int i = lq; i < 4 * N1; i += G)
+               {
+                  double W[4];
+                  trace (tb, uc, i / N1, i % N1, W);
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) sH[(slot * 4 * N1 + i) * 4 + c] = W[c];
+               }
+            }
+         }
+         else if (p == 2)
+         {
             // ---- faces: one numerical flux per UNIQUE face point of the tile, along the visiting
             //      cell's outward normal (assemble_explicit.cc:176-206, 303-341; periodic: src_mpi
-            //      186-260); a face shared by two cells of the tile serves both ----
+            //      186-260); a face shared by two cells of the tile serves both.  A job owns the
+            //      sH slots of its face point(s): it reads the traces parked there, then overwrites
+            //      them with the flux. ----
             const int njq = td.nj * N1;
             for (int idx = tid; idx < njq; idx += THREADS)
             {
@@ -360,7 +391,9 @@ namespace dflo
                const double nx = (f == 0) ? -1.0 : (f == 1) ? 1.0 : 0.0;
                const double ny = (f == 2) ? -1.0 : (f == 3) ? 1.0 : 0.0;
                double Wo[4], Wn[4], Ao[4], An[4], H[4];
-               trace (tb, su + sa * D, f, q, Wo);
+               double *ho = sH + ((sa * 4 + f) * N1 + q) * 4;
+#pragma unroll
+               for (int c = 0; c < 4; ++c) Wo[c] = ho[c];
                if (FLUX == FLUX_LXF) // the only flux that reads the cell averages (equation.h:357-359)
                {
 #pragma unroll
@@ -370,7 +403,13 @@ namespace dflo
                if (nb >= 0)
                {
                   const int qn = (fl & FACE_FLIP) ? N1 - 1 - q : q;
-                  if (job.slot_b >= 0)
+                  if (fl & JOB_SHARED)
+                  {
+                     const double *hn = sH + ((job.slot_b * 4 + (f ^ 1)) * N1 + qn) * 4;
+#pragma unroll
+                     for (int c = 0; c < 4; ++c) Wn[c] = hn[c];
+                  }
+                  else if (job.slot_b >= 0)
                      trace (tb, su + job.slot_b * D, f ^ 1, qn, Wn);
                   else
                      trace (tb, A.u + (size_t) nb * D, f ^ 1, qn, Wn);
@@ -412,15 +451,16 @@ namespace dflo
                const double sg = plus ? 1.0 : -1.0;
                numerical_flux<FLUX> (sg * nx, sg * ny, L, R, AL, AR, H);
 #pragma unroll
-               for (int c = 0; c < 4; ++c) sH[((sa * 4 + f) * N1 + q) * 4 + c] = sg * H[c];
+               for (int c = 0; c < 4; ++c) ho[c] = sg * H[c];
                if (fl & JOB_SHARED) // the neighbour's outward normal is -n
                {
+                  double *hn = sH + ((job.slot_b * 4 + (f ^ 1)) * N1 + q) * 4;
 #pragma unroll
-                  for (int c = 0; c < 4; ++c) sH[((job.slot_b * 4 + (f ^ 1)) * N1 + q) * 4 + c] = -(sg * H[c]);
+                  for (int c = 0; c < 4; ++c) hn[c] = -(sg * H[c]);
                }
             }
          }
-         else if (p == 2)
+         else if (p == 3)
          {
             if (!active || lq >= NS) return;
             const double hx = sGeom[slot * 4 + 2], hy = sGeom[slot * 4 + 3];
@@ -518,7 +558,7 @@ namespace dflo
             if (!persistent) fence_async_smem (); // make this thread's shared-memory writes visible to the bulk-copy engine
 #endif
          }
-         else // p == 3
+         else if (p == 4)
          {
             double *dst = A.out + (size_t) c0 * D;
 #if defined(__CUDA_ARCH__)
@@ -533,23 +573,37 @@ namespace dflo
 #else
             for (int i = tid; i < ncb * D; i += THREADS) dst[i] = su[i];
 #endif
+            // compute_cell_average of the updated solution, claw.cc:562-597, in two steps: weighted
+            // sums along x, one (cell, component, row) per thread (scratch = the flux array sF)
+            if (A.mode == MODE_STAGE && BASIS == BASIS_QK)
+            {
+               const double *gw = t_gw (tb);
+               for (int j = tid; j < ncb * 4 * N1; j += THREADS)
+               {
+                  const int b = j % N1, sc = j / N1; // sc = slot * 4 + component
+                  double r = 0.0;
+#pragma unroll
+                  for (int a = 0; a < N1; ++a) r = fma (gw[a], su[sc * NS + a + N1 * b], r);
+                  sF[j] = gw[b] * r;
+               }
+            }
+         }
+         else // p == 5
+         {
             if (A.mode == MODE_STAGE)
             {
-               // compute_cell_average of the updated solution, claw.cc:562-597
-               const double *gw = t_gw (tb);
                for (int j = tid; j < ncb * 4; j += THREADS)
                {
-                  const int s = j / 4, c = j % 4;
                   double v;
                   if (BASIS == BASIS_QK)
                   {
                      v = 0.0;
-                     for (int b = 0; b < N1; ++b)
-                        for (int a = 0; a < N1; ++a) v += gw[a] * gw[b] * su[s * D + c * NS + a + N1 * b];
+#pragma unroll
+                     for (int b = 0; b < N1; ++b) v += sF[j * N1 + b];
                   }
                   else
-                     v = su[s * D + c * NS];
-                  A.avg_out[(size_t) (c0 + s) * 4 + c] = v;
+                     v = su[(j / 4) * D + (j % 4) * NS];
+                  A.avg_out[(size_t) c0 * 4 + j] = v;
                }
             }
 #if defined(__CUDA_ARCH__)
@@ -599,7 +653,7 @@ namespace dflo
          {
             const int s = it & 1;
             double *st = sm + K::P_STAGE + s * K::STAGE_DOUBLES;
-            if (it >= 2) mbar_wait (&bars[2 + s], ((it >> 1) - 1) & 1);
+            if (it >= 2) mbar_wait_parked (&bars[2 + s], ((it >> 1) - 1) & 1);
             const TileDesc td = A.tiles[t];
             if (lane == 0)
             {
@@ -621,7 +675,7 @@ namespace dflo
             }
             if (need_old)
             {
-               if (it >= 1) mbar_wait (&bars[5], (it - 1) & 1);
+               if (it >= 1) mbar_wait_parked (&bars[5], (it - 1) & 1);
                if (lane == 0)
                {
                   mbar_expect_tx (&bars[4], (unsigned) td.ncb * cell_bytes);
@@ -644,11 +698,17 @@ namespace dflo
          const TileDesc td = *reinterpret_cast<const TileDesc *> (st + K::S_TD);
          K::work (1, A, td, v, nullptr, tid, true);
          named_barrier<1, K::THREADS> ();
-         if (need_old) mbar_wait (&bars[4], it & 1);
          K::work (2, A, td, v, nullptr, tid, true);
          named_barrier<1, K::THREADS> ();
-         if (need_old && tid == 0) mbar_arrive (&bars[5]);
+         if (need_old) mbar_wait (&bars[4], it & 1);
          K::work (3, A, td, v, nullptr, tid, true);
+         named_barrier<1, K::THREADS> ();
+         if (need_old && tid == 0) mbar_arrive (&bars[5]);
+         K::work (4, A, td, v, nullptr, tid, true);
+         named_barrier<1, K::THREADS> ();
+         K::work (5, A, td, v, nullptr, tid, true);
+         // the next tile's phase 1 writes sF, which phase 5 is still reading in slower warps
+         named_barrier<1, K::THREADS> ();
          mbar_arrive (&bars[2 + s]);
       }
    }
