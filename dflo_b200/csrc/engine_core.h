@@ -325,7 +325,7 @@ namespace dflo
       double *rhs = nullptr;
       double *d_time = nullptr;       // t, dt, dt accumulator, final time
       double *d_scratch = nullptr;    // [1] reductions
-      int *d_nbr = nullptr, *d_halo_cells = nullptr;
+      int *d_nbr = nullptr, *d_halo_cells = nullptr, *d_rowdesc = nullptr;
       FaceJob *d_jobs = nullptr;
       TileDesc *d_tiles = nullptr;
       unsigned char *d_fflags = nullptr;
@@ -365,7 +365,13 @@ namespace dflo
          else { n_rk = 3; ark[0] = 0.0; ark[1] = 3.0 / 4.0; ark[2] = 1.0 / 3.0; }
          const int layers = tvb () ? 2 : 1;
          std::string e;
-         if (!build_local_mesh (mesh, rank, world, layers, tile_nx (tab.n1), tile_ny (tab.n1), lm, e)) return fail (DFLO_E_INVALID, e);
+         // stage-kernel flavour decides the tile shape: register-blocked row kernel (Qk, CUDA) or the
+         // generic phase kernel
+         const bool row = bk.use_row_kernel (tab.basis, tab.n1);
+         const int tx = row ? row_tx (tab.n1) : tile_nx (tab.n1), ty = row ? row_ty (tab.n1) : tile_ny (tab.n1);
+         if (!build_local_mesh (mesh, rank, world, layers, tx, ty, lm, e, row)) return fail (DFLO_E_INVALID, e);
+         bk.prepare_tables (tab);
+         if (row) d_rowdesc = upload (lm.rowdesc);
          n_global_bfaces = mesh.n_boundary_faces;
 
          const size_t nd = (size_t) lm.n_local * D ();
@@ -438,7 +444,7 @@ namespace dflo
             bk.free (AVG[i]);
          }
          void *ptrs[] = {rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
-                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles};
+                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles, d_rowdesc};
          for (void *p : ptrs) bk.free (p);
          for (int k = 0; k < 2; ++k)
          {
@@ -747,6 +753,7 @@ namespace dflo
          a.tab = d_stage_tab;
          a.time = d_time;
          a.dt_cell = nullptr;
+         a.rowdesc = d_rowdesc;
          a.mode = mode;
          a.compat_mpi = prm.compat == DFLO_COMPAT_MPI;
          a.ark = ark[rk];

@@ -5,6 +5,7 @@
 // RK stage on the same stream.  There is no CPU fallback: without a CUDA device create() returns
 // DFLO_E_NO_DEVICE.
 #include "abi_impl.h"
+#include "row_kernel.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -103,6 +104,7 @@ namespace
       ncclComm_t comm = nullptr;
       bool use_graphs = true;
       bool persistent = true;
+      bool row_kernel = true;  // register-blocked stage kernel for Qk (row_kernel.cuh); DFLO_B200_STAGE=tile selects the phase kernel
       int n_sm = 148;
       bool capturing = false;
       struct Graph
@@ -147,6 +149,8 @@ namespace
          note (cudaDeviceGetAttribute (&n_sm, cudaDevAttrMultiProcessorCount, device));
          const char *ps = std::getenv ("DFLO_B200_PERSISTENT");
          persistent = ps ? (std::atoi (ps) != 0) : true;
+         const char *sk = std::getenv ("DFLO_B200_STAGE");
+         row_kernel = !(sk && std::string (sk) == "tile");
          const char *g = std::getenv ("DFLO_B200_GRAPHS");
          use_graphs = g ? (std::atoi (g) != 0) : true;
          if (world > 1)
@@ -239,9 +243,44 @@ namespace
       }
       // The stage kernel.  Default: the pipelined persistent form (one producer warp streaming tiles
       // through two shared-memory stages); DFLO_B200_PERSISTENT=0 selects the one-tile-per-block form.
+      bool use_row_kernel (int basis, int n1) const { return row_kernel && basis == dflo::BASIS_QK && n1 >= 2; }
+      // 1-D tables of the row kernel as constant-bank operands
+      void prepare_tables (const dflo::FeTables &t)
+      {
+         if (t.basis != dflo::BASIS_QK) return;
+         dflo::RowConst rc;
+         std::memset (&rc, 0, sizeof (rc));
+         for (int i = 0; i < t.n1; ++i)
+         {
+            for (int j = 0; j < t.n1; ++j) rc.dw[i][j] = t.dw[i][j];
+            rc.e0[i] = t.e[0][i];
+            rc.e1[i] = t.e[1][i];
+            rc.gw[i] = t.gw[i];
+         }
+         note (cudaMemcpyToSymbolAsync (dflo::c_row, &rc, sizeof (rc), (size_t) t.n1 * sizeof (rc), cudaMemcpyHostToDevice, stream));
+         note (cudaStreamSynchronize (stream));
+      }
+      template <int N1, int FLUX> void launch_row (int n_tiles, const dflo::StageArgs &a)
+      {
+         typedef dflo::RowShape<N1, FLUX> S;
+         constexpr size_t smem = S::SMEM_DOUBLES * sizeof (double);
+         static const cudaError_t rc = cudaFuncSetAttribute (dflo::row_stage_kernel<N1, FLUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+         note (rc);
+         ++launches;
+         dflo::row_stage_kernel<N1, FLUX><<<n_tiles, S::THREADS, smem, stream>>> (a);
+         note (cudaPeekAtLastError ());
+      }
       template <class K> void launch_stage (int n_tiles, const typename K::Args &a)
       {
          if (n_tiles <= 0) return;
+         if constexpr (K::BASIS_ID == dflo::BASIS_QK && K::N1_ID >= 2)
+         {
+            if (row_kernel)
+            {
+               launch_row<K::N1_ID, K::FLUX_ID> (n_tiles, a);
+               return;
+            }
+         }
          if (!persistent)
          {
             launch<K> (n_tiles, a);

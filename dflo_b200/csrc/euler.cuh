@@ -331,6 +331,284 @@ namespace dflo
          hllc_flux (nx, ny, Wp, Wm, H);
    }
 
+   //---------------------------------------------------------------------------------------------
+   // Axis-aligned forms.  On the Cartesian cells the engine accepts every face normal is +-e_x or
+   // +-e_y, and every flux of claw.h:271-325 is antisymmetric, H(-n, Wb, Wa) = -H(n, Wa, Wb), so a
+   // face is always solved along +e_x (or +e_y, by exchanging the two momentum components) with
+   // the LOW-side cell's trace as the first state.  These are the general formulas above with
+   // n = (1,0) substituted (x*1 = x, x*0 = 0 exactly) and the vanishing terms dropped.
+   //---------------------------------------------------------------------------------------------
+   // s = sqrt(x) and r = 1/x from ONE reciprocal-square-root seed
+   DFLO_HD void sqrt_and_rcp (double x, double &s, double &r)
+   {
+#if defined(__CUDA_ARCH__)
+      const double y = fast_rsqrt (x);
+      const double s0 = x * y;
+      s = fma (fma (-s0, s0, x), 0.5 * y, s0);
+      r = y * y;
+#else
+      s = sqrt (x);
+      r = 1.0 / x;
+#endif
+   }
+
+   // equation.h:158-193, x column only: F_x(W)
+   DFLO_HD void flux_x (const double W[4], double Fx[4])
+   {
+      const double r = fast_rcp (W[RHO]);
+      const double u = W[0] * r, v = W[1] * r;
+      const double p = GM1 * (W[ENE] - 0.5 * (W[0] * u + W[1] * v));
+      Fx[0] = W[0] * u + p;
+      Fx[1] = W[1] * u;
+      Fx[RHO] = W[0];
+      Fx[ENE] = u * (W[ENE] + p);
+   }
+
+   DFLO_HD double max_eigenvalue_x (const double A[4])
+   {
+      const double r = fast_rcp (A[RHO]);
+      const double p = GM1 * (A[ENE] - 0.5 * (A[0] * A[0] + A[1] * A[1]) * r);
+      return fabs (A[0] * r) + fast_sqrt (GAMMA * p * r);
+   }
+
+   DFLO_HD void lxf_flux_x (const double Wp[4], const double Wm[4], const double Ap[4], const double Am[4], double H[4])
+   {
+      const double rp = fast_rcp (Wp[RHO]), rm = fast_rcp (Wm[RHO]);
+      const double vnp = Wp[0] * rp, vnm = Wm[0] * rm;
+      const double pp = GM1 * (Wp[ENE] - 0.5 * (Wp[0] * Wp[0] + Wp[1] * Wp[1]) * rp);
+      const double pm = GM1 * (Wm[ENE] - 0.5 * (Wm[0] * Wm[0] + Wm[1] * Wm[1]) * rm);
+      const double lambda = std_max (max_eigenvalue_x (Ap), max_eigenvalue_x (Am));
+      H[0] = 0.5 * ((pp + pm) + Wp[0] * vnp + Wm[0] * vnm + lambda * (Wp[0] - Wm[0]));
+      H[1] = 0.5 * (Wp[1] * vnp + Wm[1] * vnm + lambda * (Wp[1] - Wm[1]));
+      H[RHO] = 0.5 * (Wp[RHO] * vnp + Wm[RHO] * vnm + lambda * (Wp[RHO] - Wm[RHO]));
+      H[ENE] = 0.5 * ((Wp[ENE] + pp) * vnp + (Wm[ENE] + pm) * vnm + lambda * (Wp[ENE] - Wm[ENE]));
+   }
+
+   DFLO_HD void steger_warming_flux_x (const double Wp[4], const double Wm[4], double H[4])
+   {
+      const double rp = fast_rcp (Wp[RHO]), rm = fast_rcp (Wm[RHO]);
+      const double up = Wp[0] * rp, vp = Wp[1] * rp, um = Wm[0] * rm, vm = Wm[1] * rm;
+      const double q2p = up * up + vp * vp, q2m = um * um + vm * vm;
+      const double pp = GM1 * (Wp[ENE] - 0.5 * Wp[RHO] * q2p);
+      const double pm = GM1 * (Wm[ENE] - 0.5 * Wm[RHO] * q2m);
+      const double cp = fast_sqrt (GAMMA * pp * rp), cm = fast_sqrt (GAMMA * pm * rm);
+      const double l1p = std_max (up, 0.0), l2p = std_max (up + cp, 0.0), l3p = std_max (up - cp, 0.0);
+      const double ap = 2.0 * GM1 * l1p + l2p + l3p;
+      const double fp = 0.5 * Wp[RHO] / GAMMA;
+      const double l1m = std_min (um, 0.0), l2m = std_min (um + cm, 0.0), l3m = std_min (um - cm, 0.0);
+      const double am = 2.0 * GM1 * l1m + l2m + l3m;
+      const double fm = 0.5 * Wm[RHO] / GAMMA;
+      const double dlp = cp * (l2p - l3p), dlm = cm * (l2m - l3m);
+      H[0] = fp * (ap * up + dlp) + fm * (am * um + dlm);
+      H[1] = fp * (ap * vp) + fm * (am * vm);
+      H[RHO] = fp * ap + fm * am;
+      H[ENE] = fp * (0.5 * ap * q2p + up * dlp + cp * cp * (l2p + l3p) / GM1)
+               + fm * (0.5 * am * q2m + um * dlm + cm * cm * (l2m + l3m) / GM1);
+   }
+
+   DFLO_HD void roe_flux_x (const double Wl[4], const double Wr[4], double H[4])
+   {
+      double sl, rl, sr, rr;
+      sqrt_and_rcp (Wl[RHO], sl, rl);
+      sqrt_and_rcp (Wr[RHO], sr, rr);
+      const double fl = sl * fast_rcp (sl + sr), fr = 1.0 - fl;
+      const double ul = Wl[0] * rl, vl = Wl[1] * rl, ur = Wr[0] * rr, vr = Wr[1] * rr;
+      const double v2l = ul * ul + vl * vl, v2r = ur * ur + vr * vr;
+      const double u = ul * fl + ur * fr, v = vl * fl + vr * fr;
+      const double v2 = u * u + v * v;
+      const double du = ur - ul, dv = vr - vl;
+      const double pl = GM1 * (Wl[ENE] - 0.5 * Wl[RHO] * v2l);
+      const double pr = GM1 * (Wr[ENE] - 0.5 * Wr[RHO] * v2r);
+      const double hl = (GAMMA / GM1) * pl * rl + 0.5 * v2l;
+      const double hr = (GAMMA / GM1) * pr * rr + 0.5 * v2r;
+      const double dens = sl * sr;
+      const double h = hl * fl + hr * fr;
+      const double c2 = GM1 * (h - 0.5 * v2);
+      double c, ic2;
+      sqrt_and_rcp (c2, c, ic2);
+      const double drho = Wr[RHO] - Wl[RHO], dp = pr - pl;
+      const double t = dens * c * du;
+      const double a1 = (dp - t) * (0.5 * ic2);
+      const double a2 = drho - dp * ic2;
+      const double a3 = (dp + t) * (0.5 * ic2);
+      double l1 = fabs (u - c), l3 = fabs (u + c);
+      const double l2 = fabs (u);
+      const double delta = 0.1 * c;            // Harten fix on the acoustic waves only (528-531)
+      const double idelta = 10.0 * (c * ic2);  // 1 / delta
+      if (l1 < delta) l1 = 0.5 * (l1 * l1 * idelta + delta);
+      if (l3 < delta) l3 = 0.5 * (l3 * l3 * idelta + delta);
+      const double w1 = l1 * a1, w2 = l2 * a2, w3 = l3 * a3, w4 = l2 * dens;
+      const double Drho = w1 + w2 + w3;
+      const double cu = c * u;
+      const double Dene = w1 * (h - cu) + w2 * 0.5 * v2 + w4 * (v * dv) + w3 * (h + cu);
+      const double D0 = (u - c) * w1 + u * w2 + (u + c) * w3;
+      const double D1 = v * Drho + dv * w4;
+      H[RHO] = 0.5 * (Wl[0] + Wr[0] - Drho);
+      H[ENE] = 0.5 * ((Wl[ENE] + pl) * ul + (Wr[ENE] + pr) * ur - Dene);
+      H[0] = 0.5 * (pl + pr) + 0.5 * (Wl[0] * ul + Wr[0] * ur) - 0.5 * D0;
+      H[1] = 0.5 * (Wl[1] * ul + Wr[1] * ur) - 0.5 * D1;
+   }
+
+   DFLO_HD void hllc_flux_x (const double Wl[4], const double Wr[4], double H[4])
+   {
+      double sql, rl, sqr, rr;
+      sqrt_and_rcp (Wl[RHO], sql, rl);
+      sqrt_and_rcp (Wr[RHO], sqr, rr);
+      const double fl = sql * fast_rcp (sql + sqr), fr = 1.0 - fl;
+      const double ul = Wl[0] * rl, vl = Wl[1] * rl, ur = Wr[0] * rr, vr = Wr[1] * rr;
+      const double v2l = ul * ul + vl * vl, v2r = ur * ur + vr * vr;
+      const double u = ul * fl + ur * fr, v = vl * fl + vr * fr;
+      const double v2 = u * u + v * v;
+      const double pl = GM1 * (Wl[ENE] - 0.5 * Wl[RHO] * v2l);
+      const double pr = GM1 * (Wr[ENE] - 0.5 * Wr[RHO] * v2r);
+      const double hl = (Wl[ENE] + pl) * rl, hr = (Wr[ENE] + pr) * rr;
+      const double cl = fast_sqrt (GAMMA * pl * rl), cr = fast_sqrt (GAMMA * pr * rr);
+      const double h = hl * fl + hr * fr;
+      const double c = fast_sqrt (GM1 * (h - 0.5 * v2));
+      const double s_l = std_min (u - c, ul - cl);
+      const double s_r = std_max (u + c, ur + cr);
+      const double ml = Wl[RHO] * (s_l - ul), mr = Wr[RHO] * (s_r - ur);
+      const double s_m = (pl - pr - ml * ul + mr * ur) * fast_rcp (mr - ml);
+      const double ps = Wr[RHO] * (ur - s_r) * (ur - s_m) + pr;
+      if (s_m >= 0.0)
+      {
+         if (s_l > 0.0)
+         {
+            H[RHO] = Wl[RHO] * ul;
+            H[0] = Wl[0] * ul + pl;
+            H[1] = Wl[1] * ul;
+            H[ENE] = (Wl[ENE] + pl) * ul;
+         }
+         else
+         {
+            const double inv = fast_rcp (s_l - s_m);
+            const double smu = s_l - ul;
+            H[RHO] = Wl[RHO] * smu * inv * s_m;
+            H[0] = (Wl[0] * smu + (ps - pl)) * inv * s_m + ps;
+            H[1] = (Wl[1] * smu) * inv * s_m;
+            H[ENE] = ((smu * Wl[ENE] - pl * ul + ps * s_m) * inv + ps) * s_m;
+         }
+      }
+      else
+      {
+         if (s_r >= 0.0)
+         {
+            const double inv = fast_rcp (s_r - s_m);
+            const double smu = s_r - ur;
+            H[RHO] = Wr[RHO] * smu * inv * s_m;
+            H[0] = (Wr[0] * smu + (ps - pr)) * inv * s_m + ps;
+            H[1] = (Wr[1] * smu) * inv * s_m;
+            H[ENE] = ((smu * Wr[ENE] - pr * ur + ps * s_m) * inv + ps) * s_m;
+         }
+         else
+         {
+            H[RHO] = Wr[RHO] * ur;
+            H[0] = Wr[0] * ur + pr;
+            H[1] = Wr[1] * ur;
+            H[ENE] = (Wr[ENE] + pr) * ur;
+         }
+      }
+   }
+
+   DFLO_HD void kinetic_split_flux_x (double sign, const double W[4], double H[4])
+   {
+      const double r = fast_rcp (W[RHO]);
+      const double vn = W[0] * r;
+      const double p = GM1 * (W[ENE] - 0.5 * (W[0] * W[0] + W[1] * W[1]) * r);
+      const double beta = 0.5 * W[RHO] * fast_rcp (p);
+      const double sb = fast_sqrt (beta);
+      const double s = vn * sb;
+      const double ex = exp (-s * s);
+      const double x = fabs (s);
+      const double t = fast_rcp (1.0 + 0.3275911 * x);
+      const double y = 1.0
+                       - (((((1.061405429 * t + -1.453152027) * t) + 1.421413741) * t + -0.284496736) * t + 0.254829592)
+                            * t * ex;
+      const double erf_s = (s < 0) ? -y : y;
+      const double A = 0.5 * (1.0 + sign * erf_s);
+      const double B = 0.5 * sign * ex * fast_rcp (1.7724538509055160273 * sb);
+      const double uf = vn * A + B;
+      H[0] = p * A + W[0] * uf;
+      H[1] = W[1] * uf;
+      H[RHO] = W[RHO] * uf;
+      H[ENE] = (W[ENE] + p) * vn * A + (W[ENE] + 0.5 * p) * B;
+   }
+
+   DFLO_HD void kfvs_flux_x (const double Wp[4], const double Wm[4], double H[4])
+   {
+      double pf[4], mf[4];
+      kinetic_split_flux_x (+1.0, Wp, pf);
+      kinetic_split_flux_x (-1.0, Wm, mf);
+      for (int c = 0; c < 4; ++c) H[c] = pf[c] + mf[c];
+   }
+
+   // Numerical flux along +e_DIR (DIR = 0: x, 1: y) between the low-side state Wl and the
+   // high-side state Wr; Al, Ar = the two cell averages (read by LxF only).  The y form is the x
+   // form with the momentum components exchanged on the way in and out.
+   template <int FLUX, int DIR>
+   DFLO_HD void numerical_flux_axis (const double Wl[4], const double Wr[4], const double Al[4], const double Ar[4], double H[4])
+   {
+      const double L[4] = {Wl[DIR], Wl[1 - DIR], Wl[RHO], Wl[ENE]};
+      const double R[4] = {Wr[DIR], Wr[1 - DIR], Wr[RHO], Wr[ENE]};
+      double G[4];
+      if (FLUX == FLUX_LXF)
+      {
+         const double AL[4] = {Al[DIR], Al[1 - DIR], Al[RHO], Al[ENE]};
+         const double AR[4] = {Ar[DIR], Ar[1 - DIR], Ar[RHO], Ar[ENE]};
+         lxf_flux_x (L, R, AL, AR, G);
+      }
+      else if (FLUX == FLUX_SW)
+         steger_warming_flux_x (L, R, G);
+      else if (FLUX == FLUX_KFVS)
+         kfvs_flux_x (L, R, G);
+      else if (FLUX == FLUX_ROE)
+         roe_flux_x (L, R, G);
+      else
+         hllc_flux_x (L, R, G);
+      H[DIR] = G[0];
+      H[1 - DIR] = G[1];
+      H[RHO] = G[RHO];
+      H[ENE] = G[ENE];
+   }
+
+   // The flux through a face with normal direction e_DIR exactly as the reference evaluates it:
+   // numerical_normal_flux (n, W+, W-) with W+ the trace of the cell that integrates the face
+   // ("plus") and n its outward normal.  plus_low: that cell is the one on the low-coordinate side
+   // (n = +e_DIR); otherwise n = -e_DIR, which is the +e_DIR problem mirrored in DIR (normal
+   // momentum negated on the way in and out -- every intermediate is identical or negated, so
+   // the result is bit-for-bit the mirrored one).  Returns the flux along +e_DIR.
+   template <int FLUX, int DIR>
+   DFLO_HD void face_flux_axis (bool plus_low, const double Wlo[4], const double Whi[4], const double Alo[4], const double Ahi[4],
+                                double H[4])
+   {
+      const double sg = plus_low ? 1.0 : -1.0;
+      double P[4], M[4], AP[4], AM[4], G[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+      {
+         P[c] = plus_low ? Wlo[c] : Whi[c];
+         M[c] = plus_low ? Whi[c] : Wlo[c];
+      }
+      P[DIR] *= sg;
+      M[DIR] *= sg;
+      if (FLUX == FLUX_LXF)
+      {
+#pragma unroll
+         for (int c = 0; c < 4; ++c)
+         {
+            AP[c] = plus_low ? Alo[c] : Ahi[c];
+            AM[c] = plus_low ? Ahi[c] : Alo[c];
+         }
+         AP[DIR] *= sg;
+         AM[DIR] *= sg;
+      }
+      numerical_flux_axis<FLUX, DIR> (P, M, AP, AM, G);
+      // reference flux along n = sg*e_DIR is (sg*G[DIR], G[others]); along +e_DIR: times sg
+#pragma unroll
+      for (int c = 0; c < 4; ++c) H[c] = sg * G[c];
+      H[DIR] = G[DIR];
+   }
+
    // equation.h:939-1033
    DFLO_HD void compute_wminus (int kind, double nx, double ny, const double Wp[4], const double g[4], double Wm[4])
    {

@@ -89,6 +89,7 @@ namespace dflo
       const double *tab;      // flat stage tables
       const double *time;     // device scalars: [0] elapsed time, [1] dt
       const double *dt_cell;  // optional per-cell dt (local time stepping), else nullptr
+      const int *rowdesc;     // tile descriptors of the register-blocked Qk kernel (row_desc.h), or nullptr
       int mode;
       int compat_mpi;
       double ark;
@@ -169,6 +170,8 @@ namespace dflo
       static constexpr int MIN_BLOCKS = DFLO_STAGE_MIN_BLOCKS; // resident blocks per SM the register budget is held to
       static constexpr int NPHASE = 6;
       static constexpr int FLUX_ID = FLUX;
+      static constexpr int BASIS_ID = BASIS;
+      static constexpr int N1_ID = N1;
       static constexpr int TAB = stage_table_size (BASIS, N1);
       // shared memory carve-up (in doubles); every bulk-copy destination is 16-byte aligned
       static constexpr int O_TAB = 2;                                // [0,2): the mbarrier

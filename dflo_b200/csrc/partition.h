@@ -24,6 +24,7 @@
 #pragma once
 
 #include "../../include/dflo_b200.h"
+#include "row_desc.h"
 
 #include <algorithm>
 #include <cmath>
@@ -63,6 +64,10 @@ namespace dflo
       std::vector<int> halo_cells;   // local cell ids staged after the tile's own cells
       std::vector<int> job_start;    // [n_tiles+1] into jobs (in units of jobs)
       std::vector<int> jobs;         // 4 ints per unique face, see FaceJob in kernels.cuh
+
+      // descriptors of the register-blocked Qk stage kernel (row_desc.h), rowdesc_stride ints per tile
+      std::vector<int> rowdesc;
+      int rowdesc_stride = 0;
    };
 
    constexpr int JOB_SHARED_FLAG = 8; // job flag beside DFLO_FACE_* (kernels.cuh JOB_SHARED): the flux also serves the neighbour slot
@@ -240,8 +245,137 @@ namespace dflo
       }
    }
 
+   // Does tile t respect the capacities of the row kernel (staged halo cells, L jobs, G jobs <= cap)?
+   inline bool row_tile_fits (const LocalMesh &L, int t, int cap)
+   {
+      int nL = 0, nG = 0;
+      for (int j = L.job_start[t]; j < L.job_start[t + 1]; ++j)
+      {
+         const int a = L.jobs[4 * (size_t) j], nb = L.jobs[4 * (size_t) j + 1], slot_b = L.jobs[4 * (size_t) j + 2];
+         const int flags = L.jobs[4 * (size_t) j + 3];
+         if (flags & JOB_SHARED_FLAG) continue;
+         const bool high = (a & 1) != 0;
+         if (nb >= 0)
+         {
+            if (slot_b < 0) return false; // neighbour beyond the staged halo
+            if (high) ++nG; else ++nL;
+         }
+         else if (!high)
+            ++nL;
+      }
+      return nL <= cap && nG <= cap;
+   }
+
+   // Tile jobs for the row kernel: tiles that overflow its capacities (ragged tiles of general
+   // meshes, the strip-shaped tiles of a redundantly updated ghost layer) are halved until they fit.
+   inline void build_tiles_for_row (LocalMesh &L, int cap)
+   {
+      for (;;)
+      {
+         build_tile_jobs (L);
+         std::vector<int> ts (1, 0);
+         int owned = 0;
+         bool split = false;
+         for (int t = 0; t < L.n_tiles; ++t)
+         {
+            const int c0 = L.tile_start[t], c1 = L.tile_start[t + 1];
+            int pieces = 1;
+            if (c1 - c0 > 1 && !row_tile_fits (L, t, cap))
+            {
+               ts.push_back (c0 + (c1 - c0) / 2);
+               pieces = 2;
+               split = true;
+            }
+            ts.push_back (c1);
+            if (t < L.n_tiles_owned) owned += pieces;
+         }
+         if (!split) return;
+         L.tile_start = ts;
+         L.n_tiles_owned = owned;
+      }
+   }
+
+   // Row-kernel descriptors (row_desc.h) from the generic unique-face lists
+   inline bool build_row_desc (LocalMesh &L, int tc, int nh, std::string &err)
+   {
+      const int stride = rowd_ints (tc, nh);
+      L.rowdesc_stride = stride;
+      L.rowdesc.assign ((size_t) std::max (1, L.n_tiles) * stride, 0);
+      const int UNSET = 0x7fffffff;
+      for (int t = 0; t < L.n_tiles; ++t)
+      {
+         int *d = &L.rowdesc[(size_t) t * stride];
+         const int c0 = L.tile_start[t], ncb = L.tile_start[t + 1] - c0;
+         const int nhl = L.halo_start[t + 1] - L.halo_start[t];
+         int *halo = d + rowd_off_halo (), *nbhi = d + rowd_off_nbhi (nh), *lj = d + rowd_off_ljob (tc, nh), *gj = d + rowd_off_gjob (tc, nh);
+         for (int i = 0; i < nhl; ++i) halo[i] = L.halo_cells[L.halo_start[t] + i];
+         for (int i = 0; i < 2 * tc; ++i) nbhi[i] = UNSET;
+         int nL = 0, nG = 0;
+         for (int j = L.job_start[t]; j < L.job_start[t + 1]; ++j)
+         {
+            const int a = L.jobs[4 * (size_t) j], nb = L.jobs[4 * (size_t) j + 1], slot_b = L.jobs[4 * (size_t) j + 2];
+            const int flags = L.jobs[4 * (size_t) j + 3];
+            const int sa = a >> 2, f = a & 3, dir = f >> 1;
+            const bool high = (f & 1) != 0;
+            const bool plus_own = nb < 0 || (flags & (DFLO_FACE_OWNER | DFLO_FACE_PERIODIC));
+            const int flip = (flags & DFLO_FACE_FLIP) ? ROWD_FLIP : 0;
+            if (flags & JOB_SHARED_FLAG)
+            {
+               // listed from the owner (plus) cell sa; the low-side cell's thread solves it
+               const int lo = high ? sa : slot_b, hi = high ? slot_b : sa;
+               nbhi[2 * lo + dir] = hi | (high ? ROWD_PLUS : 0);
+            }
+            else if (nb >= 0)
+            {
+               if (slot_b < 0 || nL >= nh || nG >= nh)
+               {
+                  err = "internal: row-kernel tile exceeds its capacities";
+                  return false;
+               }
+               if (high)
+               {
+                  gj[nG] = slot_b | (dir << 16) | flip;
+                  nbhi[2 * sa + dir] = (tc + nG) | (plus_own ? ROWD_PLUS : 0);
+                  ++nG;
+               }
+               else
+               {
+                  lj[2 * nL] = (2 * sa + dir) | (plus_own ? ROWD_PLUS : 0) | flip;
+                  lj[2 * nL + 1] = slot_b;
+                  ++nL;
+               }
+            }
+            else if (high)
+               nbhi[2 * sa + dir] = nb; // -1 - local boundary face
+            else
+            {
+               if (nL >= nh)
+               {
+                  err = "internal: row-kernel tile exceeds its capacities";
+                  return false;
+               }
+               lj[2 * nL] = (2 * sa + dir) | ROWD_PLUS;
+               lj[2 * nL + 1] = nb;
+               ++nL;
+            }
+         }
+         for (int i = 0; i < 2 * ncb; ++i)
+            if (nbhi[i] == UNSET)
+            {
+               err = "internal: a high face of a tile cell has no agent";
+               return false;
+            }
+         d[0] = c0;
+         d[1] = ncb;
+         d[2] = nhl;
+         d[3] = nL;
+         d[4] = nG;
+      }
+      return true;
+   }
+
    inline bool build_local_mesh (const dflo_flat_mesh &m, int rank, int world, int layers, int tile_x, int tile_y,
-                                 LocalMesh &L, std::string &err)
+                                 LocalMesh &L, std::string &err, bool row = false)
    {
       if (world < 1 || rank < 0 || rank >= world || m.n_cells < world)
       {
@@ -322,7 +456,13 @@ namespace dflo
                L.nbr[4 * (size_t) l + f] = l; // never evaluated
          }
       }
-      build_tile_jobs (L);
+      if (row)
+      {
+         build_tiles_for_row (L, L.tile_halo_max);
+         if (!build_row_desc (L, L.tile_cells, L.tile_halo_max, err)) return false;
+      }
+      else
+         build_tile_jobs (L);
       if (world == 1) return true;
 
       // Halo lists.  What we receive: our ghosts, grouped by owner.  What we send to peer p: the

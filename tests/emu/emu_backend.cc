@@ -60,6 +60,9 @@ namespace
       // the stage kernel: one tile per emulated block (the CUDA build pipelines tiles through a
       // persistent kernel; the per-tile phase code is the same)
       template <class K> void launch_stage (int n_tiles, const typename K::Args &a) { launch<K> (n_tiles, a); }
+      // the register-blocked Qk kernel exists only as CUDA code; the emulation runs the phase kernel
+      bool use_row_kernel (int, int) const { return false; }
+      void prepare_tables (const dflo::FeTables &) {}
       template <class K> void launch1d (int n, const typename K::Args &a)
       {
          ++launches;
@@ -116,6 +119,74 @@ int dflo_emu_n_local (dflo_emu_ctx *c) { return c->eng.lm.n_local; }
 int dflo_emu_n_compute (dflo_emu_ctx *c) { return c->eng.lm.n_compute; }
 }
 
+// Host-side check of the row-kernel tile descriptors (row_desc.h): rebuilds the local mesh the way
+// the CUDA backend does for a Qk context and verifies that every face of every computed cell has
+// exactly one agent, pointing at the right neighbour with the right "plus" side.  Returns the
+// number of inconsistencies (0 = ok), -1 if the mesh could not be built.
+extern "C" int dflo_emu_rowdesc_check (const dflo_flat_mesh *mesh, int n1, int rank, int world, int layers, int *n_tiles_out)
+{
+   using namespace dflo;
+   LocalMesh L;
+   std::string err;
+   const int tc = row_tc (n1), nh = row_nh (n1);
+   if (!build_local_mesh (*mesh, rank, world, layers, row_tx (n1), row_ty (n1), L, err, true)) return -1;
+   if (n_tiles_out) *n_tiles_out = L.n_tiles;
+   int bad = 0;
+   std::vector<int> covered ((size_t) L.n_local * 4, 0);
+   for (int t = 0; t < L.n_tiles; ++t)
+   {
+      const int *d = &L.rowdesc[(size_t) t * L.rowdesc_stride];
+      const int c0 = d[0], ncb = d[1], nhl = d[2], nL = d[3], nG = d[4];
+      const int *halo = d + rowd_off_halo (), *nbhi = d + rowd_off_nbhi (nh), *lj = d + rowd_off_ljob (tc, nh), *gj = d + rowd_off_gjob (tc, nh);
+      if (c0 != L.tile_start[t] || ncb != L.tile_start[t + 1] - c0 || ncb > tc || nhl > nh || nL > nh || nG > nh) ++bad;
+      auto su_cell = [&] (int slot) { return slot < tc ? c0 + slot : halo[slot - tc]; };
+      auto expect_plus = [&] (int cell, int f) {
+         const int nb = L.nbr[4 * (size_t) cell + f];
+         return nb < 0 || (L.fflags[4 * (size_t) cell + f] & (DFLO_FACE_OWNER | DFLO_FACE_PERIODIC)) != 0;
+      };
+      for (int s = 0; s < ncb; ++s)
+         for (int dir = 0; dir < 2; ++dir)
+         {
+            const int cell = c0 + s, f = 2 * dir + 1, code = nbhi[2 * s + dir];
+            const int nb = L.nbr[4 * (size_t) cell + f];
+            ++covered[4 * (size_t) cell + f];
+            if (code < 0) { if (code != nb) ++bad; continue; }
+            const int idx = code & 0xffff;
+            const bool plus = (code & ROWD_PLUS) != 0;
+            if (plus != expect_plus (cell, f)) ++bad;
+            if (idx < tc)
+            {
+               if (c0 + idx != nb || idx >= ncb) ++bad;
+               if (L.fflags[4 * (size_t) cell + f] & DFLO_FACE_PERIODIC) ++bad; // periodic partners go through ghost slots
+               ++covered[4 * (size_t) nb + (f ^ 1)];
+            }
+            else
+            {
+               const int g = idx - tc;
+               if (g >= nG) { ++bad; continue; }
+               if (su_cell (gj[g] & 0xffff) != nb || ((gj[g] >> 16) & 1) != dir) ++bad;
+               if (((gj[g] & ROWD_FLIP) != 0) != ((L.fflags[4 * (size_t) cell + f] & DFLO_FACE_FLIP) != 0)) ++bad;
+            }
+         }
+      for (int j = 0; j < nL; ++j)
+      {
+         const int w = lj[2 * j], nbs = lj[2 * j + 1];
+         const int s = (w & 0xffff) >> 1, dir = w & 1, cell = c0 + s, f = 2 * dir;
+         const int nb = L.nbr[4 * (size_t) cell + f];
+         ++covered[4 * (size_t) cell + f];
+         if (s >= ncb) { ++bad; continue; }
+         if (((w & ROWD_PLUS) != 0) != expect_plus (cell, f)) ++bad;
+         if (nbs < 0) { if (nbs != nb) ++bad; }
+         else if (su_cell (nbs) != nb) ++bad;
+         if (((w & ROWD_FLIP) != 0) != ((L.fflags[4 * (size_t) cell + f] & DFLO_FACE_FLIP) != 0)) ++bad;
+      }
+   }
+   for (int c = 0; c < L.n_compute; ++c)
+      for (int f = 0; f < 4; ++f)
+         if (covered[4 * (size_t) c + f] != 1) ++bad;
+   return bad;
+}
+
 // point-wise device physics (dflo_b200/csrc/euler.cuh) exposed for unit tests against the oracle
 extern "C" {
 void dflo_emu_numerical_flux (int flux, const double n[2], const double Wp[4], const double Wm[4], const double Ap[4],
@@ -130,6 +201,24 @@ void dflo_emu_numerical_flux (int flux, const double n[2], const double Wp[4], c
       default: dflo::numerical_flux<4> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
    }
 }
+// flux along +e_dir of a face whose integrating ("plus") cell is the low-side one (plus_low) or the high-side one
+void dflo_emu_face_flux_axis (int flux, int dir, int plus_low, const double Wl[4], const double Wr[4], const double Al[4],
+                              const double Ar[4], double H[4])
+{
+#define DFLO_AX(F) \
+   if (dir == 0) dflo::face_flux_axis<F, 0> (plus_low != 0, Wl, Wr, Al, Ar, H); \
+   else dflo::face_flux_axis<F, 1> (plus_low != 0, Wl, Wr, Al, Ar, H);
+   switch (flux)
+   {
+      case 0: DFLO_AX (0) break;
+      case 1: DFLO_AX (1) break;
+      case 2: DFLO_AX (2) break;
+      case 3: DFLO_AX (3) break;
+      default: DFLO_AX (4) break;
+   }
+#undef DFLO_AX
+}
+void dflo_emu_flux_x (const double W[4], double Fx[4]) { dflo::flux_x (W, Fx); }
 void dflo_emu_flux_matrix (const double W[4], double F[8])
 {
    double Fx[4], Fy[4];

@@ -333,3 +333,33 @@ def test_partition_ranges_and_halo_symmetry(world, layers_case):
         assert L.dflo_emu_n_local(e.h) > e.cell_range()[1] - e.cell_range()[0]
     for e in engines:
         e.close()
+
+
+ROW_MESHES = [
+    ("isentropic_vortex", [16], PERIODIC_BOX), ("isentropic_vortex", [41], PERIODIC_BOX), ("isentropic_vortex", [3], PERIODIC_BOX),
+    ("sod_tube", [100, 10], SOD_BC), ("forward_step", [0.05], STEP_BC),
+    ("double_mach", [16], {0: "outflow", 1: "slip", 2: "outflow", 3: "inflow", 4: "inflow"}),
+]
+
+
+@pytest.mark.parametrize("kind,args,bc", ROW_MESHES, ids=[m[0] + str(m[1][0]) for m in ROW_MESHES])
+@pytest.mark.parametrize("world,layers", [(1, 1), (2, 1), (3, 2)])
+def test_row_kernel_tile_descriptors(kind, args, bc, world, layers):
+    """row_desc.h: every face of every computed cell has exactly one agent in the register-blocked
+    stage kernel's tile descriptors (own thread / L job), with the right neighbour, ghost-trace
+    source, flip and reference "plus" side -- on lattice tiles, ragged multi-block tiles, tiny
+    periodic meshes (periodic partner inside the tile) and the strip tiles of a ghost layer."""
+    L = emu_lib()
+    L.dflo_emu_rowdesc_check.argtypes = [ctypes.POINTER(abi.FlatMesh), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.POINTER(ctypes.c_int)]
+    params, pair = abi.make_params(bc=bc, basis="Qk", degree=1, flux="lxf")
+    m = abi.Mesh(kind, args, lib=L)
+    flat = m.flatten(params, pair)
+    if m.n_cells < world:
+        pytest.skip("mesh smaller than world")
+    for n1 in (2, 3, 4, 5):
+        for rank in range(world):
+            nt = ctypes.c_int(0)
+            bad = L.dflo_emu_rowdesc_check(flat, n1, rank, world, layers, ctypes.byref(nt))
+            assert bad == 0, (n1, rank, bad)
+            assert nt.value >= 1

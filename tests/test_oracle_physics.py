@@ -170,3 +170,39 @@ def test_minmod_device():
     assert mm(-2.0, -3.0, -1.5, 1.0) == -1.5
     assert mm(2.0, -3.0, 4.0, 1.0) == 0.0           # sign change -> 0
     assert mm(2.0, 3.0, 0.0, 1.0) == 0.0
+
+
+def test_axis_fluxes_match_reference_convention():
+    """euler.cuh face_flux_axis (what the register-blocked stage kernel calls: the face solved
+    along +e_x / +e_y, the integrating cell on either side) against the reference's general-normal
+    flux called the way MeshWorker does: n = outward normal of the integrating ("plus") cell."""
+    L = emu_lib()
+    g = GOLD
+    P = O.Physics("restated")
+    fmat_r = np.array([P.flux_matrix(w) for w in g["WR"]])
+    worst = 0.0
+    for f in range(5):
+        for i in range(0, len(g["WL"]), 2):
+            lo, hi, alo, ahi = g["WL"][i], g["WR"][i], g["AL"][i], g["AR"][i]
+            scale = max(1.0, np.abs(g["fmat"][i]).max(), np.abs(fmat_r[i]).max())
+            for d in (0, 1):
+                e = np.array([1.0, 0.0]) if d == 0 else np.array([0.0, 1.0])
+                for plus_low in (1, 0):
+                    # reference call: plus cell first, its outward normal; flux along +e_d = sign * that
+                    want = P.flux(f, e, lo, hi, alo, ahi) if plus_low else -P.flux(f, -e, hi, lo, ahi, alo)
+                    if not np.all(np.isfinite(want)):
+                        continue
+                    got = np.zeros(4)
+                    args = [np.ascontiguousarray(a, dtype=np.float64) for a in (lo, hi, alo, ahi)]
+                    L.dflo_emu_face_flux_axis(f, d, plus_low, *[a.ctypes.data_as(_dp) for a in args], got.ctypes.data_as(_dp))
+                    err = np.abs(got - want).max() / scale
+                    worst = max(worst, err)
+                    assert err <= 2e-13, (FLUXES[f], i, d, plus_low, got, want)
+    # zero normal velocity: the reference's A&S ERF is not odd at s = 0; the mirrored evaluation must reproduce it
+    W = np.array([0.0, 0.0, 1.4, 8.8])
+    for d in (0, 1):
+        e = np.array([1.0, 0.0]) if d == 0 else np.array([0.0, 1.0])
+        want = -P.flux(O.FLUX["kfvs"], -e, W, W, W, W)
+        got = np.zeros(4)
+        L.dflo_emu_face_flux_axis(O.FLUX["kfvs"], d, 0, *[W.ctypes.data_as(_dp)] * 4, got.ctypes.data_as(_dp))
+        assert np.abs(got - want).max() <= 1e-14 * 8.8
