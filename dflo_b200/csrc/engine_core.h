@@ -754,6 +754,9 @@ namespace dflo
          a.time = d_time;
          a.dt_cell = nullptr;
          a.rowdesc = d_rowdesc;
+         a.n_cells_u = lm.n_local;
+         a.pf_tiles = bk.stage_prefetch_tiles ();
+         a.dbg = bk.debug_flags ();
          a.mode = mode;
          a.compat_mpi = prm.compat == DFLO_COMPAT_MPI;
          a.ark = ark[rk];

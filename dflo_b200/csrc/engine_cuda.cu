@@ -243,6 +243,16 @@ namespace
       }
       // The stage kernel.  Default: the pipelined persistent form (one producer warp streaming tiles
       // through two shared-memory stages); DFLO_B200_PERSISTENT=0 selects the one-tile-per-block form.
+      int stage_prefetch_tiles () const
+      {
+         static const char *e = std::getenv ("DFLO_B200_PF_TILES");
+         return e ? std::atoi (e) : n_sm * DFLO_ROW_MIN_BLOCKS;
+      }
+      int debug_flags () const
+      {
+         static const char *e = std::getenv ("DFLO_B200_DBG");
+         return e ? std::atoi (e) : 0;
+      }
       bool use_row_kernel (int basis, int n1) const { return row_kernel && basis == dflo::BASIS_QK && n1 >= 2; }
       // 1-D tables of the row kernel as constant-bank operands
       void prepare_tables (const dflo::FeTables &t)

@@ -90,6 +90,9 @@ namespace dflo
       const double *time;     // device scalars: [0] elapsed time, [1] dt
       const double *dt_cell;  // optional per-cell dt (local time stepping), else nullptr
       const int *rowdesc;     // tile descriptors of the register-blocked Qk kernel (row_desc.h), or nullptr
+      int n_cells_u;          // cells held by u / u_old (bounds the L2 prefetch hints)
+      int pf_tiles;           // row kernel: prefetch distance in tiles (resident blocks of the device)
+      int dbg;                // developer timing experiments only (DFLO_B200_DBG): 1 no Riemann solves, 2 no volume fluxes, 4 no extra-warp jobs
       int mode;
       int compat_mpi;
       double ark;

@@ -23,7 +23,10 @@ namespace dflo
 {
    // tile shape (cells) per N1; TC = tx*ty is a multiple of 32 so that TC*N1 threads are whole warps
    constexpr int row_tx (int n1) { return n1 == 2 ? 8 : 8; }
-   constexpr int row_ty (int n1) { return n1 == 2 ? 8 : 4; }
+#ifndef DFLO_ROW_TY
+#define DFLO_ROW_TY 4
+#endif
+   constexpr int row_ty (int n1) { return n1 == 2 ? 8 : DFLO_ROW_TY; }
    constexpr int row_tc (int n1) { return row_tx (n1) * row_ty (n1); }
    constexpr int row_nh (int n1) { return 2 * (row_tx (n1) + row_ty (n1)); } // staged halo cells = L-job = G-job capacity
 

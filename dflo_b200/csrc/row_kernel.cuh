@@ -41,24 +41,42 @@ namespace dflo
    {
       static constexpr int NS = N1 * N1, D = 4 * NS;
       static constexpr int TC = row_tc (N1), NH = row_nh (N1);
-      static constexpr int CS = D + 2;                      // padded cell stride in shared memory (doubles)
-      static constexpr int MAIN = TC * N1, EXTRA = 64, THREADS = MAIN + EXTRA;
-      static constexpr int MIN_BLOCKS = N1 <= 4 ? 3 : 2;
+#ifndef DFLO_ROW_PAD
+#define DFLO_ROW_PAD 2
+#endif
+      static constexpr int CS = D + DFLO_ROW_PAD;           // padded cell stride in shared memory (doubles)
+      #ifndef DFLO_ROW_EXTRA
+#define DFLO_ROW_EXTRA 32
+#endif
+      static constexpr int MAIN = TC * N1, EXTRA = DFLO_ROW_EXTRA, THREADS = MAIN + EXTRA;
+      #ifndef DFLO_ROW_MIN_BLOCKS
+#define DFLO_ROW_MIN_BLOCKS 4
+#endif
+      static constexpr int MIN_BLOCKS = N1 <= 4 ? DFLO_ROW_MIN_BLOCKS : 2;
       static constexpr int DESC_INTS = rowd_ints (TC, NH);
       static constexpr int OFF_HALO = rowd_off_halo (), OFF_NBHI = rowd_off_nbhi (NH), OFF_LJOB = rowd_off_ljob (TC, NH),
                            OFF_GJOB = rowd_off_gjob (TC, NH);
-      // shared memory carve-up in doubles; every bulk-copy destination is 16-byte aligned
+      // shared memory carve-up in doubles; every bulk-copy destination is 16-byte aligned.
+      //   [O_U, O_X)   the tile's cells (padded), live to the end
+      //   [O_X, ...)   halo cells | ghost traces | low-face traces -> fluxes: dead once the fluxes
+      //                have been read into registers; the y part of the residual (sR, row order,
+      //                padded like su) is then written over this region, and the partial cell
+      //                averages over its tail
       static constexpr int O_U = 2;                               // [0,2): mbarrier
-      static constexpr int O_R = O_U + (TC + NH) * CS;            // y part of the residual, row order, padded like su
-      static constexpr int O_T = O_R + TC * CS;                   // low-face traces -> fluxes: 2 halves x [2 dirs][TC][N1] double2
+      static constexpr int O_X = O_U + TC * CS;
+      static constexpr int O_G = O_X + NH * CS;                   // ghost traces [NH][N1][4]
+      static constexpr int O_T = O_G + NH * N1 * 4;               // 2 halves x [2 dirs][TC][N1] double2
       static constexpr int T_HALF = 2 * TC * N1 * 2;
-      static constexpr int O_G = O_T + 2 * T_HALF;                // ghost traces [NH][N1][4]
-      static constexpr int O_GEOM = O_G + NH * N1 * 4;            // x0 y0 hx hy of the tile cells
+      static constexpr int X_END_A = O_T + 2 * T_HALF;
+      static constexpr int O_R = O_X;
+      static constexpr int O_PART = O_R + TC * CS;                // [TC][N1][4]
+      static constexpr int X_END_B = O_PART + TC * N1 * 4;
+      static constexpr int O_GEOM = X_END_A > X_END_B ? X_END_A : X_END_B;   // x0 y0 hx hy of the tile cells
       static constexpr int O_AVG = O_GEOM + TC * 4;               // cell averages tile + halo (LxF only)
       static constexpr int O_DESC = O_AVG + (FLUX == FLUX_LXF ? (TC + NH) * 4 : 0);
       static constexpr int SMEM_DOUBLES = O_DESC + DESC_INTS / 2;
       static_assert (MAIN % 32 == 0, "whole warps");
-      static_assert (THREADS >= TC + NH + 1, "one staging copy per thread");
+      static_assert (THREADS >= TC + NH + 2, "one staging copy per thread");
       static_assert (CS % 2 == 0 && DESC_INTS % 4 == 0, "16-byte aligned bulk copies");
    };
 
@@ -236,7 +254,12 @@ namespace dflo
          mbar_expect_tx (sm, bytes);
       }
       __syncthreads ();
-      if (tid < ncb + nh)
+      if (DFLO_ROW_PAD == 0 && tid < ncb)
+      {
+         if (tid == 0) bulk_g2s (su, A.u + (size_t) c0 * D, (unsigned) ncb * cell_bytes, sm);
+         if (FLUX == FLUX_LXF) bulk_g2s (sAvg + tid * 4, A.avg + (size_t) (c0 + tid) * 4, 32u, sm);
+      }
+      else if (tid < ncb + nh)
       {
          const int cell = tid < ncb ? c0 + tid : gdesc[S::OFF_HALO + tid - ncb];
          const int slot = tid < ncb ? tid : TC + tid - ncb;
@@ -250,6 +273,23 @@ namespace dflo
          if (need_old)
             asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u_old + (size_t) c0 * D), "r"((unsigned) ncb * cell_bytes) : "memory");
       }
+      else if (tid == S::THREADS - 2)
+      {
+         // Pull the inputs of the tile that will run in this block's slot a wave later from HBM
+         // into L2 now (a hint: on a uniform tiling that tile starts pf_tiles * TC cells further on)
+         const int bt = (int) blockIdx.x + A.pf_tiles;
+         if (bt < (int) gridDim.x)
+         {
+            const size_t pc0 = (size_t) c0 + (size_t) A.pf_tiles * TC;
+            if (pc0 + TC <= (size_t) A.n_cells_u)
+            {
+               asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u + pc0 * D), "r"((unsigned) TC * cell_bytes) : "memory");
+               if (need_old) asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u_old + pc0 * D), "r"((unsigned) TC * cell_bytes) : "memory");
+            }
+            asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.rowdesc + (size_t) bt * S::DESC_INTS), "r"((unsigned) (S::DESC_INTS * sizeof (int))) : "memory");
+         }
+      }
+      const double dt_global = A.time[1]; // issued before the wait: its latency hides behind the staging
       mbar_wait (sm, 0);
 
       const bool main_thread = tid < S::MAIN;
@@ -308,7 +348,7 @@ namespace dflo
       if (!main_thread)
       {
          // G jobs: low-face traces of the cells beyond the tile's high edges
-         const int nG = sdesc[4];
+         const int nG = (A.dbg & 4) ? 0 : sdesc[4];
          for (int j = tid - S::MAIN; j < nG * N1; j += S::EXTRA)
          {
             const int g = j / N1, q = j % N1;
@@ -336,7 +376,13 @@ namespace dflo
             else
                load4 (sG + ((idx - TC) * N1 + rb) * 4, Wn);
             if (FLUX == FLUX_LXF) load4 (sAvg + (idx < TC ? idx : (sdesc[S::OFF_GJOB + idx - TC] & 0xffff)) * 4, An);
-            face_flux_axis<FLUX, 0> ((code & ROWD_PLUS) != 0, WR, Wn, Ao, An, H);
+            if (A.dbg & 1)
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c) H[c] = WR[c] + Wn[c];
+            }
+            else
+               face_flux_axis<FLUX, 0> ((code & ROWD_PLUS) != 0, WR, Wn, Ao, An, H);
             if (idx < TC) store_pt<TH> (sT, idx * N1 + rb, H);
          }
          else
@@ -375,7 +421,13 @@ namespace dflo
             else
                load4 (sG + ((idx - TC) * N1 + ca) * 4, Wn);
             if (FLUX == FLUX_LXF) load4 (sAvg + (idx < TC ? idx : (sdesc[S::OFF_GJOB + idx - TC] & 0xffff)) * 4, An);
-            face_flux_axis<FLUX, 1> ((code & ROWD_PLUS) != 0, WT, Wn, Ao, An, H);
+            if (A.dbg & 1)
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c) H[c] = WT[c] + Wn[c];
+            }
+            else
+               face_flux_axis<FLUX, 1> ((code & ROWD_PLUS) != 0, WT, Wn, Ao, An, H);
             if (idx < TC) store_pt<TH> (sT, TC * N1 + col_pos<N1> (idx, ca), H);
          }
          else
@@ -403,7 +455,7 @@ namespace dflo
       if (!main_thread)
       {
          // L jobs: low faces of tile cells whose neighbour is a halo cell, a periodic partner or a boundary
-         const int nL = sdesc[3];
+         const int nL = (A.dbg & 4) ? 0 : sdesc[3];
          for (int j = tid - S::MAIN; j < nL * N1; j += S::EXTRA)
          {
             const int job = j / N1, q = j % N1;
@@ -446,7 +498,13 @@ namespace dflo
       __syncthreads ();
 
       // ================= P3: volume terms and lifting =================
-      double rrow[4][N1];
+      // the low-face fluxes move to registers; after the barrier the exchange arrays are dead and
+      // sR is written over them
+      double HL[4], HB[4];
+      if (row_on) load_pt<TH> (sT, pT_row, HL);
+      if (col_on) load_pt<TH> (sT, pT_col, HB);
+      __syncthreads ();
+      double rrow[4][N1], uold[4][N1];
       if (col_on)
       {
          // y part: F_y at the column's nodes, contraction with D.w along y, top/bottom lifting
@@ -459,14 +517,18 @@ namespace dflo
             // F_y(W) = F_x with the momentum components exchanged
             const double W[4] = {uc[1 * NS + b * N1], uc[0 * NS + b * N1], uc[2 * NS + b * N1], uc[3 * NS + b * N1]};
             double F[4];
-            flux_x (W, F);
+            if (A.dbg & 2)
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c) F[c] = W[c];
+            }
+            else
+               flux_x (W, F);
             Fy[0][b] = F[1];
             Fy[1][b] = F[0];
             Fy[2][b] = F[2];
             Fy[3][b] = F[3];
          }
-         double HB[4];
-         load_pt<TH> (sT, pT_col, HB);
          const double hw = hx * T.gw[ca];
          double *rc = sR + cs * CS + ca;
 #pragma unroll
@@ -493,12 +555,16 @@ namespace dflo
          {
             const double W[4] = {u[0][a], u[1][a], u[2][a], u[3][a]};
             double F[4];
-            flux_x (W, F);
+            if (A.dbg & 2)
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c) F[c] = W[c];
+            }
+            else
+               flux_x (W, F);
 #pragma unroll
             for (int c = 0; c < 4; ++c) Fx[c][a] = F[c];
          }
-         double HL[4];
-         load_pt<TH> (sT, pT_row, HL);
          const double hw = hy * T.gw[rb];
 #pragma unroll
          for (int c = 0; c < 4; ++c)
@@ -525,15 +591,23 @@ namespace dflo
             }
          }
       }
+      // old_solution of the own row: requested before the barrier so the loads fly while the block
+      // drains P3 (the lines were pulled into L2 by the bulk prefetch at the start)
+      if (row_on && need_old)
+      {
+#pragma unroll
+         for (int c = 0; c < 4; ++c) load_line<N1> (A.u_old + ((size_t) (c0 + rs) * D + rb * N1) + c * NS, uold[c]);
+      }
       __syncthreads ();
 
       // ================= P4: M^-1, Euler step, RK combine, write-back, cell average =================
-      double *sPart = sT; // [TC][N1][4] partial cell averages (the fluxes in sT are dead)
+      double *sPart = sm + S::O_PART; // [TC][N1][4] partial cell averages
+      const unsigned row_mask = __ballot_sync (0xffffffffu, row_on);
       if (row_on)
       {
          const int cell = c0 + rs;
          const double hx = sGeom[rs * 4 + 2], hy = sGeom[rs * 4 + 3];
-         const double dt = A.dt_cell ? A.dt_cell[cell] : A.time[1];
+         const double dt = A.dt_cell ? A.dt_cell[cell] : dt_global;
          const size_t goff = (size_t) cell * D + rb * N1;
          const double wbh = T.gw[rb] * hx * hy;
          double part[4];
@@ -549,15 +623,14 @@ namespace dflo
             }
             else
             {
-               double u[N1], uo[N1];
+               double u[N1];
                load_line<N1> (su + rs * CS + c * NS + rb * N1, u);
-               if (need_old) load_line<N1> (A.u_old + goff + c * NS, uo);
 #pragma unroll
                for (int a = 0; a < N1; ++a)
                {
                   const double invm = fast_rcp (T.gw[a] * wbh); // claw.cc:228-258 on a Cartesian cell
                   const double un = u[a] + dt * (rrow[c][a] + ry[a]) * invm;
-                  v[a] = need_old ? (1.0 - A.ark) * un + A.ark * uo[a] : un;
+                  v[a] = need_old ? (1.0 - A.ark) * un + A.ark * uold[c][a] : un;
                }
             }
             store_line<N1> (A.out + goff + c * NS, v);
@@ -566,9 +639,25 @@ namespace dflo
             for (int a = 0; a < N1; ++a) s = fma (T.gw[a], v[a], s);
             part[c] = T.gw[rb] * s;
          }
-         if (A.mode == MODE_STAGE) store4 (sPart + (rs * N1 + rb) * 4, part);
+         if (A.mode == MODE_STAGE)
+         {
+            if (N1 == 2 || N1 == 4)
+            {
+               // compute_cell_average (claw.cc:562-597): the N1 row sums of a cell sit in adjacent
+               // lanes; the first lane adds them in row order
+               const int lane0 = (tid & 31) - rb;
+               double v[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+               for (int b = 0; b < N1; ++b)
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) v[c] += __shfl_sync (row_mask, part[c], lane0 + b);
+               if (rb == 0) store4 (A.avg_out + (size_t) cell * 4, v);
+            }
+            else
+               store4 (sPart + (rs * N1 + rb) * 4, part);
+         }
       }
-      if (A.mode == MODE_STAGE)
+      if (A.mode == MODE_STAGE && N1 != 2 && N1 != 4)
       {
          __syncthreads ();
          for (int j = tid; j < ncb * 4; j += S::THREADS) // compute_cell_average of the updated solution, claw.cc:562-597

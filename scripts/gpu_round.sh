@@ -23,7 +23,7 @@ PY
 if [ "$1" = "ncu" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_run.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'stage_persistent|phase_kernel' -s 6 -c 2 -f -o gpurun_out/prof_stage \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'row_stage|stage_persistent|phase_kernel' -s 6 -c 2 -f -o gpurun_out/prof_stage \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_run.log 2>&1
 fi
 ls -la gpurun_out

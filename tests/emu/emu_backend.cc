@@ -63,6 +63,8 @@ namespace
       // the register-blocked Qk kernel exists only as CUDA code; the emulation runs the phase kernel
       bool use_row_kernel (int, int) const { return false; }
       void prepare_tables (const dflo::FeTables &) {}
+      int stage_prefetch_tiles () const { return 0; }
+      int debug_flags () const { return 0; }
       template <class K> void launch1d (int n, const typename K::Args &a)
       {
          ++launches;
