@@ -325,7 +325,7 @@ namespace dflo
       double *rhs = nullptr;
       double *d_time = nullptr;       // t, dt, dt accumulator, final time
       double *d_scratch = nullptr;    // [1] reductions
-      int *d_nbr = nullptr, *d_halo_cells = nullptr, *d_rowdesc = nullptr;
+      int *d_nbr = nullptr, *d_halo_cells = nullptr, *d_rowdesc = nullptr, *d_send_entries = nullptr;
       FaceJob *d_jobs = nullptr;
       TileDesc *d_tiles = nullptr;
       unsigned char *d_fflags = nullptr;
@@ -346,6 +346,9 @@ namespace dflo
       bool have_programs = false, programs_time_dependent = false;
       int n_global_bfaces = 0;
 
+      // halo exchange fused into the stage kernel: row kernel, peer memory mapped, nothing between
+      // the stage kernel and the exchange (no limiter)
+      bool fused_halo () { return !lm.peers.empty () && !tvb () && !pos () && bk.use_row_kernel (tab.basis, tab.n1) && bk.p2p_fused_ok (); }
       int D () const { return tab.D; }
       bool tvb () const { return prm.limiter_type == DFLO_LIMITER_TVB && tab.k > 0; }
       bool pos () const { return prm.pos_lim && tab.k > 0; }
@@ -399,7 +402,8 @@ namespace dflo
                td[t].nh = lm.halo_start[t + 1] - lm.halo_start[t];
                td[t].j0 = lm.job_start[t];
                td[t].nj = lm.job_start[t + 1] - lm.job_start[t];
-               td[t].pad0 = td[t].pad1 = 0;
+               td[t].pad0 = t >= lm.n_tiles_owned; // ghost tile: means only
+               td[t].pad1 = 0;
             }
             d_tiles = upload (td);
          }
@@ -431,12 +435,19 @@ namespace dflo
                d_send_u[k].push_back (bk.template alloc<double> (std::max<size_t> (1, pr.send_cells[k].size ()) * D ()));
                d_send_avg[k].push_back (bk.template alloc<double> (std::max<size_t> (1, pr.send_cells[k].size ()) * 4));
             }
+         // direct peer-memory halo (NVLink P2P) when the backend can map the peers' buffers
+         if (!lm.peers.empty ())
+         {
+            d_send_entries = upload (pad1 (lm.send_entries));
+            bk.p2p_setup (U, AVG, lm.peers, d_send_cells, D (), d_send_entries, lm.n_send_tiles);
+         }
          return bk.check (error);
       }
 
       void release ()
       {
          bk.sync ();
+         bk.p2p_teardown ();
          bk.drop_graphs ();
          for (int i = 0; i < 3; ++i)
          {
@@ -444,7 +455,7 @@ namespace dflo
             bk.free (AVG[i]);
          }
          void *ptrs[] = {rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
-                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles, d_rowdesc};
+                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles, d_rowdesc, d_send_entries};
          for (void *p : ptrs) bk.free (p);
          for (int k = 0; k < 2; ++k)
          {
@@ -559,6 +570,7 @@ namespace dflo
          eval_boundary (false);
          StageArgs a = stage_args (0, MODE_RHS);
          a.out = rhs;
+         if (fused_halo ()) a.fx = bk.p2p_fused_args (cur); // waits for the last fused exchange, publishes nothing
          launch_stage (bk, tab.basis, tab.n1, prm.flux_type, lm.n_tiles_owned, a);
          return bk.check (error);
       }
@@ -757,6 +769,8 @@ namespace dflo
          a.n_cells_u = lm.n_local;
          a.pf_tiles = bk.stage_prefetch_tiles ();
          a.dbg = bk.debug_flags ();
+         a.n_tiles_owned = lm.n_tiles_owned;
+         a.fx = nullptr;
          a.mode = mode;
          a.compat_mpi = prm.compat == DFLO_COMPAT_MPI;
          a.ark = ark[rk];
@@ -841,6 +855,8 @@ namespace dflo
          StageArgs a = stage_args (rk, MODE_STAGE);
          a.out = U[out];
          a.avg_out = AVG[out];
+         const bool fused = fused_halo ();
+         if (fused) a.fx = bk.p2p_fused_args (out);
          launch_stage (bk, tab.basis, tab.n1, prm.flux_type, lm.n_tiles, a);
          if (tvb () || pos ())
          {
@@ -848,7 +864,7 @@ namespace dflo
             launch_limiter (bk, tab.basis, tab.n1, l);
          }
          cur = out;
-         exchange_halo (cur);
+         if (!fused) exchange_halo (cur);
       }
 
       void enqueue_step ()
@@ -870,6 +886,7 @@ namespace dflo
       void exchange_halo (int buf)
       {
          if (lm.peers.empty ()) return;
+         if (bk.p2p_exchange (buf)) return;
          for (size_t p = 0; p < lm.peers.size (); ++p)
             for (int k = 0; k < 2; ++k)
             {

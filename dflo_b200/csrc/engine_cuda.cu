@@ -5,6 +5,7 @@
 // RK stage on the same stream.  There is no CPU fallback: without a CUDA device create() returns
 // DFLO_E_NO_DEVICE.
 #include "abi_impl.h"
+#include "p2p_halo.cuh"
 #include "row_kernel.cuh"
 
 #include <cuda_runtime.h>
@@ -32,6 +33,7 @@ namespace
       decltype (&ncclSend) Send = nullptr;
       decltype (&ncclRecv) Recv = nullptr;
       decltype (&ncclAllReduce) AllReduce = nullptr;
+      decltype (&ncclAllGather) AllGather = nullptr;
       std::string error;
 
       bool load ()
@@ -64,6 +66,7 @@ namespace
          DFLO_NCCL_SYM (Send)
          DFLO_NCCL_SYM (Recv)
          DFLO_NCCL_SYM (AllReduce)
+         DFLO_NCCL_SYM (AllGather)
 #undef DFLO_NCCL_SYM
          return true;
       }
@@ -115,6 +118,20 @@ namespace
       };
       std::map<int, Graph> graphs;
       int64_t launches_at_capture = 0;
+      // peer-memory halo (p2p_halo.cuh)
+      bool p2p = false;
+      dflo::P2PArgs p2p_args;
+      double *p2p_U[3] = {nullptr, nullptr, nullptr}, *p2p_A[3] = {nullptr, nullptr, nullptr};
+      double *p2p_peerU[dflo::P2P_MAX_WORLD][3], *p2p_peerA[dflo::P2P_MAX_WORLD][3];
+      std::vector<void *> p2p_opened;
+      unsigned long long *p2p_flags = nullptr, *p2p_epochs = nullptr;
+      unsigned int *p2p_counter = nullptr;
+      int p2p_grid = 1;
+      bool p2p_fused = false;
+      dflo::P2PFused *p2p_fused_dev = nullptr;
+      unsigned int *p2p_send_counters = nullptr;
+      bool p2p_fused_ok () const { return p2p && p2p_fused; }
+      const dflo::P2PFused *p2p_fused_args (int buf) const { return p2p_fused_dev + buf; }
 
       void note (cudaError_t e)
       {
@@ -335,7 +352,9 @@ namespace
       }
       bool capture_begin ()
       {
-         if (!use_graphs || world > 1) return false; // sharded steps run eagerly (NCCL on the stream)
+         static const char *gs = std::getenv ("DFLO_B200_GRAPHS_SHARDED");
+         // sharded steps are captured when the halo goes over peer memory; with NCCL on the stream they run eagerly unless asked
+         if (!use_graphs || (world > 1 && !p2p && !(gs && std::atoi (gs)))) return false;
          if (cudaStreamBeginCapture (stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
          {
             (void) cudaGetLastError ();
@@ -392,7 +411,205 @@ namespace
       void halo_wait () {}
       void allreduce_min_dt (double *p)
       {
-         if (comm) note (nccl ().AllReduce (p, p, 1, ncclDouble, ncclMin, comm, stream));
+         if (p2p)
+         {
+            dflo::P2PArgs a = p2p_args;
+            a.dt_val = p;
+            ++launches;
+            dflo::dt_min_kernel<<<1, 32, 0, stream>>> (a);
+            note (cudaPeekAtLastError ());
+         }
+         else if (comm)
+            note (nccl ().AllReduce (p, p, 1, ncclDouble, ncclMin, comm, stream));
+      }
+
+      // ---- peer-memory halo: map the peers' buffers once (CUDA IPC handles over the NCCL communicator) ----
+      template <class Peers>
+      void p2p_setup (double **U, double **AVG, const Peers &peers, const std::vector<int *> *d_send_cells, int D, const int *d_send_entries,
+                      int n_send_tiles)
+      {
+         const char *env = std::getenv ("DFLO_B200_P2P");
+         if (!comm || world < 2 || world > dflo::P2P_MAX_WORLD || (env && std::atoi (env) == 0)) return;
+         const int W = world, NH = 7; // handles per rank: U0 U1 U2 A0 A1 A2 flags
+         p2p_flags = alloc<unsigned long long> (4 * W);
+         p2p_epochs = alloc<unsigned long long> (4);
+         p2p_counter = alloc<unsigned int> (1);
+         zero (p2p_flags, 4 * W * sizeof (unsigned long long));
+         zero (p2p_counter, sizeof (unsigned int));
+         const unsigned long long ones[4] = {1, 1, 1, 0};
+         h2d (p2p_epochs, ones, sizeof (ones));
+         std::vector<cudaIpcMemHandle_t> hs ((size_t) W * NH);
+         int ok = 1;
+         void *mine[NH] = {U[0], U[1], U[2], AVG[0], AVG[1], AVG[2], p2p_flags};
+         for (int i = 0; i < NH; ++i)
+            if (cudaIpcGetMemHandle (&hs[(size_t) rank * NH + i], mine[i]) != cudaSuccess) ok = 0;
+         (void) cudaGetLastError ();
+         char *d_h = alloc<char> (hs.size () * sizeof (cudaIpcMemHandle_t));
+         const size_t per = NH * sizeof (cudaIpcMemHandle_t);
+         h2d (d_h + rank * per, &hs[(size_t) rank * NH], per);
+         note (nccl ().AllGather (d_h + rank * per, d_h, per, ncclChar, comm, stream));
+         d2h (hs.data (), d_h, hs.size () * sizeof (cudaIpcMemHandle_t));
+         free (d_h);
+         std::memset (&p2p_args, 0, sizeof (p2p_args));
+         auto open_handle = [&] (const cudaIpcMemHandle_t &h) -> void * {
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle (&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+            {
+               (void) cudaGetLastError ();
+               ok = 0;
+               return nullptr;
+            }
+            p2p_opened.push_back (ptr);
+            return ptr;
+         };
+         for (int r = 0; r < W && ok; ++r)
+            p2p_args.all_flags[r] = r == rank ? p2p_flags : static_cast<unsigned long long *> (open_handle (hs[(size_t) r * NH + 6]));
+         int np = 0, ns = 0;
+         size_t items = 0;
+         for (size_t pi = 0; pi < peers.size () && ok; ++pi)
+         {
+            const int r = peers[pi].rank;
+            for (int i = 0; i < 3 && ok; ++i)
+            {
+               p2p_peerU[np][i] = static_cast<double *> (open_handle (hs[(size_t) r * NH + i]));
+               p2p_peerA[np][i] = static_cast<double *> (open_handle (hs[(size_t) r * NH + 3 + i]));
+            }
+            p2p_args.peer_flags[np] = p2p_args.all_flags[r];
+            p2p_args.peer_rank[np] = r;
+            for (int k = 0; k < 2; ++k)
+            {
+               const int n = (int) peers[pi].send_cells[k].size ();
+               if (!n) continue;
+               dflo::P2PSeg sg;
+               sg.cells = d_send_cells[k][pi];
+               sg.n = n;
+               sg.peer = np;
+               sg.dst_cell0 = peers[pi].dst_start[k];
+               p2p_args.seg[ns++] = sg;
+               items += (size_t) n * D / 2;
+            }
+            ++np;
+         }
+         // every rank must take the same path
+         int *d_ok = alloc<int> (1);
+         h2d (d_ok, &ok, sizeof (int));
+         note (nccl ().AllReduce (d_ok, d_ok, 1, ncclInt, ncclMin, comm, stream));
+         d2h (&ok, d_ok, sizeof (int));
+         free (d_ok);
+         if (!ok)
+         {
+            p2p_teardown ();
+            return;
+         }
+         for (int i = 0; i < 3; ++i)
+         {
+            p2p_U[i] = U[i];
+            p2p_A[i] = AVG[i];
+         }
+         p2p_args.my_flags = p2p_flags;
+         p2p_args.epochs = p2p_epochs;
+         p2p_args.counter = p2p_counter;
+         p2p_args.nseg = ns;
+         p2p_args.npeers = np;
+         p2p_args.me = rank;
+         p2p_args.world = W;
+         p2p_args.D = D;
+         if (std::getenv ("DFLO_B200_P2P_TRACE"))
+         {
+            p2p_args.trace = alloc<unsigned long long> (4 * 4096);
+            zero (p2p_args.trace, 4 * 4096 * sizeof (unsigned long long));
+         }
+         p2p_grid = (int) std::min<size_t> (n_sm, std::max<size_t> (1, items / 512));
+         // fused form: one descriptor per output buffer
+         p2p_send_counters = alloc<unsigned int> (2);
+         zero (p2p_send_counters, 2 * sizeof (unsigned int));
+         p2p_fused_dev = alloc<dflo::P2PFused> (3);
+         for (int b = 0; b < 3; ++b)
+         {
+            dflo::P2PFused f;
+            std::memset (&f, 0, sizeof (f));
+            for (int q = 0; q < np; ++q)
+            {
+               f.dstU[q] = p2p_peerU[q][b];
+               f.dstA[q] = p2p_peerA[q][b];
+               f.peer_flags[q] = p2p_args.peer_flags[q];
+               f.peer_rank[q] = p2p_args.peer_rank[q];
+            }
+            f.my_flags = p2p_flags;
+            f.epochs = p2p_epochs;
+            f.send_counter = p2p_send_counters;
+            f.block_counter = p2p_send_counters + 1;
+            f.send_entries = d_send_entries;
+            f.n_send_tiles = n_send_tiles;
+            f.npeers = np;
+            f.me = rank;
+            f.world = W;
+            h2d (p2p_fused_dev + b, &f, sizeof (f));
+         }
+         sync ();
+         const char *fe = std::getenv ("DFLO_B200_P2P_FUSED");
+         p2p_fused = n_send_tiles > 0 && !(fe && std::atoi (fe) == 0);
+         p2p = true;
+      }
+      void p2p_teardown ()
+      {
+         if (p2p && p2p_args.trace) // developer timeline: per exchange, ns relative to the previous exchange's end
+         {
+            std::vector<unsigned long long> t (4 * 4096);
+            sync ();
+            d2h (t.data (), p2p_args.trace, t.size () * sizeof (unsigned long long));
+            unsigned long long e_last = 0;
+            d2h (&e_last, p2p_epochs, sizeof (e_last));
+            const int hi = (int) std::min<unsigned long long> (e_last, 4096);
+            for (int e = std::max (2, hi - 12); e < hi; ++e)
+               std::fprintf (stderr, "[p2p rank %d] exch %d: since prev end %7.2f us | push start->copied %6.2f | fence+flag %6.2f | wait peers %6.2f\n", rank, e,
+                             (t[4 * e] - t[4 * (e - 1) + 3]) * 1e-3, (t[4 * e + 1] - t[4 * e]) * 1e-3, (t[4 * e + 2] - t[4 * e + 1]) * 1e-3,
+                             (t[4 * e + 3] - t[4 * e + 2]) * 1e-3);
+            free (p2p_args.trace);
+            p2p_args.trace = nullptr;
+         }
+         if (comm && (p2p || !p2p_opened.empty ()))
+         {
+            // nobody unmaps or frees while a peer may still be storing into it
+            int *d = alloc<int> (1);
+            zero (d, sizeof (int));
+            note (nccl ().AllReduce (d, d, 1, ncclInt, ncclSum, comm, stream));
+            sync ();
+            free (d);
+         }
+         for (void *q : p2p_opened) cudaIpcCloseMemHandle (q);
+         p2p_opened.clear ();
+         free (p2p_flags);
+         free (p2p_epochs);
+         free (p2p_counter);
+         free (p2p_fused_dev);
+         free (p2p_send_counters);
+         p2p_fused_dev = nullptr;
+         p2p_send_counters = nullptr;
+         p2p_fused = false;
+         p2p_flags = p2p_epochs = nullptr;
+         p2p_counter = nullptr;
+         p2p = false;
+      }
+      // one stage's exchange of buffer `buf`: push to the peers, then wait for theirs
+      bool p2p_exchange (int buf)
+      {
+         if (!p2p) return false;
+         dflo::P2PArgs a = p2p_args;
+         a.srcU = p2p_U[buf];
+         a.srcA = p2p_A[buf];
+         for (int p = 0; p < a.npeers; ++p)
+         {
+            a.dstU[p] = p2p_peerU[p][buf];
+            a.dstA[p] = p2p_peerA[p][buf];
+         }
+         ++launches;
+         static const int dbg = std::getenv ("DFLO_B200_P2P_DBG") ? std::atoi (std::getenv ("DFLO_B200_P2P_DBG")) : 0; // timing experiments only
+         if (dbg & 4) return true;
+         if (dbg & 1) a.nseg = 0;
+         dflo::halo_push_kernel<<<p2p_grid, 256, 0, stream>>> (a);
+         note (cudaPeekAtLastError ());
+         return true;
       }
       void allreduce_sum (double *p, int n)
       {

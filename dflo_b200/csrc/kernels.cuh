@@ -73,6 +73,8 @@ namespace dflo
       int c0, ncb, h0, nh, j0, nj, pad0, pad1;
    };
 
+   struct P2PFused; // p2p_halo.cuh (CUDA backend only)
+
    struct StageArgs
    {
       const double *u;        // current_solution   [n_local][D]
@@ -92,6 +94,8 @@ namespace dflo
       const int *rowdesc;     // tile descriptors of the register-blocked Qk kernel (row_desc.h), or nullptr
       int n_cells_u;          // cells held by u / u_old (bounds the L2 prefetch hints)
       int pf_tiles;           // row kernel: prefetch distance in tiles (resident blocks of the device)
+      int n_tiles_owned;      // tiles >= this one are redundantly updated ghost cells: only their means are stored
+      const P2PFused *fx;     // row kernel: halo exchange over peer memory fused into the stage kernel, or nullptr
       int dbg;                // developer timing experiments only (DFLO_B200_DBG): 1 no Riemann solves, 2 no volume fluxes, 4 no extra-warp jobs
       int mode;
       int compat_mpi;
@@ -567,8 +571,12 @@ namespace dflo
          else if (p == 4)
          {
             double *dst = A.out + (size_t) c0 * D;
+            // td.pad0: a tile of redundantly updated ghost cells -- only its means are kept, the
+            // solution itself arrives with the halo exchange (possibly before this tile runs)
+            const bool keep = td.pad0 == 0;
 #if defined(__CUDA_ARCH__)
-            if (persistent) // fire-and-forget 16-byte stores: the stage buffer is free as soon as they are issued
+            if (!keep) {}
+            else if (persistent) // fire-and-forget 16-byte stores: the stage buffer is free as soon as they are issued
             {
                const double2 *s2 = reinterpret_cast<const double2 *> (su);
                double2 *d2 = reinterpret_cast<double2 *> (dst);
@@ -577,7 +585,8 @@ namespace dflo
             else if (tid == 0) // the tile goes back as one bulk copy shared -> global
                bulk_s2g (dst, su, (unsigned) (ncb * D * sizeof (double)));
 #else
-            for (int i = tid; i < ncb * D; i += THREADS) dst[i] = su[i];
+            if (keep)
+               for (int i = tid; i < ncb * D; i += THREADS) dst[i] = su[i];
 #endif
             // compute_cell_average of the updated solution, claw.cc:562-597, in two steps: weighted
             // sums along x, one (cell, component, row) per thread (scratch = the flux array sF)

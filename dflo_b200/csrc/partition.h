@@ -39,6 +39,7 @@ namespace dflo
       int rank;
       std::vector<int> send_cells[2]; // local (owned) cell ids to send, per ghost layer of the peer
       int recv_start[2], recv_count[2]; // contiguous local ranges receiving from this peer
+      int dst_start[2];                 // where send_cells[k] land in the PEER's local cell numbering (its recv_start for us)
    };
 
    struct LocalMesh
@@ -68,6 +69,9 @@ namespace dflo
       // descriptors of the register-blocked Qk stage kernel (row_desc.h), rowdesc_stride ints per tile
       std::vector<int> rowdesc;
       int rowdesc_stride = 0;
+      // fused halo exchange (p2p_halo.cuh): per tile, the owned cells a peer needs
+      std::vector<int> send_entries; // 3 ints per entry: local cell, peer index (into peers), destination cell on the peer
+      int n_send_tiles = 0;
    };
 
    constexpr int JOB_SHARED_FLAG = 8; // job flag beside DFLO_FACE_* (kernels.cuh JOB_SHARED): the flux also serves the neighbour slot
@@ -191,6 +195,32 @@ namespace dflo
          }
          tile_start.push_back (first + (int) queue.size ());
       }
+   }
+
+   // Sharded contexts: tiles that touch the partition cut (they own cells a peer needs and read
+   // ghost cells) come first in the tile order, so their results travel to the peers while the
+   // interior tiles are still being worked on.
+   inline void boundary_tiles_first (const dflo_flat_mesh &m, int b, int e, std::vector<int> &order, std::vector<int> &tile_start)
+   {
+      const int nt = (int) tile_start.size () - 1;
+      std::vector<char> cut (nt, 0);
+      for (int t = 0; t < nt; ++t)
+         for (int i = tile_start[t]; i < tile_start[t + 1] && !cut[t]; ++i)
+            for (int f = 0; f < 4; ++f)
+            {
+               const int nb = m.neighbor[4 * (size_t) order[i] + f];
+               if (nb >= 0 && (nb < b || nb >= e)) cut[t] = 1;
+            }
+      std::vector<int> o2, ts (1, 0);
+      for (int pass = 1; pass >= 0; --pass)
+         for (int t = 0; t < nt; ++t)
+            if (cut[t] == pass)
+            {
+               o2.insert (o2.end (), order.begin () + tile_start[t], order.begin () + tile_start[t + 1]);
+               ts.push_back ((int) o2.size ());
+            }
+      order.swap (o2);
+      tile_start.swap (ts);
    }
 
    // Unique-face job lists and tile halos (needs L.nbr / L.fflags / L.tile_start filled in)
@@ -400,6 +430,7 @@ namespace dflo
       L.tile_halo_max = 2 * (tile_x + tile_y);
       std::vector<int> order;
       order_owned_cells (m, L.begin, L.end, tile_x, tile_y, order, L.tile_start);
+      if (world > 1) boundary_tiles_first (m, L.begin, L.end, order, L.tile_start);
       L.n_tiles_owned = (int) L.tile_start.size () - 1;
       std::vector<int> owned_g2l (L.n_owned);
       for (int i = 0; i < L.n_owned; ++i)
@@ -471,7 +502,7 @@ namespace dflo
       for (int p = 0; p < world; ++p)
       {
          peers[p].rank = p;
-         for (int k = 0; k < 2; ++k) peers[p].recv_start[k] = peers[p].recv_count[k] = 0;
+         for (int k = 0; k < 2; ++k) peers[p].recv_start[k] = peers[p].recv_count[k] = peers[p].dst_start[k] = 0;
       }
       for (int k = 0; k < 2; ++k)
       {
@@ -489,15 +520,59 @@ namespace dflo
          if (p == rank) continue;
          std::vector<int> pg1, pg2;
          ghost_layers (m, world, p, layers, pg1, pg2);
-         for (int g : pg1)
-            if (g >= L.begin && g < L.end) peers[p].send_cells[0].push_back (owned_g2l[g - L.begin]);
-         for (int g : pg2)
-            if (g >= L.begin && g < L.end) peers[p].send_cells[1].push_back (owned_g2l[g - L.begin]);
+         int pb, pe;
+         partition_range (m.n_cells, world, p, pb, pe);
+         for (size_t i = 0; i < pg1.size (); ++i)
+            if (pg1[i] >= L.begin && pg1[i] < L.end)
+            {
+               if (peers[p].send_cells[0].empty ()) peers[p].dst_start[0] = (pe - pb) + (int) i;
+               peers[p].send_cells[0].push_back (owned_g2l[pg1[i] - L.begin]);
+            }
+         for (size_t i = 0; i < pg2.size (); ++i)
+            if (pg2[i] >= L.begin && pg2[i] < L.end)
+            {
+               if (peers[p].send_cells[1].empty ()) peers[p].dst_start[1] = (pe - pb) + (int) pg1.size () + (int) i;
+               peers[p].send_cells[1].push_back (owned_g2l[pg2[i] - L.begin]);
+            }
       }
       for (int p = 0; p < world; ++p)
          if (p != rank
              && (peers[p].recv_count[0] || peers[p].recv_count[1] || !peers[p].send_cells[0].empty () || !peers[p].send_cells[1].empty ()))
             L.peers.push_back (peers[p]);
+      if (row)
+      {
+         // per owned tile: which of its cells go where (fused exchange), and whether it reads ghosts
+         std::vector<std::vector<int>> per_tile (L.n_tiles);
+         std::vector<int> tile_of (L.n_owned, 0);
+         for (int t = 0; t < L.n_tiles_owned; ++t)
+            for (int c = L.tile_start[t]; c < L.tile_start[t + 1]; ++c) tile_of[c] = t;
+         for (size_t pi = 0; pi < L.peers.size (); ++pi)
+            for (int k = 0; k < 2; ++k)
+               for (size_t j = 0; j < L.peers[pi].send_cells[k].size (); ++j)
+               {
+                  const int c = L.peers[pi].send_cells[k][j];
+                  std::vector<int> &v = per_tile[tile_of[c]];
+                  v.push_back (c);
+                  v.push_back ((int) pi);
+                  v.push_back (L.peers[pi].dst_start[k] + (int) j);
+               }
+         L.send_entries.clear ();
+         L.n_send_tiles = 0;
+         const int nh = L.tile_halo_max;
+         for (int t = 0; t < L.n_tiles; ++t)
+         {
+            int *d = &L.rowdesc[(size_t) t * L.rowdesc_stride];
+            int reads_ghost = 0;
+            for (int i = 0; i < d[2]; ++i)
+               if (d[rowd_off_halo () + i] >= L.n_owned) reads_ghost = 1;
+            (void) nh;
+            d[5] = reads_ghost;
+            d[6] = (int) (L.send_entries.size () / 3);
+            d[7] = (int) (per_tile[t].size () / 3);
+            if (d[7]) ++L.n_send_tiles;
+            L.send_entries.insert (L.send_entries.end (), per_tile[t].begin (), per_tile[t].end ());
+         }
+      }
       return true;
    }
 }

@@ -25,6 +25,7 @@
 #pragma once
 
 #include "kernels.cuh"
+#include "p2p_halo.cuh"
 #include "row_desc.h"
 
 namespace dflo
@@ -248,6 +249,16 @@ namespace dflo
       // ---- stage the tile: per-cell bulk copies into the padded layout, descriptor, geometry ----
       if (tid == 0)
       {
+         if (A.fx && gdesc[5])
+         {
+            // fused halo exchange: this tile reads ghost cells -- the peers' stores of the previous
+            // exchange must have landed (boundary tiles run first, so this rarely spins)
+            const P2PFused &F = *A.fx;
+            // epochs[0] = number of the NEXT exchange to publish; the last published one is needed here
+            const unsigned long long e = *reinterpret_cast<volatile unsigned long long *> (F.epochs) - 1;
+            for (int p = 0; p < F.npeers; ++p)
+               while (ld_acquire_sys (F.my_flags + F.world + F.peer_rank[p]) < e) {}
+         }
          unsigned bytes = (unsigned) (ncb + nh) * cell_bytes + (unsigned) ncb * 32u + (unsigned) (S::DESC_INTS * sizeof (int));
          if (FLUX == FLUX_LXF) bytes += (unsigned) (ncb + nh) * 32u;
          mbar_init (sm, 1);
@@ -610,6 +621,9 @@ namespace dflo
          const double dt = A.dt_cell ? A.dt_cell[cell] : dt_global;
          const size_t goff = (size_t) cell * D + rb * N1;
          const double wbh = T.gw[rb] * hx * hy;
+         // a tile of redundantly updated ghost cells keeps only its means: the solution itself
+         // arrives with the halo exchange (possibly before this tile runs)
+         const bool owned_tile = (int) blockIdx.x < A.n_tiles_owned;
          double part[4];
 #pragma unroll
          for (int c = 0; c < 4; ++c)
@@ -633,7 +647,7 @@ namespace dflo
                   v[a] = need_old ? (1.0 - A.ark) * un + A.ark * uold[c][a] : un;
                }
             }
-            store_line<N1> (A.out + goff + c * NS, v);
+            if (owned_tile) store_line<N1> (A.out + goff + c * NS, v);
             double s = 0.0;
 #pragma unroll
             for (int a = 0; a < N1; ++a) s = fma (T.gw[a], v[a], s);
@@ -667,6 +681,56 @@ namespace dflo
 #pragma unroll
             for (int b = 0; b < N1; ++b) v += sPart[(s * N1 + b) * 4 + c];
             A.avg_out[(size_t) c0 * 4 + j] = v;
+         }
+      }
+
+      // ================= fused halo exchange over peer memory (p2p_halo.cuh) =================
+      if (A.fx)
+      {
+         const P2PFused &F = *A.fx;
+         const int n_send = gdesc[7];
+         if (A.mode == MODE_STAGE && n_send > 0)
+         {
+            __syncthreads (); // the tile's write-back is complete and visible to the block
+            const int *ent = F.send_entries + 3 * (size_t) gdesc[6];
+            constexpr int D2 = D / 2;
+            for (int i = tid; i < n_send * D2; i += S::THREADS)
+            {
+               const int e = i / D2, c = i - e * D2;
+               const int cell = ent[3 * e], pi = ent[3 * e + 1], dc = ent[3 * e + 2];
+               reinterpret_cast<double2 *> (F.dstU[pi] + (size_t) dc * D)[c] = __ldcg (reinterpret_cast<const double2 *> (A.out + (size_t) cell * D) + c);
+            }
+            for (int i = tid; i < n_send * 2; i += S::THREADS)
+            {
+               const int e = i >> 1;
+               const int cell = ent[3 * e], pi = ent[3 * e + 1], dc = ent[3 * e + 2];
+               reinterpret_cast<double2 *> (F.dstA[pi] + (size_t) dc * 4)[i & 1] = __ldcg (reinterpret_cast<const double2 *> (A.avg_out + (size_t) cell * 4) + (i & 1));
+            }
+            __threadfence ();
+            __syncthreads ();
+            if (tid == 0)
+            {
+               const unsigned int done = atomicAdd (F.send_counter, 1u);
+               if (done == (unsigned int) F.n_send_tiles - 1)
+               {
+                  // last sending tile of this stage: everything the peers need is on its way
+                  *F.send_counter = 0;
+                  __threadfence_system ();
+                  const unsigned long long e = *reinterpret_cast<volatile unsigned long long *> (F.epochs);
+                  for (int p = 0; p < F.npeers; ++p) st_release_sys (F.peer_flags[p] + F.world + F.me, e);
+               }
+            }
+         }
+         if (tid == 0)
+         {
+            // the epoch advances when the LAST block of the launch retires: every tile that waits
+            // or publishes has read it by then
+            const unsigned int done = atomicAdd (F.block_counter, 1u);
+            if (done == gridDim.x - 1)
+            {
+               *F.block_counter = 0;
+               if (A.mode == MODE_STAGE) *F.epochs = *reinterpret_cast<volatile unsigned long long *> (F.epochs) + 1;
+            }
          }
       }
    }

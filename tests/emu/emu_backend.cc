@@ -65,6 +65,12 @@ namespace
       void prepare_tables (const dflo::FeTables &) {}
       int stage_prefetch_tiles () const { return 0; }
       int debug_flags () const { return 0; }
+      // peer-memory halo exists only on the CUDA backend
+      template <class P, class V> void p2p_setup (double **, double **, const P &, const V *, int, const int *, int) {}
+      bool p2p_fused_ok () const { return false; }
+      const dflo::P2PFused *p2p_fused_args (int) const { return nullptr; }
+      void p2p_teardown () {}
+      bool p2p_exchange (int) { return false; }
       template <class K> void launch1d (int n, const typename K::Args &a)
       {
          ++launches;
