@@ -286,7 +286,15 @@ namespace dflo
    void launch_limiter (BK &bk, int basis, int n1, const LimiterArgs &a)
    {
       if (n1 == 1) return;
-#define DFLO_LIM(B, N) bk.template launch<LimiterKernel<B, N>> (LimiterKernel<B, N>::grid (a.n_compute), a)
+      // one thread per cell (LimiterCellKernel); DFLO_B200_LIMITER=block selects the block-per-cells form
+#define DFLO_LIM(B, N)                                                                          \
+   do                                                                                           \
+   {                                                                                            \
+      if (bk.limiter_block_form ())                                                             \
+         bk.template launch<LimiterKernel<B, N>> (LimiterKernel<B, N>::grid (a.n_compute), a);  \
+      else                                                                                      \
+         bk.template launch1d<LimiterCellKernel<B, N>> (a.n_compute, a);                        \
+   } while (0)
       if (basis == BASIS_QK)
       {
          if (n1 == 2) DFLO_LIM (BASIS_QK, 2);

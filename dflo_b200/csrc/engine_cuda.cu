@@ -265,6 +265,11 @@ namespace
          static const char *e = std::getenv ("DFLO_B200_PF_TILES");
          return e ? std::atoi (e) : n_sm * DFLO_ROW_MIN_BLOCKS;
       }
+      bool limiter_block_form () const
+      {
+         static const char *e = std::getenv ("DFLO_B200_LIMITER");
+         return e && std::string (e) == "block";
+      }
       int debug_flags () const
       {
          static const char *e = std::getenv ("DFLO_B200_DBG");

@@ -1159,6 +1159,324 @@ namespace dflo
    };
 
    //---------------------------------------------------------------------------------------------
+   // The same limiters as LimiterKernel, one THREAD per cell (thread_kernel form).  The block form
+   // above spends most of its time in block barriers around steps that only one thread per cell
+   // can do (the characteristic minmod decision, the theta reductions); here a thread walks
+   // through all steps of its cell on its own, reading the cell's DoFs straight from global memory
+   // (consecutive loads of a thread hit the L1 sectors its earlier loads brought in) and writing
+   // only if the cell changes -- which on most cells of most stages it does not.  Every
+   // arithmetic expression is the one of LimiterKernel, in the same order, so both forms give
+   // bit-identical results.
+   //---------------------------------------------------------------------------------------------
+   template <int BASIS, int N1>
+   struct LimiterCellKernel
+   {
+      typedef LimiterArgs Args;
+      typedef LimiterKernel<BASIS, N1> LK;
+      static constexpr int NS = LK::NS, D = LK::D, NGLL = LK::NGLL, NPOS = LK::NPOS;
+
+      static DFLO_DEV void thread (const Args &A, int cell)
+      {
+         if (N1 == 1 || cell >= A.n_compute) return; // degree 0: both limiters return at once
+         const double *tb = A.tab;
+         double *uc = A.u + (size_t) cell * D;
+         const double eps = 1.0e-13;
+         double av[4];
+#pragma unroll
+         for (int c = 0; c < 4; ++c) av[c] = A.avg[(size_t) cell * 4 + c];
+         int flag = 0;
+         // Qk: smallest / largest nodal value per component, kept up to date for the positivity
+         // fast path below
+         double lo[4] = {1.0e300, 1.0e300, 1.0e300, 1.0e300}, hi[4] = {-1.0e300, -1.0e300, -1.0e300, -1.0e300};
+         bool have_bounds = false;
+
+         if (A.tvb)
+         {
+            const double hx = A.geom[(size_t) cell * 4 + 2], hy = A.geom[(size_t) cell * 4 + 3];
+            const double dx = sqrt (hx * hx + hy * hy) / 1.4142135623730951; // diameter / sqrt(dim)
+            const double Mdx2 = A.M * dx * dx;
+            const double beta = (BASIS == BASIS_QK) ? A.beta : 0.5 * A.beta;
+            double Dx[4], Dy[4], dbx[4], dfx[4], dby[4], dfy[4];
+            // mean slopes of the cell, limiter.cc:268-281 (Qk) / 412-420 (Pk)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+               double sx = 0.0, sy = 0.0;
+               if (BASIS == BASIS_QK)
+               {
+                  const double *gw = LK::t_gw (tb), *gd = LK::t_gdiff (tb);
+                  for (int b = 0; b < N1; ++b)
+                     for (int a = 0; a < N1; ++a)
+                     {
+                        const double u = uc[c * NS + a + N1 * b];
+                        sx += (gd[a] * gw[b]) * u;
+                        sy += (gw[a] * gd[b]) * u;
+                        lo[c] = std_min (lo[c], u);
+                        hi[c] = std_max (hi[c], u);
+                     }
+                  Dx[c] = dx * (sx / hx);
+                  Dy[c] = dx * (sy / hy);
+               }
+               else
+               {
+                  Dx[c] = uc[c * NS + 1] * 1.7320508075688772; // sqrt(3); base index 1 / k+1
+                  Dy[c] = uc[c * NS + N1] * 1.7320508075688772;
+               }
+               dbx[c] = dfx[c] = Dx[c];
+               dby[c] = dfy[c] = Dy[c];
+            }
+            have_bounds = BASIS == BASIS_QK;
+            const double ang_mom = Dx[1] - Dy[0];
+            // lcell/rcell/bcell/tcell (claw.cc:357-379); periodic partners count as neighbours
+            for (int f = 0; f < 4; ++f)
+            {
+               const int nb = A.nbr[(size_t) cell * 4 + f];
+               if (nb < 0) continue;
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  const double an = A.avg[(size_t) nb * 4 + c];
+                  if (f == 0) dbx[c] = av[c] - an;
+                  if (f == 1) dfx[c] = an - av[c];
+                  if (f == 2) dby[c] = av[c] - an;
+                  if (f == 3) dfy[c] = an - av[c];
+               }
+            }
+            EigenMatrices em;
+            if (A.char_lim)
+            {
+               compute_eigen_matrix (av, em);
+               transform_to_char (em.Lx, dbx);
+               transform_to_char (em.Lx, dfx);
+               transform_to_char (em.Ly, dby);
+               transform_to_char (em.Ly, dfy);
+               transform_to_char (em.Lx, Dx);
+               transform_to_char (em.Ly, Dy);
+            }
+            double Dxn[4], Dyn[4], change_x = 0.0, change_y = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+               Dxn[c] = minmod (Dx[c], beta * dbx[c], beta * dfx[c], Mdx2);
+               Dyn[c] = minmod (Dy[c], beta * dby[c], beta * dfy[c], Mdx2);
+               change_x += fabs (Dxn[c] - Dx[c]);
+               change_y += fabs (Dyn[c] - Dy[c]);
+            }
+            change_x /= 4;
+            change_y /= 4;
+            if (change_x + change_y > 1.0e-10)
+            {
+               if (BASIS == BASIS_QK)
+               {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                  {
+                     Dxn[c] /= dx;
+                     Dyn[c] /= dx;
+                  }
+               }
+               if (A.char_lim)
+               {
+                  transform_to_con (em.Rx, Dxn);
+                  transform_to_con (em.Ry, Dyn);
+               }
+               if (BASIS == BASIS_PK && A.cam) // limiter.cc:496-500
+               {
+                  Dyn[0] = 0.5 * (Dyn[0] - (ang_mom - Dxn[1]));
+                  Dxn[1] = ang_mom + Dyn[0];
+               }
+               flag |= 1;
+               // rewrite the cell as mean + limited linear part (limiter.cc:356-366 / 501-511)
+               if (BASIS == BASIS_QK)
+               {
+                  const double *gx = LK::t_gx (tb);
+                  const double x0 = A.geom[(size_t) cell * 4 + 0], y0 = A.geom[(size_t) cell * 4 + 1];
+                  for (int b = 0; b < N1; ++b)
+                     for (int a = 0; a < N1; ++a)
+                     {
+                        const double dr0 = (x0 + gx[a] * hx) - (x0 + 0.5 * hx);
+                        const double dr1 = (y0 + gx[b] * hy) - (y0 + 0.5 * hy);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                        {
+                           const double v = av[c] + dr0 * Dxn[c] + dr1 * Dyn[c];
+                           uc[c * NS + a + N1 * b] = v;
+                           lo[c] = (a + b == 0) ? v : std_min (lo[c], v);
+                           hi[c] = (a + b == 0) ? v : std_max (hi[c], v);
+                        }
+                     }
+               }
+               else
+               {
+                  for (int m = 1; m < NS; ++m)
+#pragma unroll
+                     for (int c = 0; c < 4; ++c)
+                     {
+                        double v = 0.0;
+                        if (m == 1) v = Dxn[c] / 1.7320508075688772;
+                        if (m == N1) v = Dyn[c] / 1.7320508075688772;
+                        uc[c * NS + m] = v;
+                     }
+               }
+            }
+         }
+
+         if (A.pos_lim)
+         {
+            if (std_min (av[RHO], pressure (av)) < eps) // positivity.cc:26-39
+            {
+#if defined(__CUDA_ARCH__)
+               atomicOr (A.err, (unsigned int) ERR_NEGATIVE_STATE);
+#else
+               *A.err |= ERR_NEGATIVE_STATE;
+#endif
+            }
+            // Fast path.  Rigorous bounds on every component at every positivity point from the
+            // cell's own coefficients (Qk: nodal range times the positive / negative weight sums of
+            // the 1-D interpolation to the GLL points; Pk: mean +- sum |mode| max|basis|).  If even
+            // the bounds keep density and pressure away from the thresholds by a margin far above
+            // round-off, the exact evaluation below would return theta1 = theta2 = 1: nothing to do.
+            {
+               double vlo[4], vhi[4];
+               if (BASIS == BASIS_QK)
+               {
+                  if (!have_bounds)
+                     for (int m = 0; m < NS; ++m)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                        {
+                           const double u = uc[c * NS + m];
+                           lo[c] = std_min (lo[c], u);
+                           hi[c] = std_max (hi[c], u);
+                        }
+                  const double *gli = LK::t_gli (tb);
+                  double wp = 1.0, wm = 0.0; // the Gauss direction of a point set is the identity
+                  for (int j = 0; j < NGLL; ++j)
+                  {
+                     double p = 0.0, q = 0.0;
+                     for (int a = 0; a < N1; ++a)
+                     {
+                        const double w = gli[j * N1 + a];
+                        p += std_max (w, 0.0);
+                        q += std_min (w, 0.0);
+                     }
+                     wp = std_max (wp, p);
+                     wm = std_min (wm, q);
+                  }
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                  {
+                     vlo[c] = wp * lo[c] + wm * hi[c];
+                     vhi[c] = wp * hi[c] + wm * lo[c];
+                  }
+               }
+               else
+               {
+                  const double *pp = LK::t_phipos (tb);
+                  double spread[4] = {0.0, 0.0, 0.0, 0.0};
+                  for (int m = 1; m < NS; ++m)
+                  {
+                     double cm = 0.0;
+                     for (int i = 0; i < 2 * NPOS; ++i) cm = std_max (cm, fabs (pp[i * NS + m]));
+#pragma unroll
+                     for (int c = 0; c < 4; ++c) spread[c] += cm * fabs (uc[c * NS + m]);
+                  }
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                  {
+                     vlo[c] = uc[c * NS] - spread[c];
+                     vhi[c] = uc[c * NS] + spread[c];
+                  }
+               }
+               const double m0 = std_max (fabs (vlo[0]), fabs (vhi[0])), m1 = std_max (fabs (vlo[1]), fabs (vhi[1]));
+               const double scale = 1.0 + std_max (fabs (vhi[ENE]), std_max (fabs (vhi[RHO]), std_max (m0, m1)));
+               const double margin = 1.0e-9 * scale;
+               if (vlo[RHO] > margin && GM1 * (vlo[ENE] - 0.5 * (m0 * m0 + m1 * m1) / vlo[RHO]) > margin)
+               {
+                  if (A.flags_out) A.flags_out[cell] = flag;
+                  return;
+               }
+            }
+            // density at the GLL x Gauss point sets (positivity.cc:68-78)
+            double rho_min = 1.0e20;
+            for (int i = 0; i < 2 * NPOS; ++i) rho_min = std_min (rho_min, LK::point_value (tb, uc, i / NPOS, i % NPOS, RHO));
+            const double rat = fabs (av[RHO] - eps) / (fabs (av[RHO] - rho_min) + 1.0e-13);
+            const double theta1 = std_min (rat, 1.0);
+            if (theta1 < 1.0)
+            {
+               flag += 2;
+               // scale density about its mean (positivity.cc:85-110)
+               for (int m = 0; m < NS; ++m)
+               {
+                  if (BASIS == BASIS_QK)
+                     uc[RHO * NS + m] = theta1 * uc[RHO * NS + m] + (1.0 - theta1) * av[RHO];
+                  else if (m > 0)
+                     uc[RHO * NS + m] *= theta1;
+               }
+            }
+            // pressure at every point; where negative, the admissible fraction t towards the mean
+            // (positivity.cc:134-179)
+            double theta2 = 1.0;
+            for (int idx = 0; idx < 2 * NPOS; ++idx)
+            {
+               const int set = idx / NPOS, pt = idx % NPOS;
+               const double mx = LK::point_value (tb, uc, set, pt, 0);
+               const double my = LK::point_value (tb, uc, set, pt, 1);
+               const double rho = LK::point_value (tb, uc, set, pt, RHO);
+               const double E = LK::point_value (tb, uc, set, pt, ENE);
+               const double pre = GM1 * (E - 0.5 * (mx * mx + my * my) / rho);
+               double t = 1.0;
+               if (pre < eps)
+               {
+                  const double drho = rho - av[RHO];
+                  const double dm0 = mx - av[0], dm1 = my - av[1];
+                  const double dE = E - av[ENE];
+                  const double a1 = 2.0 * drho * dE - (dm0 * dm0 + dm1 * dm1);
+                  double b1 = 2.0 * drho * (av[ENE] - eps / GM1) + 2.0 * av[RHO] * dE - 2.0 * (av[0] * dm0 + av[1] * dm1);
+                  double c1 = 2.0 * av[RHO] * av[ENE] - (av[0] * av[0] + av[1] * av[1]) - 2.0 * eps * av[RHO] / GM1;
+                  b1 /= a1;
+                  c1 /= a1;
+                  const double Dd = sqrt (fabs (b1 * b1 - 4.0 * c1));
+                  const double t1 = 0.5 * (-b1 - Dd), t2 = 0.5 * (-b1 + Dd);
+                  if (t1 > -1.0e-12 && t1 < 1.0 + 1.0e-12)
+                     t = t1;
+                  else if (t2 > -1.0e-12 && t2 < 1.0 + 1.0e-12)
+                     t = t2;
+                  else
+                  {
+                     t = 0.0;
+#if defined(__CUDA_ARCH__)
+                     atomicOr (A.err, (unsigned int) ERR_POSLIM_ROOT);
+#else
+                     *A.err |= ERR_POSLIM_ROOT;
+#endif
+                  }
+                  t = std_min (1.0, t);
+                  t = std_max (0.0, t);
+                  if (fabs (1.0 - t) < 1.0e-14) t = 0.0;
+               }
+               theta2 = std_min (theta2, t);
+            }
+            if (theta2 < 1.0)
+            {
+               flag += 4;
+               // scale all components about the mean (positivity.cc:182-206)
+               for (int m = 0; m < NS; ++m)
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                  {
+                     if (BASIS == BASIS_QK)
+                        uc[c * NS + m] = theta2 * uc[c * NS + m] + (1.0 - theta2) * av[c];
+                     else if (m > 0)
+                        uc[c * NS + m] *= theta2;
+                  }
+            }
+         }
+         if (A.flags_out) A.flags_out[cell] = flag;
+      }
+   };
+
+   //---------------------------------------------------------------------------------------------
    // compute_time_step_cartesian, claw.cc:484-511: per-cell dt from the cell averages
    //---------------------------------------------------------------------------------------------
    DFLO_DEV double cell_time_step (const double *avg, const double *geom, double cfl, int degree)

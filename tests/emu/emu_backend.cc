@@ -10,6 +10,7 @@
 
 #include <cstdlib>
 #include <map>
+#include <string>
 #include <vector>
 
 namespace
@@ -65,6 +66,7 @@ namespace
       void prepare_tables (const dflo::FeTables &) {}
       int stage_prefetch_tiles () const { return 0; }
       int debug_flags () const { return 0; }
+      bool limiter_block_form () const { static const char *e = std::getenv ("DFLO_EMU_LIMITER"); return e && std::string (e) == "block"; }
       // peer-memory halo exists only on the CUDA backend
       template <class P, class V> void p2p_setup (double **, double **, const P &, const V *, int, const int *, int) {}
       bool p2p_fused_ok () const { return false; }
