@@ -293,7 +293,7 @@ namespace dflo
       if (bk.limiter_block_form ())                                                             \
          bk.template launch<LimiterKernel<B, N>> (LimiterKernel<B, N>::grid (a.n_compute), a);  \
       else                                                                                      \
-         bk.template launch1d<LimiterCellKernel<B, N>> (a.n_compute, a);                        \
+         bk.template launch<LimiterCellKernel<B, N>> (LimiterCellKernel<B, N>::grid (a.n_compute), a); \
    } while (0)
       if (basis == BASIS_QK)
       {

@@ -1174,12 +1174,42 @@ namespace dflo
       typedef LimiterArgs Args;
       typedef LimiterKernel<BASIS, N1> LK;
       static constexpr int NS = LK::NS, D = LK::D, NGLL = LK::NGLL, NPOS = LK::NPOS;
+      // block form: CPB cells are staged with coalesced loads into shared memory (odd row stride:
+      // the per-thread walks over a cell are then free of bank conflicts), one thread per cell
+      // works on its row, changed cells are written back
+      static constexpr int THREADS = D > 64 ? 64 : 128;
+      static constexpr int CPB = THREADS;
+      static constexpr int MIN_BLOCKS = 1;
+      static constexpr int NPHASE = 2;
+      static constexpr int ROW = D + 1;
+      static constexpr int SMEM_DOUBLES = CPB * ROW;
+      static int grid (int n_compute) { return (n_compute + CPB - 1) / CPB; }
 
-      static DFLO_DEV void thread (const Args &A, int cell)
+      static DFLO_DEV void phase (int p, const Args &A, double *sm, int tid, int bid)
       {
-         if (N1 == 1 || cell >= A.n_compute) return; // degree 0: both limiters return at once
+         if (N1 == 1) return; // degree 0: both limiters return at once
+         const int c0 = bid * CPB;
+         const int ncb = (A.n_compute - c0 < CPB) ? A.n_compute - c0 : CPB;
+         if (p == 0)
+         {
+            const double *src = A.u + (size_t) c0 * D;
+            for (int i = tid; i < ncb * D; i += THREADS) sm[(i / D) * ROW + (i % D)] = src[i];
+         }
+         else if (tid < ncb)
+         {
+            double *uc = sm + tid * ROW;
+            if (cell_work (A, c0 + tid, uc))
+            {
+               double *dst = A.u + (size_t) (c0 + tid) * D;
+               for (int i = 0; i < D; ++i) dst[i] = uc[i];
+            }
+         }
+      }
+
+      // all limiter steps of one cell on its DoFs uc (in place); returns true if they changed
+      static DFLO_DEV bool cell_work (const Args &A, int cell, double *uc)
+      {
          const double *tb = A.tab;
-         double *uc = A.u + (size_t) cell * D;
          const double eps = 1.0e-13;
          double av[4];
 #pragma unroll
@@ -1211,8 +1241,11 @@ namespace dflo
                         const double u = uc[c * NS + a + N1 * b];
                         sx += (gd[a] * gw[b]) * u;
                         sy += (gw[a] * gd[b]) * u;
-                        lo[c] = std_min (lo[c], u);
-                        hi[c] = std_max (hi[c], u);
+                        if (A.pos_lim)
+                        {
+                           lo[c] = std_min (lo[c], u);
+                           hi[c] = std_max (hi[c], u);
+                        }
                      }
                   Dx[c] = dx * (sx / hx);
                   Dy[c] = dx * (sy / hy);
@@ -1394,7 +1427,7 @@ namespace dflo
                if (vlo[RHO] > margin && GM1 * (vlo[ENE] - 0.5 * (m0 * m0 + m1 * m1) / vlo[RHO]) > margin)
                {
                   if (A.flags_out) A.flags_out[cell] = flag;
-                  return;
+                  return flag != 0;
                }
             }
             // density at the GLL x Gauss point sets (positivity.cc:68-78)
@@ -1473,6 +1506,7 @@ namespace dflo
             }
          }
          if (A.flags_out) A.flags_out[cell] = flag;
+         return flag != 0;
       }
    };
 
