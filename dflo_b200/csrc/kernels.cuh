@@ -96,6 +96,7 @@ namespace dflo
       int pf_tiles;           // row kernel: prefetch distance in tiles (resident blocks of the device)
       int n_tiles_owned;      // tiles >= this one are redundantly updated ghost cells: only their means are stored
       const P2PFused *fx;     // row kernel: halo exchange over peer memory fused into the stage kernel, or nullptr
+      long long *trace;       // developer timeline (DFLO_B200_DBG & 8): 8 clock stamps per block, or nullptr
       int dbg;                // developer timing experiments only (DFLO_B200_DBG): 1 no Riemann solves, 2 no volume fluxes, 4 no extra-warp jobs
       int mode;
       int compat_mpi;
