@@ -9,7 +9,8 @@ M^-1, RK combine, cell average, configured limiters) over the whole mesh; one Do
 scalar unknown advanced through one RK stage.  Workload at N = 1: BASELINE.json configs[1]
 (isentropic vortex, Q3, 256x256 Cartesian cells, periodic, Roe flux, SSP-RK3).  For N > 1 the
 per-GPU work is kept (weak scaling): the periodic box is extended to 256N x 256 cells and sharded
-by cell id, one NCCL halo exchange per stage.
+by cell id, one halo exchange per stage stored straight into the peers' memory over NVLink
+(fused into the stage kernel; NCCL send/recv as fallback).
 
 Timing: `value` = device-resident throughput: every step is one dflo_b200_advance() call (CUDA
 graph replay) timed with CUDA events on the ctx stream; L2 (126 MB) is flushed before every timed
@@ -326,7 +327,8 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "cells": nx * ny, "dofs": n_dof, "rk_stages": n_rk,
-                       "parallelism": "cells sharded by id over %d GPU(s), 1 NCCL halo exchange per stage" % world,
+                       "parallelism": "cells sharded by id over %d GPU(s), 1 halo exchange per stage over NVLink peer memory "
+                                      "(fused into the stage kernel)" % world,
                        "l2": "flushed before every timed step (256 MB rewrite)" if flush is not None else "not flushed",
                        "timing": "CUDA events on the ctx stream around each step's graph launch, summed, max over ranks"},
             "value_back_to_back_no_flush": updates_per_step * args.steps / (ms_b2b * 1e-3) / 1e6,
