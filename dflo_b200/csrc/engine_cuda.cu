@@ -292,33 +292,8 @@ namespace
          note (cudaMemcpyToSymbolAsync (dflo::c_row, &rc, sizeof (rc), (size_t) t.n1 * sizeof (rc), cudaMemcpyHostToDevice, stream));
          note (cudaStreamSynchronize (stream));
       }
-      // pipelined persistent form of the row kernel, opt-in with DFLO_B200_ROW_PIPE=1: it hides the staging
-      // latency but fits only 3 blocks (12 main warps) per SM and measures slower than 4 one-tile blocks
-      template <int N1, int FLUX> void launch_row_pipelined (int n_tiles, const dflo::StageArgs &a)
-      {
-         typedef dflo::RowShape<N1, FLUX> S;
-         typedef dflo::RowPersist<N1, FLUX> P;
-         constexpr size_t smem = P::SMEM_DOUBLES * sizeof (double);
-         static int blocks_per_sm = -1;
-         if (blocks_per_sm < 0)
-         {
-            note (cudaFuncSetAttribute (dflo::row_stage_pipelined_kernel<N1, FLUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            int n = 0;
-            note (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&n, dflo::row_stage_pipelined_kernel<N1, FLUX>, S::THREADS, smem));
-            blocks_per_sm = n > 0 ? n : 1;
-         }
-         ++launches;
-         dflo::row_stage_pipelined_kernel<N1, FLUX><<<std::min (n_tiles, n_sm * blocks_per_sm), S::THREADS, smem, stream>>> (a, n_tiles);
-         note (cudaPeekAtLastError ());
-      }
       template <int N1, int FLUX> void launch_row (int n_tiles, const dflo::StageArgs &a)
       {
-         static const bool pipe = std::getenv ("DFLO_B200_ROW_PIPE") && std::atoi (std::getenv ("DFLO_B200_ROW_PIPE")) != 0;
-         if (pipe && N1 <= 4)
-         {
-            launch_row_pipelined<N1, FLUX> (n_tiles, a);
-            return;
-         }
          typedef dflo::RowShape<N1, FLUX> S;
          constexpr size_t smem = S::SMEM_DOUBLES * sizeof (double);
          static const cudaError_t rc = cudaFuncSetAttribute (dflo::row_stage_kernel<N1, FLUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);

@@ -231,35 +231,78 @@ namespace dflo
       H[3] = G[3];
    }
 
-   // where the pieces of one tile live in shared memory
-   struct RowView
-   {
-      double *tile, *halo; // staged DoFs, padded cell stride CS: tile cells, halo cells
-      double *sR, *sT, *sG, *sGeom, *sAvg, *sPart;
-      int *sdesc;
-   };
-
-#define DFLO_STAMP(i) do { if (A.trace && threadIdx.x == 0) A.trace[(size_t) tile_index * 8 + (i)] = clock64 (); } while (0)
-
-   // Everything after the staging of one tile: traces, Riemann problems, volume terms and lifting,
-   // update and write-back, the fused halo stores.  Block-wide barriers inside: every thread of
-   // the block calls it.
-   struct NoHook
-   {
-      __device__ __forceinline__ void operator() () const {}
-   };
-
-   template <int N1, int FLUX, class Hook>
-   __device__ __forceinline__ void row_tile_compute (const StageArgs &A, const RowView &V, int tile_index, int c0, int ncb, double dt_global,
-                                                     bool need_old, const Hook &idle_hook)
+   template <int N1, int FLUX>
+   __global__ void __launch_bounds__ (RowShape<N1, FLUX>::THREADS, RowShape<N1, FLUX>::MIN_BLOCKS) row_stage_kernel (const StageArgs A)
    {
       typedef RowShape<N1, FLUX> S;
       constexpr int NS = S::NS, D = S::D, TC = S::TC, CS = S::CS, TH = S::T_HALF;
+      extern __shared__ __align__ (16) double sm[];
+      double *su = sm + S::O_U, *sR = sm + S::O_R, *sT = sm + S::O_T, *sG = sm + S::O_G, *sGeom = sm + S::O_GEOM, *sAvg = sm + S::O_AVG;
+      int *sdesc = reinterpret_cast<int *> (sm + S::O_DESC);
       const RowConst &T = c_row[N1];
       const int tid = threadIdx.x;
-      double *sR = V.sR, *sT = V.sT, *sG = V.sG, *sGeom = V.sGeom, *sAvg = V.sAvg;
-      int *sdesc = V.sdesc;
-      auto cell_ptr = [&] (int slot) -> const double * { return slot < TC ? V.tile + slot * CS : V.halo + (slot - TC) * CS; };
+      const int *gdesc = A.rowdesc + (size_t) blockIdx.x * S::DESC_INTS;
+      const int c0 = gdesc[0], ncb = gdesc[1], nh = gdesc[2];
+      const bool need_old = A.mode == MODE_STAGE && A.ark != 0.0;
+      constexpr unsigned cell_bytes = (unsigned) (D * sizeof (double));
+
+      // ---- stage the tile: per-cell bulk copies into the padded layout, descriptor, geometry ----
+      if (tid == 0)
+      {
+         if (A.fx && gdesc[5])
+         {
+            // fused halo exchange: this tile reads ghost cells -- the peers' stores of the previous
+            // exchange must have landed (boundary tiles run first, so this rarely spins)
+            const P2PFused &F = *A.fx;
+            // epochs[0] = number of the NEXT exchange to publish; the last published one is needed here
+            const unsigned long long e = *reinterpret_cast<volatile unsigned long long *> (F.epochs) - 1;
+            for (int p = 0; p < F.npeers; ++p)
+               while (ld_acquire_sys (F.my_flags + F.world + F.peer_rank[p]) < e) {}
+         }
+         unsigned bytes = (unsigned) (ncb + nh) * cell_bytes + (unsigned) ncb * 32u + (unsigned) (S::DESC_INTS * sizeof (int));
+         if (FLUX == FLUX_LXF) bytes += (unsigned) (ncb + nh) * 32u;
+         mbar_init (sm, 1);
+         mbar_expect_tx (sm, bytes);
+      }
+      __syncthreads ();
+      if (DFLO_ROW_PAD == 0 && tid < ncb)
+      {
+         if (tid == 0) bulk_g2s (su, A.u + (size_t) c0 * D, (unsigned) ncb * cell_bytes, sm);
+         if (FLUX == FLUX_LXF) bulk_g2s (sAvg + tid * 4, A.avg + (size_t) (c0 + tid) * 4, 32u, sm);
+      }
+      else if (tid < ncb + nh)
+      {
+         const int cell = tid < ncb ? c0 + tid : gdesc[S::OFF_HALO + tid - ncb];
+         const int slot = tid < ncb ? tid : TC + tid - ncb;
+         bulk_g2s (su + slot * CS, A.u + (size_t) cell * D, cell_bytes, sm);
+         if (FLUX == FLUX_LXF) bulk_g2s (sAvg + slot * 4, A.avg + (size_t) cell * 4, 32u, sm);
+      }
+      else if (tid == S::THREADS - 1)
+      {
+         bulk_g2s (sdesc, gdesc, (unsigned) (S::DESC_INTS * sizeof (int)), sm);
+         bulk_g2s (sGeom, A.geom + (size_t) c0 * 4, (unsigned) ncb * 32u, sm);
+         if (need_old)
+            asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u_old + (size_t) c0 * D), "r"((unsigned) ncb * cell_bytes) : "memory");
+      }
+      else if (tid == S::THREADS - 2)
+      {
+         // Pull the inputs of the tile that will run in this block's slot a wave later from HBM
+         // into L2 now (a hint: on a uniform tiling that tile starts pf_tiles * TC cells further on)
+         const int bt = (int) blockIdx.x + A.pf_tiles;
+         if (bt < (int) gridDim.x)
+         {
+            const size_t pc0 = (size_t) c0 + (size_t) A.pf_tiles * TC;
+            if (pc0 + TC <= (size_t) A.n_cells_u)
+            {
+               asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u + pc0 * D), "r"((unsigned) TC * cell_bytes) : "memory");
+               if (need_old) asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u_old + pc0 * D), "r"((unsigned) TC * cell_bytes) : "memory");
+            }
+            asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.rowdesc + (size_t) bt * S::DESC_INTS), "r"((unsigned) (S::DESC_INTS * sizeof (int))) : "memory");
+         }
+      }
+      const double dt_global = A.time[1]; // issued before the wait: its latency hides behind the staging
+      mbar_wait (sm, 0);
+
       const bool main_thread = tid < S::MAIN;
       // row role: cell slot rs, Gauss row rb;  column role: cell slot cs, Gauss column ca
       const int rs = tid / N1, rb = tid % N1;
@@ -274,7 +317,7 @@ namespace dflo
       // ================= P1: traces =================
       if (row_on)
       {
-         const double *uc = V.tile + rs * CS + rb * N1;
+         const double *uc = su + rs * CS + rb * N1;
          double WL[4];
 #pragma unroll
          for (int c = 0; c < 4; ++c)
@@ -295,7 +338,7 @@ namespace dflo
       }
       if (col_on)
       {
-         const double *uc = V.tile + cs * CS + ca;
+         const double *uc = su + cs * CS + ca;
          double WB[4];
 #pragma unroll
          for (int c = 0; c < 4; ++c)
@@ -324,12 +367,11 @@ namespace dflo
             const int slot = code & 0xffff, dir = (code >> 16) & 1;
             const int qq = (code & ROWD_FLIP) ? N1 - 1 - q : q;
             double W[4];
-            row_trace<N1> (cell_ptr (slot), 2 * dir, qq, W);
+            row_trace<N1> (su + slot * CS, 2 * dir, qq, W);
             store4 (sG + j * 4, W);
          }
       }
       __syncthreads ();
-      DFLO_STAMP (3);
 
       // ================= P2: Riemann problems =================
       if (row_on)
@@ -438,7 +480,7 @@ namespace dflo
             if (nb >= 0)
             {
                const int qn = (w0 & ROWD_FLIP) ? N1 - 1 - q : q;
-               row_trace<N1> (cell_ptr (nb), 2 * dir + 1, qn, Wn);
+               row_trace<N1> (su + nb * CS, 2 * dir + 1, qn, Wn);
                if (FLUX == FLUX_LXF) load4 (sAvg + nb * 4, An);
             }
             else
@@ -465,7 +507,6 @@ namespace dflo
          }
       }
       __syncthreads ();
-      DFLO_STAMP (4);
 
       // ================= P3: volume terms and lifting =================
       // the low-face fluxes move to registers; after the barrier the exchange arrays are dead and
@@ -474,14 +515,12 @@ namespace dflo
       if (row_on) load_pt<TH> (sT, pT_row, HL);
       if (col_on) load_pt<TH> (sT, pT_col, HB);
       __syncthreads ();
-      // the edge-job warp has nothing to do from here on: the pipelined kernel lets it stage the next tile
-      if (!main_thread) idle_hook ();
       double rrow[4][N1], uold[4][N1];
       if (col_on)
       {
          // y part: F_y at the column's nodes, contraction with D.w along y, top/bottom lifting
          const double hx = sGeom[cs * 4 + 2];
-         const double *uc = V.tile + cs * CS + ca;
+         const double *uc = su + cs * CS + ca;
          double Fy[4][N1];
 #pragma unroll
          for (int b = 0; b < N1; ++b)
@@ -518,7 +557,7 @@ namespace dflo
       if (row_on)
       {
          const double hx = sGeom[rs * 4 + 2], hy = sGeom[rs * 4 + 3];
-         const double *uc = V.tile + rs * CS + rb * N1;
+         const double *uc = su + rs * CS + rb * N1;
          double u[4][N1], Fx[4][N1];
 #pragma unroll
          for (int c = 0; c < 4; ++c) load_line<N1> (uc + c * NS, u[c]);
@@ -570,11 +609,10 @@ namespace dflo
 #pragma unroll
          for (int c = 0; c < 4; ++c) load_line<N1> (A.u_old + ((size_t) (c0 + rs) * D + rb * N1) + c * NS, uold[c]);
       }
-      if (main_thread) named_barrier<1, S::MAIN> (); // main warps only: the edge-job warp is off staging the next tile
-      DFLO_STAMP (5);
+      __syncthreads ();
 
       // ================= P4: M^-1, Euler step, RK combine, write-back, cell average =================
-      double *sPart = V.sPart; // [TC][N1][4] partial cell averages
+      double *sPart = sm + S::O_PART; // [TC][N1][4] partial cell averages
       const unsigned row_mask = __ballot_sync (0xffffffffu, row_on);
       if (row_on)
       {
@@ -585,7 +623,7 @@ namespace dflo
          const double wbh = T.gw[rb] * hx * hy;
          // a tile of redundantly updated ghost cells keeps only its means: the solution itself
          // arrives with the halo exchange (possibly before this tile runs)
-         const bool owned_tile = tile_index < A.n_tiles_owned;
+         const bool owned_tile = (int) blockIdx.x < A.n_tiles_owned;
          double part[4];
 #pragma unroll
          for (int c = 0; c < 4; ++c)
@@ -600,7 +638,7 @@ namespace dflo
             else
             {
                double u[N1];
-               load_line<N1> (V.tile + rs * CS + c * NS + rb * N1, u);
+               load_line<N1> (su + rs * CS + c * NS + rb * N1, u);
 #pragma unroll
                for (int a = 0; a < N1; ++a)
                {
@@ -635,8 +673,8 @@ namespace dflo
       }
       if (A.mode == MODE_STAGE && N1 != 2 && N1 != 4)
       {
-         if (main_thread) named_barrier<1, S::MAIN> ();
-         for (int j = tid; main_thread && j < ncb * 4; j += S::MAIN) // compute_cell_average of the updated solution, claw.cc:562-597
+         __syncthreads ();
+         for (int j = tid; j < ncb * 4; j += S::THREADS) // compute_cell_average of the updated solution, claw.cc:562-597
          {
             const int s = j >> 2, c = j & 3;
             double v = 0.0;
@@ -646,37 +684,30 @@ namespace dflo
          }
       }
 
-      DFLO_STAMP (6);
-      if (A.trace && threadIdx.x == 0)
-      {
-         unsigned smid;
-         asm volatile ("mov.u32 %0, %%smid;" : "=r"(smid));
-         A.trace[(size_t) tile_index * 8 + 7] = smid;
-      }
       // ================= fused halo exchange over peer memory (p2p_halo.cuh) =================
       if (A.fx)
       {
          const P2PFused &F = *A.fx;
-         const int n_send = sdesc[7];
+         const int n_send = gdesc[7];
          if (A.mode == MODE_STAGE && n_send > 0)
          {
-            if (main_thread) named_barrier<1, S::MAIN> (); // the tile's write-back is complete and visible to the block
-            const int *ent = F.send_entries + 3 * (size_t) sdesc[6];
+            __syncthreads (); // the tile's write-back is complete and visible to the block
+            const int *ent = F.send_entries + 3 * (size_t) gdesc[6];
             constexpr int D2 = D / 2;
-            for (int i = tid; main_thread && i < n_send * D2; i += S::MAIN)
+            for (int i = tid; i < n_send * D2; i += S::THREADS)
             {
                const int e = i / D2, c = i - e * D2;
                const int cell = ent[3 * e], pi = ent[3 * e + 1], dc = ent[3 * e + 2];
                reinterpret_cast<double2 *> (F.dstU[pi] + (size_t) dc * D)[c] = __ldcg (reinterpret_cast<const double2 *> (A.out + (size_t) cell * D) + c);
             }
-            for (int i = tid; main_thread && i < n_send * 2; i += S::MAIN)
+            for (int i = tid; i < n_send * 2; i += S::THREADS)
             {
                const int e = i >> 1;
                const int cell = ent[3 * e], pi = ent[3 * e + 1], dc = ent[3 * e + 2];
                reinterpret_cast<double2 *> (F.dstA[pi] + (size_t) dc * 4)[i & 1] = __ldcg (reinterpret_cast<const double2 *> (A.avg_out + (size_t) cell * 4) + (i & 1));
             }
             __threadfence ();
-            if (main_thread) named_barrier<1, S::MAIN> ();
+            __syncthreads ();
             if (tid == 0)
             {
                const unsigned int done = atomicAdd (F.send_counter, 1u);
@@ -690,89 +721,6 @@ namespace dflo
                }
             }
          }
-      }
-   }
-
-   template <int N1, int FLUX>
-   __global__ void __launch_bounds__ (RowShape<N1, FLUX>::THREADS, RowShape<N1, FLUX>::MIN_BLOCKS) row_stage_kernel (const StageArgs A)
-   {
-      typedef RowShape<N1, FLUX> S;
-      const int tile_index = blockIdx.x;
-      DFLO_STAMP (0);
-      constexpr int D = S::D, TC = S::TC, CS = S::CS;
-      extern __shared__ __align__ (16) double sm[];
-      double *su = sm + S::O_U, *sR = sm + S::O_R, *sT = sm + S::O_T, *sG = sm + S::O_G, *sGeom = sm + S::O_GEOM, *sAvg = sm + S::O_AVG;
-      int *sdesc = reinterpret_cast<int *> (sm + S::O_DESC);
-      const int tid = threadIdx.x;
-      const int *gdesc = A.rowdesc + (size_t) blockIdx.x * S::DESC_INTS;
-      const int c0 = gdesc[0], ncb = gdesc[1], nh = gdesc[2];
-      const bool need_old = A.mode == MODE_STAGE && A.ark != 0.0;
-      constexpr unsigned cell_bytes = (unsigned) (D * sizeof (double));
-
-      // ---- stage the tile: per-cell bulk copies into the padded layout, descriptor, geometry ----
-      if (tid == 0)
-      {
-         if (A.fx && gdesc[5])
-         {
-            // fused halo exchange: this tile reads ghost cells -- the peers' stores of the previous
-            // exchange must have landed (boundary tiles run first, so this rarely spins)
-            const P2PFused &F = *A.fx;
-            // epochs[0] = number of the NEXT exchange to publish; the last published one is needed here
-            const unsigned long long e = *reinterpret_cast<volatile unsigned long long *> (F.epochs) - 1;
-            for (int p = 0; p < F.npeers; ++p)
-               while (ld_acquire_sys (F.my_flags + F.world + F.peer_rank[p]) < e) {}
-         }
-         unsigned bytes = (unsigned) (ncb + nh) * cell_bytes + (unsigned) ncb * 32u + (unsigned) (S::DESC_INTS * sizeof (int));
-         if (FLUX == FLUX_LXF) bytes += (unsigned) (ncb + nh) * 32u;
-         mbar_init (sm, 1);
-         mbar_expect_tx (sm, bytes);
-      }
-      __syncthreads ();
-      if (DFLO_ROW_PAD == 0 && tid < ncb)
-      {
-         if (tid == 0) bulk_g2s (su, A.u + (size_t) c0 * D, (unsigned) ncb * cell_bytes, sm);
-         if (FLUX == FLUX_LXF) bulk_g2s (sAvg + tid * 4, A.avg + (size_t) (c0 + tid) * 4, 32u, sm);
-      }
-      else if (tid < ncb + nh)
-      {
-         const int cell = tid < ncb ? c0 + tid : gdesc[S::OFF_HALO + tid - ncb];
-         const int slot = tid < ncb ? tid : TC + tid - ncb;
-         bulk_g2s (su + slot * CS, A.u + (size_t) cell * D, cell_bytes, sm);
-         if (FLUX == FLUX_LXF) bulk_g2s (sAvg + slot * 4, A.avg + (size_t) cell * 4, 32u, sm);
-      }
-      else if (tid == S::THREADS - 1)
-      {
-         bulk_g2s (sdesc, gdesc, (unsigned) (S::DESC_INTS * sizeof (int)), sm);
-         bulk_g2s (sGeom, A.geom + (size_t) c0 * 4, (unsigned) ncb * 32u, sm);
-         if (need_old)
-            asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u_old + (size_t) c0 * D), "r"((unsigned) ncb * cell_bytes) : "memory");
-      }
-      else if (tid == S::THREADS - 2)
-      {
-         // Pull the inputs of the tile that will run in this block's slot a wave later from HBM
-         // into L2 now (a hint: on a uniform tiling that tile starts pf_tiles * TC cells further on)
-         const int bt = (int) blockIdx.x + A.pf_tiles;
-         if (bt < (int) gridDim.x)
-         {
-            const size_t pc0 = (size_t) c0 + (size_t) A.pf_tiles * TC;
-            if (pc0 + TC <= (size_t) A.n_cells_u)
-            {
-               asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u + pc0 * D), "r"((unsigned) TC * cell_bytes) : "memory");
-               if (need_old) asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u_old + pc0 * D), "r"((unsigned) TC * cell_bytes) : "memory");
-            }
-            asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.rowdesc + (size_t) bt * S::DESC_INTS), "r"((unsigned) (S::DESC_INTS * sizeof (int))) : "memory");
-         }
-      }
-      const double dt_global = A.time[1]; // issued before the wait: its latency hides behind the staging
-      DFLO_STAMP (1);
-      mbar_wait (sm, 0);
-      DFLO_STAMP (2);
-
-      const RowView V = {su, su + TC * CS, sR, sT, sG, sGeom, sAvg, sm + S::O_PART, sdesc};
-      row_tile_compute<N1, FLUX> (A, V, tile_index, c0, ncb, dt_global, need_old, NoHook ());
-      if (A.fx)
-      {
-         const P2PFused &F = *A.fx;
          if (tid == 0)
          {
             // the epoch advances when the LAST block of the launch retires: every tile that waits
@@ -783,125 +731,6 @@ namespace dflo
                *F.block_counter = 0;
                if (A.mode == MODE_STAGE) *F.epochs = *reinterpret_cast<volatile unsigned long long *> (F.epochs) + 1;
             }
-         }
-      }
-   }
-
-   //---------------------------------------------------------------------------------------------
-   // Pipelined form: persistent blocks walk over the tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
-   // with TWO staging buffers.  While the main warps run P3/P4 of tile i, the edge-job warp (idle by
-   // then) stages tile i+1 into the other buffer with the same per-cell bulk copies, so the
-   // staging latency (descriptor read, TMA round trip: a quarter of a block's life in the
-   // one-tile-per-block form) disappears from the critical path and neighbouring blocks drift out
-   // of phase instead of all waiting / all computing together.
-   //---------------------------------------------------------------------------------------------
-   template <int N1, int FLUX>
-   struct RowPersist
-   {
-      typedef RowShape<N1, FLUX> S;
-      static constexpr int TC = S::TC, NH = S::NH, CS = S::CS;
-      static constexpr int BLOCKS = N1 <= 4 ? 3 : 1;
-      // [bars | tile0 | halo0 | sG | sT | halo1 | tile1 | small0 | small1]; the y residual of a tile
-      // (sR, then sPart) overlays halo0|sG|sT.. for buffer 0 and sG|sT|halo1.. for buffer 1
-      static constexpr int O_A0 = 4;
-      static constexpr int O_H0 = O_A0 + TC * CS;
-      static constexpr int O_G = O_H0 + NH * CS;
-      static constexpr int O_T = O_G + NH * N1 * 4;
-      static constexpr int O_H1 = O_T + 2 * S::T_HALF;
-      static constexpr int O_A1 = O_H1 + NH * CS;
-      static constexpr int O_SMALL = O_A1 + TC * CS;
-      static constexpr int SM_GEOM = 0, SM_AVG = TC * 4, SM_DESC = SM_AVG + (FLUX == FLUX_LXF ? (TC + NH) * 4 : 0);
-      static constexpr int SMALL = SM_DESC + S::DESC_INTS / 2;
-      static constexpr int SMEM_DOUBLES = O_SMALL + 2 * SMALL;
-      static_assert (TC * CS + TC * N1 * 4 <= O_H1 - O_H0, "sR + sPart fit over the dead exchange region");
-      static_assert (SMALL % 2 == 0 && O_SMALL % 2 == 0, "16-byte aligned bulk copies");
-   };
-
-   template <int N1, int FLUX>
-   __global__ void __launch_bounds__ (RowShape<N1, FLUX>::THREADS, RowPersist<N1, FLUX>::BLOCKS) row_stage_pipelined_kernel (const StageArgs A, int n_tiles)
-   {
-      typedef RowShape<N1, FLUX> S;
-      typedef RowPersist<N1, FLUX> P;
-      constexpr int D = S::D, TC = S::TC, CS = S::CS;
-      constexpr unsigned cell_bytes = (unsigned) (D * sizeof (double));
-      extern __shared__ __align__ (16) double sm[];
-      unsigned long long *bars = reinterpret_cast<unsigned long long *> (sm);
-      const int tid = threadIdx.x;
-      const bool need_old = A.mode == MODE_STAGE && A.ark != 0.0;
-      const double dt_global = A.time[1];
-      if (tid == 0)
-      {
-         mbar_init (&bars[0], 1);
-         mbar_init (&bars[1], 1);
-      }
-      __syncthreads ();
-
-      // stage tile t into buffer b: called by the whole edge-job warp
-      auto stage_tile = [&] (int t, int b) {
-         const int lane = tid - S::MAIN;
-         const int *gdesc = A.rowdesc + (size_t) t * S::DESC_INTS;
-         const int c0 = gdesc[0], ncb = gdesc[1], nh = gdesc[2];
-         double *tile = sm + (b ? P::O_A1 : P::O_A0), *halo = sm + (b ? P::O_H1 : P::O_H0);
-         double *small = sm + P::O_SMALL + b * P::SMALL;
-         if (lane == 0)
-         {
-            if (A.fx && gdesc[5])
-            {
-               // fused halo exchange: the tile reads ghost cells -- the peers' previous exchange must have landed
-               const P2PFused &F = *A.fx;
-               const unsigned long long e = *reinterpret_cast<volatile unsigned long long *> (F.epochs) - 1;
-               for (int p = 0; p < F.npeers; ++p)
-                  while (ld_acquire_sys (F.my_flags + F.world + F.peer_rank[p]) < e) {}
-            }
-            unsigned bytes = (unsigned) (ncb + nh) * cell_bytes + (unsigned) ncb * 32u + (unsigned) (S::DESC_INTS * sizeof (int));
-            if (FLUX == FLUX_LXF) bytes += (unsigned) (ncb + nh) * 32u;
-            mbar_expect_tx (&bars[b], bytes);
-         }
-         fence_async_smem (); // the buffer was last written through the generic proxy (sR of an earlier tile)
-         __syncwarp ();
-         for (int i = lane; i < ncb + nh; i += 32)
-         {
-            const int cell = i < ncb ? c0 + i : gdesc[S::OFF_HALO + i - ncb];
-            bulk_g2s (i < ncb ? tile + i * CS : halo + (i - ncb) * CS, A.u + (size_t) cell * D, cell_bytes, &bars[b]);
-            if (FLUX == FLUX_LXF) bulk_g2s (small + P::SM_AVG + (i < ncb ? i : TC + i - ncb) * 4, A.avg + (size_t) cell * 4, 32u, &bars[b]);
-         }
-         if (lane == 0)
-         {
-            bulk_g2s (small + P::SM_DESC, gdesc, (unsigned) (S::DESC_INTS * sizeof (int)), &bars[b]);
-            bulk_g2s (small + P::SM_GEOM, A.geom + (size_t) c0 * 4, (unsigned) ncb * 32u, &bars[b]);
-            if (need_old)
-               asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u_old + (size_t) c0 * D), "r"((unsigned) ncb * cell_bytes) : "memory");
-         }
-      };
-
-      if (tid >= S::MAIN && (int) blockIdx.x < n_tiles) stage_tile (blockIdx.x, 0);
-      int it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it)
-      {
-         const int b = it & 1;
-         mbar_wait (&bars[b], (it >> 1) & 1);
-         double *small = sm + P::O_SMALL + b * P::SMALL;
-         int *sdesc = reinterpret_cast<int *> (small + P::SM_DESC);
-         double *sR = sm + (b ? P::O_G : P::O_H0);
-         const RowView V = {sm + (b ? P::O_A1 : P::O_A0), sm + (b ? P::O_H1 : P::O_H0), sR, sm + P::O_T, sm + P::O_G, small + P::SM_GEOM,
-                            small + P::SM_AVG, sR + TC * CS, sdesc};
-         const int tn = t + gridDim.x;
-         auto hook = [&] () {
-            if (tn < n_tiles) stage_tile (tn, b ^ 1);
-         };
-         row_tile_compute<N1, FLUX> (A, V, t, sdesc[0], sdesc[1], dt_global, need_old, hook);
-         __syncthreads (); // the exchange region and this buffer are free again
-      }
-      if (A.fx && tid == 0)
-      {
-         // the epoch advances when the LAST block of the launch retires: every tile that waits or
-         // publishes has read it by then
-         const P2PFused &F = *A.fx;
-         const unsigned int done = atomicAdd (F.block_counter, 1u);
-         if (done == gridDim.x - 1)
-         {
-            *F.block_counter = 0;
-            if (A.mode == MODE_STAGE) *F.epochs = *reinterpret_cast<volatile unsigned long long *> (F.epochs) + 1;
          }
       }
    }
