@@ -117,6 +117,11 @@ namespace dflo
       double *time;
       int n_cells, degree;
       double cfl;
+      // single-GPU: the block that retires last also finalises the step (DtFinalizeKernel's work),
+      // saving a launch; sharded contexts reduce over the ranks in between and keep it separate
+      unsigned int *done;
+      int finalize, nblocks;
+      double time_step;
    };
    struct DtKernel // phase kernel: per-cell dt, block minimum, one atomic per block
    {
@@ -147,9 +152,32 @@ namespace dflo
 #if defined(__CUDA_ARCH__)
             // positive doubles order like their bit patterns
             atomicMin ((unsigned long long *) (A.time + 2), (unsigned long long) __double_as_longlong (m));
+            bool last = false;
+            if (A.finalize)
+            {
+               __threadfence ();
+               last = atomicAdd (A.done, 1u) == (unsigned int) A.nblocks - 1;
+               if (last)
+               {
+                  *A.done = 0;
+                  __threadfence ();
+               }
+            }
+            const double acc = last ? *reinterpret_cast<volatile double *> (A.time + 2) : 0.0;
 #else
             if (m < A.time[2]) A.time[2] = m;
+            const bool last = A.finalize && ++*A.done == (unsigned int) A.nblocks;
+            if (last) *A.done = 0;
+            const double acc = A.time[2];
 #endif
+            if (last) // claw.cc:468-476, as DtFinalizeKernel
+            {
+               double dt = acc;
+               if (dt > 0 && A.time_step > 0) dt = std_min (dt, A.time_step);
+               if (A.time[0] + dt > A.time[3]) dt = A.time[3] - A.time[0];
+               A.time[1] = dt;
+               A.time[2] = 1.0e20;
+            }
          }
       }
    };
@@ -397,7 +425,8 @@ namespace dflo
          d_time = bk.template alloc<double> (4);
          const double t0[4] = {0.0, 0.0, 1.0e20, 1.0e20};
          bk.h2d (d_time, t0, sizeof (t0));
-         d_scratch = bk.template alloc<double> (4);
+         d_scratch = bk.template alloc<double> (4); // [0] reductions, [2] block counter of the dt kernel
+         bk.zero (d_scratch, 4 * sizeof (double));
          d_nbr = upload (lm.nbr);
          d_halo_cells = upload (pad1 (lm.halo_cells));
          d_jobs = upload_aligned_jobs ();
@@ -879,7 +908,12 @@ namespace dflo
          a.n_cells = lm.n_owned;
          a.degree = tab.k;
          a.cfl = prm.cfl;
-         bk.template launch<DtKernel> (DtKernel::grid (a.n_cells), a);
+         a.done = reinterpret_cast<unsigned int *> (d_scratch + 2);
+         a.nblocks = DtKernel::grid (a.n_cells);
+         a.finalize = lm.peers.empty ();
+         a.time_step = prm.time_step;
+         bk.template launch<DtKernel> (a.nblocks, a);
+         if (a.finalize) return;
          bk.allreduce_min_dt (d_time + 2);
          DtFinalizeArgs f;
          f.time = d_time;
