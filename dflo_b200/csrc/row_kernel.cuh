@@ -53,7 +53,10 @@ namespace dflo
       #ifndef DFLO_ROW_MIN_BLOCKS
 #define DFLO_ROW_MIN_BLOCKS 4
 #endif
-      static constexpr int MIN_BLOCKS = N1 <= 4 ? DFLO_ROW_MIN_BLOCKS : 2;
+#ifndef DFLO_ROW_MIN_BLOCKS_N3
+#define DFLO_ROW_MIN_BLOCKS_N3 6
+#endif
+      static constexpr int MIN_BLOCKS = N1 == 3 ? DFLO_ROW_MIN_BLOCKS_N3 : N1 <= 4 ? DFLO_ROW_MIN_BLOCKS : 2;
       static constexpr int DESC_INTS = rowd_ints (TC, NH);
       static constexpr int OFF_HALO = rowd_off_halo (), OFF_NBHI = rowd_off_nbhi (NH), OFF_LJOB = rowd_off_ljob (TC, NH),
                            OFF_GJOB = rowd_off_gjob (TC, NH);
