@@ -74,12 +74,32 @@ def initial_dofs(nx, ny, x0, x1, y0, y1, k):
 
 
 def sample_clocks(stop, out):
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """SM clock + throttle reasons while the timed region runs (B200_PROFILING.md clocks line).  NVML is
+    polled every 2 ms (the timed region of this workload lasts tens of milliseconds, too short for
+    nvidia-smi's loop mode); nvidia-smi -lms is the fallback when the NVML binding is missing."""
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        names = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        while not stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            out.append("%d, %d, %s" % (sm, mx, ", ".join("Active" if r & bit else "Not Active" for _, bit in names)))
+            time.sleep(0.002)
+        return
+    except Exception:
+        pass
     q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     try:
-        p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i",
-                              os.environ.get("LOCAL_RANK", "0"), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", str(dev), "-lms", "100"],
+                             stdout=subprocess.PIPE, text=True)
     except Exception:
         return
     while not stop.is_set():
