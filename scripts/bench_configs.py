@@ -3,7 +3,9 @@
 ConservationLaw<2>::run), one GPU: MDoF-updates/s per config with device-resident state (CUDA events
 around each dflo_b200_advance), the stage kernel alone, and the HBM-roofline fraction of the whole
 stage (stage kernel + limiter).  bench.py stays the contract line for configs[1]; this script fills
-the per-config table of DESIGN.md.   python scripts/bench_configs.py [--small] [--steps N]"""
+the per-config table of DESIGN.md.   python scripts/bench_configs.py [--small] [--steps N]
+Under torchrun (one rank per GPU) the same mesh is sharded over the ranks: strong scaling, e.g. of
+configs[3] (double Mach reflection, ~1M cells), the case BASELINE.json names for 1 -> 8 GPUs."""
 import argparse
 import ctypes
 import json
@@ -32,6 +34,13 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--configs", default="cfg1,cfg2,cfg3,cfg4,cfg5")
     args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # strong scaling of a configuration over the GPUs of one node: launched under torchrun
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = abi.load_library()
     L.dflo_claw_create.restype = ctypes.c_void_p
     L.dflo_claw_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
@@ -51,7 +60,15 @@ def main():
             mesh = SMALL[key]
         h = L.dflo_claw_create(os.path.join(PRM, prm).encode(), mesh.encode(), None, abi.COMPAT["mpi"])
         assert h, L.dflo_host_last_error()
-        rc = L.dflo_claw_setup(h, 0, 0, 1, None)
+        idbuf = None
+        if world > 1:
+            idbuf = (ctypes.c_char * 128)()
+            if rank == 0:
+                assert L.dflo_b200_nccl_unique_id(idbuf) == 0
+            tt = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
+            dist.broadcast(tt, 0)
+            idbuf = ctypes.create_string_buffer(bytes(tt.cpu().tolist()), 128)
+        rc = L.dflo_claw_setup(h, local, rank, world, idbuf)
         assert rc == 0, L.dflo_host_last_error()
         ctx = ctypes.c_void_p(L.dflo_claw_engine(h))
         n_dofs = L.dflo_claw_n_dofs(h)
@@ -68,16 +85,23 @@ def main():
             total += ms.value
         kms = ctypes.c_float(0.0)
         L.dflo_b200_time_stage_kernel(ctx, n_rk - 1, 10, 0, ctypes.byref(kms))
+        if world > 1:
+            v = torch.tensor([total, kms.value], dtype=torch.float64, device="cuda")
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            total, kms.value = float(v[0]), float(v[1])
         limited = p.limiter_type != 0 or p.pos_lim != 0
         bpu = (32.0 + 64.0 / D) if limited else (24.0 + 32.0 / D)
         ms_stage = total / args.steps / n_rk
-        line = {"config": key, "mesh": mesh, "cells": n_dofs // D, "dofs": n_dofs, "rk_stages": n_rk, "limited": bool(limited),
+        line = {"config": key, "n_gpus": world, "mesh": mesh, "cells": n_dofs // D, "dofs": n_dofs, "rk_stages": n_rk, "limited": bool(limited),
                 "ms_per_step": total / args.steps, "mdof_per_s": n_dofs * n_rk * args.steps / (total * 1e-3) / 1e6,
                 "stage_kernel_ms": kms.value, "ms_per_stage_all_kernels": ms_stage,
                 "bytes_per_dof_update": bpu, "hbm_frac_whole_stage": n_dofs * bpu / (ms_stage * 1e-3) / 1e9 / peak, "t_end": t.value}
-        print(json.dumps(line), flush=True)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
         out.append(line)
         L.dflo_claw_destroy(h)
+    if world > 1:
+        dist.destroy_process_group()
     return out
 
 
