@@ -679,6 +679,60 @@ namespace dflo
       m.Ly[3][0] = beta * (phi2 + c * v); m.Ly[3][1] = -beta * g1 * u; m.Ly[3][2] = -beta * (c + g1 * v); m.Ly[3][3] = beta * g1;
    }
 
+   // The same matrices in two halves (identical expressions, hence identical values): the limiter
+   // needs the left eigenvectors of every cell but the right ones only where it actually limits.
+   struct EigenLeft
+   {
+      double Lx[4][4], Ly[4][4];
+   };
+   struct EigenRight
+   {
+      double Rx[4][4], Ry[4][4];
+   };
+   DFLO_HD void compute_eigen_left (const double W[4], EigenLeft &m)
+   {
+      const double g1 = GM1;
+      const double rho = W[RHO], E = W[ENE];
+      const double u = W[0] / rho, v = W[1] / rho;
+      const double q2 = u * u + v * v;
+      const double p = g1 * (E - 0.5 * rho * q2);
+      const double c2 = GAMMA * p / rho;
+      const double c = sqrt (c2);
+      const double beta = 0.5 / c2;
+      const double phi2 = 0.5 * g1 * q2;
+
+      m.Lx[0][0] = 1 - phi2 / c2;         m.Lx[0][1] = g1 * u / c2;          m.Lx[0][2] = g1 * v / c2;    m.Lx[0][3] = -g1 / c2;
+      m.Lx[1][0] = v;                     m.Lx[1][1] = 0;                    m.Lx[1][2] = -1;             m.Lx[1][3] = 0;
+      m.Lx[2][0] = beta * (phi2 - c * u); m.Lx[2][1] = beta * (c - g1 * u);  m.Lx[2][2] = -beta * g1 * v; m.Lx[2][3] = beta * g1;
+      m.Lx[3][0] = beta * (phi2 + c * u); m.Lx[3][1] = -beta * (c + g1 * u); m.Lx[3][2] = -beta * g1 * v; m.Lx[3][3] = beta * g1;
+
+      m.Ly[0][0] = 1 - phi2 / c2;         m.Ly[0][1] = g1 * u / c2;    m.Ly[0][2] = g1 * v / c2;          m.Ly[0][3] = -g1 / c2;
+      m.Ly[1][0] = -u;                    m.Ly[1][1] = 1;              m.Ly[1][2] = 0;                    m.Ly[1][3] = 0;
+      m.Ly[2][0] = beta * (phi2 - c * v); m.Ly[2][1] = -beta * g1 * u; m.Ly[2][2] = beta * (c - g1 * v);  m.Ly[2][3] = beta * g1;
+      m.Ly[3][0] = beta * (phi2 + c * v); m.Ly[3][1] = -beta * g1 * u; m.Ly[3][2] = -beta * (c + g1 * v); m.Ly[3][3] = beta * g1;
+   }
+   DFLO_HD void compute_eigen_right (const double W[4], EigenRight &m)
+   {
+      const double g1 = GM1;
+      const double rho = W[RHO], E = W[ENE];
+      const double u = W[0] / rho, v = W[1] / rho;
+      const double q2 = u * u + v * v;
+      const double p = g1 * (E - 0.5 * rho * q2);
+      const double c2 = GAMMA * p / rho;
+      const double c = sqrt (c2);
+      const double h = c2 / g1 + 0.5 * q2;
+
+      m.Rx[0][0] = 1;        m.Rx[0][1] = 0;   m.Rx[0][2] = 1;         m.Rx[0][3] = 1;
+      m.Rx[1][0] = u;        m.Rx[1][1] = 0;   m.Rx[1][2] = u + c;     m.Rx[1][3] = u - c;
+      m.Rx[2][0] = v;        m.Rx[2][1] = -1;  m.Rx[2][2] = v;         m.Rx[2][3] = v;
+      m.Rx[3][0] = 0.5 * q2; m.Rx[3][1] = -v;  m.Rx[3][2] = h + c * u; m.Rx[3][3] = h - c * u;
+
+      m.Ry[0][0] = 1;        m.Ry[0][1] = 0;   m.Ry[0][2] = 1;         m.Ry[0][3] = 1;
+      m.Ry[1][0] = u;        m.Ry[1][1] = 1;   m.Ry[1][2] = u;         m.Ry[1][3] = u;
+      m.Ry[2][0] = v;        m.Ry[2][1] = 0;   m.Ry[2][2] = v + c;     m.Ry[2][3] = v - c;
+      m.Ry[3][0] = 0.5 * q2; m.Ry[3][1] = u;   m.Ry[3][2] = h + c * v; m.Ry[3][3] = h - c * v;
+   }
+
    // equation.h:270-285: W (conserved order) -> characteristic (result in matrix row order)
    DFLO_HD void transform_to_char (const double L[4][4], double W[4])
    {

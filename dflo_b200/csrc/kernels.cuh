@@ -1276,16 +1276,24 @@ namespace dflo
                   if (f == 3) dfy[c] = an - av[c];
                }
             }
-            EigenMatrices em;
             if (A.char_lim)
             {
-               compute_eigen_matrix (av, em);
-               transform_to_char (em.Lx, dbx);
-               transform_to_char (em.Lx, dfx);
-               transform_to_char (em.Ly, dby);
-               transform_to_char (em.Ly, dfy);
-               transform_to_char (em.Lx, Dx);
-               transform_to_char (em.Ly, Dy);
+               EigenLeft el; // the right eigenvectors are needed only if the cell is actually limited
+               compute_eigen_left (av, el);
+               transform_to_char (el.Lx, Dx);
+               transform_to_char (el.Ly, Dy);
+               // TVB with M > 0: where every characteristic slope is below M dx^2 minmod returns it
+               // unchanged (limiter.cc:20-21) whatever the neighbours are: nothing more to do
+               bool small = true;
+#pragma unroll
+               for (int c = 0; c < 4; ++c) small = small && fabs (Dx[c]) < Mdx2 && fabs (Dy[c]) < Mdx2;
+               if (!small)
+               {
+                  transform_to_char (el.Lx, dbx);
+                  transform_to_char (el.Lx, dfx);
+                  transform_to_char (el.Ly, dby);
+                  transform_to_char (el.Ly, dfy);
+               }
             }
             double Dxn[4], Dyn[4], change_x = 0.0, change_y = 0.0;
 #pragma unroll
@@ -1311,8 +1319,10 @@ namespace dflo
                }
                if (A.char_lim)
                {
-                  transform_to_con (em.Rx, Dxn);
-                  transform_to_con (em.Ry, Dyn);
+                  EigenRight er;
+                  compute_eigen_right (av, er);
+                  transform_to_con (er.Rx, Dxn);
+                  transform_to_con (er.Ry, Dyn);
                }
                if (BASIS == BASIS_PK && A.cam) // limiter.cc:496-500
                {
