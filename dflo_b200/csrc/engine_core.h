@@ -83,7 +83,7 @@ namespace dflo
       const double *geom;
       const double *gx;          // Gauss nodes [nqf]
       const ExprInstr *code;     // all programs back to back
-      const int *prog_start;     // [10*4 + 1] offsets; empty program => keep the stored value
+      const int *prog_start;     // [10*4][2] begin, end of each program; empty program => keep the stored value
       const double *time;        // [0] t, [1] dt
       int n_bfaces, nqf;
       int use_t_plus_dt;
@@ -103,7 +103,7 @@ namespace dflo
          const double t = A.time[0] + (A.use_t_plus_dt ? A.time[1] : 0.0);
          for (int c = 0; c < 4; ++c)
          {
-            const int p0 = A.prog_start[id * 4 + c], p1 = A.prog_start[id * 4 + c + 1];
+            const int p0 = A.prog_start[2 * (id * 4 + c)], p1 = A.prog_start[2 * (id * 4 + c) + 1];
             if (p1 > p0) A.bc_g[(size_t) j * 4 + c] = expr_eval (A.code + p0, p1 - p0, x, y, t);
          }
       }
@@ -371,6 +371,7 @@ namespace dflo
       unsigned int *d_err = nullptr;
       ExprInstr *d_code = nullptr;
       int *d_prog_start = nullptr;
+      int *d_prog_start_t = nullptr;  // same table with the time-independent programs emptied: the per-stage refresh
       double *d_ext = nullptr;        // staging for set/get_solution
       size_t ext_capacity = 0;
       uint32_t *d_dofmap = nullptr;
@@ -381,6 +382,7 @@ namespace dflo
       // boundary expressions
       std::vector<ExprInstr> programs[DFLO_MAX_BOUNDARIES][4];
       bool have_programs = false, programs_time_dependent = false;
+      bool program_uses_t[DFLO_MAX_BOUNDARIES][4] = {};
       int n_global_bfaces = 0;
 
       // halo exchange fused into the stage kernel: row kernel, peer memory mapped, nothing between
@@ -465,7 +467,8 @@ namespace dflo
          bk.zero (d_flags, lm.n_local * sizeof (int));
          d_err = bk.template alloc<unsigned int> (1);
          bk.zero (d_err, sizeof (unsigned int));
-         d_prog_start = bk.template alloc<int> (DFLO_MAX_BOUNDARIES * 4 + 1);
+         d_prog_start = bk.template alloc<int> (DFLO_MAX_BOUNDARIES * 4 * 2);
+         d_prog_start_t = bk.template alloc<int> (DFLO_MAX_BOUNDARIES * 4 * 2);
          for (auto &pr : lm.peers)
             for (int k = 0; k < 2; ++k)
             {
@@ -493,7 +496,7 @@ namespace dflo
             bk.free (AVG[i]);
          }
          void *ptrs[] = {rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
-                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles, d_rowdesc, d_send_entries};
+                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_prog_start_t, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles, d_rowdesc, d_send_entries};
          for (void *p : ptrs) bk.free (p);
          for (int k = 0; k < 2; ++k)
          {
@@ -572,21 +575,26 @@ namespace dflo
          bool uses_t = false;
          if (!cc.compile (text, code, e, &uses_t)) return fail (DFLO_E_EXPR, e);
          programs[id][comp] = code;
-         // flatten all programs
+         program_uses_t[id][comp] = uses_t;
+         // flatten all programs; the kernel reads program k as code[start[2k] .. start[2k+1])
          std::vector<ExprInstr> all;
-         std::vector<int> start (DFLO_MAX_BOUNDARIES * 4 + 1, 0);
+         std::vector<int> start (DFLO_MAX_BOUNDARIES * 4 * 2, 0), start_t (DFLO_MAX_BOUNDARIES * 4 * 2, 0);
          for (int b = 0; b < DFLO_MAX_BOUNDARIES; ++b)
             for (int c = 0; c < 4; ++c)
             {
-               start[b * 4 + c] = all.size ();
+               const int k = b * 4 + c;
+               start[2 * k] = start_t[2 * k] = all.size ();
                all.insert (all.end (), programs[b][c].begin (), programs[b][c].end ());
+               start[2 * k + 1] = all.size ();
+               start_t[2 * k + 1] = program_uses_t[b][c] ? (int) all.size () : start_t[2 * k]; // empty: keep the stored value
             }
-         start[DFLO_MAX_BOUNDARIES * 4] = all.size ();
          bk.sync ();
          bk.free (d_code);
          d_code = bk.template alloc<ExprInstr> (std::max<size_t> (1, all.size ()));
          bk.h2d (d_code, all.data (), all.size () * sizeof (ExprInstr));
          bk.h2d (d_prog_start, start.data (), start.size () * sizeof (int));
+         bk.h2d (d_prog_start_t, start_t.data (), start_t.size () * sizeof (int));
+         bk.sync ();
          have_programs = true;
          programs_time_dependent = programs_time_dependent || uses_t;
          bk.drop_graphs ();
@@ -880,7 +888,8 @@ namespace dflo
          bk.template launch1d<CellAverageKernel> (n_cells * 4, a);
       }
 
-      void eval_boundary (bool t_plus_dt)
+      // time_dependent_only: the per-stage refresh inside a step -- programs without t keep their values
+      void eval_boundary (bool t_plus_dt, bool time_dependent_only = false)
       {
          if (!have_programs || lm.bf_id.empty ()) return;
          BcEvalArgs a;
@@ -891,7 +900,7 @@ namespace dflo
          a.geom = d_geom;
          a.gx = d_gx;
          a.code = d_code;
-         a.prog_start = d_prog_start;
+         a.prog_start = time_dependent_only ? d_prog_start_t : d_prog_start;
          a.time = d_time;
          a.n_bfaces = lm.bf_id.size ();
          a.nqf = tab.n1;
@@ -946,7 +955,9 @@ namespace dflo
          for (int rk = 0; rk < n_rk; ++rk)
          {
             // bc time: t for rk 0, t+dt afterwards (src/claw.cc:736-745); always t in src_mpi
-            if (programs_time_dependent) eval_boundary (rk > 0 && prm.compat == DFLO_COMPAT_SRC);
+            // refreshed only when the BC time changes: t for rk 0, then t+dt once (src) or never (src_mpi)
+            const bool plus_dt = rk > 0 && prm.compat == DFLO_COMPAT_SRC;
+            if (programs_time_dependent && (rk == 0 || (rk == 1 && plus_dt))) eval_boundary (plus_dt, true);
             enqueue_stage (rk);
          }
          DtFinalizeArgs f;

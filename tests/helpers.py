@@ -227,3 +227,48 @@ class Case:
     def close(self):
         for e in self.engines:
             e.close()
+
+
+DMR_TOP = ("57.1576766498*(x<1.0/6.0+(1+20*t)/sqrt(3))", "-33.0*(x<1.0/6.0+(1+20*t)/sqrt(3))",
+           "8.0*(x<1.0/6.0+(1+20*t)/sqrt(3)) + 1.4*(x>=1.0/6.0+(1+20*t)/sqrt(3))",
+           "563.5*(x<1.0/6.0+(1+20*t)/sqrt(3)) + 2.5*(x>=1.0/6.0+(1+20*t)/sqrt(3))")
+
+
+def dmr_bc_values(o, t):
+    """g(x_q, t) of the double Mach reflection input.prm at the oracle's boundary q-points (numpy)."""
+    _, _, bid, xq = o.bfaces()
+    g = np.zeros((o.n_bfaces, o.nqf, 4))
+    g[...] = (57.1576766498, -33.0, 8.0, 563.5)
+    x = xq[..., 0]
+    post = x < 1.0 / 6.0 + (1.0 + 20.0 * t) / np.sqrt(3.0)
+    top = np.stack([57.1576766498 * post, -33.0 * post, 8.0 * post + 1.4 * (~post), 563.5 * post + 2.5 * (~post)], axis=-1)
+    g[bid == 3] = top[bid == 3]
+    return g
+
+
+def time_dependent_bc_case(backend, compat, nsteps=3):
+    """Double Mach reflection with the moving-shock top boundary as a device-evaluated expression,
+    n whole steps of dflo_b200_advance against the oracle fed g(x, t_bc) stage by stage with the BC
+    time of the chosen tree (src: t, then t+dt; src_mpi: always t).  Returns the relative error."""
+    prm = dict(basis="Qk", degree=2, flux="hllc", limiter="TVB", char_lim=True, beta=1.0, M=100.0, cfl=0.9, compat=compat)
+    c = Case(("double_mach", [16]), DMR_BC, ic_dmr, backend=backend, **prm)
+    o, e = c.oracle, c.engine
+    for comp, ex in enumerate(DMR_TOP):
+        e.set_boundary_expression(3, comp, ex)
+    for comp, v in enumerate((57.1576766498, -33.0, 8.0, 563.5)):
+        e.set_boundary_expression(4, comp, repr(v))
+    o.set_bc_values(dmr_bc_values(o, 0.0))
+    c.limit_initial()
+    t = 0.0
+    for _ in range(nsteps):
+        dt = o.compute_dt(t)
+        for rk in range(o.n_rk):
+            t_bc = t + dt if (rk > 0 and compat == "src") else t
+            o.set_bc_values(dmr_bc_values(o, t_bc))
+            err, _ = o.rk_stage(rk, dt)
+            assert err == 0
+        o.commit_step()
+        t += dt
+    te, _ = e.advance(nsteps)
+    assert abs(te - t) <= 1e-12 * t
+    return c.rel_err(), c

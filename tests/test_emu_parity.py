@@ -185,3 +185,14 @@ def test_sharded_matches_single(case, world):
     assert many.rel_err() <= TOL_STEP_SHOCK
     one.close()
     many.close()
+
+
+@pytest.mark.parametrize("compat", ["src", "mpi"])
+def test_time_dependent_boundary_expression_under_advance(compat):
+    """The moving-shock top boundary of the double Mach reflection (examples/double_mach_reflection/
+    input.prm:35-41) evaluated on the device at each stage's BC time (src/claw.cc:736-745 vs
+    src_mpi/claw.cc:769-773) inside dflo_b200_advance."""
+    from helpers import time_dependent_bc_case
+    err, c = time_dependent_bc_case("emu", compat)
+    assert err <= TOL_STEP_SHOCK
+    c.close()

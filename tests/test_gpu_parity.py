@@ -242,3 +242,13 @@ def test_full_size_cfg3_mass_conservation():
     assert np.abs(rows[:, :, 1]).max() <= 1e-12      # no y momentum appears
     assert np.count_nonzero(eng.limited_flags()) > 0
     eng.close()
+
+
+@pytest.mark.parametrize("compat", ["src", "mpi"])
+def test_time_dependent_boundary_expression_under_advance(compat):
+    """Device-evaluated moving-shock boundary of the double Mach reflection inside the captured step,
+    refreshed only when the BC time changes (src: t, then t+dt; src_mpi: t)."""
+    from helpers import time_dependent_bc_case
+    err, c = time_dependent_bc_case("cuda", compat)
+    assert err <= TOL_STEP_SHOCK
+    c.close()
