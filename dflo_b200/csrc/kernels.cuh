@@ -1180,7 +1180,8 @@ namespace dflo
       // works on its row, changed cells are written back
       static constexpr int THREADS = D > 64 ? 64 : 128;
       static constexpr int CPB = THREADS;
-      static constexpr int MIN_BLOCKS = 1;
+      // up to Q2 / P3 four blocks fit the shared memory of an SM: hold the compiler to 128 registers for them
+      static constexpr int MIN_BLOCKS = D <= 40 ? 4 : 1;
       static constexpr int NPHASE = 2;
       static constexpr int ROW = D + 1;
       static constexpr int SMEM_DOUBLES = CPB * ROW;
