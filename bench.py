@@ -8,8 +8,8 @@ One "step" = one full time step of the hot path (compute_time_step + n_rk RK sta
 M^-1, RK combine, cell average, configured limiters) over the whole mesh; one DoF-update = one
 scalar unknown advanced through one RK stage.  Workload at N = 1: BASELINE.json configs[1]
 (isentropic vortex, Q3, 256x256 Cartesian cells, periodic, Roe flux, SSP-RK3).  For N > 1 the
-per-GPU work is kept (weak scaling): the periodic box is extended to 256N x 256 cells and sharded
-by cell id, one halo exchange per stage stored straight into the peers' memory over NVLink
+per-GPU work is kept (weak scaling): the periodic box is extended to 256 x 256N cells and sharded
+by cell id (each rank a 256 x 256 square), one halo exchange per stage stored straight into the peers' memory over NVLink
 (fused into the stage kernel; NCCL send/recv as fallback).
 
 Timing: `value` = device-resident throughput: every step is one dflo_b200_advance() call (CUDA
@@ -262,8 +262,10 @@ def main():
         nccl_id = bytes(t.cpu().tolist())
 
     desc, basis, k, flux, npg = WORKLOADS[args.workload]
-    nx, ny = npg * world, npg
-    x0, x1, y0, y1 = -5.0 * world, 5.0 * world, -5.0, 5.0
+    # weak scaling: the box grows in y, so the contiguous cell-id range of a rank is a compact
+    # npg x npg square (cells are numbered x fastest) with 2 x npg interface cells
+    nx, ny = npg, npg * world
+    x0, x1, y0, y1 = -5.0, 5.0, -5.0 * world, 5.0 * world
     params, pair = abi.make_params(basis=basis, degree=k, flux=flux, bc=PERIODIC, cfl=0.9, compat="mpi")
     mesh = abi.Mesh("rectangle", [nx, ny, x0, x1, y0, y1, 4, 2, 1, 3])
     flat = mesh.flatten(params, pair)

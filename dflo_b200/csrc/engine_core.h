@@ -923,7 +923,7 @@ namespace dflo
          a.time_step = prm.time_step;
          bk.template launch<DtKernel> (a.nblocks, a);
          if (a.finalize) return;
-         bk.allreduce_min_dt (d_time + 2);
+         if (bk.allreduce_min_dt (d_time + 2, true, prm.time_step)) return; // reduced over the ranks and finalised in one launch
          DtFinalizeArgs f;
          f.time = d_time;
          f.time_step = prm.time_step;

@@ -414,18 +414,21 @@ namespace
          if (comm) note (nccl ().GroupEnd ());
       }
       void halo_wait () {}
-      void allreduce_min_dt (double *p)
+      // returns true if the step was also finalised (dt clipped and published, accumulator reset)
+      bool allreduce_min_dt (double *p, bool finalize = false, double time_step = 0.0)
       {
          if (p2p)
          {
             dflo::P2PArgs a = p2p_args;
             a.dt_val = p;
             ++launches;
-            dflo::dt_min_kernel<<<1, 32, 0, stream>>> (a);
+            dflo::dt_min_kernel<<<1, 32, 0, stream>>> (a, finalize ? 1 : 0, time_step);
             note (cudaPeekAtLastError ());
+            return finalize;
          }
          else if (comm)
             note (nccl ().AllReduce (p, p, 1, ncclDouble, ncclMin, comm, stream));
+         return false;
       }
 
       // ---- peer-memory halo: map the peers' buffers once (CUDA IPC handles over the NCCL communicator) ----
@@ -440,6 +443,12 @@ namespace
          p2p_epochs = alloc<unsigned long long> (4);
          p2p_counter = alloc<unsigned int> (1);
          zero (p2p_flags, 4 * W * sizeof (unsigned long long));
+         {
+            // the dt slots (words 2W .. 4W) are armed with -1: a non-negative value is a message
+            std::vector<double> arm (2 * W, -1.0);
+            h2d (p2p_flags + 2 * W, arm.data (), arm.size () * sizeof (double));
+            sync ();
+         }
          zero (p2p_counter, sizeof (unsigned int));
          const unsigned long long ones[4] = {1, 1, 1, 0};
          h2d (p2p_epochs, ones, sizeof (ones));

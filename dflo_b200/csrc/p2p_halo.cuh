@@ -35,7 +35,7 @@ namespace dflo
       int dst_cell0;    // first cell of the peer's ghost range these land in
    };
 
-   // flag block of a rank, in 8-byte words indexed by SOURCE rank: done[W] | data[W] | dtflag[W] | dtslot[W]
+   // flag block of a rank, in 8-byte words indexed by SOURCE rank: (unused)[W] | data[W] | dt slots, even epochs[W] | odd epochs[W]
    struct P2PArgs
    {
       const double *srcU, *srcA;
@@ -129,31 +129,44 @@ namespace dflo
       }
    }
 
-   // global minimum of *dt_val over the ranks (compute_time_step, reference src_mpi/claw.cc:579)
-   __global__ void dt_min_kernel (const P2PArgs a)
+   // global minimum of *dt_val over the ranks (compute_time_step, reference src_mpi/claw.cc:579),
+   // optionally followed by the finalisation of the step (DtFinalizeKernel's work: a launch less).
+   // The value itself is the message: every rank stores it into slot [parity][me] of each other
+   // rank's flag block (one 8-byte store: no data/flag pair, no system fence), spins until its own
+   // slots [parity][r] turn non-negative, and re-arms them with -1 for the exchange after next.
+   __global__ void dt_min_kernel (const P2PArgs a, int finalize, double time_step)
    {
       const int r = threadIdx.x;
       const unsigned long long e = *reinterpret_cast<volatile unsigned long long *> (a.epochs + 2);
+      const int par = (int) (e & 1ull);
       const double v = *a.dt_val;
+      __shared__ double got[P2P_MAX_WORLD];
+      if (r < a.world) got[r] = v;
       if (r < a.world && r != a.me)
       {
-         unsigned long long *f = a.all_flags[r];
-         reinterpret_cast<double *> (f + 3 * a.world)[a.me] = v;
-         __threadfence_system ();
-         st_release_sys (f + 2 * a.world + a.me, e);
-         while (ld_acquire_sys (a.my_flags + 2 * a.world + r) < e) {}
+         reinterpret_cast<volatile double *> (a.all_flags[r] + (2 + par) * a.world)[a.me] = v;
+         volatile double *mine = reinterpret_cast<volatile double *> (a.my_flags + (2 + par) * a.world) + r;
+         double w;
+         while ((w = *mine) < 0.0) {}
+         *mine = -1.0;
+         got[r] = w;
       }
       __syncthreads ();
       if (r == 0)
       {
          double m = v;
-         for (int q = 0; q < a.world; ++q)
-            if (q != a.me)
-            {
-               const double w = reinterpret_cast<volatile double *> (a.my_flags + 3 * a.world)[q];
-               m = (w < m) ? w : m;
-            }
-         *a.dt_val = m;
+         for (int q = 0; q < a.world; ++q) m = (got[q] < m) ? got[q] : m;
+         double *time = a.dt_val - 2; // dt_val = time + 2 (the accumulator)
+         if (finalize) // claw.cc:468-476, as DtFinalizeKernel
+         {
+            double dt = m;
+            if (dt > 0 && time_step > 0) dt = (time_step < dt) ? time_step : dt;
+            if (time[0] + dt > time[3]) dt = time[3] - time[0];
+            time[1] = dt;
+            time[2] = 1.0e20;
+         }
+         else
+            *a.dt_val = m;
          a.epochs[2] = e + 1;
       }
    }

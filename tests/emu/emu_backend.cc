@@ -47,7 +47,7 @@ namespace
       void timer_start () {}
       void timer_stop () {}
       float timer_ms () { return 0.0f; }
-      void allreduce_min_dt (double *) {} // single-rank advance only in emulation
+      bool allreduce_min_dt (double *, bool = false, double = 0.0) { return false; } // single-rank advance only in emulation
       void allreduce_sum (double *, int) {}
 
       template <class K> void launch (int grid, const typename K::Args &a)
