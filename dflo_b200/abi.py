@@ -41,6 +41,9 @@ class FlatMesh(ctypes.Structure):
     ]
 
 
+INDICATOR = {"limiter": 0, "density": 1, "energy": 2}   # src/parameters.cc:229-237
+
+
 class Params(ctypes.Structure):
     _fields_ = [
         ("basis", ctypes.c_int32), ("degree", ctypes.c_int32), ("flux_type", ctypes.c_int32),
@@ -49,6 +52,7 @@ class Params(ctypes.Structure):
         ("M", ctypes.c_double), ("beta", ctypes.c_double), ("gravity", ctypes.c_double),
         ("cfl", ctypes.c_double), ("time_step", ctypes.c_double),
         ("bc_kind", ctypes.c_int32 * MAX_BOUNDARIES),
+        ("shock_indicator", ctypes.c_int32), ("reserved0", ctypes.c_int32),
     ]
 
 
@@ -60,10 +64,11 @@ class DfloError(RuntimeError):
 
 def make_params(basis="Qk", degree=1, flux="lxf", limiter="none", char_lim=False, pos_lim=False,
                 conserve_angular_momentum=False, M=0.0, beta=1.0, gravity=0.0, cfl=0.9,
-                time_step=-1.0, bc=None, compat="src"):
+                time_step=-1.0, bc=None, compat="src", shock_indicator="limiter"):
     """bc: {boundary_id: kind} or {boundary_id: ("periodic", partner)}; default outflow
     (reference src/parameters.cc:384). Returns (Params, periodic_pair[10])."""
     p = Params()
+    p.shock_indicator = INDICATOR[shock_indicator]
     p.basis, p.degree, p.flux_type = BASIS[basis], degree, FLUX[flux]
     p.limiter_type = LIMITER[limiter]
     p.char_lim, p.pos_lim = int(char_lim), int(pos_lim)
@@ -159,6 +164,7 @@ def _declare_engine(L, prefix):
     f("advance").argtypes = [vp, ctypes.c_int, ctypes.c_double, c_double_p, c_double_p]
     f("poll_error").argtypes = [vp]
     f("get_limited_flags").argtypes = [vp, c_int_p]
+    f("get_shock_indicator").argtypes = [vp, c_double_p]
     f("launch_count").restype = ctypes.c_int64
     f("launch_count").argtypes = [vp]
     f("stream").restype = vp
@@ -367,6 +373,11 @@ class Engine:
         f = np.zeros(self.n_cells, dtype=np.int32)
         self._check(self._f("get_limited_flags")(self.h, f.ctypes.data_as(c_int_p)))
         return f
+
+    def shock_indicator(self):
+        s = np.zeros(self.n_cells)
+        self._check(self._f("get_shock_indicator")(self.h, _dp(s)))
+        return s
 
     def launch_count(self):
         return self._f("launch_count")(self.h)

@@ -117,6 +117,7 @@
    }                                                                                                                     \
    int DFLO_ABI_CAT (PREFIX, poll_error) (CTX *c) { return c ? c->eng.poll_error () : DFLO_E_INVALID; }                  \
    int DFLO_ABI_CAT (PREFIX, get_limited_flags) (CTX *c, int32_t *f) { return (c && f) ? c->eng.get_limited_flags (f) : DFLO_E_INVALID; } \
+   int DFLO_ABI_CAT (PREFIX, get_shock_indicator) (CTX *c, double *s) { return (c && s) ? c->eng.get_shock_indicator (s) : DFLO_E_INVALID; } \
    int64_t DFLO_ABI_CAT (PREFIX, launch_count) (const CTX *c) { return c ? c->eng.bk.launches : 0; }                     \
    void *DFLO_ABI_CAT (PREFIX, stream) (const CTX *c) { return c ? c->eng.bk.stream_handle () : nullptr; }               \
    int DFLO_ABI_CAT (PREFIX, synchronize) (CTX *c)                                                                       \

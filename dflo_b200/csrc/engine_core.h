@@ -340,6 +340,27 @@ namespace dflo
 #undef DFLO_LIM
    }
 
+   template <class BK>
+   void launch_indicator (BK &bk, int basis, int n1, const IndicatorArgs &a)
+   {
+      if (n1 == 1) return;
+#define DFLO_IND(B, N) bk.template launch1d<IndicatorKernel<B, N>> (a.n_cells, a)
+      if (basis == BASIS_QK)
+      {
+         if (n1 == 2) DFLO_IND (BASIS_QK, 2);
+         else if (n1 == 3) DFLO_IND (BASIS_QK, 3);
+         else if (n1 == 4) DFLO_IND (BASIS_QK, 4);
+         else DFLO_IND (BASIS_QK, 5);
+      }
+      else
+      {
+         if (n1 == 2) DFLO_IND (BASIS_PK, 2);
+         else if (n1 == 3) DFLO_IND (BASIS_PK, 3);
+         else DFLO_IND (BASIS_PK, 4);
+      }
+#undef DFLO_IND
+   }
+
    //---------------------------------------------------------------------------------------------
    // The engine
    //---------------------------------------------------------------------------------------------
@@ -369,6 +390,7 @@ namespace dflo
       double *d_geom = nullptr, *d_bc_g = nullptr, *d_stage_tab = nullptr, *d_lim_tab = nullptr, *d_gw = nullptr, *d_gx = nullptr;
       int *d_bkind = nullptr, *d_bf_cell = nullptr, *d_bf_face = nullptr, *d_bf_id = nullptr, *d_l2g = nullptr, *d_flags = nullptr;
       unsigned int *d_err = nullptr;
+      double *d_shock = nullptr;       // shock_indicator per local cell
       ExprInstr *d_code = nullptr;
       int *d_prog_start = nullptr;
       int *d_prog_start_t = nullptr;  // same table with the time-independent programs emptied: the per-stage refresh
@@ -391,6 +413,7 @@ namespace dflo
       int D () const { return tab.D; }
       bool tvb () const { return prm.limiter_type == DFLO_LIMITER_TVB && tab.k > 0; }
       bool pos () const { return prm.pos_lim && tab.k > 0; }
+      bool kxrcf () const { return tvb () && prm.shock_indicator != DFLO_INDICATOR_LIMITER; }
 
       int init (const dflo_flat_mesh &mesh, const dflo_params &p, int rank, int world)
       {
@@ -398,6 +421,11 @@ namespace dflo
          if (p.basis != DFLO_BASIS_QK && p.basis != DFLO_BASIS_PK) return fail (DFLO_E_INVALID, "unknown basis");
          if (!build_tables (p.basis, p.degree, tab)) return fail (DFLO_E_UNSUPPORTED, "degree out of range (Qk 0..4, Pk 0..3)");
          if (p.flux_type < 0 || p.flux_type > 4) return fail (DFLO_E_INVALID, "unknown flux");
+         if (p.shock_indicator < 0 || p.shock_indicator > 2) return fail (DFLO_E_INVALID, "unknown shock indicator");
+         // the KXRCF pass reads post-update neighbour DoFs, which a sharded context holds for ghost
+         // cells only after the halo exchange that follows the limiter
+         if (p.shock_indicator != DFLO_INDICATOR_LIMITER && world > 1)
+            return fail (DFLO_E_UNSUPPORTED, "KXRCF shock indicator on a sharded context");
          if (mesh.n_cells <= 0) return fail (DFLO_E_INVALID, "empty mesh");
          for (int b = 0; b < mesh.n_boundary_faces; ++b)
             if (mesh.bface_id[b] < 0 || mesh.bface_id[b] >= DFLO_MAX_BOUNDARIES) return fail (DFLO_E_INVALID, "boundary id out of range");
@@ -463,6 +491,12 @@ namespace dflo
          d_lim_tab = upload (pack_limiter_tables (tab));
          d_gw = upload (std::vector<double> (tab.gw, tab.gw + tab.n1));
          d_gx = upload (std::vector<double> (tab.gx, tab.gx + tab.n1));
+         d_shock = bk.template alloc<double> (lm.n_local);
+         {
+            std::vector<double> all ((size_t) lm.n_local, 1.0e20); // indicator.cc:18-22
+            bk.h2d (d_shock, all.data (), all.size () * sizeof (double));
+            bk.sync ();
+         }
          d_flags = bk.template alloc<int> (lm.n_local);
          bk.zero (d_flags, lm.n_local * sizeof (int));
          d_err = bk.template alloc<unsigned int> (1);
@@ -496,7 +530,7 @@ namespace dflo
             bk.free (AVG[i]);
          }
          void *ptrs[] = {rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
-                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_code, d_prog_start, d_prog_start_t, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles, d_rowdesc, d_send_entries};
+                         d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_shock, d_code, d_prog_start, d_prog_start_t, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles, d_rowdesc, d_send_entries};
          for (void *p : ptrs) bk.free (p);
          for (int k = 0; k < 2; ++k)
          {
@@ -537,6 +571,15 @@ namespace dflo
          bk.d2h (loc.data (), AVG[cur], loc.size () * sizeof (double));
          for (int l = 0; l < lm.n_owned; ++l)
             for (int c = 0; c < 4; ++c) avg[(size_t) lm.l2g[l] * 4 + c] = loc[(size_t) l * 4 + c];
+         return bk.check (error);
+      }
+
+      int get_shock_indicator (double *ind)
+      {
+         bk.sync ();
+         std::vector<double> loc (lm.n_owned);
+         bk.d2h (loc.data (), d_shock, loc.size () * sizeof (double));
+         for (int l = 0; l < lm.n_owned; ++l) ind[lm.l2g[l]] = loc[l];
          return bk.check (error);
       }
 
@@ -659,6 +702,7 @@ namespace dflo
          {
             LimiterArgs a = limiter_args (cur);
             a.pos_lim = 0;
+            enqueue_indicator (cur);
             launch_limiter (bk, tab.basis, tab.n1, a);
             exchange_halo (cur);
          }
@@ -863,6 +907,7 @@ namespace dflo
          a.fflags = d_fflags;
          a.geom = d_geom;
          a.tab = d_lim_tab;
+         a.shock = kxrcf () ? d_shock : nullptr;
          a.flags_out = d_flags;
          a.err = d_err;
          a.n_compute = lm.n_owned;
@@ -873,6 +918,23 @@ namespace dflo
          a.M = prm.M;
          a.beta = prm.beta;
          return a;
+      }
+
+      // compute_shock_indicator (claw.cc:763, 1000) of buffer buf; "limiter" type: all cells, no pass
+      void enqueue_indicator (int buf)
+      {
+         if (!kxrcf ()) return;
+         IndicatorArgs a;
+         a.u = U[buf];
+         a.avg = AVG[buf];
+         a.nbr = d_nbr;
+         a.fflags = d_fflags;
+         a.geom = d_geom;
+         a.tab = d_stage_tab;
+         a.shock = d_shock;
+         a.n_cells = lm.n_owned;
+         a.component = prm.shock_indicator == DFLO_INDICATOR_DENSITY ? RHO : ENE;
+         launch_indicator (bk, tab.basis, tab.n1, a);
       }
 
       void compute_cell_average (int buf, int n_cells)
@@ -943,6 +1005,7 @@ namespace dflo
          if (tvb () || pos ())
          {
             LimiterArgs l = limiter_args (out);
+            enqueue_indicator (out);
             launch_limiter (bk, tab.basis, tab.n1, l);
          }
          cur = out;

@@ -317,9 +317,9 @@ namespace dflo
             err = "mesh refinement is not supported by the B200 engine (set refinement = false)";
             return false;
          }
-         if (shock_indicator != "limiter")
+         if (shock_indicator == "u2")
          {
-            err = "only 'shock indicator = limiter' is supported by the B200 engine; got " + shock_indicator;
+            err = "'shock indicator = u2' belongs to the MOOD path, which the B200 engine does not cover";
             return false;
          }
          if (diffusion_coef != 0.0)
@@ -336,6 +336,7 @@ namespace dflo
          p.pos_lim = pos_lim;
          p.conserve_angular_momentum = conserve_angular_momentum;
          p.compat = compat;
+         p.shock_indicator = shock_indicator == "density" ? DFLO_INDICATOR_DENSITY : shock_indicator == "energy" ? DFLO_INDICATOR_ENERGY : DFLO_INDICATOR_LIMITER; // parameters.cc:229-237
          p.M = M;
          p.beta = beta;
          p.gravity = gravity;

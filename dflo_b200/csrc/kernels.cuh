@@ -772,6 +772,7 @@ namespace dflo
       const unsigned char *fflags;
       const double *geom;
       const double *tab;      // flat limiter tables
+      const double *shock;    // shock_indicator per cell (TVB only where > 1, limiter.cc:263, 406), or nullptr: every cell
       int *flags_out;         // [n_local] bit0 TVB rewrote, bit1 theta1<1, bit2 theta2<1
       unsigned int *err;      // device error word
       int n_compute;
@@ -891,6 +892,7 @@ namespace dflo
             // characteristic projection, minmod (limiter.cc:283-345 / 425-486)
             if (!A.tvb || tid >= ncb) return;
             const int s = tid, cl = c0 + tid;
+            if (A.shock && !(A.shock[cl] > 1.0)) return; // limiter.cc:263, 406
             const double hx = A.geom[(size_t) cl * 4 + 2], hy = A.geom[(size_t) cl * 4 + 3];
             const double dx = sqrt (hx * hx + hy * hy) / 1.4142135623730951; // diameter / sqrt(dim)
             const double Mdx2 = A.M * dx * dx;
@@ -1222,7 +1224,7 @@ namespace dflo
          double lo[4] = {1.0e300, 1.0e300, 1.0e300, 1.0e300}, hi[4] = {-1.0e300, -1.0e300, -1.0e300, -1.0e300};
          bool have_bounds = false;
 
-         if (A.tvb)
+         if (A.tvb && (!A.shock || A.shock[cell] > 1.0)) // limiter.cc:263, 406
          {
             const double hx = A.geom[(size_t) cell * 4 + 2], hy = A.geom[(size_t) cell * 4 + 3];
             const double dx = sqrt (hx * hx + hy * hy) / 1.4142135623730951; // diameter / sqrt(dim)
@@ -1519,6 +1521,81 @@ namespace dflo
          }
          if (A.flags_out) A.flags_out[cell] = flag;
          return flag != 0;
+      }
+   };
+
+   //---------------------------------------------------------------------------------------------
+   // KXRCF shock indicator, compute_shock_indicator_kxrcf (indicator.cc:50-198), one thread per
+   // cell: the jump of density (or energy) over the inflow part of the cell's interior faces,
+   // normalised by diameter^((k+1)/2) x inflow measure x cell mean.  Reads the freshly updated
+   // solution of the cell and of its face neighbours BEFORE any cell is limited, which is why it
+   // is its own pass (the reference, too, fills shock_indicator for all cells first, claw.cc:763).
+   //---------------------------------------------------------------------------------------------
+   struct IndicatorArgs
+   {
+      const double *u, *avg;
+      const int *nbr;
+      const unsigned char *fflags;
+      const double *geom;
+      const double *tab;   // flat stage tables (end-point values / face tables, Gauss weights)
+      double *shock;
+      int n_cells, component;
+   };
+
+   template <int BASIS, int N1>
+   struct IndicatorKernel
+   {
+      typedef IndicatorArgs Args;
+      typedef StageKernel<BASIS, N1, FLUX_LXF> SK;
+      static constexpr int NS = SK::NS, D = SK::D;
+
+      // component c of cell ucell at point q of its face f (the fma chain of StageKernel::trace)
+      static DFLO_DEV double trace1 (const double *tb, const double *ucell, int f, int q, int c)
+      {
+         double s = 0.0;
+         if (BASIS == BASIS_QK)
+         {
+            const double *e = SK::t_e (tb, f & 1);
+            const int base = (f < 2) ? N1 * q : q, stride = (f < 2) ? 1 : N1;
+            for (int a = 0; a < N1; ++a) s = fma (e[a], ucell[c * NS + base + a * stride], s);
+         }
+         else
+         {
+            const double *pf = SK::t_phiface (tb) + (f * N1 + q) * NS;
+            for (int m = 0; m < NS; ++m) s = fma (pf[m], ucell[c * NS + m], s);
+         }
+         return s;
+      }
+
+      static DFLO_DEV void thread (const Args &A, int cell)
+      {
+         if (cell >= A.n_cells) return;
+         const double *tb = A.tab;
+         const double *gw = SK::t_gw (tb);
+         const double hx = A.geom[(size_t) cell * 4 + 2], hy = A.geom[(size_t) cell * 4 + 3];
+         const double *av = A.avg + (size_t) cell * 4;
+         const double vel[2] = {av[0] / av[RHO], av[1] / av[RHO]};                       // :108-110
+         double ind = 0.0, inflow_measure = 0.0;
+         for (int f = 0; f < 4; ++f)
+         {
+            const int nb = A.nbr[(size_t) cell * 4 + f];
+            const int fl = A.fflags[(size_t) cell * 4 + f];
+            if (nb < 0 || (fl & FACE_PERIODIC)) continue;                                // at_boundary(f): nothing, :181-186
+            const double nx = (f == 0) ? -1.0 : (f == 1) ? 1.0 : 0.0, ny = (f == 2) ? -1.0 : (f == 3) ? 1.0 : 0.0;
+            const int inflow_status = (vel[0] * nx + vel[1] * ny < 0);                   // :125
+            const double len = (f < 2) ? hy : hx;
+            for (int q = 0; q < N1; ++q)
+            {
+               const double own = trace1 (tb, A.u + (size_t) cell * D, f, q, A.component);
+               const double nbv = trace1 (tb, A.u + (size_t) nb * D, f ^ 1, q, A.component);
+               const double jxw = gw[q] * len;
+               ind += inflow_status * (own - nbv) * jxw;
+               inflow_measure += inflow_status * jxw;
+            }
+         }
+         const double diameter = sqrt (hx * hx + hy * hy);
+         const double denominator = pow (diameter, 0.5 * N1) * inflow_measure * av[A.component]; // :189-194
+         A.shock[cell] = fabs (ind) / denominator;
       }
    };
 

@@ -6,7 +6,7 @@
  *     assemble_system(integrator)            src/assemble_explicit.cc:433-452
  *     solve() rk3 branch + RK combine        src/claw.cc:694-713, 757-760
  *     compute_cell_average()                 src/claw.cc:562-597
- *     compute_shock_indicator() "limiter"    src/indicator.cc:15-22
+ *     compute_shock_indicator()              src/indicator.cc:15-31 (limiter), 50-198 (KXRCF density / energy)
  *     apply_limiter() TVB Qk/Pk              src/limiter.cc:224-516
  *     apply_positivity_limiter()             src/positivity.cc:16-208
  * plus compute_time_step() (src/claw.cc:444-511).  INTEGRATION.md shows the call sites a dflo
@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFLO_B200_ABI_VERSION 1
+#define DFLO_B200_ABI_VERSION 2
 #define DFLO_MAX_BOUNDARIES 10 /* Parameters::AllParameters::max_n_boundaries, src/parameters.h:370 */
 
 /* error codes */
@@ -56,6 +56,10 @@ enum { DFLO_BC_INFLOW = 0, DFLO_BC_OUTFLOW = 1, DFLO_BC_SLIP = 2, DFLO_BC_PRESSU
 enum { DFLO_BASIS_QK = 0, DFLO_BASIS_PK = 1 };
 /* Parameters::Limiter::LimiterType, src/parameters.h:243 */
 enum { DFLO_LIMITER_NONE = 0, DFLO_LIMITER_TVB = 1 };
+/* Parameters::Limiter::ShockIndType, src/parameters.h: which cells the TVB limiter may touch.
+ * limiter: every cell (src/indicator.cc:18-22); density / energy: the KXRCF indicator of that variable
+ * (src/indicator.cc:50-198), cells with indicator > 1 (src/limiter.cc:263, 406) */
+enum { DFLO_INDICATOR_LIMITER = 0, DFLO_INDICATOR_DENSITY = 1, DFLO_INDICATOR_ENERGY = 2 };
 /* which tree's semantics where src/ and src_mpi/ differ (SURVEY.md 8a "semantic forks") */
 enum { DFLO_COMPAT_SRC = 0, DFLO_COMPAT_MPI = 1 };
 
@@ -105,6 +109,8 @@ typedef struct
    double cfl;                         /* "cfl" */
    double time_step;                   /* "time step" (<=0: unused), src/claw.cc:471-472 */
    int32_t bc_kind[DFLO_MAX_BOUNDARIES];   /* DFLO_BC_* per boundary id */
+   int32_t shock_indicator;            /* DFLO_INDICATOR_* ("shock indicator" in subsection limiter) */
+   int32_t reserved0;
 } dflo_params;
 
 typedef struct dflo_ctx dflo_ctx;
@@ -163,6 +169,8 @@ int dflo_b200_limit_initial_condition (dflo_ctx *ctx);
 int dflo_b200_advance (dflo_ctx *ctx, int n_steps, double final_time, double *elapsed_time, double *last_dt);
 /* poll the device error word (DFLO_E_NEGATIVE_STATE / DFLO_E_POSLIM_ROOT), synchronises */
 int dflo_b200_poll_error (dflo_ctx *ctx);
+/* shock_indicator of the last stage (src/indicator.cc), [n_cells_global]; 1e20 everywhere for DFLO_INDICATOR_LIMITER */
+int dflo_b200_get_shock_indicator (dflo_ctx *ctx, double *ind);
 /* per-cell limiter activity of the last stage: bit0 TVB rewrote the cell, bit1 theta1<1, bit2 theta2<1 */
 int dflo_b200_get_limited_flags (dflo_ctx *ctx, int32_t *flags /* [n_cells_global] */);
 

@@ -458,6 +458,47 @@ namespace
    }
 
    //---------------------------------------------------------------------------------------------
+   // compute_shock_indicator, indicator.cc:15-31 and compute_shock_indicator_kxrcf, 50-198
+   // (same-level neighbours only: the engine has no hanging nodes).  Periodic faces are boundary
+   // faces to cell->at_boundary(): like the reference, nothing is done on them.
+   //---------------------------------------------------------------------------------------------
+   void compute_shock_indicator (oracle_ctx &o)
+   {
+      const int nc = o.cells.size ();
+      if (o.prm.shock_indicator == 0)
+      {
+         std::fill (o.shock_indicator.begin (), o.shock_indicator.end (), 1e20); // :18-22
+         return;
+      }
+      const int component = o.prm.shock_indicator == 1 ? RHO : ENE;               // :70-82
+      const int nqf = o.fe.n1;
+      std::vector<double> W (nqf * NC), Wn (nqf * NC);
+      for (int c = 0; c < nc; ++c)
+      {
+         const Cell &cl = o.cells[c];
+         double cell_shock_ind = 0, inflow_measure = 0;
+         double vel[2];
+         for (int i = 0; i < 2; ++i) vel[i] = o.cell_average[c * NC + i] / o.cell_average[c * NC + RHO]; // :108-110
+         for (int f = 0; f < 4; ++f)
+         {
+            if (!o.shared[c * 4 + f]) continue;                                   // at_boundary: nothing, :181-186
+            const int n = cl.nbr[f], nf = f ^ 1;                                  // neighbor_of_neighbor
+            face_values (o, c, f, W.data ());
+            face_values (o, n, nf, Wn.data ());
+            for (int q = 0; q < nqf; ++q)
+            {
+               const int inflow_status = (vel[0] * NORMAL[f][0] + vel[1] * NORMAL[f][1] < 0);      // :125
+               cell_shock_ind += inflow_status * (W[q * NC + component] - Wn[q * NC + component]) * face_JxW (o, cl, f, q);
+               inflow_measure += inflow_status * face_JxW (o, cl, f, q);
+            }
+         }
+         const double cell_norm = o.cell_average[c * NC + component];            // :189-194
+         const double denominator = std::pow (o.diameter (cl), 0.5 * (o.fe.k + 1)) * inflow_measure * cell_norm;
+         o.shock_indicator[c] = std::fabs (cell_shock_ind) / denominator;
+      }
+   }
+
+   //---------------------------------------------------------------------------------------------
    // assemble_explicit.cc:127-248 (+ periodic branch of src_mpi/assemble_explicit.cc:186-260)
    //---------------------------------------------------------------------------------------------
    void integrate_boundary_term (const oracle_ctx &o, int cno, int f, double *local)
@@ -1002,7 +1043,7 @@ namespace
       for (size_t j = 0; j < o.current.size (); ++j) o.current[j] += o.newton_update[j];           // :757
       for (size_t j = 0; j < o.current.size (); ++j) o.current[j] = (1.0 - a) * o.current[j] + a * o.old[j]; // :760
       compute_cell_average (o);                                                                     // :762
-      std::fill (o.shock_indicator.begin (), o.shock_indicator.end (), 1e20);                       // indicator.cc:18-22
+      compute_shock_indicator (o);                                                                  // :763
       std::fill (o.limited.begin (), o.limited.end (), 0);
       apply_limiter (o);                                                                            // :764
       if (o.prm.pos_lim) return apply_positivity_limiter (o);                                       // :766
@@ -1206,8 +1247,11 @@ double oracle_compute_dt (oracle_ctx *o, double elapsed, double final_time, doub
 {
    return compute_time_step (*o, elapsed, final_time, time_step);
 }
+void oracle_compute_shock_indicator (oracle_ctx *o) { compute_shock_indicator (*o); }
+void oracle_get_shock_indicator (const oracle_ctx *o, double *ind) { std::copy (o->shock_indicator.begin (), o->shock_indicator.end (), ind); }
 void oracle_apply_limiter (oracle_ctx *o)
 {
+   compute_shock_indicator (*o); // claw.cc:1000-1001
    std::fill (o->limited.begin (), o->limited.end (), 0);
    apply_limiter (*o);
 }

@@ -35,6 +35,7 @@ typedef struct
                             (src/assemble_explicit.cc:203-204); _MPI: BC-reflected average
                             (src_mpi/assemble_explicit.cc:296-321) */
    int n_threads;        /* >1: cells integrated in parallel chunks, serial copier (WorkStream) */
+   int shock_indicator;  /* 0 limiter (all cells, indicator.cc:18-22), 1 density, 2 energy (KXRCF, indicator.cc:50-198) */
 } oracle_params;
 
 typedef struct oracle_ctx oracle_ctx;
@@ -45,6 +46,9 @@ oracle_ctx *oracle_create (int n_vertices, const double *vertices /*[nv][2]*/, i
                            const int *cells /*[nc][4]*/, int n_blines, const int *blines /*[nb][2]*/,
                            const int *bline_id /*[nb]*/, const oracle_params *prm);
 void oracle_destroy (oracle_ctx *);
+/* compute_shock_indicator of the current solution / cell averages; values per cell */
+void oracle_compute_shock_indicator (oracle_ctx *);
+void oracle_get_shock_indicator (const oracle_ctx *, double *ind /*[nc]*/);
 const char *oracle_last_error (void);
 
 int oracle_n_cells (const oracle_ctx *);

@@ -24,7 +24,7 @@ class OracleParams(ctypes.Structure):
         ("M", ctypes.c_double), ("beta", ctypes.c_double), ("gravity", ctypes.c_double),
         ("cfl", ctypes.c_double),
         ("bc_kind", ctypes.c_int * 10), ("periodic_pair", ctypes.c_int * 10),
-        ("compat", ctypes.c_int), ("n_threads", ctypes.c_int),
+        ("compat", ctypes.c_int), ("n_threads", ctypes.c_int), ("shock_indicator", ctypes.c_int),
     ]
 
 
@@ -134,7 +134,7 @@ class Physics:
 
 def make_params(basis="Qk", degree=1, flux="lxf", limiter="none", char_lim=False, pos_lim=False,
                 conserve_angular_momentum=False, M=0.0, beta=1.0, gravity=0.0, cfl=0.9,
-                bc=None, compat="src", n_threads=1):
+                bc=None, compat="src", n_threads=1, shock_indicator="limiter"):
     """bc: {boundary_id: kind} or {boundary_id: ("periodic", partner_id)}; default outflow
     (src/parameters.cc:384)."""
     p = OracleParams()
@@ -156,6 +156,7 @@ def make_params(basis="Qk", degree=1, flux="lxf", limiter="none", char_lim=False
             p.bc_kind[b] = BC[kind]
     p.compat = 0 if compat == "src" else 1
     p.n_threads = n_threads
+    p.shock_indicator = {"limiter": 0, "density": 1, "energy": 2}[shock_indicator]
     return p
 
 
@@ -255,6 +256,11 @@ class Oracle:
     def compute_dt(self, elapsed=0.0, final_time=1e20, time_step=-1.0):
         return self.L.oracle_compute_dt(self.h, ctypes.c_double(elapsed), ctypes.c_double(final_time),
                                         ctypes.c_double(time_step))
+
+    def shock_indicator(self):
+        s = np.zeros(self.n_cells)
+        self.L.oracle_get_shock_indicator(self.h, _d(s))
+        return s
 
     def apply_limiter(self):
         self.L.oracle_apply_limiter(self.h)

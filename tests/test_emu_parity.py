@@ -196,3 +196,16 @@ def test_time_dependent_boundary_expression_under_advance(compat):
     err, c = time_dependent_bc_case("emu", compat)
     assert err <= TOL_STEP_SHOCK
     c.close()
+
+
+@pytest.mark.parametrize("variable", ["density", "energy"])
+@pytest.mark.parametrize("basis,k", [("Qk", 1), ("Qk", 2), ("Pk", 2)])
+def test_kxrcf_shock_indicator_gates_the_limiter(basis, k, variable):
+    """`shock indicator = density | energy`: the KXRCF indicator (src/indicator.cc:50-198) decides
+    which cells the TVB limiter may touch (src/limiter.cc:263, 406)."""
+    from helpers import kxrcf_case
+    err, ind_err, flips, c = kxrcf_case("emu", basis, k, variable)
+    assert err <= TOL_STEP_SHOCK and ind_err <= 1e-10 and flips == 0
+    flags = c.oracle.limited_flags()
+    assert 0 < np.count_nonzero(flags) < flags.size          # selective: the shock region only
+    c.close()

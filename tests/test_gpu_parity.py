@@ -252,3 +252,16 @@ def test_time_dependent_boundary_expression_under_advance(compat):
     err, c = time_dependent_bc_case("cuda", compat)
     assert err <= TOL_STEP_SHOCK
     c.close()
+
+
+@pytest.mark.parametrize("variable", ["density", "energy"])
+@pytest.mark.parametrize("basis,k", [("Qk", 1), ("Qk", 2), ("Qk", 3), ("Pk", 2)])
+def test_kxrcf_shock_indicator_gates_the_limiter(basis, k, variable):
+    """KXRCF shock indicator (src/indicator.cc:50-198) on the device: indicator values, limiter
+    decisions and solution against the oracle."""
+    from helpers import kxrcf_case
+    err, ind_err, flips, c = kxrcf_case("cuda", basis, k, variable)
+    assert err <= TOL_STEP_SHOCK and ind_err <= 1e-10 and flips == 0
+    flags = c.oracle.limited_flags()
+    assert 0 < np.count_nonzero(flags) < flags.size
+    c.close()
