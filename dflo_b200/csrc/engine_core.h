@@ -422,10 +422,6 @@ namespace dflo
          if (!build_tables (p.basis, p.degree, tab)) return fail (DFLO_E_UNSUPPORTED, "degree out of range (Qk 0..4, Pk 0..3)");
          if (p.flux_type < 0 || p.flux_type > 4) return fail (DFLO_E_INVALID, "unknown flux");
          if (p.shock_indicator < 0 || p.shock_indicator > 2) return fail (DFLO_E_INVALID, "unknown shock indicator");
-         // the KXRCF pass reads post-update neighbour DoFs, which a sharded context holds for ghost
-         // cells only after the halo exchange that follows the limiter
-         if (p.shock_indicator != DFLO_INDICATOR_LIMITER && world > 1)
-            return fail (DFLO_E_UNSUPPORTED, "KXRCF shock indicator on a sharded context");
          if (mesh.n_cells <= 0) return fail (DFLO_E_INVALID, "empty mesh");
          for (int b = 0; b < mesh.n_boundary_faces; ++b)
             if (mesh.bface_id[b] < 0 || mesh.bface_id[b] >= DFLO_MAX_BOUNDARIES) return fail (DFLO_E_INVALID, "boundary id out of range");
@@ -1005,6 +1001,10 @@ namespace dflo
          if (tvb () || pos ())
          {
             LimiterArgs l = limiter_args (out);
+            // KXRCF on a sharded context: the indicator of an owned cell reads its neighbours'
+            // post-update DoFs; for ghost neighbours they arrive with an extra exchange of the
+            // pre-limiter state (the exchange after the limiter then overwrites them)
+            if (kxrcf () && !lm.peers.empty ()) exchange_halo (out);
             enqueue_indicator (out);
             launch_limiter (bk, tab.basis, tab.n1, l);
          }

@@ -20,7 +20,7 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))
 
 from dflo_b200 import abi  # noqa: E402
-from helpers import DMR_BC, PERIODIC_BOX, SOD_BC, ic_dmr, ic_sod, ic_vortex  # noqa: E402
+from helpers import DMR_BC, PERIODIC_BOX, SOD_BC, ic_dmr, ic_sod, ic_sod_moving, ic_vortex  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 CASES = [
@@ -32,6 +32,9 @@ CASES = [
     ("dmr_Q2_hllc_tvb", ("double_mach", [16]), DMR_BC, ic_dmr,
      dict(basis="Qk", degree=2, flux="hllc", limiter="TVB", char_lim=True, beta=1.0, M=100.0, cfl=0.9),
      (57.1576766498, -33.0, 8.0, 563.5), 3, 1e-9),
+    ("sod_Q2_kxrcf_density", ("sod_tube", [100, 10]), {0: "outflow", 1: "outflow", 2: "inflow"}, ic_sod_moving,
+     dict(basis="Qk", degree=2, flux="hllc", limiter="TVB", char_lim=True, beta=2.0, M=0.0, cfl=0.5, shock_indicator="density"),
+     (0.3, 0.1, 1.0, 2.55), 3, 1e-9),
 ]
 
 
