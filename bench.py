@@ -137,6 +137,19 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(workload):
+    """dram read + write bytes of one launch of the stage kernel from the committed ncu capture
+    (profiles/), or None when no capture of this workload is on file."""
+    p = os.path.join(ROOT, "profiles", "r01d_stage_kernel_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d.get("workload") == workload:
+            return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 def cpu_baseline(workload, budget_s=15.0, threads=None):
     """The oracle (kind 'port': restated assembly; physics = the reference's own equation.h object
     code when oracle/_ref was built) timed on this box's host cores on a bounded sample."""
@@ -360,7 +373,7 @@ def main():
                     "steps": e2e_steps, "what": "set_solution(pinned host) + advance(1 step) + get_solution(pinned host) per step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "StageKernel<%s,%d,%s>" % (basis, k + 1, flux),
+                         "traffic": measured_traffic(args.workload) if world == 1 else None, "kernel": "StageKernel<%s,%d,%s>" % (basis, k + 1, flux),
                          "kernel_ms": k_ms, "kernel_ms_l2_warm": k_ms_warm,
                          "algorithmic_bytes_per_launch": alg_bytes_launch,
                          "bytes_per_dof_update": bytes_per_update, "peak_source": peak_src},
