@@ -768,12 +768,6 @@ namespace dflo
          StageArgs a = stage_args (rk, MODE_STAGE);
          a.out = U[out];
          a.avg_out = AVG[out];
-         long long *d_trace = nullptr;
-         if (bk.debug_flags () & 8)
-         {
-            d_trace = bk.template alloc<long long> ((size_t) lm.n_tiles * 8);
-            a.trace = d_trace;
-         }
          double total = 0.0;
          for (int r = 0; r < reps; ++r)
          {
@@ -784,29 +778,6 @@ namespace dflo
             total += bk.timer_ms ();
          }
          bk.sync ();
-         if (d_trace)
-         {
-            // developer timeline of the last launch: mean cycles per phase over the blocks, and the span of one SM
-            std::vector<long long> t ((size_t) lm.n_tiles * 8);
-            bk.d2h (t.data (), d_trace, t.size () * sizeof (long long));
-            double ph[6] = {0, 0, 0, 0, 0, 0};
-            long long sm0_first = 0, sm0_last = 0;
-            int sm0_blocks = 0;
-            for (int b = 0; b < lm.n_tiles; ++b)
-            {
-               for (int i = 0; i < 6; ++i) ph[i] += (double) (t[(size_t) b * 8 + i + 1] - t[(size_t) b * 8 + i]);
-               if (t[(size_t) b * 8 + 7] == 0)
-               {
-                  if (!sm0_blocks || t[(size_t) b * 8] < sm0_first) sm0_first = t[(size_t) b * 8];
-                  if (!sm0_blocks || t[(size_t) b * 8 + 6] > sm0_last) sm0_last = t[(size_t) b * 8 + 6];
-                  ++sm0_blocks;
-               }
-            }
-            std::fprintf (stderr, "[stage trace] %d blocks; mean cycles: issue-staging %.0f | wait staging %.0f | P1 %.0f | P2 %.0f | P3 %.0f | P4 %.0f ; SM0 ran %d blocks in %lld cycles\n",
-                          lm.n_tiles, ph[0] / lm.n_tiles, ph[1] / lm.n_tiles, ph[2] / lm.n_tiles, ph[3] / lm.n_tiles, ph[4] / lm.n_tiles, ph[5] / lm.n_tiles,
-                          sm0_blocks, sm0_last - sm0_first);
-            bk.free (d_trace);
-         }
          bk.free (scratch);
          *avg_ms = (float) (total / reps);
          return bk.check (error);
@@ -886,7 +857,6 @@ namespace dflo
          a.dbg = bk.debug_flags ();
          a.n_tiles_owned = lm.n_tiles_owned;
          a.fx = nullptr;
-         a.trace = nullptr;
          a.mode = mode;
          a.compat_mpi = prm.compat == DFLO_COMPAT_MPI;
          a.ark = ark[rk];

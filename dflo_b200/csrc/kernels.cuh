@@ -96,8 +96,7 @@ namespace dflo
       int pf_tiles;           // row kernel: prefetch distance in tiles (resident blocks of the device)
       int n_tiles_owned;      // tiles >= this one are redundantly updated ghost cells: only their means are stored
       const P2PFused *fx;     // row kernel: halo exchange over peer memory fused into the stage kernel, or nullptr
-      long long *trace;       // developer timeline (DFLO_B200_DBG & 8): 8 clock stamps per block, or nullptr
-      int dbg;                // developer timing experiments only (DFLO_B200_DBG): 1 no Riemann solves, 2 no volume fluxes, 4 no extra-warp jobs
+      int dbg;                // developer timing experiments only (DFLO_B200_DBG): 1 no Riemann solves, 2 no volume fluxes, 4 no edge jobs
       int mode;
       int compat_mpi;
       double ark;
@@ -292,8 +291,8 @@ namespace dflo
             // cells, old_solution of the tile, geometry, the unique-face list and (LxF) the cell
             // averages.  Later phases touch global memory only to write.
             const int h0 = td.h0, nh = td.nh, nj = td.nj;
-            const unsigned cell_bytes = (unsigned) (D * sizeof (double));
 #if defined(__CUDA_ARCH__)
+            const unsigned cell_bytes = (unsigned) (D * sizeof (double));
             if (tid == 0)
             {
                unsigned bytes = (unsigned) (ncb + nh) * cell_bytes + (unsigned) ncb * 32u + (unsigned) nj * 16u;

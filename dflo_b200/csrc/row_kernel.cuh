@@ -13,7 +13,7 @@
 //     table operands (D.w, l_a(0), l_a(1), w_a) are constant-bank immediates.
 //   * every face is solved once per tile, along +e_x / +e_y, by the thread that owns the low-side
 //     cell's row/column (row_desc.h); tile-edge low faces and the traces of halo cells are the job
-//     of two extra warps.  Neighbouring threads exchange one 32-byte trace and one 32-byte flux
+//     of one extra warp.  Neighbouring threads exchange one 32-byte trace and one 32-byte flux
 //     per face point through shared memory; nothing else is shared except the y part of the
 //     residual, which is transposed back to row order through one padded buffer.
 //   * the tile and its halo cells arrive by per-cell bulk async copies (TMA) into a padded layout
@@ -42,10 +42,7 @@ namespace dflo
    {
       static constexpr int NS = N1 * N1, D = 4 * NS;
       static constexpr int TC = row_tc (N1), NH = row_nh (N1);
-#ifndef DFLO_ROW_PAD
-#define DFLO_ROW_PAD 2
-#endif
-      static constexpr int CS = D + DFLO_ROW_PAD;           // padded cell stride in shared memory (doubles)
+      static constexpr int CS = D + 2;                      // padded cell stride in shared memory (doubles)
       #ifndef DFLO_ROW_EXTRA
 #define DFLO_ROW_EXTRA 32
 #endif
@@ -268,12 +265,7 @@ namespace dflo
          mbar_expect_tx (sm, bytes);
       }
       __syncthreads ();
-      if (DFLO_ROW_PAD == 0 && tid < ncb)
-      {
-         if (tid == 0) bulk_g2s (su, A.u + (size_t) c0 * D, (unsigned) ncb * cell_bytes, sm);
-         if (FLUX == FLUX_LXF) bulk_g2s (sAvg + tid * 4, A.avg + (size_t) (c0 + tid) * 4, 32u, sm);
-      }
-      else if (tid < ncb + nh)
+      if (tid < ncb + nh)
       {
          const int cell = tid < ncb ? c0 + tid : gdesc[S::OFF_HALO + tid - ncb];
          const int slot = tid < ncb ? tid : TC + tid - ncb;
