@@ -21,7 +21,8 @@
 //     (64-bit, even/odd cell interleave for N1 = 4) free of bank conflicts; old_solution is
 //     prefetched into L2 by one bulk prefetch and read straight into registers at the end.
 //
-// Per Q3 cell this is ~4 k SASS instructions (~3 k fp64) against ~21 k (8 k) in the phase kernel.
+// Per Q3 cell this is ~8 k SASS thread-instructions (4.0 k fp64) against 11.5 k (4.1 k) in the phase
+// kernel, and a third of its shared-memory wavefronts.
 #pragma once
 
 #include "kernels.cuh"
