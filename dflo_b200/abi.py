@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DFLO_B200_LIB") or os.path.join(_HERE, "csrc", "libdflo_b200.so")
 
 MAX_BOUNDARIES = 10
-FLUX = {"lxf": 0, "sw": 1, "kfvs": 2, "roe": 3, "hllc": 4}
+FLUX = {"lxf": 0, "sw": 1, "kfvs": 2, "roe": 3, "hllc": 4, "kep": 5}
 BC = {"inflow": 0, "outflow": 1, "slip": 2, "pressure": 3, "farfield": 4, "periodic": 5}
 BASIS = {"Qk": 0, "Pk": 1}
 LIMITER = {"none": 0, "TVB": 1}

@@ -286,6 +286,7 @@ namespace dflo
             case FLUX_SW: bk.template launch_stage<StageKernel<BASIS, N1, FLUX_SW>> (n_tiles, a); break;
             case FLUX_KFVS: bk.template launch_stage<StageKernel<BASIS, N1, FLUX_KFVS>> (n_tiles, a); break;
             case FLUX_ROE: bk.template launch_stage<StageKernel<BASIS, N1, FLUX_ROE>> (n_tiles, a); break;
+            case FLUX_KEP: bk.template launch_stage<StageKernel<BASIS, N1, FLUX_KEP>> (n_tiles, a); break;
             default: bk.template launch_stage<StageKernel<BASIS, N1, FLUX_HLLC>> (n_tiles, a); break;
          }
       }
@@ -420,7 +421,7 @@ namespace dflo
          prm = p;
          if (p.basis != DFLO_BASIS_QK && p.basis != DFLO_BASIS_PK) return fail (DFLO_E_INVALID, "unknown basis");
          if (!build_tables (p.basis, p.degree, tab)) return fail (DFLO_E_UNSUPPORTED, "degree out of range (Qk 0..4, Pk 0..3)");
-         if (p.flux_type < 0 || p.flux_type > 4) return fail (DFLO_E_INVALID, "unknown flux");
+         if (p.flux_type < 0 || p.flux_type > 5) return fail (DFLO_E_INVALID, "unknown flux");
          if (p.shock_indicator < 0 || p.shock_indicator > 2) return fail (DFLO_E_INVALID, "unknown shock indicator");
          if (mesh.n_cells <= 0) return fail (DFLO_E_INVALID, "empty mesh");
          for (int b = 0; b < mesh.n_boundary_faces; ++b)

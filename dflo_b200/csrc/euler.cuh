@@ -27,7 +27,10 @@ namespace dflo
    constexpr int RHO = 2;
    constexpr int ENE = 3;
 
-   enum FluxType { FLUX_LXF = 0, FLUX_SW = 1, FLUX_KFVS = 2, FLUX_ROE = 3, FLUX_HLLC = 4 };
+   enum FluxType { FLUX_LXF = 0, FLUX_SW = 1, FLUX_KFVS = 2, FLUX_ROE = 3, FLUX_HLLC = 4, FLUX_KEP = 5 };
+   // fluxes that read the two cell averages besides the two traces (lxf: equation.h:357-359; kep:
+   // its dissipation matrix is built from them, src_mpi/equation.h:900)
+   DFLO_HD constexpr bool flux_uses_averages (int flux) { return flux == FLUX_LXF || flux == FLUX_KEP; }
    enum BCKind { BC_INFLOW = 0, BC_OUTFLOW = 1, BC_SLIP = 2, BC_PRESSURE = 3, BC_FARFIELD = 4, BC_PERIODIC = 5 };
 
    // std::max / std::min with the C++ library's exact semantics ((a<b)?b:a and (b<a)?b:a).  They
@@ -314,6 +317,95 @@ namespace dflo
       for (int c = 0; c < 4; ++c) H[c] = pf[c] + mf[c];
    }
 
+   // Kinetic-energy preserving, entropy-stable flux of the MPI tree (src_mpi/equation.h: logavg 27-45,
+   // kep_diff_matrix 749-837 built from the two CELL AVERAGES, kep_flux 842-921).  Written once for a
+   // general normal; the axis forms below call it with n = (1, 0).
+   DFLO_HD double logavg (double a, double b)
+   {
+      const double xi = b / a;
+      const double f = (xi - 1.0) / (xi + 1.0);
+      const double u = f * f;
+      double F;
+      if (u < 1.0e-2)
+      {
+         const double u2 = u * u, u3 = u2 * u;
+         F = 1.0 + u / 3.0 + u2 / 5.0 + u3 / 7.0;
+      }
+      else
+         F = log (xi) / 2.0 / f;
+      return 0.5 * (a + b) / F;
+   }
+   DFLO_HD void kep_flux (double nx, double ny, const double Wl[4], const double Wr[4], const double Al[4], const double Ar[4], double H[4])
+   {
+      // central part, from the two traces
+      double p, beta, rho, vel[2], vel2, betal, betar, vl[2], vr[2], v2l, v2r, pl, pr;
+      {
+         const double rl = 1.0 / Wl[RHO], rr = 1.0 / Wr[RHO];
+         vl[0] = Wl[0] * rl; vl[1] = Wl[1] * rl; vr[0] = Wr[0] * rr; vr[1] = Wr[1] * rr;
+         v2l = vl[0] * vl[0] + vl[1] * vl[1];
+         v2r = vr[0] * vr[0] + vr[1] * vr[1];
+         vel[0] = 0.5 * (vl[0] + vr[0]);
+         vel[1] = 0.5 * (vl[1] + vr[1]);
+         vel2 = 0.5 * (v2l + v2r);
+         pl = GM1 * (Wl[ENE] - 0.5 * Wl[RHO] * v2l);
+         pr = GM1 * (Wr[ENE] - 0.5 * Wr[RHO] * v2r);
+         betal = 0.5 * Wl[RHO] / pl;
+         betar = 0.5 * Wr[RHO] / pr;
+         rho = logavg (Wl[RHO], Wr[RHO]);
+         beta = logavg (betal, betar);
+         p = 0.5 * (Wl[RHO] + Wr[RHO]) / (betal + betar);
+      }
+      const double vn = vel[0] * nx + vel[1] * ny;
+      const double frho = rho * vn;
+      const double f0 = nx * p + vel[0] * frho, f1 = ny * p + vel[1] * frho;
+      const double fE = 0.5 * (1.0 / (GM1 * beta) - vel2) * frho + f0 * vel[0] + f1 * vel[1];
+      // dissipation matrix R |Lambda| S R^T from the two averages
+      double Dm[4][4];
+      {
+         const double rl = 1.0 / Al[RHO], rr = 1.0 / Ar[RHO];
+         const double al0 = Al[0] * rl, al1 = Al[1] * rl, ar0 = Ar[0] * rr, ar1 = Ar[1] * rr;
+         const double a2l = al0 * al0 + al1 * al1, a2r = ar0 * ar0 + ar1 * ar1;
+         const double vnl = al0 * nx + al1 * ny, vnr = ar0 * nx + ar1 * ny;
+         const double w0 = 0.5 * (al0 + ar0), w1 = 0.5 * (al1 + ar1);
+         const double wn = w0 * nx + w1 * ny, w2 = w0 * w0 + w1 * w1;
+         const double qpl = GM1 * (Al[ENE] - 0.5 * Al[RHO] * a2l), qpr = GM1 * (Ar[ENE] - 0.5 * Ar[RHO] * a2r);
+         const double bl = 0.5 * Al[RHO] / qpl, br = 0.5 * Ar[RHO] / qpr;
+         const double rhoA = logavg (Al[RHO], Ar[RHO]);
+         const double betaA = logavg (bl, br);
+         const double a = sqrt (0.5 * GAMMA / betaA);
+         const double pA = 0.5 * (Al[RHO] + Ar[RHO]) / (bl + br);
+         const double Hh = a * a / GM1 + 0.5 * w2;
+         const double v1 = w0 * ny - w1 * nx;
+         const double R[4][4] = {{1, 1, 0, 1},
+                                 {w0 - a * nx, w0, ny, w0 + a * nx},
+                                 {w1 - a * ny, w1, -nx, w1 + a * ny},
+                                 {Hh - a * wn, 0.5 * w2, v1, Hh + a * wn}};
+         const double cl = sqrt (GAMMA * qpl / Al[RHO]), cr = sqrt (GAMMA * qpr / Ar[RHO]);
+         const double L0 = fabs (wn - a) + (1.0 / 6.0) * fabs ((vnl - cl) - (vnr - cr));
+         const double L3 = fabs (wn + a) + (1.0 / 6.0) * fabs ((vnl + cl) - (vnr + cr));
+         const double L12 = fabs (wn);
+         const double Dd[4] = {L0 * (0.5 * rhoA / GAMMA), L12 * (GM1 * rhoA / GAMMA), L12 * pA, L3 * (0.5 * rhoA / GAMMA)};
+         for (int i = 0; i < 4; ++i)
+            for (int j = i; j < 4; ++j)
+            {
+               double s = 0;
+               for (int k = 0; k < 4; ++k) s += R[i][k] * Dd[k] * R[j][k];
+               Dm[i][j] = Dm[j][i] = s;
+            }
+      }
+      // jump in the entropy variables of the traces
+      const double ds = log (pr / pl) - GAMMA * log (Wr[RHO] / Wl[RHO]);
+      const double dV[4] = {-ds / GM1 - (betar * v2r - betal * v2l), 2.0 * (betar * vr[0] - betal * vl[0]),
+                            2.0 * (betar * vr[1] - betal * vl[1]), -2.0 * (betar - betal)};
+      double Diff[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = 0; i < 4; ++i)
+         for (int j = 0; j < 4; ++j) Diff[i] += Dm[i][j] * dV[j];
+      H[RHO] = frho - 0.5 * Diff[0];
+      H[0] = f0 - 0.5 * Diff[1];
+      H[1] = f1 - 0.5 * Diff[2];
+      H[ENE] = fE - 0.5 * Diff[3];
+   }
+
    // claw.h:271-325 with the switch resolved at compile time
    template <int FLUX>
    DFLO_HD void numerical_flux (double nx, double ny, const double Wp[4], const double Wm[4], const double Ap[4],
@@ -327,6 +419,8 @@ namespace dflo
          kfvs_flux (nx, ny, Wp, Wm, H);
       else if (FLUX == FLUX_ROE)
          roe_flux (nx, ny, Wp, Wm, H);
+      else if (FLUX == FLUX_KEP)
+         kep_flux (nx, ny, Wp, Wm, Ap, Am, H);
       else
          hllc_flux (nx, ny, Wp, Wm, H);
    }
@@ -551,11 +645,14 @@ namespace dflo
       const double L[4] = {Wl[DIR], Wl[1 - DIR], Wl[RHO], Wl[ENE]};
       const double R[4] = {Wr[DIR], Wr[1 - DIR], Wr[RHO], Wr[ENE]};
       double G[4];
-      if (FLUX == FLUX_LXF)
+      if (flux_uses_averages (FLUX))
       {
          const double AL[4] = {Al[DIR], Al[1 - DIR], Al[RHO], Al[ENE]};
          const double AR[4] = {Ar[DIR], Ar[1 - DIR], Ar[RHO], Ar[ENE]};
-         lxf_flux_x (L, R, AL, AR, G);
+         if (FLUX == FLUX_LXF)
+            lxf_flux_x (L, R, AL, AR, G);
+         else
+            kep_flux (1.0, 0.0, L, R, AL, AR, G);
       }
       else if (FLUX == FLUX_SW)
          steger_warming_flux_x (L, R, G);
@@ -591,7 +688,7 @@ namespace dflo
       }
       P[DIR] *= sg;
       M[DIR] *= sg;
-      if (FLUX == FLUX_LXF)
+      if (flux_uses_averages (FLUX))
       {
 #pragma unroll
          for (int c = 0; c < 4; ++c)

@@ -194,7 +194,7 @@ namespace dflo
          };
          if (!sel ("mesh type", "ucd|gmsh") || !sel ("basis", "Qk|Pk") || !sel ("mapping", "q1|q2|cartesian")
              || !sel ("time stepping/time step type", "global|local") || !sel ("linear solver/output", "quiet|verbose")
-             || !sel ("linear solver/method", "gmres|direct|umfpack|rk3|mood") || !sel ("flux/flux", "lxf|sw|kfvs|roe|hllc")
+             || !sel ("linear solver/method", "gmres|direct|umfpack|rk3|mood") || !sel ("flux/flux", "lxf|sw|kfvs|roe|hllc|kep")
              || !sel ("flux/stab", "constant|mesh") || !sel ("limiter/shock indicator", "limiter|density|energy|u2")
              || !sel ("limiter/type", "none|TVB") || !sel ("output/format", "vtk|tecplot")
              || !sel ("initial condition/function", "none|rt|isenvort|vortsys"))
@@ -330,7 +330,7 @@ namespace dflo
          p.basis = basis == "Qk" ? DFLO_BASIS_QK : DFLO_BASIS_PK;
          p.degree = degree;
          p.flux_type = flux == "lxf" ? DFLO_FLUX_LXF : flux == "sw" ? DFLO_FLUX_SW : flux == "kfvs" ? DFLO_FLUX_KFVS
-                     : flux == "roe" ? DFLO_FLUX_ROE : DFLO_FLUX_HLLC;
+                     : flux == "roe" ? DFLO_FLUX_ROE : flux == "kep" ? DFLO_FLUX_KEP : DFLO_FLUX_HLLC;
          p.limiter_type = limiter_type == "TVB" ? DFLO_LIMITER_TVB : DFLO_LIMITER_NONE;
          p.char_lim = char_lim;
          p.pos_lim = pos_lim;

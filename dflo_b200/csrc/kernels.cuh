@@ -189,7 +189,7 @@ namespace dflo
       static constexpr int O_UOLD = O_W + (BASIS == BASIS_PK ? TC * 4 * NQ : 0);   // old_solution of the tile
       static constexpr int O_GEOM = O_UOLD + TC * D;                             // x0 y0 hx hy per tile cell
       static constexpr int O_AVG = O_GEOM + TC * 4;                              // cell averages, tile + halo (LxF only)
-      static constexpr int O_JOBS = O_AVG + (FLUX == FLUX_LXF ? (TC + NH) * 4 : 0);
+      static constexpr int O_JOBS = O_AVG + (flux_uses_averages (FLUX) ? (TC + NH) * 4 : 0);
       static constexpr int O_DT = O_JOBS + TC * 4 * 2;                           // FaceJob = 2 doubles
       static constexpr int SMEM_DOUBLES = O_DT + 2;
       // pipelined (persistent) form: barriers | tables | work arrays | old_solution | dt | 2 input stages
@@ -204,7 +204,7 @@ namespace dflo
       static constexpr int S_U = 0;                                  // offsets inside one input stage
       static constexpr int S_GEOM = S_U + (TC + NH) * D;
       static constexpr int S_AVG = S_GEOM + TC * 4;
-      static constexpr int S_JOBS = S_AVG + (FLUX == FLUX_LXF ? (TC + NH) * 4 : 0);
+      static constexpr int S_JOBS = S_AVG + (flux_uses_averages (FLUX) ? (TC + NH) * 4 : 0);
       static constexpr int S_TD = S_JOBS + TC * 4 * 2;
       static constexpr int STAGE_DOUBLES = S_TD + 4;
       static constexpr int PERSIST_SMEM_DOUBLES = P_STAGE + 2 * STAGE_DOUBLES;
@@ -297,7 +297,7 @@ namespace dflo
             {
                unsigned bytes = (unsigned) (ncb + nh) * cell_bytes + (unsigned) ncb * 32u + (unsigned) nj * 16u;
                if (need_old) bytes += (unsigned) ncb * cell_bytes;
-               if (FLUX == FLUX_LXF) bytes += (unsigned) (ncb + nh) * 32u;
+               if (flux_uses_averages (FLUX)) bytes += (unsigned) (ncb + nh) * 32u;
                mbar_init (sm, 1);
                mbar_expect_tx (sm, bytes);
             }
@@ -308,13 +308,13 @@ namespace dflo
                if (need_old) bulk_g2s (sUold, A.u_old + (size_t) c0 * D, (unsigned) ncb * cell_bytes, sm);
                bulk_g2s (sGeom, A.geom + (size_t) c0 * 4, (unsigned) ncb * 32u, sm);
                if (nj) bulk_g2s (sJobs, A.jobs + td.j0, (unsigned) nj * 16u, sm);
-               if (FLUX == FLUX_LXF) bulk_g2s (sAvg, A.avg + (size_t) c0 * 4, (unsigned) ncb * 32u, sm);
+               if (flux_uses_averages (FLUX)) bulk_g2s (sAvg, A.avg + (size_t) c0 * 4, (unsigned) ncb * 32u, sm);
             }
             else if (tid <= nh)
             {
                const int hc = A.halo_cells[h0 + tid - 1];
                bulk_g2s (su + (TC + tid - 1) * D, A.u + (size_t) hc * D, cell_bytes, sm);
-               if (FLUX == FLUX_LXF) bulk_g2s (sAvg + (TC + tid - 1) * 4, A.avg + (size_t) hc * 4, 32u, sm);
+               if (flux_uses_averages (FLUX)) bulk_g2s (sAvg + (TC + tid - 1) * 4, A.avg + (size_t) hc * 4, 32u, sm);
             }
             if (tid == THREADS - 1) v.sDt[0] = A.time[1];
             for (int i = tid; i < TAB; i += THREADS) tb[i] = A.tab[i];
@@ -326,7 +326,7 @@ namespace dflo
                for (int i = tid; i < ncb * D; i += THREADS) sUold[i] = A.u_old[(size_t) c0 * D + i];
             for (int i = tid; i < ncb * 4; i += THREADS) sGeom[i] = A.geom[(size_t) c0 * 4 + i];
             for (int i = tid; i < nj; i += THREADS) sJobs[i] = A.jobs[td.j0 + i];
-            if (FLUX == FLUX_LXF)
+            if (flux_uses_averages (FLUX))
             {
                for (int i = tid; i < ncb * 4; i += THREADS) sAvg[i] = A.avg[(size_t) c0 * 4 + i];
                for (int i = tid; i < nh * 4; i += THREADS) sAvg[TC * 4 + i] = A.avg[(size_t) A.halo_cells[h0 + i / 4] * 4 + i % 4];
@@ -404,7 +404,7 @@ namespace dflo
                double *ho = sH + ((sa * 4 + f) * N1 + q) * 4;
 #pragma unroll
                for (int c = 0; c < 4; ++c) Wo[c] = ho[c];
-               if (FLUX == FLUX_LXF) // the only flux that reads the cell averages (equation.h:357-359)
+               if (flux_uses_averages (FLUX)) // the only flux that reads the cell averages (equation.h:357-359)
                {
 #pragma unroll
                   for (int c = 0; c < 4; ++c) Ao[c] = sAvg[sa * 4 + c];
@@ -423,7 +423,7 @@ namespace dflo
                      trace (tb, su + job.slot_b * D, f ^ 1, qn, Wn);
                   else
                      trace (tb, A.u + (size_t) nb * D, f ^ 1, qn, Wn);
-                  if (FLUX == FLUX_LXF)
+                  if (flux_uses_averages (FLUX))
                   {
 #pragma unroll
                      for (int c = 0; c < 4; ++c) An[c] = job.slot_b >= 0 ? sAvg[job.slot_b * 4 + c] : A.avg[(size_t) nb * 4 + c];
@@ -438,7 +438,7 @@ namespace dflo
 #pragma unroll
                   for (int c = 0; c < 4; ++c) g[c] = A.bc_g[((size_t) bf * N1 + q) * 4 + c];
                   compute_wminus (kind, nx, ny, Wo, g, Wn);
-                  if (FLUX == FLUX_LXF)
+                  if (flux_uses_averages (FLUX))
                   {
                      if (A.compat_mpi) // src_mpi/assemble_explicit.cc:296-321
                         compute_wminus (kind, nx, ny, Ao, g, An);
@@ -673,20 +673,20 @@ namespace dflo
             if (lane == 0)
             {
                unsigned bytes = (unsigned) (td.ncb + td.nh) * cell_bytes + (unsigned) td.ncb * 32u + (unsigned) td.nj * 16u + 32u;
-               if (K::FLUX_ID == FLUX_LXF) bytes += (unsigned) (td.ncb + td.nh) * 32u;
+               if (flux_uses_averages (K::FLUX_ID)) bytes += (unsigned) (td.ncb + td.nh) * 32u;
                mbar_expect_tx (&bars[s], bytes);
                bulk_g2s (st + K::S_U, A.u + (size_t) td.c0 * K::D, (unsigned) td.ncb * cell_bytes, &bars[s]);
                bulk_g2s (st + K::S_GEOM, A.geom + (size_t) td.c0 * 4, (unsigned) td.ncb * 32u, &bars[s]);
                if (td.nj) bulk_g2s (st + K::S_JOBS, A.jobs + td.j0, (unsigned) td.nj * 16u, &bars[s]);
                bulk_g2s (st + K::S_TD, A.tiles + t, 32u, &bars[s]);
-               if (K::FLUX_ID == FLUX_LXF) bulk_g2s (st + K::S_AVG, A.avg + (size_t) td.c0 * 4, (unsigned) td.ncb * 32u, &bars[s]);
+               if (flux_uses_averages (K::FLUX_ID)) bulk_g2s (st + K::S_AVG, A.avg + (size_t) td.c0 * 4, (unsigned) td.ncb * 32u, &bars[s]);
             }
             __syncwarp ();
             for (int h = lane; h < td.nh; h += 32)
             {
                const int hc = A.halo_cells[td.h0 + h];
                bulk_g2s (st + K::S_U + (K::TC + h) * K::D, A.u + (size_t) hc * K::D, cell_bytes, &bars[s]);
-               if (K::FLUX_ID == FLUX_LXF) bulk_g2s (st + K::S_AVG + (K::TC + h) * 4, A.avg + (size_t) hc * 4, 32u, &bars[s]);
+               if (flux_uses_averages (K::FLUX_ID)) bulk_g2s (st + K::S_AVG + (K::TC + h) * 4, A.avg + (size_t) hc * 4, 32u, &bars[s]);
             }
             if (need_old)
             {

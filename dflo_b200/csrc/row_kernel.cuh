@@ -75,7 +75,7 @@ namespace dflo
       static constexpr int X_END_B = O_PART + TC * N1 * 4;
       static constexpr int O_GEOM = X_END_A > X_END_B ? X_END_A : X_END_B;   // x0 y0 hx hy of the tile cells
       static constexpr int O_AVG = O_GEOM + TC * 4;               // cell averages tile + halo (LxF only)
-      static constexpr int O_DESC = O_AVG + (FLUX == FLUX_LXF ? (TC + NH) * 4 : 0);
+      static constexpr int O_DESC = O_AVG + (flux_uses_averages (FLUX) ? (TC + NH) * 4 : 0);
       static constexpr int SMEM_DOUBLES = O_DESC + DESC_INTS / 2;
       static_assert (MAIN % 32 == 0, "whole warps");
       static_assert (THREADS >= TC + NH + 2, "one staging copy per thread");
@@ -214,7 +214,7 @@ namespace dflo
       L[3] = Wlo[3];
       R[2] = Whi[2];
       R[3] = Whi[3];
-      if (FLUX == FLUX_LXF)
+      if (flux_uses_averages (FLUX))
       {
          AL[0] = dir ? Alo[1] : Alo[0];
          AL[1] = dir ? Alo[0] : Alo[1];
@@ -261,7 +261,7 @@ namespace dflo
                while (ld_acquire_sys (F.my_flags + F.world + F.peer_rank[p]) < e) {}
          }
          unsigned bytes = (unsigned) (ncb + nh) * cell_bytes + (unsigned) ncb * 32u + (unsigned) (S::DESC_INTS * sizeof (int));
-         if (FLUX == FLUX_LXF) bytes += (unsigned) (ncb + nh) * 32u;
+         if (flux_uses_averages (FLUX)) bytes += (unsigned) (ncb + nh) * 32u;
          mbar_init (sm, 1);
          mbar_expect_tx (sm, bytes);
       }
@@ -271,7 +271,7 @@ namespace dflo
          const int cell = tid < ncb ? c0 + tid : gdesc[S::OFF_HALO + tid - ncb];
          const int slot = tid < ncb ? tid : TC + tid - ncb;
          bulk_g2s (su + slot * CS, A.u + (size_t) cell * D, cell_bytes, sm);
-         if (FLUX == FLUX_LXF) bulk_g2s (sAvg + slot * 4, A.avg + (size_t) cell * 4, 32u, sm);
+         if (flux_uses_averages (FLUX)) bulk_g2s (sAvg + slot * 4, A.avg + (size_t) cell * 4, 32u, sm);
       }
       else if (tid == S::THREADS - 1)
       {
@@ -374,7 +374,7 @@ namespace dflo
       {
          const int code = sdesc[S::OFF_NBHI + 2 * rs];
          double Wn[4], Ao[4], An[4], H[4];
-         if (FLUX == FLUX_LXF) load4 (sAvg + rs * 4, Ao);
+         if (flux_uses_averages (FLUX)) load4 (sAvg + rs * 4, Ao);
          if (code >= 0)
          {
             const int idx = code & 0xffff;
@@ -382,7 +382,7 @@ namespace dflo
                load_pt<TH> (sT, idx * N1 + rb, Wn);
             else
                load4 (sG + ((idx - TC) * N1 + rb) * 4, Wn);
-            if (FLUX == FLUX_LXF) load4 (sAvg + (idx < TC ? idx : (sdesc[S::OFF_GJOB + idx - TC] & 0xffff)) * 4, An);
+            if (flux_uses_averages (FLUX)) load4 (sAvg + (idx < TC ? idx : (sdesc[S::OFF_GJOB + idx - TC] & 0xffff)) * 4, An);
             if (A.dbg & 1)
             {
 #pragma unroll
@@ -400,7 +400,7 @@ namespace dflo
             double g[4];
             load4 (A.bc_g + ((size_t) bf * N1 + rb) * 4, g);
             compute_wminus (kind, 1.0, 0.0, WR, g, Wn);
-            if (FLUX == FLUX_LXF)
+            if (flux_uses_averages (FLUX))
             {
                if (A.compat_mpi)
                   compute_wminus (kind, 1.0, 0.0, Ao, g, An);
@@ -419,7 +419,7 @@ namespace dflo
       {
          const int code = sdesc[S::OFF_NBHI + 2 * cs + 1];
          double Wn[4], Ao[4], An[4], H[4];
-         if (FLUX == FLUX_LXF) load4 (sAvg + cs * 4, Ao);
+         if (flux_uses_averages (FLUX)) load4 (sAvg + cs * 4, Ao);
          if (code >= 0)
          {
             const int idx = code & 0xffff;
@@ -427,7 +427,7 @@ namespace dflo
                load_pt<TH> (sT, TC * N1 + col_pos<N1> (idx, ca), Wn);
             else
                load4 (sG + ((idx - TC) * N1 + ca) * 4, Wn);
-            if (FLUX == FLUX_LXF) load4 (sAvg + (idx < TC ? idx : (sdesc[S::OFF_GJOB + idx - TC] & 0xffff)) * 4, An);
+            if (flux_uses_averages (FLUX)) load4 (sAvg + (idx < TC ? idx : (sdesc[S::OFF_GJOB + idx - TC] & 0xffff)) * 4, An);
             if (A.dbg & 1)
             {
 #pragma unroll
@@ -444,7 +444,7 @@ namespace dflo
             double g[4];
             load4 (A.bc_g + ((size_t) bf * N1 + ca) * 4, g);
             compute_wminus (kind, 0.0, 1.0, WT, g, Wn);
-            if (FLUX == FLUX_LXF)
+            if (flux_uses_averages (FLUX))
             {
                if (A.compat_mpi)
                   compute_wminus (kind, 0.0, 1.0, Ao, g, An);
@@ -472,12 +472,12 @@ namespace dflo
             const int p = dir ? TC * N1 + col_pos<N1> (s, q) : s * N1 + q;
             double Wo[4], Wn[4], Ao[4], An[4], H[4];
             load_pt<TH> (sT, p, Wo);
-            if (FLUX == FLUX_LXF) load4 (sAvg + s * 4, Ao);
+            if (flux_uses_averages (FLUX)) load4 (sAvg + s * 4, Ao);
             if (nb >= 0)
             {
                const int qn = (w0 & ROWD_FLIP) ? N1 - 1 - q : q;
                row_trace<N1> (su + nb * CS, 2 * dir + 1, qn, Wn);
-               if (FLUX == FLUX_LXF) load4 (sAvg + nb * 4, An);
+               if (flux_uses_averages (FLUX)) load4 (sAvg + nb * 4, An);
             }
             else
             {
@@ -487,7 +487,7 @@ namespace dflo
                load4 (A.bc_g + ((size_t) bf * N1 + q) * 4, g);
                const double nx = dir ? 0.0 : -1.0, ny = dir ? -1.0 : 0.0;
                compute_wminus (kind, nx, ny, Wo, g, Wn);
-               if (FLUX == FLUX_LXF)
+               if (flux_uses_averages (FLUX))
                {
                   if (A.compat_mpi)
                      compute_wminus (kind, nx, ny, Ao, g, An);

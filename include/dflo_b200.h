@@ -48,8 +48,9 @@ enum
    DFLO_E_NO_DEVICE = -8       /* no CUDA device: the engine has no CPU fallback */
 };
 
-/* Parameters::Flux::FluxType, src/parameters.h:229 */
-enum { DFLO_FLUX_LXF = 0, DFLO_FLUX_SW = 1, DFLO_FLUX_KFVS = 2, DFLO_FLUX_ROE = 3, DFLO_FLUX_HLLC = 4 };
+/* Parameters::Flux::FluxType, src/parameters.h:229; kep (kinetic-energy preserving, entropy stable) exists in the
+ * MPI tree only: src_mpi/parameters.cc:150-180, src_mpi/equation.h:842-921 */
+enum { DFLO_FLUX_LXF = 0, DFLO_FLUX_SW = 1, DFLO_FLUX_KFVS = 2, DFLO_FLUX_ROE = 3, DFLO_FLUX_HLLC = 4, DFLO_FLUX_KEP = 5 };
 /* EulerEquations::BoundaryKind, src/equation.h:862-869; periodic from src_mpi/equation.h */
 enum { DFLO_BC_INFLOW = 0, DFLO_BC_OUTFLOW = 1, DFLO_BC_SLIP = 2, DFLO_BC_PRESSURE = 3, DFLO_BC_FARFIELD = 4, DFLO_BC_PERIODIC = 5 };
 /* Parameters::AllParameters::BasisType, src/parameters.h:390 */

@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-FLUX = {"lxf": 0, "sw": 1, "kfvs": 2, "roe": 3, "hllc": 4}          # src/parameters.h:229
+FLUX = {"lxf": 0, "sw": 1, "kfvs": 2, "roe": 3, "hllc": 4, "kep": 5}   # src/parameters.h:229; kep: src_mpi/parameters.cc:179
 BC = {"inflow": 0, "outflow": 1, "slip": 2, "pressure": 3, "farfield": 4, "periodic": 5}
 QK, PK = 0, 1
 

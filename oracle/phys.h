@@ -18,10 +18,14 @@
 extern "C" {
 #endif
 
-enum { PHYS_FLUX_LXF = 0, PHYS_FLUX_SW = 1, PHYS_FLUX_KFVS = 2, PHYS_FLUX_ROE = 3, PHYS_FLUX_HLLC = 4 };
+enum { PHYS_FLUX_LXF = 0, PHYS_FLUX_SW = 1, PHYS_FLUX_KFVS = 2, PHYS_FLUX_ROE = 3, PHYS_FLUX_HLLC = 4,
+       PHYS_FLUX_KEP = 5 /* src_mpi only: src_mpi/parameters.cc:150-180, src_mpi/equation.h:842-921 */ };
 enum { PHYS_BC_INFLOW = 0, PHYS_BC_OUTFLOW = 1, PHYS_BC_SLIP = 2, PHYS_BC_PRESSURE = 3, PHYS_BC_FARFIELD = 4 };
 
 const char *phys_impl_name (void);
+/* restated kep_flux of the MPI tree (phys_kep_restated.c), used by both implementations: src/equation.h has none */
+void phys_kep_flux_restated (const double n[2], const double Wl[4], const double Wr[4], const double Al[4],
+                             const double Ar[4], double out[4]);
 
 /* claw.h:271-325 numerical_normal_flux -> equation.h lxf/sw/kfvs/roe/hllc */
 void phys_numerical_flux (int flux_type, const double n[2], const double Wp[4], const double Wm[4],

@@ -60,6 +60,7 @@ void phys_numerical_flux (int flux_type, const double n[2], const double Wp[4], 
       case PHYS_FLUX_KFVS: EE::kfvs_flux (normal, wp, wm, f); break;
       case PHYS_FLUX_ROE: EE::roe_flux (normal, wp, wm, f); break;
       case PHYS_FLUX_HLLC: EE::hllc_flux (normal, wp, wm, f); break;
+      case PHYS_FLUX_KEP: phys_kep_flux_restated (n, Wp, Wm, Ap, Am, out); break; // src_mpi only, see phys_kep_restated.c
       default: assert (false);
    }
 }

@@ -335,6 +335,7 @@ void phys_numerical_flux (int flux_type, const double n[2], const double Wp[4], 
       case PHYS_FLUX_KFVS: kfvs (n, Wp, Wm, out); break;
       case PHYS_FLUX_ROE: roe (n, Wp, Wm, out); break;
       case PHYS_FLUX_HLLC: hllc (n, Wp, Wm, out); break;
+      case PHYS_FLUX_KEP: phys_kep_flux_restated (n, Wp, Wm, Ap, Am, out); break;
       default: out[0] = out[1] = out[2] = out[3] = NAN;
    }
 }

@@ -1,7 +1,7 @@
 """Case lists shared by the CPU-emulation tier and the GPU tier (same inputs, same tolerances)."""
 from helpers import (DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, ic_dmr, ic_pulse, ic_smooth, ic_sod, ic_step, ic_vortex)
 
-ALL_FLUXES = ["lxf", "sw", "kfvs", "roe", "hllc"]
+ALL_FLUXES = ["lxf", "sw", "kfvs", "roe", "hllc", "kep"]   # kep: src_mpi only
 BASES = [("Qk", 0), ("Qk", 1), ("Qk", 2), ("Qk", 3), ("Qk", 4), ("Pk", 1), ("Pk", 2), ("Pk", 3)]
 
 # (id, mesh, bc, ic, params, n_steps): the five BASELINE configurations at oracle-friendly sizes

@@ -208,7 +208,8 @@ void dflo_emu_numerical_flux (int flux, const double n[2], const double Wp[4], c
       case 1: dflo::numerical_flux<1> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
       case 2: dflo::numerical_flux<2> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
       case 3: dflo::numerical_flux<3> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
-      default: dflo::numerical_flux<4> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
+      case 4: dflo::numerical_flux<4> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
+      default: dflo::numerical_flux<5> (n[0], n[1], Wp, Wm, Ap, Am, H); break;
    }
 }
 // flux along +e_dir of a face whose integrating ("plus") cell is the low-side one (plus_low) or the high-side one
@@ -224,7 +225,8 @@ void dflo_emu_face_flux_axis (int flux, int dir, int plus_low, const double Wl[4
       case 1: DFLO_AX (1) break;
       case 2: DFLO_AX (2) break;
       case 3: DFLO_AX (3) break;
-      default: DFLO_AX (4) break;
+      case 4: DFLO_AX (4) break;
+      default: DFLO_AX (5) break;
    }
 #undef DFLO_AX
 }

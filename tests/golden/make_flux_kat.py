@@ -64,9 +64,22 @@ def main():
     tochar = np.array([P.to_char(eig[i, 1], WR[i]) for i in range(n)])
     tocon = np.array([P.to_con(eig[i, 0], WR[i]) for i in range(n)])
     scal = np.array([[P.pressure(w), P.sound_speed(w), P.max_eigenvalue(w)] for w in WL])
+    # kep_flux exists only in the MPI tree: its header src_mpi/equation.h, compiled unmodified into a
+    # library of its own (oracle/_ref/libphys_reference_mpi.so, oracle/Makefile `ref`)
+    import ctypes
+    M = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "libphys_reference_mpi.so"))
+    M.phys_mpi_impl_name.restype = ctypes.c_char_p
+    assert M.phys_mpi_impl_name().decode().startswith("reference:src_mpi")
+    dp = ctypes.POINTER(ctypes.c_double)
+    flux_kep = np.zeros((n, 4))
+    for i in range(n):
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (N[i], WL[i], WR[i], AL[i], AR[i])]
+        o = np.zeros(4)
+        M.phys_mpi_kep_flux(*[x.ctypes.data_as(dp) for x in a], o.ctypes.data_as(dp))
+        flux_kep[i] = o
     out = os.path.join(HERE, "flux_kat.npz")
     np.savez_compressed(out, WL=WL, WR=WR, AL=AL, AR=AR, N=N, G=G, flux=flux, fmat=fmat, wminus=wminus, eig=eig,
-                        tochar=tochar, tocon=tocon, scal=scal)
+                        tochar=tochar, tocon=tocon, scal=scal, flux_kep=flux_kep)
     print("wrote", out, os.path.getsize(out), "bytes;", P.name)
 
 
