@@ -73,10 +73,12 @@ def initial_dofs(nx, ny, x0, x1, y0, y1, k):
     return np.ascontiguousarray(u).reshape(-1)
 
 
-def sample_clocks(stop, out):
+def sample_clocks(stop, out, ready=None):
     """SM clock + throttle reasons while the timed region runs (B200_PROFILING.md clocks line).  NVML is
-    polled every 2 ms (the timed region of this workload lasts tens of milliseconds, too short for
-    nvidia-smi's loop mode); nvidia-smi -lms is the fallback when the NVML binding is missing."""
+    polled back to back (the timed region of this workload lasts milliseconds, too short for
+    nvidia-smi's loop mode); `ready` is set once NVML is initialised so that the caller starts the
+    timed region only when the sampler is live.  nvidia-smi -lms is the fallback when the NVML binding
+    is missing."""
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     try:
         import pynvml
@@ -84,6 +86,9 @@ def sample_clocks(stop, out):
         h = pynvml.nvmlDeviceGetHandleByIndex(dev)
         mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
         names = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        if ready is not None:
+            ready.set()
         while not stop.is_set():
             sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
             try:
@@ -91,22 +96,26 @@ def sample_clocks(stop, out):
             except Exception:
                 r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             out.append("%d, %d, %s" % (sm, mx, ", ".join("Active" if r & bit else "Not Active" for _, bit in names)))
-            time.sleep(0.002)
+            time.sleep(0.0002)
         return
     except Exception:
         pass
     q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     try:
-        p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", str(dev), "-lms", "100"],
+        p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", str(dev), "-lms", "20"],
                              stdout=subprocess.PIPE, text=True)
     except Exception:
+        if ready is not None:
+            ready.set()
         return
     while not stop.is_set():
         line = p.stdout.readline()
         if not line:
             break
         out.append(line.strip())
+        if ready is not None:
+            ready.set()
     p.terminate()
 
 
@@ -307,10 +316,12 @@ def main():
     t = 0.0
     for _ in range(args.warmup):
         t, _ = timed_step(t)
-    clk_lines, stop = [], threading.Event()
-    th = threading.Thread(target=sample_clocks, args=(stop, clk_lines), daemon=True)
+    clk_lines, stop, clk_ready = [], threading.Event(), threading.Event()
+    th = threading.Thread(target=sample_clocks, args=(stop, clk_lines, clk_ready), daemon=True)
     if rank == 0:
         th.start()
+        clk_ready.wait(10.0)
+        del clk_lines[:]          # keep only samples taken inside the timed region
     barrier()
     launches0 = eng.launch_count()
     wall0 = time.perf_counter()
@@ -320,12 +331,12 @@ def main():
         ms_total += ms
     barrier()
     wall = time.perf_counter() - wall0
+    stop.set()
     launches = eng.launch_count() - launches0
     # back-to-back (no flush, one advance call, one graph launch per step): launch-overhead view
     barrier()
     tb, _ = eng.advance(args.steps, elapsed=t)
     ms_b2b = eng.last_advance_ms()
-    stop.set()
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     e2e_steps = max(3, min(args.steps, 20))
