@@ -17,7 +17,7 @@ MAX_BOUNDARIES = 10
 FLUX = {"lxf": 0, "sw": 1, "kfvs": 2, "roe": 3, "hllc": 4, "kep": 5}
 BC = {"inflow": 0, "outflow": 1, "slip": 2, "pressure": 3, "farfield": 4, "periodic": 5}
 BASIS = {"Qk": 0, "Pk": 1}
-LIMITER = {"none": 0, "TVB": 1}
+LIMITER = {"none": 0, "TVB": 1, "minmax": 2}   # minmax: src_mpi/parameters.h:235
 COMPAT = {"src": 0, "mpi": 1}
 FACE_OWNER, FACE_PERIODIC, FACE_FLIP = 1, 2, 4
 

@@ -320,7 +320,7 @@ namespace dflo
 #define DFLO_LIM(B, N)                                                                          \
    do                                                                                           \
    {                                                                                            \
-      if (bk.limiter_block_form ())                                                             \
+      if (bk.limiter_block_form () && a.tvb != 2)                                               \
          bk.template launch<LimiterKernel<B, N>> (LimiterKernel<B, N>::grid (a.n_compute), a);  \
       else                                                                                      \
          bk.template launch<LimiterCellKernel<B, N>> (LimiterCellKernel<B, N>::grid (a.n_compute), a); \
@@ -412,7 +412,9 @@ namespace dflo
       // the stage kernel and the exchange (no limiter)
       bool fused_halo () { return !lm.peers.empty () && !tvb () && !pos () && bk.use_row_kernel (tab.basis, tab.n1) && bk.p2p_fused_ok (); }
       int D () const { return tab.D; }
-      bool tvb () const { return prm.limiter_type == DFLO_LIMITER_TVB && tab.k > 0; }
+      // a slope limiter that reads the neighbours' new means runs after the stage kernel: TVB, or the
+      // minmax limiter of the MPI tree (src_mpi/limiter.cc:36-70)
+      bool tvb () const { return (prm.limiter_type == DFLO_LIMITER_TVB || prm.limiter_type == DFLO_LIMITER_MINMAX) && tab.k > 0; }
       bool pos () const { return prm.pos_lim && tab.k > 0; }
       bool kxrcf () const { return tvb () && prm.shock_indicator != DFLO_INDICATOR_LIMITER; }
 
@@ -423,6 +425,9 @@ namespace dflo
          if (!build_tables (p.basis, p.degree, tab)) return fail (DFLO_E_UNSUPPORTED, "degree out of range (Qk 0..4, Pk 0..3)");
          if (p.flux_type < 0 || p.flux_type > 5) return fail (DFLO_E_INVALID, "unknown flux");
          if (p.shock_indicator < 0 || p.shock_indicator > 2) return fail (DFLO_E_INVALID, "unknown shock indicator");
+         if (p.limiter_type < DFLO_LIMITER_NONE || p.limiter_type > DFLO_LIMITER_MINMAX) return fail (DFLO_E_INVALID, "unknown limiter type");
+         if (p.limiter_type == DFLO_LIMITER_MINMAX && p.basis != DFLO_BASIS_QK) // src_mpi/parameters.cc:610-611
+            return fail (DFLO_E_UNSUPPORTED, "minmax limiter is implemented only for Qk");
          if (mesh.n_cells <= 0) return fail (DFLO_E_INVALID, "empty mesh");
          for (int b = 0; b < mesh.n_boundary_faces; ++b)
             if (mesh.bface_id[b] < 0 || mesh.bface_id[b] >= DFLO_MAX_BOUNDARIES) return fail (DFLO_E_INVALID, "boundary id out of range");
@@ -878,7 +883,7 @@ namespace dflo
          a.flags_out = d_flags;
          a.err = d_err;
          a.n_compute = lm.n_owned;
-         a.tvb = tvb ();
+         a.tvb = tvb () ? (prm.limiter_type == DFLO_LIMITER_MINMAX ? 2 : 1) : 0;
          a.char_lim = prm.char_lim;
          a.pos_lim = pos ();
          a.cam = prm.conserve_angular_momentum;

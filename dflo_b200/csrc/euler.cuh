@@ -119,6 +119,16 @@ namespace dflo
       G[ENE] = -W[1];
    }
 
+   // src_mpi/equation.h:1189-1202: forcing vector of an external force f = (f_x, f_y); the hard-wired
+   // forcing of src/ above is the case f = (0,-1)
+   DFLO_HD void forcing_ext (const double W[4], double fx, double fy, double G[4])
+   {
+      G[0] = W[RHO] * fx;
+      G[1] = W[RHO] * fy;
+      G[RHO] = 0.0;
+      G[ENE] = W[0] * fx + W[1] * fy;
+   }
+
    // |v.n| + c of a cell average, equation.h:119-137
    DFLO_HD double max_eigenvalue_normal (const double A[4], double nx, double ny)
    {
@@ -828,6 +838,41 @@ namespace dflo
       m.Ry[1][0] = u;        m.Ry[1][1] = 1;   m.Ry[1][2] = u;         m.Ry[1][3] = u;
       m.Ry[2][0] = v;        m.Ry[2][1] = 0;   m.Ry[2][2] = v + c;     m.Ry[2][3] = v - c;
       m.Ry[3][0] = 0.5 * q2; m.Ry[3][1] = u;   m.Ry[3][2] = h + c * v; m.Ry[3][3] = h - c * v;
+   }
+
+   // src_mpi/equation.h:299-335: eigenvector matrices along the streamline direction (kx,ky), the
+   // projection of the minmax limiter (src_mpi/limiter.cc:450).  The reference obtains (kx,ky) as
+   // (cos,sin)(atan2(v,u)); here it is the normalised velocity, (1,0) for a gas at rest -- the same
+   // direction to round-off without the fp64 trigonometric slow paths.
+   struct EigenStream
+   {
+      double R[4][4], L[4][4];
+   };
+   DFLO_HD void compute_eigen_stream (const double W[4], EigenStream &m)
+   {
+      const double g1 = GM1;
+      const double rho = W[RHO], E = W[ENE];
+      const double u = W[0] / rho, v = W[1] / rho;
+      const double q2 = u * u + v * v;
+      const double p = g1 * (E - 0.5 * rho * q2);
+      const double c2 = GAMMA * p / rho;
+      const double c = sqrt (c2);
+      const double beta = 0.5 / c2;
+      const double phi2 = 0.5 * g1 * q2;
+      const double h = c2 / g1 + 0.5 * q2;
+      const double q = sqrt (q2);
+      const double kx = (q > 0.0) ? u / q : 1.0, ky = (q > 0.0) ? v / q : 0.0;
+      const double uk = u * kx + v * ky;
+
+      m.R[0][0] = 1;        m.R[0][1] = 0;               m.R[0][2] = 1;          m.R[0][3] = 1;
+      m.R[1][0] = u;        m.R[1][1] = ky;              m.R[1][2] = u + kx * c; m.R[1][3] = u - kx * c;
+      m.R[2][0] = v;        m.R[2][1] = -kx;             m.R[2][2] = v + ky * c; m.R[2][3] = v - ky * c;
+      m.R[3][0] = 0.5 * q2; m.R[3][1] = ky * u - kx * v; m.R[3][2] = h + c * uk; m.R[3][3] = h - c * uk;
+
+      m.L[0][0] = 1 - phi2 / c2;          m.L[0][1] = g1 * u / c2;               m.L[0][2] = g1 * v / c2;               m.L[0][3] = -g1 / c2;
+      m.L[1][0] = -(ky * u - kx * v);     m.L[1][1] = ky;                        m.L[1][2] = -kx;                       m.L[1][3] = 0;
+      m.L[2][0] = beta * (phi2 - c * uk); m.L[2][1] = beta * (kx * c - g1 * u);  m.L[2][2] = beta * (ky * c - g1 * v);  m.L[2][3] = beta * g1;
+      m.L[3][0] = beta * (phi2 + c * uk); m.L[3][1] = -beta * (kx * c + g1 * u); m.L[3][2] = -beta * (ky * c + g1 * v); m.L[3][3] = beta * g1;
    }
 
    // equation.h:270-285: W (conserved order) -> characteristic (result in matrix row order)

@@ -196,7 +196,7 @@ namespace dflo
              || !sel ("time stepping/time step type", "global|local") || !sel ("linear solver/output", "quiet|verbose")
              || !sel ("linear solver/method", "gmres|direct|umfpack|rk3|mood") || !sel ("flux/flux", "lxf|sw|kfvs|roe|hllc|kep")
              || !sel ("flux/stab", "constant|mesh") || !sel ("limiter/shock indicator", "limiter|density|energy|u2")
-             || !sel ("limiter/type", "none|TVB") || !sel ("output/format", "vtk|tecplot")
+             || !sel ("limiter/type", "none|TVB|minmax") || !sel ("output/format", "vtk|tecplot")
              || !sel ("initial condition/function", "none|rt|isenvort|vortsys"))
             return false;
          mesh_type = get ("mesh type");
@@ -281,6 +281,11 @@ namespace dflo
             err = "TVB limiter works on cartesian grids only";
             return false;
          }
+         if (limiter_type == "minmax" && basis != "Qk") // src_mpi/parameters.cc:610-611
+         {
+            err = "minmax limiter is implemented only for Qk";
+            return false;
+         }
          if (basis == "Pk" && mapping != "cartesian")
          {
             err = "Pk basis can only be used with Cartesian grids";
@@ -331,7 +336,7 @@ namespace dflo
          p.degree = degree;
          p.flux_type = flux == "lxf" ? DFLO_FLUX_LXF : flux == "sw" ? DFLO_FLUX_SW : flux == "kfvs" ? DFLO_FLUX_KFVS
                      : flux == "roe" ? DFLO_FLUX_ROE : flux == "kep" ? DFLO_FLUX_KEP : DFLO_FLUX_HLLC;
-         p.limiter_type = limiter_type == "TVB" ? DFLO_LIMITER_TVB : DFLO_LIMITER_NONE;
+         p.limiter_type = limiter_type == "TVB" ? DFLO_LIMITER_TVB : limiter_type == "minmax" ? DFLO_LIMITER_MINMAX : DFLO_LIMITER_NONE;
          p.char_lim = char_lim;
          p.pos_lim = pos_lim;
          p.conserve_angular_momentum = conserve_angular_momentum;

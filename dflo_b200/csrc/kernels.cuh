@@ -27,8 +27,10 @@
 
 #if defined(__CUDACC__)
 #define DFLO_DEV __device__ __forceinline__
+#define DFLO_DEV_NOINLINE __device__ __noinline__
 #else
 #define DFLO_DEV inline
+#define DFLO_DEV_NOINLINE inline
 #endif
 
 namespace dflo
@@ -775,7 +777,7 @@ namespace dflo
       int *flags_out;         // [n_local] bit0 TVB rewrote, bit1 theta1<1, bit2 theta2<1
       unsigned int *err;      // device error word
       int n_compute;
-      int tvb, char_lim, pos_lim, cam;
+      int tvb, char_lim, pos_lim, cam; // tvb: 0 none, 1 TVB, 2 minmax (Qk, LimiterCellKernel only)
       double M, beta;
    };
 
@@ -1209,6 +1211,120 @@ namespace dflo
          }
       }
 
+      // apply_limiter_minmax_Qk of the MPI tree (src_mpi/limiter.cc:400-553) on one cell: slopes
+      // scaled so that the linear reconstruction at the four face centres stays inside the range
+      // of the neighbour means.  As in the reference, without characteristic limiting the range
+      // starts from 0 (zero-initialised avg_min / avg_max, :438), and only true interior faces
+      // bring neighbours (!at_boundary, :454: periodic partners do not).  The mean gradient is
+      // taken with the Gauss(k+1) rule of the TVB limiter instead of the reference's QGauss(nq)
+      // (:407-413) -- both are exact for the integrand.  Returns 1 if the cell was rewritten.  Not
+      // inlined, and everything passed by value: the register allocation and the stack frame of the
+      // TVB / positivity path stay what they were.
+      struct MinmaxIn
+      {
+         const double *avg, *geom, *tab;
+         const int *nbr;
+         const unsigned char *fflags;
+         double M;
+         int char_lim;
+      };
+      static DFLO_DEV_NOINLINE int minmax_cell (const MinmaxIn A, int cell, double *uc)
+      {
+         const double *tb = A.tab;
+         const double hx = A.geom[(size_t) cell * 4 + 2], hy = A.geom[(size_t) cell * 4 + 3];
+         const double dx = sqrt (hx * hx + hy * hy) / 1.4142135623730951;
+         const double Mdx2 = A.M * dx * dx;
+         double av[4], avc[4], amin[4] = {0.0, 0.0, 0.0, 0.0}, amax[4] = {0.0, 0.0, 0.0, 0.0}, Dx[4], Dy[4];
+#pragma unroll
+         for (int c = 0; c < 4; ++c) avc[c] = av[c] = A.avg[(size_t) cell * 4 + c];
+         EigenStream es;
+         if (A.char_lim)
+         {
+            compute_eigen_stream (av, es);
+            transform_to_char (es.L, avc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) amin[c] = amax[c] = avc[c];
+         }
+         for (int f = 0; f < 4; ++f)
+         {
+            const int nb = A.nbr[(size_t) cell * 4 + f];
+            if (nb < 0 || (A.fflags[(size_t) cell * 4 + f] & FACE_PERIODIC)) continue;
+            double an[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) an[c] = A.avg[(size_t) nb * 4 + c];
+            if (A.char_lim) transform_to_char (es.L, an);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+               amin[c] = std_min (amin[c], an[c]);
+               amax[c] = std_max (amax[c], an[c]);
+            }
+         }
+         const double *gw = LK::t_gw (tb), *gd = LK::t_gdiff (tb);
+#pragma unroll
+         for (int c = 0; c < 4; ++c)
+         {
+            double sx = 0.0, sy = 0.0;
+            for (int b = 0; b < N1; ++b)
+               for (int a = 0; a < N1; ++a)
+               {
+                  const double u = uc[c * NS + a + N1 * b];
+                  sx += (gd[a] * gw[b]) * u;
+                  sy += (gw[a] * gd[b]) * u;
+               }
+            Dx[c] = sx / hx;
+            Dy[c] = sy / hy;
+         }
+         if (A.char_lim)
+         {
+            transform_to_char (es.L, Dx);
+            transform_to_char (es.L, Dy);
+         }
+         double theta[4] = {1.0, 1.0, 1.0, 1.0}, change = 0.0;
+#pragma unroll
+         for (int c = 0; c < 4; ++c)
+         {
+            const double dumin = amin[c] - avc[c], dumax = amax[c] - avc[c];
+            if (dumax - dumin > Mdx2)
+               for (int f = 0; f < 4; ++f)
+               {
+                  // face centre - cell centre (src_mpi/limiter.cc:500)
+                  const double dr0 = (f == 0) ? -0.5 * hx : (f == 1) ? 0.5 * hx : 0.0;
+                  const double dr1 = (f == 2) ? -0.5 * hy : (f == 3) ? 0.5 * hy : 0.0;
+                  const double du = dr0 * Dx[c] + dr1 * Dy[c];
+                  if (du > 0.0)
+                     theta[c] = std_min (theta[c], dumax / du);
+                  else if (du < 0.0)
+                     theta[c] = std_min (theta[c], dumin / du);
+               }
+            change += theta[c];
+         }
+         change /= 4;
+         if (!(change < 0.99)) return 0;
+#pragma unroll
+         for (int c = 0; c < 4; ++c)
+         {
+            Dx[c] *= theta[c];
+            Dy[c] *= theta[c];
+         }
+         if (A.char_lim)
+         {
+            transform_to_con (es.R, Dx);
+            transform_to_con (es.R, Dy);
+         }
+         const double *gx = LK::t_gx (tb);
+         const double x0 = A.geom[(size_t) cell * 4 + 0], y0 = A.geom[(size_t) cell * 4 + 1];
+         for (int b = 0; b < N1; ++b)
+            for (int a = 0; a < N1; ++a)
+            {
+               const double dr0 = (x0 + gx[a] * hx) - (x0 + 0.5 * hx);
+               const double dr1 = (y0 + gx[b] * hy) - (y0 + 0.5 * hy);
+#pragma unroll
+               for (int c = 0; c < 4; ++c) uc[c * NS + a + N1 * b] = av[c] + dr0 * Dx[c] + dr1 * Dy[c];
+            }
+         return 1;
+      }
+
       // all limiter steps of one cell on its DoFs uc (in place); returns true if they changed
       static DFLO_DEV bool cell_work (const Args &A, int cell, double *uc)
       {
@@ -1223,7 +1339,12 @@ namespace dflo
          double lo[4] = {1.0e300, 1.0e300, 1.0e300, 1.0e300}, hi[4] = {-1.0e300, -1.0e300, -1.0e300, -1.0e300};
          bool have_bounds = false;
 
-         if (A.tvb && (!A.shock || A.shock[cell] > 1.0)) // limiter.cc:263, 406
+         if (BASIS == BASIS_QK && A.tvb == 2 && (!A.shock || A.shock[cell] > 1.0)) // src_mpi/limiter.cc:437
+         {
+            const typename LimiterCellKernel::MinmaxIn in = {A.avg, A.geom, A.tab, A.nbr, A.fflags, A.M, A.char_lim};
+            flag |= minmax_cell (in, cell, uc);
+         }
+         if (A.tvb == 1 && (!A.shock || A.shock[cell] > 1.0)) // limiter.cc:263, 406
          {
             const double hx = A.geom[(size_t) cell * 4 + 2], hy = A.geom[(size_t) cell * 4 + 3];
             const double dx = sqrt (hx * hx + hy * hy) / 1.4142135623730951; // diameter / sqrt(dim)

@@ -55,8 +55,9 @@ enum { DFLO_FLUX_LXF = 0, DFLO_FLUX_SW = 1, DFLO_FLUX_KFVS = 2, DFLO_FLUX_ROE = 
 enum { DFLO_BC_INFLOW = 0, DFLO_BC_OUTFLOW = 1, DFLO_BC_SLIP = 2, DFLO_BC_PRESSURE = 3, DFLO_BC_FARFIELD = 4, DFLO_BC_PERIODIC = 5 };
 /* Parameters::AllParameters::BasisType, src/parameters.h:390 */
 enum { DFLO_BASIS_QK = 0, DFLO_BASIS_PK = 1 };
-/* Parameters::Limiter::LimiterType, src/parameters.h:243 */
-enum { DFLO_LIMITER_NONE = 0, DFLO_LIMITER_TVB = 1 };
+/* Parameters::Limiter::LimiterType, src/parameters.h:243; minmax (Barth-Jespersen type, Qk only) exists in the
+ * MPI tree only: src_mpi/parameters.h:235, src_mpi/limiter.cc:400-553 */
+enum { DFLO_LIMITER_NONE = 0, DFLO_LIMITER_TVB = 1, DFLO_LIMITER_MINMAX = 2 };
 /* Parameters::Limiter::ShockIndType, src/parameters.h: which cells the TVB limiter may touch.
  * limiter: every cell (src/indicator.cc:18-22); density / energy: the KXRCF indicator of that variable
  * (src/indicator.cc:50-198), cells with indicator > 1 (src/limiter.cc:263, 406) */

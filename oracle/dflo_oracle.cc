@@ -249,6 +249,7 @@ struct oracle_ctx
    UnitValues face[4];      // QGauss<1>(k+1) projected to face f (A2)
    UnitValues posx, posy;   // positivity.cc:43-47
    UnitValues support;      // Qk unit support points (limiter.cc:234)
+   UnitValues mmgrad;       // QGauss<2>(nq) of the minmax limiter (src_mpi/limiter.cc:407-413)
    std::vector<Cell> cells;
    std::vector<char> shared;    // [nc][4] face shared through vertices (cell->neighbor() exists)
    int n_bfaces;
@@ -897,8 +898,125 @@ namespace
       }
    }
 
-   void apply_limiter (oracle_ctx &o) // limiter.cc:35-65
+   //---------------------------------------------------------------------------------------------
+   // src_mpi/limiter.cc:400-553, the Barth-Jespersen type "minmax" limiter of the MPI tree (Qk only,
+   // src_mpi/parameters.cc:610-611).  Restated as written, including two properties a reader might
+   // not expect: (1) without characteristic limiting avg_min / avg_max start from the
+   // zero-initialised Vector<double>(n_components) (limiter.cc:438, 446-451 assign them only under
+   // char_lim), so the bounds always contain 0; (2) only faces with !cell->at_boundary() contribute
+   // neighbours (:453-454), i.e. periodic partners do not.  The mean gradient uses QGauss(nq) with
+   // nq = k/2+1 (k even) or (k+1)/2+1 (k odd) (:407-412).
+   //---------------------------------------------------------------------------------------------
+   void apply_limiter_minmax_Qk (oracle_ctx &o)
    {
+      if (o.fe.k == 0) return;
+      const int D = o.D (), ns = o.fe.ns, nq = o.mmgrad.nq;
+      std::vector<double> grad (nq * NC * 2);
+      for (size_t c = 0; c < o.cells.size (); ++c)
+      {
+         if (!(o.shock_indicator[c] > 1.0)) continue;                               // :437
+         const Cell &cl = o.cells[c];
+         double *u = &o.current[c * D];
+         const double dx = o.diameter (cl) / std::sqrt (2.0);
+         const double Mdx2 = o.prm.M * dx * dx;
+         const double h[2] = {cl.hx, cl.hy};
+         double avg_min[NC] = {0, 0, 0, 0}, avg_max[NC] = {0, 0, 0, 0}, avg_cell[NC], avg_nbr[NC];
+         for (int i = 0; i < NC; ++i) avg_cell[i] = o.cell_average[c * NC + i];
+         double Rx[16], Lx[16];
+         if (o.prm.char_lim)                                                        // :446-452
+         {
+            // compute_eigen_matrix (W, R, L): the streamline-direction matrices, src_mpi/equation.h:299-335
+            phys_eigen_stream_restated (&o.cell_average[c * NC], Rx, Lx);
+            phys_to_char (Lx, avg_cell);
+            for (int i = 0; i < NC; ++i) avg_min[i] = avg_max[i] = avg_cell[i];
+         }
+         for (int f = 0; f < 4; ++f)
+            if (o.shared[c * 4 + f])                                                // :454
+            {
+               for (int i = 0; i < NC; ++i) avg_nbr[i] = o.cell_average[cl.nbr[f] * NC + i];
+               if (o.prm.char_lim) phys_to_char (Lx, avg_nbr);
+               for (int i = 0; i < NC; ++i)
+               {
+                  avg_min[i] = std::min (avg_min[i], avg_nbr[i]);
+                  avg_max[i] = std::max (avg_max[i], avg_nbr[i]);
+               }
+            }
+         // get_function_gradients at QGauss(nq), :473-490
+         for (int q = 0; q < nq; ++q)
+         {
+            for (int k = 0; k < NC * 2; ++k) grad[q * NC * 2 + k] = 0.0;
+            for (int i = 0; i < D; ++i)
+               for (int d = 0; d < 2; ++d)
+                  grad[(q * NC + i / ns) * 2 + d] += u[i] * (o.mmgrad.dphi[((i % ns) * nq + q) * 2 + d] / h[d]);
+         }
+         double dumin[NC], dumax[NC], Dx[NC], Dy[NC];
+         for (int i = 0; i < NC; ++i)
+         {
+            dumin[i] = avg_min[i] - avg_cell[i];
+            dumax[i] = avg_max[i] - avg_cell[i];
+            double avg_grad[2] = {0, 0};
+            for (int q = 0; q < nq; ++q)
+               for (int d = 0; d < 2; ++d) avg_grad[d] += grad[(q * NC + i) * 2 + d] * (o.mmgrad.w[q] * cl.hx * cl.hy);
+            for (int d = 0; d < 2; ++d) avg_grad[d] /= (cl.hx * cl.hy);
+            Dx[i] = avg_grad[0];
+            Dy[i] = avg_grad[1];
+         }
+         if (o.prm.char_lim)                                                        // :491-495
+         {
+            phys_to_char (Lx, Dx);
+            phys_to_char (Lx, Dy);
+         }
+         double theta[NC] = {1.0, 1.0, 1.0, 1.0};
+         const double xc = cl.x0 + 0.5 * cl.hx, yc = cl.y0 + 0.5 * cl.hy;
+         for (int f = 0; f < 4; ++f)                                                // :498-510, all four faces
+         {
+            const double fx = (f == 0) ? cl.x0 : (f == 1) ? cl.x0 + cl.hx : xc;
+            const double fy = (f == 2) ? cl.y0 : (f == 3) ? cl.y0 + cl.hy : yc;
+            const double dr[2] = {fx - xc, fy - yc};
+            for (int i = 0; i < NC; ++i)
+               if (dumax[i] - dumin[i] > Mdx2)
+               {
+                  const double du = dr[0] * Dx[i] + dr[1] * Dy[i];
+                  if (du > 0.0)
+                     theta[i] = std::min (theta[i], dumax[i] / du);
+                  else if (du < 0.0)
+                     theta[i] = std::min (theta[i], dumin[i] / du);
+               }
+         }
+         double change = 0;
+         for (int i = 0; i < NC; ++i) change += theta[i];
+         change /= NC;
+         if (change < 0.99)                                                         // :519
+         {
+            for (int i = 0; i < NC; ++i)
+            {
+               Dx[i] *= theta[i];
+               Dy[i] *= theta[i];
+            }
+            if (o.prm.char_lim)
+            {
+               phys_to_con (Rx, Dx);
+               phys_to_con (Rx, Dy);
+            }
+            for (int i = 0; i < D; ++i)
+            {
+               const int comp_i = i / ns;
+               const double px = cl.x0 + o.support.x[i % ns] * cl.hx, py = cl.y0 + o.support.y[i % ns] * cl.hy;
+               const double dr[2] = {px - xc, py - yc};
+               u[i] = o.cell_average[c * NC + comp_i] + dr[0] * Dx[comp_i] + dr[1] * Dy[comp_i];
+            }
+            o.limited[c] |= 1;
+         }
+      }
+   }
+
+   void apply_limiter (oracle_ctx &o) // limiter.cc:35-65, src_mpi/limiter.cc:36-70
+   {
+      if (o.prm.limiter_type == ORACLE_LIMITER_MINMAX)
+      {
+         if (o.prm.basis == ORACLE_BASIS_QK) apply_limiter_minmax_Qk (o);
+         return;
+      }
       if (o.prm.limiter_type != ORACLE_LIMITER_TVB) return;
       if (o.prm.basis == ORACLE_BASIS_QK)
          apply_limiter_TVB_Qk (o);
@@ -1083,6 +1201,20 @@ oracle_ctx *oracle_create (int nv, const double *V, int nc, const int *C, int nb
          }
       o->vol.init (fe, x, y, w);
       o->support.init (fe, x, y, w); // Qk: support points == Gauss points, same order (A3)
+   }
+   {
+      const int k = fe.k;
+      const int nq = (k % 2 == 0) ? k / 2 + 1 : (k + 1) / 2 + 1; // src_mpi/limiter.cc:407-412
+      std::vector<double> gx, gw, x, y, w;
+      gauss_rule (nq, gx, gw);
+      for (int b = 0; b < nq; ++b)
+         for (int a = 0; a < nq; ++a)
+         {
+            x.push_back (gx[a]);
+            y.push_back (gx[b]);
+            w.push_back (gw[a] * gw[b]);
+         }
+      o->mmgrad.init (fe, x, y, w);
    }
    for (int f = 0; f < 4; ++f)
    {

@@ -16,7 +16,7 @@ extern "C" {
 #endif
 
 enum { ORACLE_BASIS_QK = 0, ORACLE_BASIS_PK = 1 };         /* parameters.h:390 */
-enum { ORACLE_LIMITER_NONE = 0, ORACLE_LIMITER_TVB = 1 };  /* parameters.h:243 */
+enum { ORACLE_LIMITER_NONE = 0, ORACLE_LIMITER_TVB = 1, ORACLE_LIMITER_MINMAX = 2 };  /* parameters.h:243, src_mpi/parameters.h:235 */
 enum { ORACLE_BC_PERIODIC = 5 };                           /* src_mpi/equation.h BoundaryKind::periodic */
 enum { ORACLE_COMPAT_SRC = 0, ORACLE_COMPAT_MPI = 1 };
 

@@ -141,7 +141,7 @@ def make_params(basis="Qk", degree=1, flux="lxf", limiter="none", char_lim=False
     p.basis = QK if basis == "Qk" else PK
     p.degree = degree
     p.flux_type = FLUX[flux]
-    p.limiter_type = 0 if limiter == "none" else 1
+    p.limiter_type = {"none": 0, "TVB": 1, "tvb": 1, "minmax": 2}[limiter]
     p.char_lim, p.pos_lim = int(char_lim), int(pos_lim)
     p.conserve_angular_momentum = int(conserve_angular_momentum)
     p.M, p.beta, p.gravity, p.cfl = M, beta, gravity, cfl

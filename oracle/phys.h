@@ -27,6 +27,11 @@ const char *phys_impl_name (void);
 void phys_kep_flux_restated (const double n[2], const double Wl[4], const double Wr[4], const double Al[4],
                              const double Ar[4], double out[4]);
 
+/* restated streamline eigenvector matrices (src_mpi/equation.h:299-335) and external forcing vector
+ * (src_mpi/equation.h:1189-1202) of the MPI tree (phys_kep_restated.c), used by both implementations */
+void phys_eigen_stream_restated (const double W[4], double R[16], double L[16]);
+void phys_ext_forcing_restated (const double W[4], const double f[2], double G[4]);
+
 /* claw.h:271-325 numerical_normal_flux -> equation.h lxf/sw/kfvs/roe/hllc */
 void phys_numerical_flux (int flux_type, const double n[2], const double Wp[4], const double Wm[4],
                           const double Ap[4], const double Am[4], double out[4]);

@@ -131,3 +131,49 @@ void phys_kep_flux_restated (const double normal[2], const double W_l[4], const 
    normal_flux[1] -= 0.5 * Diff[2];
    normal_flux[ENE] -= 0.5 * Diff[3];
 }
+
+/* src_mpi/equation.h:299-335: left / right eigenvector matrices along the streamline direction
+ * (kx,ky) = (cos, sin)(atan2(v,u)), used by the minmax limiter (src_mpi/limiter.cc:450).  Row-major 4x4,
+ * variable order of the transforms (rho, m_x, m_y, E) as in the x / y matrices. */
+void phys_eigen_stream_restated (const double W[4], double R[16], double L[16])
+{
+   double g1 = GAMMA - 1.0;
+   double rho = W[RHO];
+   double E = W[ENE];
+   double u = W[0] / rho;
+   double v = W[1] / rho;
+   double q2 = u * u + v * v;
+   double p = g1 * (E - 0.5 * rho * q2);
+   double c2 = GAMMA * p / rho;
+   double c = sqrt (c2);
+   double beta = 0.5 / c2;
+   double phi2 = 0.5 * g1 * q2;
+   double h = c2 / g1 + 0.5 * q2;
+   double theta = atan2 (v, u);
+   double kx = cos (theta);
+   double ky = sin (theta);
+   double uk = u * kx + v * ky;
+
+   R[0] = 1;         R[1] = 0;                 R[2] = 1;           R[3] = 1;
+   R[4] = u;         R[5] = ky;                R[6] = u + kx * c;  R[7] = u - kx * c;
+   R[8] = v;         R[9] = -kx;               R[10] = v + ky * c; R[11] = v - ky * c;
+   R[12] = 0.5 * q2; R[13] = ky * u - kx * v;  R[14] = h + c * uk; R[15] = h - c * uk;
+
+   L[0] = 1 - phi2 / c2;          L[1] = g1 * u / c2;              L[2] = g1 * v / c2;               L[3] = -g1 / c2;
+   L[4] = -(ky * u - kx * v);     L[5] = ky;                       L[6] = -kx;                       L[7] = 0;
+   L[8] = beta * (phi2 - c * uk); L[9] = beta * (kx * c - g1 * u); L[10] = beta * (ky * c - g1 * v); L[11] = beta * g1;
+   L[12] = beta * (phi2 + c * uk); L[13] = -beta * (kx * c + g1 * u); L[14] = -beta * (ky * c + g1 * v); L[15] = beta * g1;
+}
+
+/* src_mpi/equation.h:1189-1202 */
+void phys_ext_forcing_restated (const double W[4], const double f[2], double G[4])
+{
+   int d;
+   G[RHO] = 0.0;
+   G[ENE] = 0.0;
+   for (d = 0; d < 2; ++d)
+   {
+      G[d] = W[RHO] * f[d];
+      G[ENE] += W[d] * f[d];
+   }
+}

@@ -37,3 +37,22 @@ extern "C" __attribute__ ((visibility ("default"))) void phys_mpi_kep_flux (cons
    double (&f)[4] = *reinterpret_cast<double (*)[4]> (out);
    EulerEquations<2>::kep_flux (normal, Row (Wl), Row (Wr), vec4 (Al), vec4 (Ar), f);
 }
+
+// src_mpi/equation.h:299-335, the streamline-direction eigenvector matrices the minmax limiter
+// projects with (src_mpi/limiter.cc:450); row-major 4x4
+extern "C" __attribute__ ((visibility ("default"))) void phys_mpi_eigen_stream (const double W[4], double R[16], double L[16])
+{
+   double (&r)[4][4] = *reinterpret_cast<double (*)[4][4]> (R);
+   double (&l)[4][4] = *reinterpret_cast<double (*)[4][4]> (L);
+   EulerEquations<2>::compute_eigen_matrix (vec4 (W), r, l);
+}
+
+// src_mpi/equation.h:1189-1202, forcing vector of an external force f (src_mpi/assemble_explicit.cc:56-58, 84)
+extern "C" __attribute__ ((visibility ("default"))) void phys_mpi_ext_forcing (const double W[4], const double f[2], double G[4])
+{
+   dealii::Vector<double> ef (2);
+   ef[0] = f[0];
+   ef[1] = f[1];
+   double (&g)[4] = *reinterpret_cast<double (*)[4]> (G);
+   EulerEquations<2>::compute_forcing_vector (Row (W), ef, g);
+}

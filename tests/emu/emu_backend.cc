@@ -259,4 +259,16 @@ void dflo_emu_eigen (const double W[4], double Rx[16], double Lx[16], double Ry[
       }
 }
 double dflo_emu_minmod (double a, double b, double c, double Mdx2) { return dflo::minmod (a, b, c, Mdx2); }
+void dflo_emu_eigen_stream (const double W[4], double R[16], double L[16])
+{
+   dflo::EigenStream m;
+   dflo::compute_eigen_stream (W, m);
+   for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j)
+      {
+         R[4 * i + j] = m.R[i][j];
+         L[4 * i + j] = m.L[i][j];
+      }
+}
+void dflo_emu_forcing_ext (const double W[4], const double f[2], double G[4]) { dflo::forcing_ext (W, f[0], f[1], G); }
 }

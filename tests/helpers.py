@@ -283,6 +283,17 @@ def ic_sod_moving(x, y):
     return np.stack([rho * u, rho * v, rho, p / 0.4 + 0.5 * rho * (u * u + v * v)], axis=-1)
 
 
+def ic_sod_moving_wavy(x, y):
+    """ic_sod_moving with smooth ripples of density, velocity and pressure: no characteristic variable is
+    exactly constant in any cell, so the sign tests of the minmax limiter (`du > 0` on the mean slope,
+    src_mpi/limiter.cc:504-508) never sit on round-off noise."""
+    rho = np.where(x <= 0.5, 1.0, 0.125) * (1.0 + 0.05 * np.sin(9.0 * x + 2.0) * np.cos(40.0 * y + 1.0))
+    p = np.where(x <= 0.5, 1.0, 0.1) * (1.0 + 0.04 * np.cos(7.0 * x + 0.3) * np.sin(33.0 * y + 0.7))
+    u = 0.3 + 0.03 * np.sin(11.0 * x + 1.1) * np.cos(29.0 * y + 0.2)
+    v = 0.1 + 0.02 * np.cos(8.0 * x + 0.5) * np.sin(37.0 * y + 1.9)
+    return np.stack([rho * u, rho * v, rho, p / 0.4 + 0.5 * rho * (u * u + v * v)], axis=-1)
+
+
 def kxrcf_case(backend, basis, k, variable, nsteps=3):
     """Moving Sod problem with the TVB limiter gated by the KXRCF shock indicator of `variable`
     (src/indicator.cc:50-198, src/limiter.cc:263, 406): indicator values, limiter decisions and

@@ -153,7 +153,7 @@ def test_tvb_large_M_leaves_smooth_data_untouched():
 
 # ---- sharded engine: N in-process ranks with an emulated halo exchange ------------------------
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("case", ["vortex_Q2_roe", "sod_P2_tvb_pos", "step_Q1_tvb"])
+@pytest.mark.parametrize("case", ["vortex_Q2_roe", "sod_P2_tvb_pos", "step_Q1_tvb", "sod_Q2_minmax"])
 def test_sharded_matches_single(case, world):
     if case == "vortex_Q2_roe":
         args = (("isentropic_vortex", [6]), PERIODIC_BOX, ic_vortex)
@@ -163,6 +163,11 @@ def test_sharded_matches_single(case, world):
         args = (("sod_tube", [18, 3]), SOD_BC, ic_sod)
         prm = dict(basis="Pk", degree=2, flux="hllc", limiter="TVB", char_lim=True, pos_lim=True, M=0.0, beta=2.0, cfl=0.5)
         bval = (0.0, 0.0, 1.0, 2.5)
+    elif case == "sod_Q2_minmax":
+        from helpers import ic_sod_moving_wavy
+        args = (("sod_tube", [18, 3]), SOD_BC, ic_sod_moving_wavy)
+        prm = dict(basis="Qk", degree=2, flux="hllc", limiter="minmax", char_lim=True, pos_lim=True, M=0.0, beta=2.0, cfl=0.4)
+        bval = (0.3, 0.1, 1.0, 2.5)
     else:
         args = (("forward_step", [0.2]), STEP_BC, ic_step)
         prm = dict(basis="Qk", degree=1, flux="lxf", limiter="TVB", char_lim=True, M=0.0, beta=2.0, cfl=0.5)
@@ -209,3 +214,27 @@ def test_kxrcf_shock_indicator_gates_the_limiter(basis, k, variable):
     flags = c.oracle.limited_flags()
     assert 0 < np.count_nonzero(flags) < flags.size          # selective: the shock region only
     c.close()
+
+
+@pytest.mark.parametrize("k,char_lim,pos_lim", [(1, True, False), (2, True, True), (2, False, False), (3, True, False)])
+def test_minmax_limiter(k, char_lim, pos_lim):
+    """limiter type = minmax of the MPI tree (src_mpi/limiter.cc:400-553, Qk only): moving Sod problem so
+    that the streamline direction of the characteristic projection is defined (with a smooth ripple: on an
+    exactly constant cell the reference's `du > 0` test reads round-off noise); decisions and solution
+    against the oracle, with and without the characteristic projection (without it the reference's
+    range starts from 0) and with the positivity limiter behind it."""
+    from helpers import ic_sod_moving_wavy
+    c = Case(("sod_tube", [20, 3]), SOD_BC, ic_sod_moving_wavy, basis="Qk", degree=k, flux="hllc", limiter="minmax",
+             char_lim=char_lim, pos_lim=pos_lim, M=0.0, beta=2.0, cfl=0.4)
+    c.set_boundary(values=(0.3, 0.1, 1.0, 2.5))
+    c.limit_initial()
+    flips = sum(c.step()[0] for _ in range(2))
+    assert c.rel_err() <= TOL_STEP_SHOCK and flips == 0
+    assert np.count_nonzero(c.oracle.limited_flags() & 1) > 0
+    c.close()
+
+
+def test_minmax_limiter_is_qk_only():
+    """src_mpi/parameters.cc:610-611: 'minmax limiter is implemented only for Qk'."""
+    with pytest.raises(Exception):
+        Case(("sod_tube", [8, 2]), SOD_BC, ic_sod, basis="Pk", degree=1, flux="lxf", limiter="minmax", M=0.0, beta=1.0, cfl=0.4)

@@ -265,3 +265,19 @@ def test_kxrcf_shock_indicator_gates_the_limiter(basis, k, variable):
     flags = c.oracle.limited_flags()
     assert 0 < np.count_nonzero(flags) < flags.size
     c.close()
+
+
+@pytest.mark.parametrize("k,char_lim,pos_lim", [(1, True, False), (2, True, True), (2, False, False), (3, True, True)])
+def test_minmax_limiter(k, char_lim, pos_lim):
+    """limiter type = minmax of the MPI tree (src_mpi/limiter.cc:400-553) on the device: limiter decisions
+    and solution against the oracle on a rippled moving Sod problem (see tests/test_emu_parity.py)."""
+    from helpers import ic_sod_moving_wavy
+    c = Case(("sod_tube", [40, 4]), SOD_BC, ic_sod_moving_wavy, backend="cuda", basis="Qk", degree=k, flux="hllc",
+             limiter="minmax", char_lim=char_lim, pos_lim=pos_lim, M=0.0, beta=2.0, cfl=0.4)
+    c.set_boundary(values=(0.3, 0.1, 1.0, 2.5))
+    c.limit_initial()
+    flips = sum(c.step()[0] for _ in range(3))
+    assert c.rel_err() <= TOL_STEP_SHOCK and flips == 0
+    flags = c.oracle.limited_flags()
+    assert 0 < np.count_nonzero(flags & 1) < flags.size
+    c.close()

@@ -169,6 +169,7 @@ def test_prm_rejects_undeclared_keys_and_bad_combinations(lib, tmp_path):
         "undeclared": base + "\nset no such key = 1\n",                                     # ParameterHandler: error
         "tvb_needs_cartesian": base.replace("set mapping   = cartesian", "set mapping   = q1"),   # parameters.cc:536-541
         "bad_flux": base.replace("set flux = hllc", "set flux = hllx"),
+        "minmax_needs_qk": base.replace("set type = TVB", "set type = minmax"),           # src_mpi/parameters.cc:610-611
     }
     for name, text in cases.items():
         p = tmp_path / (name + ".prm")
@@ -176,6 +177,12 @@ def test_prm_rejects_undeclared_keys_and_bad_combinations(lib, tmp_path):
         h = L.dflo_claw_create(str(p).encode(), b"sod_tube 10 2", None, 0)
         assert not h, name
         assert L.dflo_host_last_error()
+    # limiter type = minmax (src_mpi/parameters.cc:205) is accepted on Qk
+    p = tmp_path / "minmax_qk.prm"
+    p.write_text(base.replace("set type = TVB", "set type = minmax").replace("set basis     = Pk", "set basis     = Qk"))
+    h = L.dflo_claw_create(str(p).encode(), b"sod_tube 10 2", None, 0)
+    assert h, L.dflo_host_last_error()
+    L.dflo_claw_destroy(h)
     # src/ does not know periodic boundaries (SURVEY 8a forks): compat=src rejects them, compat=mpi accepts
     vort = os.path.join(PRM_DIR, "cfg1_isentropic_vortex_Q1_lxf.prm").encode()
     h = L.dflo_claw_create(vort, b"isentropic_vortex 4", None, abi.COMPAT["mpi"])

@@ -238,3 +238,45 @@ def test_kep_flux_restated_bit_exact_vs_src_mpi_golden(restated):
         Fn = restated.flux_matrix(W) @ nn
         H = restated.flux(O.FLUX["kep"], nn, W, W, W, W)
         assert np.abs(H - Fn).max() <= 1e-11 * max(1.0, np.abs(Fn).max())
+
+
+def test_mpi_extras_restated_bit_exact_and_device_functions():
+    """Streamline eigenvector matrices of the minmax limiter (src_mpi/equation.h:299-335) and the external
+    forcing vector (src_mpi/equation.h:1189-1202): the plain-C restatement is bit-exact to the golden vectors
+    produced by that header's own object code (tests/golden/make_mpi_extras_kat.py); where oracle/_ref
+    exists the object code is re-checked; the product's device functions (normalised velocity instead of
+    cos/sin(atan2)) agree to round-off, and L R = I."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mpi_extras_kat.npz"))
+    Lr = O.load("restated")
+    E = emu_lib()
+    ref = None
+    p = os.path.join(os.path.dirname(O.lib_path("physref")), "libphys_reference_mpi.so")
+    if os.path.exists(p):
+        ref = ctypes.CDLL(p)
+    for i in range(len(g["W"])):
+        w, f = np.ascontiguousarray(g["W"][i]), np.ascontiguousarray(g["F"][i])
+        R, L, G = np.zeros(16), np.zeros(16), np.zeros(4)
+        Lr.phys_eigen_stream_restated(w.ctypes.data_as(_dp), R.ctypes.data_as(_dp), L.ctypes.data_as(_dp))
+        Lr.phys_ext_forcing_restated(w.ctypes.data_as(_dp), f.ctypes.data_as(_dp), G.ctypes.data_as(_dp))
+        assert _same(R, g["R"][i]) and _same(L, g["L"][i]) and _same(G, g["G"][i]), i
+        if ref is not None:
+            R2, L2, G2 = np.zeros(16), np.zeros(16), np.zeros(4)
+            ref.phys_mpi_eigen_stream(w.ctypes.data_as(_dp), R2.ctypes.data_as(_dp), L2.ctypes.data_as(_dp))
+            ref.phys_mpi_ext_forcing(w.ctypes.data_as(_dp), f.ctypes.data_as(_dp), G2.ctypes.data_as(_dp))
+            assert _same(R2, g["R"][i]) and _same(L2, g["L"][i]) and _same(G2, g["G"][i]), i
+        Rd, Ld, Gd = np.zeros(16), np.zeros(16), np.zeros(4)
+        E.dflo_emu_eigen_stream(w.ctypes.data_as(_dp), Rd.ctypes.data_as(_dp), Ld.ctypes.data_as(_dp))
+        E.dflo_emu_forcing_ext(w.ctypes.data_as(_dp), f.ctypes.data_as(_dp), Gd.ctypes.data_as(_dp))
+        assert np.abs(Rd - g["R"][i]).max() <= 1e-13 * max(1.0, np.abs(g["R"][i]).max()), i
+        assert np.abs(Ld - g["L"][i]).max() <= 1e-13 * max(1.0, np.abs(g["L"][i]).max()), i
+        assert np.abs(Gd - g["G"][i]).max() <= 1e-14 * max(1.0, np.abs(g["G"][i]).max()), i
+        I = Ld.reshape(4, 4) @ Rd.reshape(4, 4)
+        assert np.abs(I - np.eye(4)).max() <= 1e-10 * max(1.0, np.abs(Rd).max() * np.abs(Ld).max()), i
+    # the forcing of src/ (equation.h:829-850) is the external force (0,-1)
+    P = O.Physics("restated")
+    for i in range(20):
+        w, f, G = np.ascontiguousarray(g["W"][i]), np.array([0.0, -1.0]), np.zeros(4), 
+        Lr.phys_ext_forcing_restated(w.ctypes.data_as(_dp), f.ctypes.data_as(_dp), G.ctypes.data_as(_dp))
+        G0 = np.zeros(4)
+        Lr.phys_forcing(w.ctypes.data_as(_dp), G0.ctypes.data_as(_dp))
+        assert np.array_equal(G + 0.0, G0 + 0.0), i
