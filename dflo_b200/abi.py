@@ -157,6 +157,7 @@ def _declare_engine(L, prefix):
     f("commit_step").argtypes = [vp]
     f("set_boundary_values").argtypes = [vp, c_double_p]
     f("set_boundary_expression").argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
+    f("set_external_force").argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p]
     f("assemble_rhs").argtypes = [vp, ctypes.c_double]
     f("rk_stage").argtypes = [vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, c_double_p]
     f("compute_dt").argtypes = [vp, ctypes.c_double, ctypes.c_double, c_double_p]
@@ -344,6 +345,10 @@ class Engine:
 
     def set_boundary_expression(self, boundary_id, comp, expr):
         self._check(self._f("set_boundary_expression")(self.h, boundary_id, comp, expr.encode()))
+
+    def set_external_force(self, fx_expr, fy_expr):
+        """"f_0 value" / "f_1 value" of the MPI tree (src_mpi/parameters.cc:488-497)."""
+        self._check(self._f("set_external_force")(self.h, fx_expr.encode(), fy_expr.encode()))
 
     def assemble_rhs(self, t_bc=0.0):
         self._check(self._f("assemble_rhs")(self.h, float(t_bc)))

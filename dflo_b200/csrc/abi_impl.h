@@ -97,6 +97,10 @@
    {                                                                                                                     \
       return (c && e) ? c->eng.set_boundary_expression (id, comp, e) : DFLO_E_INVALID;                                   \
    }                                                                                                                     \
+   int DFLO_ABI_CAT (PREFIX, set_external_force) (CTX *c, const char *fx, const char *fy)                                \
+   {                                                                                                                     \
+      return (c && fx && fy) ? c->eng.set_external_force (fx, fy) : DFLO_E_INVALID;                                      \
+   }                                                                                                                     \
    int DFLO_ABI_CAT (PREFIX, assemble_rhs) (CTX *c, double t) { return c ? c->eng.assemble_rhs (t) : DFLO_E_INVALID; }   \
    int DFLO_ABI_CAT (PREFIX, get_rhs) (CTX *c, double *r, const uint32_t *m, size_t n)                                   \
    {                                                                                                                     \

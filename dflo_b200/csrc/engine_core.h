@@ -109,6 +109,34 @@ namespace dflo
       }
    };
 
+   // external force f_d(x,y) of the MPI tree at the cell quadrature points, from the two compiled
+   // expressions, with t = 0 (src_mpi/assemble_explicit.cc:56-58: vector_value_list on a
+   // FunctionParser whose time is never set)
+   struct ExtForceEvalArgs
+   {
+      double *ext_force;         // [n_cells][n1*n1][2]
+      const double *geom;
+      const double *gx;          // Gauss nodes [n1]
+      const ExprInstr *code;     // program of f_0 then f_1
+      int len0, len1;
+      int n_cells, n1;
+   };
+   struct ExtForceEvalKernel
+   {
+      typedef ExtForceEvalArgs Args;
+      static DFLO_DEV void thread (const Args &A, int j)
+      {
+         const int nq = A.n1 * A.n1;
+         if (j >= A.n_cells * nq) return;
+         const int cell = j / nq, q = j % nq;
+         const double *g = A.geom + (size_t) cell * 4;
+         const double x = g[0] + A.gx[q % A.n1] * g[2];
+         const double y = g[1] + A.gx[q / A.n1] * g[3];
+         A.ext_force[(size_t) j * 2] = expr_eval (A.code, A.len0, x, y, 0.0);
+         A.ext_force[(size_t) j * 2 + 1] = expr_eval (A.code + A.len0, A.len1, x, y, 0.0);
+      }
+   };
+
    // time scalars on the device: [0] t, [1] dt, [2] dt accumulator (min over cells), [3] final time
    struct DtArgs
    {
@@ -320,12 +348,19 @@ namespace dflo
 #define DFLO_LIM(B, N)                                                                          \
    do                                                                                           \
    {                                                                                            \
-      if (bk.limiter_block_form () && a.tvb != 2)                                               \
+      if (bk.limiter_block_form ())                                                             \
          bk.template launch<LimiterKernel<B, N>> (LimiterKernel<B, N>::grid (a.n_compute), a);  \
       else                                                                                      \
          bk.template launch<LimiterCellKernel<B, N>> (LimiterCellKernel<B, N>::grid (a.n_compute), a); \
    } while (0)
-      if (basis == BASIS_QK)
+      if (basis == BASIS_QK && a.tvb == 2) // minmax limiter (src_mpi/limiter.cc:400-553): instantiations of their own
+      {
+         if (n1 == 2) bk.template launch<LimiterCellKernel<BASIS_QK, 2, 1>> (LimiterCellKernel<BASIS_QK, 2, 1>::grid (a.n_compute), a);
+         else if (n1 == 3) bk.template launch<LimiterCellKernel<BASIS_QK, 3, 1>> (LimiterCellKernel<BASIS_QK, 3, 1>::grid (a.n_compute), a);
+         else if (n1 == 4) bk.template launch<LimiterCellKernel<BASIS_QK, 4, 1>> (LimiterCellKernel<BASIS_QK, 4, 1>::grid (a.n_compute), a);
+         else bk.template launch<LimiterCellKernel<BASIS_QK, 5, 1>> (LimiterCellKernel<BASIS_QK, 5, 1>::grid (a.n_compute), a);
+      }
+      else if (basis == BASIS_QK)
       {
          if (n1 == 2) DFLO_LIM (BASIS_QK, 2);
          else if (n1 == 3) DFLO_LIM (BASIS_QK, 3);
@@ -388,6 +423,7 @@ namespace dflo
       FaceJob *d_jobs = nullptr;
       TileDesc *d_tiles = nullptr;
       unsigned char *d_fflags = nullptr;
+      double *d_ext_force = nullptr; // [n_local][n_q][2], allocated by set_external_force
       double *d_geom = nullptr, *d_bc_g = nullptr, *d_stage_tab = nullptr, *d_lim_tab = nullptr, *d_gw = nullptr, *d_gx = nullptr;
       int *d_bkind = nullptr, *d_bf_cell = nullptr, *d_bf_face = nullptr, *d_bf_id = nullptr, *d_l2g = nullptr, *d_flags = nullptr;
       unsigned int *d_err = nullptr;
@@ -531,7 +567,7 @@ namespace dflo
             bk.free (U[i]);
             bk.free (AVG[i]);
          }
-         void *ptrs[] = {rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
+         void *ptrs[] = {d_ext_force, rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
                          d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_shock, d_code, d_prog_start, d_prog_start_t, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles, d_rowdesc, d_send_entries};
          for (void *p : ptrs) bk.free (p);
          for (int k = 0; k < 2; ++k)
@@ -644,6 +680,39 @@ namespace dflo
          programs_time_dependent = programs_time_dependent || uses_t;
          bk.drop_graphs ();
          eval_boundary (false); // values at the current time
+         return bk.check (error);
+      }
+
+      // "f_0 value" / "f_1 value" of the MPI tree (src_mpi/parameters.cc:355-360, 488-497): the external
+      // force replaces the hard-wired (0,-1) of src/ in the forcing term gravity * G
+      // (src_mpi/equation.h:1189-1202, src_mpi/assemble_explicit.cc:84, 108-111)
+      int set_external_force (const char *fx, const char *fy)
+      {
+         ExprCompiler cc;
+         std::string e;
+         std::vector<ExprInstr> c0, c1;
+         if (!cc.compile (fx, c0, e, nullptr)) return fail (DFLO_E_EXPR, e);
+         if (!cc.compile (fy, c1, e, nullptr)) return fail (DFLO_E_EXPR, e);
+         std::vector<ExprInstr> all (c0);
+         all.insert (all.end (), c1.begin (), c1.end ());
+         bk.sync ();
+         const size_t nq = (size_t) tab.n1 * tab.n1;
+         if (!d_ext_force) d_ext_force = bk.template alloc<double> ((size_t) lm.n_local * nq * 2);
+         ExprInstr *d_fcode = bk.template alloc<ExprInstr> (std::max<size_t> (1, all.size ()));
+         bk.h2d (d_fcode, all.data (), all.size () * sizeof (ExprInstr));
+         ExtForceEvalArgs a;
+         a.ext_force = d_ext_force;
+         a.geom = d_geom;
+         a.gx = d_gx;
+         a.code = d_fcode;
+         a.len0 = c0.size ();
+         a.len1 = c1.size ();
+         a.n_cells = lm.n_local;
+         a.n1 = tab.n1;
+         bk.template launch1d<ExtForceEvalKernel> (a.n_cells * (int) nq, a);
+         bk.sync ();
+         bk.free (d_fcode);
+         bk.drop_graphs ();
          return bk.check (error);
       }
 
@@ -867,6 +936,7 @@ namespace dflo
          a.compat_mpi = prm.compat == DFLO_COMPAT_MPI;
          a.ark = ark[rk];
          a.gravity = prm.gravity;
+         a.ext_force = d_ext_force;
          return a;
       }
 

@@ -227,6 +227,17 @@ namespace dflo
                }
             }
       }
+      // MPI tree: the forcing term is gravity * (rho f, m.f) with the external force of the deck
+      // (src_mpi/assemble_explicit.cc:56-58, 84); src/ keeps its hard-wired f = (0,-1)
+      if (compat == DFLO_COMPAT_MPI && parameters.gravity != 0.0)
+      {
+         rc = dflo_b200_set_external_force (ctx, parameters.external_force[0].c_str (), parameters.external_force[1].c_str ());
+         if (rc)
+         {
+            error = dflo_b200_last_error (ctx);
+            return rc;
+         }
+      }
       std::vector<double> u;
       set_initial_condition (u);
       rc = dflo_b200_set_solution (ctx, u.data (), nullptr, u.size ());   // also cell averages (:997)

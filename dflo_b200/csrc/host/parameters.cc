@@ -55,6 +55,8 @@ namespace dflo
          d ("diffusion power", "2.0");
          d ("diffusion coefficient", "0.0");
          d ("gravity", "0.0");
+         d ("f_0 value", "0.0"); // components of the external force, src_mpi/parameters.cc:355-360
+         d ("f_1 value", "0.0");
          d ("time stepping/stationary", "false");
          d ("time stepping/cfl", "0.0");
          d ("time stepping/time step type", "global");
@@ -207,6 +209,8 @@ namespace dflo
          diffusion_power = num ("diffusion power");
          diffusion_coef = num ("diffusion coefficient");
          gravity = num ("gravity");
+         external_force[0] = get ("f_0 value"); // src_mpi/parameters.cc:488-497
+         external_force[1] = get ("f_1 value");
          cfl = num ("time stepping/cfl");
          time_step_type = get ("time stepping/time step type");
          time_step = num ("time stepping/time step");

@@ -22,6 +22,7 @@ namespace dflo
          std::string basis;          // "Qk" | "Pk"
          std::string mapping;        // "q1" | "q2" | "cartesian"
          double diffusion_power, diffusion_coef, gravity;
+         std::string external_force[2]; // "f_0 value", "f_1 value" in x,y,t (MPI tree only)
          // time stepping
          bool is_stationary;
          double cfl, time_step, final_time, theta;

@@ -27,10 +27,8 @@
 
 #if defined(__CUDACC__)
 #define DFLO_DEV __device__ __forceinline__
-#define DFLO_DEV_NOINLINE __device__ __noinline__
 #else
 #define DFLO_DEV inline
-#define DFLO_DEV_NOINLINE inline
 #endif
 
 namespace dflo
@@ -103,6 +101,8 @@ namespace dflo
       int compat_mpi;
       double ark;
       double gravity;
+      const double *ext_force; // [n_local][n_q][2] external force at the cell quadrature points (src_mpi/assemble_explicit.cc:56-58),
+                               // or nullptr: the hard-wired (0,-1) of src/ (equation.h:829-850)
    };
 
 #if defined(__CUDACC__)
@@ -507,7 +507,10 @@ namespace dflo
                   double W[4], Gv[4];
 #pragma unroll
                   for (int c = 0; c < 4; ++c) W[c] = uc[c * NS + lq];
-                  forcing (W, Gv);
+                  if (A.ext_force)
+                     forcing_ext (W, A.ext_force[((size_t) cell * NQ + lq) * 2], A.ext_force[((size_t) cell * NQ + lq) * 2 + 1], Gv);
+                  else
+                     forcing (W, Gv);
 #pragma unroll
                   for (int c = 0; c < 4; ++c) r[c] += A.gravity * Gv[c] * (wa * wb * hx * hy);
                }
@@ -540,7 +543,10 @@ namespace dflo
                      double W[4], Gv[4];
 #pragma unroll
                      for (int c = 0; c < 4; ++c) W[c] = sW[(slot * 4 + c) * NQ + q];
-                     forcing (W, Gv);
+                     if (A.ext_force)
+                        forcing_ext (W, A.ext_force[((size_t) cell * NQ + q) * 2], A.ext_force[((size_t) cell * NQ + q) * 2 + 1], Gv);
+                     else
+                        forcing (W, Gv);
                      const double w = gw[q % N1] * gw[q / N1] * hx * hy * ph[q * NS + m];
 #pragma unroll
                      for (int c = 0; c < 4; ++c) r[c] += A.gravity * Gv[c] * w;
@@ -1172,7 +1178,7 @@ namespace dflo
    // arithmetic expression is the one of LimiterKernel, in the same order, so both forms give
    // bit-identical results.
    //---------------------------------------------------------------------------------------------
-   template <int BASIS, int N1>
+   template <int BASIS, int N1, int MINMAX = 0> // MINMAX = 1: the minmax limiter instead of TVB, an instantiation of its own
    struct LimiterCellKernel
    {
       typedef LimiterArgs Args;
@@ -1217,9 +1223,7 @@ namespace dflo
       // starts from 0 (zero-initialised avg_min / avg_max, :438), and only true interior faces
       // bring neighbours (!at_boundary, :454: periodic partners do not).  The mean gradient is
       // taken with the Gauss(k+1) rule of the TVB limiter instead of the reference's QGauss(nq)
-      // (:407-413) -- both are exact for the integrand.  Returns 1 if the cell was rewritten.  Not
-      // inlined, and everything passed by value: the register allocation and the stack frame of the
-      // TVB / positivity path stay what they were.
+      // (:407-413) -- both are exact for the integrand.  Returns 1 if the cell was rewritten.
       struct MinmaxIn
       {
          const double *avg, *geom, *tab;
@@ -1228,7 +1232,7 @@ namespace dflo
          double M;
          int char_lim;
       };
-      static DFLO_DEV_NOINLINE int minmax_cell (const MinmaxIn A, int cell, double *uc)
+      static DFLO_DEV int minmax_cell (const MinmaxIn A, int cell, double *uc)
       {
          const double *tb = A.tab;
          const double hx = A.geom[(size_t) cell * 4 + 2], hy = A.geom[(size_t) cell * 4 + 3];
@@ -1339,12 +1343,12 @@ namespace dflo
          double lo[4] = {1.0e300, 1.0e300, 1.0e300, 1.0e300}, hi[4] = {-1.0e300, -1.0e300, -1.0e300, -1.0e300};
          bool have_bounds = false;
 
-         if (BASIS == BASIS_QK && A.tvb == 2 && (!A.shock || A.shock[cell] > 1.0)) // src_mpi/limiter.cc:437
+         if (MINMAX && BASIS == BASIS_QK && A.tvb == 2 && (!A.shock || A.shock[cell] > 1.0)) // src_mpi/limiter.cc:437
          {
             const typename LimiterCellKernel::MinmaxIn in = {A.avg, A.geom, A.tab, A.nbr, A.fflags, A.M, A.char_lim};
             flag |= minmax_cell (in, cell, uc);
          }
-         if (A.tvb == 1 && (!A.shock || A.shock[cell] > 1.0)) // limiter.cc:263, 406
+         if (!MINMAX && A.tvb == 1 && (!A.shock || A.shock[cell] > 1.0)) // limiter.cc:263, 406
          {
             const double hx = A.geom[(size_t) cell * 4 + 2], hy = A.geom[(size_t) cell * 4 + 3];
             const double dx = sqrt (hx * hx + hy * hy) / 1.4142135623730951; // diameter / sqrt(dim)

@@ -591,7 +591,13 @@ namespace dflo
             {
                const double W[4] = {u[0][a], u[1][a], u[2][a], u[3][a]};
                double Gv[4];
-               forcing (W, Gv);
+               if (A.ext_force)
+               {
+                  const double *f = A.ext_force + ((size_t) (c0 + rs) * NS + rb * N1 + a) * 2;
+                  forcing_ext (W, f[0], f[1], Gv);
+               }
+               else
+                  forcing (W, Gv);
                const double w = A.gravity * (T.gw[a] * T.gw[rb] * hx * hy);
 #pragma unroll
                for (int c = 0; c < 4; ++c) rrow[c][a] += Gv[c] * w;

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFLO_B200_ABI_VERSION 2
+#define DFLO_B200_ABI_VERSION 3
 #define DFLO_MAX_BOUNDARIES 10 /* Parameters::AllParameters::max_n_boundaries, src/parameters.h:370 */
 
 /* error codes */
@@ -154,6 +154,12 @@ int dflo_b200_set_boundary_values (dflo_ctx *ctx, const double *g /* [n_boundary
 /* ... or the muparser-style expression in x,y,t of one component (src/parameters.cc:470-511); it is
  * compiled to bytecode and evaluated on the device at the BC time of every stage. */
 int dflo_b200_set_boundary_expression (dflo_ctx *ctx, int boundary_id, int component, const char *expr);
+/* ---- external force of the MPI tree ("f_0 value" / "f_1 value", src_mpi/parameters.cc:355-360, 488-497) ----
+ * Two muparser-style expressions in x,y, evaluated once at the cell quadrature points (with t = 0 like the
+ * reference, whose FunctionParser time is never set: src_mpi/assemble_explicit.cc:56-58).  From then on the forcing
+ * term gravity * G of the cell integral uses G = (rho f, m.f) (src_mpi/equation.h:1189-1202) instead of the
+ * hard-wired f = (0,-1) of src/equation.h:829-850. */
+int dflo_b200_set_external_force (dflo_ctx *ctx, const char *fx_expr, const char *fy_expr);
 
 /* ---- the hot path ---- */
 /* assemble_system: right_hand_side from current_solution (src/assemble_explicit.cc:433-452) */

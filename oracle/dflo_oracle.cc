@@ -250,6 +250,7 @@ struct oracle_ctx
    UnitValues posx, posy;   // positivity.cc:43-47
    UnitValues support;      // Qk unit support points (limiter.cc:234)
    UnitValues mmgrad;       // QGauss<2>(nq) of the minmax limiter (src_mpi/limiter.cc:407-413)
+   std::vector<double> ext_force; // [nc][nq][2] external force at the cell quadrature points (MPI tree), empty: src forcing
    std::vector<Cell> cells;
    std::vector<char> shared;    // [nc][4] face shared through vertices (cell->neighbor() exists)
    int n_bfaces;
@@ -419,7 +420,10 @@ namespace
             W[q * NC + c] += u[i] * o.vol.phi[(i % ns) * nq + q];
          }
          phys_flux_matrix (&W[q * NC], &flux[q * 8]);
-         phys_forcing (&W[q * NC], &forcing[q * NC]);
+         if (o.ext_force.empty ())
+            phys_forcing (&W[q * NC], &forcing[q * NC]);                                           // src: equation.h:829-850
+         else // src_mpi/assemble_explicit.cc:56-58, 84
+            phys_ext_forcing_restated (&W[q * NC], &o.ext_force[((size_t) cno * nq + q) * 2], &forcing[q * NC]);
       }
       const double h[2] = {cl.hx, cl.hy};
       for (int i = 0; i < D; ++i)
@@ -1363,6 +1367,15 @@ void oracle_set_solution (oracle_ctx *o, const double *u)
 
 void oracle_get_solution (const oracle_ctx *o, double *u) { std::copy (o->current.begin (), o->current.end (), u); }
 void oracle_commit_step (oracle_ctx *o) { o->old = o->current; }
+/* external force values at the cell quadrature points (parameters.external_force.vector_value_list,
+ * src_mpi/assemble_explicit.cc:56-58); NULL restores the hard-wired forcing of src/ */
+void oracle_set_external_force (oracle_ctx *o, const double *f)
+{
+   if (!f)
+      o->ext_force.clear ();
+   else
+      o->ext_force.assign (f, f + (size_t) o->cells.size () * o->vol.nq * 2);
+}
 void oracle_set_bc_values (oracle_ctx *o, const double *g)
 {
    std::copy (g, g + (size_t) o->n_bfaces * o->fe.n1 * NC, o->bc_values.begin ());

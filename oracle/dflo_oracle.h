@@ -72,6 +72,7 @@ void oracle_set_initial_condition (oracle_ctx *, const double *f);
 void oracle_set_solution (oracle_ctx *, const double *u);   /* sets current AND old */
 void oracle_get_solution (const oracle_ctx *, double *u);
 void oracle_commit_step (oracle_ctx *);                     /* old_solution = current (claw.cc:1110) */
+void oracle_set_external_force (oracle_ctx *, const double *f /*[nc][nq][2] or NULL*/); /* src_mpi/assemble_explicit.cc:56-58 */
 void oracle_set_bc_values (oracle_ctx *, const double *g /*[nbf][nqf][4]*/);
 
 void oracle_compute_cell_average (oracle_ctx *);            /* claw.cc:562-597 */

@@ -239,6 +239,12 @@ class Oracle:
         if self.n_bfaces:
             self.L.oracle_set_bc_values(self.h, _d(g))
 
+    def set_external_force(self, f):
+        """f: [n_cells][nq][2] values of the MPI tree's external force at the cell quadrature points."""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        assert f.shape == (self.n_cells, self.nq, 2)
+        self.L.oracle_set_external_force(self.h, _d(f))
+
     def compute_cell_average(self):
         self.L.oracle_compute_cell_average(self.h)
 

@@ -171,6 +171,15 @@ class Case:
         for e in self.engines:
             e.set_boundary_values(g)
 
+    def set_external_force(self, fx_expr, fy_expr, fn):
+        """External force of the MPI tree: the engine compiles the two expressions, the oracle gets the values
+        of the python callable fn(x, y) -> (fx, fy) at its cell quadrature points."""
+        xq = self.oracle.cell_qpoints()
+        fx, fy = fn(xq[..., 0], xq[..., 1])
+        self.oracle.set_external_force(np.stack([fx + 0 * xq[..., 0], fy + 0 * xq[..., 0]], axis=-1))
+        for e in self.engines:
+            e.set_external_force(fx_expr, fy_expr)
+
     def solution(self):
         u = np.zeros(self.oracle.n_cells * self.oracle.D)
         for e in self.engines:

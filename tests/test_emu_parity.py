@@ -238,3 +238,22 @@ def test_minmax_limiter_is_qk_only():
     """src_mpi/parameters.cc:610-611: 'minmax limiter is implemented only for Qk'."""
     with pytest.raises(Exception):
         Case(("sod_tube", [8, 2]), SOD_BC, ic_sod, basis="Pk", degree=1, flux="lxf", limiter="minmax", M=0.0, beta=1.0, cfl=0.4)
+
+
+@pytest.mark.parametrize("basis,k,flux", [("Qk", 1, "lxf"), ("Qk", 3, "roe"), ("Pk", 2, "hllc"), ("Qk", 2, "kep")])
+def test_external_force_mpi(basis, k, flux):
+    """External force of the MPI tree (f_0 / f_1 value, src_mpi/assemble_explicit.cc:56-58, 84;
+    src_mpi/equation.h:1189-1202): forcing term gravity * (rho f, m.f) with a position-dependent f, right-hand
+    side and a step against the oracle; f = (0,-1) reproduces the hard-wired forcing of src/ bit for bit."""
+    bc = {1: "inflow", 2: "slip", 3: "pressure", 0: "farfield"}
+    c = Case(("forward_step", [0.2]), bc, ic_smooth, basis=basis, degree=k, flux=flux, cfl=0.5, compat="mpi", gravity=0.7)
+    c.set_boundary(values=(0.5, 0.1, 1.2, 3.0), wiggle=0.1)
+    r_src = c.rhs_pair()[1].copy()
+    c.set_external_force("0.0", "-1.0", lambda x, y: (0.0 * x, -1.0 + 0.0 * x))
+    assert np.array_equal(c.rhs_pair()[1], r_src)
+    c.set_external_force("0.3*sin(2*x)+y", "-1.0+0.2*x*y", lambda x, y: (0.3 * np.sin(2 * x) + y, -1.0 + 0.2 * x * y))
+    _rhs_ok(c)
+    assert np.abs(c.rhs_pair()[1] - r_src).max() > 1e-3
+    c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()

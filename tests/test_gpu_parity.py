@@ -281,3 +281,23 @@ def test_minmax_limiter(k, char_lim, pos_lim):
     flags = c.oracle.limited_flags()
     assert 0 < np.count_nonzero(flags & 1) < flags.size
     c.close()
+
+
+@pytest.mark.parametrize("basis,k,flux", [("Qk", 1, "lxf"), ("Qk", 3, "roe"), ("Pk", 2, "hllc"), ("Qk", 2, "kep")])
+def test_external_force_mpi(basis, k, flux):
+    """External force of the MPI tree (f_0 / f_1 value, src_mpi/assemble_explicit.cc:56-58, 84;
+    src_mpi/equation.h:1189-1202): forcing term gravity * (rho f, m.f) with a position-dependent f, right-hand
+    side and a step against the oracle; f = (0,-1) reproduces the hard-wired forcing of src/ bit for bit."""
+    bc = {1: "inflow", 2: "slip", 3: "pressure", 0: "farfield"}
+    c = Case(("forward_step", [0.2]), bc, ic_smooth, backend="cuda", basis=basis, degree=k, flux=flux, cfl=0.5, compat="mpi", gravity=0.7)
+    c.set_boundary(values=(0.5, 0.1, 1.2, 3.0), wiggle=0.1)
+    r_src = c.rhs_pair()[1].copy()
+    c.set_external_force("0.0", "-1.0", lambda x, y: (0.0 * x, -1.0 + 0.0 * x))
+    assert np.array_equal(c.rhs_pair()[1], r_src)
+    c.set_external_force("0.3*sin(2*x)+y", "-1.0+0.2*x*y", lambda x, y: (0.3 * np.sin(2 * x) + y, -1.0 + 0.2 * x * y))
+    r_o, r_e = c.rhs_pair()
+    assert np.abs(r_o - r_e).max() <= TOL_RHS * max(1.0, np.abs(r_o).max()) * np.sqrt(c.oracle.D)
+    assert np.abs(c.rhs_pair()[1] - r_src).max() > 1e-3
+    c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
