@@ -276,7 +276,10 @@ def test_minmax_limiter(k, char_lim, pos_lim):
              limiter="minmax", char_lim=char_lim, pos_lim=pos_lim, M=0.0, beta=2.0, cfl=0.4)
     c.set_boundary(values=(0.3, 0.1, 1.0, 2.5))
     c.limit_initial()
-    flips = sum(c.step()[0] for _ in range(3))
+    # without the characteristic projection the reference's range starts from 0 (src_mpi/limiter.cc:438): minima of
+    # density are never limited and this shock problem blows up after three steps, in the oracle as well -- one step
+    flips = sum(c.step()[0] for _ in range(3 if char_lim else 1))
+    assert np.isfinite(c.oracle.solution()).all()
     assert c.rel_err() <= TOL_STEP_SHOCK and flips == 0
     flags = c.oracle.limited_flags()
     assert 0 < np.count_nonzero(flags & 1) < flags.size
