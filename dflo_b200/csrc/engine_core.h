@@ -9,6 +9,7 @@
 #include "../../include/dflo_b200.h"
 #include "expr.h"
 #include "kernels.cuh"
+#include "cell_stage.cuh"
 #include "partition.h"
 #include "tables.h"
 #include "tables_pack.h"
@@ -340,6 +341,28 @@ namespace dflo
       }
    }
 
+   // thread-per-cell stage kernel of the Pk basis (cell_stage.cuh)
+   template <class BK, int N1>
+   void launch_cell_stage_n (BK &bk, int flux, const CellStageArgs &a)
+   {
+      switch (flux)
+      {
+         case FLUX_LXF: bk.template launch<PkCellStageKernel<N1, FLUX_LXF>> (PkCellStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+         case FLUX_SW: bk.template launch<PkCellStageKernel<N1, FLUX_SW>> (PkCellStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+         case FLUX_KFVS: bk.template launch<PkCellStageKernel<N1, FLUX_KFVS>> (PkCellStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+         case FLUX_ROE: bk.template launch<PkCellStageKernel<N1, FLUX_ROE>> (PkCellStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+         case FLUX_KEP: bk.template launch<PkCellStageKernel<N1, FLUX_KEP>> (PkCellStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+         default: bk.template launch<PkCellStageKernel<N1, FLUX_HLLC>> (PkCellStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+      }
+   }
+   template <class BK>
+   void launch_cell_stage (BK &bk, int n1, int flux, const CellStageArgs &a)
+   {
+      if (n1 == 2) launch_cell_stage_n<BK, 2> (bk, flux, a);
+      else if (n1 == 3) launch_cell_stage_n<BK, 3> (bk, flux, a);
+      else launch_cell_stage_n<BK, 4> (bk, flux, a);
+   }
+
    template <class BK>
    void launch_limiter (BK &bk, int basis, int n1, const LimiterArgs &a)
    {
@@ -478,7 +501,7 @@ namespace dflo
          const bool row = bk.use_row_kernel (tab.basis, tab.n1);
          const int tx = row ? row_tx (tab.n1) : tile_nx (tab.n1), ty = row ? row_ty (tab.n1) : tile_ny (tab.n1);
          if (!build_local_mesh (mesh, rank, world, layers, tx, ty, lm, e, row)) return fail (DFLO_E_INVALID, e);
-         bk.prepare_tables (tab);
+         bk.prepare_tables (tab, pack_stage_tables (tab));
          if (row) d_rowdesc = upload (lm.rowdesc);
          n_global_bfaces = mesh.n_boundary_faces;
 
@@ -731,7 +754,7 @@ namespace dflo
          StageArgs a = stage_args (0, MODE_RHS);
          a.out = rhs;
          if (fused_halo ()) a.fx = bk.p2p_fused_args (cur); // waits for the last fused exchange, publishes nothing
-         launch_stage (bk, tab.basis, tab.n1, prm.flux_type, lm.n_tiles_owned, a);
+         run_stage (a, true);
          return bk.check (error);
       }
 
@@ -848,7 +871,7 @@ namespace dflo
          {
             if (scratch) bk.zero (scratch, flush_bytes);
             bk.timer_start ();
-            launch_stage (bk, tab.basis, tab.n1, prm.flux_type, lm.n_tiles, a);
+            run_stage (a, false);
             bk.timer_stop ();
             total += bk.timer_ms ();
          }
@@ -907,6 +930,40 @@ namespace dflo
          for (int i = 0; i < 3; ++i)
             if (i != cur && i != old) return i;
          return 0;
+      }
+
+      // the stage kernel in the form that fits the basis: thread-per-cell for Pk (cell_stage.cuh), row kernel
+      // for Qk on the device, else the tile kernel.  owned_only: right-hand side of the owned cells only.
+      void run_stage (const StageArgs &a, bool owned_only)
+      {
+         if (tab.basis == BASIS_PK && tab.n1 >= 2 && bk.use_pk_cell_kernel ())
+         {
+            CellStageArgs c;
+            c.u = a.u;
+            c.u_old = a.u_old;
+            c.out = a.out;
+            c.avg = a.avg;
+            c.avg_out = a.avg_out;
+            c.nbr = d_nbr;
+            c.fflags = d_fflags;
+            c.geom = a.geom;
+            c.bc_g = a.bc_g;
+            c.bkind = a.bkind;
+            c.tab = a.tab;
+            c.time = a.time;
+            c.dt_cell = a.dt_cell;
+            c.ext_force = a.ext_force;
+            c.n_compute = owned_only ? lm.n_owned : lm.n_compute;
+            c.n_keep = lm.n_owned;
+            c.mode = a.mode;
+            c.compat_mpi = a.compat_mpi;
+            c.ark = a.ark;
+            c.gravity = a.gravity;
+            bk.note_cell_stage ();
+            launch_cell_stage (bk, tab.n1, prm.flux_type, c);
+            return;
+         }
+         launch_stage (bk, tab.basis, tab.n1, prm.flux_type, owned_only ? lm.n_tiles_owned : lm.n_tiles, a);
       }
 
       StageArgs stage_args (int rk, int mode)
@@ -1043,7 +1100,7 @@ namespace dflo
          a.avg_out = AVG[out];
          const bool fused = fused_halo ();
          if (fused) a.fx = bk.p2p_fused_args (out);
-         launch_stage (bk, tab.basis, tab.n1, prm.flux_type, lm.n_tiles, a);
+         run_stage (a, false);
          if (tvb () || pos ())
          {
             LimiterArgs l = limiter_args (out);

@@ -277,8 +277,14 @@ namespace
       }
       bool use_row_kernel (int basis, int n1) const { return row_kernel && basis == dflo::BASIS_QK && n1 >= 2; }
       // 1-D tables of the row kernel as constant-bank operands
-      void prepare_tables (const dflo::FeTables &t)
+      void prepare_tables (const dflo::FeTables &t, const std::vector<double> &flat)
       {
+         if (t.basis == dflo::BASIS_PK && t.n1 >= 2 && t.n1 <= 4) // thread-per-cell Pk stage kernel: the flat stage table
+         {
+            note (cudaMemcpyToSymbolAsync (dflo::c_pk_tab, flat.data (), flat.size () * sizeof (double),
+                                           (size_t) t.n1 * dflo::PK_TAB_MAX * sizeof (double), cudaMemcpyHostToDevice, stream));
+            note (cudaStreamSynchronize (stream));
+         }
          if (t.basis != dflo::BASIS_QK) return;
          dflo::RowConst rc;
          std::memset (&rc, 0, sizeof (rc));
@@ -332,6 +338,13 @@ namespace
          dflo::stage_persistent_kernel<K><<<grid, K::THREADS + 32, smem, stream>>> (a, n_tiles);
          note (cudaPeekAtLastError ());
       }
+      // thread-per-cell Pk stage kernel (cell_stage.cuh); DFLO_B200_PK=tile selects the tile kernel
+      bool use_pk_cell_kernel () const
+      {
+         static const char *e = std::getenv ("DFLO_B200_PK");
+         return !(e && std::string (e) == "tile");
+      }
+      void note_cell_stage () {}
       template <class K> void launch1d (int n, const typename K::Args &a)
       {
          if (n <= 0) return;

@@ -25,6 +25,11 @@ namespace
       std::map<int, std::vector<Pending>> recv_plan;
       bool halo_pending = false;
 
+      static int64_t &cell_stage_launches ()
+      {
+         static int64_t n = 0;
+         return n;
+      }
       int open (int, int r, int w, const void *, std::string &)
       {
          rank = r;
@@ -63,7 +68,10 @@ namespace
       template <class K> void launch_stage (int n_tiles, const typename K::Args &a) { launch<K> (n_tiles, a); }
       // the register-blocked Qk kernel exists only as CUDA code; the emulation runs the phase kernel
       bool use_row_kernel (int, int) const { return false; }
-      void prepare_tables (const dflo::FeTables &) {}
+      void prepare_tables (const dflo::FeTables &, const std::vector<double> &) {}
+      // thread-per-cell Pk stage kernel (cell_stage.cuh): DFLO_EMU_PK=cell; default: the tile kernel
+      bool use_pk_cell_kernel () const { const char *e = std::getenv ("DFLO_EMU_PK"); return e && std::string (e) == "cell"; }
+      void note_cell_stage () { ++cell_stage_launches (); }
       int stage_prefetch_tiles () const { return 0; }
       int debug_flags () const { return 0; }
       bool limiter_block_form () const { static const char *e = std::getenv ("DFLO_EMU_LIMITER"); return e && std::string (e) == "block"; }
@@ -123,6 +131,7 @@ void dflo_emu_halo_put_recv (dflo_emu_ctx *c, int peer, const double *in)
    }
    c->eng.bk.recv_plan.erase (peer);
 }
+int64_t dflo_emu_cell_stage_launches (void) { return EmuBackend::cell_stage_launches (); }
 int dflo_emu_n_peers (dflo_emu_ctx *c) { return c->eng.lm.peers.size (); }
 int dflo_emu_peer_rank (dflo_emu_ctx *c, int i) { return c->eng.lm.peers[i].rank; }
 int dflo_emu_n_local (dflo_emu_ctx *c) { return c->eng.lm.n_local; }

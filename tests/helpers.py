@@ -31,7 +31,7 @@ def build_emu():
     src = [os.path.join(EMU_DIR, "emu_backend.cc")] + [os.path.join(ROOT, "dflo_b200", "csrc", f)
                                                        for f in ("tables.cc", "host/mesh.cc", "host/host_abi.cc")]
     deps = src + [os.path.join(ROOT, "dflo_b200", "csrc", f) for f in
-                  ("kernels.cuh", "euler.cuh", "engine_core.h", "abi_impl.h", "partition.h", "expr.h", "tables.h",
+                  ("kernels.cuh", "cell_stage.cuh", "euler.cuh", "engine_core.h", "abi_impl.h", "partition.h", "expr.h", "tables.h",
                    "tables_pack.h")]
     if os.path.exists(EMU_LIB) and all(os.path.getmtime(EMU_LIB) >= os.path.getmtime(d) for d in deps):
         return EMU_LIB

@@ -3,11 +3,14 @@ engine_core.h, partition.h), compiled for the host by tests/emu and run thread b
 the CPU oracle.  Same cases and tolerances as the GPU tier (tests/test_gpu_parity.py); this tier
 exists so index arithmetic, buffer rotation, limiter logic and halo lists are proven before GPU
 time is spent.  It never stands in for the CUDA library: the GPU tier calls libdflo_b200.so only."""
+import ctypes
+
 import numpy as np
 import pytest
 
 from cases import ALL_FLUXES, BASELINE_SMALL, BASES, TOL_RHS, TOL_STEP_SHOCK, TOL_STEP_SMOOTH
-from helpers import (DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, Case, ic_dmr, ic_pulse, ic_smooth, ic_sod, ic_step, ic_vortex)
+from helpers import (DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, Case, emu_lib, ic_dmr, ic_pulse, ic_smooth, ic_sod, ic_step,
+                     ic_vortex)
 
 
 def _rhs_ok(c):
@@ -257,3 +260,59 @@ def test_external_force_mpi(basis, k, flux):
     c.step()
     assert c.rel_err() <= TOL_STEP_SMOOTH
     c.close()
+
+
+@pytest.fixture
+def pk_cell_kernel(monkeypatch):
+    """Selects the thread-per-cell Pk stage kernel (dflo_b200/csrc/cell_stage.cuh, the default on the device) in the
+    CPU emulation, whose default is the tile kernel."""
+    monkeypatch.setenv("DFLO_EMU_PK", "cell")
+    L = emu_lib()
+    L.dflo_emu_cell_stage_launches.restype = ctypes.c_int64
+    before = L.dflo_emu_cell_stage_launches()
+    yield
+    assert L.dflo_emu_cell_stage_launches() > before, "the cell stage kernel did not run"
+
+
+@pytest.mark.parametrize("flux", ALL_FLUXES)
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_pk_cell_kernel_rhs_and_step_periodic(pk_cell_kernel, k, flux):
+    c = Case(("isentropic_vortex", [6]), PERIODIC_BOX, ic_vortex, basis="Pk", degree=k, flux=flux, cfl=0.5)
+    _rhs_ok(c)
+    c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+@pytest.mark.parametrize("compat", ["src", "mpi"])
+def test_pk_cell_kernel_boundaries_gravity_external_force(pk_cell_kernel, compat):
+    bc = {1: "inflow", 2: "slip", 3: "pressure", 0: "farfield"}
+    c = Case(("forward_step", [0.2]), bc, ic_smooth, basis="Pk", degree=2, flux="lxf", cfl=0.5, compat=compat, gravity=0.7)
+    c.set_boundary(values=(0.5, 0.1, 1.2, 3.0), wiggle=0.1)
+    _rhs_ok(c)
+    if compat == "mpi":
+        c.set_external_force("0.3*sin(2*x)+y", "-1.0+0.2*x*y", lambda x, y: (0.3 * np.sin(2 * x) + y, -1.0 + 0.2 * x * y))
+        _rhs_ok(c)
+    c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_pk_cell_kernel_sod_tvb_positivity_sharded(pk_cell_kernel, world):
+    """cfg3 in small: P2, HLLC, TVB + positivity; the sharded runs (2-layer halo, ghost layer 1 updated
+    redundantly by the cell kernel, means only) equal the single run bit for bit."""
+    prm = dict(basis="Pk", degree=2, flux="hllc", limiter="TVB", char_lim=True, pos_lim=True, M=0.0, beta=2.0, cfl=0.5)
+    one = Case(("sod_tube", [18, 3]), SOD_BC, ic_sod, **prm)
+    many = Case(("sod_tube", [18, 3]), SOD_BC, ic_sod, world=world, **prm)
+    for c in (one, many):
+        c.set_boundary(values=(0.0, 0.0, 1.0, 2.5))
+        c.limit_initial()
+    flips = 0
+    for _ in range(2):
+        one.step()
+        flips += many.step()[0]
+    assert np.array_equal(one.solution(), many.solution())
+    assert many.rel_err() <= TOL_STEP_SHOCK and flips == 0
+    one.close()
+    many.close()
