@@ -358,9 +358,9 @@ namespace dflo
    template <class BK>
    void launch_cell_stage (BK &bk, int n1, int flux, const CellStageArgs &a)
    {
+      // P1 and P2; P3 (40 coefficients + 40 residuals per thread) does not fit the register file and stays on the tile kernel
       if (n1 == 2) launch_cell_stage_n<BK, 2> (bk, flux, a);
-      else if (n1 == 3) launch_cell_stage_n<BK, 3> (bk, flux, a);
-      else launch_cell_stage_n<BK, 4> (bk, flux, a);
+      else launch_cell_stage_n<BK, 3> (bk, flux, a);
    }
 
    template <class BK>
@@ -932,11 +932,12 @@ namespace dflo
          return 0;
       }
 
-      // the stage kernel in the form that fits the basis: thread-per-cell for Pk (cell_stage.cuh), row kernel
+      // the stage kernel in the form that fits the basis: thread-per-cell for P1 / P2 (cell_stage.cuh; measured on
+      // B200, 512 x 512 cells HLLC: P1 62 us against 127 us for the tile kernel, P2 136 / 216, P3 1101 / 487), row kernel
       // for Qk on the device, else the tile kernel.  owned_only: right-hand side of the owned cells only.
       void run_stage (const StageArgs &a, bool owned_only)
       {
-         if (tab.basis == BASIS_PK && tab.n1 >= 2 && bk.use_pk_cell_kernel ())
+         if (tab.basis == BASIS_PK && tab.n1 >= 2 && tab.n1 <= 3 && bk.use_pk_cell_kernel ())
          {
             CellStageArgs c;
             c.u = a.u;

@@ -279,7 +279,7 @@ namespace
       // 1-D tables of the row kernel as constant-bank operands
       void prepare_tables (const dflo::FeTables &t, const std::vector<double> &flat)
       {
-         if (t.basis == dflo::BASIS_PK && t.n1 >= 2 && t.n1 <= 4) // thread-per-cell Pk stage kernel: the flat stage table
+         if (t.basis == dflo::BASIS_PK && t.n1 >= 2 && t.n1 <= 3) // thread-per-cell Pk stage kernel: the flat stage table
          {
             note (cudaMemcpyToSymbolAsync (dflo::c_pk_tab, flat.data (), flat.size () * sizeof (double),
                                            (size_t) t.n1 * dflo::PK_TAB_MAX * sizeof (double), cudaMemcpyHostToDevice, stream));
