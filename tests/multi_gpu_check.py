@@ -20,7 +20,7 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))
 
 from dflo_b200 import abi  # noqa: E402
-from helpers import DMR_BC, PERIODIC_BOX, SOD_BC, ic_dmr, ic_sod, ic_sod_moving, ic_vortex  # noqa: E402
+from helpers import DMR_BC, PERIODIC_BOX, SOD_BC, ic_dmr, ic_sod, ic_sod_moving, ic_sod_moving_wavy, ic_vortex  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 CASES = [
@@ -35,6 +35,9 @@ CASES = [
     ("sod_Q2_kxrcf_density", ("sod_tube", [100, 10]), {0: "outflow", 1: "outflow", 2: "inflow"}, ic_sod_moving,
      dict(basis="Qk", degree=2, flux="hllc", limiter="TVB", char_lim=True, beta=2.0, M=0.0, cfl=0.5, shock_indicator="density"),
      (0.3, 0.1, 1.0, 2.55), 3, 1e-9),
+    ("sod_Q2_minmax_pos", ("sod_tube", [100, 10]), SOD_BC, ic_sod_moving_wavy,
+     dict(basis="Qk", degree=2, flux="hllc", limiter="minmax", char_lim=True, pos_lim=True, beta=2.0, M=0.0, cfl=0.4),
+     (0.3, 0.1, 1.0, 2.5), 3, 1e-9),
 ]
 
 
