@@ -127,6 +127,9 @@ def _declare_host(L):
     L.dflo_mesh_flat.restype = ctypes.POINTER(FlatMesh)
     L.dflo_mesh_flat.argtypes = [ctypes.c_void_p]
     L.dflo_expr_eval.argtypes = [ctypes.c_char_p, ctypes.c_int, c_double_p, c_double_p, ctypes.c_double, c_double_p]
+    L.dflo_host_write_solution_vtu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_size_t,
+                                               ctypes.c_int, ctypes.c_double, ctypes.c_uint, ctypes.c_char_p]
+    L.dflo_host_write_shock_vtu.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_char_p]
 
 
 def _declare_engine(L, prefix):
@@ -233,6 +236,22 @@ class Mesh:
             raise DfloError(rc, self.L.dflo_host_last_error().decode())
         self.flat = self.L.dflo_mesh_flat(self.h)
         return self.flat
+
+    def write_solution_vtu(self, path, u, basis, degree, schlieren_plot=False, time=0.0, cycle=0):
+        """output_results on a host copy of the solution (src/output.cc:33-68); basis: "Qk" | "Pk"."""
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        rc = self.L.dflo_host_write_solution_vtu(self.h, {"Qk": 0, "Pk": 1}[basis], degree, _dp(u), u.size,
+                                                 int(schlieren_plot), time, cycle, path.encode())
+        if rc:
+            raise DfloError(rc, self.L.dflo_host_last_error().decode())
+
+    def write_shock_vtu(self, path, shock_indicator, mu_shock=None):
+        """shock.vtu of src/output.cc:70-79."""
+        s = np.ascontiguousarray(shock_indicator, dtype=np.float64)
+        mu = None if mu_shock is None else np.ascontiguousarray(mu_shock, dtype=np.float64)
+        rc = self.L.dflo_host_write_shock_vtu(self.h, None if mu is None else _dp(mu), _dp(s), path.encode())
+        if rc:
+            raise DfloError(rc, self.L.dflo_host_last_error().decode())
 
     def flat_arrays(self):
         fm = self.flat.contents

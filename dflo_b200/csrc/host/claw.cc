@@ -4,6 +4,7 @@
 #include "../expr.h"
 #include "host_error.h"
 #include "mesh_handle.h"
+#include "output.h"
 
 #include <cmath>
 #include <cstdio>
@@ -245,6 +246,8 @@ namespace dflo
       if (rc) error = dflo_b200_last_error (ctx);
       elapsed_time = 0.0;
       time_iter = 0;
+      next_output_time = parameters.output_time_step; // src/claw.cc:1016-1017
+      next_output_iter = parameters.output_iter_step;
       return rc;
    }
 
@@ -281,6 +284,11 @@ namespace dflo
    {
       if (!ctx) return DFLO_E_INVALID;
       int steps = 0;
+      if (output_enabled && time_iter == 0 && output_file_number == 0) // initial solution, src/claw.cc:1010
+      {
+         const int rc = output_results (output_dir);
+         if (rc) return rc;
+      }
       while (elapsed_time < parameters.final_time && (max_steps < 0 || steps < max_steps))
       {
          int rc;
@@ -317,6 +325,15 @@ namespace dflo
          }
          ++time_iter;
          ++steps;
+         // "Save solution for visualization", src/claw.cc:1093-1099
+         if (output_enabled && (elapsed_time >= next_output_time || time_iter == next_output_iter
+                                || std::fabs (elapsed_time - parameters.final_time) < 1.0e-13))
+         {
+            rc = output_results (output_dir);
+            if (rc) return rc;
+            next_output_time = elapsed_time + parameters.output_time_step;
+            next_output_iter = time_iter + parameters.output_iter_step;
+         }
       }
       return DFLO_OK;
    }
@@ -327,75 +344,49 @@ namespace dflo
       return dflo_b200_get_solution (ctx, u.data (), nullptr, u.size ());
    }
 
-   // output_results (src/output.cc:33-87): one VTK quad per cell and Gauss sub-cell, point data
-   // named like the reference's (XMomentum YMomentum Density Energy + derived XVelocity YVelocity
-   // Pressure, src/equation.cc:59-187).  Values are the DG polynomial evaluated at the cell corners.
-   int ConservationLaw::output_results (const std::string &path)
+   // output_results (src/output.cc:33-87): host copy of current_solution -> VTU (host/output.cc).
+   // path: a file name, or "" / "dir/" for the reference's own numbering solution-NNN.vtu (output.cc:47-49,
+   // "Writing file ..." line included) plus shock.vtu with mu_shock and shock_indicator (output.cc:70-79).
+   int ConservationLaw::output_results (const std::string &path_in)
    {
       std::vector<double> u;
       const int rc = get_solution (u);
       if (rc) return rc;
-      FILE *fp = std::fopen (path.c_str (), "w");
-      if (!fp) return DFLO_E_INVALID;
-      const int nc = flat.n_cells (), ns = tab.ns, D = tab.D, n1 = tab.n1;
-      // corner values: Qk through the end-point Lagrange values, Pk through the face tables
-      std::vector<double> val ((size_t) nc * 4 * 4);
-      const double cx[4] = {0, 1, 1, 0}, cy[4] = {0, 0, 1, 1};
-      for (int cell = 0; cell < nc; ++cell)
-         for (int v = 0; v < 4; ++v)
-            for (int c = 0; c < 4; ++c)
-            {
-               double s = 0.0;
-               const double *uc = &u[(size_t) cell * D + c * ns];
-               if (tab.basis == BASIS_QK)
-               {
-                  for (int b = 0; b < n1; ++b)
-                     for (int a = 0; a < n1; ++a) s += tab.e[(int) cx[v]][a] * tab.e[(int) cy[v]][b] * uc[a + n1 * b];
-               }
-               else
-               {
-                  for (int m = 0; m < ns; ++m)
-                  {
-                     // orthonormal Legendre at the end points: sqrt(2i+1) (+-1)^i
-                     const double lx = std::sqrt (2.0 * tab.px[m] + 1.0) * ((cx[v] == 0 && tab.px[m] % 2) ? -1.0 : 1.0);
-                     const double ly = std::sqrt (2.0 * tab.py[m] + 1.0) * ((cy[v] == 0 && tab.py[m] % 2) ? -1.0 : 1.0);
-                     s += lx * ly * uc[m];
-                  }
-               }
-               val[((size_t) cell * 4 + v) * 4 + c] = s;
-            }
-      std::fprintf (fp, "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n"
-                        "<UnstructuredGrid>\n<Piece NumberOfPoints=\"%d\" NumberOfCells=\"%d\">\n<Points>\n"
-                        "<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n", 4 * nc, nc);
-      for (int cell = 0; cell < nc; ++cell)
-         for (int v = 0; v < 4; ++v)
-            std::fprintf (fp, "%.10g %.10g 0\n", flat.origin[2 * cell] + cx[v] * flat.size[2 * cell],
-                          flat.origin[2 * cell + 1] + cy[v] * flat.size[2 * cell + 1]);
-      std::fprintf (fp, "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int32\" Name=\"connectivity\" format=\"ascii\">\n");
-      for (int i = 0; i < 4 * nc; ++i) std::fprintf (fp, "%d%c", i, (i % 4 == 3) ? '\n' : ' ');
-      std::fprintf (fp, "</DataArray>\n<DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">\n");
-      for (int i = 1; i <= nc; ++i) std::fprintf (fp, "%d\n", 4 * i);
-      std::fprintf (fp, "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n");
-      for (int i = 0; i < nc; ++i) std::fprintf (fp, "9\n");
-      std::fprintf (fp, "</DataArray>\n</Cells>\n<PointData>\n");
-      const char *names[7] = {"XMomentum", "YMomentum", "Density", "Energy", "XVelocity", "YVelocity", "Pressure"};
-      for (int k = 0; k < 7; ++k)
+      std::string path = path_in, dir;
+      const bool numbered = path.empty () || path.back () == '/';
+      if (numbered)
       {
-         std::fprintf (fp, "<DataArray type=\"Float64\" Name=\"%s\" format=\"ascii\">\n", names[k]);
-         for (size_t p = 0; p < (size_t) nc * 4; ++p)
-         {
-            const double *w = &val[p * 4];
-            double v = 0.0;
-            if (k < 4) v = w[k];
-            else if (k == 4) v = w[0] / w[2];
-            else if (k == 5) v = w[1] / w[2];
-            else v = 0.4 * (w[3] - 0.5 * (w[0] * w[0] + w[1] * w[1]) / w[2]);
-            std::fprintf (fp, "%.10g\n", v);
-         }
-         std::fprintf (fp, "</DataArray>\n");
+         dir = path;
+         char name[64];
+         std::snprintf (name, sizeof (name), "solution-%03u.vtu", output_file_number);
+         path = dir + name;
+         std::printf ("Writing file %s\n", path.c_str ());
       }
-      std::fprintf (fp, "</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
-      std::fclose (fp);
+      if (!write_solution_vtu (tab, flat, u.data (), parameters.schlieren_plot, elapsed_time, output_file_number, path))
+      {
+         error = "cannot write " + path;
+         return DFLO_E_INVALID;
+      }
+      if (numbered)
+      {
+         ++output_file_number;
+         return write_shock_file (dir + "shock.vtu");
+      }
+      return DFLO_OK;
+   }
+
+   // "Write shock indicator", src/output.cc:70-79.  mu_shock is the shock-capturing viscosity of the implicit
+   // path (zero on the explicit path); shock_indicator is the one of the last stage.
+   int ConservationLaw::write_shock_file (const std::string &path)
+   {
+      std::vector<double> ind ((size_t) flat.n_cells (), 0.0);
+      const int rc = dflo_b200_get_shock_indicator (ctx, ind.data ());
+      if (rc) return rc;
+      if (!write_shock_vtu (flat, nullptr, ind.data (), path))
+      {
+         error = "cannot write " + path;
+         return DFLO_E_INVALID;
+      }
       return DFLO_OK;
    }
 }
@@ -489,5 +480,16 @@ int dflo_claw_get_solution (dflo_claw *c, double *u, size_t n)
 {
    return dflo_b200_get_solution (c->claw->ctx, u, nullptr, n);
 }
-int dflo_claw_write_vtu (dflo_claw *c, const char *path) { return c->claw->output_results (path); }
+int dflo_claw_write_vtu (dflo_claw *c, const char *path)
+{
+   const int rc = c->claw->output_results (path ? path : "");
+   if (rc) dflo::host_error () = c->claw->error;
+   return rc;
+}
+void dflo_claw_set_output (dflo_claw *c, const char *dir)
+{
+   c->claw->output_enabled = dir != nullptr;
+   c->claw->output_dir = dir ? dir : "";
+   if (!c->claw->output_dir.empty () && c->claw->output_dir.back () != '/') c->claw->output_dir += '/';
+}
 }

@@ -34,7 +34,15 @@ namespace dflo
 
       void set_initial_condition (std::vector<double> &u) const;   // src/ic.cc:104-182
       int get_solution (std::vector<double> &u);
-      int output_results (const std::string &path);                // src/output.cc (VTU)
+      int output_results (const std::string &path);                // src/output.cc:33-68 (VTU; "" or "dir/": solution-NNN.vtu + shock.vtu)
+      int write_shock_file (const std::string &path);              // src/output.cc:70-79
+      unsigned int output_file_number = 0;                         // the static counter of output.cc:47
+      // run() writes the initial solution and then follows "output: time step / iter step" (src/claw.cc:1010-1017,
+      // 1093-1099) into output_dir ("" = working directory like the reference) when enabled
+      bool output_enabled = false;
+      std::string output_dir;
+      double next_output_time = 0.0;
+      int next_output_iter = 0;
 
       Parameters::AllParameters parameters;
       dflo_params engine_params;

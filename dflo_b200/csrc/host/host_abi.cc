@@ -4,6 +4,8 @@
 #include "host_error.h"
 #include "mesh.h"
 #include "mesh_handle.h"
+#include "output.h"
+#include "../tables.h"
 
 #include <cstring>
 #include <string>
@@ -108,6 +110,33 @@ int dflo_expr_eval (const char *expr, int n, const double *x, const double *y, d
       return DFLO_E_EXPR;
    }
    for (int i = 0; i < n; ++i) out[i] = dflo::expr_eval (code.data (), (int) code.size (), x[i], y[i], t);
+   return DFLO_OK;
+}
+
+int dflo_host_write_solution_vtu (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, int schlieren_plot,
+                                  double time, unsigned int cycle, const char *path)
+{
+   dflo::FeTables tab;
+   if (!m || !m->flattened || !u || !path || !dflo::build_tables (basis, degree, tab) || n != (size_t) m->flat.n_cells () * tab.D)
+   {
+      dflo::host_error () = "write_solution_vtu: mesh not flattened, unsupported element or wrong vector length";
+      return DFLO_E_INVALID;
+   }
+   if (!dflo::write_solution_vtu (tab, m->flat, u, schlieren_plot != 0, time, cycle, path))
+   {
+      dflo::host_error () = std::string ("cannot write ") + path;
+      return DFLO_E_INVALID;
+   }
+   return DFLO_OK;
+}
+
+int dflo_host_write_shock_vtu (const dflo_mesh *m, const double *mu_shock, const double *shock_indicator, const char *path)
+{
+   if (!m || !m->flattened || !shock_indicator || !path || !dflo::write_shock_vtu (m->flat, mu_shock, shock_indicator, path))
+   {
+      dflo::host_error () = "write_shock_vtu: mesh not flattened or file not writable";
+      return DFLO_E_INVALID;
+   }
    return DFLO_OK;
 }
 }

@@ -1,7 +1,9 @@
 // dflo_b200: standalone driver with dflo's command line (reference src/main.cc:13-81):
-//     dflo_b200 input.prm [--mesh "<generator> <args>"] [--steps N] [--compat src|mpi] [--vtu out.vtu] [--quiet]
+//     dflo_b200 input.prm [--mesh "<generator> <args>"] [--steps N] [--compat src|mpi] [--vtu out.vtu] [--output-dir DIR] [--quiet]
 // Reads the same input.prm, prints the same per-step lines (src/claw.cc:1031-1041, 768) and runs
-// the explicit RK stages on GPU 0 through the C ABI.
+// the explicit RK stages on GPU 0 through the C ABI.  --output-dir DIR turns on the reference's output schedule
+// (initial solution, "output: time step / iter step", final time; solution-NNN.vtu + shock.vtu, src/output.cc)
+// with the files going to DIR ("." = the working directory, which is where the reference writes).
 #include "../../../include/dflo_host.h"
 
 #include <chrono>
@@ -14,10 +16,11 @@ int main (int argc, char **argv)
 {
    if (argc < 2)
    {
-      std::fprintf (stderr, "usage: %s input.prm [--mesh \"kind args\"] [--steps N] [--compat src|mpi] [--vtu file] [--quiet]\n", argv[0]);
+      std::fprintf (stderr, "usage: %s input.prm [--mesh \"kind args\"] [--steps N] [--compat src|mpi] [--vtu file] [--output-dir DIR] [--quiet]\n", argv[0]);
       return 1;
    }
-   std::string mesh, vtu;
+   std::string mesh, vtu, outdir;
+   bool output = false;
    int steps = -1, compat = DFLO_COMPAT_SRC, verbose = 1;
    for (int i = 2; i < argc; ++i)
    {
@@ -25,6 +28,11 @@ int main (int argc, char **argv)
       else if (!std::strcmp (argv[i], "--steps") && i + 1 < argc) steps = std::atoi (argv[++i]);
       else if (!std::strcmp (argv[i], "--compat") && i + 1 < argc) compat = std::strcmp (argv[++i], "mpi") ? DFLO_COMPAT_SRC : DFLO_COMPAT_MPI;
       else if (!std::strcmp (argv[i], "--vtu") && i + 1 < argc) vtu = argv[++i];
+      else if (!std::strcmp (argv[i], "--output-dir") && i + 1 < argc)
+      {
+         output = true;
+         outdir = argv[++i];
+      }
       else if (!std::strcmp (argv[i], "--quiet")) verbose = 0;
    }
    const auto t0 = std::chrono::steady_clock::now ();
@@ -35,6 +43,7 @@ int main (int argc, char **argv)
                             "----------------------------------------------------\n", dflo_host_last_error ());
       return 1;
    }
+   if (output) dflo_claw_set_output (claw, outdir == "." ? "" : outdir.c_str ());
    int rc = dflo_claw_setup (claw, 0, 0, 1, nullptr);
    double t = 0.0;
    int done = 0;

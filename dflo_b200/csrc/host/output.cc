@@ -1,0 +1,136 @@
+// VTU writers, see output.h.  ASCII data arrays (%.10g); file structure follows what deal.II's DataOut writes
+// for a discontinuous field: no vertex is shared between cells.
+#include "output.h"
+
+#include <cstdio>
+#include <vector>
+
+namespace dflo
+{
+   namespace
+   {
+      const double gas_gamma = 1.4; // src/equation.cc:33
+
+      void vtu_head (FILE *fp, int n_points, int n_cells, double time, unsigned int cycle, bool with_flags)
+      {
+         std::fprintf (fp, "<?xml version=\"1.0\"?>\n");
+         if (with_flags) std::fprintf (fp, "<!-- time %.16g cycle %u -->\n", time, cycle); // DataOutBase::VtkFlags (time, cycle)
+         std::fprintf (fp, "<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n"
+                           "<Piece NumberOfPoints=\"%d\" NumberOfCells=\"%d\">\n<Points>\n"
+                           "<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n", n_points, n_cells);
+      }
+
+      // nsub x nsub quads on the (nsub+1)^2 lexicographic points of every cell
+      void vtu_cells (FILE *fp, int nc, int nsub)
+      {
+         const int np1 = nsub + 1, npc = np1 * np1, n_out = nc * nsub * nsub;
+         std::fprintf (fp, "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int32\" Name=\"connectivity\" format=\"ascii\">\n");
+         for (int cell = 0; cell < nc; ++cell)
+            for (int j = 0; j < nsub; ++j)
+               for (int i = 0; i < nsub; ++i)
+               {
+                  const int p0 = cell * npc + i + np1 * j;
+                  std::fprintf (fp, "%d %d %d %d\n", p0, p0 + 1, p0 + 1 + np1, p0 + np1);
+               }
+         std::fprintf (fp, "</DataArray>\n<DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">\n");
+         for (int i = 1; i <= n_out; ++i) std::fprintf (fp, "%d\n", 4 * i);
+         std::fprintf (fp, "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n");
+         for (int i = 0; i < n_out; ++i) std::fprintf (fp, "9\n");
+         std::fprintf (fp, "</DataArray>\n</Cells>\n");
+      }
+
+      void vtu_points (FILE *fp, const FlatMesh &flat, int nsub)
+      {
+         for (int cell = 0; cell < flat.n_cells (); ++cell)
+            for (int j = 0; j <= nsub; ++j)
+               for (int i = 0; i <= nsub; ++i)
+                  std::fprintf (fp, "%.10g %.10g 0\n", flat.origin[2 * cell] + (double) i / nsub * flat.size[2 * cell],
+                                flat.origin[2 * cell + 1] + (double) j / nsub * flat.size[2 * cell + 1]);
+      }
+   }
+
+   bool write_solution_vtu (const FeTables &tab, const FlatMesh &flat, const double *u, bool schlieren_plot, double time,
+                            unsigned int cycle, const std::string &path)
+   {
+      FILE *fp = std::fopen (path.c_str (), "w");
+      if (!fp) return false;
+      const int nc = flat.n_cells (), ns = tab.ns, D = tab.D;
+      const int nsub = tab.k > 0 ? tab.k : 1, np1 = nsub + 1, npc = np1 * np1;
+      // basis values and unit-cell gradients at the equispaced patch vertices
+      std::vector<double> phi ((size_t) npc * ns), dpx ((size_t) npc * ns), dpy ((size_t) npc * ns);
+      for (int j = 0; j < np1; ++j)
+         for (int i = 0; i < np1; ++i)
+         {
+            const size_t v = (size_t) (i + np1 * j) * ns;
+            eval_basis (tab, (double) i / nsub, (double) j / nsub, &phi[v], &dpx[v], &dpy[v]);
+         }
+      std::vector<double> val ((size_t) nc * npc * 4), schl (schlieren_plot ? (size_t) nc * npc : 0);
+      for (int cell = 0; cell < nc; ++cell)
+         for (int v = 0; v < npc; ++v)
+         {
+            const double *pv = &phi[(size_t) v * ns];
+            for (int c = 0; c < 4; ++c)
+            {
+               const double *uc = &u[(size_t) cell * D + c * ns];
+               double s = 0.0;
+               for (int m = 0; m < ns; ++m) s += pv[m] * uc[m];
+               val[((size_t) cell * npc + v) * 4 + c] = s;
+            }
+            if (schlieren_plot)
+            {
+               // duh[density] . duh[density] in real coordinates (src/equation.cc:122-124)
+               const double *ur = &u[(size_t) cell * D + 2 * ns];
+               double gx = 0.0, gy = 0.0;
+               for (int m = 0; m < ns; ++m)
+               {
+                  gx += dpx[(size_t) v * ns + m] * ur[m];
+                  gy += dpy[(size_t) v * ns + m] * ur[m];
+               }
+               gx /= flat.size[2 * cell];
+               gy /= flat.size[2 * cell + 1];
+               schl[(size_t) cell * npc + v] = gx * gx + gy * gy;
+            }
+         }
+      vtu_head (fp, npc * nc, nc * nsub * nsub, time, cycle, true);
+      vtu_points (fp, flat, nsub);
+      vtu_cells (fp, nc, nsub);
+      std::fprintf (fp, "<PointData>\n");
+      // component_names (src/equation.h) then Postprocessor::get_names (src/equation.cc:130-145)
+      const char *names[8] = {"XMomentum", "YMomentum", "Density", "Energy", "XVelocity", "YVelocity", "Pressure", "schlieren_plot"};
+      const int n_arrays = schlieren_plot ? 8 : 7;
+      for (int k = 0; k < n_arrays; ++k)
+      {
+         std::fprintf (fp, "<DataArray type=\"Float64\" Name=\"%s\" format=\"ascii\">\n", names[k]);
+         for (size_t p = 0; p < (size_t) nc * npc; ++p)
+         {
+            const double *w = &val[p * 4];
+            double v;
+            if (k < 4) v = w[k];
+            else if (k == 4) v = w[0] / w[2];
+            else if (k == 5) v = w[1] / w[2];
+            else if (k == 6) v = (gas_gamma - 1.0) * (w[3] - 0.5 * (w[0] * w[0] + w[1] * w[1]) / w[2]);
+            else v = schl[p];
+            std::fprintf (fp, "%.10g\n", v);
+         }
+         std::fprintf (fp, "</DataArray>\n");
+      }
+      std::fprintf (fp, "</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+      return std::fclose (fp) == 0;
+   }
+
+   bool write_shock_vtu (const FlatMesh &flat, const double *mu_shock, const double *shock_indicator, const std::string &path)
+   {
+      FILE *fp = std::fopen (path.c_str (), "w");
+      if (!fp) return false;
+      const int nc = flat.n_cells ();
+      vtu_head (fp, 4 * nc, nc, 0.0, 0, false);
+      vtu_points (fp, flat, 1);
+      vtu_cells (fp, nc, 1);
+      std::fprintf (fp, "<CellData>\n<DataArray type=\"Float64\" Name=\"mu_shock\" format=\"ascii\">\n");
+      for (int i = 0; i < nc; ++i) std::fprintf (fp, "%.10g\n", mu_shock ? mu_shock[i] : 0.0);
+      std::fprintf (fp, "</DataArray>\n<DataArray type=\"Float64\" Name=\"shock_indicator\" format=\"ascii\">\n");
+      for (int i = 0; i < nc; ++i) std::fprintf (fp, "%.10g\n", shock_indicator[i]);
+      std::fprintf (fp, "</DataArray>\n</CellData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+      return std::fclose (fp) == 0;
+   }
+}

@@ -212,4 +212,33 @@ namespace dflo
       t.D = 4 * t.ns;
       return true;
    }
+
+   // value and unit-cell gradient of every scalar basis function at a point of the unit square (output path:
+   // what DataOut::build_patches evaluates on its sub-cell vertices)
+   void eval_basis (const FeTables &t, double x, double y, double *phi, double *dphix, double *dphiy)
+   {
+      if (t.basis == BASIS_QK)
+      {
+         for (int b = 0; b < t.n1; ++b)
+            for (int a = 0; a < t.n1; ++a)
+            {
+               const double la = lagrange (t.gx, t.n1, a, x), lb = lagrange (t.gx, t.n1, b, y);
+               phi[a + t.n1 * b] = la * lb;
+               dphix[a + t.n1 * b] = lagrange_deriv (t.gx, t.n1, a, x) * lb;
+               dphiy[a + t.n1 * b] = la * lagrange_deriv (t.gx, t.n1, b, y);
+            }
+      }
+      else
+      {
+         for (int m = 0; m < t.ns; ++m)
+         {
+            double lx, dlx, ly, dly;
+            leg01 (t.px[m], x, lx, dlx);
+            leg01 (t.py[m], y, ly, dly);
+            phi[m] = lx * ly;
+            dphix[m] = dlx * ly;
+            dphiy[m] = lx * dly;
+         }
+      }
+   }
 }

@@ -39,4 +39,6 @@ namespace dflo
 
    // returns false if (basis, degree) is outside the supported range
    bool build_tables (int basis, int degree, FeTables &t);
+   // phi[ns], dphix[ns], dphiy[ns]: every scalar basis function and its unit-cell gradient at (x,y) in [0,1]^2
+   void eval_basis (const FeTables &t, double x, double y, double *phi, double *dphix, double *dphiy);
 }

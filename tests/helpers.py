@@ -29,10 +29,10 @@ _emu = None
 def build_emu():
     """g++ build of tests/emu (the product's kernel phase code on a CPU emulation backend)."""
     src = [os.path.join(EMU_DIR, "emu_backend.cc")] + [os.path.join(ROOT, "dflo_b200", "csrc", f)
-                                                       for f in ("tables.cc", "host/mesh.cc", "host/host_abi.cc")]
+                                                       for f in ("tables.cc", "host/mesh.cc", "host/output.cc", "host/host_abi.cc")]
     deps = src + [os.path.join(ROOT, "dflo_b200", "csrc", f) for f in
                   ("kernels.cuh", "cell_stage.cuh", "euler.cuh", "engine_core.h", "abi_impl.h", "partition.h", "expr.h", "tables.h",
-                   "tables_pack.h")]
+                   "tables_pack.h", "host/output.h", "host/mesh.h")]
     if os.path.exists(EMU_LIB) and all(os.path.getmtime(EMU_LIB) >= os.path.getmtime(d) for d in deps):
         return EMU_LIB
     os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)

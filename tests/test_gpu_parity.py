@@ -1,4 +1,6 @@
 """GPU tier: the CUDA library, called through the C ABI, against the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -304,3 +306,51 @@ def test_external_force_mpi(basis, k, flux):
     c.step()
     assert c.rel_err() <= TOL_STEP_SMOOTH
     c.close()
+
+
+def test_run_loop_output_schedule_and_vtu_files(tmp_path):
+    """ConservationLaw::run with output on (src/claw.cc:1010-1017, 1093-1099; src/output.cc:33-79): initial
+    solution, then every `output: iter step` steps, numbered solution-NNN.vtu + shock.vtu, each file equal to
+    the host writer applied to the engine's solution at that moment."""
+    import ctypes
+    import filecmp
+    from test_host import PRM_DIR, _claw_api, _read_vtu
+    L = _claw_api(abi.load_library())
+    L.dflo_claw_set_output.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    L.dflo_claw_set_output.restype = None
+    L.dflo_claw_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, abi.c_double_p, ctypes.POINTER(ctypes.c_int)]
+    L.dflo_claw_get_solution.argtypes = [ctypes.c_void_p, abi.c_double_p, ctypes.c_size_t]
+    L.dflo_claw_write_vtu.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    over = b"subsection output\n set iter step = 2\n set schlieren plot = true\nend\n"
+    h = L.dflo_claw_create(os.path.join(PRM_DIR, "cfg3_sod_P2_hllc_tvb_pos.prm").encode(), b"sod_tube 40 4", over, abi.COMPAT["src"])
+    assert h, L.dflo_host_last_error()
+    h = ctypes.c_void_p(h)
+    out = str(tmp_path) + "/"
+    L.dflo_claw_set_output(h, out.encode())
+    assert L.dflo_claw_setup(h, 0, 0, 1, None) == 0, L.dflo_host_last_error()
+    t, done = ctypes.c_double(0.0), ctypes.c_int(0)
+    assert L.dflo_claw_run(h, 5, 0, ctypes.byref(t), ctypes.byref(done)) == 0, L.dflo_host_last_error()
+    assert done.value == 5 and t.value > 0
+    files = sorted(os.listdir(out))
+    assert files == ["shock.vtu", "solution-000.vtu", "solution-001.vtu", "solution-002.vtu"]   # it = 0, 2, 4
+    nc, D = 160, 24
+    f0, f2 = _read_vtu(out + "solution-000.vtu"), _read_vtu(out + "solution-002.vtu")
+    assert f0["n_cells"] == nc * 4 and f0["n_points"] == nc * 9 and f0["point_names"][-1] == "schlieren_plot"
+    # initial file: the Sod states (examples/sod_shock_tube/input.prm:45-50), untouched by the limiters
+    x = f0["points"][:, 0]
+    left = x < 0.5 - 1e-12
+    np.testing.assert_allclose(f0["point"]["Density"][left], 1.0, rtol=1e-9)
+    np.testing.assert_allclose(f0["point"]["Pressure"][x > 0.5 + 1e-12], 0.1, rtol=1e-9)
+    assert np.abs(f2["point"]["XVelocity"]).max() > 0.1                 # the waves have started
+    assert np.abs(f2["point"]["Pressure"] - f0["point"]["Pressure"]).max() > 1e-3
+    # explicit numbered write now (after step 5) == host writer on the solution read back through the C ABI
+    assert L.dflo_claw_write_vtu(h, out.encode()) == 0
+    u = np.zeros(nc * D)
+    assert L.dflo_claw_get_solution(h, abi._dp(u), u.size) == 0
+    mesh = abi.Mesh(handle=L.dflo_claw_mesh(h), owned=False)
+    mesh.write_solution_vtu(out + "check.vtu", u, "Pk", 2, schlieren_plot=True, time=t.value, cycle=3)
+    assert filecmp.cmp(out + "solution-003.vtu", out + "check.vtu", shallow=False)
+    sh = _read_vtu(out + "shock.vtu")
+    assert sh["n_cells"] == nc and sh["cell_names"] == ["mu_shock", "shock_indicator"]
+    assert np.all(sh["cell"]["shock_indicator"] == 1e20)                # `shock indicator = limiter`, src/indicator.cc:15-31
+    L.dflo_claw_destroy(h)

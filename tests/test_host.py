@@ -370,3 +370,111 @@ def test_row_kernel_tile_descriptors(kind, args, bc, world, layers):
             bad = L.dflo_emu_rowdesc_check(flat, n1, rank, world, layers, ctypes.byref(nt))
             assert bad == 0, (n1, rank, bad)
             assert nt.value >= 1
+
+
+# ---------------------------------------------------------------------------------------------
+# output path: VTU writers of src/output.cc:33-87 on a host copy of the solution
+# ---------------------------------------------------------------------------------------------
+def _read_vtu(path):
+    import xml.etree.ElementTree as ET
+    piece = ET.parse(path).getroot().find("UnstructuredGrid/Piece")
+    arr = lambda e: np.array(e.text.split(), dtype=np.float64)
+    kids = lambda tag: list(piece.find(tag)) if piece.find(tag) is not None else []
+    out = dict(n_points=int(piece.get("NumberOfPoints")), n_cells=int(piece.get("NumberOfCells")),
+               points=arr(piece.find("Points/DataArray")).reshape(-1, 3),
+               cells={e.get("Name"): arr(e).astype(np.int64) for e in piece.find("Cells")},
+               point_names=[e.get("Name") for e in kids("PointData")],
+               cell_names=[e.get("Name") for e in kids("CellData")])
+    out["point"] = {e.get("Name"): arr(e) for e in kids("PointData")}
+    out["cell"] = {e.get("Name"): arr(e) for e in kids("CellData")}
+    return out
+
+
+@pytest.mark.parametrize("basis,k", [("Qk", 1), ("Qk", 3), ("Pk", 1), ("Pk", 2), ("Pk", 3), ("Qk", 0)])
+def test_vtu_output_reproduces_the_dg_polynomial(lib, tmp_path, basis, k):
+    """solution-NNN.vtu: degree x degree sub-quads per cell (DataOut::build_patches (mapping, fe.degree),
+    src/output.cc:45), the reference's array names in the reference's order (component_names + Postprocessor,
+    src/equation.cc:59-145), vertex values = the cell's own polynomial.  The field is a polynomial the element
+    represents exactly, so the file must reproduce it (and |grad rho|^2) at every patch vertex to the 10
+    digits written; DoFs come from the oracle's interpolation/projection."""
+    from oracle import oracle as O
+    nx, ny = 4, 3
+    bc = {0: "slip", 1: "outflow", 2: "inflow"}
+    params, pair = abi.make_params(bc=bc, basis=basis, degree=k)
+    mesh = abi.Mesh("rectangle", [nx, ny, 0.0, 1.0, 0.0, 0.6, 0, 1, 2, 2], lib=lib)
+    mesh.flatten(params, pair)
+    v, c, bl, bi = mesh.primitive()
+    o = O.Oracle(v, c, bl, bi, O.make_params(bc=bc, basis=basis, degree=k))
+    a, b = (k, k) if basis == "Qk" else (max(k - 1, 0), min(k, 1))   # x^a y^b stays inside Qk / Pk
+
+    def field(x, y):
+        rho = 2.0 + 0.3 * x ** k + 0.2 * y ** k + 0.1 * x ** a * y ** b
+        return np.stack([0.5 + 0.4 * x ** a * y ** b, -0.2 + 0.1 * x ** k, rho, 5.0 + y ** k + 0.5 * x ** min(k, 1)], axis=-1)
+
+    def grad_rho(x, y):
+        dx = 0.3 * k * x ** max(k - 1, 0) * (k > 0) + 0.1 * a * x ** max(a - 1, 0) * y ** b * (a > 0)
+        dy = 0.2 * k * y ** max(k - 1, 0) * (k > 0) + 0.1 * b * x ** a * y ** max(b - 1, 0) * (b > 0)
+        return dx, dy
+
+    xq = o.cell_qpoints()
+    o.set_initial_condition(field(xq[..., 0], xq[..., 1]))
+    u = o.solution()
+    path = str(tmp_path / "solution-000.vtu")
+    mesh.write_solution_vtu(path, u, basis, k, schlieren_plot=True, time=0.25, cycle=7)
+    assert "<!-- time 0.25 cycle 7 -->" in open(path).read(300)
+    f = _read_vtu(path)
+    nsub = max(k, 1)
+    nc = nx * ny
+    assert f["n_points"] == nc * (nsub + 1) ** 2 and f["n_cells"] == nc * nsub ** 2
+    assert f["point_names"] == ["XMomentum", "YMomentum", "Density", "Energy", "XVelocity", "YVelocity", "Pressure",
+                                "schlieren_plot"]
+    # geometry: every cell's own (nsub+1)^2 lexicographic vertices, nothing shared between cells
+    fa = mesh.flat_arrays()
+    t = np.arange(nsub + 1) / nsub
+    px = fa["origin"][:, None, None, 0] + t[None, None, :] * fa["size"][:, None, None, 0] + 0 * t[None, :, None]
+    py = fa["origin"][:, None, None, 1] + t[None, :, None] * fa["size"][:, None, None, 1] + 0 * t[None, None, :]
+    np.testing.assert_allclose(f["points"][:, 0], px.reshape(-1), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(f["points"][:, 1], py.reshape(-1), rtol=1e-9, atol=1e-12)
+    assert np.all(f["points"][:, 2] == 0)
+    conn = f["cells"]["connectivity"].reshape(-1, 4)
+    assert np.all(f["cells"]["types"] == 9) and np.array_equal(f["cells"]["offsets"], 4 * np.arange(1, len(conn) + 1))
+    assert np.array_equal(conn // (nsub + 1) ** 2, np.repeat(np.arange(nc), nsub ** 2)[:, None] * np.ones(4, np.int64))
+    q = f["points"][conn]                                   # counter-clockwise unit sub-quads
+    assert np.all(q[:, 1, 0] > q[:, 0, 0]) and np.all(q[:, 2, 1] > q[:, 1, 1]) and np.all(q[:, 3, 0] == q[:, 0, 0])
+    # values
+    w = field(px.reshape(-1), py.reshape(-1))
+    if k == 0:   # piecewise constants: the cell value at every vertex
+        xc = fa["origin"] + 0.5 * fa["size"]
+        w = np.repeat(field(xc[:, 0], xc[:, 1]), 4, axis=0)
+    for i, name in enumerate(["XMomentum", "YMomentum", "Density", "Energy"]):
+        np.testing.assert_allclose(f["point"][name], w[:, i], rtol=2e-9, atol=1e-11)
+    np.testing.assert_allclose(f["point"]["XVelocity"], w[:, 0] / w[:, 2], rtol=2e-9)
+    np.testing.assert_allclose(f["point"]["YVelocity"], w[:, 1] / w[:, 2], rtol=2e-9, atol=1e-11)
+    np.testing.assert_allclose(f["point"]["Pressure"], 0.4 * (w[:, 3] - 0.5 * (w[:, 0] ** 2 + w[:, 1] ** 2) / w[:, 2]), rtol=2e-9)
+    gx, gy = grad_rho(px.reshape(-1), py.reshape(-1)) if k > 0 else (np.zeros(4 * nc), np.zeros(4 * nc))
+    np.testing.assert_allclose(f["point"]["schlieren_plot"], gx ** 2 + gy ** 2, rtol=1e-8, atol=1e-10)
+    # without the schlieren switch the array is absent (Postprocessor::get_names)
+    mesh.write_solution_vtu(path, u, basis, k)
+    assert _read_vtu(path)["point_names"][-1] == "Pressure"
+    # wrong vector length / unwritable path are errors, not silent truncation
+    with pytest.raises(abi.DfloError):
+        mesh.write_solution_vtu(path, u[:-1], basis, k)
+    with pytest.raises(abi.DfloError):
+        mesh.write_solution_vtu(str(tmp_path / "no_such_dir" / "x.vtu"), u, basis, k)
+
+
+def test_shock_vtu_cell_data(lib, tmp_path):
+    """shock.vtu (src/output.cc:70-79): one quad per cell, cell data mu_shock and shock_indicator."""
+    params, pair = abi.make_params(bc={0: "slip", 1: "outflow", 2: "inflow"}, basis="Qk", degree=2)
+    mesh = abi.Mesh("sod_tube", [10, 2], lib=lib)
+    mesh.flatten(params, pair)
+    nc = mesh.n_cells
+    ind = np.linspace(0.0, 3.0, nc)
+    path = str(tmp_path / "shock.vtu")
+    mesh.write_shock_vtu(path, ind)
+    f = _read_vtu(path)
+    assert f["n_cells"] == nc and f["n_points"] == 4 * nc and f["cell_names"] == ["mu_shock", "shock_indicator"]
+    np.testing.assert_allclose(f["cell"]["shock_indicator"], ind, rtol=1e-9)
+    assert np.all(f["cell"]["mu_shock"] == 0)
+    mesh.write_shock_vtu(path, ind, mu_shock=2 * ind)
+    np.testing.assert_allclose(_read_vtu(path)["cell"]["mu_shock"], 2 * ind, rtol=1e-9)
