@@ -612,7 +612,9 @@ namespace dflo
          compute_cell_average (cur, lm.n_owned);
          exchange_halo (cur);
          old = cur;
-         bk.drop_graphs ();
+         // a step graph is a function of the starting buffer alone; only the out-of-graph halo exchange above
+         // (its epochs are baked into the captured launches) makes the captured steps stale
+         if (!lm.peers.empty ()) bk.drop_graphs ();
          return bk.check (error);
       }
 

@@ -104,6 +104,26 @@ def test_advance_graph_matches_stagewise():
     b.close()
 
 
+def test_set_solution_between_advances_reuses_the_step_graphs():
+    """set_solution on a single-GPU ctx keeps the captured step graphs (they depend on the starting buffer only):
+    advance - set_solution - advance must equal a fresh ctx bit for bit, whichever buffer the state sits in."""
+    prm = dict(basis="Qk", degree=2, flux="hllc", cfl=0.9, limiter="TVB", char_lim=True, M=0.0, beta=2.0)
+    a = Case(("sod_tube", [40, 4]), SOD_BC, ic_sod, backend="cuda", **prm)
+    b = Case(("sod_tube", [40, 4]), SOD_BC, ic_sod, backend="cuda", **prm)
+    for c in (a, b):
+        c.set_boundary(values=(0.0, 0.0, 1.0, 2.5))
+    ta, _ = a.engine.advance(4)
+    ref = a.solution().copy()
+    assert np.all(np.isfinite(ref)) and 0 < ta < 1 and np.abs(ref - a.u0).max() > 1e-3
+    for n_before in (1, 2, 3):          # leaves the state in each of the rotating buffers
+        b.engine.advance(n_before)
+        b.engine.set_solution(b.u0)
+        tb, _ = b.engine.advance(4)
+        assert tb == ta and np.array_equal(b.solution(), ref)
+    a.close()
+    b.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json full sizes: no oracle can follow here in seconds, so the checks are the
 # size-independent properties of the scheme (conservation, free-stream preservation, translation
