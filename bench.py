@@ -367,7 +367,7 @@ def main():
     # Independent batches pipeline: E2E_CTX contexts (a ctx is single-threaded by contract, include/dflo_b200.h), one
     # host thread and one pinned buffer each, run the same set_solution + advance + get_solution per step, and the copy
     # in of one batch overlaps the copy out of the other.  Single GPU only; sharded contexts keep the serial number.
-    E2E_CTX = int(os.environ.get("DFLO_BENCH_E2E_CTX", "2"))
+    E2E_CTX = int(os.environ.get("DFLO_BENCH_E2E_CTX", "3"))
     e2e_pipe_s = None
     if world == 1 and E2E_CTX > 1:
         try:

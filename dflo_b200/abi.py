@@ -129,6 +129,9 @@ def _declare_host(L):
     L.dflo_expr_eval.argtypes = [ctypes.c_char_p, ctypes.c_int, c_double_p, c_double_p, ctypes.c_double, c_double_p]
     L.dflo_host_write_solution_vtu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_size_t,
                                                ctypes.c_int, ctypes.c_double, ctypes.c_uint, ctypes.c_char_p]
+    L.dflo_host_write_solution_piece_vtu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_size_t,
+                                                     ctypes.c_int, ctypes.c_double, ctypes.c_uint, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.c_int, ctypes.c_char_p]
     L.dflo_host_write_shock_vtu.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_char_p]
 
 
@@ -237,11 +240,13 @@ class Mesh:
         self.flat = self.L.dflo_mesh_flat(self.h)
         return self.flat
 
-    def write_solution_vtu(self, path, u, basis, degree, schlieren_plot=False, time=0.0, cycle=0):
-        """output_results on a host copy of the solution (src/output.cc:33-68); basis: "Qk" | "Pk"."""
+    def write_solution_vtu(self, path, u, basis, degree, schlieren_plot=False, time=0.0, cycle=0, cells=None, subdomain=-1):
+        """output_results on a host copy of the solution (src/output.cc:33-68); basis: "Qk" | "Pk"; cells = (begin, end)
+        writes one process' piece like src_mpi/output.cc (u stays the global vector)."""
         u = np.ascontiguousarray(u, dtype=np.float64)
-        rc = self.L.dflo_host_write_solution_vtu(self.h, {"Qk": 0, "Pk": 1}[basis], degree, _dp(u), u.size,
-                                                 int(schlieren_plot), time, cycle, path.encode())
+        c0, c1 = (0, -1) if cells is None else cells
+        rc = self.L.dflo_host_write_solution_piece_vtu(self.h, {"Qk": 0, "Pk": 1}[basis], degree, _dp(u), u.size,
+                                                       int(schlieren_plot), time, cycle, c0, c1, subdomain, path.encode())
         if rc:
             raise DfloError(rc, self.L.dflo_host_last_error().decode())
 

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <sstream>
+#include <sys/stat.h>
 
 namespace dflo
 {
@@ -201,11 +202,13 @@ namespace dflo
    }
 
    // setup_system (src/claw.cc:270-386) + the start of run() (:981-1003)
-   int ConservationLaw::setup_system (int device, int rank, int world, const void *nccl_unique_id)
+   int ConservationLaw::setup_system (int device, int rank_, int world_, const void *nccl_unique_id)
    {
       if (!ok ()) return DFLO_E_INVALID;
       if (ctx) dflo_b200_destroy (ctx);
       ctx = nullptr;
+      rank = world_ > 1 ? rank_ : 0;
+      world = world_ > 1 ? world_ : 1;
       int rc = world > 1 ? dflo_b200_create_sharded (&flat_view, &engine_params, device, rank, world, nccl_unique_id, &ctx)
                          : dflo_b200_create (&flat_view, &engine_params, device, &ctx);
       if (rc)
@@ -344,17 +347,38 @@ namespace dflo
       return dflo_b200_get_solution (ctx, u.data (), nullptr, u.size ());
    }
 
-   // output_results (src/output.cc:33-87): host copy of current_solution -> VTU (host/output.cc).
-   // path: a file name, or "" / "dir/" for the reference's own numbering solution-NNN.vtu (output.cc:47-49,
-   // "Writing file ..." line included) plus shock.vtu with mu_shock and shock_indicator (output.cc:70-79).
+   // output_results: host copy of current_solution -> VTU (host/output.cc).
+   // path = a file name: this rank's cells into that file.  path = "" / "dir/": the reference's own numbering --
+   //   src (one process):   dir/solution-NNN.vtu ("Writing file ..." line included) + dir/shock.vtu with mu_shock and
+   //                        shock_indicator (src/output.cc:33-79);
+   //   src_mpi, or sharded: dir/output/solution-NNNN.RRR.vtu = the cells this rank owns plus the "subdomain" array,
+   //                        and on rank 0 dir/master_file.visit listing the pieces of every output so far
+   //                        (src_mpi/output.cc:34-86; the directory is created if missing).
    int ConservationLaw::output_results (const std::string &path_in)
    {
       std::vector<double> u;
-      const int rc = get_solution (u);
+      int rc = get_solution (u); // sharded: fills the owned range only
       if (rc) return rc;
+      int64_t c0 = 0, c1 = flat.n_cells ();
+      if (world > 1) dflo_b200_cell_range (ctx, &c0, &c1);
       std::string path = path_in, dir;
       const bool numbered = path.empty () || path.back () == '/';
-      if (numbered)
+      const bool pieces = numbered && (world > 1 || compat == DFLO_COMPAT_MPI);
+      if (pieces)
+      {
+         dir = path;
+         ::mkdir ((dir + "output").c_str (), 0777);
+         std::vector<std::string> names;
+         for (int r = 0; r < world; ++r)
+         {
+            char name[64];
+            std::snprintf (name, sizeof (name), "output/solution-%04u.%03d.vtu", output_file_number, r);
+            names.push_back (name);
+         }
+         path = dir + names[rank];
+         all_files.push_back (names);
+      }
+      else if (numbered)
       {
          dir = path;
          char name[64];
@@ -362,16 +386,19 @@ namespace dflo
          path = dir + name;
          std::printf ("Writing file %s\n", path.c_str ());
       }
-      if (!write_solution_vtu (tab, flat, u.data (), parameters.schlieren_plot, elapsed_time, output_file_number, path))
+      if (!write_solution_vtu (tab, flat, u.data (), parameters.schlieren_plot, elapsed_time, output_file_number, path, (int) c0,
+                               (int) c1, pieces ? rank : -1))
       {
          error = "cannot write " + path;
          return DFLO_E_INVALID;
       }
-      if (numbered)
+      if (pieces && rank == 0 && !write_visit_record (all_files, dir + "master_file.visit"))
       {
-         ++output_file_number;
-         return write_shock_file (dir + "shock.vtu");
+         error = "cannot write " + dir + "master_file.visit";
+         return DFLO_E_INVALID;
       }
+      if (numbered) ++output_file_number;
+      if (numbered && !pieces) return write_shock_file (dir + "shock.vtu");
       return DFLO_OK;
    }
 

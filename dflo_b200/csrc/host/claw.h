@@ -39,6 +39,8 @@ namespace dflo
       unsigned int output_file_number = 0;                         // the static counter of output.cc:47
       // run() writes the initial solution and then follows "output: time step / iter step" (src/claw.cc:1010-1017,
       // 1093-1099) into output_dir ("" = working directory like the reference) when enabled
+      std::vector<std::vector<std::string>> all_files;             // the static all_files of src_mpi/output.cc:70
+      int rank = 0, world = 1;                                     // set by setup_system
       bool output_enabled = false;
       std::string output_dir;
       double next_output_time = 0.0;

@@ -113,21 +113,28 @@ int dflo_expr_eval (const char *expr, int n, const double *x, const double *y, d
    return DFLO_OK;
 }
 
-int dflo_host_write_solution_vtu (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, int schlieren_plot,
-                                  double time, unsigned int cycle, const char *path)
+int dflo_host_write_solution_piece_vtu (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, int schlieren_plot,
+                                        double time, unsigned int cycle, int cell_begin, int cell_end, int subdomain, const char *path)
 {
    dflo::FeTables tab;
-   if (!m || !m->flattened || !u || !path || !dflo::build_tables (basis, degree, tab) || n != (size_t) m->flat.n_cells () * tab.D)
+   if (!m || !m->flattened || !u || !path || !dflo::build_tables (basis, degree, tab) || n != (size_t) m->flat.n_cells () * tab.D
+       || cell_begin < 0 || cell_end > m->flat.n_cells () || (cell_end >= 0 && cell_begin > cell_end))
    {
-      dflo::host_error () = "write_solution_vtu: mesh not flattened, unsupported element or wrong vector length";
+      dflo::host_error () = "write_solution_vtu: mesh not flattened, unsupported element, wrong vector length or bad cell range";
       return DFLO_E_INVALID;
    }
-   if (!dflo::write_solution_vtu (tab, m->flat, u, schlieren_plot != 0, time, cycle, path))
+   if (!dflo::write_solution_vtu (tab, m->flat, u, schlieren_plot != 0, time, cycle, path, cell_begin, cell_end, subdomain))
    {
       dflo::host_error () = std::string ("cannot write ") + path;
       return DFLO_E_INVALID;
    }
    return DFLO_OK;
+}
+
+int dflo_host_write_solution_vtu (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, int schlieren_plot,
+                                  double time, unsigned int cycle, const char *path)
+{
+   return dflo_host_write_solution_piece_vtu (m, basis, degree, u, n, schlieren_plot, time, cycle, 0, -1, -1, path);
 }
 
 int dflo_host_write_shock_vtu (const dflo_mesh *m, const double *mu_shock, const double *shock_indicator, const char *path)

@@ -20,7 +20,7 @@ namespace dflo
                            "<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n", n_points, n_cells);
       }
 
-      // nsub x nsub quads on the (nsub+1)^2 lexicographic points of every cell
+      // nsub x nsub quads on the (nsub+1)^2 lexicographic points of each of the nc cells written
       void vtu_cells (FILE *fp, int nc, int nsub)
       {
          const int np1 = nsub + 1, npc = np1 * np1, n_out = nc * nsub * nsub;
@@ -39,9 +39,9 @@ namespace dflo
          std::fprintf (fp, "</DataArray>\n</Cells>\n");
       }
 
-      void vtu_points (FILE *fp, const FlatMesh &flat, int nsub)
+      void vtu_points (FILE *fp, const FlatMesh &flat, int nsub, int c0, int c1)
       {
-         for (int cell = 0; cell < flat.n_cells (); ++cell)
+         for (int cell = c0; cell < c1; ++cell)
             for (int j = 0; j <= nsub; ++j)
                for (int i = 0; i <= nsub; ++i)
                   std::fprintf (fp, "%.10g %.10g 0\n", flat.origin[2 * cell] + (double) i / nsub * flat.size[2 * cell],
@@ -50,11 +50,14 @@ namespace dflo
    }
 
    bool write_solution_vtu (const FeTables &tab, const FlatMesh &flat, const double *u, bool schlieren_plot, double time,
-                            unsigned int cycle, const std::string &path)
+                            unsigned int cycle, const std::string &path, int cell_begin, int cell_end, int subdomain)
    {
+      if (cell_end < 0) cell_end = flat.n_cells ();
+      if (cell_begin < 0 || cell_begin > cell_end || cell_end > flat.n_cells ()) return false;
       FILE *fp = std::fopen (path.c_str (), "w");
       if (!fp) return false;
-      const int nc = flat.n_cells (), ns = tab.ns, D = tab.D;
+      const int nc = cell_end - cell_begin, ns = tab.ns, D = tab.D;
+      u += (size_t) cell_begin * D; // rows below are relative to the first cell written
       const int nsub = tab.k > 0 ? tab.k : 1, np1 = nsub + 1, npc = np1 * np1;
       // basis values and unit-cell gradients at the equispaced patch vertices
       std::vector<double> phi ((size_t) npc * ns), dpx ((size_t) npc * ns), dpy ((size_t) npc * ns);
@@ -86,13 +89,13 @@ namespace dflo
                   gx += dpx[(size_t) v * ns + m] * ur[m];
                   gy += dpy[(size_t) v * ns + m] * ur[m];
                }
-               gx /= flat.size[2 * cell];
-               gy /= flat.size[2 * cell + 1];
+               gx /= flat.size[2 * (cell_begin + cell)];
+               gy /= flat.size[2 * (cell_begin + cell) + 1];
                schl[(size_t) cell * npc + v] = gx * gx + gy * gy;
             }
          }
       vtu_head (fp, npc * nc, nc * nsub * nsub, time, cycle, true);
-      vtu_points (fp, flat, nsub);
+      vtu_points (fp, flat, nsub, cell_begin, cell_end);
       vtu_cells (fp, nc, nsub);
       std::fprintf (fp, "<PointData>\n");
       // component_names (src/equation.h) then Postprocessor::get_names (src/equation.cc:130-145)
@@ -114,7 +117,23 @@ namespace dflo
          }
          std::fprintf (fp, "</DataArray>\n");
       }
+      if (subdomain >= 0) // locally_owned_subdomain of every cell of the piece, src_mpi/output.cc:51-54
+      {
+         std::fprintf (fp, "<DataArray type=\"Float64\" Name=\"subdomain\" format=\"ascii\">\n");
+         for (size_t p = 0; p < (size_t) nc * npc; ++p) std::fprintf (fp, "%d\n", subdomain);
+         std::fprintf (fp, "</DataArray>\n");
+      }
       std::fprintf (fp, "</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+      return std::fclose (fp) == 0;
+   }
+
+   bool write_visit_record (const std::vector<std::vector<std::string>> &all_files, const std::string &path)
+   {
+      FILE *fp = std::fopen (path.c_str (), "w");
+      if (!fp) return false;
+      if (!all_files.empty ()) std::fprintf (fp, "!NBLOCKS %zu\n", all_files[0].size ());
+      for (const auto &step : all_files)
+         for (const auto &f : step) std::fprintf (fp, "%s\n", f.c_str ());
       return std::fclose (fp) == 0;
    }
 
@@ -124,13 +143,14 @@ namespace dflo
       if (!fp) return false;
       const int nc = flat.n_cells ();
       vtu_head (fp, 4 * nc, nc, 0.0, 0, false);
-      vtu_points (fp, flat, 1);
+      vtu_points (fp, flat, 1, 0, nc);
       vtu_cells (fp, nc, 1);
-      std::fprintf (fp, "<CellData>\n<DataArray type=\"Float64\" Name=\"mu_shock\" format=\"ascii\">\n");
-      for (int i = 0; i < nc; ++i) std::fprintf (fp, "%.10g\n", mu_shock ? mu_shock[i] : 0.0);
+      // DataOut stores cell data as the same value on every vertex of the cell's patch and writes point data only
+      std::fprintf (fp, "<PointData>\n<DataArray type=\"Float64\" Name=\"mu_shock\" format=\"ascii\">\n");
+      for (int i = 0; i < 4 * nc; ++i) std::fprintf (fp, "%.10g\n", mu_shock ? mu_shock[i / 4] : 0.0);
       std::fprintf (fp, "</DataArray>\n<DataArray type=\"Float64\" Name=\"shock_indicator\" format=\"ascii\">\n");
-      for (int i = 0; i < nc; ++i) std::fprintf (fp, "%.10g\n", shock_indicator[i]);
-      std::fprintf (fp, "</DataArray>\n</CellData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+      for (int i = 0; i < 4 * nc; ++i) std::fprintf (fp, "%.10g\n", shock_indicator[i / 4]);
+      std::fprintf (fp, "</DataArray>\n</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
       return std::fclose (fp) == 0;
    }
 }

@@ -70,18 +70,25 @@ dflo_ctx *dflo_claw_engine (dflo_claw *c);
  * final time; prints the reference's per-step lines when verbose */
 int dflo_claw_run (dflo_claw *c, int max_steps, int verbose, double *elapsed_time, int *steps_done);
 int dflo_claw_get_solution (dflo_claw *c, double *u, size_t n);
-/* output_results (src/output.cc:33-87).  path = a file name: the solution only; path = NULL, "" or "dir/": the
- * reference's numbered solution-NNN.vtu (counter advances) plus shock.vtu in that directory.  Every cell is written
- * as degree x degree sub-quads like DataOut::build_patches (mapping, fe.degree); point data XMomentum YMomentum
- * Density Energy XVelocity YVelocity Pressure [schlieren_plot] (src/equation.cc:59-145). */
+/* output_results (src/output.cc:33-87, src_mpi/output.cc:34-86).  path = a file name: the solution (this rank's cells)
+ * only.  path = NULL, "" or "dir/": the reference's numbered files in that directory, counter advancing --
+ *   compat src, one process: solution-NNN.vtu + shock.vtu;
+ *   compat mpi, or a sharded setup: output/solution-NNNN.RRR.vtu (this rank's cells, extra array "subdomain") and, on
+ *   rank 0, master_file.visit.
+ * Every cell is written as degree x degree sub-quads like DataOut::build_patches (mapping, fe.degree); point data
+ * XMomentum YMomentum Density Energy XVelocity YVelocity Pressure [schlieren_plot] (src/equation.cc:59-145). */
 int dflo_claw_write_vtu (dflo_claw *c, const char *path);
 /* dir != NULL: dflo_claw_run writes the initial solution and then follows "output: time step / iter step" and the
  * final time like src/claw.cc:1010-1017, 1093-1099 (dir "" = working directory, as the reference); NULL: off (default) */
 void dflo_claw_set_output (dflo_claw *c, const char *dir);
 /* the same writers on a host copy of the solution (reference DoF layout, n = n_cells * 4 * n_s), no engine involved;
- * mesh must be flattened.  shock file: mu_shock may be NULL (zeros). */
+ * mesh must be flattened.  shock file: mu_shock may be NULL (zeros); both arrays are written the way DataOut writes
+ * cell vectors, as point data constant on the four vertices of each cell. */
 int dflo_host_write_solution_vtu (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, int schlieren_plot,
                                   double time, unsigned int cycle, const char *path);
+/* the piece of cells [cell_begin, cell_end) (cell_end < 0: to the last cell); subdomain >= 0 adds the "subdomain" array */
+int dflo_host_write_solution_piece_vtu (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, int schlieren_plot,
+                                        double time, unsigned int cycle, int cell_begin, int cell_end, int subdomain, const char *path);
 int dflo_host_write_shock_vtu (const dflo_mesh *m, const double *mu_shock, const double *shock_indicator, const char *path);
 
 #ifdef __cplusplus

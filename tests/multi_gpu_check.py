@@ -41,6 +41,63 @@ CASES = [
 ]
 
 
+def sharded_output_check(L, rank, world, local):
+    """The standalone driver on a sharded setup (src_mpi/output.cc:34-86): every rank writes
+    output/solution-NNNN.RRR.vtu with the cells it owns, rank 0 master_file.visit; the pieces put end to end must be
+    the file the single-GPU driver writes for the same run, byte for byte in every data array."""
+    import ctypes
+    import shutil
+    from test_host import PRM_DIR, _claw_api, _read_vtu
+    _claw_api(L)
+    L.dflo_claw_set_output.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    L.dflo_claw_set_output.restype = None
+    L.dflo_claw_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, abi.c_double_p, ctypes.POINTER(ctypes.c_int)]
+    L.dflo_claw_write_vtu.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    out = "/tmp/dflo_b200_sharded_output/"
+    if rank == 0:
+        shutil.rmtree(out, ignore_errors=True)
+        os.makedirs(out)
+    idbuf = (abi.ctypes.c_char * 128)()
+    if rank == 0:
+        assert L.dflo_b200_nccl_unique_id(idbuf) == 0
+    t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    nccl_id = bytes(t.cpu().tolist())
+    over = b"subsection output\n set iter step = 2\nend\n"
+    prm = os.path.join(PRM_DIR, "cfg3_sod_P2_hllc_tvb_pos.prm").encode()
+
+    def drive(world_, rank_, where):
+        h = ctypes.c_void_p(L.dflo_claw_create(prm, b"sod_tube 100 10", over, abi.COMPAT["src"]))
+        assert h, L.dflo_host_last_error()
+        L.dflo_claw_set_output(h, where.encode())
+        assert L.dflo_claw_setup(h, local, rank_, world_, nccl_id if world_ > 1 else None) == 0, L.dflo_host_last_error()
+        tt, done = ctypes.c_double(0.0), ctypes.c_int(0)
+        assert L.dflo_claw_run(h, 4, 0, ctypes.byref(tt), ctypes.byref(done)) == 0, L.dflo_host_last_error()
+        L.dflo_claw_destroy(h)
+        return tt.value
+
+    t_sh = drive(world, rank, out)
+    dist.barrier()
+    good = True
+    if rank == 0:
+        os.makedirs(out + "single")
+        t_1 = drive(1, 0, out + "single/")
+        visit = open(out + "master_file.visit").read().split()
+        good = visit[:2] == ["!NBLOCKS", str(world)] and len(visit) == 2 + 3 * world and t_1 == t_sh
+        for n in range(3):                                    # it = 0, 2, 4
+            whole = _read_vtu(out + "single/solution-%03d.vtu" % n)
+            parts = [_read_vtu(out + "output/solution-%04d.%03d.vtu" % (n, r)) for r in range(world)]
+            good = good and visit[2 + n * world:2 + (n + 1) * world] == ["output/solution-%04d.%03d.vtu" % (n, r) for r in range(world)]
+            good = good and all(np.all(p["point"]["subdomain"] == r) for r, p in enumerate(parts))
+            good = good and np.array_equal(np.concatenate([p["points"] for p in parts]), whole["points"])
+            for name in whole["point_names"]:
+                good = good and np.array_equal(np.concatenate([p["point"][name] for p in parts]), whole["point"][name])
+        print("%-22s world %d: pieces of 3 outputs == single-GPU files, master_file.visit lists %d files  %s"
+              % ("driver_output_sod_P2", world, len(visit) - 2, "OK" if good else "FAIL"), flush=True)
+    dist.barrier()
+    return good
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -116,6 +173,7 @@ def main():
             print("%-22s world %d: |sharded - single| = %.3e (t %.3e)  rel err vs oracle = %.3e  %s"
                   % (name, world, d1, abs(t_sh - t_1), do, "OK" if good else "FAIL"), flush=True)
         dist.barrier()
+    ok = sharded_output_check(L, rank, world, local) and ok
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -371,6 +371,21 @@ def test_run_loop_output_schedule_and_vtu_files(tmp_path):
     mesh.write_solution_vtu(out + "check.vtu", u, "Pk", 2, schlieren_plot=True, time=t.value, cycle=3)
     assert filecmp.cmp(out + "solution-003.vtu", out + "check.vtu", shallow=False)
     sh = _read_vtu(out + "shock.vtu")
-    assert sh["n_cells"] == nc and sh["cell_names"] == ["mu_shock", "shock_indicator"]
-    assert np.all(sh["cell"]["shock_indicator"] == 1e20)                # `shock indicator = limiter`, src/indicator.cc:15-31
+    assert sh["n_cells"] == nc and sh["point_names"] == ["mu_shock", "shock_indicator"]
+    assert np.all(sh["point"]["shock_indicator"] == 1e20)               # `shock indicator = limiter`, src/indicator.cc:15-31
+    L.dflo_claw_destroy(h)
+    # MPI tree (src_mpi/output.cc:34-86): output/solution-NNNN.RRR.vtu with "subdomain" + master_file.visit, no shock.vtu
+    out2 = out + "mpi/"
+    os.makedirs(out2)
+    h = ctypes.c_void_p(L.dflo_claw_create(os.path.join(PRM_DIR, "cfg1_isentropic_vortex_Q1_lxf.prm").encode(),
+                                           b"isentropic_vortex 8", b"subsection output\n set iter step = 1\nend\n", abi.COMPAT["mpi"]))
+    assert h, L.dflo_host_last_error()
+    L.dflo_claw_set_output(h, out2.encode())
+    assert L.dflo_claw_setup(h, 0, 0, 1, None) == 0, L.dflo_host_last_error()
+    assert L.dflo_claw_run(h, 2, 0, ctypes.byref(t), ctypes.byref(done)) == 0, L.dflo_host_last_error()
+    assert sorted(os.listdir(out2)) == ["master_file.visit", "output"]
+    assert sorted(os.listdir(out2 + "output")) == ["solution-%04d.000.vtu" % i for i in range(3)]
+    assert open(out2 + "master_file.visit").read().split() == ["!NBLOCKS", "1"] + ["output/solution-%04d.000.vtu" % i for i in range(3)]
+    f = _read_vtu(out2 + "output/solution-0002.000.vtu")
+    assert f["n_cells"] == 64 and f["point_names"][-2:] == ["Pressure", "subdomain"] and np.all(f["point"]["subdomain"] == 0)
     L.dflo_claw_destroy(h)

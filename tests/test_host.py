@@ -463,8 +463,9 @@ def test_vtu_output_reproduces_the_dg_polynomial(lib, tmp_path, basis, k):
         mesh.write_solution_vtu(str(tmp_path / "no_such_dir" / "x.vtu"), u, basis, k)
 
 
-def test_shock_vtu_cell_data(lib, tmp_path):
-    """shock.vtu (src/output.cc:70-79): one quad per cell, cell data mu_shock and shock_indicator."""
+def test_shock_vtu_cell_vectors(lib, tmp_path):
+    """shock.vtu (src/output.cc:70-79): one quad per cell, mu_shock and shock_indicator the way DataOut writes cell
+    vectors -- point data, constant on the four vertices of a cell."""
     params, pair = abi.make_params(bc={0: "slip", 1: "outflow", 2: "inflow"}, basis="Qk", degree=2)
     mesh = abi.Mesh("sod_tube", [10, 2], lib=lib)
     mesh.flatten(params, pair)
@@ -473,8 +474,41 @@ def test_shock_vtu_cell_data(lib, tmp_path):
     path = str(tmp_path / "shock.vtu")
     mesh.write_shock_vtu(path, ind)
     f = _read_vtu(path)
-    assert f["n_cells"] == nc and f["n_points"] == 4 * nc and f["cell_names"] == ["mu_shock", "shock_indicator"]
-    np.testing.assert_allclose(f["cell"]["shock_indicator"], ind, rtol=1e-9)
-    assert np.all(f["cell"]["mu_shock"] == 0)
+    assert f["n_cells"] == nc and f["n_points"] == 4 * nc and f["point_names"] == ["mu_shock", "shock_indicator"]
+    assert f["cell_names"] == []
+    np.testing.assert_allclose(f["point"]["shock_indicator"], np.repeat(ind, 4), rtol=1e-9)
+    assert np.all(f["point"]["mu_shock"] == 0)
     mesh.write_shock_vtu(path, ind, mu_shock=2 * ind)
-    np.testing.assert_allclose(_read_vtu(path)["cell"]["mu_shock"], 2 * ind, rtol=1e-9)
+    np.testing.assert_allclose(_read_vtu(path)["point"]["mu_shock"], np.repeat(2 * ind, 4), rtol=1e-9)
+
+
+def test_vtu_pieces_of_the_mpi_tree_tile_the_whole_file(lib, tmp_path):
+    """src_mpi/output.cc:34-86: every process writes the cells it owns (+ "subdomain"); the pieces of a partition put
+    end to end are the single-process file."""
+    bc = {0: "slip", 1: "outflow", 2: "inflow"}
+    params, pair = abi.make_params(bc=bc, basis="Pk", degree=2)
+    mesh = abi.Mesh("sod_tube", [12, 3], lib=lib)
+    mesh.flatten(params, pair)
+    nc, D = mesh.n_cells, 24
+    u = np.random.default_rng(3).uniform(0.5, 2.0, nc * D)
+    whole = str(tmp_path / "whole.vtu")
+    mesh.write_solution_vtu(whole, u, "Pk", 2, schlieren_plot=True, time=0.5, cycle=2)
+    fw = _read_vtu(whole)
+    cuts = [0, 10, 11, 36]
+    pts, arrays = [], {n: [] for n in fw["point_names"]}
+    for r in range(3):
+        p = str(tmp_path / ("solution-0002.%03d.vtu" % r))
+        mesh.write_solution_vtu(p, u, "Pk", 2, schlieren_plot=True, time=0.5, cycle=2, cells=(cuts[r], cuts[r + 1]), subdomain=r)
+        f = _read_vtu(p)
+        n = cuts[r + 1] - cuts[r]
+        assert f["n_cells"] == 4 * n and f["n_points"] == 9 * n and f["point_names"] == fw["point_names"] + ["subdomain"]
+        assert np.all(f["point"]["subdomain"] == r)
+        assert f["cells"]["connectivity"].max() == 9 * n - 1          # piece-local point numbering
+        pts.append(f["points"])
+        for name in fw["point_names"]:
+            arrays[name].append(f["point"][name])
+    assert np.array_equal(np.concatenate(pts), fw["points"])
+    for name in fw["point_names"]:
+        assert np.array_equal(np.concatenate(arrays[name]), fw["point"][name])
+    with pytest.raises(abi.DfloError):
+        mesh.write_solution_vtu(whole, u, "Pk", 2, cells=(5, nc + 1))
