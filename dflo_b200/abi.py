@@ -132,6 +132,7 @@ def _declare_host(L):
     L.dflo_host_write_solution_piece_vtu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_size_t,
                                                      ctypes.c_int, ctypes.c_double, ctypes.c_uint, ctypes.c_int, ctypes.c_int,
                                                      ctypes.c_int, ctypes.c_char_p]
+    L.dflo_host_angular_momentum.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_size_t, c_double_p]
     L.dflo_host_write_shock_vtu.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_char_p]
 
 
@@ -249,6 +250,16 @@ class Mesh:
                                                        int(schlieren_plot), time, cycle, c0, c1, subdomain, path.encode())
         if rc:
             raise DfloError(rc, self.L.dflo_host_last_error().decode())
+
+    def angular_momentum(self, u, basis, degree):
+        """compute_angular_momentum (src/claw.cc:604-635) of a host copy of the solution."""
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        v = ctypes.c_double(0.0)
+        rc = self.L.dflo_host_angular_momentum(self.h, {"Qk": 0, "Pk": 1}[basis], degree, _dp(u), u.size,
+                                               ctypes.cast(ctypes.byref(v), c_double_p))
+        if rc:
+            raise DfloError(rc, self.L.dflo_host_last_error().decode())
+        return v.value
 
     def write_shock_vtu(self, path, shock_indicator, mu_shock=None):
         """shock.vtu of src/output.cc:70-79."""

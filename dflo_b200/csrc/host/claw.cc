@@ -328,6 +328,13 @@ namespace dflo
          }
          ++time_iter;
          ++steps;
+         if (parameters.ang_mom_step > 0 && time_iter % parameters.ang_mom_step == 0 && world == 1) // src/claw.cc:1075-1076
+         {
+            double am = 0.0;
+            rc = compute_angular_momentum (am);
+            if (rc) return rc;
+            std::printf ("Total angular momentum: %18.8e %24.14e\n", elapsed_time, am);
+         }
          // "Save solution for visualization", src/claw.cc:1093-1099
          if (output_enabled && (elapsed_time >= next_output_time || time_iter == next_output_iter
                                 || std::fabs (elapsed_time - parameters.final_time) < 1.0e-13))
@@ -345,6 +352,18 @@ namespace dflo
    {
       u.assign ((size_t) n_dofs (), 0.0);
       return dflo_b200_get_solution (ctx, u.data (), nullptr, u.size ());
+   }
+
+   // compute_angular_momentum, src/claw.cc:604-635 (this rank's cells)
+   int ConservationLaw::compute_angular_momentum (double &value)
+   {
+      std::vector<double> u;
+      const int rc = get_solution (u);
+      if (rc) return rc;
+      int64_t c0 = 0, c1 = flat.n_cells ();
+      if (world > 1) dflo_b200_cell_range (ctx, &c0, &c1);
+      value = angular_momentum (tab, flat, u.data (), (int) c0, (int) c1);
+      return DFLO_OK;
    }
 
    // output_results: host copy of current_solution -> VTU (host/output.cc).
@@ -512,6 +531,10 @@ int dflo_claw_write_vtu (dflo_claw *c, const char *path)
    const int rc = c->claw->output_results (path ? path : "");
    if (rc) dflo::host_error () = c->claw->error;
    return rc;
+}
+int dflo_claw_angular_momentum (dflo_claw *c, double *value)
+{
+   return value ? c->claw->compute_angular_momentum (*value) : DFLO_E_INVALID;
 }
 void dflo_claw_set_output (dflo_claw *c, const char *dir)
 {

@@ -36,6 +36,7 @@ namespace dflo
       int get_solution (std::vector<double> &u);
       int output_results (const std::string &path);                // src/output.cc:33-68 (VTU; "" or "dir/": solution-NNN.vtu + shock.vtu)
       int write_shock_file (const std::string &path);              // src/output.cc:70-79
+      int compute_angular_momentum (double &value);                // src/claw.cc:604-635
       unsigned int output_file_number = 0;                         // the static counter of output.cc:47
       // run() writes the initial solution and then follows "output: time step / iter step" (src/claw.cc:1010-1017,
       // 1093-1099) into output_dir ("" = working directory like the reference) when enabled

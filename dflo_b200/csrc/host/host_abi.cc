@@ -137,6 +137,18 @@ int dflo_host_write_solution_vtu (const dflo_mesh *m, int basis, int degree, con
    return dflo_host_write_solution_piece_vtu (m, basis, degree, u, n, schlieren_plot, time, cycle, 0, -1, -1, path);
 }
 
+int dflo_host_angular_momentum (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, double *value)
+{
+   dflo::FeTables tab;
+   if (!m || !m->flattened || !u || !value || !dflo::build_tables (basis, degree, tab) || n != (size_t) m->flat.n_cells () * tab.D)
+   {
+      dflo::host_error () = "angular_momentum: mesh not flattened, unsupported element or wrong vector length";
+      return DFLO_E_INVALID;
+   }
+   *value = dflo::angular_momentum (tab, m->flat, u);
+   return DFLO_OK;
+}
+
 int dflo_host_write_shock_vtu (const dflo_mesh *m, const double *mu_shock, const double *shock_indicator, const char *path)
 {
    if (!m || !m->flattened || !shock_indicator || !path || !dflo::write_shock_vtu (m->flat, mu_shock, shock_indicator, path))

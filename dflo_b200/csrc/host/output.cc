@@ -127,6 +127,37 @@ namespace dflo
       return std::fclose (fp) == 0;
    }
 
+   // cell loop of compute_angular_momentum, src/claw.cc:604-635: QGauss(k+1)^2, cross = x m_y - y m_x
+   double angular_momentum (const FeTables &tab, const FlatMesh &flat, const double *u, int cell_begin, int cell_end)
+   {
+      if (cell_end < 0) cell_end = flat.n_cells ();
+      const int n1 = tab.n1, nq = n1 * n1, ns = tab.ns, D = tab.D;
+      double total = 0.0;
+      for (int cell = cell_begin; cell < cell_end; ++cell)
+      {
+         const double x0 = flat.origin[2 * cell], y0 = flat.origin[2 * cell + 1], hx = flat.size[2 * cell], hy = flat.size[2 * cell + 1];
+         const double *mx = &u[(size_t) cell * D], *my = mx + ns;
+         for (int q = 0; q < nq; ++q)
+         {
+            double vx = 0.0, vy = 0.0;
+            if (tab.basis == BASIS_QK) // collocated: the DoF is the value at the Gauss point
+            {
+               vx = mx[q];
+               vy = my[q];
+            }
+            else
+               for (int m = 0; m < ns; ++m)
+               {
+                  vx += tab.phi[q][m] * mx[m];
+                  vy += tab.phi[q][m] * my[m];
+               }
+            const double x = x0 + tab.gx[q % n1] * hx, y = y0 + tab.gx[q / n1] * hy;
+            total += (x * vy - y * vx) * (tab.gw[q % n1] * tab.gw[q / n1] * hx * hy);
+         }
+      }
+      return total;
+   }
+
    bool write_visit_record (const std::vector<std::vector<std::string>> &all_files, const std::string &path)
    {
       FILE *fp = std::fopen (path.c_str (), "w");

@@ -18,6 +18,8 @@ namespace dflo
    // subdomain >= 0 adding the "subdomain" array of src_mpi/output.cc:51-54; u is always the global vector.
    bool write_solution_vtu (const FeTables &tab, const FlatMesh &flat, const double *u, bool schlieren_plot, double time,
                             unsigned int cycle, const std::string &path, int cell_begin = 0, int cell_end = -1, int subdomain = -1);
+   // compute_angular_momentum (src/claw.cc:604-635): sum over cells [cell_begin, cell_end) of int (x m_y - y m_x)
+   double angular_momentum (const FeTables &tab, const FlatMesh &flat, const double *u, int cell_begin = 0, int cell_end = -1);
    // master_file.visit (DataOutBase::write_visit_record, src_mpi/output.cc:70-84): "!NBLOCKS n" and then the n piece
    // files of every output so far, one per line
    bool write_visit_record (const std::vector<std::vector<std::string>> &all_files, const std::string &path);

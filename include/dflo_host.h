@@ -81,6 +81,11 @@ int dflo_claw_write_vtu (dflo_claw *c, const char *path);
 /* dir != NULL: dflo_claw_run writes the initial solution and then follows "output: time step / iter step" and the
  * final time like src/claw.cc:1010-1017, 1093-1099 (dir "" = working directory, as the reference); NULL: off (default) */
 void dflo_claw_set_output (dflo_claw *c, const char *dir);
+/* compute_angular_momentum (src/claw.cc:604-635) of the cells this rank owns: int (x m_y - y m_x) with QGauss(k+1)^2.
+ * dflo_claw_run prints the reference's "Total angular momentum:" line every `output: compute angular momentum` steps
+ * (src/claw.cc:1075-1076) on unsharded setups. */
+int dflo_claw_angular_momentum (dflo_claw *c, double *value);
+int dflo_host_angular_momentum (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, double *value);
 /* the same writers on a host copy of the solution (reference DoF layout, n = n_cells * 4 * n_s), no engine involved;
  * mesh must be flattened.  shock file: mu_shock may be NULL (zeros); both arrays are written the way DataOut writes
  * cell vectors, as point data constant on the four vertices of each cell. */

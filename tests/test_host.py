@@ -512,3 +512,30 @@ def test_vtu_pieces_of_the_mpi_tree_tile_the_whole_file(lib, tmp_path):
         assert np.array_equal(np.concatenate(arrays[name]), fw["point"][name])
     with pytest.raises(abi.DfloError):
         mesh.write_solution_vtu(whole, u, "Pk", 2, cells=(5, nc + 1))
+
+
+@pytest.mark.parametrize("basis,k", [("Qk", 1), ("Qk", 3), ("Pk", 1), ("Pk", 2), ("Pk", 3)])
+def test_angular_momentum_of_a_polynomial_field(lib, basis, k):
+    """compute_angular_momentum (src/claw.cc:604-635): int (x m_y - y m_x) with QGauss(k+1)^2 per cell -- exact
+    for momentum of total degree <= k, checked against a much finer quadrature of the analytic field."""
+    bc = {0: "slip", 1: "outflow", 2: "inflow"}
+    params, pair = abi.make_params(bc=bc, basis=basis, degree=k)
+    nx, ny, x0, x1, y0, y1 = 5, 3, -0.4, 1.1, 0.2, 0.8
+    mesh = abi.Mesh("rectangle", [nx, ny, x0, x1, y0, y1, 0, 1, 2, 2], lib=lib)
+    mesh.flatten(params, pair)
+    v, c, bl, bi = mesh.primitive()
+    o = O.Oracle(v, c, bl, bi, O.make_params(bc=bc, basis=basis, degree=k))
+    mxf = lambda x, y: 0.3 + 0.7 * x ** k - 0.2 * y ** k + 0.5 * x ** (k - 1) * y
+    myf = lambda x, y: -0.1 + 0.4 * y ** k + 0.9 * x * y ** (k - 1)
+    xq = o.cell_qpoints()
+    X, Y = xq[..., 0], xq[..., 1]
+    o.set_initial_condition(np.stack([mxf(X, Y), myf(X, Y), 1.0 + 0 * X, 3.0 + 0 * X], axis=-1))
+    got = mesh.angular_momentum(o.solution(), basis, k)
+    g, w = np.polynomial.legendre.leggauss(12)
+    gx, wx = 0.5 * (x1 - x0) * g + 0.5 * (x1 + x0), 0.5 * (x1 - x0) * w
+    gy, wy = 0.5 * (y1 - y0) * g + 0.5 * (y1 + y0), 0.5 * (y1 - y0) * w
+    XX, YY = np.meshgrid(gx, gy, indexing="ij")
+    want = np.sum((XX * myf(XX, YY) - YY * mxf(XX, YY)) * wx[:, None] * wy[None, :])
+    assert abs(got - want) <= 1e-13 * max(1.0, abs(want))
+    with pytest.raises(abi.DfloError):
+        mesh.angular_momentum(o.solution()[:-1], basis, k)
