@@ -373,7 +373,7 @@ def test_run_loop_output_schedule_and_vtu_files(tmp_path):
     am = ctypes.c_double(0.0)                                          # compute_angular_momentum, src/claw.cc:604-635
     L.dflo_claw_angular_momentum.argtypes = [ctypes.c_void_p, abi.c_double_p]
     assert L.dflo_claw_angular_momentum(h, ctypes.cast(ctypes.byref(am), abi.c_double_p)) == 0
-    assert am.value == mesh.angular_momentum(u, "Pk", 2) and am.value < -1e-4
+    assert am.value == mesh.angular_momentum(u, "Pk", 2) and am.value < -1e-5
     sh = _read_vtu(out + "shock.vtu")
     assert sh["n_cells"] == nc and sh["point_names"] == ["mu_shock", "shock_indicator"]
     assert np.all(sh["point"]["shock_indicator"] == 1e20)               # `shock indicator = limiter`, src/indicator.cc:15-31
