@@ -24,7 +24,7 @@ cur_fn, cur_loc, active = None, None, False
 for ln in dis.splitlines():
     m = re.match(r"\s*\.section\s+\.text\.(\S+)", ln) or re.match(r"\s*//-+ \.text\.(\S+)", ln)
     if m:
-        active = pat in m.group(1) and ("phase_kernel" in m.group(1) or "persistent" in m.group(1)) and (KIND in m.group(1))
+        active = pat in m.group(1) and KIND in m.group(1)
         continue
     if not active:
         continue
