@@ -244,6 +244,10 @@ namespace dflo
       const int tid = threadIdx.x;
       const int *gdesc = A.rowdesc + (size_t) blockIdx.x * S::DESC_INTS;
       const int c0 = gdesc[0], ncb = gdesc[1], nh = gdesc[2];
+      // halo thread i = tid - TC: its cell id is requested together with the header, not after it (one trip less
+      // in front of the copies); entries past nh are inside the descriptor and unused
+      int halo_cell = 0;
+      if (tid >= TC && tid < TC + S::NH) halo_cell = gdesc[S::OFF_HALO + tid - TC];
       const bool need_old = A.mode == MODE_STAGE && A.ark != 0.0;
       constexpr unsigned cell_bytes = (unsigned) (D * sizeof (double));
 
@@ -266,10 +270,10 @@ namespace dflo
          mbar_expect_tx (sm, bytes);
       }
       __syncthreads ();
-      if (tid < ncb + nh)
+      if (tid < ncb || (tid >= TC && tid - TC < nh))
       {
-         const int cell = tid < ncb ? c0 + tid : gdesc[S::OFF_HALO + tid - ncb];
-         const int slot = tid < ncb ? tid : TC + tid - ncb;
+         const int cell = tid < TC ? c0 + tid : halo_cell;
+         const int slot = tid;
          bulk_g2s (su + slot * CS, A.u + (size_t) cell * D, cell_bytes, sm);
          if (flux_uses_averages (FLUX)) bulk_g2s (sAvg + slot * 4, A.avg + (size_t) cell * 4, 32u, sm);
       }
