@@ -132,6 +132,8 @@ def _declare_host(L):
     L.dflo_host_write_solution_piece_vtu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_size_t,
                                                      ctypes.c_int, ctypes.c_double, ctypes.c_uint, ctypes.c_int, ctypes.c_int,
                                                      ctypes.c_int, ctypes.c_char_p]
+    L.dflo_host_write_solution_tecplot.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_size_t,
+                                                   ctypes.c_int, ctypes.c_double, ctypes.c_char_p]
     L.dflo_host_angular_momentum.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_size_t, c_double_p]
     L.dflo_host_write_shock_vtu.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_char_p]
 
@@ -248,6 +250,14 @@ class Mesh:
         c0, c1 = (0, -1) if cells is None else cells
         rc = self.L.dflo_host_write_solution_piece_vtu(self.h, {"Qk": 0, "Pk": 1}[basis], degree, _dp(u), u.size,
                                                        int(schlieren_plot), time, cycle, c0, c1, subdomain, path.encode())
+        if rc:
+            raise DfloError(rc, self.L.dflo_host_last_error().decode())
+
+    def write_solution_tecplot(self, path, u, basis, degree, schlieren_plot=False, time=0.0):
+        """output_results with "output: format = tecplot" (src/output.cc:51-52, 65-66)."""
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        rc = self.L.dflo_host_write_solution_tecplot(self.h, {"Qk": 0, "Pk": 1}[basis], degree, _dp(u), u.size,
+                                                     int(schlieren_plot), time, path.encode())
         if rc:
             raise DfloError(rc, self.L.dflo_host_last_error().decode())
 

@@ -383,6 +383,7 @@ namespace dflo
       std::string path = path_in, dir;
       const bool numbered = path.empty () || path.back () == '/';
       const bool pieces = numbered && (world > 1 || compat == DFLO_COMPAT_MPI);
+      const bool tecplot = parameters.output_format == "tecplot"; // src only; src_mpi always writes vtu
       if (pieces)
       {
          dir = path;
@@ -401,12 +402,15 @@ namespace dflo
       {
          dir = path;
          char name[64];
-         std::snprintf (name, sizeof (name), "solution-%03u.vtu", output_file_number);
+         std::snprintf (name, sizeof (name), "solution-%03u.%s", output_file_number, tecplot ? "plt" : "vtu"); // output.cc:48-52
          path = dir + name;
          std::printf ("Writing file %s\n", path.c_str ());
       }
-      if (!write_solution_vtu (tab, flat, u.data (), parameters.schlieren_plot, elapsed_time, output_file_number, path, (int) c0,
-                               (int) c1, pieces ? rank : -1))
+      const bool written = (tecplot && numbered && !pieces)
+                              ? write_solution_tecplot (tab, flat, u.data (), parameters.schlieren_plot, elapsed_time, path)
+                              : write_solution_vtu (tab, flat, u.data (), parameters.schlieren_plot, elapsed_time, output_file_number, path,
+                                                    (int) c0, (int) c1, pieces ? rank : -1);
+      if (!written)
       {
          error = "cannot write " + path;
          return DFLO_E_INVALID;
@@ -417,7 +421,7 @@ namespace dflo
          return DFLO_E_INVALID;
       }
       if (numbered) ++output_file_number;
-      if (numbered && !pieces) return write_shock_file (dir + "shock.vtu");
+      if (numbered && !pieces) return write_shock_file (dir + (tecplot ? "shock.plt" : "shock.vtu"));
       return DFLO_OK;
    }
 
@@ -428,7 +432,8 @@ namespace dflo
       std::vector<double> ind ((size_t) flat.n_cells (), 0.0);
       const int rc = dflo_b200_get_shock_indicator (ctx, ind.data ());
       if (rc) return rc;
-      if (!write_shock_vtu (flat, nullptr, ind.data (), path))
+      const bool tecplot = path.size () > 4 && path.compare (path.size () - 4, 4, ".plt") == 0;
+      if (!(tecplot ? write_shock_tecplot (flat, nullptr, ind.data (), path) : write_shock_vtu (flat, nullptr, ind.data (), path)))
       {
          error = "cannot write " + path;
          return DFLO_E_INVALID;

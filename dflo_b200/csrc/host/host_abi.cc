@@ -137,6 +137,23 @@ int dflo_host_write_solution_vtu (const dflo_mesh *m, int basis, int degree, con
    return dflo_host_write_solution_piece_vtu (m, basis, degree, u, n, schlieren_plot, time, cycle, 0, -1, -1, path);
 }
 
+int dflo_host_write_solution_tecplot (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, int schlieren_plot,
+                                      double time, const char *path)
+{
+   dflo::FeTables tab;
+   if (!m || !m->flattened || !u || !path || !dflo::build_tables (basis, degree, tab) || n != (size_t) m->flat.n_cells () * tab.D)
+   {
+      dflo::host_error () = "write_solution_tecplot: mesh not flattened, unsupported element or wrong vector length";
+      return DFLO_E_INVALID;
+   }
+   if (!dflo::write_solution_tecplot (tab, m->flat, u, schlieren_plot != 0, time, path))
+   {
+      dflo::host_error () = std::string ("cannot write ") + path;
+      return DFLO_E_INVALID;
+   }
+   return DFLO_OK;
+}
+
 int dflo_host_angular_momentum (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, double *value)
 {
    dflo::FeTables tab;

@@ -49,6 +49,67 @@ namespace dflo
       }
    }
 
+   namespace
+   {
+      // values of the 4 conserved variables [point][4] and of |grad rho|^2 [point] at the (nsub+1)^2 patch
+      // vertices of cells [cell_begin, cell_end)
+      void eval_patches (const FeTables &tab, const FlatMesh &flat, const double *u, bool schlieren_plot, int cell_begin, int cell_end,
+                         std::vector<double> &val, std::vector<double> &schl)
+      {
+         const int nc = cell_end - cell_begin, ns = tab.ns, D = tab.D;
+         const int nsub = tab.k > 0 ? tab.k : 1, np1 = nsub + 1, npc = np1 * np1;
+         u += (size_t) cell_begin * D; // rows below are relative to the first cell written
+         // basis values and unit-cell gradients at the equispaced patch vertices
+         std::vector<double> phi ((size_t) npc * ns), dpx ((size_t) npc * ns), dpy ((size_t) npc * ns);
+         for (int j = 0; j < np1; ++j)
+            for (int i = 0; i < np1; ++i)
+            {
+               const size_t v = (size_t) (i + np1 * j) * ns;
+               eval_basis (tab, (double) i / nsub, (double) j / nsub, &phi[v], &dpx[v], &dpy[v]);
+            }
+         val.assign ((size_t) nc * npc * 4, 0.0);
+         schl.assign (schlieren_plot ? (size_t) nc * npc : 0, 0.0);
+         for (int cell = 0; cell < nc; ++cell)
+            for (int v = 0; v < npc; ++v)
+            {
+               const double *pv = &phi[(size_t) v * ns];
+               for (int c = 0; c < 4; ++c)
+               {
+                  const double *uc = &u[(size_t) cell * D + c * ns];
+                  double s = 0.0;
+                  for (int m = 0; m < ns; ++m) s += pv[m] * uc[m];
+                  val[((size_t) cell * npc + v) * 4 + c] = s;
+               }
+               if (schlieren_plot)
+               {
+                  // duh[density] . duh[density] in real coordinates (src/equation.cc:122-124)
+                  const double *ur = &u[(size_t) cell * D + 2 * ns];
+                  double gx = 0.0, gy = 0.0;
+                  for (int m = 0; m < ns; ++m)
+                  {
+                     gx += dpx[(size_t) v * ns + m] * ur[m];
+                     gy += dpy[(size_t) v * ns + m] * ur[m];
+                  }
+                  gx /= flat.size[2 * (cell_begin + cell)];
+                  gy /= flat.size[2 * (cell_begin + cell) + 1];
+                  schl[(size_t) cell * npc + v] = gx * gx + gy * gy;
+               }
+            }
+      }
+
+      // component_names (src/equation.h) then Postprocessor::get_names (src/equation.cc:130-145)
+      const char *const output_names[8] = {"XMomentum", "YMomentum", "Density", "Energy", "XVelocity", "YVelocity", "Pressure", "schlieren_plot"};
+
+      double output_value (int k, const double *w, const std::vector<double> &schl, size_t p)
+      {
+         if (k < 4) return w[k];
+         if (k == 4) return w[0] / w[2];
+         if (k == 5) return w[1] / w[2];
+         if (k == 6) return (gas_gamma - 1.0) * (w[3] - 0.5 * (w[0] * w[0] + w[1] * w[1]) / w[2]);
+         return schl[p];
+      }
+   }
+
    bool write_solution_vtu (const FeTables &tab, const FlatMesh &flat, const double *u, bool schlieren_plot, double time,
                             unsigned int cycle, const std::string &path, int cell_begin, int cell_end, int subdomain)
    {
@@ -56,65 +117,19 @@ namespace dflo
       if (cell_begin < 0 || cell_begin > cell_end || cell_end > flat.n_cells ()) return false;
       FILE *fp = std::fopen (path.c_str (), "w");
       if (!fp) return false;
-      const int nc = cell_end - cell_begin, ns = tab.ns, D = tab.D;
-      u += (size_t) cell_begin * D; // rows below are relative to the first cell written
-      const int nsub = tab.k > 0 ? tab.k : 1, np1 = nsub + 1, npc = np1 * np1;
-      // basis values and unit-cell gradients at the equispaced patch vertices
-      std::vector<double> phi ((size_t) npc * ns), dpx ((size_t) npc * ns), dpy ((size_t) npc * ns);
-      for (int j = 0; j < np1; ++j)
-         for (int i = 0; i < np1; ++i)
-         {
-            const size_t v = (size_t) (i + np1 * j) * ns;
-            eval_basis (tab, (double) i / nsub, (double) j / nsub, &phi[v], &dpx[v], &dpy[v]);
-         }
-      std::vector<double> val ((size_t) nc * npc * 4), schl (schlieren_plot ? (size_t) nc * npc : 0);
-      for (int cell = 0; cell < nc; ++cell)
-         for (int v = 0; v < npc; ++v)
-         {
-            const double *pv = &phi[(size_t) v * ns];
-            for (int c = 0; c < 4; ++c)
-            {
-               const double *uc = &u[(size_t) cell * D + c * ns];
-               double s = 0.0;
-               for (int m = 0; m < ns; ++m) s += pv[m] * uc[m];
-               val[((size_t) cell * npc + v) * 4 + c] = s;
-            }
-            if (schlieren_plot)
-            {
-               // duh[density] . duh[density] in real coordinates (src/equation.cc:122-124)
-               const double *ur = &u[(size_t) cell * D + 2 * ns];
-               double gx = 0.0, gy = 0.0;
-               for (int m = 0; m < ns; ++m)
-               {
-                  gx += dpx[(size_t) v * ns + m] * ur[m];
-                  gy += dpy[(size_t) v * ns + m] * ur[m];
-               }
-               gx /= flat.size[2 * (cell_begin + cell)];
-               gy /= flat.size[2 * (cell_begin + cell) + 1];
-               schl[(size_t) cell * npc + v] = gx * gx + gy * gy;
-            }
-         }
+      const int nc = cell_end - cell_begin;
+      const int nsub = tab.k > 0 ? tab.k : 1, npc = (nsub + 1) * (nsub + 1);
+      std::vector<double> val, schl;
+      eval_patches (tab, flat, u, schlieren_plot, cell_begin, cell_end, val, schl);
       vtu_head (fp, npc * nc, nc * nsub * nsub, time, cycle, true);
       vtu_points (fp, flat, nsub, cell_begin, cell_end);
       vtu_cells (fp, nc, nsub);
       std::fprintf (fp, "<PointData>\n");
-      // component_names (src/equation.h) then Postprocessor::get_names (src/equation.cc:130-145)
-      const char *names[8] = {"XMomentum", "YMomentum", "Density", "Energy", "XVelocity", "YVelocity", "Pressure", "schlieren_plot"};
       const int n_arrays = schlieren_plot ? 8 : 7;
       for (int k = 0; k < n_arrays; ++k)
       {
-         std::fprintf (fp, "<DataArray type=\"Float64\" Name=\"%s\" format=\"ascii\">\n", names[k]);
-         for (size_t p = 0; p < (size_t) nc * npc; ++p)
-         {
-            const double *w = &val[p * 4];
-            double v;
-            if (k < 4) v = w[k];
-            else if (k == 4) v = w[0] / w[2];
-            else if (k == 5) v = w[1] / w[2];
-            else if (k == 6) v = (gas_gamma - 1.0) * (w[3] - 0.5 * (w[0] * w[0] + w[1] * w[1]) / w[2]);
-            else v = schl[p];
-            std::fprintf (fp, "%.10g\n", v);
-         }
+         std::fprintf (fp, "<DataArray type=\"Float64\" Name=\"%s\" format=\"ascii\">\n", output_names[k]);
+         for (size_t p = 0; p < (size_t) nc * npc; ++p) std::fprintf (fp, "%.10g\n", output_value (k, &val[p * 4], schl, p));
          std::fprintf (fp, "</DataArray>\n");
       }
       if (subdomain >= 0) // locally_owned_subdomain of every cell of the piece, src_mpi/output.cc:51-54
@@ -124,6 +139,68 @@ namespace dflo
          std::fprintf (fp, "</DataArray>\n");
       }
       std::fprintf (fp, "</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+      return std::fclose (fp) == 0;
+   }
+
+   // "output: format = tecplot" (src/output.cc:51-52, 65-66): DataOut::write_tecplot -- ASCII FEBLOCK zone of
+   // quadrilaterals: all x, all y, then every variable over the same patch vertices, then 1-based connectivity
+   bool write_solution_tecplot (const FeTables &tab, const FlatMesh &flat, const double *u, bool schlieren_plot, double time,
+                                const std::string &path)
+   {
+      FILE *fp = std::fopen (path.c_str (), "w");
+      if (!fp) return false;
+      const int nc = flat.n_cells ();
+      const int nsub = tab.k > 0 ? tab.k : 1, np1 = nsub + 1, npc = np1 * np1;
+      std::vector<double> val, schl;
+      eval_patches (tab, flat, u, schlieren_plot, 0, nc, val, schl);
+      const int n_arrays = schlieren_plot ? 8 : 7;
+      std::fprintf (fp, "# This file was generated by dflo_b200 in the layout of the deal.II tecplot writer.\n#\n"
+                        "# For a description of the Tecplot format see the Tecplot documentation.\n#\nVariables=\"x\", \"y\"");
+      for (int k = 0; k < n_arrays; ++k) std::fprintf (fp, ", \"%s\"", output_names[k]);
+      std::fprintf (fp, "\nzone t=\"time=%.10g\" f=feblock, n=%d, e=%d, et=quadrilateral\n", time, nc * npc, nc * nsub * nsub);
+      for (int d = 0; d < 2; ++d)
+      {
+         for (int cell = 0; cell < nc; ++cell)
+            for (int j = 0; j < np1; ++j)
+               for (int i = 0; i < np1; ++i)
+                  std::fprintf (fp, "%.10g\n", flat.origin[2 * cell + d] + (double) (d == 0 ? i : j) / nsub * flat.size[2 * cell + d]);
+         std::fprintf (fp, "\n");
+      }
+      for (int k = 0; k < n_arrays; ++k)
+      {
+         for (size_t p = 0; p < (size_t) nc * npc; ++p) std::fprintf (fp, "%.10g\n", output_value (k, &val[p * 4], schl, p));
+         std::fprintf (fp, "\n");
+      }
+      for (int cell = 0; cell < nc; ++cell)
+         for (int j = 0; j < nsub; ++j)
+            for (int i = 0; i < nsub; ++i)
+            {
+               const int p0 = cell * npc + i + np1 * j + 1;
+               std::fprintf (fp, "%d %d %d %d\n", p0, p0 + 1, p0 + 1 + np1, p0 + np1);
+            }
+      return std::fclose (fp) == 0;
+   }
+
+   // shock.plt (src/output.cc:80-84)
+   bool write_shock_tecplot (const FlatMesh &flat, const double *mu_shock, const double *shock_indicator, const std::string &path)
+   {
+      FILE *fp = std::fopen (path.c_str (), "w");
+      if (!fp) return false;
+      const int nc = flat.n_cells ();
+      std::fprintf (fp, "# This file was generated by dflo_b200 in the layout of the deal.II tecplot writer.\n#\n"
+                        "Variables=\"x\", \"y\", \"mu_shock\", \"shock_indicator\"\n"
+                        "zone t=\"\" f=feblock, n=%d, e=%d, et=quadrilateral\n", 4 * nc, nc);
+      for (int d = 0; d < 2; ++d)
+      {
+         for (int cell = 0; cell < nc; ++cell)
+            for (int v = 0; v < 4; ++v) std::fprintf (fp, "%.10g\n", flat.origin[2 * cell + d] + (d == 0 ? v % 2 : v / 2) * flat.size[2 * cell + d]);
+         std::fprintf (fp, "\n");
+      }
+      for (int i = 0; i < 4 * nc; ++i) std::fprintf (fp, "%.10g\n", mu_shock ? mu_shock[i / 4] : 0.0);
+      std::fprintf (fp, "\n");
+      for (int i = 0; i < 4 * nc; ++i) std::fprintf (fp, "%.10g\n", shock_indicator[i / 4]);
+      std::fprintf (fp, "\n");
+      for (int cell = 0; cell < nc; ++cell) std::fprintf (fp, "%d %d %d %d\n", 4 * cell + 1, 4 * cell + 2, 4 * cell + 4, 4 * cell + 3);
       return std::fclose (fp) == 0;
    }
 

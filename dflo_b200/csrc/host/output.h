@@ -18,6 +18,11 @@ namespace dflo
    // subdomain >= 0 adding the "subdomain" array of src_mpi/output.cc:51-54; u is always the global vector.
    bool write_solution_vtu (const FeTables &tab, const FlatMesh &flat, const double *u, bool schlieren_plot, double time,
                             unsigned int cycle, const std::string &path, int cell_begin = 0, int cell_end = -1, int subdomain = -1);
+   // solution-NNN.plt for "output: format = tecplot" (src/output.cc:51-52, 65-66): the same patches and variables as
+   // an ASCII FEBLOCK zone of quadrilaterals
+   bool write_solution_tecplot (const FeTables &tab, const FlatMesh &flat, const double *u, bool schlieren_plot, double time,
+                                const std::string &path);
+   bool write_shock_tecplot (const FlatMesh &flat, const double *mu_shock, const double *shock_indicator, const std::string &path);
    // compute_angular_momentum (src/claw.cc:604-635): sum over cells [cell_begin, cell_end) of int (x m_y - y m_x)
    double angular_momentum (const FeTables &tab, const FlatMesh &flat, const double *u, int cell_begin = 0, int cell_end = -1);
    // master_file.visit (DataOutBase::write_visit_record, src_mpi/output.cc:70-84): "!NBLOCKS n" and then the n piece

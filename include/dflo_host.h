@@ -91,6 +91,11 @@ int dflo_host_angular_momentum (const dflo_mesh *m, int basis, int degree, const
  * cell vectors, as point data constant on the four vertices of each cell. */
 int dflo_host_write_solution_vtu (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, int schlieren_plot,
                                   double time, unsigned int cycle, const char *path);
+/* "output: format = tecplot" (src/output.cc:51-52, 65-66): the same patches and variables as an ASCII FEBLOCK zone of
+ * quadrilaterals; dflo_claw_write_vtu / the run loop write solution-NNN.plt + shock.plt instead of .vtu when the input
+ * file asks for it (src tree only; src_mpi always writes vtu) */
+int dflo_host_write_solution_tecplot (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, int schlieren_plot,
+                                      double time, const char *path);
 /* the piece of cells [cell_begin, cell_end) (cell_end < 0: to the last cell); subdomain >= 0 adds the "subdomain" array */
 int dflo_host_write_solution_piece_vtu (const dflo_mesh *m, int basis, int degree, const double *u, size_t n, int schlieren_plot,
                                         double time, unsigned int cycle, int cell_begin, int cell_end, int subdomain, const char *path);

@@ -390,6 +390,20 @@ def test_run_loop_output_schedule_and_vtu_files(tmp_path):
     assert sorted(os.listdir(out2)) == ["master_file.visit", "output"]
     assert sorted(os.listdir(out2 + "output")) == ["solution-%04d.000.vtu" % i for i in range(3)]
     assert open(out2 + "master_file.visit").read().split() == ["!NBLOCKS", "1"] + ["output/solution-%04d.000.vtu" % i for i in range(3)]
+    L.dflo_claw_destroy(h)
+    # "output: format = tecplot" (src/output.cc:51-52, 65-66, 80-84): solution-NNN.plt + shock.plt
+    out3 = out + "plt/"
+    os.makedirs(out3)
+    h = ctypes.c_void_p(L.dflo_claw_create(os.path.join(PRM_DIR, "cfg3_sod_P2_hllc_tvb_pos.prm").encode(), b"sod_tube 20 2",
+                                           b"subsection output\n set iter step = 1\n set format = tecplot\nend\n", abi.COMPAT["src"]))
+    assert h, L.dflo_host_last_error()
+    L.dflo_claw_set_output(h, out3.encode())
+    assert L.dflo_claw_setup(h, 0, 0, 1, None) == 0, L.dflo_host_last_error()
+    assert L.dflo_claw_run(h, 1, 0, ctypes.byref(t), ctypes.byref(done)) == 0, L.dflo_host_last_error()
+    assert sorted(os.listdir(out3)) == ["shock.plt", "solution-000.plt", "solution-001.plt"]
+    head = open(out3 + "solution-001.plt").read(600)
+    assert '"XMomentum", "YMomentum", "Density", "Energy", "XVelocity", "YVelocity", "Pressure"' in head
+    assert "f=feblock, n=360, e=160, et=quadrilateral" in head
     f = _read_vtu(out2 + "output/solution-0002.000.vtu")
     assert f["n_cells"] == 64 and f["point_names"][-2:] == ["Pressure", "subdomain"] and np.all(f["point"]["subdomain"] == 0)
     L.dflo_claw_destroy(h)

@@ -539,3 +539,29 @@ def test_angular_momentum_of_a_polynomial_field(lib, basis, k):
     assert abs(got - want) <= 1e-13 * max(1.0, abs(want))
     with pytest.raises(abi.DfloError):
         mesh.angular_momentum(o.solution()[:-1], basis, k)
+
+
+def test_tecplot_output_carries_the_same_patches_as_the_vtu(lib, tmp_path):
+    """"output: format = tecplot" (src/output.cc:51-52, 65-66): FEBLOCK zone, x / y / variables over the same patch
+    vertices as the VTU file, 1-based counter-clockwise quadrilaterals."""
+    bc = {0: "slip", 1: "outflow", 2: "inflow"}
+    params, pair = abi.make_params(bc=bc, basis="Qk", degree=2)
+    mesh = abi.Mesh("sod_tube", [6, 2], lib=lib)
+    mesh.flatten(params, pair)
+    nc, D = mesh.n_cells, 36
+    u = np.random.default_rng(5).uniform(0.5, 2.0, nc * D)
+    vtu, plt = str(tmp_path / "s.vtu"), str(tmp_path / "s.plt")
+    mesh.write_solution_vtu(vtu, u, "Qk", 2, schlieren_plot=True, time=0.125)
+    mesh.write_solution_tecplot(plt, u, "Qk", 2, schlieren_plot=True, time=0.125)
+    f = _read_vtu(vtu)
+    lines = [ln for ln in open(plt).read().splitlines() if not ln.startswith("#")]
+    assert lines[0] == 'Variables="x", "y", ' + ", ".join('"%s"' % n for n in f["point_names"])
+    assert lines[1] == 'zone t="time=0.125" f=feblock, n=%d, e=%d, et=quadrilateral' % (f["n_points"], f["n_cells"])
+    blocks = "\n".join(lines[2:]).split("\n\n")
+    assert len(blocks) == 2 + 8 + 1
+    np.testing.assert_array_equal(np.array(blocks[0].split(), float), f["points"][:, 0])
+    np.testing.assert_array_equal(np.array(blocks[1].split(), float), f["points"][:, 1])
+    for i, name in enumerate(f["point_names"]):
+        np.testing.assert_array_equal(np.array(blocks[2 + i].split(), float), f["point"][name])
+    conn = np.array(blocks[-1].split(), int).reshape(-1, 4)
+    np.testing.assert_array_equal(conn - 1, f["cells"]["connectivity"].reshape(-1, 4))
