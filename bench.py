@@ -89,7 +89,9 @@ def sample_clocks(stop, out, ready=None):
         pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
         if ready is not None:
             ready.set()
-        while not stop.is_set():
+        last = False
+        while not last:
+            last = stop.is_set()      # one more sample after the stop request: a slow NVML never leaves the list empty
             sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
             try:
                 r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
