@@ -433,8 +433,8 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "cells": nx * ny, "dofs": n_dof, "rk_stages": n_rk,
-                       "parallelism": "cells sharded by id over %d GPU(s), 1 halo exchange per stage over NVLink peer memory "
-                                      "(fused into the stage kernel)" % world,
+                       "parallelism": ("cells sharded by id over %d GPUs, 1 halo exchange per stage over NVLink peer memory "
+                                       "(fused into the stage kernel)" % world) if world > 1 else "one GPU, no exchange",
                        "l2": "flushed before every timed step (256 MB rewrite)" if flush is not None else "not flushed",
                        "timing": "CUDA events on the ctx stream around each step's graph launch, summed, max over ranks"},
             "value_back_to_back_no_flush": updates_per_step * args.steps / (ms_b2b * 1e-3) / 1e6,
@@ -442,7 +442,7 @@ def main():
             "e2e": e2e_entry(updates_per_step, e2e_steps, e2e_s, e2e_pipe_s, E2E_CTX, owned_dof),
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(args.workload) if world == 1 else None, "kernel": "StageKernel<%s,%d,%s>" % (basis, k + 1, flux),
+                         "traffic": measured_traffic(args.workload) if world == 1 else None, "kernel": "row_stage_kernel<%d,%s>" % (k + 1, flux) if basis == "Qk" else "PkCellStageKernel<%d,%s>" % (k + 1, flux),
                          "kernel_ms": k_ms, "kernel_ms_l2_warm": k_ms_warm,
                          "algorithmic_bytes_per_launch": alg_bytes_launch,
                          "bytes_per_dof_update": bytes_per_update, "peak_source": peak_src},
