@@ -125,9 +125,20 @@ namespace dflo
       vtu_points (fp, flat, nsub, cell_begin, cell_end);
       vtu_cells (fp, nc, nsub);
       std::fprintf (fp, "<PointData>\n");
-      const int n_arrays = schlieren_plot ? 8 : 7;
-      for (int k = 0; k < n_arrays; ++k)
+      // DataOutBase::write_vtu writes the vector-valued ranges first -- the momentum (component_interpretation,
+      // src/equation.h:48-59) and the velocity (Postprocessor, src/equation.cc:147-166), each as one 3-component array
+      // named by its components joined with "__" -- and then the scalars in the order they were added
+      for (int k0 : {0, 4})
       {
+         std::fprintf (fp, "<DataArray type=\"Float64\" Name=\"%s__%s\" NumberOfComponents=\"3\" format=\"ascii\">\n", output_names[k0],
+                       output_names[k0 + 1]);
+         for (size_t p = 0; p < (size_t) nc * npc; ++p)
+            std::fprintf (fp, "%.10g %.10g 0\n", output_value (k0, &val[p * 4], schl, p), output_value (k0 + 1, &val[p * 4], schl, p));
+         std::fprintf (fp, "</DataArray>\n");
+      }
+      for (int k : {2, 3, 6, 7})
+      {
+         if (k == 7 && !schlieren_plot) continue;
          std::fprintf (fp, "<DataArray type=\"Float64\" Name=\"%s\" format=\"ascii\">\n", output_names[k]);
          for (size_t p = 0; p < (size_t) nc * npc; ++p) std::fprintf (fp, "%.10g\n", output_value (k, &val[p * 4], schl, p));
          std::fprintf (fp, "</DataArray>\n");

@@ -12,8 +12,9 @@ namespace dflo
 {
    // solution-NNN.vtu: what DataOut::build_patches (mapping, fe.degree) + write_vtu produce for a DG field --
    // every cell is cut into max(degree,1)^2 sub-quads whose vertices carry the cell's own polynomial, so the
-   // field stays discontinuous across cells.  Point data: XMomentum YMomentum Density Energy XVelocity
-   // YVelocity Pressure [schlieren_plot] [subdomain].  Returns false when the file cannot be written.
+   // field stays discontinuous across cells.  Point data as DataOutBase::write_vtu orders them: the vector ranges
+   // XMomentum__YMomentum and XVelocity__YVelocity (3 components, z = 0), then the scalars Density Energy Pressure
+   // [schlieren_plot] [subdomain].  Returns false when the file cannot be written.
    // [cell_begin, cell_end) (cell_end < 0: all cells): the piece one process of the MPI tree writes, with
    // subdomain >= 0 adding the "subdomain" array of src_mpi/output.cc:51-54; u is always the global vector.
    bool write_solution_vtu (const FeTables &tab, const FlatMesh &flat, const double *u, bool schlieren_plot, double time,

@@ -75,8 +75,9 @@ int dflo_claw_get_solution (dflo_claw *c, double *u, size_t n);
  *   compat src, one process: solution-NNN.vtu + shock.vtu;
  *   compat mpi, or a sharded setup: output/solution-NNNN.RRR.vtu (this rank's cells, extra array "subdomain") and, on
  *   rank 0, master_file.visit.
- * Every cell is written as degree x degree sub-quads like DataOut::build_patches (mapping, fe.degree); point data
- * XMomentum YMomentum Density Energy XVelocity YVelocity Pressure [schlieren_plot] (src/equation.cc:59-145). */
+ * Every cell is written as degree x degree sub-quads like DataOut::build_patches (mapping, fe.degree); point data in
+ * the order of DataOutBase::write_vtu: the vector ranges XMomentum__YMomentum and XVelocity__YVelocity (3 components),
+ * then Density Energy Pressure [schlieren_plot] (src/equation.h:32-59, src/equation.cc:59-166). */
 int dflo_claw_write_vtu (dflo_claw *c, const char *path);
 /* dir != NULL: dflo_claw_run writes the initial solution and then follows "output: time step / iter step" and the
  * final time like src/claw.cc:1010-1017, 1093-1099 (dir "" = working directory, as the reference); NULL: off (default) */

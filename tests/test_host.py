@@ -386,6 +386,12 @@ def _read_vtu(path):
                point_names=[e.get("Name") for e in kids("PointData")],
                cell_names=[e.get("Name") for e in kids("CellData")])
     out["point"] = {e.get("Name"): arr(e) for e in kids("PointData")}
+    for e in kids("PointData"):          # vector ranges "A__B" (3 components, z = 0): also under their component names
+        if e.get("NumberOfComponents") == "3":
+            v = arr(e).reshape(-1, 3)
+            assert np.all(v[:, 2] == 0)
+            for i, n in enumerate(e.get("Name").split("__")):
+                out["point"][n] = v[:, i]
     out["cell"] = {e.get("Name"): arr(e) for e in kids("CellData")}
     return out
 
@@ -426,8 +432,8 @@ def test_vtu_output_reproduces_the_dg_polynomial(lib, tmp_path, basis, k):
     nsub = max(k, 1)
     nc = nx * ny
     assert f["n_points"] == nc * (nsub + 1) ** 2 and f["n_cells"] == nc * nsub ** 2
-    assert f["point_names"] == ["XMomentum", "YMomentum", "Density", "Energy", "XVelocity", "YVelocity", "Pressure",
-                                "schlieren_plot"]
+    # DataOutBase::write_vtu: vector ranges first (momentum, velocity), then the scalars in the order added
+    assert f["point_names"] == ["XMomentum__YMomentum", "XVelocity__YVelocity", "Density", "Energy", "Pressure", "schlieren_plot"]
     # geometry: every cell's own (nsub+1)^2 lexicographic vertices, nothing shared between cells
     fa = mesh.flat_arrays()
     t = np.arange(nsub + 1) / nsub
@@ -555,13 +561,14 @@ def test_tecplot_output_carries_the_same_patches_as_the_vtu(lib, tmp_path):
     mesh.write_solution_tecplot(plt, u, "Qk", 2, schlieren_plot=True, time=0.125)
     f = _read_vtu(vtu)
     lines = [ln for ln in open(plt).read().splitlines() if not ln.startswith("#")]
-    assert lines[0] == 'Variables="x", "y", ' + ", ".join('"%s"' % n for n in f["point_names"])
+    names = ["XMomentum", "YMomentum", "Density", "Energy", "XVelocity", "YVelocity", "Pressure", "schlieren_plot"]
+    assert lines[0] == 'Variables="x", "y", ' + ", ".join('"%s"' % n for n in names)   # tecplot: one variable per component
     assert lines[1] == 'zone t="time=0.125" f=feblock, n=%d, e=%d, et=quadrilateral' % (f["n_points"], f["n_cells"])
     blocks = "\n".join(lines[2:]).split("\n\n")
     assert len(blocks) == 2 + 8 + 1
     np.testing.assert_array_equal(np.array(blocks[0].split(), float), f["points"][:, 0])
     np.testing.assert_array_equal(np.array(blocks[1].split(), float), f["points"][:, 1])
-    for i, name in enumerate(f["point_names"]):
+    for i, name in enumerate(names):
         np.testing.assert_array_equal(np.array(blocks[2 + i].split(), float), f["point"][name])
     conn = np.array(blocks[-1].split(), int).reshape(-1, 4)
     np.testing.assert_array_equal(conn - 1, f["cells"]["connectivity"].reshape(-1, 4))
