@@ -572,3 +572,15 @@ def test_tecplot_output_carries_the_same_patches_as_the_vtu(lib, tmp_path):
         np.testing.assert_array_equal(np.array(blocks[2 + i].split(), float), f["point"][name])
     conn = np.array(blocks[-1].split(), int).reshape(-1, 4)
     np.testing.assert_array_equal(conn - 1, f["cells"]["connectivity"].reshape(-1, 4))
+
+
+def test_bench_e2e_entry_contract():
+    """bench.py `e2e`: the contract keys, and the batches-in-flight figure next to the serial chain."""
+    import bench
+    serial = bench.e2e_entry(12_000_000, 20, 0.03, None, 3, 4_194_304)
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(serial)
+    assert serial["in_flight"] == 1 and serial["h2d_bytes_per_step"] == serial["d2h_bytes_per_step"] == 4_194_304 * 8
+    assert abs(serial["value"] - 12_000_000 * 20 / 0.03 / 1e6) < 1e-6
+    piped = bench.e2e_entry(12_000_000, 20, 0.03, 0.05, 3, 4_194_304)
+    assert piped["in_flight"] == 3 and piped["steps"] == 60 and piped["value_one_context_serial"] == serial["value"]
+    assert abs(piped["value"] - 12_000_000 * 60 / 0.05 / 1e6) < 1e-6
