@@ -164,7 +164,18 @@ namespace dflo
       {
          const int cell = bid * THREADS + tid;
          if (p == 0)
-            sm[tid] = cell < A.n_cells ? cell_time_step (A.avg + (size_t) cell * 4, A.geom + (size_t) cell * 4, A.cfl, A.degree) : 1.0e20;
+         {
+            double d = 1.0e20;
+            if (cell < A.n_cells)
+            {
+               d = cell_time_step (A.avg + (size_t) cell * 4, A.geom + (size_t) cell * 4, A.cfl, A.degree);
+               // a NaN or non-positive cell value (negative density / pressure in the mean) must not poison the
+               // block minimum, nor take part in the bit-pattern atomicMin below: the cell is skipped, as
+               // `std::min (global_dt, dt(c))` skips a NaN in the reference (claw.cc:508)
+               if (!(d > 0.0)) d = 1.0e20;
+            }
+            sm[tid] = d;
+         }
          else if (p == 1)
          {
             if (tid < 16)
@@ -223,6 +234,20 @@ namespace dflo
          if (j != 0) return;
          double dt = A.time[2];
          if (dt > 0 && A.time_step > 0) dt = std_min (dt, A.time_step);
+         if (A.time[0] + dt > A.time[3]) dt = A.time[3] - A.time[0];
+         A.time[1] = dt;
+         A.time[2] = 1.0e20;
+      }
+   };
+   struct FixedDtKernel // claw.cc:457-461: "time step" of the input file when cfl <= 0 (global time stepping)
+   {
+      typedef DtFinalizeArgs Args;
+      static DFLO_DEV void thread (const Args &A, int j)
+      {
+         if (j != 0) return;
+         // the reference leaves global_dt untouched in this branch; the sensible reading (and what the
+         // host front end did in round 1) is dt = time_step, clipped so that t + dt <= final time
+         double dt = A.time_step;
          if (A.time[0] + dt > A.time[3]) dt = A.time[3] - A.time[0];
          A.time[1] = dt;
          A.time[2] = 1.0e20;
@@ -488,6 +513,8 @@ namespace dflo
          if (p.limiter_type == DFLO_LIMITER_MINMAX && p.basis != DFLO_BASIS_QK) // src_mpi/parameters.cc:610-611
             return fail (DFLO_E_UNSUPPORTED, "minmax limiter is implemented only for Qk");
          if (mesh.n_cells <= 0) return fail (DFLO_E_INVALID, "empty mesh");
+         // claw.cc:457-461: cfl <= 0 selects the fixed time step of the input file, which must then be given
+         if (!(p.cfl > 0.0) && !(p.time_step > 0.0)) return fail (DFLO_E_INVALID, "cfl <= 0 needs a positive time step");
          for (int b = 0; b < mesh.n_boundary_faces; ++b)
             if (mesh.bface_id[b] < 0 || mesh.bface_id[b] >= DFLO_MAX_BOUNDARIES) return fail (DFLO_E_INVALID, "boundary id out of range");
          // claw.cc:141-159
@@ -501,6 +528,9 @@ namespace dflo
          const bool row = bk.use_row_kernel (tab.basis, tab.n1);
          const int tx = row ? row_tx (tab.n1) : tile_nx (tab.n1), ty = row ? row_ty (tab.n1) : tile_ny (tab.n1);
          if (!build_local_mesh (mesh, rank, world, layers, tx, ty, lm, e, row)) return fail (DFLO_E_INVALID, e);
+         // the 1-D kernels (layout, pack, cell averages) index DoFs with 32-bit ints
+         if ((int64_t) lm.n_local * D () > (int64_t) 0x7fffffff)
+            return fail (DFLO_E_UNSUPPORTED, "more than 2^31-1 DoFs on one rank: shard the mesh over more GPUs");
          bk.prepare_tables (tab, pack_stage_tables (tab));
          if (row) d_rowdesc = upload (lm.rowdesc);
          n_global_bfaces = mesh.n_boundary_faces;
@@ -1074,6 +1104,14 @@ namespace dflo
 
       void enqueue_dt ()
       {
+         if (prm.cfl <= 0.0) // claw.cc:457-461: the time step of the input file, no cell loop
+         {
+            DtFinalizeArgs f;
+            f.time = d_time;
+            f.time_step = prm.time_step;
+            bk.template launch1d<FixedDtKernel> (1, f);
+            return;
+         }
          DtArgs a;
          a.avg = AVG[cur];
          a.geom = d_geom;
@@ -1190,6 +1228,9 @@ namespace dflo
          }
          if (dof_map)
          {
+            // a bad map would read or write device memory out of bounds in LayoutKernel
+            for (size_t i = 0; i < n; ++i)
+               if ((size_t) dof_map[i] >= n) return fail (DFLO_E_INVALID, "dof_map entry out of range");
             if (dofmap_capacity < n)
             {
                bk.sync ();

@@ -153,7 +153,7 @@ namespace dflo
 
    // set_initial_condition: Qk interpolates at the support (= Gauss) points, Pk projects with
    // QGauss(k+1) and the diagonal mass matrix (src/ic.cc:104-182)
-   void ConservationLaw::set_initial_condition (std::vector<double> &u) const
+   int ConservationLaw::set_initial_condition (std::vector<double> &u, std::string &err) const
    {
       const int nc = flat.n_cells (), n1 = tab.n1, ns = tab.ns, D = tab.D, nq = tab.nq;
       u.assign ((size_t) nc * D, 0.0);
@@ -163,8 +163,14 @@ namespace dflo
       {
          ExprCompiler cc;
          std::string e;
+         // FunctionParser::initialize throws on a syntax error (src/parameters.cc:524-526): report it
+         // instead of running on a component that silently evaluates to zero
          for (int c = 0; c < 4; ++c)
-            if (!cc.compile (parameters.ic_expr[c], code[c], e)) code[c].clear ();
+            if (!cc.compile (parameters.ic_expr[c], code[c], e))
+            {
+               err = "initial condition: w_" + std::to_string (c) + " value: " + e;
+               return DFLO_E_EXPR;
+            }
       }
       std::vector<double> f ((size_t) nq * 4);
       for (int cell = 0; cell < nc; ++cell)
@@ -199,6 +205,7 @@ namespace dflo
                }
          }
       }
+      return DFLO_OK;
    }
 
    // setup_system (src/claw.cc:270-386) + the start of run() (:981-1003)
@@ -243,7 +250,8 @@ namespace dflo
          }
       }
       std::vector<double> u;
-      set_initial_condition (u);
+      rc = set_initial_condition (u, error);
+      if (rc) return rc;
       rc = dflo_b200_set_solution (ctx, u.data (), nullptr, u.size ());   // also cell averages (:997)
       if (!rc) rc = dflo_b200_limit_initial_condition (ctx);              // :1000-1002
       if (rc) error = dflo_b200_last_error (ctx);
@@ -506,7 +514,12 @@ const char *dflo_claw_boundary_expression (const dflo_claw *c, int id, int comp)
 int dflo_claw_initial_condition (dflo_claw *c, double *u, size_t n)
 {
    std::vector<double> v;
-   c->claw->set_initial_condition (v);
+   const int rc = c->claw->set_initial_condition (v, c->claw->error);
+   if (rc)
+   {
+      dflo::host_error () = c->claw->error;
+      return rc;
+   }
    if (v.size () != n) return DFLO_E_INVALID;
    std::memcpy (u, v.data (), n * sizeof (double));
    return DFLO_OK;

@@ -32,7 +32,7 @@ namespace dflo
       // the time loop (src/claw.cc:1026-1110), at most max_steps steps (<0: until final time)
       int run (int max_steps, bool verbose);
 
-      void set_initial_condition (std::vector<double> &u) const;   // src/ic.cc:104-182
+      int set_initial_condition (std::vector<double> &u, std::string &err) const;   // src/ic.cc:104-182
       int get_solution (std::vector<double> &u);
       int output_results (const std::string &path);                // src/output.cc:33-68 (VTU; "" or "dir/": solution-NNN.vtu + shock.vtu)
       int write_shock_file (const std::string &path);              // src/output.cc:70-79

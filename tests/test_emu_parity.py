@@ -316,3 +316,41 @@ def test_pk_cell_kernel_sod_tvb_positivity_sharded(pk_cell_kernel, world):
     assert many.rel_err() <= TOL_STEP_SHOCK and flips == 0
     one.close()
     many.close()
+
+
+def test_fixed_time_step_when_cfl_is_not_positive():
+    """claw.cc:457-461: global time stepping with cfl <= 0 takes `time step` from the input file -- through
+    compute_dt and through advance (which must not take silent zero-length steps), clipped at the final time;
+    cfl <= 0 without a time step is refused at creation."""
+    c = Case(("isentropic_vortex", [6]), PERIODIC_BOX, ic_vortex, basis="Qk", degree=1, flux="lxf", cfl=0.0, time_step=1e-3)
+    e = c.engine
+    assert e.compute_dt(0.0) == 1e-3
+    assert e.compute_dt(0.0, final_time=4e-4) == 4e-4
+    t, dt = e.advance(5)
+    assert abs(t - 5e-3) < 1e-15 and dt == 1e-3
+    t, dt = e.advance(3, elapsed=t, final_time=6.5e-3)
+    assert abs(t - 6.5e-3) < 1e-15
+    # same steps on the oracle with the same dt
+    o = c.oracle
+    for dt_o in [1e-3] * 6 + [0.5e-3]:
+        for rk in range(o.n_rk):
+            assert o.rk_stage(rk, dt_o)[0] == 0
+        o.commit_step()
+    assert c.rel_err() <= 1e-12
+    c.close()
+    for bad in (0.0, -1.0):
+        with pytest.raises(Exception):
+            Case(("isentropic_vortex", [4]), PERIODIC_BOX, ic_vortex, basis="Qk", degree=1, flux="lxf", cfl=bad, time_step=-1.0)
+
+
+def test_time_step_skips_cells_without_a_valid_value():
+    """std::min (global_dt, dt(c)) skips a NaN dt(c) (claw.cc:508): one broken cell mean must not turn the global
+    time step into NaN, 0 or a negative number."""
+    c = Case(("isentropic_vortex", [6]), PERIODIC_BOX, ic_vortex, basis="Qk", degree=1, flux="lxf", cfl=0.5)
+    dt_ok = c.engine.compute_dt(0.0)
+    u = c.u0.copy().reshape(-1, 4, 4)
+    u[7, 2, :] = -1.0          # negative density in one cell: sound speed NaN
+    c.engine.set_solution(u.reshape(-1))
+    dt = c.engine.compute_dt(0.0)
+    assert np.isfinite(dt) and dt > 0 and abs(dt - dt_ok) < 0.2 * dt_ok
+    c.close()

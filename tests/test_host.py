@@ -584,3 +584,22 @@ def test_bench_e2e_entry_contract():
     piped = bench.e2e_entry(12_000_000, 20, 0.03, 0.05, 3, 4_194_304)
     assert piped["in_flight"] == 3 and piped["steps"] == 60 and piped["value_one_context_serial"] == serial["value"]
     assert abs(piped["value"] - 12_000_000 * 60 / 0.05 / 1e6) < 1e-6
+
+
+def test_initial_condition_syntax_error_is_reported(lib, tmp_path):
+    """FunctionParser::initialize throws on a malformed `initial condition/w_i value` (src/parameters.cc:524-526);
+    the front end must report it instead of running on an all-zero component."""
+    L = _claw_api(lib)
+    base = open(os.path.join(PRM_DIR, "cfg3_sod_P2_hllc_tvb_pos.prm")).read()
+    p = tmp_path / "bad_ic.prm"
+    p.write_text(base.replace("set w_2 value = 1.0*(x<=0.5) + 0.125*(x>0.5)", "set w_2 value = 1.0*(x<=0.5 + 0.125*(x>0.5)"))
+    h = L.dflo_claw_create(str(p).encode(), b"sod_tube 10 2", None, 0)
+    if h:   # the deck parses: the error must surface when the initial condition is evaluated
+        n = L.dflo_claw_n_dofs(h)
+        u = np.zeros(n)
+        rc = L.dflo_claw_initial_condition(h, u.ctypes.data_as(abi.c_double_p), n)
+        assert rc != 0
+        assert b"w_2" in L.dflo_host_last_error()
+        L.dflo_claw_destroy(h)
+    else:
+        assert L.dflo_host_last_error()
