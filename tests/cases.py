@@ -22,3 +22,7 @@ BASELINE_SMALL = [
 TOL_RHS = 1e-13
 TOL_STEP_SMOOTH = 1e-12
 TOL_STEP_SHOCK = 1e-9   # limiter branch flips at the reference's 1e-10 "change" threshold
+
+# 20-step horizons of SURVEY.md 8(d): (config key, generator size for the GPU tier, for the CPU-emulation tier)
+BASELINE_HORIZON = [("cfg1", [32], [16]), ("cfg2", [48], [10]), ("cfg3", [200, 20], [40, 4]), ("cfg4", [24], [8]), ("cfg5", [0.04], [0.1])]
+TOL_20_SMOOTH = 1e-11

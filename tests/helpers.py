@@ -112,7 +112,7 @@ def ic_blast(x, y):
 class Case:
     """One configuration built twice: oracle (CPU restatement) and engine (C ABI)."""
 
-    def __init__(self, mesh, bc, ic, backend="emu", oracle_variant="restated", world=1, **prm):
+    def __init__(self, mesh, bc, ic, backend="emu", oracle_variant="restated", world=1, oracle_threads=1, **prm):
         self.prm_kw = dict(prm)
         self.lib = emu_lib() if backend == "emu" else abi.load_library()
         self.prefix = "dflo_emu_" if backend == "emu" else "dflo_b200_"
@@ -122,7 +122,7 @@ class Case:
         self.flat = self.mesh.flatten(self.params, self.pair)
         v, c, bl, bi = self.mesh.primitive()
         okw = {k: v_ for k, v_ in prm.items() if k != "time_step"}
-        self.oracle = O.Oracle(v, c, bl, bi, O.make_params(bc=bc, **okw), variant=oracle_variant)
+        self.oracle = O.Oracle(v, c, bl, bi, O.make_params(bc=bc, n_threads=oracle_threads, **okw), variant=oracle_variant)
         xq = self.oracle.cell_qpoints()
         self.oracle.set_initial_condition(ic(xq[..., 0], xq[..., 1]))
         self.oracle.compute_cell_average()
@@ -204,18 +204,23 @@ class Case:
             e.limit_initial_condition()
         self.exchange()
 
-    def step(self):
+    def step(self, bc_fn=None):
         """One full time step on both sides with the oracle's dt; returns (#cells whose limiter
-        decision differs summed over the stages, dt_oracle, dt_engine)."""
+        decision differs summed over the stages, dt_oracle, dt_engine).  bc_fn(oracle, t_bc) -> g gives the oracle
+        the boundary values of a time-dependent deck at the BC time of the stage (src: t, then t+dt, claw.cc:736-745;
+        src_mpi: always t); the engine evaluates its compiled boundary expressions at the same time."""
         o = self.oracle
         dt_o = o.compute_dt(self.t)
         dt_e = min(e.compute_dt(self.t) for e in self.engines)
         flagdiff = 0
         for rk in range(o.n_rk):
+            t_bc = self.t + dt_o if (rk > 0 and self.prm_kw.get("compat", "src") == "src" and bc_fn is not None) else self.t
+            if bc_fn is not None:
+                o.set_bc_values(bc_fn(o, t_bc))
             err, _ = o.rk_stage(rk, dt_o)
             assert err == 0, "oracle limiter error %d" % err
             for e in self.engines:
-                e.rk_stage(rk, self.t, dt_o)
+                e.rk_stage(rk, t_bc, dt_o)
             self.exchange()
             fo = o.limited_flags()
             fe = np.zeros_like(fo)
@@ -238,6 +243,30 @@ class Case:
             e.close()
 
 
+def parity_horizons(c, nsteps=20, bc_fn=None, limit_initial=None):
+    """L-infinity of the engine against the oracle at the horizons of SURVEY.md 8(d): one right-hand side, one step,
+    `nsteps` steps (relative to max(1, |.|_inf), conserved variables), stage by stage with the oracle's dt, plus the
+    number of cells whose limiter decision differed and the largest relative dt difference."""
+    if limit_initial is None:
+        limit_initial = c.prm_kw.get("limiter", "none") != "none"
+    if bc_fn is not None:
+        c.oracle.set_bc_values(bc_fn(c.oracle, 0.0))
+    if limit_initial:
+        c.limit_initial()
+    r_o, r_e = c.rhs_pair()
+    out = {"rhs": float(np.abs(r_o - r_e).max() / max(1.0, np.abs(r_o).max())), "limiter_flips": 0, "dt_rel": 0.0}
+    for s in range(nsteps):
+        flips, dt_o, dt_e = c.step(bc_fn=bc_fn)
+        out["limiter_flips"] += flips
+        out["dt_rel"] = max(out["dt_rel"], abs(dt_o - dt_e) / dt_o)
+        if s == 0:
+            out["step1"] = float(c.rel_err())
+    out["step%d" % nsteps] = float(c.rel_err())
+    out["steps"] = nsteps
+    out["t_end"] = c.t
+    return out
+
+
 DMR_TOP = ("57.1576766498*(x<1.0/6.0+(1+20*t)/sqrt(3))", "-33.0*(x<1.0/6.0+(1+20*t)/sqrt(3))",
            "8.0*(x<1.0/6.0+(1+20*t)/sqrt(3)) + 1.4*(x>=1.0/6.0+(1+20*t)/sqrt(3))",
            "563.5*(x<1.0/6.0+(1+20*t)/sqrt(3)) + 2.5*(x>=1.0/6.0+(1+20*t)/sqrt(3))")
@@ -253,6 +282,56 @@ def dmr_bc_values(o, t):
     top = np.stack([57.1576766498 * post, -33.0 * post, 8.0 * post + 1.4 * (~post), 563.5 * post + 2.5 * (~post)], axis=-1)
     g[bid == 3] = top[bid == 3]
     return g
+
+
+# The five BASELINE.json configurations as (mesh generator, boundary kinds, initial condition, parameters, constant
+# boundary state); `size` is the generator's argument list, so the same case runs at test, parity and bench sizes.
+BASELINE_CASES = {
+    "cfg1": ("isentropic_vortex", PERIODIC_BOX, ic_vortex, dict(basis="Qk", degree=1, flux="lxf", cfl=0.9, compat="mpi"), None),
+    "cfg2": ("isentropic_vortex", PERIODIC_BOX, ic_vortex, dict(basis="Qk", degree=3, flux="roe", cfl=0.9, compat="mpi"), None),
+    "cfg3": ("sod_tube", SOD_BC, ic_sod,
+             dict(basis="Pk", degree=2, flux="hllc", limiter="TVB", char_lim=True, pos_lim=True, beta=2.0, M=0.0, cfl=0.9), (0.0, 0.0, 1.0, 2.5)),
+    "cfg4": ("double_mach", DMR_BC, ic_dmr,
+             dict(basis="Qk", degree=2, flux="hllc", limiter="TVB", char_lim=True, beta=1.0, M=100.0, cfl=0.9), "dmr"),
+    "cfg5": ("forward_step", STEP_BC, ic_step,
+             dict(basis="Qk", degree=3, flux="kfvs", limiter="TVB", char_lim=True, pos_lim=True, beta=2.0, M=0.0, cfl=0.5), (4.2, 0.0, 1.4, 8.8)),
+}
+
+
+def baseline_case(key, size, backend="cuda", oracle_variant="restated", oracle_threads=1):
+    """Builds BASELINE configuration `key` on both sides.  Returns (Case, bc_fn): bc_fn is None for constant boundary
+    states; for the double Mach reflection it feeds the oracle the moving-shock top boundary of
+    examples/double_mach_reflection/input.prm:35-41 that the engine evaluates on the device from the expressions."""
+    gen, bc, ic, prm, g = BASELINE_CASES[key]
+    c = Case((gen, list(size)), bc, ic, backend=backend, oracle_variant=oracle_variant, oracle_threads=oracle_threads, **prm)
+    bc_fn = None
+    if g == "dmr":
+        for comp, ex in enumerate(DMR_TOP):
+            c.engine.set_boundary_expression(3, comp, ex)
+        for comp, v in enumerate((57.1576766498, -33.0, 8.0, 563.5)):
+            c.engine.set_boundary_expression(4, comp, repr(v))
+        bc_fn = dmr_bc_values
+    elif g is not None:
+        c.set_boundary(values=g)
+    return c, bc_fn
+
+
+def check_horizons(key, size, backend, nsteps=20):
+    """The tolerances of SURVEY.md 8(d) at the three horizons; returns the measured numbers."""
+    c, bc_fn = baseline_case(key, size, backend=backend, oracle_threads=4)
+    h = parity_horizons(c, nsteps=nsteps, bc_fn=bc_fn)
+    shocked = c.prm_kw.get("limiter", "none") != "none"
+    D = c.oracle.D
+    c.close()
+    assert h["rhs"] <= 1e-13 * np.sqrt(D), h
+    assert h["dt_rel"] <= 1e-12, h
+    if shocked:
+        assert h["step1"] <= 1e-9 and h["step%d" % nsteps] <= 1e-9, h
+        if c.prm_kw["flux"] != "kfvs":   # DESIGN.md: the reference's A&S ERF jumps by 2e-9 at s = 0
+            assert h["limiter_flips"] == 0, h
+    else:
+        assert h["step1"] <= 1e-12 and h["step%d" % nsteps] <= 1e-11, h
+    return h
 
 
 def time_dependent_bc_case(backend, compat, nsteps=3):

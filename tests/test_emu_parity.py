@@ -8,8 +8,8 @@ import ctypes
 import numpy as np
 import pytest
 
-from cases import ALL_FLUXES, BASELINE_SMALL, BASES, TOL_RHS, TOL_STEP_SHOCK, TOL_STEP_SMOOTH
-from helpers import (DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, Case, emu_lib, ic_dmr, ic_pulse, ic_smooth, ic_sod, ic_step,
+from cases import ALL_FLUXES, BASELINE_HORIZON, BASELINE_SMALL, BASES, TOL_RHS, TOL_STEP_SHOCK, TOL_STEP_SMOOTH
+from helpers import (check_horizons, DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, Case, emu_lib, ic_dmr, ic_pulse, ic_smooth, ic_sod, ic_step,
                      ic_vortex)
 
 
@@ -354,3 +354,9 @@ def test_time_step_skips_cells_without_a_valid_value():
     dt = c.engine.compute_dt(0.0)
     assert np.isfinite(dt) and dt > 0 and abs(dt - dt_ok) < 0.2 * dt_ok
     c.close()
+
+
+@pytest.mark.parametrize("key,_,size", BASELINE_HORIZON, ids=[b[0] for b in BASELINE_HORIZON])
+def test_baseline_configs_20_step_horizon(key, _, size):
+    """SURVEY.md 8(d) horizons (1 RHS / 1 step / 20 steps) on the CPU emulation of the kernel code."""
+    check_horizons(key, size, "emu")

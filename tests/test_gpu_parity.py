@@ -4,9 +4,9 @@ import os
 import numpy as np
 import pytest
 
-from cases import ALL_FLUXES, BASELINE_SMALL, BASES, TOL_RHS, TOL_STEP_SHOCK, TOL_STEP_SMOOTH
+from cases import ALL_FLUXES, BASELINE_HORIZON, BASELINE_SMALL, BASES, TOL_RHS, TOL_STEP_SHOCK, TOL_STEP_SMOOTH
 from dflo_b200 import abi
-from helpers import (DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, Case, ic_dmr, ic_pulse, ic_smooth, ic_sod, ic_vortex)
+from helpers import (check_horizons, DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, Case, ic_dmr, ic_pulse, ic_smooth, ic_sod, ic_vortex)
 
 pytestmark = pytest.mark.gpu
 
@@ -87,6 +87,13 @@ def test_baseline_configs_small(name, mesh, bc, ic, prm, nsteps):
     if "kfvs" not in name:   # see DESIGN.md: the reference's A&S ERF jumps by 2e-9 at s = 0
         assert flips == 0
     c.close()
+
+
+@pytest.mark.parametrize("key,size,_", BASELINE_HORIZON, ids=[b[0] for b in BASELINE_HORIZON])
+def test_baseline_configs_20_step_horizon(key, size, _):
+    """L-infinity against the oracle after 1 RHS / 1 step / 20 steps, all five BASELINE configurations
+    (cfg4 with its time-dependent boundary expression), limiter decisions bit for bit."""
+    check_horizons(key, size, "cuda")
 
 
 def test_advance_graph_matches_stagewise():
