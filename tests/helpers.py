@@ -5,6 +5,7 @@ import ctypes
 import os
 import subprocess
 import sys
+import time
 
 import numpy as np
 
@@ -140,6 +141,7 @@ class Case:
         self.engine = self.engines[0]
         self.g = None
         self.t = 0.0
+        self.oracle_seconds = 0.0   # wall time spent in the oracle's compute_dt + rk_stage calls (bench.py cpu_baseline)
 
     # emulated halo exchange between in-process ranks
     def exchange(self):
@@ -210,14 +212,18 @@ class Case:
         the boundary values of a time-dependent deck at the BC time of the stage (src: t, then t+dt, claw.cc:736-745;
         src_mpi: always t); the engine evaluates its compiled boundary expressions at the same time."""
         o = self.oracle
+        w0 = time.perf_counter()
         dt_o = o.compute_dt(self.t)
+        self.oracle_seconds += time.perf_counter() - w0
         dt_e = min(e.compute_dt(self.t) for e in self.engines)
         flagdiff = 0
         for rk in range(o.n_rk):
             t_bc = self.t + dt_o if (rk > 0 and self.prm_kw.get("compat", "src") == "src" and bc_fn is not None) else self.t
             if bc_fn is not None:
                 o.set_bc_values(bc_fn(o, t_bc))
+            w0 = time.perf_counter()
             err, _ = o.rk_stage(rk, dt_o)
+            self.oracle_seconds += time.perf_counter() - w0
             assert err == 0, "oracle limiter error %d" % err
             for e in self.engines:
                 e.rk_stage(rk, t_bc, dt_o)
@@ -324,7 +330,7 @@ def check_horizons(key, size, backend, nsteps=20):
     D = c.oracle.D
     c.close()
     assert h["rhs"] <= 1e-13 * np.sqrt(D), h
-    assert h["dt_rel"] <= 1e-12, h
+    assert h["dt_rel"] <= (1e-9 if shocked else 1e-12), h   # dt follows the means: same tolerance as the state
     if shocked:
         assert h["step1"] <= 1e-9 and h["step%d" % nsteps] <= 1e-9, h
         if c.prm_kw["flux"] != "kfvs":   # the reference's A&S ERF jumps by 2e-9 at s = 0
