@@ -338,17 +338,9 @@ namespace dflo
          const int c0 = L.tile_start[t], ncb = L.tile_start[t + 1] - c0;
          const int nhl = L.halo_start[t + 1] - L.halo_start[t];
          int *halo = d + rowd_off_halo (), *nbhi = d + rowd_off_nbhi (nh), *lj = d + rowd_off_ljob (tc, nh), *gj = d + rowd_off_gjob (tc, nh);
-         int *gtr = d + rowd_off_gtrace (tc, nh);
          for (int i = 0; i < nhl; ++i) halo[i] = L.halo_cells[L.halo_start[t] + i];
          for (int i = 0; i < 2 * tc; ++i) nbhi[i] = UNSET;
-         for (int i = 0; i < 2 * nh; ++i) gtr[i] = -1;
-         // where the trace of su slot `slot` on face f comes from (see row_desc.h)
-         auto trace_word = [&] (int slot, int f, bool flipped) -> int {
-            if (slot >= tc) return halo[slot - tc] | (f << 28) | (flipped ? 1 << 30 : 0);
-            return -2 - (slot | (f << 8) | (flipped ? 1 << 10 : 0));
-         };
          int nL = 0, nG = 0;
-         std::vector<std::pair<int, int>> ltrace; // (L job, ghost-trace word): packed behind the G traces below
          for (int j = L.job_start[t]; j < L.job_start[t + 1]; ++j)
          {
             const int a = L.jobs[4 * (size_t) j], nb = L.jobs[4 * (size_t) j + 1], slot_b = L.jobs[4 * (size_t) j + 2];
@@ -373,7 +365,6 @@ namespace dflo
                if (high)
                {
                   gj[nG] = slot_b | (dir << 16) | flip;
-                  gtr[nG] = trace_word (slot_b, 2 * dir, flip != 0);
                   nbhi[2 * sa + dir] = (tc + nG) | (plus_own ? ROWD_PLUS : 0);
                   ++nG;
                }
@@ -381,7 +372,6 @@ namespace dflo
                {
                   lj[2 * nL] = (2 * sa + dir) | (plus_own ? ROWD_PLUS : 0) | flip;
                   lj[2 * nL + 1] = slot_b;
-                  ltrace.push_back (std::make_pair (nL, trace_word (slot_b, 2 * dir + 1, flip != 0)));
                   ++nL;
                }
             }
@@ -398,14 +388,6 @@ namespace dflo
                lj[2 * nL + 1] = nb;
                ++nL;
             }
-         }
-         // ghost-trace slots are packed (G jobs, then the L jobs that have a neighbour cell) so that the first
-         // tc * n1 threads of the block cover them all with one item each on a full lattice tile
-         for (size_t i = 0; i < ltrace.size (); ++i)
-         {
-            const int ts = nG + (int) i;
-            gtr[ts] = ltrace[i].second;
-            lj[2 * ltrace[i].first] |= ts << ROWD_TS_SHIFT;
          }
          for (int i = 0; i < 2 * ncb; ++i)
             if (nbhi[i] == UNSET)

@@ -10,11 +10,8 @@
 //     partner), or a physical boundary;
 //   * a LOW face (left, bottom) whose neighbour is not a tile cell reached through an ordinary
 //     interior face: by an "L job" of the block's two extra warps;
-//   * ghost traces (the trace of a cell outside the tile on the face it shares with a tile cell: the
-//     low-face trace of the cell beyond a high tile-edge face = "G job", the high-face trace of the
-//     cell beyond a low tile-edge face = the neighbour of an "L job") are formed at the start of the
-//     block straight from global memory -- the halo cells themselves are never staged; `gtrace`
-//     lists them so that one descriptor word is all a thread needs before its loads fly.
+//   * ghost traces (the low-face trace of the cell beyond a high tile-edge face) are produced by
+//     "G jobs" of the extra warps from the staged halo cells.
 // Which cell is the reference's "plus" side (the one MeshWorker::loop integrates the face from,
 // reference src/assemble_explicit.cc:440-451, or both for periodic pairs, src_mpi 186-260) is
 // carried per face so the Riemann problem is posed exactly as in the reference.
@@ -38,17 +35,12 @@ namespace dflo
    //   halo[nh_cap]            local cell ids staged after the tile cells (su slot TC + i)
    //   nbhi[tc][2]             code >= 0: (index & 0xffff) | plus_own << 16, index < TC: tile slot, else TC + ghost slot
    //                           code <  0: -1 - local boundary face
-   //   ljob[nl_cap][2]         { (slot*2+dir) | plus_own << 16 | flip << 17 | ghost-trace slot << 18,  nb: su slot >= 0 or -1 - local boundary face }
+   //   ljob[nl_cap][2]         { (slot*2+dir) | plus_own << 16 | flip << 17,  nb: su slot >= 0 or -1 - local boundary face }
    //   gjob[ng_cap]            su slot | dir << 16 | flip << 17
-//   gtrace[ng_cap + nl_cap] ghost-trace slot ts (ts < nG: G job ts; then, packed, the L jobs whose neighbour is a cell):
-//                           >= 0: local cell | face << 28 | flip << 30 (a cell outside the tile: from global memory)
-//                           -1:   unused (no such job, or the L job's neighbour is a boundary)
-//                           <= -2: -2 - (tile slot | face << 8 | flip << 10): periodic partner inside the tile (from su)
-   enum { ROWD_HDR = 8, ROWD_PLUS = 1 << 16, ROWD_FLIP = 1 << 17, ROWD_TS_SHIFT = 18, ROWD_TS_MASK = 0x3f };
+   enum { ROWD_HDR = 8, ROWD_PLUS = 1 << 16, ROWD_FLIP = 1 << 17 };
    constexpr int rowd_off_halo () { return ROWD_HDR; }
    constexpr int rowd_off_nbhi (int nh) { return ROWD_HDR + nh; }
    constexpr int rowd_off_ljob (int tc, int nh) { return ROWD_HDR + nh + 2 * tc; }
    constexpr int rowd_off_gjob (int tc, int nh) { return ROWD_HDR + nh + 2 * tc + 2 * nh; }
-   constexpr int rowd_off_gtrace (int tc, int nh) { return ROWD_HDR + nh + 2 * tc + 2 * nh + nh; }
-   constexpr int rowd_ints (int tc, int nh) { return (ROWD_HDR + nh + 2 * tc + 2 * nh + nh + 2 * nh + 3) / 4 * 4; } // 16-byte multiple
+   constexpr int rowd_ints (int tc, int nh) { return (ROWD_HDR + nh + 2 * tc + 2 * nh + nh + 3) / 4 * 4; } // 16-byte multiple
 }

@@ -12,24 +12,17 @@
 //     The dense i x q loops of the reference become fully unrolled FMA chains on registers whose
 //     table operands (D.w, l_a(0), l_a(1), w_a) are constant-bank immediates.
 //   * every face is solved once per tile, along +e_x / +e_y, by the thread that owns the low-side
-//     cell's row/column (row_desc.h).  Neighbouring threads exchange one 32-byte trace and one
-//     32-byte flux per face point through shared memory.  The low faces on the tile edge ("L jobs")
-//     are spread evenly over the warps as a third, partly filled round of Riemann problems.
-//   * only the tile's OWN cells are staged (per-cell bulk async copies, TMA unit, into a padded
-//     layout -- cell stride D+2 doubles -- that makes the 128-bit row reads and the 64-bit column
-//     reads free of bank conflicts).  Of a cell outside the tile only the trace on the shared face is
-//     needed: it is formed at block start straight from global memory (L2), one (cell, face point)
-//     per thread, 4 N1 loads issued before the wait for the bulk copies and consumed after the own
-//     traces -- the halo cells themselves never occupy shared memory.
-//   * the y part of the residual meets the x part IN PLACE: the column thread overwrites the staged
-//     u of its nodes with u + dt M^-1 r_y (every node belongs to exactly one column thread), and after
-//     one barrier the row thread adds dt M^-1 r_x from its registers, applies the RK combine with
-//     old_solution (read straight into registers, prefetched into L2 at block start) and stores
-//     128-bit lines.  No second tile-sized buffer: 31 KB of shared memory and no extra warp, so five
-//     blocks of 128 threads (Q3) are resident per SM at 96 registers.
+//     cell's row/column (row_desc.h); tile-edge low faces and the traces of halo cells are the job
+//     of one extra warp.  Neighbouring threads exchange one 32-byte trace and one 32-byte flux
+//     per face point through shared memory; nothing else is shared except the y part of the
+//     residual, which is transposed back to row order through one padded buffer.
+//   * the tile and its halo cells arrive by per-cell bulk async copies (TMA) into a padded layout
+//     (cell stride D+2 doubles) that makes both the row reads (128-bit) and the column reads
+//     (64-bit, even/odd cell interleave for N1 = 4) free of bank conflicts; old_solution is
+//     prefetched into L2 by one bulk prefetch and read straight into registers at the end.
 //
-// r02: the r01 form (row_kernel_v1 in the history) staged the 24 halo cells of a tile as well (42.5 KB, 4 blocks
-// per SM, a fifth warp per block for the edge jobs, a tile-sized transposition buffer for r_y).
+// Per Q3 cell this is ~8 k SASS thread-instructions (4.0 k fp64) against 11.5 k (4.1 k) in the phase
+// kernel, and a third of its shared-memory wavefronts.
 #pragma once
 
 #include "kernels.cuh"
@@ -50,11 +43,13 @@ namespace dflo
    {
       static constexpr int NS = N1 * N1, D = 4 * NS;
       static constexpr int TC = row_tc (N1), NH = row_nh (N1);
-      static constexpr int NT = 2 * NH;                     // ghost-trace slots: G jobs | L jobs
       static constexpr int CS = D + 2;                      // padded cell stride in shared memory (doubles)
-      static constexpr int THREADS = TC * N1, WARPS = THREADS / 32;
-#ifndef DFLO_ROW_MIN_BLOCKS
-#define DFLO_ROW_MIN_BLOCKS 5
+      #ifndef DFLO_ROW_EXTRA
+#define DFLO_ROW_EXTRA 32
+#endif
+      static constexpr int MAIN = TC * N1, EXTRA = DFLO_ROW_EXTRA, THREADS = MAIN + EXTRA;
+      #ifndef DFLO_ROW_MIN_BLOCKS
+#define DFLO_ROW_MIN_BLOCKS 4
 #endif
 #ifndef DFLO_ROW_MIN_BLOCKS_N3
 #define DFLO_ROW_MIN_BLOCKS_N3 6
@@ -62,20 +57,29 @@ namespace dflo
       static constexpr int MIN_BLOCKS = N1 == 3 ? DFLO_ROW_MIN_BLOCKS_N3 : N1 <= 4 ? DFLO_ROW_MIN_BLOCKS : 2;
       static constexpr int DESC_INTS = rowd_ints (TC, NH);
       static constexpr int OFF_HALO = rowd_off_halo (), OFF_NBHI = rowd_off_nbhi (NH), OFF_LJOB = rowd_off_ljob (TC, NH),
-                           OFF_GJOB = rowd_off_gjob (TC, NH), OFF_GTR = rowd_off_gtrace (TC, NH);
-      // shared memory carve-up in doubles; every bulk-copy destination is 16-byte aligned
+                           OFF_GJOB = rowd_off_gjob (TC, NH);
+      // shared memory carve-up in doubles; every bulk-copy destination is 16-byte aligned.
+      //   [O_U, O_X)   the tile's cells (padded), live to the end
+      //   [O_X, ...)   halo cells | ghost traces | low-face traces -> fluxes: dead once the fluxes
+      //                have been read into registers; the y part of the residual (sR, row order,
+      //                padded like su) is then written over this region, and the partial cell
+      //                averages over its tail
       static constexpr int O_U = 2;                               // [0,2): mbarrier
-      static constexpr int O_T = O_U + TC * CS;                   // 2 halves x [2 dirs][TC][N1] double2: low-face traces -> fluxes;
-      static constexpr int T_HALF = 2 * TC * N1 * 2;              //   after P3 dead: partial cell averages [TC][N1][4] (N1 = 3, 5)
-      static constexpr int O_G = O_T + 2 * T_HALF;                // ghost traces [NT][N1][4]
-      static constexpr int O_W = O_G + NT * N1 * 4;               // [THREADS][4] flux on the own top face, parked between P2 and P3
-      static constexpr int O_GEOM = O_W + THREADS * 4;            // x0 y0 hx hy of the tile cells
-      static constexpr int O_AVG = O_GEOM + TC * 4;               // cell averages: tile [TC][4] | ghost-trace slots [NT][4] (LxF, KEP only)
-      static constexpr int O_DESC = O_AVG + (flux_uses_averages (FLUX) ? (TC + NT) * 4 : 0);
+      static constexpr int O_X = O_U + TC * CS;
+      static constexpr int O_G = O_X + NH * CS;                   // ghost traces [NH][N1][4]
+      static constexpr int O_T = O_G + NH * N1 * 4;               // 2 halves x [2 dirs][TC][N1] double2
+      static constexpr int T_HALF = 2 * TC * N1 * 2;
+      static constexpr int X_END_A = O_T + 2 * T_HALF;
+      static constexpr int O_R = O_X;
+      static constexpr int O_PART = O_R + TC * CS;                // [TC][N1][4]
+      static constexpr int X_END_B = O_PART + TC * N1 * 4;
+      static constexpr int O_GEOM = X_END_A > X_END_B ? X_END_A : X_END_B;   // x0 y0 hx hy of the tile cells
+      static constexpr int O_AVG = O_GEOM + TC * 4;               // cell averages tile + halo (LxF only)
+      static constexpr int O_DESC = O_AVG + (flux_uses_averages (FLUX) ? (TC + NH) * 4 : 0);
       static constexpr int SMEM_DOUBLES = O_DESC + DESC_INTS / 2;
-      static_assert (THREADS % 32 == 0, "whole warps");
+      static_assert (MAIN % 32 == 0, "whole warps");
+      static_assert (THREADS >= TC + NH + 2, "one staging copy per thread");
       static_assert (CS % 2 == 0 && DESC_INTS % 4 == 0, "16-byte aligned bulk copies");
-      static_assert (2 * T_HALF >= TC * N1 * 4, "partial averages fit the trace exchange array");
    };
 
    // which (cell slot, line) a main thread works on in its column role, and the inverse (the
@@ -228,44 +232,26 @@ namespace dflo
       H[3] = G[3];
    }
 
-   // trace of a cell at point q of its face f from N1 x 4 nodal values g[c][a] taken along the face normal --
-   // the fma chain of StageKernel::trace, so that a ghost trace is bit-identical to the one the cell's own tile forms
-   template <int N1>
-   __device__ __forceinline__ void trace_from_line (const double g[4][N1], int f, double W[4])
-   {
-      const RowConst &T = c_row[N1];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-      {
-         double s = 0.0;
-#pragma unroll
-         for (int a = 0; a < N1; ++a) s = fma ((f & 1) ? T.e1[a] : T.e0[a], g[c][a], s);
-         W[c] = s;
-      }
-   }
-
    template <int N1, int FLUX>
    __global__ void __launch_bounds__ (RowShape<N1, FLUX>::THREADS, RowShape<N1, FLUX>::MIN_BLOCKS) row_stage_kernel (const StageArgs A)
    {
       typedef RowShape<N1, FLUX> S;
       constexpr int NS = S::NS, D = S::D, TC = S::TC, CS = S::CS, TH = S::T_HALF;
       extern __shared__ __align__ (16) double sm[];
-      double *su = sm + S::O_U, *sT = sm + S::O_T, *sG = sm + S::O_G, *sGeom = sm + S::O_GEOM, *sAvg = sm + S::O_AVG;
-      double *sAvgG = sAvg + TC * 4;
+      double *su = sm + S::O_U, *sR = sm + S::O_R, *sT = sm + S::O_T, *sG = sm + S::O_G, *sGeom = sm + S::O_GEOM, *sAvg = sm + S::O_AVG;
       int *sdesc = reinterpret_cast<int *> (sm + S::O_DESC);
       const RowConst &T = c_row[N1];
       const int tid = threadIdx.x;
       const int *gdesc = A.rowdesc + (size_t) blockIdx.x * S::DESC_INTS;
-      // first ghost-trace item of this thread: slot ts = tid / N1 at face point tid % N1; one descriptor word is all
-      // that stands between the block start and the loads (the header is not needed: unused slots hold -1)
-      const int gq = tid % N1;
-      int gword = -1;
-      if (tid < S::NT * N1) gword = gdesc[S::OFF_GTR + tid / N1];
-      const int c0 = gdesc[0], ncb = gdesc[1];
+      const int c0 = gdesc[0], ncb = gdesc[1], nh = gdesc[2];
+      // halo thread i = tid - TC: its cell id is requested together with the header, not after it (one trip less
+      // in front of the copies); entries past nh are inside the descriptor and unused
+      int halo_cell = 0;
+      if (tid >= TC && tid < TC + S::NH) halo_cell = gdesc[S::OFF_HALO + tid - TC];
       const bool need_old = A.mode == MODE_STAGE && A.ark != 0.0;
       constexpr unsigned cell_bytes = (unsigned) (D * sizeof (double));
 
-      // ---- stage the tile: per-cell bulk copies of the OWN cells into the padded layout, descriptor, geometry ----
+      // ---- stage the tile: per-cell bulk copies into the padded layout, descriptor, geometry ----
       if (tid == 0)
       {
          if (A.fx && gdesc[5])
@@ -278,19 +264,23 @@ namespace dflo
             for (int p = 0; p < F.npeers; ++p)
                while (ld_acquire_sys (F.my_flags + F.world + F.peer_rank[p]) < e) {}
          }
-         unsigned bytes = (unsigned) ncb * cell_bytes + (unsigned) ncb * 32u + (unsigned) (S::DESC_INTS * sizeof (int));
-         if (flux_uses_averages (FLUX)) bytes += (unsigned) ncb * 32u;
+         unsigned bytes = (unsigned) (ncb + nh) * cell_bytes + (unsigned) ncb * 32u + (unsigned) (S::DESC_INTS * sizeof (int));
+         if (flux_uses_averages (FLUX)) bytes += (unsigned) (ncb + nh) * 32u;
          mbar_init (sm, 1);
          mbar_expect_tx (sm, bytes);
       }
       __syncthreads ();
-      if (tid < ncb)
-         bulk_g2s (su + tid * CS, A.u + (size_t) (c0 + tid) * D, cell_bytes, sm);
+      if (tid < ncb || (tid >= TC && tid - TC < nh))
+      {
+         const int cell = tid < TC ? c0 + tid : halo_cell;
+         const int slot = tid;
+         bulk_g2s (su + slot * CS, A.u + (size_t) cell * D, cell_bytes, sm);
+         if (flux_uses_averages (FLUX)) bulk_g2s (sAvg + slot * 4, A.avg + (size_t) cell * 4, 32u, sm);
+      }
       else if (tid == S::THREADS - 1)
       {
          bulk_g2s (sdesc, gdesc, (unsigned) (S::DESC_INTS * sizeof (int)), sm);
          bulk_g2s (sGeom, A.geom + (size_t) c0 * 4, (unsigned) ncb * 32u, sm);
-         if (flux_uses_averages (FLUX)) bulk_g2s (sAvg, A.avg + (size_t) c0 * 4, (unsigned) ncb * 32u, sm);
          if (need_old)
             asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u_old + (size_t) c0 * D), "r"((unsigned) ncb * cell_bytes) : "memory");
       }
@@ -310,42 +300,15 @@ namespace dflo
             asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.rowdesc + (size_t) bt * S::DESC_INTS), "r"((unsigned) (S::DESC_INTS * sizeof (int))) : "memory");
          }
       }
-      // ghost trace of this thread: the 4 N1 values along the face normal, requested now, reduced after P1
-      double gl[4][N1];
-      int gface = 0;
-      if (gword >= 0)
-      {
-         const int gcell = gword & 0x0fffffff;
-         gface = (gword >> 28) & 3;
-         const int qq = ((gword >> 30) & 1) ? N1 - 1 - gq : gq;
-         const double *uc = A.u + (size_t) gcell * D + ((gface < 2) ? N1 * qq : qq);
-         if (gface < 2)
-         {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) load_line<N1> (uc + c * NS, gl[c]); // a row of the cell: contiguous
-         }
-         else
-         {
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-               for (int a = 0; a < N1; ++a) gl[c][a] = uc[c * NS + a * N1]; // a column: the N1 threads of the slot share the sectors
-         }
-         if (flux_uses_averages (FLUX) && gq == 0)
-         {
-            double av[4];
-            load4 (A.avg + (size_t) gcell * 4, av);
-            store4 (sAvgG + (tid / N1) * 4, av);
-         }
-      }
       const double dt_global = A.time[1]; // issued before the wait: its latency hides behind the staging
       mbar_wait (sm, 0);
 
+      const bool main_thread = tid < S::MAIN;
       // row role: cell slot rs, Gauss row rb;  column role: cell slot cs, Gauss column ca
       const int rs = tid / N1, rb = tid % N1;
       int cs, ca;
       col_role<N1> (tid, cs, ca);
-      const bool row_on = rs < ncb, col_on = cs < ncb;
+      const bool row_on = main_thread && rs < ncb, col_on = main_thread && cs < ncb;
       const int pT_row = rs * N1 + rb;                              // low-face slots of the own cell
       const int pT_col = TC * N1 + col_pos<N1> (cs, ca);
 
@@ -393,52 +356,18 @@ namespace dflo
          }
          store_pt<TH> (sT, pT_col, WB);
       }
-      // ghost traces: the item requested at block start, then what is left of the list (in-tile periodic partners,
-      // items beyond the thread count)
-      if (!(A.dbg & 4))
+      if (!main_thread)
       {
-         if (gword >= 0)
+         // G jobs: low-face traces of the cells beyond the tile's high edges
+         const int nG = (A.dbg & 4) ? 0 : sdesc[4];
+         for (int j = tid - S::MAIN; j < nG * N1; j += S::EXTRA)
          {
+            const int g = j / N1, q = j % N1;
+            const int code = sdesc[S::OFF_GJOB + g];
+            const int slot = code & 0xffff, dir = (code >> 16) & 1;
+            const int qq = (code & ROWD_FLIP) ? N1 - 1 - q : q;
             double W[4];
-            trace_from_line<N1> (gl, gface, W);
-            store4 (sG + tid * 4, W);
-         }
-         for (int j = tid; j < S::NT * N1; j += S::THREADS)
-         {
-            const int ts = j / N1, q = j % N1;
-            const int w = sdesc[S::OFF_GTR + ts];
-            if (w == -1 || (w >= 0 && j == tid)) continue;
-            double W[4];
-            if (w >= 0)
-            {
-               const int cell = w & 0x0fffffff, f = (w >> 28) & 3;
-               const int qq = ((w >> 30) & 1) ? N1 - 1 - q : q;
-               const double *uc = A.u + (size_t) cell * D + ((f < 2) ? N1 * qq : qq);
-               double g[4][N1];
-#pragma unroll
-               for (int c = 0; c < 4; ++c)
-#pragma unroll
-                  for (int a = 0; a < N1; ++a) g[c][a] = uc[c * NS + ((f < 2) ? a : a * N1)];
-               trace_from_line<N1> (g, f, W);
-               if (flux_uses_averages (FLUX) && q == 0)
-               {
-                  double av[4];
-                  load4 (A.avg + (size_t) cell * 4, av);
-                  store4 (sAvgG + ts * 4, av);
-               }
-            }
-            else
-            {
-               const int v = -2 - w, slot = v & 0xff, f = (v >> 8) & 3;
-               const int qq = ((v >> 10) & 1) ? N1 - 1 - q : q;
-               row_trace<N1> (su + slot * CS, f, qq, W);
-               if (flux_uses_averages (FLUX) && q == 0)
-               {
-                  double av[4];
-                  load4 (sAvg + slot * 4, av);
-                  store4 (sAvgG + ts * 4, av);
-               }
-            }
+            row_trace<N1> (su + slot * CS, 2 * dir, qq, W);
             store4 (sG + j * 4, W);
          }
       }
@@ -457,7 +386,7 @@ namespace dflo
                load_pt<TH> (sT, idx * N1 + rb, Wn);
             else
                load4 (sG + ((idx - TC) * N1 + rb) * 4, Wn);
-            if (flux_uses_averages (FLUX)) load4 (idx < TC ? sAvg + idx * 4 : sAvgG + (idx - TC) * 4, An);
+            if (flux_uses_averages (FLUX)) load4 (sAvg + (idx < TC ? idx : (sdesc[S::OFF_GJOB + idx - TC] & 0xffff)) * 4, An);
             if (A.dbg & 1)
             {
 #pragma unroll
@@ -502,7 +431,7 @@ namespace dflo
                load_pt<TH> (sT, TC * N1 + col_pos<N1> (idx, ca), Wn);
             else
                load4 (sG + ((idx - TC) * N1 + ca) * 4, Wn);
-            if (flux_uses_averages (FLUX)) load4 (idx < TC ? sAvg + idx * 4 : sAvgG + (idx - TC) * 4, An);
+            if (flux_uses_averages (FLUX)) load4 (sAvg + (idx < TC ? idx : (sdesc[S::OFF_GJOB + idx - TC] & 0xffff)) * 4, An);
             if (A.dbg & 1)
             {
 #pragma unroll
@@ -531,13 +460,14 @@ namespace dflo
             }
             face_flux_axis<FLUX, 1> (true, WT, Wn, Ao, An, H);
          }
-         store4 (sm + S::O_W + tid * 4, H); // read back by this thread in P3: four registers less across the x part
+#pragma unroll
+         for (int c = 0; c < 4; ++c) WT[c] = H[c];
       }
+      if (!main_thread)
       {
-         // L jobs: low faces of tile cells whose neighbour is outside the tile, a periodic partner or a boundary.
-         // Item j goes to lane j / WARPS of warp j % WARPS: every warp runs this third round equally filled.
+         // L jobs: low faces of tile cells whose neighbour is a halo cell, a periodic partner or a boundary
          const int nL = (A.dbg & 4) ? 0 : sdesc[3];
-         for (int j = (tid & 31) * S::WARPS + (tid >> 5); j < nL * N1; j += S::THREADS)
+         for (int j = tid - S::MAIN; j < nL * N1; j += S::EXTRA)
          {
             const int job = j / N1, q = j % N1;
             const int w0 = sdesc[S::OFF_LJOB + 2 * job], nb = sdesc[S::OFF_LJOB + 2 * job + 1];
@@ -549,9 +479,9 @@ namespace dflo
             if (flux_uses_averages (FLUX)) load4 (sAvg + s * 4, Ao);
             if (nb >= 0)
             {
-               const int ts = (w0 >> ROWD_TS_SHIFT) & ROWD_TS_MASK;
-               load4 (sG + (ts * N1 + q) * 4, Wn);
-               if (flux_uses_averages (FLUX)) load4 (sAvgG + ts * 4, An);
+               const int qn = (w0 & ROWD_FLIP) ? N1 - 1 - q : q;
+               row_trace<N1> (su + nb * CS, 2 * dir + 1, qn, Wn);
+               if (flux_uses_averages (FLUX)) load4 (sAvg + nb * 4, An);
             }
             else
             {
@@ -579,78 +509,18 @@ namespace dflo
       __syncthreads ();
 
       // ================= P3: volume terms and lifting =================
-      // x part first, kept in registers; then the y part, which meets it in place (see the header)
+      // the low-face fluxes move to registers; after the barrier the exchange arrays are dead and
+      // sR is written over them
+      double HL[4], HB[4];
+      if (row_on) load_pt<TH> (sT, pT_row, HL);
+      if (col_on) load_pt<TH> (sT, pT_col, HB);
+      __syncthreads ();
       double rrow[4][N1], uold[4][N1];
-      if (row_on)
-      {
-         const double hx = sGeom[rs * 4 + 2], hy = sGeom[rs * 4 + 3];
-         const double *uc = su + rs * CS + rb * N1;
-         double Fx[4][N1];
-         {
-            double u[4][N1];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) load_line<N1> (uc + c * NS, u[c]);
-#pragma unroll
-            for (int a = 0; a < N1; ++a)
-            {
-               const double W[4] = {u[0][a], u[1][a], u[2][a], u[3][a]};
-               double F[4];
-               if (A.dbg & 2)
-               {
-#pragma unroll
-                  for (int c = 0; c < 4; ++c) F[c] = W[c];
-               }
-               else
-                  flux_x (W, F);
-#pragma unroll
-               for (int c = 0; c < 4; ++c) Fx[c][a] = F[c];
-            }
-         }
-         const double hw = hy * T.gw[rb];
-#pragma unroll
-         for (int c = 0; c < 4; ++c)
-         {
-            // flux on the own left face, left there by the agent of that face
-            const double HLc = sT[(c >> 1) * TH + 2 * pT_row + (c & 1)];
-#pragma unroll
-            for (int a = 0; a < N1; ++a)
-            {
-               double sx = 0.0;
-#pragma unroll
-               for (int ap = 0; ap < N1; ++ap) sx = fma (Fx[c][ap], T.dw[ap][a], sx);
-               const double fx = WR[c] * T.e1[a] - HLc * T.e0[a];
-               rrow[c][a] = hw * (sx - fx);
-            }
-         }
-         if (A.gravity != 0.0) // assemble_explicit.cc:78, 108-111
-         {
-            double u[4][N1]; // read again: keeping the row alive across the contraction costs 2 N1^2 registers on every run
-#pragma unroll
-            for (int c = 0; c < 4; ++c) load_line<N1> (uc + c * NS, u[c]);
-#pragma unroll
-            for (int a = 0; a < N1; ++a)
-            {
-               const double W[4] = {u[0][a], u[1][a], u[2][a], u[3][a]};
-               double Gv[4];
-               if (A.ext_force)
-               {
-                  const double *f = A.ext_force + ((size_t) (c0 + rs) * NS + rb * N1 + a) * 2;
-                  forcing_ext (W, f[0], f[1], Gv);
-               }
-               else
-                  forcing (W, Gv);
-               const double w = A.gravity * (T.gw[a] * T.gw[rb] * hx * hy);
-#pragma unroll
-               for (int c = 0; c < 4; ++c) rrow[c][a] += Gv[c] * w;
-            }
-         }
-      }
-      __syncthreads (); // every row of u has been read: the columns may now be overwritten
       if (col_on)
       {
          // y part: F_y at the column's nodes, contraction with D.w along y, top/bottom lifting
-         const double hx = sGeom[cs * 4 + 2], hy = sGeom[cs * 4 + 3];
-         double *uc = su + cs * CS + ca;
+         const double hx = sGeom[cs * 4 + 2];
+         const double *uc = su + cs * CS + ca;
          double Fy[4][N1];
 #pragma unroll
          for (int b = 0; b < N1; ++b)
@@ -671,26 +541,70 @@ namespace dflo
             Fy[3][b] = F[3];
          }
          const double hw = hx * T.gw[ca];
-         const double dt = A.dt_cell ? A.dt_cell[c0 + cs] : dt_global;
-         const double wah = T.gw[ca] * hx * hy;
+         double *rc = sR + cs * CS + ca;
 #pragma unroll
          for (int c = 0; c < 4; ++c)
-         {
-            const double HBc = sT[(c >> 1) * TH + 2 * pT_col + (c & 1)]; // flux on the own bottom face
-            const double WTc = sm[S::O_W + tid * 4 + c];                 // ... and on the own top face
 #pragma unroll
             for (int b = 0; b < N1; ++b)
             {
                double sy = 0.0;
 #pragma unroll
                for (int bp = 0; bp < N1; ++bp) sy = fma (Fy[c][bp], T.dw[bp][b], sy);
-               const double fy = WTc * T.e1[b] - HBc * T.e0[b];
-               const double ry = hw * (sy - fy);
-               // MODE_STAGE: u + dt M^-1 r_y (claw.cc:228-258 on a Cartesian cell: M^-1 = 1 / (w_a w_b hx hy));  MODE_RHS: r_y
-               if (A.mode == MODE_RHS)
-                  uc[c * NS + b * N1] = ry;
+               const double fy = WT[c] * T.e1[b] - HB[c] * T.e0[b];
+               rc[c * NS + b * N1] = hw * (sy - fy);
+            }
+      }
+      if (row_on)
+      {
+         const double hx = sGeom[rs * 4 + 2], hy = sGeom[rs * 4 + 3];
+         const double *uc = su + rs * CS + rb * N1;
+         double u[4][N1], Fx[4][N1];
+#pragma unroll
+         for (int c = 0; c < 4; ++c) load_line<N1> (uc + c * NS, u[c]);
+#pragma unroll
+         for (int a = 0; a < N1; ++a)
+         {
+            const double W[4] = {u[0][a], u[1][a], u[2][a], u[3][a]};
+            double F[4];
+            if (A.dbg & 2)
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c) F[c] = W[c];
+            }
+            else
+               flux_x (W, F);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Fx[c][a] = F[c];
+         }
+         const double hw = hy * T.gw[rb];
+#pragma unroll
+         for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int a = 0; a < N1; ++a)
+            {
+               double sx = 0.0;
+#pragma unroll
+               for (int ap = 0; ap < N1; ++ap) sx = fma (Fx[c][ap], T.dw[ap][a], sx);
+               const double fx = WR[c] * T.e1[a] - HL[c] * T.e0[a];
+               rrow[c][a] = hw * (sx - fx);
+            }
+         if (A.gravity != 0.0) // assemble_explicit.cc:78, 108-111
+         {
+#pragma unroll
+            for (int a = 0; a < N1; ++a)
+            {
+               const double W[4] = {u[0][a], u[1][a], u[2][a], u[3][a]};
+               double Gv[4];
+               if (A.ext_force)
+               {
+                  const double *f = A.ext_force + ((size_t) (c0 + rs) * NS + rb * N1 + a) * 2;
+                  forcing_ext (W, f[0], f[1], Gv);
+               }
                else
-                  uc[c * NS + b * N1] = fma (dt * fast_rcp (T.gw[b] * wah), ry, uc[c * NS + b * N1]);
+                  forcing (W, Gv);
+               const double w = A.gravity * (T.gw[a] * T.gw[rb] * hx * hy);
+#pragma unroll
+               for (int c = 0; c < 4; ++c) rrow[c][a] += Gv[c] * w;
             }
          }
       }
@@ -703,8 +617,8 @@ namespace dflo
       }
       __syncthreads ();
 
-      // ================= P4: x part, RK combine, write-back, cell average =================
-      double *sPart = sT; // [TC][N1][4] partial cell averages (the trace exchange array is dead)
+      // ================= P4: M^-1, Euler step, RK combine, write-back, cell average =================
+      double *sPart = sm + S::O_PART; // [TC][N1][4] partial cell averages
       const unsigned row_mask = __ballot_sync (0xffffffffu, row_on);
       if (row_on)
       {
@@ -720,16 +634,22 @@ namespace dflo
 #pragma unroll
          for (int c = 0; c < 4; ++c)
          {
-            double w[N1], v[N1];
-            load_line<N1> (su + rs * CS + c * NS + rb * N1, w);
-#pragma unroll
-            for (int a = 0; a < N1; ++a)
+            double ry[N1], v[N1];
+            load_line<N1> (sR + rs * CS + c * NS + rb * N1, ry);
+            if (A.mode == MODE_RHS)
             {
-               if (A.mode == MODE_RHS)
-                  v[a] = rrow[c][a] + w[a];
-               else
+#pragma unroll
+               for (int a = 0; a < N1; ++a) v[a] = rrow[c][a] + ry[a];
+            }
+            else
+            {
+               double u[N1];
+               load_line<N1> (su + rs * CS + c * NS + rb * N1, u);
+#pragma unroll
+               for (int a = 0; a < N1; ++a)
                {
-                  const double un = fma (dt * fast_rcp (T.gw[a] * wbh), rrow[c][a], w[a]);
+                  const double invm = fast_rcp (T.gw[a] * wbh); // claw.cc:228-258 on a Cartesian cell
+                  const double un = u[a] + dt * (rrow[c][a] + ry[a]) * invm;
                   v[a] = need_old ? (1.0 - A.ark) * un + A.ark * uold[c][a] : un;
                }
             }
@@ -774,11 +694,11 @@ namespace dflo
       if (A.fx)
       {
          const P2PFused &F = *A.fx;
-         const int n_send = sdesc[7];
+         const int n_send = gdesc[7];
          if (A.mode == MODE_STAGE && n_send > 0)
          {
             __syncthreads (); // the tile's write-back is complete and visible to the block
-            const int *ent = F.send_entries + 3 * (size_t) sdesc[6];
+            const int *ent = F.send_entries + 3 * (size_t) gdesc[6];
             constexpr int D2 = D / 2;
             for (int i = tid; i < n_send * D2; i += S::THREADS)
             {
