@@ -525,7 +525,9 @@ def main():
     # npg x npg square (cells are numbered x fastest) with 2 x npg interface cells
     nx, ny = npg, npg * world
     x0, x1, y0, y1 = -5.0, 5.0, -5.0 * world, 5.0 * world
-    params, pair = abi.make_params(basis=basis, degree=k, flux=flux, bc=PERIODIC, cfl=0.9, compat="mpi")
+    fixed_dt = float(os.environ.get("DFLO_BENCH_FIXED_DT", "0"))     # developer experiments: no time-step reduction at all
+    params, pair = abi.make_params(basis=basis, degree=k, flux=flux, bc=PERIODIC, cfl=0.0 if fixed_dt > 0 else 0.9,
+                                   time_step=fixed_dt if fixed_dt > 0 else -1.0, compat="mpi")
     mesh = abi.Mesh("rectangle", [nx, ny, x0, x1, y0, y1, 4, 2, 1, 3])
     flat = mesh.flatten(params, pair)
     eng = abi.Engine(flat, params, device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
@@ -547,6 +549,8 @@ def main():
         if flush is not None:
             flush.zero_()
             torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()            # untimed: the ranks launch the step within microseconds of each other
         t, _ = eng.advance(1, elapsed=t)
         return t, eng.last_advance_ms()
 

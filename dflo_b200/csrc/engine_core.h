@@ -1020,6 +1020,7 @@ namespace dflo
          a.n_cells_u = lm.n_local;
          a.pf_tiles = bk.stage_prefetch_tiles ();
          a.dbg = bk.debug_flags ();
+         a.pdl = 0;
          a.n_tiles_owned = lm.n_tiles_owned;
          a.fx = nullptr;
          a.mode = mode;
@@ -1133,12 +1134,13 @@ namespace dflo
       }
 
       // stage kernel + limiters + halo for rk, reading d_time for dt
-      void enqueue_stage (int rk)
+      void enqueue_stage (int rk, int pdl = 0)
       {
          const int out = free_buffer ();
          StageArgs a = stage_args (rk, MODE_STAGE);
          a.out = U[out];
          a.avg_out = AVG[out];
+         a.pdl = pdl;
          const bool fused = fused_halo ();
          if (fused) a.fx = bk.p2p_fused_args (out);
          run_stage (a, false);
@@ -1164,8 +1166,19 @@ namespace dflo
             // bc time: t for rk 0, t+dt afterwards (src/claw.cc:736-745); always t in src_mpi
             // refreshed only when the BC time changes: t for rk 0, then t+dt once (src) or never (src_mpi)
             const bool plus_dt = rk > 0 && prm.compat == DFLO_COMPAT_SRC;
-            if (programs_time_dependent && (rk == 0 || (rk == 1 && plus_dt))) eval_boundary (plus_dt, true);
-            enqueue_stage (rk);
+            const bool bc_refresh = programs_time_dependent && (rk == 0 || (rk == 1 && plus_dt));
+            if (bc_refresh) eval_boundary (plus_dt, true);
+            // programmatic dependent launch (row kernel): the first stage starts beside the time-step kernels -- they
+            // only write the time scalars, which the stage reads in its last phase; a later stage is scheduled into the
+            // tail of the stage before it when nothing sits between the two launches (no limiter, no stand-alone exchange)
+            int pdl = 0;
+            if (!bc_refresh && bk.use_row_kernel (tab.basis, tab.n1) && prm.cfl > 0.0)
+            {
+               const bool back_to_back = !(tvb () || pos ()) && (lm.peers.empty () || fused_halo ());
+               if (rk == 0 && bk.pdl_level () >= 1) pdl = 1;
+               else if (rk > 0 && back_to_back && bk.pdl_level () >= 2) pdl = 2;
+            }
+            enqueue_stage (rk, pdl);
          }
          DtFinalizeArgs f;
          f.time = d_time;

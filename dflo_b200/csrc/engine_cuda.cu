@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <typeinfo>
+#include <vector>
 
 namespace
 {
@@ -81,6 +83,7 @@ namespace
    __global__ void __launch_bounds__ (K::THREADS, K::MIN_BLOCKS) phase_kernel (const typename K::Args a)
    {
       extern __shared__ __align__ (16) double dflo_smem[];
+      dflo::pdl_launch_dependents (); // no-op unless the next launch on the stream asks for programmatic serialization
 #pragma unroll
       for (int p = 0; p < K::NPHASE; ++p)
       {
@@ -133,6 +136,54 @@ namespace
       bool p2p_fused_ok () const { return p2p && p2p_fused; }
       const dflo::P2PFused *p2p_fused_args (int buf) const { return p2p_fused_dev + buf; }
 
+      // developer timeline (DFLO_B200_KTRACE=1): every launch bracketed by events on the ctx stream, steps run eagerly;
+      // per-kernel averages are printed when the ctx closes.  Off by default: nothing is recorded.
+      bool ktrace = false;
+      struct KSpan
+      {
+         const char *name;
+         cudaEvent_t a, b;
+      };
+      std::vector<KSpan> kspans;
+      std::map<std::string, std::pair<double, long>> ktotals;
+      void k_begin (const char *name)
+      {
+         if (!ktrace) return;
+         KSpan sp;
+         sp.name = name;
+         cudaEventCreate (&sp.a);
+         cudaEventCreate (&sp.b);
+         cudaEventRecord (sp.a, stream);
+         kspans.push_back (sp);
+      }
+      void k_end ()
+      {
+         if (ktrace) cudaEventRecord (kspans.back ().b, stream);
+      }
+      void k_collect ()
+      {
+         if (!ktrace) return;
+         cudaStreamSynchronize (stream);
+         for (auto &sp : kspans)
+         {
+            float ms = 0.f;
+            cudaEventElapsedTime (&ms, sp.a, sp.b);
+            auto &t = ktotals[sp.name];
+            t.first += ms;
+            t.second += 1;
+            cudaEventDestroy (sp.a);
+            cudaEventDestroy (sp.b);
+         }
+         kspans.clear ();
+      }
+      void k_report ()
+      {
+         if (!ktrace) return;
+         k_collect ();
+         for (auto &kv : ktotals)
+            std::fprintf (stderr, "[ktrace rank %d] %-28s n %6ld  avg %8.2f us\n", rank, kv.first.c_str (), kv.second.second, 1e3 * kv.second.first / kv.second.second);
+      }
+
       void note (cudaError_t e)
       {
          if (e != cudaSuccess && first_error == cudaSuccess) first_error = e;
@@ -170,6 +221,9 @@ namespace
          row_kernel = !(sk && std::string (sk) == "tile");
          const char *g = std::getenv ("DFLO_B200_GRAPHS");
          use_graphs = g ? (std::atoi (g) != 0) : true;
+         const char *kt = std::getenv ("DFLO_B200_KTRACE");
+         ktrace = kt && std::atoi (kt) != 0;
+         if (ktrace) use_graphs = false;
          if (world > 1)
          {
             if (!nccl_id)
@@ -196,6 +250,7 @@ namespace
 
       void close ()
       {
+         k_report ();
          if (comm) nccl ().CommDestroy (comm);
          comm = nullptr;
          if (ev0) cudaEventDestroy (ev0);
@@ -226,7 +281,11 @@ namespace
          note (cudaStreamSynchronize (stream));
       }
       void zero (void *d, size_t b) { note (cudaMemsetAsync (d, 0, b, stream)); }
-      void sync () { note (cudaStreamSynchronize (stream)); }
+      void sync ()
+      {
+         note (cudaStreamSynchronize (stream));
+         if (ktrace && !kspans.empty () && !capturing) k_collect ();
+      }
       void *stream_handle () const { return (void *) stream; }
 
       int check (std::string &err)
@@ -255,7 +314,9 @@ namespace
             note (rc);
          }
          ++launches;
+         k_begin (typeid (K).name ());
          phase_kernel<K><<<grid, K::THREADS, smem, stream>>> (a);
+         k_end ();
          note (cudaPeekAtLastError ());
       }
       // The stage kernel.  Default: the pipelined persistent form (one producer warp streaming tiles
@@ -274,6 +335,13 @@ namespace
       {
          static const char *e = std::getenv ("DFLO_B200_DBG");
          return e ? std::atoi (e) : 0;
+      }
+      // programmatic dependent launch of the stage kernels (DFLO_B200_PDL: 0 off, 1 first stage beside the time-step
+      // kernels, 2 also stage after stage); off while tracing (the event pairs would serialise it anyway)
+      int pdl_level () const
+      {
+         static const char *e = std::getenv ("DFLO_B200_PDL");
+         return ktrace ? 0 : e ? std::atoi (e) : 2;
       }
       bool use_row_kernel (int basis, int n1) const { return row_kernel && basis == dflo::BASIS_QK && n1 >= 2; }
       // 1-D tables of the row kernel as constant-bank operands
@@ -305,7 +373,25 @@ namespace
          static const cudaError_t rc = cudaFuncSetAttribute (dflo::row_stage_kernel<N1, FLUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
          note (rc);
          ++launches;
-         dflo::row_stage_kernel<N1, FLUX><<<n_tiles, S::THREADS, smem, stream>>> (a);
+         k_begin (a.mode == dflo::MODE_RHS ? "row_stage(rhs)" : a.ark == 0.0 ? "row_stage(rk0)" : "row_stage(rk>0)");
+         if (a.pdl)
+         {
+            // programmatic dependent launch: blocks may be scheduled while the predecessor's last blocks still run
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3 (n_tiles);
+            cfg.blockDim = dim3 (S::THREADS);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            note (cudaLaunchKernelEx (&cfg, dflo::row_stage_kernel<N1, FLUX>, a));
+         }
+         else
+            dflo::row_stage_kernel<N1, FLUX><<<n_tiles, S::THREADS, smem, stream>>> (a);
+         k_end ();
          note (cudaPeekAtLastError ());
       }
       template <class K> void launch_stage (int n_tiles, const typename K::Args &a)
@@ -349,7 +435,9 @@ namespace
       {
          if (n <= 0) return;
          ++launches;
+         k_begin (typeid (K).name ());
          thread_kernel<K><<<(n + 255) / 256, 256, 0, stream>>> (a, n);
+         k_end ();
          note (cudaPeekAtLastError ());
       }
 
@@ -435,7 +523,23 @@ namespace
             dflo::P2PArgs a = p2p_args;
             a.dt_val = p;
             ++launches;
-            dflo::dt_min_kernel<<<1, 32, 0, stream>>> (a, finalize ? 1 : 0, time_step);
+            k_begin ("dt_min_kernel");
+            if (pdl_level () >= 1)
+            {
+               cudaLaunchConfig_t cfg = {};
+               cfg.gridDim = dim3 (1);
+               cfg.blockDim = dim3 (32);
+               cfg.stream = stream;
+               cudaLaunchAttribute at[1];
+               at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+               at[0].val.programmaticStreamSerializationAllowed = 1;
+               cfg.attrs = at;
+               cfg.numAttrs = 1;
+               note (cudaLaunchKernelEx (&cfg, dflo::dt_min_kernel, a, finalize ? 1 : 0, time_step));
+            }
+            else
+               dflo::dt_min_kernel<<<1, 32, 0, stream>>> (a, finalize ? 1 : 0, time_step);
+            k_end ();
             note (cudaPeekAtLastError ());
             return finalize;
          }
@@ -634,7 +738,9 @@ namespace
          static const int dbg = std::getenv ("DFLO_B200_P2P_DBG") ? std::atoi (std::getenv ("DFLO_B200_P2P_DBG")) : 0; // timing experiments only
          if (dbg & 4) return true;
          if (dbg & 1) a.nseg = 0;
+         k_begin ("halo_push_kernel");
          dflo::halo_push_kernel<<<p2p_grid, 256, 0, stream>>> (a);
+         k_end ();
          note (cudaPeekAtLastError ());
          return true;
       }

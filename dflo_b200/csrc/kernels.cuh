@@ -96,6 +96,9 @@ namespace dflo
       int pf_tiles;           // row kernel: prefetch distance in tiles (resident blocks of the device)
       int n_tiles_owned;      // tiles >= this one are redundantly updated ghost cells: only their means are stored
       const P2PFused *fx;     // row kernel: halo exchange over peer memory fused into the stage kernel, or nullptr
+      int pdl;                // row kernel launched as a programmatic dependent of its predecessor on the stream: 0 no;
+                              // 1 the predecessor only wrote the time scalars (everything else may be read at once);
+                              // 2 the predecessor wrote u / cell averages (nothing of this step's data may be read before the wait)
       int dbg;                // developer timing experiments only (DFLO_B200_DBG): 1 no Riemann solves, 2 no volume fluxes, 4 no edge jobs
       int mode;
       int compat_mpi;
@@ -108,6 +111,11 @@ namespace dflo
 #if defined(__CUDACC__)
    // ---- sm_100a asynchronous bulk copies (TMA unit, 1-D): global -> shared completing on an
    //      mbarrier, shared -> global as a bulk group ----
+   // Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+   // while its predecessor on the stream still runs; it must not read what the predecessor writes before pdl_wait (),
+   // which returns when the predecessor has completed and flushed.  Both are no-ops in an ordinary launch.
+   __device__ __forceinline__ void pdl_launch_dependents () { asm volatile ("griddepcontrol.launch_dependents;" ::: "memory"); }
+   __device__ __forceinline__ void pdl_wait () { asm volatile ("griddepcontrol.wait;" ::: "memory"); }
    __device__ __forceinline__ unsigned smem_addr (const void *p) { return (unsigned) __cvta_generic_to_shared (p); }
    __device__ __forceinline__ void mbar_init (void *bar, unsigned count)
    {

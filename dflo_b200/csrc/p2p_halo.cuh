@@ -136,6 +136,11 @@ namespace dflo
    // slots [parity][r] turn non-negative, and re-arms them with -1 for the exchange after next.
    __global__ void dt_min_kernel (const P2PArgs a, int finalize, double time_step)
    {
+      // launched as a programmatic dependent of the per-cell time-step kernel and itself the predecessor of the first
+      // stage kernel: that one may start at once (it reads dt in its last phase, behind its own wait for this kernel);
+      // this one waits here for the local minimum to be complete
+      asm volatile ("griddepcontrol.launch_dependents;" ::: "memory");
+      asm volatile ("griddepcontrol.wait;" ::: "memory");
       const int r = threadIdx.x;
       const unsigned long long e = *reinterpret_cast<volatile unsigned long long *> (a.epochs + 2);
       const int par = (int) (e & 1ull);

@@ -243,6 +243,7 @@ namespace dflo
       const RowConst &T = c_row[N1];
       const int tid = threadIdx.x;
       const int *gdesc = A.rowdesc + (size_t) blockIdx.x * S::DESC_INTS;
+      pdl_launch_dependents (); // the next kernel on the stream may be scheduled into the tail of this one
       const int c0 = gdesc[0], ncb = gdesc[1], nh = gdesc[2];
       // halo thread i = tid - TC: its cell id is requested together with the header, not after it (one trip less
       // in front of the copies); entries past nh are inside the descriptor and unused
@@ -250,6 +251,9 @@ namespace dflo
       if (tid >= TC && tid < TC + S::NH) halo_cell = gdesc[S::OFF_HALO + tid - TC];
       const bool need_old = A.mode == MODE_STAGE && A.ark != 0.0;
       constexpr unsigned cell_bytes = (unsigned) (D * sizeof (double));
+      // launched into the tail of the previous stage kernel: its output is this kernel's input (the descriptor words
+      // above are static data)
+      if (A.pdl == 2) pdl_wait ();
 
       // ---- stage the tile: per-cell bulk copies into the padded layout, descriptor, geometry ----
       if (tid == 0)
@@ -300,7 +304,6 @@ namespace dflo
             asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.rowdesc + (size_t) bt * S::DESC_INTS), "r"((unsigned) (S::DESC_INTS * sizeof (int))) : "memory");
          }
       }
-      const double dt_global = A.time[1]; // issued before the wait: its latency hides behind the staging
       mbar_wait (sm, 0);
 
       const bool main_thread = tid < S::MAIN;
@@ -624,7 +627,9 @@ namespace dflo
       {
          const int cell = c0 + rs;
          const double hx = sGeom[rs * 4 + 2], hy = sGeom[rs * 4 + 3];
-         const double dt = A.dt_cell ? A.dt_cell[cell] : dt_global;
+         // first stage of a step launched beside the time-step kernels (pdl == 1): dt is the only thing they write
+         if (A.pdl == 1) pdl_wait ();
+         const double dt = A.dt_cell ? A.dt_cell[cell] : A.time[1];
          const size_t goff = (size_t) cell * D + rb * N1;
          const double wbh = T.gw[rb] * hx * hy;
          // a tile of redundantly updated ghost cells keeps only its means: the solution itself
@@ -691,51 +696,44 @@ namespace dflo
       }
 
       // ================= fused halo exchange over peer memory (p2p_halo.cuh) =================
-      if (A.fx)
+      // Only the tiles that own cells a peer needs do anything here (the descriptor copy in shared memory says so):
+      // the other blocks retire without touching global memory again.
+      if (A.fx && A.mode == MODE_STAGE && sdesc[7] > 0)
       {
          const P2PFused &F = *A.fx;
-         const int n_send = gdesc[7];
-         if (A.mode == MODE_STAGE && n_send > 0)
+         const int n_send = sdesc[7];
+         __syncthreads (); // the tile's write-back is complete and visible to the block
+         const int *ent = F.send_entries + 3 * (size_t) sdesc[6];
+         constexpr int D2 = D / 2;
+         for (int i = tid; i < n_send * D2; i += S::THREADS)
          {
-            __syncthreads (); // the tile's write-back is complete and visible to the block
-            const int *ent = F.send_entries + 3 * (size_t) gdesc[6];
-            constexpr int D2 = D / 2;
-            for (int i = tid; i < n_send * D2; i += S::THREADS)
-            {
-               const int e = i / D2, c = i - e * D2;
-               const int cell = ent[3 * e], pi = ent[3 * e + 1], dc = ent[3 * e + 2];
-               reinterpret_cast<double2 *> (F.dstU[pi] + (size_t) dc * D)[c] = __ldcg (reinterpret_cast<const double2 *> (A.out + (size_t) cell * D) + c);
-            }
-            for (int i = tid; i < n_send * 2; i += S::THREADS)
-            {
-               const int e = i >> 1;
-               const int cell = ent[3 * e], pi = ent[3 * e + 1], dc = ent[3 * e + 2];
-               reinterpret_cast<double2 *> (F.dstA[pi] + (size_t) dc * 4)[i & 1] = __ldcg (reinterpret_cast<const double2 *> (A.avg_out + (size_t) cell * 4) + (i & 1));
-            }
-            __threadfence ();
-            __syncthreads ();
-            if (tid == 0)
-            {
-               const unsigned int done = atomicAdd (F.send_counter, 1u);
-               if (done == (unsigned int) F.n_send_tiles - 1)
-               {
-                  // last sending tile of this stage: everything the peers need is on its way
-                  *F.send_counter = 0;
-                  __threadfence_system ();
-                  const unsigned long long e = *reinterpret_cast<volatile unsigned long long *> (F.epochs);
-                  for (int p = 0; p < F.npeers; ++p) st_release_sys (F.peer_flags[p] + F.world + F.me, e);
-               }
-            }
+            const int e = i / D2, c = i - e * D2;
+            const int cell = ent[3 * e], pi = ent[3 * e + 1], dc = ent[3 * e + 2];
+            reinterpret_cast<double2 *> (F.dstU[pi] + (size_t) dc * D)[c] = __ldcg (reinterpret_cast<const double2 *> (A.out + (size_t) cell * D) + c);
          }
+         for (int i = tid; i < n_send * 2; i += S::THREADS)
+         {
+            const int e = i >> 1;
+            const int cell = ent[3 * e], pi = ent[3 * e + 1], dc = ent[3 * e + 2];
+            reinterpret_cast<double2 *> (F.dstA[pi] + (size_t) dc * 4)[i & 1] = __ldcg (reinterpret_cast<const double2 *> (A.avg_out + (size_t) cell * 4) + (i & 1));
+         }
+         __threadfence ();
+         __syncthreads ();
          if (tid == 0)
          {
-            // the epoch advances when the LAST block of the launch retires: every tile that waits
-            // or publishes has read it by then
-            const unsigned int done = atomicAdd (F.block_counter, 1u);
-            if (done == gridDim.x - 1)
+            const unsigned int done = atomicAdd (F.send_counter, 1u);
+            if (done == (unsigned int) F.n_send_tiles - 1)
             {
-               *F.block_counter = 0;
-               if (A.mode == MODE_STAGE) *F.epochs = *reinterpret_cast<volatile unsigned long long *> (F.epochs) + 1;
+               // last sending tile of this stage: everything the peers need is on its way
+               *F.send_counter = 0;
+               __threadfence_system ();
+               const unsigned long long e = *reinterpret_cast<volatile unsigned long long *> (F.epochs);
+               for (int p = 0; p < F.npeers; ++p) st_release_sys (F.peer_flags[p] + F.world + F.me, e);
+               // The epoch advances here, not when the launch retires (that took an atomic per block).  The tiles that
+               // wait for the peers are the boundary tiles, first in the tile order, and have read the epoch long before
+               // the last sender finishes; a waiting tile that starts later reads the advanced value and waits for the
+               // flags of THIS exchange instead -- raised unconditionally by every peer, and implying the earlier ones.
+               *reinterpret_cast<volatile unsigned long long *> (F.epochs) = e + 1;
             }
          }
       }

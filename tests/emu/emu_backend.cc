@@ -68,6 +68,7 @@ namespace
       template <class K> void launch_stage (int n_tiles, const typename K::Args &a) { launch<K> (n_tiles, a); }
       // the register-blocked Qk kernel exists only as CUDA code; the emulation runs the phase kernel
       bool use_row_kernel (int, int) const { return false; }
+      int pdl_level () const { return 0; }
       void prepare_tables (const dflo::FeTables &, const std::vector<double> &) {}
       // thread-per-cell Pk stage kernel (cell_stage.cuh): DFLO_EMU_PK=cell; default: the tile kernel
       bool use_pk_cell_kernel () const { const char *e = std::getenv ("DFLO_EMU_PK"); return e && std::string (e) == "cell"; }
