@@ -38,6 +38,7 @@ class FlatMesh(ctypes.Structure):
         ("neighbor", c_int_p), ("face_flags", c_u8_p),
         ("n_boundary_faces", ctypes.c_int32),
         ("bface_cell", c_int_p), ("bface_face", c_int_p), ("bface_id", c_int_p),
+        ("cell_vertices", c_double_p), ("neighbor_face", c_u8_p),
     ]
 
 
@@ -52,7 +53,7 @@ class Params(ctypes.Structure):
         ("M", ctypes.c_double), ("beta", ctypes.c_double), ("gravity", ctypes.c_double),
         ("cfl", ctypes.c_double), ("time_step", ctypes.c_double),
         ("bc_kind", ctypes.c_int32 * MAX_BOUNDARIES),
-        ("shock_indicator", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("shock_indicator", ctypes.c_int32), ("mapping", ctypes.c_int32),
     ]
 
 
@@ -64,11 +65,12 @@ class DfloError(RuntimeError):
 
 def make_params(basis="Qk", degree=1, flux="lxf", limiter="none", char_lim=False, pos_lim=False,
                 conserve_angular_momentum=False, M=0.0, beta=1.0, gravity=0.0, cfl=0.9,
-                time_step=-1.0, bc=None, compat="src", shock_indicator="limiter"):
+                time_step=-1.0, bc=None, compat="src", shock_indicator="limiter", mapping="cartesian"):
     """bc: {boundary_id: kind} or {boundary_id: ("periodic", partner)}; default outflow
     (reference src/parameters.cc:384). Returns (Params, periodic_pair[10])."""
     p = Params()
     p.shock_indicator = INDICATOR[shock_indicator]
+    p.mapping = {"cartesian": 0, "q1": 1}[mapping]
     p.basis, p.degree, p.flux_type = BASIS[basis], degree, FLUX[flux]
     p.limiter_type = LIMITER[limiter]
     p.char_lim, p.pos_lim = int(char_lim), int(pos_lim)

@@ -642,9 +642,10 @@ namespace dflo
          compute_cell_average (cur, lm.n_owned);
          exchange_halo (cur);
          old = cur;
-         // a step graph is a function of the starting buffer alone; only the out-of-graph halo exchange above
-         // (its epochs are baked into the captured launches) makes the captured steps stale
-         if (!lm.peers.empty ()) bk.drop_graphs ();
+         // a step graph is a function of the starting buffer alone, on sharded contexts too: the exchange epochs are
+         // device-side counters (p2p_halo.cuh), advanced by the exchange above on every rank alike, so the captured
+         // steps stay valid (DFLO_B200_KEEP_GRAPHS=0 restores the r01 behaviour of capturing again)
+         if (!lm.peers.empty () && !bk.keep_graphs_sharded ()) bk.drop_graphs ();
          return bk.check (error);
       }
 

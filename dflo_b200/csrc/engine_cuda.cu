@@ -343,6 +343,11 @@ namespace
          static const char *e = std::getenv ("DFLO_B200_PDL");
          return ktrace ? 0 : e ? std::atoi (e) : 2;
       }
+      bool keep_graphs_sharded () const
+      {
+         static const char *e = std::getenv ("DFLO_B200_KEEP_GRAPHS");
+         return p2p && !(e && std::atoi (e) == 0); // with NCCL on the stream the steps are not captured to begin with
+      }
       bool use_row_kernel (int basis, int n1) const { return row_kernel && basis == dflo::BASIS_QK && n1 >= 2; }
       // 1-D tables of the row kernel as constant-bank operands
       void prepare_tables (const dflo::FeTables &t, const std::vector<double> &flat)

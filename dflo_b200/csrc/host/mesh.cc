@@ -23,6 +23,8 @@ namespace dflo
       m.bface_cell = bface_cell.data ();
       m.bface_face = bface_face.data ();
       m.bface_id = bface_id.data ();
+      m.cell_vertices = vertices.data ();
+      m.neighbor_face = neighbor_face.data ();
       return m;
    }
 
@@ -47,6 +49,9 @@ namespace dflo
       out.size.resize (2 * (size_t) nc);
       out.neighbor.assign (4 * (size_t) nc, -1);
       out.face_flags.assign (4 * (size_t) nc, 0);
+      out.vertices.resize (8 * (size_t) nc);
+      out.neighbor_face.resize (4 * (size_t) nc);
+      for (size_t i = 0; i < out.neighbor_face.size (); ++i) out.neighbor_face[i] = (uint8_t) ((i & 3) ^ 1);
 
       struct Side { int cell, face; };
       std::unordered_map<uint64_t, std::pair<Side, Side>> edges;
@@ -58,16 +63,36 @@ namespace dflo
          const double x0 = V[2 * v[0]], y0 = V[2 * v[0] + 1];
          const double hx = V[2 * v[1]] - x0, hy = V[2 * v[2] + 1] - y0;
          const double tol = 1e-12 * (std::fabs (hx) + std::fabs (hy));
+         for (int i = 0; i < 4; ++i)
+         {
+            out.vertices[8 * (size_t) c + 2 * i] = V[2 * v[i]];
+            out.vertices[8 * (size_t) c + 2 * i + 1] = V[2 * v[i] + 1];
+         }
          if (!(hx > 0 && hy > 0) || std::fabs (V[2 * v[1] + 1] - y0) > tol || std::fabs (V[2 * v[2]] - x0) > tol
              || std::fabs (V[2 * v[3]] - (x0 + hx)) > tol || std::fabs (V[2 * v[3] + 1] - (y0 + hy)) > tol)
          {
-            err = "cell " + std::to_string (c) + " is not an axis-aligned rectangle with lexicographic vertices (mapping = cartesian)";
-            return false;
+            if (out.cartesian)
+               out.why_not_cartesian = "cell " + std::to_string (c) + " is not an axis-aligned rectangle with lexicographic vertices (mapping = cartesian)";
+            out.cartesian = false;
+            // MappingQ1: the Jacobian of the bilinear map must be positive at the four vertices
+            const double *q = &out.vertices[8 * (size_t) c];
+            for (int i = 0; i < 4; ++i)
+            {
+               const double xi = i & 1, eta = i >> 1;
+               const double xxi = (q[2] - q[0]) * (1 - eta) + (q[6] - q[4]) * eta, xeta = (q[4] - q[0]) * (1 - xi) + (q[6] - q[2]) * xi;
+               const double yxi = (q[3] - q[1]) * (1 - eta) + (q[7] - q[5]) * eta, yeta = (q[5] - q[1]) * (1 - xi) + (q[7] - q[3]) * xi;
+               if (!(xxi * yeta - xeta * yxi > 0.0))
+               {
+                  err = "cell " + std::to_string (c) + " has a non-positive Jacobian (vertices not in deal.II's lexicographic order, or not convex)";
+                  return false;
+               }
+            }
          }
          out.origin[2 * (size_t) c] = x0;
          out.origin[2 * (size_t) c + 1] = y0;
-         out.size[2 * (size_t) c] = hx;
-         out.size[2 * (size_t) c + 1] = hy;
+         // off Cartesian meshes these are only nominal sizes (tile ordering heuristics); the q1 kernels use the vertices
+         out.size[2 * (size_t) c] = out.cartesian ? hx : std::hypot (hx, V[2 * v[1] + 1] - y0);
+         out.size[2 * (size_t) c + 1] = out.cartesian ? hy : std::hypot (V[2 * v[2]] - x0, hy);
          for (int f = 0; f < 4; ++f)
          {
             const uint64_t k = edge_key (v[FV[f][0]], v[FV[f][1]]);
@@ -93,16 +118,21 @@ namespace dflo
          const Side a = kv.second.first, b = kv.second.second;
          if (b.cell >= 0)
          {
-            if ((a.face ^ 1) != b.face)
+            // do the two cells run along the shared line in the same direction?  (deal.II orients 2-D meshes so that they
+            // do; a mesh that does not is still integrated correctly with the face points of one side reversed)
+            const bool rev = pm.cells[4 * (size_t) a.cell + FV[a.face][0]] != pm.cells[4 * (size_t) b.cell + FV[b.face][0]];
+            if ((a.face ^ 1) != b.face || rev)
             {
-               err = "neighbouring cells are not equally oriented (mapping = cartesian)";
-               return false;
+               if (out.cartesian) out.why_not_cartesian = "neighbouring cells are not equally oriented (mapping = cartesian)";
+               out.cartesian = false;
             }
             out.neighbor[4 * (size_t) a.cell + a.face] = b.cell;
             out.neighbor[4 * (size_t) b.cell + b.face] = a.cell;
+            out.neighbor_face[4 * (size_t) a.cell + a.face] = (uint8_t) b.face;
+            out.neighbor_face[4 * (size_t) b.cell + b.face] = (uint8_t) a.face;
             // MeshWorker::loop integrates an interior face once, from the smaller cell
-            out.face_flags[4 * (size_t) a.cell + a.face] = a.cell < b.cell ? DFLO_FACE_OWNER : 0;
-            out.face_flags[4 * (size_t) b.cell + b.face] = b.cell < a.cell ? DFLO_FACE_OWNER : 0;
+            out.face_flags[4 * (size_t) a.cell + a.face] = (a.cell < b.cell ? DFLO_FACE_OWNER : 0) | (rev ? DFLO_FACE_FLIP : 0);
+            out.face_flags[4 * (size_t) b.cell + b.face] = (b.cell < a.cell ? DFLO_FACE_OWNER : 0) | (rev ? DFLO_FACE_FLIP : 0);
          }
          else
          {
@@ -125,9 +155,10 @@ namespace dflo
             const int id = bid[4 * (size_t) c + f];
             if (id >= 0 && bc_kind[id] == DFLO_BC_PERIODIC) by_id[id].push_back (Side{c, f});
          }
-      auto tangential = [&] (const Side &s) {
-         return s.face < 2 ? out.origin[2 * (size_t) s.cell + 1] + 0.5 * out.size[2 * (size_t) s.cell + 1]
-                           : out.origin[2 * (size_t) s.cell] + 0.5 * out.size[2 * (size_t) s.cell];
+      auto tangential = [&] (const Side &s) { // centre of the face along the boundary it lies on
+         const double *q = &out.vertices[8 * (size_t) s.cell];
+         const int a = FV[s.face][0], b = FV[s.face][1];
+         return s.face < 2 ? 0.5 * (q[2 * a + 1] + q[2 * b + 1]) : 0.5 * (q[2 * a] + q[2 * b]);
       };
       for (auto &kv : by_id)
       {

@@ -30,6 +30,10 @@ namespace dflo
       std::vector<int32_t> neighbor;
       std::vector<uint8_t> face_flags;
       std::vector<int32_t> bface_cell, bface_face, bface_id;
+      std::vector<double> vertices;        // [nc][4][2]
+      std::vector<uint8_t> neighbor_face;  // [nc][4]
+      bool cartesian = true;               // every cell an axis-aligned rectangle, every neighbour across face f on its face f ^ 1
+      std::string why_not_cartesian;
       dflo_flat_mesh view () const;
       int n_cells () const { return origin.size () / 2; }
       int n_bfaces () const { return bface_cell.size (); }
@@ -37,8 +41,9 @@ namespace dflo
 
    // Derive neighbours, MeshWorker face ownership, periodic partners and the boundary-face list.
    // bc_kind[id] == DFLO_BC_PERIODIC marks periodic ids, periodic_pair[id] their partner id.
-   // Returns false (and sets err) for cells that are not axis-aligned rectangles in lexicographic
-   // orientation (MappingCartesian), non-manifold faces or unmatched periodic faces.
+   // General straight-sided quadrilaterals are accepted (mapping = q1): FlatMesh::cartesian says whether the mesh also
+   // qualifies for mapping = cartesian.  Returns false (and sets err) for cells with a non-positive Jacobian,
+   // non-manifold faces or unmatched periodic faces.
    bool flatten (const PrimitiveMesh &pm, const int bc_kind[DFLO_MAX_BOUNDARIES],
                  const int periodic_pair[DFLO_MAX_BOUNDARIES], FlatMesh &out, std::string &err);
 

@@ -78,8 +78,13 @@ enum
                               (src_mpi/assemble_explicit.cc:247-250) */
 };
 
+/* "mapping" of input.prm (src/claw.cc:165-190): cartesian = MappingCartesian (axis-aligned rectangles, the fast kernels);
+ * q1 = MappingQ1 (straight-sided quadrilaterals: per-point Jacobians, general normals, compute_time_step_q) -- Qk basis,
+ * no TVB / positivity limiter (src/parameters.cc:545-549 refuses TVB and Pk off Cartesian grids). */
+enum { DFLO_MAPPING_CARTESIAN = 0, DFLO_MAPPING_Q1 = 1 };
+
 /* Mesh topology and geometry flattened once from the host mesh (deal.II Triangulation +
- * DoFHandler in dflo; src/claw.cc:270-386).  Cartesian cells only (mapping = cartesian). */
+ * DoFHandler in dflo; src/claw.cc:270-386). */
 typedef struct
 {
    int32_t n_cells;
@@ -92,6 +97,11 @@ typedef struct
    const int32_t *bface_cell;   /* [n_boundary_faces] */
    const int32_t *bface_face;   /* [n_boundary_faces] local face number 0..3 */
    const int32_t *bface_id;     /* [n_boundary_faces] boundary id 0..9 */
+   /* mapping = q1 only (may be NULL for mapping = cartesian, where cell_origin / cell_size say it all and the
+    * neighbour across face f sees the face as its face f ^ 1): */
+   const double *cell_vertices;   /* [n_cells][4][2] vertices in deal.II's lexicographic order (cell->vertex(0..3)) */
+   const uint8_t *neighbor_face;  /* [n_cells][4] the neighbour's local number of the shared face; DFLO_FACE_FLIP in
+                                     face_flags when the two cells run along the face in opposite directions */
 } dflo_flat_mesh;
 
 /* The subset of Parameters::AllParameters (src/parameters.h:112-414) the hot path reads. */
@@ -112,7 +122,7 @@ typedef struct
    double time_step;                   /* "time step" (<=0: unused), src/claw.cc:471-472 */
    int32_t bc_kind[DFLO_MAX_BOUNDARIES];   /* DFLO_BC_* per boundary id */
    int32_t shock_indicator;            /* DFLO_INDICATOR_* ("shock indicator" in subsection limiter) */
-   int32_t reserved0;
+   int32_t mapping;                    /* DFLO_MAPPING_* ("mapping"); 0 = cartesian */
 } dflo_params;
 
 typedef struct dflo_ctx dflo_ctx;

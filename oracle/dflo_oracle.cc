@@ -232,10 +232,13 @@ namespace
    struct Cell
    {
       double x0, y0, hx, hy;
+      double vx[4], vy[4]; // vertices, deal.II lexicographic order (A1); MappingQ1 works from these
+      int nbr_face[4];   // the neighbour's local number of the shared face (f ^ 1 on lattice meshes)
       int nbr[4];        // neighbour cell or -1 (boundary)
       int bid[4];        // boundary id if at boundary
       int bface[4];      // index into the non-periodic boundary-face list, or -1
-      bool flip[4];      // periodic face_flip (never set on these axis-aligned meshes)
+      bool flip[4];      // the neighbour runs through the face quadrature points in the opposite order (periodic face_flip;
+                         // general quads whose two cells see the shared line in opposite directions)
    };
 
    const double NORMAL[4][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}}; // MappingCartesian, A6
@@ -266,9 +269,67 @@ struct oracle_ctx
    double ark[3];
    int n_rk;
 
+   UnitValues dtq;          // QIterated(QTrapez,3): the 4x4 equispaced points of compute_time_step_q (claw.cc:522)
+
    int D () const { return fe.D; }
-   double JxW (const Cell &c, int q) const { return vol.w[q] * c.hx * c.hy; }
-   double diameter (const Cell &c) const { return std::sqrt (c.hx * c.hx + c.hy * c.hy); }
+   bool q1 () const { return prm.mapping == ORACLE_MAPPING_Q1; }
+   // MappingQ1: x(xi,eta) = sum_v N_v(xi,eta) x_v, N = (1-xi)(1-eta), xi(1-eta), (1-xi)eta, xi eta;  J = d(x,y)/d(xi,eta)
+   void jacobian (const Cell &c, double xi, double eta, double J[4]) const
+   {
+      J[0] = (c.vx[1] - c.vx[0]) * (1.0 - eta) + (c.vx[3] - c.vx[2]) * eta; // x_xi
+      J[1] = (c.vx[2] - c.vx[0]) * (1.0 - xi) + (c.vx[3] - c.vx[1]) * xi;   // x_eta
+      J[2] = (c.vy[1] - c.vy[0]) * (1.0 - eta) + (c.vy[3] - c.vy[2]) * eta; // y_xi
+      J[3] = (c.vy[2] - c.vy[0]) * (1.0 - xi) + (c.vy[3] - c.vy[1]) * xi;   // y_eta
+   }
+   void map_point (const Cell &c, double xi, double eta, double &x, double &y) const
+   {
+      if (!q1 ())
+      {
+         x = c.x0 + xi * c.hx;
+         y = c.y0 + eta * c.hy;
+         return;
+      }
+      const double n0 = (1.0 - xi) * (1.0 - eta), n1 = xi * (1.0 - eta), n2 = (1.0 - xi) * eta, n3 = xi * eta;
+      x = n0 * c.vx[0] + n1 * c.vx[1] + n2 * c.vx[2] + n3 * c.vx[3];
+      y = n0 * c.vy[0] + n1 * c.vy[1] + n2 * c.vy[2] + n3 * c.vy[3];
+   }
+   double JxW (const Cell &c, int q) const
+   {
+      if (!q1 ()) return vol.w[q] * c.hx * c.hy;
+      double J[4];
+      jacobian (c, vol.x[q], vol.y[q], J);
+      return vol.w[q] * (J[0] * J[3] - J[1] * J[2]);
+   }
+   // cell->diameter(): the longer diagonal;  cell->measure(): the area of the quadrilateral
+   double diameter (const Cell &c) const
+   {
+      if (!q1 ()) return std::sqrt (c.hx * c.hx + c.hy * c.hy);
+      const double d1 = std::hypot (c.vx[3] - c.vx[0], c.vy[3] - c.vy[0]), d2 = std::hypot (c.vx[2] - c.vx[1], c.vy[2] - c.vy[1]);
+      return std::max (d1, d2);
+   }
+   double measure (const Cell &c) const
+   {
+      if (!q1 ()) return c.hx * c.hy;
+      return 0.5 * ((c.vx[3] - c.vx[0]) * (c.vy[2] - c.vy[1]) - (c.vx[2] - c.vx[1]) * (c.vy[3] - c.vy[0]));
+   }
+   // outward unit normal and length of face f (straight edge from vertex FACE_VERT[f][0] to FACE_VERT[f][1])
+   void face_geometry (const Cell &c, int f, double n[2], double &len) const
+   {
+      static const int FV[4][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}};
+      static const double CART[4][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}};
+      if (!q1 ())
+      {
+         n[0] = CART[f][0];
+         n[1] = CART[f][1];
+         len = f < 2 ? c.hy : c.hx;
+         return;
+      }
+      const double tx = c.vx[FV[f][1]] - c.vx[FV[f][0]], ty = c.vy[FV[f][1]] - c.vy[FV[f][0]];
+      len = std::sqrt (tx * tx + ty * ty);
+      const double s = (f == 1 || f == 2) ? 1.0 : -1.0; // (t_y, -t_x) points out of faces 1 and 2 of a positively oriented cell
+      n[0] = s * ty / len;
+      n[1] = -s * tx / len;
+   }
 };
 
 namespace
@@ -299,15 +360,35 @@ namespace
                          && std::fabs (V[2 * v[2]] - cl.x0) <= tol
                          && std::fabs (V[2 * v[3]] - (cl.x0 + cl.hx)) <= tol
                          && std::fabs (V[2 * v[3] + 1] - (cl.y0 + cl.hy)) <= tol;
-         if (!ok)
+         for (int i = 0; i < 4; ++i)
+         {
+            cl.vx[i] = V[2 * v[i]];
+            cl.vy[i] = V[2 * v[i] + 1];
+         }
+         if (!ok && !o.q1 ())
          {
             g_error = "cell is not an axis-aligned rectangle in lexicographic orientation (MappingCartesian)";
             return false;
+         }
+         if (o.q1 ())
+         {
+            // MappingQ1 needs a positive Jacobian at every vertex (convex, counter-clockwise in lexicographic order)
+            for (int i = 0; i < 4; ++i)
+            {
+               double J[4];
+               o.jacobian (cl, i & 1, i >> 1, J);
+               if (!(J[0] * J[3] - J[1] * J[2] > 0.0))
+               {
+                  g_error = "cell with a non-positive Jacobian (vertex order is not deal.II's lexicographic one, or the cell is not convex)";
+                  return false;
+               }
+            }
          }
          for (int f = 0; f < 4; ++f)
          {
             face_map[key (v[FACE_VERT[f][0]], v[FACE_VERT[f][1]])].push_back (std::make_pair (c, f));
             cl.nbr[f] = -1;
+            cl.nbr_face[f] = f ^ 1;
             cl.bid[f] = 0;
             cl.bface[f] = -1;
             cl.flip[f] = false;
@@ -322,6 +403,11 @@ namespace
          {
             o.cells[lst[0].first].nbr[lst[0].second] = lst[1].first;
             o.cells[lst[1].first].nbr[lst[1].second] = lst[0].first;
+            o.cells[lst[0].first].nbr_face[lst[0].second] = lst[1].second;
+            o.cells[lst[1].first].nbr_face[lst[1].second] = lst[0].second;
+            // same two vertices; opposite order = the two cells run along the line in opposite directions
+            const bool rev = C[4 * lst[0].first + FACE_VERT[lst[0].second][0]] != C[4 * lst[1].first + FACE_VERT[lst[1].second][0]];
+            o.cells[lst[0].first].flip[lst[0].second] = o.cells[lst[1].first].flip[lst[1].second] = rev;
          }
          else if (lst.size () == 1)
          {
@@ -354,14 +440,19 @@ namespace
          {
             const int c = cf.first, f = cf.second;
             Cell &cl = o.cells[c];
-            const double tc = (f < 2) ? cl.y0 + 0.5 * cl.hy : cl.x0 + 0.5 * cl.hx;
+            // tangential coordinate of the face centre
+            auto face_tc = [] (const Cell &k, int ff) {
+               const int a = FACE_VERT[ff][0], b = FACE_VERT[ff][1];
+               return (ff < 2) ? 0.5 * (k.vy[a] + k.vy[b]) : 0.5 * (k.vx[a] + k.vx[b]);
+            };
+            const double tc = face_tc (cl, f);
             int found = -1;
             for (auto &cf2 : partners)
             {
                if (cf2.second != (f ^ 1)) continue;
                const Cell &c2 = o.cells[cf2.first];
-               const double tc2 = (f < 2) ? c2.y0 + 0.5 * c2.hy : c2.x0 + 0.5 * c2.hx;
-               if (std::fabs (tc - tc2) < 1e-9 * (cl.hx + cl.hy)) found = cf2.first;
+               const double tc2 = face_tc (c2, cf2.second);
+               if (std::fabs (tc - tc2) < 1e-9 * (std::fabs (cl.hx) + std::fabs (cl.hy))) found = cf2.first;
             }
             if (found < 0)
             {
@@ -432,6 +523,17 @@ namespace
          const int ci = i / ns, bi = i % ns;
          for (int q = 0; q < nq; ++q)
          {
+            if (o.q1 ())
+            {
+               // shape_grad = J^-T grad_unit (MappingQ1 with update_gradients)
+               double J[4];
+               o.jacobian (cl, o.vol.x[q], o.vol.y[q], J);
+               const double det = J[0] * J[3] - J[1] * J[2];
+               const double gu = o.vol.dphi[(bi * nq + q) * 2], gv = o.vol.dphi[(bi * nq + q) * 2 + 1];
+               const double g[2] = {(J[3] * gu - J[2] * gv) / det, (-J[1] * gu + J[0] * gv) / det};
+               for (int d = 0; d < 2; ++d) F_i -= flux[q * 8 + 2 * ci + d] * g[d] * o.JxW (cl, q);
+            }
+            else
             for (int d = 0; d < 2; ++d)
                F_i -= flux[q * 8 + 2 * ci + d] * (o.vol.dphi[(bi * nq + q) * 2 + d] / h[d]) * o.JxW (cl, q);
             F_i -= o.prm.gravity * forcing[q * NC + ci] * o.vol.phi[bi * nq + q] * o.JxW (cl, q);
@@ -459,6 +561,12 @@ namespace
 
    double face_JxW (const oracle_ctx &o, const Cell &cl, int f, int q)
    {
+      if (o.q1 ())
+      {
+         double n[2], len;
+         o.face_geometry (cl, f, n, len);
+         return o.face[f].w[q] * len;
+      }
       return o.face[f].w[q] * (f < 2 ? cl.hy : cl.hx);
    }
 
@@ -512,16 +620,18 @@ namespace
       const int D = o.D (), ns = o.fe.ns, nqf = o.face[f].nq;
       std::vector<double> Wplus (nqf * NC), Wminus (nqf * NC), H (nqf * NC);
       face_values (o, cno, f, Wplus.data ());
+      double NRM[2], flen;
+      o.face_geometry (cl, f, NRM, flen); // fe_v.normal_vector(q): constant along a straight face
 
       if (cl.nbr[f] >= 0)
       {
          // periodic: neighbour values on its own face, both sides integrate independently
-         const int n_cell = cl.nbr[f], n_face = f ^ 1;
+         const int n_cell = cl.nbr[f], n_face = cl.nbr_face[f];
          face_values (o, n_cell, n_face, Wminus.data ());
          for (int q = 0; q < nqf; ++q)
          {
             const int q1 = cl.flip[f] ? nqf - q - 1 : q;
-            phys_numerical_flux (o.prm.flux_type, NORMAL[f], &Wplus[q * NC], &Wminus[q1 * NC],
+            phys_numerical_flux (o.prm.flux_type, NRM, &Wplus[q * NC], &Wminus[q1 * NC],
                                  &o.cell_average[cno * NC], &o.cell_average[n_cell * NC], &H[q * NC]);
          }
       }
@@ -531,14 +641,14 @@ namespace
          const double *g = &o.bc_values[(size_t) cl.bface[f] * nqf * NC];
          for (int q = 0; q < nqf; ++q)
          {
-            phys_wminus (kind, NORMAL[f], &Wplus[q * NC], &g[q * NC], &Wminus[q * NC]);
+            phys_wminus (kind, NRM, &Wplus[q * NC], &g[q * NC], &Wminus[q * NC]);
             const double *Aplus = &o.cell_average[cno * NC];
             double Aminus[NC];
             if (o.prm.compat == ORACLE_COMPAT_MPI) // src_mpi/assemble_explicit.cc:296-321
-               phys_wminus (kind, NORMAL[f], Aplus, &g[q * NC], Aminus);
+               phys_wminus (kind, NRM, Aplus, &g[q * NC], Aminus);
             else                                    // src/assemble_explicit.cc:203-204
                for (int c = 0; c < NC; ++c) Aminus[c] = Aplus[c];
-            phys_numerical_flux (o.prm.flux_type, NORMAL[f], &Wplus[q * NC], &Wminus[q * NC], Aplus,
+            phys_numerical_flux (o.prm.flux_type, NRM, &Wplus[q * NC], &Wminus[q * NC], Aplus,
                                  Aminus, &H[q * NC]);
          }
       }
@@ -558,14 +668,21 @@ namespace
    void integrate_face_term (const oracle_ctx &o, int cno, int f, double *local, double *local_nbr)
    {
       const Cell &cl = o.cells[cno];
-      const int ncno = cl.nbr[f], nf = f ^ 1;
+      const int ncno = cl.nbr[f], nf = cl.nbr_face[f];
       const Cell &ncl = o.cells[ncno];
       const int D = o.D (), ns = o.fe.ns, nqf = o.face[f].nq;
       std::vector<double> Wplus (nqf * NC), Wminus (nqf * NC), H (nqf * NC);
       face_values (o, cno, f, Wplus.data ());
       face_values (o, ncno, nf, Wminus.data ());
+      double NRM[2], flen;
+      o.face_geometry (cl, f, NRM, flen);
+      // the neighbour's q-th face point is this cell's q-th one unless the two cells run along the line in
+      // opposite directions (FEFaceValues of both sides are reinit'ed on the same face: same physical points)
+      if (cl.flip[f])
+         for (int q = 0; q < nqf / 2; ++q)
+            for (int c = 0; c < NC; ++c) std::swap (Wminus[q * NC + c], Wminus[(nqf - 1 - q) * NC + c]);
       for (int q = 0; q < nqf; ++q)
-         phys_numerical_flux (o.prm.flux_type, NORMAL[f], &Wplus[q * NC], &Wminus[q * NC],
+         phys_numerical_flux (o.prm.flux_type, NRM, &Wplus[q * NC], &Wminus[q * NC],
                               &o.cell_average[cno * NC], &o.cell_average[ncno * NC], &H[q * NC]);
       for (int i = 0; i < D; ++i)
       {
@@ -580,7 +697,7 @@ namespace
          double F_i = 0;
          const int ci = i / ns;
          for (int q = 0; q < nqf; ++q)
-            F_i -= H[q * NC + ci] * o.face[nf].phi[(i % ns) * nqf + q] * face_JxW (o, ncl, nf, q);
+            F_i -= H[q * NC + ci] * o.face[nf].phi[(i % ns) * nqf + (cl.flip[f] ? nqf - q - 1 : q)] * face_JxW (o, ncl, nf, q);
          local_nbr[i] -= F_i;
       }
    }
@@ -693,7 +810,7 @@ namespace
          for (int k = 0; k < NC; ++k) avg[k] = 0.0;
          for (int q = 0; q < nq; ++q)
             for (int k = 0; k < NC; ++k) avg[k] += val[q * NC + k] * o.JxW (cl, q);
-         const double measure = cl.hx * cl.hy;
+         const double measure = o.measure (cl);
          for (int k = 0; k < NC; ++k) avg[k] /= measure;
       }
    }
@@ -704,6 +821,26 @@ namespace
    double compute_time_step (oracle_ctx &o, double elapsed, double final_time, double time_step)
    {
       o.global_dt = 1.0e20;
+      if (o.q1 ())
+      {
+         // compute_time_step_q, claw.cc:518-557: largest eigenvalue over the 4x4 equispaced points of QIterated(QTrapez,3)
+         const int D = o.D (), ns = o.fe.ns, nq = o.dtq.nq;
+         for (size_t c = 0; c < o.cells.size (); ++c)
+         {
+            const double *u = &o.current[c * D];
+            double max_eigenvalue = 0.0;
+            for (int q = 0; q < nq; ++q)
+            {
+               double W[NC] = {0, 0, 0, 0};
+               for (int i = 0; i < D; ++i) W[i / ns] += u[i] * o.dtq.phi[(i % ns) * nq + q];
+               max_eigenvalue = std::max (max_eigenvalue, phys_max_eigenvalue (W));
+            }
+            const double h = o.diameter (o.cells[c]) / std::sqrt (2.0);
+            o.dt[c] = o.prm.cfl * h / max_eigenvalue / (2.0 * o.fe.k + 1.0);
+            o.global_dt = std::min (o.global_dt, o.dt[c]);
+         }
+      }
+      else
       for (size_t c = 0; c < o.cells.size (); ++c)
       {
          const double h = o.diameter (o.cells[c]) / std::sqrt (2.0);
@@ -1256,6 +1393,25 @@ oracle_ctx *oracle_create (int nv, const double *V, int nc, const int *C, int nb
          }
       o->posy.init (fe, x, y, w);
    }
+   {
+      // QIterated<2>(QTrapez<1>(), 3): points i/3, tensor product, x fastest (claw.cc:522)
+      std::vector<double> x, y, w;
+      for (int b = 0; b < 4; ++b)
+         for (int a = 0; a < 4; ++a)
+         {
+            x.push_back (a / 3.0);
+            y.push_back (b / 3.0);
+            w.push_back (0.0);
+         }
+      o->dtq.init (fe, x, y, w);
+   }
+   if (o->q1 () && (prm->basis != ORACLE_BASIS_QK || prm->limiter_type != ORACLE_LIMITER_NONE || prm->pos_lim))
+   {
+      // parameters.cc:545-549: TVB and Pk need Cartesian grids; the positivity limiter on mapped cells is not restated
+      g_error = "mapping = q1: Qk basis without limiters only";
+      delete o;
+      return nullptr;
+   }
    const size_t ndof = (size_t) nc * fe.D;
    o->current.assign (ndof, 0.0);
    o->old.assign (ndof, 0.0);
@@ -1306,10 +1462,7 @@ void oracle_get_bfaces (const oracle_ctx *o, int *cell, int *face, int *bid, dou
       bid[b] = o->bf_bid[b];
       const Cell &cl = o->cells[c];
       for (int q = 0; q < nqf; ++q)
-      {
-         xq[(b * nqf + q) * 2 + 0] = cl.x0 + o->face[f].x[q] * cl.hx;
-         xq[(b * nqf + q) * 2 + 1] = cl.y0 + o->face[f].y[q] * cl.hy;
-      }
+         o->map_point (cl, o->face[f].x[q], o->face[f].y[q], xq[(b * nqf + q) * 2 + 0], xq[(b * nqf + q) * 2 + 1]);
    }
 }
 
@@ -1318,10 +1471,7 @@ void oracle_get_cell_qpoints (const oracle_ctx *o, double *xq)
    const int nq = o->vol.nq;
    for (size_t c = 0; c < o->cells.size (); ++c)
       for (int q = 0; q < nq; ++q)
-      {
-         xq[(c * nq + q) * 2 + 0] = o->cells[c].x0 + o->vol.x[q] * o->cells[c].hx;
-         xq[(c * nq + q) * 2 + 1] = o->cells[c].y0 + o->vol.y[q] * o->cells[c].hy;
-      }
+         o->map_point (o->cells[c], o->vol.x[q], o->vol.y[q], xq[(c * nq + q) * 2 + 0], xq[(c * nq + q) * 2 + 1]);
 }
 
 void oracle_get_tables (const oracle_ctx *o, double *gx, double *gw)

@@ -19,6 +19,7 @@ enum { ORACLE_BASIS_QK = 0, ORACLE_BASIS_PK = 1 };         /* parameters.h:390 *
 enum { ORACLE_LIMITER_NONE = 0, ORACLE_LIMITER_TVB = 1, ORACLE_LIMITER_MINMAX = 2 };  /* parameters.h:243, src_mpi/parameters.h:235 */
 enum { ORACLE_BC_PERIODIC = 5 };                           /* src_mpi/equation.h BoundaryKind::periodic */
 enum { ORACLE_COMPAT_SRC = 0, ORACLE_COMPAT_MPI = 1 };
+enum { ORACLE_MAPPING_CARTESIAN = 0, ORACLE_MAPPING_Q1 = 1 };
 
 typedef struct
 {
@@ -36,6 +37,8 @@ typedef struct
                             (src_mpi/assemble_explicit.cc:296-321) */
    int n_threads;        /* >1: cells integrated in parallel chunks, serial copier (WorkStream) */
    int shock_indicator;  /* 0 limiter (all cells, indicator.cc:18-22), 1 density, 2 energy (KXRCF, indicator.cc:50-198) */
+   int mapping;          /* 0 cartesian (MappingCartesian), 1 q1 (MappingQ1: straight-sided quadrilaterals, claw.cc:165-190);
+                            q1: Qk only, no TVB (parameters.cc:545-549), compute_time_step_q (claw.cc:518-557) */
 } oracle_params;
 
 typedef struct oracle_ctx oracle_ctx;

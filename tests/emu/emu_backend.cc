@@ -69,6 +69,7 @@ namespace
       // the register-blocked Qk kernel exists only as CUDA code; the emulation runs the phase kernel
       bool use_row_kernel (int, int) const { return false; }
       int pdl_level () const { return 0; }
+      bool keep_graphs_sharded () const { return false; }
       void prepare_tables (const dflo::FeTables &, const std::vector<double> &) {}
       // thread-per-cell Pk stage kernel (cell_stage.cuh): DFLO_EMU_PK=cell; default: the tile kernel
       bool use_pk_cell_kernel () const { const char *e = std::getenv ("DFLO_EMU_PK"); return e && std::string (e) == "cell"; }
