@@ -25,10 +25,11 @@ namespace dflo_b200_adapter
    {
       std::vector<double> origin, size;
       std::vector<int32_t> neighbor, bface_cell, bface_face, bface_id;
-      std::vector<uint8_t> face_flags;
+      std::vector<uint8_t> face_flags, neighbor_face;
+      std::vector<double> vertices;   // [nc][4][2]: what mapping = q1 works from
       dflo_flat_mesh view () const
       {
-         dflo_flat_mesh m;
+         dflo_flat_mesh m = dflo_flat_mesh ();
          m.n_cells = (int32_t) (origin.size () / 2);
          m.cell_origin = origin.data ();
          m.cell_size = size.data ();
@@ -38,6 +39,8 @@ namespace dflo_b200_adapter
          m.bface_cell = bface_cell.data ();
          m.bface_face = bface_face.data ();
          m.bface_id = bface_id.data ();
+         m.cell_vertices = vertices.data ();
+         m.neighbor_face = neighbor_face.data ();
          return m;
       }
    };
@@ -45,17 +48,20 @@ namespace dflo_b200_adapter
    // Flatten once: what setup_system() computes cell by cell through deal.II iterators (neighbour arrays
    // src/claw.cc:336-380, cell numbering 294-298) becomes the SoA mesh of include/dflo_b200.h, plus the map from
    // (cell, local dof i) to deal.II's global dof index so that deal.II vectors can be handed over as they are.
-   // Returns DFLO_OK, or DFLO_E_UNSUPPORTED with `why` set for what the library does not cover (hanging nodes,
-   // cells that are not axis-aligned rectangles).  `cell->user_index()` must already hold the active-cell counter.
+   // Returns DFLO_OK, or DFLO_E_UNSUPPORTED with `why` set for what the library does not cover (hanging nodes; with
+   // cartesian = true also cells that are not axis-aligned rectangles -- pass false for mapping = q1).
+   // `cell->user_index()` must already hold the active-cell counter.
    template <class DoFHandlerType>
    int flatten (const DoFHandlerType &dof_handler, unsigned int dofs_per_cell, FlatMeshStorage &out, std::vector<uint32_t> &dof_map,
-                std::string &why)
+                std::string &why, bool cartesian = true)
    {
       const unsigned int nc = dof_handler.get_triangulation ().n_active_cells ();
       out.origin.assign (2 * (std::size_t) nc, 0.0);
       out.size.assign (2 * (std::size_t) nc, 0.0);
       out.neighbor.assign (4 * (std::size_t) nc, 0);
       out.face_flags.assign (4 * (std::size_t) nc, 0);
+      out.neighbor_face.assign (4 * (std::size_t) nc, 0);
+      out.vertices.assign (8 * (std::size_t) nc, 0.0);
       out.bface_cell.clear ();
       out.bface_face.clear ();
       out.bface_id.clear ();
@@ -69,7 +75,12 @@ namespace dflo_b200_adapter
          const double hx = cell->vertex (1)[0] - x0, hy = cell->vertex (2)[1] - y0;
          const double skew = std::abs (cell->vertex (1)[1] - y0) + std::abs (cell->vertex (2)[0] - x0)
                              + std::abs (cell->vertex (3)[0] - (x0 + hx)) + std::abs (cell->vertex (3)[1] - (y0 + hy));
-         if (!(hx > 0.0 && hy > 0.0) || skew > 1e-12 * (hx + hy))
+         for (unsigned int i = 0; i < 4; ++i)
+         {
+            out.vertices[8 * c + 2 * i] = cell->vertex (i)[0];
+            out.vertices[8 * c + 2 * i + 1] = cell->vertex (i)[1];
+         }
+         if (cartesian && (!(hx > 0.0 && hy > 0.0) || skew > 1e-12 * (hx + hy)))
          {
             why = "dflo_b200: cells must be axis-aligned rectangles with local x along +x (mapping = cartesian)";
             return DFLO_E_UNSUPPORTED;
@@ -97,6 +108,7 @@ namespace dflo_b200_adapter
             }
             const typename DoFHandlerType::cell_iterator nb = cell->neighbor (f);
             out.neighbor[4 * c + f] = (int32_t) nb->user_index ();
+            out.neighbor_face[4 * c + f] = (uint8_t) cell->neighbor_of_neighbor (f); // f ^ 1 on lattice meshes
             // MeshWorker::loop integrates an interior face once, from the cell that compares smaller
             // (src/assemble_explicit.cc:440-451)
             if (cell < nb) out.face_flags[4 * c + f] |= DFLO_FACE_OWNER;

@@ -120,6 +120,7 @@ namespace dealii
             return a;
          }
          bool neighbor_is_coarser (unsigned int) const { return false; }
+         unsigned int neighbor_of_neighbor (unsigned int f) const { return f ^ 1u; }
          cell_iterator neighbor (unsigned int f) const
          {
             const Triangulation<dim> &t = *dh->tria;

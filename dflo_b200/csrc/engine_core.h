@@ -10,6 +10,7 @@
 #include "expr.h"
 #include "kernels.cuh"
 #include "cell_stage.cuh"
+#include "mapped_stage.cuh"
 #include "partition.h"
 #include "tables.h"
 #include "tables_pack.h"
@@ -88,6 +89,7 @@ namespace dflo
       const double *time;        // [0] t, [1] dt
       int n_bfaces, nqf;
       int use_t_plus_dt;
+      const double *verts;       // mapping = q1: cell vertices [n_local][8], else nullptr
    };
    struct BcEvalKernel
    {
@@ -99,8 +101,16 @@ namespace dflo
          const int cell = A.bf_cell[bf], f = A.bf_face[bf], id = A.bf_id[bf];
          const double *g = A.geom + (size_t) cell * 4;
          const double s = A.gx[q];
-         const double x = g[0] + (f == 0 ? 0.0 : f == 1 ? 1.0 : s) * g[2];
-         const double y = g[1] + (f == 2 ? 0.0 : f == 3 ? 1.0 : s) * g[3];
+         double x = g[0] + (f == 0 ? 0.0 : f == 1 ? 1.0 : s) * g[2];
+         double y = g[1] + (f == 2 ? 0.0 : f == 3 ? 1.0 : s) * g[3];
+         if (A.verts) // the bilinear map of the face point
+         {
+            const double *v = A.verts + (size_t) cell * 8;
+            const double xi = f == 0 ? 0.0 : f == 1 ? 1.0 : s, eta = f == 2 ? 0.0 : f == 3 ? 1.0 : s;
+            const double n0 = (1.0 - xi) * (1.0 - eta), n1 = xi * (1.0 - eta), n2 = (1.0 - xi) * eta, n3 = xi * eta;
+            x = n0 * v[0] + n1 * v[2] + n2 * v[4] + n3 * v[6];
+            y = n0 * v[1] + n1 * v[3] + n2 * v[5] + n3 * v[7];
+         }
          const double t = A.time[0] + (A.use_t_plus_dt ? A.time[1] : 0.0);
          for (int c = 0; c < 4; ++c)
          {
@@ -151,6 +161,9 @@ namespace dflo
       unsigned int *done;
       int finalize, nblocks;
       double time_step;
+      // mapping = q1: compute_time_step_q (claw.cc:518-557) from the solution itself
+      const double *u, *verts, *dtq;
+      int n1;
    };
    struct DtKernel // phase kernel: per-cell dt, block minimum, one atomic per block
    {
@@ -168,7 +181,10 @@ namespace dflo
             double d = 1.0e20;
             if (cell < A.n_cells)
             {
-               d = cell_time_step (A.avg + (size_t) cell * 4, A.geom + (size_t) cell * 4, A.cfl, A.degree);
+               if (A.verts)
+                  d = mapped_cell_time_step (A.u + (size_t) cell * 4 * A.n1 * A.n1, A.verts + (size_t) cell * 8, A.dtq, A.n1, A.cfl, A.degree);
+               else
+                  d = cell_time_step (A.avg + (size_t) cell * 4, A.geom + (size_t) cell * 4, A.cfl, A.degree);
                // a NaN or non-positive cell value (negative density / pressure in the mean) must not poison the
                // block minimum, nor take part in the bit-pattern atomicMin below: the cell is skipped, as
                // `std::min (global_dt, dt(c))` skips a NaN in the reference (claw.cc:508)
@@ -388,6 +404,30 @@ namespace dflo
       else launch_cell_stage_n<BK, 3> (bk, flux, a);
    }
 
+   // mapped (mapping = q1) stage kernel, Qk (mapped_stage.cuh)
+   template <class BK, int N1>
+   void launch_mapped_stage_n (BK &bk, int flux, const MappedStageArgs &a)
+   {
+      switch (flux)
+      {
+         case FLUX_LXF: bk.template launch<MappedStageKernel<N1, FLUX_LXF>> (MappedStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+         case FLUX_SW: bk.template launch<MappedStageKernel<N1, FLUX_SW>> (MappedStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+         case FLUX_KFVS: bk.template launch<MappedStageKernel<N1, FLUX_KFVS>> (MappedStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+         case FLUX_ROE: bk.template launch<MappedStageKernel<N1, FLUX_ROE>> (MappedStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+         case FLUX_KEP: bk.template launch<MappedStageKernel<N1, FLUX_KEP>> (MappedStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+         default: bk.template launch<MappedStageKernel<N1, FLUX_HLLC>> (MappedStageKernel<N1, FLUX_LXF>::grid (a.n_compute), a); break;
+      }
+   }
+   template <class BK>
+   void launch_mapped_stage (BK &bk, int n1, int flux, const MappedStageArgs &a)
+   {
+      if (n1 == 1) launch_mapped_stage_n<BK, 1> (bk, flux, a);
+      else if (n1 == 2) launch_mapped_stage_n<BK, 2> (bk, flux, a);
+      else if (n1 == 3) launch_mapped_stage_n<BK, 3> (bk, flux, a);
+      else if (n1 == 4) launch_mapped_stage_n<BK, 4> (bk, flux, a);
+      else launch_mapped_stage_n<BK, 5> (bk, flux, a);
+   }
+
    template <class BK>
    void launch_limiter (BK &bk, int basis, int n1, const LimiterArgs &a)
    {
@@ -472,6 +512,8 @@ namespace dflo
       TileDesc *d_tiles = nullptr;
       unsigned char *d_fflags = nullptr;
       double *d_ext_force = nullptr; // [n_local][n_q][2], allocated by set_external_force
+      double *d_verts = nullptr, *d_dtq = nullptr; // mapping = q1: cell vertices [n_local][8], l_a(j/3) [4][n1]
+      unsigned char *d_nbr_face = nullptr;
       double *d_geom = nullptr, *d_bc_g = nullptr, *d_stage_tab = nullptr, *d_lim_tab = nullptr, *d_gw = nullptr, *d_gx = nullptr;
       int *d_bkind = nullptr, *d_bf_cell = nullptr, *d_bf_face = nullptr, *d_bf_id = nullptr, *d_l2g = nullptr, *d_flags = nullptr;
       unsigned int *d_err = nullptr;
@@ -494,7 +536,10 @@ namespace dflo
 
       // halo exchange fused into the stage kernel: row kernel, peer memory mapped, nothing between
       // the stage kernel and the exchange (no limiter)
-      bool fused_halo () { return !lm.peers.empty () && !tvb () && !pos () && bk.use_row_kernel (tab.basis, tab.n1) && bk.p2p_fused_ok (); }
+      bool mapped () const { return prm.mapping == DFLO_MAPPING_Q1; }
+      // the register-blocked Qk kernel serves mapping = cartesian on the device
+      bool row_kernel () { return !mapped () && bk.use_row_kernel (tab.basis, tab.n1); }
+      bool fused_halo () { return !lm.peers.empty () && !tvb () && !pos () && row_kernel () && bk.p2p_fused_ok (); }
       int D () const { return tab.D; }
       // a slope limiter that reads the neighbours' new means runs after the stage kernel: TVB, or the
       // minmax limiter of the MPI tree (src_mpi/limiter.cc:36-70)
@@ -513,6 +558,38 @@ namespace dflo
          if (p.limiter_type == DFLO_LIMITER_MINMAX && p.basis != DFLO_BASIS_QK) // src_mpi/parameters.cc:610-611
             return fail (DFLO_E_UNSUPPORTED, "minmax limiter is implemented only for Qk");
          if (mesh.n_cells <= 0) return fail (DFLO_E_INVALID, "empty mesh");
+         if (p.mapping != DFLO_MAPPING_CARTESIAN && p.mapping != DFLO_MAPPING_Q1) return fail (DFLO_E_UNSUPPORTED, "mapping: cartesian or q1");
+         if (p.mapping == DFLO_MAPPING_Q1)
+         {
+            // src/parameters.cc:545-549: TVB and Pk need Cartesian grids; the positivity limiter on mapped cells is not covered
+            if (p.basis != DFLO_BASIS_QK) return fail (DFLO_E_UNSUPPORTED, "mapping = q1: Pk basis can only be used with Cartesian grids");
+            if (p.limiter_type != DFLO_LIMITER_NONE) return fail (DFLO_E_UNSUPPORTED, "mapping = q1: TVB limiter works on cartesian grids only");
+            if (p.pos_lim) return fail (DFLO_E_UNSUPPORTED, "mapping = q1: the positivity limiter is not supported on mapped cells");
+            if (!mesh.cell_vertices || !mesh.neighbor_face) return fail (DFLO_E_INVALID, "mapping = q1 needs cell_vertices and neighbor_face in the flat mesh");
+         }
+         else
+         {
+            // mapping = cartesian: every neighbour sits on the opposite face and runs along it in the same direction,
+            // and (when the vertices are given) every cell is the rectangle cell_origin / cell_size describe
+            for (int c = 0; c < mesh.n_cells; ++c)
+               for (int f = 0; f < 4; ++f)
+               {
+                  if (mesh.neighbor[4 * (size_t) c + f] < 0) continue;
+                  const int fl = mesh.face_flags[4 * (size_t) c + f];
+                  if ((mesh.neighbor_face && mesh.neighbor_face[4 * (size_t) c + f] != (f ^ 1)) || ((fl & DFLO_FACE_FLIP) && !(fl & DFLO_FACE_PERIODIC)))
+                     return fail (DFLO_E_UNSUPPORTED, "neighbouring cells are not equally oriented: use mapping = q1");
+               }
+            if (mesh.cell_vertices)
+               for (int c = 0; c < mesh.n_cells; ++c)
+               {
+                  const double *q = mesh.cell_vertices + 8 * (size_t) c, *o = mesh.cell_origin + 2 * (size_t) c, *h = mesh.cell_size + 2 * (size_t) c;
+                  const double tol = 1e-12 * (fabs (h[0]) + fabs (h[1]));
+                  const bool rect = fabs (q[0] - o[0]) <= tol && fabs (q[1] - o[1]) <= tol && fabs (q[2] - (o[0] + h[0])) <= tol && fabs (q[3] - o[1]) <= tol
+                                    && fabs (q[4] - o[0]) <= tol && fabs (q[5] - (o[1] + h[1])) <= tol && fabs (q[6] - (o[0] + h[0])) <= tol
+                                    && fabs (q[7] - (o[1] + h[1])) <= tol;
+                  if (!rect) return fail (DFLO_E_UNSUPPORTED, "cell is not an axis-aligned rectangle: use mapping = q1");
+               }
+         }
          // claw.cc:457-461: cfl <= 0 selects the fixed time step of the input file, which must then be given
          if (!(p.cfl > 0.0) && !(p.time_step > 0.0)) return fail (DFLO_E_INVALID, "cfl <= 0 needs a positive time step");
          for (int b = 0; b < mesh.n_boundary_faces; ++b)
@@ -525,7 +602,7 @@ namespace dflo
          std::string e;
          // stage-kernel flavour decides the tile shape: register-blocked row kernel (Qk, CUDA) or the
          // generic phase kernel
-         const bool row = bk.use_row_kernel (tab.basis, tab.n1);
+         const bool row = row_kernel ();
          const int tx = row ? row_tx (tab.n1) : tile_nx (tab.n1), ty = row ? row_ty (tab.n1) : tile_ny (tab.n1);
          if (!build_local_mesh (mesh, rank, world, layers, tx, ty, lm, e, row)) return fail (DFLO_E_INVALID, e);
          // the 1-D kernels (layout, pack, cell averages) index DoFs with 32-bit ints
@@ -569,6 +646,22 @@ namespace dflo
          d_fflags = upload (lm.fflags);
          d_geom = upload (lm.geom);
          d_l2g = upload (lm.l2g);
+         if (mapped ())
+         {
+            d_verts = upload (lm.verts);
+            d_nbr_face = upload (lm.nbr_face);
+            // l_a(j/3), j = 0..3: the solution at the points of QIterated(QTrapez,3) (compute_time_step_q, claw.cc:522)
+            std::vector<double> dtq (4 * (size_t) tab.n1);
+            for (int j = 0; j < 4; ++j)
+               for (int a = 0; a < tab.n1; ++a)
+               {
+                  double l = 1.0;
+                  for (int m = 0; m < tab.n1; ++m)
+                     if (m != a) l *= (j / 3.0 - tab.gx[m]) / (tab.gx[a] - tab.gx[m]);
+                  dtq[(size_t) j * tab.n1 + a] = l;
+               }
+            d_dtq = upload (dtq);
+         }
          std::vector<int> kinds (std::max<size_t> (1, lm.bf_id.size ()), 0);
          for (size_t b = 0; b < lm.bf_id.size (); ++b) kinds[b] = prm.bc_kind[lm.bf_id[b]];
          d_bkind = upload (kinds);
@@ -620,7 +713,7 @@ namespace dflo
             bk.free (U[i]);
             bk.free (AVG[i]);
          }
-         void *ptrs[] = {d_ext_force, rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
+         void *ptrs[] = {d_verts, d_dtq, d_nbr_face, d_ext_force, rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
                          d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_shock, d_code, d_prog_start, d_prog_start_t, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles, d_rowdesc, d_send_entries};
          for (void *p : ptrs) bk.free (p);
          for (int k = 0; k < 2; ++k)
@@ -970,6 +1063,32 @@ namespace dflo
       // for Qk on the device, else the tile kernel.  owned_only: right-hand side of the owned cells only.
       void run_stage (const StageArgs &a, bool owned_only)
       {
+         if (mapped ())
+         {
+            MappedStageArgs m;
+            m.u = a.u;
+            m.u_old = a.u_old;
+            m.out = a.out;
+            m.avg = a.avg;
+            m.avg_out = a.avg_out;
+            m.nbr = d_nbr;
+            m.nbr_face = d_nbr_face;
+            m.fflags = d_fflags;
+            m.verts = d_verts;
+            m.bc_g = a.bc_g;
+            m.bkind = a.bkind;
+            m.tab = a.tab;
+            m.time = a.time;
+            m.ext_force = a.ext_force;
+            m.n_compute = owned_only ? lm.n_owned : lm.n_compute;
+            m.n_keep = lm.n_owned;
+            m.mode = a.mode;
+            m.compat_mpi = a.compat_mpi;
+            m.ark = a.ark;
+            m.gravity = a.gravity;
+            launch_mapped_stage (bk, tab.n1, prm.flux_type, m);
+            return;
+         }
          if (tab.basis == BASIS_PK && tab.n1 >= 2 && tab.n1 <= 3 && bk.use_pk_cell_kernel ())
          {
             CellStageArgs c;
@@ -1077,6 +1196,8 @@ namespace dflo
          a.u = U[buf];
          a.avg = AVG[buf];
          a.gw = d_gw;
+         a.gx = d_gx;
+         a.verts = mapped () ? d_verts : nullptr;
          a.n_cells = n_cells;
          a.basis = tab.basis;
          a.n1 = tab.n1;
@@ -1101,6 +1222,7 @@ namespace dflo
          a.n_bfaces = lm.bf_id.size ();
          a.nqf = tab.n1;
          a.use_t_plus_dt = t_plus_dt;
+         a.verts = mapped () ? d_verts : nullptr;
          bk.template launch1d<BcEvalKernel> (a.n_bfaces * a.nqf, a);
       }
 
@@ -1125,6 +1247,10 @@ namespace dflo
          a.nblocks = DtKernel::grid (a.n_cells);
          a.finalize = lm.peers.empty ();
          a.time_step = prm.time_step;
+         a.u = U[cur];
+         a.verts = mapped () ? d_verts : nullptr;
+         a.dtq = d_dtq;
+         a.n1 = tab.n1;
          bk.template launch<DtKernel> (a.nblocks, a);
          if (a.finalize) return;
          if (bk.allreduce_min_dt (d_time + 2, true, prm.time_step)) return; // reduced over the ranks and finalised in one launch
@@ -1173,7 +1299,7 @@ namespace dflo
             // only write the time scalars, which the stage reads in its last phase; a later stage is scheduled into the
             // tail of the stage before it when nothing sits between the two launches (no limiter, no stand-alone exchange)
             int pdl = 0;
-            if (!bc_refresh && bk.use_row_kernel (tab.basis, tab.n1) && prm.cfl > 0.0)
+            if (!bc_refresh && row_kernel () && prm.cfl > 0.0)
             {
                const bool back_to_back = !(tvb () || pos ()) && (lm.peers.empty () || fused_halo ());
                if (rk == 0 && bk.pdl_level () >= 1) pdl = 1;

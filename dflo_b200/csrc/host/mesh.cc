@@ -155,10 +155,21 @@ namespace dflo
             const int id = bid[4 * (size_t) c + f];
             if (id >= 0 && bc_kind[id] == DFLO_BC_PERIODIC) by_id[id].push_back (Side{c, f});
          }
-      auto tangential = [&] (const Side &s) { // centre of the face along the boundary it lies on
-         const double *q = &out.vertices[8 * (size_t) s.cell];
-         const int a = FV[s.face][0], b = FV[s.face][1];
-         return s.face < 2 ? 0.5 * (q[2 * a + 1] + q[2 * b + 1]) : 0.5 * (q[2 * a] + q[2 * b]);
+      // A periodic boundary is a straight side of the domain: vertical (its faces share x) or horizontal.  Faces are
+      // matched by the coordinate along the side; whether the two cells run along the line in the same direction is
+      // read off their vertex order (DFLO_FACE_FLIP), and the partner's local face number is kept (neighbor_face) --
+      // on lattice meshes that is the opposite face and no flip.
+      auto face_end = [&] (const Side &s, int which, int d) { return out.vertices[8 * (size_t) s.cell + 2 * FV[s.face][which] + d]; };
+      auto vertical = [&] (const std::vector<Side> &v) {
+         double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+         for (const Side &s : v)
+            for (int w = 0; w < 2; ++w)
+               for (int d = 0; d < 2; ++d)
+               {
+                  lo[d] = std::min (lo[d], face_end (s, w, d));
+                  hi[d] = std::max (hi[d], face_end (s, w, d));
+               }
+         return hi[0] - lo[0] < hi[1] - lo[1];
       };
       for (auto &kv : by_id)
       {
@@ -168,23 +179,29 @@ namespace dflo
             err = "periodic boundary " + std::to_string (kv.first) + " has no partner boundary";
             return false;
          }
+         const int d = vertical (kv.second) ? 1 : 0; // coordinate along the side
+         auto tangential = [&] (const Side &s) { return 0.5 * (face_end (s, 0, d) + face_end (s, 1, d)); };
          std::vector<Side> cand = by_id[partner];
          std::sort (cand.begin (), cand.end (), [&] (const Side &a, const Side &b) { return tangential (a) < tangential (b); });
          for (const Side &s : kv.second)
          {
             const double t = tangential (s);
-            const double tol = 1e-9 * (out.size[2 * (size_t) s.cell] + out.size[2 * (size_t) s.cell + 1]);
+            const double tol = 1e-9 * std::fabs (face_end (s, 1, d) - face_end (s, 0, d));
             auto lo = std::lower_bound (cand.begin (), cand.end (), t - tol, [&] (const Side &a, double val) { return tangential (a) < val; });
-            int found = -1;
-            for (auto it = lo; it != cand.end () && tangential (*it) <= t + tol; ++it)
-               if (it->face == (s.face ^ 1)) found = it->cell;
-            if (found < 0)
+            if (lo == cand.end () || tangential (*lo) > t + tol)
             {
                err = "periodic face without partner";
                return false;
             }
-            out.neighbor[4 * (size_t) s.cell + s.face] = found;
-            out.face_flags[4 * (size_t) s.cell + s.face] = DFLO_FACE_PERIODIC;
+            const bool rev = (face_end (s, 1, d) - face_end (s, 0, d)) * (face_end (*lo, 1, d) - face_end (*lo, 0, d)) < 0.0;
+            if ((lo->face != (s.face ^ 1) || rev) && out.cartesian)
+            {
+               out.cartesian = false;
+               out.why_not_cartesian = "periodic partners are not equally oriented (mapping = cartesian)";
+            }
+            out.neighbor[4 * (size_t) s.cell + s.face] = lo->cell;
+            out.neighbor_face[4 * (size_t) s.cell + s.face] = (uint8_t) lo->face;
+            out.face_flags[4 * (size_t) s.cell + s.face] = DFLO_FACE_PERIODIC | (rev ? DFLO_FACE_FLIP : 0);
          }
       }
 
@@ -275,6 +292,34 @@ namespace dflo
       lb.block (0, 0, nx, ny);
       lb.boundary ([&] (double, double, int f) { return ids[f]; });
       return lb.pm;
+   }
+
+   // A rectangle whose interior vertices are displaced smoothly (the boundary stays put, so periodic pairs and boundary
+   // ids are those of the rectangle): straight-sided general quadrilaterals for mapping = q1.  rotate != 0 also turns
+   // the vertex order of every other cell by 90 / 180 / 270 degrees, so that neighbours meet on arbitrary local faces
+   // and run along shared lines in opposite directions -- what an unoriented gmsh file can look like.
+   PrimitiveMesh make_skewed_rectangle (int nx, int ny, double x0, double x1, double y0, double y1, const int ids[4], double amp, int rotate)
+   {
+      PrimitiveMesh pm = make_rectangle (nx, ny, x0, x1, y0, y1, ids);
+      const double Lx = x1 - x0, Ly = y1 - y0, pi = 3.14159265358979323846;
+      for (int v = 0; v < pm.n_vertices (); ++v)
+      {
+         const double X = pm.vertices[2 * v], Y = pm.vertices[2 * v + 1];
+         const double s = std::sin (2.0 * pi * (X - x0) / Lx) * std::sin (2.0 * pi * (Y - y0) / Ly);
+         pm.vertices[2 * v] = X + amp * Lx / (2.0 * pi) * 0.9 * s;
+         pm.vertices[2 * v + 1] = Y + amp * Ly / (2.0 * pi) * 0.7 * s;
+      }
+      if (rotate)
+         for (int c = 0; c < pm.n_cells (); ++c)
+         {
+            int *q = &pm.cells[4 * (size_t) c];
+            for (int r = (c * 7 + c / nx) % 4; r > 0; --r) // one quarter turn: (v0 v1 v2 v3) -> (v1 v3 v0 v2), Jacobian stays positive
+            {
+               const int t[4] = {q[1], q[3], q[0], q[2]};
+               for (int i = 0; i < 4; ++i) q[i] = t[i];
+            }
+         }
+      return pm;
    }
 
    // examples/isentropic_vortex/grid.geo: [-5,5]^2; Physical Line 1 bottom, 2 right, 3 top, 4 left

@@ -50,6 +50,9 @@ namespace dflo
    // structured nx x ny block of [x0,x1]x[y0,y1], cells x fastest; ids of (left,right,bottom,top)
    PrimitiveMesh make_rectangle (int nx, int ny, double x0, double x1, double y0, double y1, const int ids[4]);
 
+   // the same rectangle with smoothly displaced interior vertices (general quadrilaterals for mapping = q1); rotate: mixed cell orientations
+   PrimitiveMesh make_skewed_rectangle (int nx, int ny, double x0, double x1, double y0, double y1, const int ids[4], double amp, int rotate);
+
    // The four BASELINE geometries, reproducing the transfinite blocks of the reference's .geo
    // files (no gmsh in this image).  Cells are emitted block by block like gmsh does.
    PrimitiveMesh make_isentropic_vortex_grid (int n_cells_per_side);          // examples/isentropic_vortex/grid.geo

@@ -311,9 +311,14 @@ namespace dflo
             err = "only 'method = rk3' (explicit SSP-RK) runs on the B200 engine; got " + solver_method;
             return false;
          }
-         if (mapping != "cartesian")
+         if (mapping != "cartesian" && mapping != "q1")
          {
-            err = "only 'mapping = cartesian' runs on the B200 engine; got " + mapping;
+            err = "only 'mapping = cartesian' and 'mapping = q1' run on the B200 engine; got " + mapping;
+            return false;
+         }
+         if (mapping == "q1" && pos_lim)
+         {
+            err = "mapping = q1: the positivity limiter is not supported on mapped cells by the B200 engine";
             return false;
          }
          if (time_step_type != "global")
@@ -345,6 +350,7 @@ namespace dflo
          p.pos_lim = pos_lim;
          p.conserve_angular_momentum = conserve_angular_momentum;
          p.compat = compat;
+         p.mapping = mapping == "q1" ? DFLO_MAPPING_Q1 : DFLO_MAPPING_CARTESIAN; // claw.cc:165-190
          p.shock_indicator = shock_indicator == "density" ? DFLO_INDICATOR_DENSITY : shock_indicator == "energy" ? DFLO_INDICATOR_ENERGY : DFLO_INDICATOR_LIMITER; // parameters.cc:229-237
          p.M = M;
          p.beta = beta;

@@ -753,6 +753,8 @@ namespace dflo
       const double *u;
       double *avg;
       const double *gw; // [N1] device
+      const double *gx; // [N1] device (mapping = q1)
+      const double *verts; // [n_cells][8] for mapping = q1, else nullptr
       int n_cells, basis, n1, ns;
    };
 
@@ -762,7 +764,22 @@ namespace dflo
       const int cell = j / 4, c = j % 4;
       const double *uc = A.u + (size_t) cell * 4 * A.ns + c * A.ns;
       double v;
-      if (A.basis == BASIS_QK)
+      if (A.basis == BASIS_QK && A.verts)
+      {
+         // mapping = q1: sum_q u_q JxW_q / measure (claw.cc:562-597 under MappingQ1)
+         const double *q = A.verts + (size_t) cell * 8;
+         v = 0.0;
+         for (int b = 0; b < A.n1; ++b)
+            for (int a = 0; a < A.n1; ++a)
+            {
+               const double xi = A.gx[a], eta = A.gx[b];
+               const double xxi = (q[2] - q[0]) * (1.0 - eta) + (q[6] - q[4]) * eta, xeta = (q[4] - q[0]) * (1.0 - xi) + (q[6] - q[2]) * xi;
+               const double yxi = (q[3] - q[1]) * (1.0 - eta) + (q[7] - q[5]) * eta, yeta = (q[5] - q[1]) * (1.0 - xi) + (q[7] - q[3]) * xi;
+               v += uc[a + A.n1 * b] * (A.gw[a] * A.gw[b] * (xxi * yeta - xeta * yxi));
+            }
+         v /= 0.5 * ((q[6] - q[0]) * (q[5] - q[3]) - (q[4] - q[2]) * (q[7] - q[1]));
+      }
+      else if (A.basis == BASIS_QK)
       {
          v = 0.0;
          for (int b = 0; b < A.n1; ++b)

@@ -1,0 +1,321 @@
+// Stage kernel for `mapping = q1` (MappingQ1: straight-sided quadrilaterals), Qk basis -- SURVEY.md 8(f) row 2.
+//
+// assemble_system (reference src/assemble_explicit.cc:30-452) with the geometry FEValues / FEFaceValues deliver under
+// MappingQ1 (src/claw.cc:165-190), M^-1 (src/claw.cc:228-258: diagonal, 1 / (w_a w_b det J) at the Gauss nodes -- "not exact
+// for general cells", as the reference notes), the RK combine (694-713, 757-760) and compute_cell_average (562-597) in
+// one launch.  On the collocated Gauss-node basis the mapped scheme keeps the sum-factorised form of the Cartesian one:
+//
+//   volume   r_(a,b) += w_b sum_a' F1~(a',b) D[a'][a] w_a'  +  w_a sum_b' F2~(a,b') D[b'][b] w_b'
+//            with the contravariant fluxes  F1~ = y_eta F_x - x_eta F_y,  F2~ = -y_xi F_x + x_xi F_y  (= det J . J^-1 F)
+//   faces    r_(a,b) -= H_0(b) l_a(0) + H_1(b) l_a(1) + H_2(a) l_b(0) + H_3(a) l_b(1),   H_f(q) = w_q |edge_f| H(n_f, W+, W-)
+//
+// A face is straight, so its outward normal and its JxW = w_q |edge| are constants of the face; the neighbour may see
+// the face as any of its own four faces (neighbor_face) and run along it in the opposite direction (DFLO_FACE_FLIP).
+// Which cell is the reference's "plus" side (MeshWorker owner, assemble_explicit.cc:440; both for periodic pairs) is
+// honoured: the non-owner evaluates the owner's Riemann problem (owner's normal = minus its own, bit for bit, because
+// both subtract the same two vertices) and negates, so the two cells subtract the same bits -- conservative to
+// round-off without atomics, and sharded = single GPU bit for bit.
+//
+// One thread per (cell, Gauss node); CPB cells per block; neighbour traces straight from global memory (L2).  This
+// is a phase kernel: the same code runs thread by thread on the CPU emulation backend of tests/emu.  It is the
+// general-geometry path, not the fast one: the register-blocked row kernel serves mapping = cartesian.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace dflo
+{
+   struct MappedStageArgs
+   {
+      const double *u, *u_old;
+      double *out;
+      const double *avg;
+      double *avg_out;
+      const int *nbr;               // [n_local][4]
+      const unsigned char *nbr_face; // [n_local][4]
+      const unsigned char *fflags;  // [n_local][4]
+      const double *verts;          // [n_local][8]
+      const double *bc_g;           // [n_bfaces][N1][4]
+      const int *bkind;
+      const double *tab;            // flat Qk stage tables: dw[N1][N1] e0[N1] e1[N1] gw[N1]
+      const double *time;
+      const double *ext_force;      // [n_local][NQ][2] or nullptr
+      int n_compute, n_keep;
+      int mode, compat_mpi;
+      double ark, gravity;
+   };
+
+   // geometry of a bilinear cell: Jacobian entries at (xi, eta)
+   DFLO_DEV void q1_jacobian (const double *v, double xi, double eta, double &xxi, double &xeta, double &yxi, double &yeta)
+   {
+      xxi = (v[2] - v[0]) * (1.0 - eta) + (v[6] - v[4]) * eta;
+      xeta = (v[4] - v[0]) * (1.0 - xi) + (v[6] - v[2]) * xi;
+      yxi = (v[3] - v[1]) * (1.0 - eta) + (v[7] - v[5]) * eta;
+      yeta = (v[5] - v[1]) * (1.0 - xi) + (v[7] - v[3]) * xi;
+   }
+   // outward unit normal and length of face f: the straight edge between the face's two vertices (deal.II order:
+   // face 0 = v0 v2, 1 = v1 v3, 2 = v0 v1, 3 = v2 v3); (t_y, -t_x) points out of faces 1 and 2
+   DFLO_DEV void q1_face (const double *v, int f, double &nx, double &ny, double &len)
+   {
+      const int a = f == 0 ? 0 : f == 1 ? 1 : f == 2 ? 0 : 2, b = f == 0 ? 2 : f == 1 ? 3 : f == 2 ? 1 : 3;
+      const double tx = v[2 * b] - v[2 * a], ty = v[2 * b + 1] - v[2 * a + 1];
+      len = sqrt (tx * tx + ty * ty);
+      const double s = (f == 1 || f == 2) ? 1.0 : -1.0;
+      nx = s * ty / len;
+      ny = -s * tx / len;
+   }
+   DFLO_DEV double q1_measure (const double *v)
+   {
+      return 0.5 * ((v[6] - v[0]) * (v[5] - v[3]) - (v[4] - v[2]) * (v[7] - v[1]));
+   }
+   DFLO_DEV double q1_diameter (const double *v)
+   {
+      const double d1 = sqrt ((v[6] - v[0]) * (v[6] - v[0]) + (v[7] - v[1]) * (v[7] - v[1]));
+      const double d2 = sqrt ((v[4] - v[2]) * (v[4] - v[2]) + (v[5] - v[3]) * (v[5] - v[3]));
+      return d1 > d2 ? d1 : d2;
+   }
+
+   template <int N1, int FLUX>
+   struct MappedStageKernel
+   {
+      typedef MappedStageArgs Args;
+      static constexpr int NQ = N1 * N1, D = 4 * NQ;
+      static constexpr int CPB = NQ >= 128 ? 1 : 128 / NQ;          // cells per block
+      static constexpr int THREADS = (CPB * NQ + 31) / 32 * 32;
+      static constexpr int MIN_BLOCKS = 2;
+      static constexpr int NPHASE = 4;
+      static constexpr int NTAB = N1 * N1 + 3 * N1;
+      static constexpr int O_TAB = 0;
+      static constexpr int O_U = (NTAB + 1) / 2 * 2;
+      static constexpr int O_F = O_U + CPB * D;                      // [CPB][NQ][8] contravariant fluxes
+      static constexpr int O_H = O_F + CPB * NQ * 8;                 // [CPB][4][N1][4] weighted face fluxes
+      static constexpr int O_P = O_H + CPB * 16 * N1;                // [CPB][NQ][4] the nodes' parts of the cell means
+      static constexpr int SMEM_DOUBLES = O_P + CPB * NQ * 4;
+      static int grid (int n_cells) { return (n_cells + CPB - 1) / CPB; }
+
+      // trace of a cell (D DoFs at `uc`) at point p of its face f -- one fma chain for own and neighbour traces
+      static DFLO_DEV void trace (const double *tb, const double *uc, int f, int p, double W[4])
+      {
+         const double *e = tb + N1 * N1 + (f & 1) * N1;
+         const int base = (f < 2) ? N1 * p : p, stride = (f < 2) ? 1 : N1;
+#pragma unroll
+         for (int c = 0; c < 4; ++c)
+         {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < N1; ++a) s = fma (e[a], uc[c * NQ + base + a * stride], s);
+            W[c] = s;
+         }
+      }
+
+      static DFLO_DEV void phase (int ph, const Args &A, double *sm, int tid, int bid)
+      {
+         double *tb = sm + O_TAB, *su = sm + O_U, *sF = sm + O_F, *sH = sm + O_H;
+         const int slot = tid / NQ, q = tid % NQ;
+         const int cell = bid * CPB + slot;
+         const bool active = slot < CPB && cell < A.n_compute;
+         const int a = q % N1, b = q / N1;
+         const double *gw = tb + N1 * N1 + 2 * N1;
+         const double *gx = A.tab + NTAB; // Gauss nodes follow the stage tables (engine_core: pack_mapped_tables)
+
+         if (ph == 0)
+         {
+            for (int i = tid; i < NTAB; i += THREADS) tb[i] = A.tab[i];
+            if (active)
+            {
+               const double *uc = A.u + (size_t) cell * D;
+#pragma unroll
+               for (int c = 0; c < 4; ++c) su[slot * D + c * NQ + q] = uc[c * NQ + q];
+            }
+            return;
+         }
+         if (!active) return;
+         const double *v = A.verts + (size_t) cell * 8;
+         double *uc = su + slot * D;
+
+         if (ph == 1)
+         {
+            // volume fluxes at the own node
+            {
+               double xxi, xeta, yxi, yeta;
+               q1_jacobian (v, gx[a], gx[b], xxi, xeta, yxi, yeta);
+               const double W[4] = {uc[q], uc[NQ + q], uc[2 * NQ + q], uc[3 * NQ + q]};
+               const double Wy[4] = {W[1], W[0], W[2], W[3]};
+               double Fx[4], G[4];
+               flux_x (W, Fx);
+               flux_x (Wy, G); // F_y(W) = F_x with the momentum components exchanged
+               const double Fy[4] = {G[1], G[0], G[2], G[3]};
+               double *f = sF + (slot * NQ + q) * 8;
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  f[c] = yeta * Fx[c] - xeta * Fy[c];
+                  f[4 + c] = -yxi * Fx[c] + xxi * Fy[c];
+               }
+            }
+            // face fluxes: 4 N1 (face, point) items per cell spread over the cell's NQ threads
+            for (int j = q; j < 4 * N1; j += NQ)
+            {
+               const int f = j / N1, p = j % N1;
+               double nx, ny, len;
+               q1_face (v, f, nx, ny, len);
+               double Wp[4], Wm[4], Ap[4], Am[4], H[4];
+               trace (tb, uc, f, p, Wp);
+               if (flux_uses_averages (FLUX))
+               {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) Ap[c] = A.avg[(size_t) cell * 4 + c];
+               }
+               const int nb = A.nbr[(size_t) cell * 4 + f];
+               if (nb >= 0)
+               {
+                  const int fl = A.fflags[(size_t) cell * 4 + f];
+                  const int nf = A.nbr_face[(size_t) cell * 4 + f];
+                  const int pn = (fl & DFLO_FACE_FLIP) ? N1 - 1 - p : p;
+                  trace (tb, A.u + (size_t) nb * D, nf, pn, Wm);
+                  if (flux_uses_averages (FLUX))
+                  {
+#pragma unroll
+                     for (int c = 0; c < 4; ++c) Am[c] = A.avg[(size_t) nb * 4 + c];
+                  }
+                  if (fl & (DFLO_FACE_OWNER | DFLO_FACE_PERIODIC))
+                     numerical_flux<FLUX> (nx, ny, Wp, Wm, Ap, Am, H);
+                  else
+                  {
+                     // the owner's Riemann problem, its normal = -(nx, ny); the flux out of this cell is minus the owner's
+                     numerical_flux<FLUX> (-nx, -ny, Wm, Wp, Am, Ap, H);
+#pragma unroll
+                     for (int c = 0; c < 4; ++c) H[c] = -H[c];
+                  }
+               }
+               else
+               {
+                  // boundary: W- from the boundary condition (assemble_explicit.cc:176-206)
+                  const int bf = -1 - nb;
+                  const int kind = A.bkind[bf];
+                  double g[4];
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) g[c] = A.bc_g[((size_t) bf * N1 + p) * 4 + c];
+                  compute_wminus (kind, nx, ny, Wp, g, Wm);
+                  if (flux_uses_averages (FLUX))
+                  {
+                     if (A.compat_mpi)
+                        compute_wminus (kind, nx, ny, Ap, g, Am);
+                     else
+                     {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) Am[c] = Ap[c];
+                     }
+                  }
+                  numerical_flux<FLUX> (nx, ny, Wp, Wm, Ap, Am, H);
+               }
+               const double w = gw[p] * len; // fe_v.JxW(q) on a straight face
+               double *h = sH + ((slot * 4 + f) * N1 + p) * 4;
+#pragma unroll
+               for (int c = 0; c < 4; ++c) h[c] = w * H[c];
+            }
+            return;
+         }
+
+         if (ph == 2)
+         {
+            // residual at the own node, M^-1, RK combine, write-back, mean parts
+            const double *dw = tb, *e0 = tb + N1 * N1, *e1 = e0 + N1;
+            double xxi, xeta, yxi, yeta;
+            q1_jacobian (v, gx[a], gx[b], xxi, xeta, yxi, yeta);
+            const double det = xxi * yeta - xeta * yxi;
+            const double wq = gw[a] * gw[b] * det; // JxW at the node
+            const double *F = sF + slot * NQ * 8;
+            const double *H0 = sH + ((slot * 4 + 0) * N1 + b) * 4, *H1 = sH + ((slot * 4 + 1) * N1 + b) * 4;
+            const double *H2 = sH + ((slot * 4 + 2) * N1 + a) * 4, *H3 = sH + ((slot * 4 + 3) * N1 + a) * 4;
+            double r[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+               double sx = 0.0, sy = 0.0;
+#pragma unroll
+               for (int ap = 0; ap < N1; ++ap) sx = fma (F[(ap + N1 * b) * 8 + c], dw[ap * N1 + a], sx);
+#pragma unroll
+               for (int bp = 0; bp < N1; ++bp) sy = fma (F[(a + N1 * bp) * 8 + 4 + c], dw[bp * N1 + b], sy);
+               r[c] = gw[b] * sx + gw[a] * sy - (H0[c] * e0[a] + H1[c] * e1[a] + H2[c] * e0[b] + H3[c] * e1[b]);
+            }
+            const double W[4] = {uc[q], uc[NQ + q], uc[2 * NQ + q], uc[3 * NQ + q]};
+            if (A.gravity != 0.0) // assemble_explicit.cc:78, 108-111
+            {
+               double Gv[4];
+               if (A.ext_force)
+                  forcing_ext (W, A.ext_force[((size_t) cell * NQ + q) * 2], A.ext_force[((size_t) cell * NQ + q) * 2 + 1], Gv);
+               else
+                  forcing (W, Gv);
+#pragma unroll
+               for (int c = 0; c < 4; ++c) r[c] += A.gravity * Gv[c] * wq;
+            }
+            double vnew[4];
+            if (A.mode == MODE_RHS)
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c) vnew[c] = r[c];
+            }
+            else
+            {
+               const double dt = A.time[1];
+               const double invm = 1.0 / wq; // claw.cc:228-258 with a collocated basis: M_ii = JxW_i
+               const bool need_old = A.ark != 0.0;
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  const double un = W[c] + dt * r[c] * invm;
+                  vnew[c] = need_old ? (1.0 - A.ark) * un + A.ark * A.u_old[(size_t) cell * D + c * NQ + q] : un;
+               }
+            }
+            if (cell < A.n_keep)
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c) A.out[(size_t) cell * D + c * NQ + q] = vnew[c];
+            }
+            // compute_cell_average (claw.cc:562-597): sum_q u_q JxW_q / measure -- the node's part
+            double *part = sm + O_P + (slot * NQ + q) * 4;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) part[c] = vnew[c] * wq;
+            return;
+         }
+
+         // ph == 3: cell averages of the updated solution
+         if (A.mode == MODE_STAGE)
+            for (int c = q; c < 4; c += NQ)
+            {
+               double s = 0.0;
+               for (int k = 0; k < NQ; ++k) s += sm[O_P + (slot * NQ + k) * 4 + c];
+               A.avg_out[(size_t) cell * 4 + c] = s / q1_measure (v);
+            }
+      }
+   };
+
+   // compute_time_step_q (claw.cc:518-557) of one cell: largest eigenvalue (equation.h:98-116: |v| + c) over the 4 x 4
+   // equispaced points of QIterated(QTrapez,3); dtq[j][a] = l_a(j/3); h = diameter / sqrt(2)
+   DFLO_DEV double mapped_cell_time_step (const double *uc, const double *v, const double *dtq, int n1, double cfl, int degree)
+   {
+      const int nq = n1 * n1;
+      double lam = 0.0;
+      for (int jy = 0; jy < 4; ++jy)
+         for (int jx = 0; jx < 4; ++jx)
+         {
+            double W[4];
+            for (int c = 0; c < 4; ++c)
+            {
+               double s = 0.0;
+               for (int b = 0; b < n1; ++b)
+               {
+                  double sb = 0.0;
+                  for (int a = 0; a < n1; ++a) sb += dtq[jx * n1 + a] * uc[c * nq + a + n1 * b];
+                  s += dtq[jy * n1 + b] * sb;
+               }
+               W[c] = s;
+            }
+            const double l = sqrt (W[0] * W[0] + W[1] * W[1]) / W[RHO] + sound_speed (W);
+            lam = l > lam ? l : lam;
+         }
+      const double h = q1_diameter (v) / 1.4142135623730951;
+      return cfl * h / lam / (2.0 * degree + 1.0);
+   }
+}

@@ -53,6 +53,8 @@ namespace dflo
       std::vector<int> nbr;      // [n_local][4] local cell / -1-local bface; self for unknown neighbours
       std::vector<uint8_t> fflags;
       std::vector<double> geom;  // [n_local][4] x0 y0 hx hy
+      std::vector<double> verts; // [n_local][8] cell vertices (mapping = q1; empty otherwise)
+      std::vector<unsigned char> nbr_face; // [n_local][4] the neighbour's local number of the shared face (mapping = q1)
       std::vector<int> bf_global, bf_id; // local boundary faces (of the computed cells) -> global bface, boundary id
       std::vector<int> bf_cell, bf_face; // local cell, face
       std::vector<HaloPeer> peers;
@@ -454,9 +456,19 @@ namespace dflo
       L.nbr.resize (4 * (size_t) L.n_local);
       L.fflags.resize (4 * (size_t) L.n_local);
       L.geom.resize (4 * (size_t) L.n_local);
+      if (m.cell_vertices && m.neighbor_face)
+      {
+         L.verts.resize (8 * (size_t) L.n_local);
+         L.nbr_face.resize (4 * (size_t) L.n_local);
+      }
       for (int l = 0; l < L.n_local; ++l)
       {
          const int g = L.l2g[l];
+         if (!L.verts.empty ())
+         {
+            for (int i = 0; i < 8; ++i) L.verts[8 * (size_t) l + i] = m.cell_vertices[8 * (size_t) g + i];
+            for (int f = 0; f < 4; ++f) L.nbr_face[4 * (size_t) l + f] = m.neighbor_face[4 * (size_t) g + f];
+         }
          L.geom[4 * (size_t) l + 0] = m.cell_origin[2 * (size_t) g];
          L.geom[4 * (size_t) l + 1] = m.cell_origin[2 * (size_t) g + 1];
          L.geom[4 * (size_t) l + 2] = m.cell_size[2 * (size_t) g];

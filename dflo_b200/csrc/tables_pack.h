@@ -35,6 +35,8 @@ namespace dflo
                for (int m = 0; m < t.ns; ++m) o.push_back (t.phiface[f][q][m]);
       }
       for (int a = 0; a < n1; ++a) o.push_back (t.gw[a]);
+      if (t.basis == BASIS_QK) // read by the mapped (q1) stage kernel only; the others take exactly stage_table_size doubles
+         for (int a = 0; a < n1; ++a) o.push_back (t.gx[a]);
       return o;
    }
 

@@ -436,23 +436,37 @@ namespace
          const int id = kv.first;
          if (id < 0 || id >= 10 || o.prm.bc_kind[id] != ORACLE_BC_PERIODIC) continue;
          const std::vector<std::pair<int, int>> &partners = by_id[o.prm.periodic_pair[id]];
+         // a periodic boundary is a straight side of the domain, vertical or horizontal: match faces by the coordinate
+         // along it (GridTools::collect_periodic_faces matches by the face centres up to the offset between the sides)
+         auto end = [&] (const std::pair<int, int> &cf, int which, int d) {
+            const Cell &k = o.cells[cf.first];
+            const int v = FACE_VERT[cf.second][which];
+            return d == 0 ? k.vx[v] : k.vy[v];
+         };
+         double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+         for (auto &cf : kv.second)
+            for (int w = 0; w < 2; ++w)
+               for (int d = 0; d < 2; ++d)
+               {
+                  lo[d] = std::min (lo[d], end (cf, w, d));
+                  hi[d] = std::max (hi[d], end (cf, w, d));
+               }
+         const int d = (hi[0] - lo[0] < hi[1] - lo[1]) ? 1 : 0;
          for (auto &cf : kv.second)
          {
             const int c = cf.first, f = cf.second;
             Cell &cl = o.cells[c];
-            // tangential coordinate of the face centre
-            auto face_tc = [] (const Cell &k, int ff) {
-               const int a = FACE_VERT[ff][0], b = FACE_VERT[ff][1];
-               return (ff < 2) ? 0.5 * (k.vy[a] + k.vy[b]) : 0.5 * (k.vx[a] + k.vx[b]);
-            };
-            const double tc = face_tc (cl, f);
+            const double tc = 0.5 * (end (cf, 0, d) + end (cf, 1, d));
             int found = -1;
             for (auto &cf2 : partners)
             {
-               if (cf2.second != (f ^ 1)) continue;
-               const Cell &c2 = o.cells[cf2.first];
-               const double tc2 = face_tc (c2, cf2.second);
-               if (std::fabs (tc - tc2) < 1e-9 * (std::fabs (cl.hx) + std::fabs (cl.hy))) found = cf2.first;
+               const double tc2 = 0.5 * (end (cf2, 0, d) + end (cf2, 1, d));
+               if (std::fabs (tc - tc2) < 1e-9 * std::fabs (end (cf, 1, d) - end (cf, 0, d)))
+               {
+                  found = cf2.first;
+                  cl.nbr_face[f] = cf2.second;
+                  cl.flip[f] = (end (cf, 1, d) - end (cf, 0, d)) * (end (cf2, 1, d) - end (cf2, 0, d)) < 0.0;
+               }
             }
             if (found < 0)
             {

@@ -240,3 +240,63 @@ def test_sod_vs_exact_riemann_solution_gpu():
         u = r.run_to(SOD_T)
         errs.append(_sod_l1(u, 2, nx, ny, r.xq, r.tables))
     _check_sod(errs, "gpu")
+
+
+# ---------------------------------------------------------------------------------------------
+# mapping = q1: the same vortex on smoothly skewed quadrilaterals
+# ---------------------------------------------------------------------------------------------
+Q1_VORTEX = [(1, (16, 32, 64), 0.5, 0.25), (2, (16, 32, 64), 0.5, 0.2), (3, (16, 32, 64), 0.25, 0.1)]   # cfl of compute_time_step_q is ~2x looser
+
+
+def _skew_args(n, rotate=0):
+    return [n, n, -5, 5, -5, 5, 4, 2, 1, 3, 0.15, rotate]
+
+
+def _q1_l2(u, k, xq, jxw, T):
+    rho = u.reshape(xq.shape[0], 4, -1)[:, 2, :]
+    ex = vortex_exact(xq[..., 0], xq[..., 1], T)[..., 2]
+    return float(np.sqrt(((rho - ex) ** 2 * jxw).sum()))
+
+
+def _q1_jxw(verts, cells, gx, gw):
+    """w_a w_b det J at the Gauss nodes of every cell (bilinear map of the four vertices)."""
+    v = verts[cells]                                         # [nc][4][2]
+    xi, eta = np.meshgrid(gx, gx, indexing="xy")             # node q = a + n1 b: xi = gx[a], eta = gx[b]
+    xi, eta = xi.reshape(-1), eta.reshape(-1)
+    w = (gw[None, :] * gw[:, None]).reshape(-1)
+    d = lambda i, j, t: (v[:, i, t] - v[:, j, t])[:, None]
+    xxi = d(1, 0, 0) * (1 - eta) + d(3, 2, 0) * eta
+    xeta = d(2, 0, 0) * (1 - xi) + d(3, 1, 0) * xi
+    yxi = d(1, 0, 1) * (1 - eta) + d(3, 2, 1) * eta
+    yeta = d(2, 0, 1) * (1 - xi) + d(3, 1, 1) * xi
+    return w[None, :] * (xxi * yeta - xeta * yxi)
+
+
+@pytest.mark.parametrize("k,ns,T,cfl", Q1_VORTEX)
+def test_q1_vortex_h_convergence_oracle(k, ns, T, cfl):
+    prm = dict(basis="Qk", degree=k, flux="roe", cfl=cfl, compat="mpi", mapping="q1")
+    errs = []
+    for n in ns[:2] if k == 3 else ns:
+        mesh = abi.Mesh("rectangle_skew", _skew_args(n))
+        v, c, bl, bi = mesh.primitive()
+        r = _OracleRunner((v, c, bl, bi), PERIODIC_BOX, prm, lambda x, y: vortex_exact(x, y, 0.0))
+        u = r.run_to(T)
+        gx, gw = r.o.tables()
+        errs.append(_q1_l2(u, k, r.o.cell_qpoints(), _q1_jxw(v, c, gx, gw), T))
+    rates = [np.log2(errs[i] / errs[i + 1]) for i in range(len(errs) - 1)]
+    assert rates[-1] >= k + (0.6 if k == 3 else 0.8), (errs, rates)     # Q3 16 -> 32 is pre-asymptotic (3.7), as on Cartesian cells
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rotate", [0, 1])
+@pytest.mark.parametrize("k,ns,T,cfl", Q1_VORTEX)
+def test_q1_vortex_h_convergence_gpu(k, ns, T, cfl, rotate):
+    assert gpu_available()
+    prm = dict(basis="Qk", degree=k, flux="roe", cfl=cfl, compat="mpi", mapping="q1")
+    errs = []
+    for n in ns:
+        r = _EngineRunner(("rectangle_skew", _skew_args(n, rotate)), PERIODIC_BOX, prm, lambda x, y: vortex_exact(x, y, 0.0))
+        v, c, _, _ = r.mesh.primitive()
+        u = r.run_to(T)
+        errs.append(_q1_l2(u, k, r.xq, _q1_jxw(v, c, *r.tables), T))
+    _check_orders(errs, k, "gpu q1 Q%d rotate %d" % (k, rotate))

@@ -5,6 +5,8 @@ exists so index arithmetic, buffer rotation, limiter logic and halo lists are pr
 time is spent.  It never stands in for the CUDA library: the GPU tier calls libdflo_b200.so only."""
 import ctypes
 
+from dflo_b200 import abi
+
 import numpy as np
 import pytest
 
@@ -360,3 +362,95 @@ def test_time_step_skips_cells_without_a_valid_value():
 def test_baseline_configs_20_step_horizon(key, _, size):
     """SURVEY.md 8(d) horizons (1 RHS / 1 step / 20 steps) on the CPU emulation of the kernel code."""
     check_horizons(key, size, "emu")
+
+
+# ---------------------------------------------------------------------------------------------
+# mapping = q1 (SURVEY.md 8(f) row 2): straight-sided general quadrilaterals, Qk
+# ---------------------------------------------------------------------------------------------
+def _q1_case(backend, k, flux, rotate, bc, ic, n=8, **extra):
+    ids = (4, 2, 1, 3)
+    return Case(("rectangle_skew", [n, n, -5, 5, -5, 5, *ids, 0.15, rotate]), bc, ic, backend=backend, basis="Qk", degree=k, flux=flux,
+                cfl=0.05 if flux == "kep" else 0.3, mapping="q1", **extra)   # kep on this coarse mesh: unstable beyond a few small steps, Cartesian or not
+
+
+@pytest.mark.parametrize("rotate", [0, 1])
+@pytest.mark.parametrize("flux", ALL_FLUXES)
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4])
+def test_q1_mapping_rhs_and_steps_periodic(k, flux, rotate):
+    """MappingQ1 on smoothly skewed quadrilaterals, periodic box: right-hand side, compute_time_step_q and three
+    steps against the oracle; rotate = 1 mixes the cell orientations (neighbours on arbitrary faces, reversed lines)."""
+    c = _q1_case("emu", k, flux, rotate, PERIODIC_BOX, ic_vortex, compat="mpi")
+    _rhs_ok(c)
+    for _ in range(3):
+        _, dt_o, dt_e = c.step()
+        assert abs(dt_o - dt_e) <= 1e-12 * dt_o
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+@pytest.mark.parametrize("compat", ["src", "mpi"])
+@pytest.mark.parametrize("k,flux", [(1, "lxf"), (2, "roe"), (3, "hllc"), (2, "kfvs")])
+def test_q1_mapping_all_boundary_kinds_gravity(k, flux, compat):
+    bc = {1: "inflow", 2: "slip", 3: "pressure", 4: "farfield"}
+    c = _q1_case("emu", k, flux, 1, bc, ic_smooth, compat=compat, gravity=0.7)
+    c.set_boundary(values=(1.0, 0.2, 1.4, 8.8), wiggle=0.05)
+    _rhs_ok(c)
+    for _ in range(2):
+        c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+def test_q1_mapping_free_stream_and_cartesian_limit():
+    """A uniform state is preserved on skewed cells (metric identities of the bilinear map), and on an undistorted
+    mesh mapping = q1 reproduces mapping = cartesian (only the time-step formula differs: claw.cc:518-557 vs 484-511)."""
+    bc = {1: "outflow", 2: "outflow", 3: "outflow", 4: "outflow"}
+    uniform = lambda x, y: np.stack([0.7 + 0 * x, -0.3 + 0 * x, 1.2 + 0 * x, 3.0 + 0 * x], axis=-1)
+    c = _q1_case("emu", 3, "hllc", 1, bc, uniform)
+    r_o, r_e = c.rhs_pair()
+    assert np.abs(r_e).max() < 1e-13 and np.abs(r_o).max() < 1e-13
+    c.close()
+    ids = (4, 2, 1, 3)
+    res = []
+    for mp in ("cartesian", "q1"):
+        c = Case(("rectangle_skew", [6, 6, -5, 5, -5, 5, *ids, 0.0, 0]), PERIODIC_BOX, ic_vortex, backend="emu", basis="Qk", degree=2,
+                 flux="roe", cfl=0.5, mapping=mp, compat="mpi")
+        res.append(c.rhs_pair()[1])
+        c.close()
+    assert np.abs(res[0] - res[1]).max() <= 1e-13 * np.abs(res[0]).max()
+
+
+def test_q1_mapping_refusals():
+    """src/parameters.cc:545-549: TVB and Pk need Cartesian grids; a skewed mesh is refused under mapping = cartesian."""
+    ids = (4, 2, 1, 3)
+    skew = ("rectangle_skew", [4, 4, -5, 5, -5, 5, *ids, 0.15, 0])
+    for kw in (dict(basis="Pk", degree=1, mapping="q1"), dict(basis="Qk", degree=1, mapping="q1", limiter="TVB"),
+               dict(basis="Qk", degree=1, mapping="q1", pos_lim=True), dict(basis="Qk", degree=1, mapping="cartesian")):
+        params, pair = abi.make_params(bc=PERIODIC_BOX, flux="lxf", **kw)
+        mesh = abi.Mesh(skew[0], skew[1], lib=emu_lib())
+        flat = mesh.flatten(params, pair)
+        with pytest.raises(abi.DfloError):
+            abi.Engine(flat, params, lib=emu_lib(), prefix="dflo_emu_")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_q1_mapping_sharded_matches_single(world):
+    """mapping = q1 on a sharded context: cells by id over the ranks, one ghost layer, the mapped stage kernel reads its
+    neighbours (ghosts included) from the exchanged buffers -- bit for bit the single-rank result."""
+    bc = {1: "inflow", 2: "slip", 3: ("periodic", 1), 4: "farfield"}
+    bc = {1: ("periodic", 3), 3: ("periodic", 1), 2: "slip", 4: "farfield"}
+    ids = (4, 2, 1, 3)
+    args = (("rectangle_skew", [7, 6, -5, 5, -5, 5, *ids, 0.15, 1]), bc, ic_smooth)
+    prm = dict(basis="Qk", degree=2, flux="hllc", cfl=0.3, mapping="q1", compat="mpi")
+    one = Case(*args, **prm)
+    many = Case(*args, world=world, **prm)
+    for c in (one, many):
+        c.set_boundary(values=(1.0, 0.2, 1.4, 8.8))
+    assert np.array_equal(one.rhs_pair()[1], many.rhs_pair()[1])
+    for _ in range(2):
+        one.step()
+        many.step()
+    assert np.array_equal(one.solution(), many.solution())
+    assert many.rel_err() <= TOL_STEP_SMOOTH
+    one.close()
+    many.close()

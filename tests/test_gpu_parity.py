@@ -414,3 +414,51 @@ def test_run_loop_output_schedule_and_vtu_files(tmp_path):
     f = _read_vtu(out2 + "output/solution-0002.000.vtu")
     assert f["n_cells"] == 64 and f["point_names"][-2:] == ["Pressure", "subdomain"] and np.all(f["point"]["subdomain"] == 0)
     L.dflo_claw_destroy(h)
+
+
+# ---------------------------------------------------------------------------------------------
+# mapping = q1: the mapped stage kernel on straight-sided general quadrilaterals
+# ---------------------------------------------------------------------------------------------
+def _q1_case(k, flux, rotate, bc, ic, n=8, **extra):
+    ids = (4, 2, 1, 3)
+    return Case(("rectangle_skew", [n, n, -5, 5, -5, 5, *ids, 0.15, rotate]), bc, ic, backend="cuda", basis="Qk", degree=k, flux=flux,
+                cfl=0.05 if flux == "kep" else 0.3, mapping="q1", **extra)
+
+
+@pytest.mark.parametrize("rotate", [0, 1])
+@pytest.mark.parametrize("flux", ALL_FLUXES)
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4])
+def test_q1_mapping_rhs_and_steps_periodic(k, flux, rotate):
+    c = _q1_case(k, flux, rotate, PERIODIC_BOX, ic_vortex, compat="mpi")
+    r_o, r_e = c.rhs_pair()
+    assert np.abs(r_o - r_e).max() <= TOL_RHS * max(1.0, np.abs(r_o).max()) * np.sqrt(c.oracle.D)
+    for _ in range(3):
+        _, dt_o, dt_e = c.step()
+        assert abs(dt_o - dt_e) <= 1e-12 * dt_o
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    # whole steps on the device (graph replay, compute_time_step_q on the device) continue the same trajectory
+    o = c.oracle
+    t = c.t
+    for _ in range(2):
+        dt = o.compute_dt(t)
+        for rk in range(o.n_rk):
+            assert o.rk_stage(rk, dt)[0] == 0
+        o.commit_step()
+        t += dt
+    te, _ = c.engine.advance(2, elapsed=c.t)
+    assert abs(te - t) <= 1e-12 * t and c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+@pytest.mark.parametrize("compat", ["src", "mpi"])
+@pytest.mark.parametrize("k,flux", [(1, "lxf"), (2, "roe"), (3, "hllc"), (2, "kfvs")])
+def test_q1_mapping_all_boundary_kinds_gravity(k, flux, compat):
+    bc = {1: "inflow", 2: "slip", 3: "pressure", 4: "farfield"}
+    c = _q1_case(k, flux, 1, bc, ic_smooth, compat=compat, gravity=0.7)
+    c.set_boundary(values=(1.0, 0.2, 1.4, 8.8), wiggle=0.05)
+    r_o, r_e = c.rhs_pair()
+    assert np.abs(r_o - r_e).max() <= TOL_RHS * max(1.0, np.abs(r_o).max()) * np.sqrt(c.oracle.D)
+    for _ in range(2):
+        c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
