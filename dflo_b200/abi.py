@@ -54,6 +54,7 @@ class Params(ctypes.Structure):
         ("cfl", ctypes.c_double), ("time_step", ctypes.c_double),
         ("bc_kind", ctypes.c_int32 * MAX_BOUNDARIES),
         ("shock_indicator", ctypes.c_int32), ("mapping", ctypes.c_int32),
+        ("local_time_step", ctypes.c_int32), ("reserved1", ctypes.c_int32),
     ]
 
 
@@ -65,12 +66,13 @@ class DfloError(RuntimeError):
 
 def make_params(basis="Qk", degree=1, flux="lxf", limiter="none", char_lim=False, pos_lim=False,
                 conserve_angular_momentum=False, M=0.0, beta=1.0, gravity=0.0, cfl=0.9,
-                time_step=-1.0, bc=None, compat="src", shock_indicator="limiter", mapping="cartesian"):
+                time_step=-1.0, bc=None, compat="src", shock_indicator="limiter", mapping="cartesian", local_time_step=False):
     """bc: {boundary_id: kind} or {boundary_id: ("periodic", partner)}; default outflow
     (reference src/parameters.cc:384). Returns (Params, periodic_pair[10])."""
     p = Params()
     p.shock_indicator = INDICATOR[shock_indicator]
     p.mapping = {"cartesian": 0, "q1": 1}[mapping]
+    p.local_time_step = int(local_time_step)
     p.basis, p.degree, p.flux_type = BASIS[basis], degree, FLUX[flux]
     p.limiter_type = LIMITER[limiter]
     p.char_lim, p.pos_lim = int(char_lim), int(pos_lim)

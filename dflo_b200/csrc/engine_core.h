@@ -164,6 +164,8 @@ namespace dflo
       // mapping = q1: compute_time_step_q (claw.cc:518-557) from the solution itself
       const double *u, *verts, *dtq;
       int n1;
+      // time step type = local: the per-cell values are kept, the minimum is neither capped nor clipped
+      double *dt_cell;
    };
    struct DtKernel // phase kernel: per-cell dt, block minimum, one atomic per block
    {
@@ -188,6 +190,7 @@ namespace dflo
                // a NaN or non-positive cell value (negative density / pressure in the mean) must not poison the
                // block minimum, nor take part in the bit-pattern atomicMin below: the cell is skipped, as
                // `std::min (global_dt, dt(c))` skips a NaN in the reference (claw.cc:508)
+               if (A.dt_cell) A.dt_cell[cell] = d; // dt(c), claw.cc:506 -- used as it is by solve(), :709
                if (!(d > 0.0)) d = 1.0e20;
             }
             sm[tid] = d;
@@ -229,8 +232,11 @@ namespace dflo
             if (last) // claw.cc:468-476, as DtFinalizeKernel
             {
                double dt = acc;
+               if (!A.dt_cell)
+               {
                if (dt > 0 && A.time_step > 0) dt = std_min (dt, A.time_step);
                if (A.time[0] + dt > A.time[3]) dt = A.time[3] - A.time[0];
+               }
                A.time[1] = dt;
                A.time[2] = 1.0e20;
             }
@@ -241,6 +247,7 @@ namespace dflo
    {
       double *time;
       double time_step;
+      int local; // time step type = local: the minimum as it is (claw.cc:469: the capping block is for "global" only)
    };
    struct DtFinalizeKernel // claw.cc:468-476
    {
@@ -249,8 +256,11 @@ namespace dflo
       {
          if (j != 0) return;
          double dt = A.time[2];
+         if (!A.local)
+         {
          if (dt > 0 && A.time_step > 0) dt = std_min (dt, A.time_step);
          if (A.time[0] + dt > A.time[3]) dt = A.time[3] - A.time[0];
+         }
          A.time[1] = dt;
          A.time[2] = 1.0e20;
       }
@@ -512,6 +522,7 @@ namespace dflo
       TileDesc *d_tiles = nullptr;
       unsigned char *d_fflags = nullptr;
       double *d_ext_force = nullptr; // [n_local][n_q][2], allocated by set_external_force
+      double *d_dt_cell = nullptr; // [n_local] dt(cell) of time step type = local
       double *d_verts = nullptr, *d_dtq = nullptr; // mapping = q1: cell vertices [n_local][8], l_a(j/3) [4][n1]
       unsigned char *d_nbr_face = nullptr;
       double *d_geom = nullptr, *d_bc_g = nullptr, *d_stage_tab = nullptr, *d_lim_tab = nullptr, *d_gw = nullptr, *d_gx = nullptr;
@@ -620,6 +631,12 @@ namespace dflo
             bk.zero (U[i], nd * sizeof (double));
             bk.zero (AVG[i], (size_t) lm.n_local * 4 * sizeof (double));
          }
+         if (prm.local_time_step)
+         {
+            if (prm.cfl <= 0.0) return fail (DFLO_E_INVALID, "time step type = local needs a cfl");
+            d_dt_cell = bk.template alloc<double> (lm.n_local);
+            bk.zero (d_dt_cell, (size_t) lm.n_local * sizeof (double));
+         }
          d_time = bk.template alloc<double> (4);
          const double t0[4] = {0.0, 0.0, 1.0e20, 1.0e20};
          bk.h2d (d_time, t0, sizeof (t0));
@@ -713,7 +730,7 @@ namespace dflo
             bk.free (U[i]);
             bk.free (AVG[i]);
          }
-         void *ptrs[] = {d_verts, d_dtq, d_nbr_face, d_ext_force, rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
+         void *ptrs[] = {d_dt_cell, d_verts, d_dtq, d_nbr_face, d_ext_force, rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
                          d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_shock, d_code, d_prog_start, d_prog_start_t, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles, d_rowdesc, d_send_entries};
          for (void *p : ptrs) bk.free (p);
          for (int k = 0; k < 2; ++k)
@@ -1080,6 +1097,7 @@ namespace dflo
             m.tab = a.tab;
             m.time = a.time;
             m.ext_force = a.ext_force;
+            m.dt_cell = a.dt_cell;
             m.n_compute = owned_only ? lm.n_owned : lm.n_compute;
             m.n_keep = lm.n_owned;
             m.mode = a.mode;
@@ -1135,7 +1153,7 @@ namespace dflo
          a.bkind = d_bkind;
          a.tab = d_stage_tab;
          a.time = d_time;
-         a.dt_cell = nullptr;
+         a.dt_cell = d_dt_cell;
          a.rowdesc = d_rowdesc;
          a.n_cells_u = lm.n_local;
          a.pf_tiles = bk.stage_prefetch_tiles ();
@@ -1233,6 +1251,7 @@ namespace dflo
             DtFinalizeArgs f;
             f.time = d_time;
             f.time_step = prm.time_step;
+            f.local = 0;
             bk.template launch1d<FixedDtKernel> (1, f);
             return;
          }
@@ -1240,9 +1259,10 @@ namespace dflo
          a.avg = AVG[cur];
          a.geom = d_geom;
          a.time = d_time;
-         a.n_cells = lm.n_owned;
+         a.n_cells = d_dt_cell ? lm.n_compute : lm.n_owned; // redundantly updated ghost cells need their dt(cell) too
          a.degree = tab.k;
          a.cfl = prm.cfl;
+         a.dt_cell = d_dt_cell;
          a.done = reinterpret_cast<unsigned int *> (d_scratch + 2);
          a.nblocks = DtKernel::grid (a.n_cells);
          a.finalize = lm.peers.empty ();
@@ -1253,10 +1273,11 @@ namespace dflo
          a.n1 = tab.n1;
          bk.template launch<DtKernel> (a.nblocks, a);
          if (a.finalize) return;
-         if (bk.allreduce_min_dt (d_time + 2, true, prm.time_step)) return; // reduced over the ranks and finalised in one launch
+         if (bk.allreduce_min_dt (d_time + 2, true, prm.local_time_step ? -2.0 : prm.time_step)) return; // reduced over the ranks and finalised in one launch
          DtFinalizeArgs f;
          f.time = d_time;
          f.time_step = prm.time_step;
+         f.local = prm.local_time_step;
          bk.template launch1d<DtFinalizeKernel> (1, f);
       }
 
@@ -1310,6 +1331,7 @@ namespace dflo
          DtFinalizeArgs f;
          f.time = d_time;
          f.time_step = prm.time_step;
+         f.local = 0;
          bk.template launch1d<AdvanceTimeKernel> (1, f);
          old = cur;
       }

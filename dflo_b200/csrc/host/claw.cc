@@ -180,7 +180,8 @@ namespace dflo
          for (int b = 0; b < n1; ++b)
             for (int a = 0; a < n1; ++a)
             {
-               const double x = x0 + tab.gx[a] * hx, y = y0 + tab.gx[b] * hy;
+               double x = x0 + tab.gx[a] * hx, y = y0 + tab.gx[b] * hy;
+               if (!flat.cartesian) flat.map (cell, tab.gx[a], tab.gx[b], x, y); // mapping = q1: the mapped support point
                double w[4];
                if (use_expr)
                   for (int c = 0; c < 4; ++c) w[c] = expr_eval (code[c].data (), (int) code[c].size (), x, y, 0.0);

@@ -322,6 +322,51 @@ namespace dflo
       return pm;
    }
 
+   // examples/compression_corner/corner.geo: a channel of height 3 whose floor turns up by 9.5 degrees at x = 1: two
+   // transfinite blocks, [0,1] x [0,3] (nx1 x ny cells) and the ramp part up to x = 5 (nx2 x ny cells, vertical grid lines,
+   // uniform in y between the ramp and the ceiling) -- trapezoids, i.e. mapping = q1.  Physical Line 1 walls (floor, ramp,
+   // ceiling), 2 inflow (left), 3 outflow (right).  (the .geo counts points: n1 = 10, n2 = 30, n3 = 20 <-> 9, 29, 19 cells)
+   PrimitiveMesh make_compression_corner (int nx1, int nx2, int ny)
+   {
+      const double H = 3.0, L1 = 1.0, L2 = 4.0, tn = std::tan (9.5 * 3.14159265358979323846 / 180.0);
+      PrimitiveMesh pm;
+      const int nx = nx1 + nx2;
+      auto vid = [&] (int i, int j) { return j * (nx + 1) + i; };
+      for (int j = 0; j <= ny; ++j)
+         for (int i = 0; i <= nx; ++i)
+         {
+            const double x = i <= nx1 ? L1 * i / nx1 : L1 + L2 * (i - nx1) / nx2;
+            const double yb = i <= nx1 ? 0.0 : tn * (x - L1);
+            pm.vertices.push_back (x);
+            pm.vertices.push_back (yb + (H - yb) * j / ny);
+         }
+      for (int blk = 0; blk < 2; ++blk) // cells block by block, like gmsh writes the two surfaces
+         for (int j = 0; j < ny; ++j)
+            for (int i = blk ? nx1 : 0; i < (blk ? nx : nx1); ++i)
+            {
+               pm.cells.push_back (vid (i, j));
+               pm.cells.push_back (vid (i + 1, j));
+               pm.cells.push_back (vid (i, j + 1));
+               pm.cells.push_back (vid (i + 1, j + 1));
+            }
+      auto line = [&] (int a, int b, int id) {
+         pm.blines.push_back (a);
+         pm.blines.push_back (b);
+         pm.bline_id.push_back (id);
+      };
+      for (int i = 0; i < nx; ++i)
+      {
+         line (vid (i, 0), vid (i + 1, 0), 1);
+         line (vid (i, ny), vid (i + 1, ny), 1);
+      }
+      for (int j = 0; j < ny; ++j)
+      {
+         line (vid (0, j), vid (0, j + 1), 2);
+         line (vid (nx, j), vid (nx, j + 1), 3);
+      }
+      return pm;
+   }
+
    // examples/isentropic_vortex/grid.geo: [-5,5]^2; Physical Line 1 bottom, 2 right, 3 top, 4 left
    PrimitiveMesh make_isentropic_vortex_grid (int n)
    {

@@ -35,6 +35,23 @@ namespace dflo
       bool cartesian = true;               // every cell an axis-aligned rectangle, every neighbour across face f on its face f ^ 1
       std::string why_not_cartesian;
       dflo_flat_mesh view () const;
+      // the cell's map from the unit square (bilinear through the four vertices; on Cartesian cells origin + xi * size),
+      // and its Jacobian J = d(x,y)/d(xi,eta) as {x_xi, x_eta, y_xi, y_eta}
+      void map (int cell, double xi, double eta, double &x, double &y) const
+      {
+         const double *q = &vertices[8 * (size_t) cell];
+         const double n0 = (1.0 - xi) * (1.0 - eta), n1 = xi * (1.0 - eta), n2 = (1.0 - xi) * eta, n3 = xi * eta;
+         x = n0 * q[0] + n1 * q[2] + n2 * q[4] + n3 * q[6];
+         y = n0 * q[1] + n1 * q[3] + n2 * q[5] + n3 * q[7];
+      }
+      void jacobian (int cell, double xi, double eta, double J[4]) const
+      {
+         const double *q = &vertices[8 * (size_t) cell];
+         J[0] = (q[2] - q[0]) * (1.0 - eta) + (q[6] - q[4]) * eta;
+         J[1] = (q[4] - q[0]) * (1.0 - xi) + (q[6] - q[2]) * xi;
+         J[2] = (q[3] - q[1]) * (1.0 - eta) + (q[7] - q[5]) * eta;
+         J[3] = (q[5] - q[1]) * (1.0 - xi) + (q[7] - q[3]) * xi;
+      }
       int n_cells () const { return origin.size () / 2; }
       int n_bfaces () const { return bface_cell.size (); }
    };
@@ -52,6 +69,8 @@ namespace dflo
 
    // the same rectangle with smoothly displaced interior vertices (general quadrilaterals for mapping = q1); rotate: mixed cell orientations
    PrimitiveMesh make_skewed_rectangle (int nx, int ny, double x0, double x1, double y0, double y1, const int ids[4], double amp, int rotate);
+
+   PrimitiveMesh make_compression_corner (int nx1_cells, int nx2_cells, int ny_cells);   // examples/compression_corner/corner.geo (mapping = q1)
 
    // The four BASELINE geometries, reproducing the transfinite blocks of the reference's .geo
    // files (no gmsh in this image).  Cells are emitted block by block like gmsh does.

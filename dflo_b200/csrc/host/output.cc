@@ -2,6 +2,7 @@
 // for a discontinuous field: no vertex is shared between cells.
 #include "output.h"
 
+#include <cmath>
 #include <cstdio>
 #include <vector>
 
@@ -44,8 +45,12 @@ namespace dflo
          for (int cell = c0; cell < c1; ++cell)
             for (int j = 0; j <= nsub; ++j)
                for (int i = 0; i <= nsub; ++i)
-                  std::fprintf (fp, "%.10g %.10g 0\n", flat.origin[2 * cell] + (double) i / nsub * flat.size[2 * cell],
-                                flat.origin[2 * cell + 1] + (double) j / nsub * flat.size[2 * cell + 1]);
+               {
+                  double x = flat.origin[2 * cell] + (double) i / nsub * flat.size[2 * cell];
+                  double y = flat.origin[2 * cell + 1] + (double) j / nsub * flat.size[2 * cell + 1];
+                  if (!flat.cartesian) flat.map (cell, (double) i / nsub, (double) j / nsub, x, y); // build_patches with MappingQ1
+                  std::fprintf (fp, "%.10g %.10g 0\n", x, y);
+               }
       }
    }
 
@@ -90,8 +95,20 @@ namespace dflo
                      gx += dpx[(size_t) v * ns + m] * ur[m];
                      gy += dpy[(size_t) v * ns + m] * ur[m];
                   }
-                  gx /= flat.size[2 * (cell_begin + cell)];
-                  gy /= flat.size[2 * (cell_begin + cell) + 1];
+                  if (flat.cartesian)
+                  {
+                     gx /= flat.size[2 * (cell_begin + cell)];
+                     gy /= flat.size[2 * (cell_begin + cell) + 1];
+                  }
+                  else // J^-T times the unit-cell gradient at the patch vertex
+                  {
+                     const int nsub1 = (int) std::lround (std::sqrt ((double) npc));
+                     double J[4];
+                     flat.jacobian (cell_begin + cell, (double) (v % nsub1) / (nsub1 - 1), (double) (v / nsub1) / (nsub1 - 1), J);
+                     const double det = J[0] * J[3] - J[1] * J[2], gu = gx, gv = gy;
+                     gx = (J[3] * gu - J[2] * gv) / det;
+                     gy = (-J[1] * gu + J[0] * gv) / det;
+                  }
                   schl[(size_t) cell * npc + v] = gx * gx + gy * gy;
                }
             }
@@ -174,7 +191,11 @@ namespace dflo
          for (int cell = 0; cell < nc; ++cell)
             for (int j = 0; j < np1; ++j)
                for (int i = 0; i < np1; ++i)
-                  std::fprintf (fp, "%.10g\n", flat.origin[2 * cell + d] + (double) (d == 0 ? i : j) / nsub * flat.size[2 * cell + d]);
+               {
+                  double xy[2] = {flat.origin[2 * cell] + (double) i / nsub * flat.size[2 * cell], flat.origin[2 * cell + 1] + (double) j / nsub * flat.size[2 * cell + 1]};
+                  if (!flat.cartesian) flat.map (cell, (double) i / nsub, (double) j / nsub, xy[0], xy[1]);
+                  std::fprintf (fp, "%.10g\n", xy[d]);
+               }
          std::fprintf (fp, "\n");
       }
       for (int k = 0; k < n_arrays; ++k)
@@ -204,7 +225,7 @@ namespace dflo
       for (int d = 0; d < 2; ++d)
       {
          for (int cell = 0; cell < nc; ++cell)
-            for (int v = 0; v < 4; ++v) std::fprintf (fp, "%.10g\n", flat.origin[2 * cell + d] + (d == 0 ? v % 2 : v / 2) * flat.size[2 * cell + d]);
+            for (int v = 0; v < 4; ++v) std::fprintf (fp, "%.10g\n", flat.vertices[8 * (size_t) cell + 2 * v + d]);
          std::fprintf (fp, "\n");
       }
       for (int i = 0; i < 4 * nc; ++i) std::fprintf (fp, "%.10g\n", mu_shock ? mu_shock[i / 4] : 0.0);
@@ -239,8 +260,15 @@ namespace dflo
                   vx += tab.phi[q][m] * mx[m];
                   vy += tab.phi[q][m] * my[m];
                }
-            const double x = x0 + tab.gx[q % n1] * hx, y = y0 + tab.gx[q / n1] * hy;
-            total += (x * vy - y * vx) * (tab.gw[q % n1] * tab.gw[q / n1] * hx * hy);
+            double x = x0 + tab.gx[q % n1] * hx, y = y0 + tab.gx[q / n1] * hy, jxw = tab.gw[q % n1] * tab.gw[q / n1] * hx * hy;
+            if (!flat.cartesian) // MappingQ1: mapped point, w det J
+            {
+               double J[4];
+               flat.map (cell, tab.gx[q % n1], tab.gx[q / n1], x, y);
+               flat.jacobian (cell, tab.gx[q % n1], tab.gx[q / n1], J);
+               jxw = tab.gw[q % n1] * tab.gw[q / n1] * (J[0] * J[3] - J[1] * J[2]);
+            }
+            total += (x * vy - y * vx) * jxw;
          }
       }
       return total;

@@ -321,9 +321,9 @@ namespace dflo
             err = "mapping = q1: the positivity limiter is not supported on mapped cells by the B200 engine";
             return false;
          }
-         if (time_step_type != "global")
+         if (time_step_type == "local" && !(cfl > 0.0))
          {
-            err = "only 'time step type = global' runs on the B200 engine";
+            err = "time step type = local needs a cfl";
             return false;
          }
          if (do_refine)
@@ -351,6 +351,8 @@ namespace dflo
          p.conserve_angular_momentum = conserve_angular_momentum;
          p.compat = compat;
          p.mapping = mapping == "q1" ? DFLO_MAPPING_Q1 : DFLO_MAPPING_CARTESIAN; // claw.cc:165-190
+         p.local_time_step = time_step_type == "local"; // claw.cc:456, 469, 709
+         p.reserved1 = 0;
          p.shock_indicator = shock_indicator == "density" ? DFLO_INDICATOR_DENSITY : shock_indicator == "energy" ? DFLO_INDICATOR_ENERGY : DFLO_INDICATOR_LIMITER; // parameters.cc:229-237
          p.M = M;
          p.beta = beta;

@@ -40,6 +40,7 @@ namespace dflo
       const double *tab;            // flat Qk stage tables: dw[N1][N1] e0[N1] e1[N1] gw[N1]
       const double *time;
       const double *ext_force;      // [n_local][NQ][2] or nullptr
+      const double *dt_cell;        // time step type = local: dt(cell), else nullptr
       int n_compute, n_keep;
       int mode, compat_mpi;
       double ark, gravity;
@@ -258,7 +259,7 @@ namespace dflo
             }
             else
             {
-               const double dt = A.time[1];
+               const double dt = A.dt_cell ? A.dt_cell[cell] : A.time[1];
                const double invm = 1.0 / wq; // claw.cc:228-258 with a collocated basis: M_ii = JxW_i
                const bool need_old = A.ark != 0.0;
 #pragma unroll

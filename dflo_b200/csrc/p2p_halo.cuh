@@ -165,8 +165,11 @@ namespace dflo
          if (finalize) // claw.cc:468-476, as DtFinalizeKernel
          {
             double dt = m;
-            if (dt > 0 && time_step > 0) dt = (time_step < dt) ? time_step : dt;
-            if (time[0] + dt > time[3]) dt = time[3] - time[0];
+            if (time_step != -2.0) // -2: time step type = local, the minimum as it is
+            {
+               if (dt > 0 && time_step > 0) dt = (time_step < dt) ? time_step : dt;
+               if (time[0] + dt > time[3]) dt = time[3] - time[0];
+            }
             time[1] = dt;
             time[2] = 1.0e20;
          }

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DFLO_B200_ABI_VERSION 3
+#define DFLO_B200_ABI_VERSION 4
 #define DFLO_MAX_BOUNDARIES 10 /* Parameters::AllParameters::max_n_boundaries, src/parameters.h:370 */
 
 /* error codes */
@@ -123,6 +123,11 @@ typedef struct
    int32_t bc_kind[DFLO_MAX_BOUNDARIES];   /* DFLO_BC_* per boundary id */
    int32_t shock_indicator;            /* DFLO_INDICATOR_* ("shock indicator" in subsection limiter) */
    int32_t mapping;                    /* DFLO_MAPPING_* ("mapping"); 0 = cartesian */
+   int32_t local_time_step;            /* "time step type = local" (src/claw.cc:444-478, 694-713): every cell advances with its own
+                                          dt(cell); the clock moves by the smallest one, which is neither capped by "time step" nor
+                                          clipped at the final time.  dflo_b200_rk_stage then uses the per-cell values of the last
+                                          dflo_b200_compute_dt, its dt argument only sets the BC time */
+   int32_t reserved1;
 } dflo_params;
 
 typedef struct dflo_ctx dflo_ctx;

@@ -866,6 +866,7 @@ namespace
          o.dt[c] = o.prm.cfl / max_eigenvalue / (2.0 * o.fe.k + 1.0);
          o.global_dt = std::min (o.global_dt, o.dt[c]);
       }
+      if (o.prm.local_time_step) return o.global_dt; // claw.cc:469: what follows is for "global" only; dt(c) stays per cell
       if (o.global_dt > 0 && time_step > 0) o.global_dt = std::min (o.global_dt, time_step);
       if (elapsed + o.global_dt > final_time) o.global_dt = final_time - elapsed;
       std::fill (o.dt.begin (), o.dt.end (), o.global_dt);
@@ -1311,7 +1312,7 @@ namespace
       // solve(), rk3 branch: claw.cc:694-713
       for (size_t c = 0; c < o.cells.size (); ++c)
          for (int i = 0; i < D; ++i)
-            o.newton_update[c * D + i] = dt * o.rhs[c * D + i] * o.inv_mass[c * D + i];
+            o.newton_update[c * D + i] = (o.prm.local_time_step ? o.dt[c] : dt) * o.rhs[c * D + i] * o.inv_mass[c * D + i]; // dt(cell_no), :709
       const double a = o.ark[rk];
       for (size_t j = 0; j < o.current.size (); ++j) o.current[j] += o.newton_update[j];           // :757
       for (size_t j = 0; j < o.current.size (); ++j) o.current[j] = (1.0 - a) * o.current[j] + a * o.old[j]; // :760

@@ -39,6 +39,8 @@ typedef struct
    int shock_indicator;  /* 0 limiter (all cells, indicator.cc:18-22), 1 density, 2 energy (KXRCF, indicator.cc:50-198) */
    int mapping;          /* 0 cartesian (MappingCartesian), 1 q1 (MappingQ1: straight-sided quadrilaterals, claw.cc:165-190);
                             q1: Qk only, no TVB (parameters.cc:545-549), compute_time_step_q (claw.cc:518-557) */
+   int local_time_step;  /* "time step type = local": solve() multiplies by dt(cell) (claw.cc:709); the clock moves by the
+                            smallest dt(cell), neither capped by "time step" nor clipped at the final time (claw.cc:469-476) */
 } oracle_params;
 
 typedef struct oracle_ctx oracle_ctx;

@@ -25,7 +25,7 @@ class OracleParams(ctypes.Structure):
         ("cfl", ctypes.c_double),
         ("bc_kind", ctypes.c_int * 10), ("periodic_pair", ctypes.c_int * 10),
         ("compat", ctypes.c_int), ("n_threads", ctypes.c_int), ("shock_indicator", ctypes.c_int),
-        ("mapping", ctypes.c_int),
+        ("mapping", ctypes.c_int), ("local_time_step", ctypes.c_int),
     ]
 
 
@@ -135,7 +135,7 @@ class Physics:
 
 def make_params(basis="Qk", degree=1, flux="lxf", limiter="none", char_lim=False, pos_lim=False,
                 conserve_angular_momentum=False, M=0.0, beta=1.0, gravity=0.0, cfl=0.9,
-                bc=None, compat="src", n_threads=1, shock_indicator="limiter", mapping="cartesian"):
+                bc=None, compat="src", n_threads=1, shock_indicator="limiter", mapping="cartesian", local_time_step=False):
     """bc: {boundary_id: kind} or {boundary_id: ("periodic", partner_id)}; default outflow
     (src/parameters.cc:384)."""
     p = OracleParams()
@@ -159,6 +159,7 @@ def make_params(basis="Qk", degree=1, flux="lxf", limiter="none", char_lim=False
     p.n_threads = n_threads
     p.shock_indicator = {"limiter": 0, "density": 1, "energy": 2}[shock_indicator]
     p.mapping = {"cartesian": 0, "q1": 1}[mapping]
+    p.local_time_step = int(local_time_step)
     return p
 
 

@@ -454,3 +454,21 @@ def test_q1_mapping_sharded_matches_single(world):
     assert many.rel_err() <= TOL_STEP_SMOOTH
     one.close()
     many.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# time step type = local (src/claw.cc:444-478, 694-713)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("basis,k,flux,mapping", [("Qk", 1, "kfvs", "cartesian"), ("Qk", 3, "roe", "cartesian"), ("Pk", 2, "hllc", "cartesian"),
+                                                  ("Qk", 1, "kfvs", "q1"), ("Qk", 2, "hllc", "q1")])
+def test_local_time_stepping(basis, k, flux, mapping):
+    """Every cell advances with its own dt(cell); the clock moves by the smallest one, which is not clipped at the final
+    time.  compute_dt, the stage update and the device-side advance against the oracle."""
+    from helpers import local_time_stepping_case
+    local_time_stepping_case("emu", basis, k, flux, mapping)
+
+
+def test_local_time_stepping_compression_corner():
+    """examples/compression_corner: Q1, KFVS, mapping = q1, time step type = local on the two-block trapezoid mesh."""
+    from helpers import compression_corner_case
+    compression_corner_case("emu")

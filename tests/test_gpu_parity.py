@@ -462,3 +462,19 @@ def test_q1_mapping_all_boundary_kinds_gravity(k, flux, compat):
         c.step()
     assert c.rel_err() <= TOL_STEP_SMOOTH
     c.close()
+
+
+@pytest.mark.parametrize("basis,k,flux,mapping", [("Qk", 1, "kfvs", "cartesian"), ("Qk", 3, "roe", "cartesian"), ("Qk", 2, "hllc", "cartesian"),
+                                                  ("Pk", 2, "hllc", "cartesian"), ("Pk", 3, "lxf", "cartesian"), ("Qk", 1, "kfvs", "q1"),
+                                                  ("Qk", 2, "hllc", "q1")])
+def test_local_time_stepping(basis, k, flux, mapping):
+    """time step type = local (src/claw.cc:444-478, 694-713) through the row kernel, the Pk cell kernel, the tile kernel
+    and the mapped kernel."""
+    from helpers import local_time_stepping_case
+    local_time_stepping_case("cuda", basis, k, flux, mapping)
+
+
+def test_compression_corner_q1_local():
+    """examples/compression_corner (Q1, KFVS, mapping = q1, time step type = local) at the size of the shipped .geo."""
+    from helpers import compression_corner_case
+    compression_corner_case("cuda", size=(9, 29, 19), nsteps=20)

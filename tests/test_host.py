@@ -60,7 +60,7 @@ def test_library_exports_every_declared_symbol(lib, header):
 
 def test_abi_version_and_strerror(lib):
     lib.dflo_b200_abi_version.restype = ctypes.c_int
-    assert lib.dflo_b200_abi_version() == 3
+    assert lib.dflo_b200_abi_version() == 4   # v4: cell_vertices / neighbor_face in the flat mesh, mapping + local_time_step in the parameters
     assert lib.dflo_b200_strerror(0) == b"ok"
     assert b"Negative states" in lib.dflo_b200_strerror(abi.E_NEGATIVE_STATE)       # positivity.cc:33-37
     assert b"positivity limiter" in lib.dflo_b200_strerror(abi.E_POSLIM_ROOT)       # positivity.cc:160-169
