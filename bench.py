@@ -441,6 +441,57 @@ def config_entry(L, key, steps, warmup, flush, peak, torch):
     return e
 
 
+def q1_entry(steps, warmup, flush, peak, torch, parity_steps, threads, with_oracle):
+    """mapping = q1: the cfg2 case on 256 x 256 smoothly skewed quadrilaterals through the mapped
+    stage kernel -- throughput, roofline fraction (same 24 + 32/D bytes per DoF-update; the 64 B of vertices per cell
+    are charged nothing), and parity at the three horizons on a 128 x 128 mesh of the same kind."""
+    from dflo_b200 import abi
+    n, k = 256, 3
+    params, pair = abi.make_params(basis="Qk", degree=k, flux="roe", bc=PERIODIC, cfl=0.45, compat="mpi", mapping="q1")
+    mesh = abi.Mesh("rectangle_skew", [n, n, -5, 5, -5, 5, 4, 2, 1, 3, 0.15, 0])
+    flat = mesh.flatten(params, pair)
+    eng = abi.Engine(flat, params)
+    D = eng.D
+    n_dof = n * n * D
+    v, c, _, _ = mesh.primitive()
+    gx, _ = gauss01(k + 1)
+    xi, eta = np.meshgrid(gx, gx, indexing="xy")
+    xi, eta = xi.reshape(-1), eta.reshape(-1)
+    N = np.stack([(1 - xi) * (1 - eta), xi * (1 - eta), (1 - xi) * eta, xi * eta], axis=0)     # [4][nq]
+    X = np.einsum("cv,vq->cq", v[c][:, :, 0], N)
+    Y = np.einsum("cv,vq->cq", v[c][:, :, 1], N)
+    u0 = np.ascontiguousarray(np.transpose(isentropic_vortex(X, Y), (0, 2, 1))).reshape(-1)     # [cell][comp][node]
+    eng.set_solution(u0)
+    t = 0.0
+    for _ in range(warmup):
+        t, _ = eng.advance(1, elapsed=t)
+    l0 = eng.launch_count()
+    total = 0.0
+    for _ in range(steps):
+        if flush is not None:
+            flush.zero_()
+            torch.cuda.synchronize()
+        t, _ = eng.advance(1, elapsed=t)
+        total += eng.last_advance_ms()
+    launches = eng.launch_count() - l0
+    kms = eng.time_stage_kernel(rk=1, reps=10, flush_bytes=FLUSH_BYTES)
+    eng.poll_error()
+    eng.close()
+    bpu = 24.0 + 32.0 / D
+    ms_step = total / steps
+    e = {"config": "q1", "workload": "isentropic_vortex, Q3, 256x256 smoothly skewed quadrilaterals, mapping = q1, Roe, RK3, periodic",
+         "mesh": "rectangle_skew 256 256 (amplitude 0.15)", "cells": n * n, "dofs": n_dof, "rk_stages": eng.n_rk, "limited": False,
+         "steps": steps, "ms_per_step": ms_step, "mdof_per_s": n_dof * eng.n_rk * steps / (total * 1e-3) / 1e6,
+         "gpu_launches": int(launches), "l2": "flushed before every timed step (256 MB rewrite)",
+         "roofline": {"bound": "hbm", "scope": "whole stage, ms_per_step / rk_stages", "bytes_per_dof_update": bpu,
+                      "achieved": n_dof * bpu / (ms_step / eng.n_rk * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                      "frac": n_dof * bpu / (ms_step / eng.n_rk * 1e-3) / 1e9 / peak},
+         "stage_kernel": {"name": "MappedStageKernel<4,roe>", "ms": kms, "bytes_per_dof_update": bpu, "frac": n_dof * bpu / (kms * 1e-3) / 1e9 / peak}}
+    if with_oracle:
+        e["linf_vs_ref"], e["cpu_baseline"] = parity_leg("q1", [128, 128], parity_steps, threads)
+    return e
+
+
 def strong_entry(L, key, steps, warmup, flush, peak, torch, dist, rank, world, local_rank, new_nccl_id):
     """One BASELINE configuration at full size sharded over the N GPUs (strong scaling), the single-GPU run of the
     same deck on rank 0 beside it, and the sharded result against the single-GPU result (bit for bit: 0)."""
@@ -490,6 +541,8 @@ def main():
                     help="other BASELINE configurations measured beside the headline (N = 1), '' = none")
     ap.add_argument("--strong", default=os.environ.get("DFLO_BENCH_STRONG", "cfg4,cfg5"),
                     help="configurations sharded over the N GPUs at full size (N > 1), '' = none")
+    ap.add_argument("--next-rows", default=os.environ.get("DFLO_BENCH_NEXT", "q1"),
+                    help="SURVEY 8(f) rows measured beside the BASELINE configurations (N = 1): q1 = mapping q1 on skewed quadrilaterals")
     ap.add_argument("--config-steps", type=int, default=20)
     ap.add_argument("--parity-steps", type=int, default=20)
     args = ap.parse_args()
@@ -727,6 +780,8 @@ def main():
                 if not args.no_cpu_baseline:
                     e["linf_vs_ref"], e["cpu_baseline"] = parity_leg(key, CONFIGS[key][2], args.parity_steps, threads)
                 cfgs.append(e)
+            if "q1" in args.next_rows.split(","):
+                cfgs.append(q1_entry(args.config_steps, 5, flush, peak, torch, args.parity_steps, threads, not args.no_cpu_baseline))
             line["configs"] = cfgs
         print(json.dumps(line))
     if world > 1:

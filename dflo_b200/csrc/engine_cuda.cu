@@ -1,9 +1,11 @@
 // The product: CUDA backend of Engine<> for sm_100a and the extern "C" entry points of
 // include/dflo_b200.h.  One CUDA stream per ctx; whole time steps are captured once into a CUDA
 // graph (one per starting solution buffer) and replayed, so a step costs one graph launch and no
-// host round trip; the halo exchange of a sharded ctx is one NCCL group of send/recv pairs per
-// RK stage on the same stream.  There is no CPU fallback: without a CUDA device create() returns
-// DFLO_E_NO_DEVICE.
+// host round trip; the stage kernels of a step are programmatic dependent launches.  The halo exchange
+// of a sharded ctx goes over peer memory (p2p_halo.cuh: stores into the peers' ghost ranges over NVLink,
+// fused into the row stage kernel where no limiter follows); one NCCL group of send/recv pairs per RK
+// stage is the fallback when the peers' buffers cannot be mapped.  There is no CPU fallback: without a
+// CUDA device create() returns DFLO_E_NO_DEVICE.
 #include "abi_impl.h"
 #include "p2p_halo.cuh"
 #include "row_kernel.cuh"
@@ -319,8 +321,10 @@ namespace
          k_end ();
          note (cudaPeekAtLastError ());
       }
-      // The stage kernel.  Default: the pipelined persistent form (one producer warp streaming tiles
-      // through two shared-memory stages); DFLO_B200_PERSISTENT=0 selects the one-tile-per-block form.
+      // Stage-kernel forms: Qk runs the register-blocked row kernel (launch_row; DFLO_B200_STAGE=tile selects the generic
+      // tile kernel instead), Pk degree 1-2 the thread-per-cell kernel (cell_stage.cuh), mapping = q1 the mapped kernel.
+      // What is left for the generic tile kernel (P3, degree 0) runs in its pipelined persistent form (one producer
+      // warp streaming tiles through two shared-memory stages) unless DFLO_B200_PERSISTENT=0.
       int stage_prefetch_tiles () const
       {
          static const char *e = std::getenv ("DFLO_B200_PF_TILES");

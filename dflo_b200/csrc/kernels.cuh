@@ -1214,8 +1214,12 @@ namespace dflo
       // works on its row, changed cells are written back
       static constexpr int THREADS = D > 64 ? 64 : 128;
       static constexpr int CPB = THREADS;
-      // up to Q2 / P3 four blocks fit the shared memory of an SM: hold the compiler to 128 registers for them
-      static constexpr int MIN_BLOCKS = D <= 40 ? 4 : 1;
+      // up to Q2 / P3 four blocks fit the shared memory of an SM: hold the compiler to 128 registers for them -- except
+      // the P2 TVB + positivity chain (cfg3), which spills 528 bytes at 128 registers: three blocks, 168 registers
+#ifndef DFLO_LIM_P2_BLOCKS
+#define DFLO_LIM_P2_BLOCKS 3
+#endif
+      static constexpr int MIN_BLOCKS = (BASIS == BASIS_PK && N1 == 3 && MINMAX == 0) ? DFLO_LIM_P2_BLOCKS : D <= 40 ? 4 : 1;
       static constexpr int NPHASE = 2;
       static constexpr int ROW = D + 1;
       static constexpr int SMEM_DOUBLES = CPB * ROW;

@@ -301,6 +301,8 @@ BASELINE_CASES = {
              dict(basis="Qk", degree=2, flux="hllc", limiter="TVB", char_lim=True, beta=1.0, M=100.0, cfl=0.9), "dmr"),
     "cfg5": ("forward_step", STEP_BC, ic_step,
              dict(basis="Qk", degree=3, flux="kfvs", limiter="TVB", char_lim=True, pos_lim=True, beta=2.0, M=0.0, cfl=0.5), (4.2, 0.0, 1.4, 8.8)),
+    # not a BASELINE configuration: cfg2 on smoothly skewed quadrilaterals, mapping = q1; size = [nx, ny]
+    "q1": ("rectangle_skew", PERIODIC_BOX, ic_vortex, dict(basis="Qk", degree=3, flux="roe", cfl=0.45, compat="mpi", mapping="q1"), None),
 }
 
 
@@ -309,6 +311,8 @@ def baseline_case(key, size, backend="cuda", oracle_variant="restated", oracle_t
     states; for the double Mach reflection it feeds the oracle the moving-shock top boundary of
     examples/double_mach_reflection/input.prm:35-41 that the engine evaluates on the device from the expressions."""
     gen, bc, ic, prm, g = BASELINE_CASES[key]
+    if key == "q1":
+        size = [size[0], size[1], -5, 5, -5, 5, 4, 2, 1, 3, 0.15, 0]
     c = Case((gen, list(size)), bc, ic, backend=backend, oracle_variant=oracle_variant, oracle_threads=oracle_threads, **prm)
     bc_fn = None
     if g == "dmr":

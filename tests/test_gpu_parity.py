@@ -478,3 +478,30 @@ def test_compression_corner_q1_local():
     """examples/compression_corner (Q1, KFVS, mapping = q1, time step type = local) at the size of the shipped .geo."""
     from helpers import compression_corner_case
     compression_corner_case("cuda", size=(9, 29, 19), nsteps=20)
+
+
+def test_compression_corner_driver_run(tmp_path):
+    """The standalone front end on the q1 example deck: setup, 30 local-time steps, a VTU file whose points are the
+    MAPPED patch vertices (all inside the channel, the ramp cells above the ramp)."""
+    import ctypes
+    import os
+    from test_host import ROOT, _claw_api, _read_vtu
+    L = _claw_api(abi.load_library())
+    L.dflo_claw_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, abi.c_double_p, ctypes.POINTER(ctypes.c_int)]
+    L.dflo_claw_write_vtu.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    prm = os.path.join(ROOT, "tests", "golden", "prm_q1", "compression_corner_Q1_kfvs_q1_local.prm")
+    h = ctypes.c_void_p(L.dflo_claw_create(prm.encode(), b"compression_corner 9 29 19", None, abi.COMPAT["src"]))
+    assert h, L.dflo_host_last_error()
+    assert L.dflo_claw_setup(h, 0, 0, 1, None) == 0, L.dflo_host_last_error()
+    t, done = ctypes.c_double(0.0), ctypes.c_int(0)
+    assert L.dflo_claw_run(h, 30, 0, ctypes.byref(t), ctypes.byref(done)) == 0, L.dflo_host_last_error()
+    assert done.value == 30 and t.value > 0
+    path = str(tmp_path / "corner.vtu")
+    assert L.dflo_claw_write_vtu(h, path.encode()) == 0, L.dflo_host_last_error()
+    f = _read_vtu(path)
+    x, y = f["points"][:, 0], f["points"][:, 1]
+    ramp = np.where(x > 1.0, np.tan(np.radians(9.5)) * (x - 1.0), 0.0)
+    assert x.min() >= -1e-12 and x.max() <= 5.0 + 1e-12 and np.all(y >= ramp - 1e-9) and y.max() <= 3.0 + 1e-12
+    assert np.any(np.abs(y - ramp) < 1e-9) and np.all(f["point"]["Density"] > 0.5)
+    assert f["point"]["Density"].max() > 1.05          # the oblique shock off the ramp is forming
+    L.dflo_claw_destroy(h)

@@ -603,3 +603,49 @@ def test_initial_condition_syntax_error_is_reported(lib, tmp_path):
         L.dflo_claw_destroy(h)
     else:
         assert L.dflo_host_last_error()
+
+
+def test_compression_corner_deck_q1_local(lib):
+    """The q1 example deck (examples/compression_corner/input.prm rewritten): mapping = q1 and time step type = local
+    reach the engine parameters; the mesh is general quadrilaterals; the host-side initial condition is evaluated at the
+    MAPPED support points."""
+    L = _claw_api(lib)
+    prm = os.path.join(ROOT, "tests", "golden", "prm_q1", "compression_corner_Q1_kfvs_q1_local.prm")
+    h = L.dflo_claw_create(prm.encode(), b"compression_corner 9 29 19", None, abi.COMPAT["src"])
+    assert h, L.dflo_host_last_error()
+    p = L.dflo_claw_params(h).contents
+    assert (p.basis, p.degree, p.flux_type, p.mapping, p.local_time_step, p.limiter_type) == (0, 1, abi.FLUX["kfvs"], 1, 1, 0)
+    assert p.bc_kind[1] == abi.BC["slip"] and p.bc_kind[2] == abi.BC["inflow"] and p.bc_kind[3] == abi.BC["outflow"]
+    m = abi.Mesh(handle=L.dflo_claw_mesh(h), owned=False, lib=lib)
+    assert m.n_cells == (9 + 29) * 19
+    L.dflo_claw_destroy(h)
+    # an initial condition that depends on x: the value at a support point of the last ramp cell is the value at its mapped position
+    over = b"subsection initial condition\n set w_2 value = 1.0 + x + 10*y\nend\n"
+    h = L.dflo_claw_create(prm.encode(), b"compression_corner 2 3 2", over, abi.COMPAT["src"])
+    assert h, L.dflo_host_last_error()
+    n = L.dflo_claw_n_dofs(h)
+    u = np.zeros(n)
+    assert L.dflo_claw_initial_condition(h, u.ctypes.data_as(abi.c_double_p), n) == 0
+    mesh = abi.Mesh(handle=L.dflo_claw_mesh(h), owned=False, lib=lib)
+    v, c, _, _ = mesh.primitive()
+    g = 0.5 - 0.5 / np.sqrt(3.0)                     # first Gauss node of QGauss(2)
+    last = v[c[-1]]                                   # [4][2] vertices of the last cell
+    N = np.array([(1 - g) * (1 - g), g * (1 - g), (1 - g) * g, g * g])
+    x, y = N @ last[:, 0], N @ last[:, 1]
+    assert abs(u.reshape(-1, 4, 4)[-1, 2, 0] - (1.0 + x + 10 * y)) < 1e-13
+    assert abs(y - (last[0, 1] + g * (last[2, 1] - last[0, 1]))) > 1e-3   # ... which is not where a rectangle would put it
+    L.dflo_claw_destroy(h)
+
+
+def test_dealii_adapter_compiles_and_flattens(tmp_path):
+    """adapters/dealii_flatten.h against adapters/dealii_mock (a MOCK of the deal.II calls it makes): compiled with g++,
+    the flat mesh equals the library's own flattening of the same rectangle, boundary expressions are captured from the
+    ParameterHandler; without a GPU the library must refuse to create a context (no CPU fallback)."""
+    import subprocess
+    exe = str(tmp_path / "test_adapter")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "adapters"),
+                    "-I" + os.path.join(ROOT, "adapters", "dealii_mock"), os.path.join(ROOT, "adapters", "test_adapter.cc"),
+                    "-L" + os.path.join(ROOT, "dflo_b200", "csrc"), "-ldflo_b200", "-Wl,-rpath," + os.path.join(ROOT, "dflo_b200", "csrc"),
+                    "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "all checks passed" in out.stdout, out.stdout + out.stderr
