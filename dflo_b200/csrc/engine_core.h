@@ -172,21 +172,45 @@ namespace dflo
       typedef DtArgs Args;
       static constexpr int THREADS = 256;
       static constexpr int MIN_BLOCKS = 1;
-      static constexpr int NPHASE = 3;
-      static constexpr int SMEM_DOUBLES = THREADS;
-      static int grid (int n) { return (n + THREADS - 1) / THREADS; }
+      static constexpr int NPHASE = 4;
+      static constexpr int SMEM_DOUBLES = 2 * THREADS;
+      // mapping = cartesian: a thread per cell.  mapping = q1 (compute_time_step_q): a thread per (cell, point) of the 4 x 4
+      // equispaced points, 16 cells per block.
+      static constexpr int QCELLS = THREADS / 16;
+      static int grid (int n, bool mapped = false) { return mapped ? (n + QCELLS - 1) / QCELLS : (n + THREADS - 1) / THREADS; }
       static DFLO_DEV void phase (int p, const Args &A, double *sm, int tid, int bid)
       {
-         const int cell = bid * THREADS + tid;
+         const bool mapped = A.verts != nullptr;
+         const int cell = mapped ? bid * QCELLS + tid / 16 : bid * THREADS + tid;
          if (p == 0)
          {
             double d = 1.0e20;
-            if (cell < A.n_cells)
+            if (mapped)
             {
-               if (A.verts)
-                  d = mapped_cell_time_step (A.u + (size_t) cell * 4 * A.n1 * A.n1, A.verts + (size_t) cell * 8, A.dtq, A.n1, A.cfl, A.degree);
-               else
-                  d = cell_time_step (A.avg + (size_t) cell * 4, A.geom + (size_t) cell * 4, A.cfl, A.degree);
+               // |v| + c (equation.h:98-116) at point (jx, jy) = tid % 16 of QIterated(QTrapez,3); dtq[j][a] = l_a(j/3)
+               d = 0.0;
+               if (cell < A.n_cells)
+               {
+                  const int n1 = A.n1, nq = n1 * n1, jx = tid & 3, jy = (tid >> 2) & 3;
+                  const double *uc = A.u + (size_t) cell * 4 * nq;
+                  double W[4];
+                  for (int c = 0; c < 4; ++c)
+                  {
+                     double s = 0.0;
+                     for (int b = 0; b < n1; ++b)
+                     {
+                        double sb = 0.0;
+                        for (int a = 0; a < n1; ++a) sb += A.dtq[jx * n1 + a] * uc[c * nq + a + n1 * b];
+                        s += A.dtq[jy * n1 + b] * sb;
+                     }
+                     W[c] = s;
+                  }
+                  d = sqrt (W[0] * W[0] + W[1] * W[1]) / W[RHO] + sound_speed (W);
+               }
+            }
+            else if (cell < A.n_cells)
+            {
+               d = cell_time_step (A.avg + (size_t) cell * 4, A.geom + (size_t) cell * 4, A.cfl, A.degree);
                // a NaN or non-positive cell value (negative density / pressure in the mean) must not poison the
                // block minimum, nor take part in the bit-pattern atomicMin below: the cell is skipped, as
                // `std::min (global_dt, dt(c))` skips a NaN in the reference (claw.cc:508)
@@ -197,11 +221,30 @@ namespace dflo
          }
          else if (p == 1)
          {
+            // mapping = q1: largest eigenvalue of the cell's 16 points -> dt(c) = cfl h / lambda / (2k+1), h = diameter / sqrt(2)
+            if (mapped)
+            {
+               double d = 1.0e20;
+               const int c = bid * QCELLS + tid;
+               if (tid < QCELLS && c < A.n_cells)
+               {
+                  double lam = 0.0;
+                  for (int i = 0; i < 16; ++i) lam = std_max (lam, sm[tid * 16 + i]); // std::max skips a NaN like the reference's loop
+                  d = A.cfl * (q1_diameter (A.verts + (size_t) c * 8) / 1.4142135623730951) / lam / (2.0 * A.degree + 1.0);
+                  if (A.dt_cell) A.dt_cell[c] = d;
+                  if (!(d > 0.0)) d = 1.0e20;
+               }
+               sm[THREADS + tid] = d;
+            }
+         }
+         else if (p == 2)
+         {
+            const double *v = sm + (mapped ? THREADS : 0);
             if (tid < 16)
             {
-               double m = sm[tid];
-               for (int i = tid + 16; i < THREADS; i += 16) m = std_min (m, sm[i]);
-               sm[tid] = m;
+               double m = v[tid];
+               for (int i = tid + 16; i < THREADS; i += 16) m = std_min (m, v[i]);
+               sm[tid] = m; // mapped: sm[0..15] (the first cell's point values) are dead by now
             }
          }
          else if (tid == 0)
@@ -551,6 +594,9 @@ namespace dflo
       // the register-blocked Qk kernel serves mapping = cartesian on the device
       bool row_kernel () { return !mapped () && bk.use_row_kernel (tab.basis, tab.n1); }
       bool fused_halo () { return !lm.peers.empty () && !tvb () && !pos () && row_kernel () && bk.p2p_fused_ok (); }
+      // the exchange follows the limiter as a kernel of its own, and every reader of ghost cells inside a step is a row
+      // stage kernel: the exchange does not wait for the peers, the ghost-reading tiles of the next stage kernel do
+      bool deferred_halo () { return !lm.peers.empty () && (tvb () || pos ()) && !kxrcf () && row_kernel () && bk.p2p_deferred_ok (); }
       int D () const { return tab.D; }
       // a slope limiter that reads the neighbours' new means runs after the stage kernel: TVB, or the
       // minmax limiter of the MPI tree (src_mpi/limiter.cc:36-70)
@@ -615,7 +661,9 @@ namespace dflo
          // generic phase kernel
          const bool row = row_kernel ();
          const int tx = row ? row_tx (tab.n1) : tile_nx (tab.n1), ty = row ? row_ty (tab.n1) : tile_ny (tab.n1);
-         if (!build_local_mesh (mesh, rank, world, layers, tx, ty, lm, e, row)) return fail (DFLO_E_INVALID, e);
+         // tiles on the partition cut come first (their cells travel while the interior is worked on); last only in the
+         // deferred-wait experiment, where they are the ones that wait for the peers
+         if (!build_local_mesh (mesh, rank, world, layers, tx, ty, lm, e, row, !((tvb () || pos ()) && BK::p2p_defer_requested ()))) return fail (DFLO_E_INVALID, e);
          // the 1-D kernels (layout, pack, cell averages) index DoFs with 32-bit ints
          if ((int64_t) lm.n_local * D () > (int64_t) 0x7fffffff)
             return fail (DFLO_E_UNSUPPORTED, "more than 2^31-1 DoFs on one rank: shard the mesh over more GPUs");
@@ -928,6 +976,7 @@ namespace dflo
          bk.h2d (d_time, td, sizeof (td));
          eval_boundary (false);
          enqueue_stage (rk);
+         if (deferred_halo ()) bk.p2p_drain (); // stage-by-stage use: the exchange is complete when the call returns
          return bk.check (error);
       }
 
@@ -987,6 +1036,7 @@ namespace dflo
             }
          }
          bk.timer_stop ();
+         if (deferred_halo ()) bk.p2p_drain (); // the last exchange of the last step: nothing in flight when the call returns
          bk.sync ();
          double t[2];
          bk.d2h (t, d_time, sizeof (t));
@@ -1160,7 +1210,7 @@ namespace dflo
          a.dbg = bk.debug_flags ();
          a.pdl = 0;
          a.n_tiles_owned = lm.n_tiles_owned;
-         a.fx = nullptr;
+         a.fx = deferred_halo () ? bk.p2p_wait_args () : nullptr;
          a.mode = mode;
          a.compat_mpi = prm.compat == DFLO_COMPAT_MPI;
          a.ark = ark[rk];
@@ -1264,7 +1314,7 @@ namespace dflo
          a.cfl = prm.cfl;
          a.dt_cell = d_dt_cell;
          a.done = reinterpret_cast<unsigned int *> (d_scratch + 2);
-         a.nblocks = DtKernel::grid (a.n_cells);
+         a.nblocks = DtKernel::grid (a.n_cells, mapped ());
          a.finalize = lm.peers.empty ();
          a.time_step = prm.time_step;
          a.u = U[cur];
@@ -1303,7 +1353,7 @@ namespace dflo
             launch_limiter (bk, tab.basis, tab.n1, l);
          }
          cur = out;
-         if (!fused) exchange_halo (cur);
+         if (!fused) exchange_halo (cur, !deferred_halo ());
       }
 
       void enqueue_step ()
@@ -1336,10 +1386,10 @@ namespace dflo
          old = cur;
       }
 
-      void exchange_halo (int buf)
+      void exchange_halo (int buf, bool wait = true)
       {
          if (lm.peers.empty ()) return;
-         if (bk.p2p_exchange (buf)) return;
+         if (bk.p2p_exchange (buf, wait)) return;
          for (size_t p = 0; p < lm.peers.size (); ++p)
             for (int k = 0; k < 2; ++k)
             {

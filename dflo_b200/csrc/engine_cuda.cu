@@ -85,7 +85,11 @@ namespace
    __global__ void __launch_bounds__ (K::THREADS, K::MIN_BLOCKS) phase_kernel (const typename K::Args a)
    {
       extern __shared__ __align__ (16) double dflo_smem[];
-      dflo::pdl_launch_dependents (); // no-op unless the next launch on the stream asks for programmatic serialization
+      // Programmatic dependent launch (no-ops in an ordinary launch): wait for the predecessor on the stream, THEN let the
+      // successor be scheduled -- a kernel that is allowed to read its inputs before its own wait (the first row stage
+      // kernel of a step) may rely on everything before its predecessor being complete.
+      dflo::pdl_wait ();
+      dflo::pdl_launch_dependents ();
 #pragma unroll
       for (int p = 0; p < K::NPHASE; ++p)
       {
@@ -97,6 +101,8 @@ namespace
    template <class K>
    __global__ void __launch_bounds__ (256) thread_kernel (const typename K::Args a, int n)
    {
+      dflo::pdl_wait (); // see phase_kernel
+      dflo::pdl_launch_dependents ();
       const int j = blockIdx.x * 256 + threadIdx.x;
       if (j < n) K::thread (a, j);
    }
@@ -137,6 +143,16 @@ namespace
       unsigned int *p2p_send_counters = nullptr;
       bool p2p_fused_ok () const { return p2p && p2p_fused; }
       const dflo::P2PFused *p2p_fused_args (int buf) const { return p2p_fused_dev + buf; }
+      // stand-alone exchange whose wait is left to the ghost-reading tiles of the next row stage kernel: an experiment
+      // (DFLO_B200_P2P_DEFER=1), off by default -- bit for bit and hang-free at 2 and 8 GPUs but no faster (cfg4 on 8 GPUs:
+      // 307 k against 313 k MDoF/s): what the strong-scaling runs lose is not the wait
+      static bool p2p_defer_requested ()
+      {
+         static const char *e = std::getenv ("DFLO_B200_P2P_DEFER");
+         return e && std::atoi (e) != 0;
+      }
+      bool p2p_deferred_ok () const { return p2p && p2p_defer_requested (); }
+      const dflo::P2PFused *p2p_wait_args () const { return p2p_fused_dev + 3; } // no senders: the row kernel only waits
 
       // developer timeline (DFLO_B200_KTRACE=1): every launch bracketed by events on the ctx stream, steps run eagerly;
       // per-kernel averages are printed when the ctx closes.  Off by default: nothing is recorded.
@@ -306,6 +322,23 @@ namespace
          return DFLO_OK;
       }
 
+      // launch configuration with the programmatic-serialization attribute when every kernel of a step is chained that way
+      // (DFLO_B200_PDL >= 3): the next kernel's blocks are scheduled while the last blocks of this one drain
+      template <class... Params, class... Args>
+      void launch_cfg (void (*kernel) (Params...), dim3 grid, dim3 block, size_t smem, Args... args)
+      {
+         cudaLaunchConfig_t cfg = {};
+         cfg.gridDim = grid;
+         cfg.blockDim = block;
+         cfg.dynamicSmemBytes = smem;
+         cfg.stream = stream;
+         cudaLaunchAttribute at[1];
+         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+         at[0].val.programmaticStreamSerializationAllowed = 1;
+         cfg.attrs = at;
+         cfg.numAttrs = pdl_level () >= 3 ? 1 : 0;
+         note (cudaLaunchKernelEx (&cfg, kernel, args...));
+      }
       template <class K> void launch (int grid, const typename K::Args &a)
       {
          if (grid <= 0) return;
@@ -317,7 +350,7 @@ namespace
          }
          ++launches;
          k_begin (typeid (K).name ());
-         phase_kernel<K><<<grid, K::THREADS, smem, stream>>> (a);
+         launch_cfg (phase_kernel<K>, dim3 (grid), dim3 (K::THREADS), smem, a);
          k_end ();
          note (cudaPeekAtLastError ());
       }
@@ -340,12 +373,12 @@ namespace
          static const char *e = std::getenv ("DFLO_B200_DBG");
          return e ? std::atoi (e) : 0;
       }
-      // programmatic dependent launch of the stage kernels (DFLO_B200_PDL: 0 off, 1 first stage beside the time-step
-      // kernels, 2 also stage after stage); off while tracing (the event pairs would serialise it anyway)
+      // programmatic dependent launch (DFLO_B200_PDL: 0 off, 1 first stage kernel beside the time-step kernels, 2 also
+      // stage after stage, 3 every kernel of the ctx chained that way); off while tracing (the event pairs serialise anyway)
       int pdl_level () const
       {
          static const char *e = std::getenv ("DFLO_B200_PDL");
-         return ktrace ? 0 : e ? std::atoi (e) : 2;
+         return ktrace ? 0 : e ? std::atoi (e) : 2; // 3 measured no faster (cfg3 6 % slower): profiles/r02_pdl_levels.md
       }
       bool keep_graphs_sharded () const
       {
@@ -445,7 +478,7 @@ namespace
          if (n <= 0) return;
          ++launches;
          k_begin (typeid (K).name ());
-         thread_kernel<K><<<(n + 255) / 256, 256, 0, stream>>> (a, n);
+         launch_cfg (thread_kernel<K>, dim3 ((n + 255) / 256), dim3 (256), 0, a, n);
          k_end ();
          note (cudaPeekAtLastError ());
       }
@@ -663,15 +696,15 @@ namespace
          // fused form: one descriptor per output buffer
          p2p_send_counters = alloc<unsigned int> (2);
          zero (p2p_send_counters, 2 * sizeof (unsigned int));
-         p2p_fused_dev = alloc<dflo::P2PFused> (3);
-         for (int b = 0; b < 3; ++b)
+         p2p_fused_dev = alloc<dflo::P2PFused> (4);
+         for (int b = 0; b < 4; ++b)
          {
             dflo::P2PFused f;
             std::memset (&f, 0, sizeof (f));
             for (int q = 0; q < np; ++q)
             {
-               f.dstU[q] = p2p_peerU[q][b];
-               f.dstA[q] = p2p_peerA[q][b];
+               f.dstU[q] = p2p_peerU[q][b < 3 ? b : 0];
+               f.dstA[q] = p2p_peerA[q][b < 3 ? b : 0];
                f.peer_flags[q] = p2p_args.peer_flags[q];
                f.peer_rank[q] = p2p_args.peer_rank[q];
             }
@@ -680,7 +713,7 @@ namespace
             f.send_counter = p2p_send_counters;
             f.block_counter = p2p_send_counters + 1;
             f.send_entries = d_send_entries;
-            f.n_send_tiles = n_send_tiles;
+            f.n_send_tiles = b < 3 ? n_send_tiles : 0; // [3]: wait-only
             f.npeers = np;
             f.me = rank;
             f.world = W;
@@ -732,10 +765,11 @@ namespace
          p2p = false;
       }
       // one stage's exchange of buffer `buf`: push to the peers, then wait for theirs
-      bool p2p_exchange (int buf)
+      bool p2p_exchange (int buf, bool wait = true)
       {
          if (!p2p) return false;
          dflo::P2PArgs a = p2p_args;
+         a.wait = wait ? 1 : 0;
          a.srcU = p2p_U[buf];
          a.srcA = p2p_A[buf];
          for (int p = 0; p < a.npeers; ++p)
@@ -748,10 +782,18 @@ namespace
          if (dbg & 4) return true;
          if (dbg & 1) a.nseg = 0;
          k_begin ("halo_push_kernel");
-         dflo::halo_push_kernel<<<p2p_grid, 256, 0, stream>>> (a);
+         launch_cfg (dflo::halo_push_kernel, dim3 (p2p_grid), dim3 (256), 0, a);
          k_end ();
          note (cudaPeekAtLastError ());
          return true;
+      }
+      // after exchanges whose wait was deferred: nothing of the peers' last exchange is still in flight when this returns
+      void p2p_drain ()
+      {
+         if (!p2p) return;
+         ++launches;
+         dflo::halo_wait_kernel<<<1, 32, 0, stream>>> (p2p_args);
+         note (cudaPeekAtLastError ());
       }
       void allreduce_sum (double *p, int n)
       {

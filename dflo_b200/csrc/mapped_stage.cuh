@@ -291,32 +291,4 @@ namespace dflo
             }
       }
    };
-
-   // compute_time_step_q (claw.cc:518-557) of one cell: largest eigenvalue (equation.h:98-116: |v| + c) over the 4 x 4
-   // equispaced points of QIterated(QTrapez,3); dtq[j][a] = l_a(j/3); h = diameter / sqrt(2)
-   DFLO_DEV double mapped_cell_time_step (const double *uc, const double *v, const double *dtq, int n1, double cfl, int degree)
-   {
-      const int nq = n1 * n1;
-      double lam = 0.0;
-      for (int jy = 0; jy < 4; ++jy)
-         for (int jx = 0; jx < 4; ++jx)
-         {
-            double W[4];
-            for (int c = 0; c < 4; ++c)
-            {
-               double s = 0.0;
-               for (int b = 0; b < n1; ++b)
-               {
-                  double sb = 0.0;
-                  for (int a = 0; a < n1; ++a) sb += dtq[jx * n1 + a] * uc[c * nq + a + n1 * b];
-                  s += dtq[jy * n1 + b] * sb;
-               }
-               W[c] = s;
-            }
-            const double l = sqrt (W[0] * W[0] + W[1] * W[1]) / W[RHO] + sound_speed (W);
-            lam = l > lam ? l : lam;
-         }
-      const double h = q1_diameter (v) / 1.4142135623730951;
-      return cfl * h / lam / (2.0 * degree + 1.0);
-   }
 }

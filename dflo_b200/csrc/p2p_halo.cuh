@@ -50,6 +50,7 @@ namespace dflo
       double *dt_val;
       unsigned long long *trace; // optional timeline (DFLO_B200_P2P_TRACE): 4 globaltimer stamps per exchange
       int nseg, npeers, me, world, D;
+      int wait;                  // 1: the kernel does not end before the peers' data of this exchange is here; 0: the readers wait
    };
    // What the fused (stage-kernel) form of the exchange needs, resident in device memory, one
    // instance per output buffer: tiles whose halo holds ghost cells wait for the peers' previous
@@ -86,6 +87,9 @@ namespace dflo
 
    __global__ void __launch_bounds__ (256) halo_push_kernel (const P2PArgs a)
    {
+      // programmatic dependent launch: wait for the kernel that wrote what is sent, then let the successor be scheduled
+      asm volatile ("griddepcontrol.wait;" ::: "memory");
+      asm volatile ("griddepcontrol.launch_dependents;" ::: "memory");
       __shared__ unsigned long long s_epoch;
       if (threadIdx.x == 0)
       {
@@ -121,12 +125,23 @@ namespace dflo
             for (int p = 0; p < a.npeers; ++p) st_release_sys (a.peer_flags[p] + a.world + a.me, s_epoch); // data has landed
             a.epochs[0] = s_epoch + 1;
             if (a.trace && s_epoch < 4096) a.trace[4 * s_epoch + 2] = global_ns ();
-            // ... and the kernel does not end before the peers' data is here
-            for (int p = 0; p < a.npeers; ++p)
-               while (ld_acquire_sys (a.my_flags + a.world + a.peer_rank[p]) < s_epoch) {}
+            // ... and the kernel does not end before the peers' data is here -- unless the readers of the ghost cells wait
+            // themselves (row stage kernel: its ghost-reading tiles, last in the tile order, check the flags)
+            if (a.wait)
+               for (int p = 0; p < a.npeers; ++p)
+                  while (ld_acquire_sys (a.my_flags + a.world + a.peer_rank[p]) < s_epoch) {}
             if (a.trace && s_epoch < 4096) a.trace[4 * s_epoch + 3] = global_ns ();
          }
       }
+   }
+
+   // the wait alone: everything the peers published up to the last exchange of this rank has landed
+   __global__ void halo_wait_kernel (const P2PArgs a)
+   {
+      if (threadIdx.x != 0) return;
+      const unsigned long long e = *reinterpret_cast<volatile unsigned long long *> (a.epochs) - 1;
+      for (int p = 0; p < a.npeers; ++p)
+         while (ld_acquire_sys (a.my_flags + a.world + a.peer_rank[p]) < e) {}
    }
 
    // global minimum of *dt_val over the ranks (compute_time_step, reference src_mpi/claw.cc:579),

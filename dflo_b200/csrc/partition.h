@@ -202,7 +202,9 @@ namespace dflo
    // Sharded contexts: tiles that touch the partition cut (they own cells a peer needs and read
    // ghost cells) come first in the tile order, so their results travel to the peers while the
    // interior tiles are still being worked on.
-   inline void boundary_tiles_first (const dflo_flat_mesh &m, int b, int e, std::vector<int> &order, std::vector<int> &tile_start)
+   // first = false puts them LAST instead: when the exchange is a kernel of its own whose wait is left to the tiles
+   // that read ghost cells, those tiles should come up when the peers' data has long arrived.
+   inline void boundary_tiles_first (const dflo_flat_mesh &m, int b, int e, std::vector<int> &order, std::vector<int> &tile_start, bool first = true)
    {
       const int nt = (int) tile_start.size () - 1;
       std::vector<char> cut (nt, 0);
@@ -214,9 +216,9 @@ namespace dflo
                if (nb >= 0 && (nb < b || nb >= e)) cut[t] = 1;
             }
       std::vector<int> o2, ts (1, 0);
-      for (int pass = 1; pass >= 0; --pass)
+      for (int k = 0; k < 2; ++k)
          for (int t = 0; t < nt; ++t)
-            if (cut[t] == pass)
+            if (cut[t] == (first ? 1 - k : k))
             {
                o2.insert (o2.end (), order.begin () + tile_start[t], order.begin () + tile_start[t + 1]);
                ts.push_back ((int) o2.size ());
@@ -407,7 +409,7 @@ namespace dflo
    }
 
    inline bool build_local_mesh (const dflo_flat_mesh &m, int rank, int world, int layers, int tile_x, int tile_y,
-                                 LocalMesh &L, std::string &err, bool row = false)
+                                 LocalMesh &L, std::string &err, bool row = false, bool boundary_first = true)
    {
       if (world < 1 || rank < 0 || rank >= world || m.n_cells < world)
       {
@@ -432,7 +434,7 @@ namespace dflo
       L.tile_halo_max = 2 * (tile_x + tile_y);
       std::vector<int> order;
       order_owned_cells (m, L.begin, L.end, tile_x, tile_y, order, L.tile_start);
-      if (world > 1) boundary_tiles_first (m, L.begin, L.end, order, L.tile_start);
+      if (world > 1) boundary_tiles_first (m, L.begin, L.end, order, L.tile_start, boundary_first);
       L.n_tiles_owned = (int) L.tile_start.size () - 1;
       std::vector<int> owned_g2l (L.n_owned);
       for (int i = 0; i < L.n_owned; ++i)

@@ -698,7 +698,7 @@ namespace dflo
       // ================= fused halo exchange over peer memory (p2p_halo.cuh) =================
       // Only the tiles that own cells a peer needs do anything here (the descriptor copy in shared memory says so):
       // the other blocks retire without touching global memory again.
-      if (A.fx && A.mode == MODE_STAGE && sdesc[7] > 0)
+      if (A.fx && A.mode == MODE_STAGE && sdesc[7] > 0 && A.fx->n_send_tiles > 0) // n_send_tiles == 0: wait-only descriptor (the exchange is a kernel of its own)
       {
          const P2PFused &F = *A.fx;
          const int n_send = sdesc[7];

@@ -82,7 +82,11 @@ namespace
       bool p2p_fused_ok () const { return false; }
       const dflo::P2PFused *p2p_fused_args (int) const { return nullptr; }
       void p2p_teardown () {}
-      bool p2p_exchange (int) { return false; }
+      bool p2p_exchange (int, bool = true) { return false; }
+      bool p2p_deferred_ok () const { return false; }
+      static bool p2p_defer_requested () { return false; }
+      const dflo::P2PFused *p2p_wait_args () const { return nullptr; }
+      void p2p_drain () {}
       template <class K> void launch1d (int n, const typename K::Args &a)
       {
          ++launches;
