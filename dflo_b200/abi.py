@@ -39,6 +39,7 @@ class FlatMesh(ctypes.Structure):
         ("n_boundary_faces", ctypes.c_int32),
         ("bface_cell", c_int_p), ("bface_face", c_int_p), ("bface_id", c_int_p),
         ("cell_vertices", c_double_p), ("neighbor_face", c_u8_p),
+        ("n_hanging_faces", ctypes.c_int32), ("hanging", c_int_p),
     ]
 
 

@@ -565,6 +565,7 @@ namespace dflo
       TileDesc *d_tiles = nullptr;
       unsigned char *d_fflags = nullptr;
       double *d_ext_force = nullptr; // [n_local][n_q][2], allocated by set_external_force
+      int *d_hang_of = nullptr, *d_hang = nullptr; // faces with hanging nodes (LocalMesh::hang_of, hang)
       double *d_dt_cell = nullptr; // [n_local] dt(cell) of time step type = local
       double *d_verts = nullptr, *d_dtq = nullptr; // mapping = q1: cell vertices [n_local][8], l_a(j/3) [4][n1]
       unsigned char *d_nbr_face = nullptr;
@@ -591,8 +592,11 @@ namespace dflo
       // halo exchange fused into the stage kernel: row kernel, peer memory mapped, nothing between
       // the stage kernel and the exchange (no limiter)
       bool mapped () const { return prm.mapping == DFLO_MAPPING_Q1; }
+      // meshes with hanging nodes run through the mapped stage kernel whatever the mapping (it is the one that knows sub-faces)
+      bool hanging = false;
+      bool general_kernel () const { return mapped () || hanging; }
       // the register-blocked Qk kernel serves mapping = cartesian on the device
-      bool row_kernel () { return !mapped () && bk.use_row_kernel (tab.basis, tab.n1); }
+      bool row_kernel () { return !general_kernel () && bk.use_row_kernel (tab.basis, tab.n1); }
       bool fused_halo () { return !lm.peers.empty () && !tvb () && !pos () && row_kernel () && bk.p2p_fused_ok (); }
       // the exchange follows the limiter as a kernel of its own, and every reader of ghost cells inside a step is a row
       // stage kernel: the exchange does not wait for the peers, the ghost-reading tiles of the next stage kernel do
@@ -616,6 +620,16 @@ namespace dflo
             return fail (DFLO_E_UNSUPPORTED, "minmax limiter is implemented only for Qk");
          if (mesh.n_cells <= 0) return fail (DFLO_E_INVALID, "empty mesh");
          if (p.mapping != DFLO_MAPPING_CARTESIAN && p.mapping != DFLO_MAPPING_Q1) return fail (DFLO_E_UNSUPPORTED, "mapping: cartesian or q1");
+         hanging = mesh.n_hanging_faces > 0;
+         if (hanging)
+         {
+            // the limiters' neighbour lists are same-level (claw.cc:336-380 asserts level or level - 1 but TVB / positivity are
+            // not restated for it); the Qk basis only (as under mapping = q1)
+            if (p.basis != DFLO_BASIS_QK || p.limiter_type != DFLO_LIMITER_NONE || p.pos_lim)
+               return fail (DFLO_E_UNSUPPORTED, "faces with hanging nodes: Qk basis without limiters only");
+            if (!mesh.cell_vertices || !mesh.neighbor_face || !mesh.hanging) return fail (DFLO_E_INVALID, "hanging nodes need cell_vertices, neighbor_face and the hanging table");
+            if (world > 1) return fail (DFLO_E_UNSUPPORTED, "faces with hanging nodes are supported on unsharded contexts only");
+         }
          if (p.mapping == DFLO_MAPPING_Q1)
          {
             // src/parameters.cc:545-549: TVB and Pk need Cartesian grids; the positivity limiter on mapped cells is not covered
@@ -711,7 +725,12 @@ namespace dflo
          d_fflags = upload (lm.fflags);
          d_geom = upload (lm.geom);
          d_l2g = upload (lm.l2g);
-         if (mapped ())
+         if (hanging)
+         {
+            d_hang_of = upload (lm.hang_of);
+            d_hang = upload (lm.hang);
+         }
+         if (general_kernel ())
          {
             d_verts = upload (lm.verts);
             d_nbr_face = upload (lm.nbr_face);
@@ -778,7 +797,7 @@ namespace dflo
             bk.free (U[i]);
             bk.free (AVG[i]);
          }
-         void *ptrs[] = {d_dt_cell, d_verts, d_dtq, d_nbr_face, d_ext_force, rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
+         void *ptrs[] = {d_hang_of, d_hang, d_dt_cell, d_verts, d_dtq, d_nbr_face, d_ext_force, rhs, d_time, d_scratch, d_nbr, d_fflags, d_geom, d_bc_g, d_stage_tab, d_lim_tab, d_gw, d_gx, d_bkind, d_bf_cell,
                          d_bf_face, d_bf_id, d_l2g, d_flags, d_err, d_shock, d_code, d_prog_start, d_prog_start_t, d_ext, d_dofmap, d_halo_cells, d_jobs, d_tiles, d_rowdesc, d_send_entries};
          for (void *p : ptrs) bk.free (p);
          for (int k = 0; k < 2; ++k)
@@ -1130,7 +1149,7 @@ namespace dflo
       // for Qk on the device, else the tile kernel.  owned_only: right-hand side of the owned cells only.
       void run_stage (const StageArgs &a, bool owned_only)
       {
-         if (mapped ())
+         if (general_kernel ())
          {
             MappedStageArgs m;
             m.u = a.u;
@@ -1148,6 +1167,8 @@ namespace dflo
             m.time = a.time;
             m.ext_force = a.ext_force;
             m.dt_cell = a.dt_cell;
+            m.hang_of = d_hang_of;
+            m.hang = d_hang;
             m.n_compute = owned_only ? lm.n_owned : lm.n_compute;
             m.n_keep = lm.n_owned;
             m.mode = a.mode;

@@ -44,6 +44,12 @@ dflo_mesh *dflo_mesh_create (const char *kind, const double *a, int n)
       const int ids[4] = {(int) a[6], (int) a[7], (int) a[8], (int) a[9]};
       m->pm = dflo::make_skewed_rectangle ((int) a[0], (int) a[1], a[2], a[3], a[4], a[5], ids, a[10], (int) a[11]);
    }
+   else if (k == "rectangle_refined" && (n == 14 || n == 15))
+   {
+      const int ids[4] = {(int) a[6], (int) a[7], (int) a[8], (int) a[9]};
+      m->pm = dflo::make_refined_rectangle ((int) a[0], (int) a[1], a[2], a[3], a[4], a[5], ids, (int) a[10], (int) a[11], (int) a[12], (int) a[13],
+                                            n == 15 ? (int) a[14] : 0);
+   }
    else if (k == "compression_corner" && n == 3)
       m->pm = dflo::make_compression_corner ((int) a[0], (int) a[1], (int) a[2]);
    else if (k == "isentropic_vortex" && n == 1)

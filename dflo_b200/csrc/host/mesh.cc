@@ -25,6 +25,8 @@ namespace dflo
       m.bface_id = bface_id.data ();
       m.cell_vertices = vertices.data ();
       m.neighbor_face = neighbor_face.data ();
+      m.n_hanging_faces = (int32_t) (hanging.size () / 6);
+      m.hanging = hanging.data ();
       return m;
    }
 
@@ -108,6 +110,46 @@ namespace dflo
             }
          }
       }
+      // hanging nodes: an unmatched edge A-B whose mid point M is a vertex, with the unmatched edges A-M and M-B on the other side
+      {
+         std::map<std::pair<long long, long long>, int> vertex_at;
+         auto vkey = [] (double x, double y) { return std::make_pair ((long long) std::llround (x * 1e9), (long long) std::llround (y * 1e9)); };
+         for (int v = 0; v < pm.n_vertices (); ++v) vertex_at[vkey (V[2 * v], V[2 * v + 1])] = v;
+         std::vector<uint64_t> single;
+         for (auto &kv : edges)
+            if (kv.second.second.cell < 0) single.push_back (kv.first);
+         std::sort (single.begin (), single.end ()); // a reproducible order of the table
+         for (uint64_t k : single)
+         {
+            const Side c = edges[k].first;
+            if (c.cell < 0) continue; // consumed as a child below
+            const int A = pm.cells[4 * (size_t) c.cell + FV[c.face][0]], B = pm.cells[4 * (size_t) c.cell + FV[c.face][1]];
+            auto it = vertex_at.find (vkey (0.5 * (V[2 * A] + V[2 * B]), 0.5 * (V[2 * A + 1] + V[2 * B + 1])));
+            if (it == vertex_at.end ()) continue;
+            const int M = it->second;
+            auto e0 = edges.find (edge_key (A, M)), e1 = edges.find (edge_key (M, B));
+            if (e0 == edges.end () || e1 == edges.end () || e0->second.second.cell >= 0 || e1->second.second.cell >= 0) continue;
+            const Side kid[2] = {e0->second.first, e1->second.first};
+            out.hanging.push_back (c.cell);
+            out.hanging.push_back (c.face);
+            for (int j = 0; j < 2; ++j)
+            {
+               out.hanging.push_back (kid[j].cell);
+               out.hanging.push_back (kid[j].face);
+               const bool rev = pm.cells[4 * (size_t) kid[j].cell + FV[kid[j].face][0]] != (j == 0 ? A : M);
+               out.neighbor[4 * (size_t) kid[j].cell + kid[j].face] = c.cell;
+               out.neighbor_face[4 * (size_t) kid[j].cell + kid[j].face] = (uint8_t) c.face;
+               out.face_flags[4 * (size_t) kid[j].cell + kid[j].face] = DFLO_FACE_COARSER | (j ? DFLO_FACE_CHILD1 : 0) | (rev ? DFLO_FACE_FLIP : 0) | DFLO_FACE_OWNER;
+            }
+            out.neighbor[4 * (size_t) c.cell + c.face] = kid[0].cell;
+            out.neighbor_face[4 * (size_t) c.cell + c.face] = (uint8_t) kid[0].face;
+            out.face_flags[4 * (size_t) c.cell + c.face] = DFLO_FACE_HANGING;
+            // the three edges are interior now: take them out of the boundary pass below
+            edges[k].second = Side{-2, -2};
+            e0->second.second = Side{-2, -2};
+            e1->second.second = Side{-2, -2};
+         }
+      }
       std::unordered_map<uint64_t, int> line_id;
       for (int b = 0; b < pm.n_blines (); ++b) line_id[edge_key (pm.blines[2 * b], pm.blines[2 * b + 1])] = pm.bline_id[b];
 
@@ -116,6 +158,7 @@ namespace dflo
       for (auto &kv : edges)
       {
          const Side a = kv.second.first, b = kv.second.second;
+         if (b.cell == -2) continue; // a face with a hanging node, or one of its halves: handled above
          if (b.cell >= 0)
          {
             // do the two cells run along the shared line in the same direction?  (deal.II orients 2-D meshes so that they
@@ -314,6 +357,80 @@ namespace dflo
          {
             int *q = &pm.cells[4 * (size_t) c];
             for (int r = (c * 7 + c / nx) % 4; r > 0; --r) // one quarter turn: (v0 v1 v2 v3) -> (v1 v3 v0 v2), Jacobian stays positive
+            {
+               const int t[4] = {q[1], q[3], q[0], q[2]};
+               for (int i = 0; i < 4; ++i) q[i] = t[i];
+            }
+         }
+      return pm;
+   }
+
+   // nx x ny cells of [x0,x1] x [y0,y1]; the cells i0 <= i < i1, j0 <= j < j1 are replaced by their four children (one level,
+   // what deal.II's refine_grid leaves behind): hanging nodes all around the patch.  Vertices live on the half-cell lattice.
+   PrimitiveMesh make_refined_rectangle (int nx, int ny, double x0, double x1, double y0, double y1, const int ids[4], int i0, int i1, int j0, int j1,
+                                         int rotate)
+   {
+      PrimitiveMesh pm;
+      const double hx = (x1 - x0) / nx, hy = (y1 - y0) / ny;
+      std::map<std::pair<int, int>, int> vid;
+      auto v = [&] (int i2, int j2) {
+         auto key = std::make_pair (i2, j2);
+         auto it = vid.find (key);
+         if (it != vid.end ()) return it->second;
+         const int id = pm.n_vertices ();
+         pm.vertices.push_back (x0 + 0.5 * hx * i2);
+         pm.vertices.push_back (y0 + 0.5 * hy * j2);
+         vid[key] = id;
+         return id;
+      };
+      auto quad = [&] (int a, int b, int s) {
+         pm.cells.push_back (v (a, b));
+         pm.cells.push_back (v (a + s, b));
+         pm.cells.push_back (v (a, b + s));
+         pm.cells.push_back (v (a + s, b + s));
+      };
+      for (int j = 0; j < ny; ++j)
+         for (int i = 0; i < nx; ++i)
+            if (i >= i0 && i < i1 && j >= j0 && j < j1)
+               for (int dj = 0; dj < 2; ++dj)
+                  for (int di = 0; di < 2; ++di) quad (2 * i + di, 2 * j + dj, 1);
+            else
+               quad (2 * i, 2 * j, 2);
+      auto line = [&] (int a, int b, int id) {
+         pm.blines.push_back (a);
+         pm.blines.push_back (b);
+         pm.bline_id.push_back (id);
+      };
+      // boundary lines at the resolution of the cells behind them
+      for (int j = 0; j < ny; ++j)
+         for (int side = 0; side < 2; ++side)
+         {
+            const int i = side ? nx - 1 : 0, i2 = side ? 2 * nx : 0;
+            if (i >= i0 && i < i1 && j >= j0 && j < j1)
+            {
+               line (v (i2, 2 * j), v (i2, 2 * j + 1), ids[side]);
+               line (v (i2, 2 * j + 1), v (i2, 2 * j + 2), ids[side]);
+            }
+            else
+               line (v (i2, 2 * j), v (i2, 2 * j + 2), ids[side]);
+         }
+      for (int i = 0; i < nx; ++i)
+         for (int side = 0; side < 2; ++side)
+         {
+            const int j = side ? ny - 1 : 0, j2 = side ? 2 * ny : 0;
+            if (i >= i0 && i < i1 && j >= j0 && j < j1)
+            {
+               line (v (2 * i, j2), v (2 * i + 1, j2), ids[2 + side]);
+               line (v (2 * i + 1, j2), v (2 * i + 2, j2), ids[2 + side]);
+            }
+            else
+               line (v (2 * i, j2), v (2 * i + 2, j2), ids[2 + side]);
+         }
+      if (rotate) // mixed cell orientations (mapping = q1 only): coarse and fine cells meet on arbitrary faces, in either direction
+         for (int c = 0; c < pm.n_cells (); ++c)
+         {
+            int *q = &pm.cells[4 * (size_t) c];
+            for (int r = (c * 5 + c / 3) % 4; r > 0; --r)
             {
                const int t[4] = {q[1], q[3], q[0], q[2]};
                for (int i = 0; i < 4; ++i) q[i] = t[i];

@@ -32,6 +32,7 @@ namespace dflo
       std::vector<int32_t> bface_cell, bface_face, bface_id;
       std::vector<double> vertices;        // [nc][4][2]
       std::vector<uint8_t> neighbor_face;  // [nc][4]
+      std::vector<int32_t> hanging;        // [nh][6] faces with a hanging node (dflo_flat_mesh::hanging)
       bool cartesian = true;               // every cell an axis-aligned rectangle, every neighbour across face f on its face f ^ 1
       std::string why_not_cartesian;
       dflo_flat_mesh view () const;
@@ -70,6 +71,9 @@ namespace dflo
    // the same rectangle with smoothly displaced interior vertices (general quadrilaterals for mapping = q1); rotate: mixed cell orientations
    PrimitiveMesh make_skewed_rectangle (int nx, int ny, double x0, double x1, double y0, double y1, const int ids[4], double amp, int rotate);
 
+   // a rectangle of nx x ny cells in which the cells i0 <= i < i1, j0 <= j < j1 are split into four: hanging nodes on the rim of the patch
+   PrimitiveMesh make_refined_rectangle (int nx, int ny, double x0, double x1, double y0, double y1, const int ids[4], int i0, int i1, int j0, int j1,
+                                         int rotate = 0);
    PrimitiveMesh make_compression_corner (int nx1_cells, int nx2_cells, int ny_cells);   // examples/compression_corner/corner.geo (mapping = q1)
 
    // The four BASELINE geometries, reproducing the transfinite blocks of the reference's .geo

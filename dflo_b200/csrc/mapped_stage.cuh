@@ -41,6 +41,7 @@ namespace dflo
       const double *time;
       const double *ext_force;      // [n_local][NQ][2] or nullptr
       const double *dt_cell;        // time step type = local: dt(cell), else nullptr
+      const int *hang_of, *hang;    // faces with hanging nodes: [n_local][4] index or -1; per face {fine cell, its face, backwards?} x 2; or nullptr
       int n_compute, n_keep;
       int mode, compat_mpi;
       double ark, gravity;
@@ -89,8 +90,8 @@ namespace dflo
       static constexpr int O_TAB = 0;
       static constexpr int O_U = (NTAB + 1) / 2 * 2;
       static constexpr int O_F = O_U + CPB * D;                      // [CPB][NQ][8] contravariant fluxes
-      static constexpr int O_H = O_F + CPB * NQ * 8;                 // [CPB][4][N1][4] weighted face fluxes
-      static constexpr int O_P = O_H + CPB * 16 * N1;                // [CPB][NQ][4] the nodes' parts of the cell means
+      static constexpr int O_H = O_F + CPB * NQ * 8;                 // [CPB][4 faces][2 halves][N1][4] weighted face fluxes (second half: hanging nodes)
+      static constexpr int O_P = O_H + CPB * 32 * N1;                // [CPB][NQ][4] the nodes' parts of the cell means
       static constexpr int SMEM_DOUBLES = O_P + CPB * NQ * 4;
       static int grid (int n_cells) { return (n_cells + CPB - 1) / CPB; }
 
@@ -109,6 +110,30 @@ namespace dflo
          }
       }
 
+      // trace of a COARSE cell at point qc of child `child` of its face f (FESubfaceValues): the trace along the normal of every
+      // tangential line, interpolated to the sub-face point with S[child][qc][.] -- one chain for both sides of the face
+      static DFLO_DEV void subtrace (const double *tb, const double *S, const double *uc, int f, int child, int qc, double W[4])
+      {
+         const double *e = tb + N1 * N1 + (f & 1) * N1;
+         const double *Sq = S + (child * N1 + qc) * N1;
+         const int stride = (f < 2) ? 1 : N1;
+#pragma unroll
+         for (int c = 0; c < 4; ++c)
+         {
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < N1; ++t)
+            {
+               const int base = (f < 2) ? N1 * t : t;
+               double in = 0.0;
+#pragma unroll
+               for (int a = 0; a < N1; ++a) in = fma (e[a], uc[c * NQ + base + a * stride], in);
+               s = fma (Sq[t], in, s);
+            }
+            W[c] = s;
+         }
+      }
+
       static DFLO_DEV void phase (int ph, const Args &A, double *sm, int tid, int bid)
       {
          double *tb = sm + O_TAB, *su = sm + O_U, *sF = sm + O_F, *sH = sm + O_H;
@@ -117,7 +142,8 @@ namespace dflo
          const bool active = slot < CPB && cell < A.n_compute;
          const int a = q % N1, b = q / N1;
          const double *gw = tb + N1 * N1 + 2 * N1;
-         const double *gx = A.tab + NTAB; // Gauss nodes follow the stage tables (engine_core: pack_mapped_tables)
+         const double *gx = A.tab + NTAB;      // Gauss nodes follow the stage tables (tables_pack.h) ...
+         const double *S = A.tab + NTAB + N1;  // ... and the sub-face interpolation table S[child][q][a]
 
          if (ph == 0)
          {
@@ -154,23 +180,63 @@ namespace dflo
                   f[4 + c] = -yxi * Fx[c] + xxi * Fy[c];
                }
             }
-            // face fluxes: 4 N1 (face, point) items per cell spread over the cell's NQ threads
-            for (int j = q; j < 4 * N1; j += NQ)
+            // face fluxes: (face, half, point) items of the cell spread over its NQ threads; the second half of a face only
+            // exists where the face has a hanging node
+            for (int j = q; j < 8 * N1; j += NQ)
             {
-               const int f = j / N1, p = j % N1;
-               double nx, ny, len;
-               q1_face (v, f, nx, ny, len);
+               const int f = j / (2 * N1), half = (j / N1) & 1, p = j % N1;
+               const int fl = A.fflags[(size_t) cell * 4 + f];
+               if (half && !(fl & DFLO_FACE_HANGING)) continue;
                double Wp[4], Wm[4], Ap[4], Am[4], H[4];
-               trace (tb, uc, f, p, Wp);
+               double w;
                if (flux_uses_averages (FLUX))
                {
 #pragma unroll
                   for (int c = 0; c < 4; ++c) Ap[c] = A.avg[(size_t) cell * 4 + c];
                }
-               const int nb = A.nbr[(size_t) cell * 4 + f];
-               if (nb >= 0)
+               if (fl & DFLO_FACE_HANGING)
                {
-                  const int fl = A.fflags[(size_t) cell * 4 + f];
+                  // coarse side of a face with a hanging node: the fine cell behind this half is the one that integrates
+                  // (MeshWorker); its Riemann problem -- its normal, its face points, its JxW -- is evaluated here
+                  // with the same bits, and this cell takes minus the flux
+                  const int *hg = A.hang + 6 * (size_t) A.hang_of[(size_t) cell * 4 + f] + 3 * half;
+                  const int fine = hg[0], nf = hg[1];
+                  const int pf = hg[2] ? N1 - 1 - p : p; // the fine side's number of this point
+                  double nx, ny, len;
+                  q1_face (A.verts + (size_t) fine * 8, nf, nx, ny, len);
+                  trace (tb, A.u + (size_t) fine * D, nf, pf, Wm);
+                  subtrace (tb, S, uc, f, half, p, Wp);
+                  if (flux_uses_averages (FLUX))
+                  {
+#pragma unroll
+                     for (int c = 0; c < 4; ++c) Am[c] = A.avg[(size_t) fine * 4 + c];
+                  }
+                  numerical_flux<FLUX> (nx, ny, Wm, Wp, Am, Ap, H);
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) H[c] = -H[c];
+                  w = gw[pf] * len;
+               }
+               else
+               {
+               double nx, ny, len;
+               q1_face (v, f, nx, ny, len);
+               trace (tb, uc, f, p, Wp);
+               const int nb = A.nbr[(size_t) cell * 4 + f];
+               if (nb >= 0 && (fl & DFLO_FACE_COARSER))
+               {
+                  // fine side: the neighbour is coarser; its trace on this half of its face, at this cell's points
+                  const int nf = A.nbr_face[(size_t) cell * 4 + f];
+                  const int pc = (fl & DFLO_FACE_FLIP) ? N1 - 1 - p : p;
+                  subtrace (tb, S, A.u + (size_t) nb * D, nf, (fl & DFLO_FACE_CHILD1) ? 1 : 0, pc, Wm);
+                  if (flux_uses_averages (FLUX))
+                  {
+#pragma unroll
+                     for (int c = 0; c < 4; ++c) Am[c] = A.avg[(size_t) nb * 4 + c];
+                  }
+                  numerical_flux<FLUX> (nx, ny, Wp, Wm, Ap, Am, H);
+               }
+               else if (nb >= 0)
+               {
                   const int nf = A.nbr_face[(size_t) cell * 4 + f];
                   const int pn = (fl & DFLO_FACE_FLIP) ? N1 - 1 - p : p;
                   trace (tb, A.u + (size_t) nb * D, nf, pn, Wm);
@@ -210,8 +276,9 @@ namespace dflo
                   }
                   numerical_flux<FLUX> (nx, ny, Wp, Wm, Ap, Am, H);
                }
-               const double w = gw[p] * len; // fe_v.JxW(q) on a straight face
-               double *h = sH + ((slot * 4 + f) * N1 + p) * 4;
+               w = gw[p] * len; // fe_v.JxW(q) on a straight face
+               }
+               double *h = sH + (((slot * 4 + f) * 2 + half) * N1 + p) * 4;
 #pragma unroll
                for (int c = 0; c < 4; ++c) h[c] = w * H[c];
             }
@@ -227,8 +294,32 @@ namespace dflo
             const double det = xxi * yeta - xeta * yxi;
             const double wq = gw[a] * gw[b] * det; // JxW at the node
             const double *F = sF + slot * NQ * 8;
-            const double *H0 = sH + ((slot * 4 + 0) * N1 + b) * 4, *H1 = sH + ((slot * 4 + 1) * N1 + b) * 4;
-            const double *H2 = sH + ((slot * 4 + 2) * N1 + a) * 4, *H3 = sH + ((slot * 4 + 3) * N1 + a) * 4;
+            // lifting: the flux of face f at this node's tangential position t -- on a face with a hanging node the two halves'
+            // fluxes tested with the coarse basis at the sub-face points, sum_half sum_q H(half, q) S[half][q][t]
+            double L[4][4]; // [face][component]
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+            {
+               const int t = f < 2 ? b : a;
+               const double *Hf = sH + ((slot * 4 + f) * 2) * N1 * 4;
+               if (A.hang_of && (A.fflags[(size_t) cell * 4 + f] & DFLO_FACE_HANGING))
+               {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) L[f][c] = 0.0;
+                  for (int half = 0; half < 2; ++half)
+                     for (int qq = 0; qq < N1; ++qq)
+                     {
+                        const double sv = S[(half * N1 + qq) * N1 + t];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) L[f][c] = fma (sv, Hf[(half * N1 + qq) * 4 + c], L[f][c]);
+                     }
+               }
+               else
+               {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) L[f][c] = Hf[t * 4 + c];
+               }
+            }
             double r[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -238,7 +329,7 @@ namespace dflo
                for (int ap = 0; ap < N1; ++ap) sx = fma (F[(ap + N1 * b) * 8 + c], dw[ap * N1 + a], sx);
 #pragma unroll
                for (int bp = 0; bp < N1; ++bp) sy = fma (F[(a + N1 * bp) * 8 + 4 + c], dw[bp * N1 + b], sy);
-               r[c] = gw[b] * sx + gw[a] * sy - (H0[c] * e0[a] + H1[c] * e1[a] + H2[c] * e0[b] + H3[c] * e1[b]);
+               r[c] = gw[b] * sx + gw[a] * sy - (L[0][c] * e0[a] + L[1][c] * e1[a] + L[2][c] * e0[b] + L[3][c] * e1[b]);
             }
             const double W[4] = {uc[q], uc[NQ + q], uc[2 * NQ + q], uc[3 * NQ + q]};
             if (A.gravity != 0.0) // assemble_explicit.cc:78, 108-111

@@ -55,6 +55,9 @@ namespace dflo
       std::vector<double> geom;  // [n_local][4] x0 y0 hx hy
       std::vector<double> verts; // [n_local][8] cell vertices (mapping = q1; empty otherwise)
       std::vector<unsigned char> nbr_face; // [n_local][4] the neighbour's local number of the shared face (mapping = q1)
+      // faces with a hanging node (unsharded contexts only): hang_of[cell*4+f] = index or -1; per face
+      // { fine cell 0, its face, runs backwards?, fine cell 1, its face, runs backwards? } in local cell numbers
+      std::vector<int> hang_of, hang;
       std::vector<int> bf_global, bf_id; // local boundary faces (of the computed cells) -> global bface, boundary id
       std::vector<int> bf_cell, bf_face; // local cell, face
       std::vector<HaloPeer> peers;
@@ -499,6 +502,29 @@ namespace dflo
             }
             else
                L.nbr[4 * (size_t) l + f] = l; // never evaluated
+         }
+      }
+      if (m.n_hanging_faces > 0)
+      {
+         if (world > 1)
+         {
+            err = "faces with hanging nodes are supported on unsharded contexts only";
+            return false;
+         }
+         std::vector<int> g2l_all (m.n_cells, -1);
+         for (int l = 0; l < L.n_local; ++l) g2l_all[L.l2g[l]] = l;
+         L.hang_of.assign (4 * (size_t) L.n_local, -1);
+         for (int h = 0; h < m.n_hanging_faces; ++h)
+         {
+            const int *e = m.hanging + 6 * (size_t) h;
+            const int lc = g2l_all[e[0]];
+            L.hang_of[4 * (size_t) lc + e[1]] = h;
+            for (int k = 0; k < 2; ++k)
+            {
+               L.hang.push_back (g2l_all[e[2 + 2 * k]]);
+               L.hang.push_back (e[3 + 2 * k]);
+               L.hang.push_back ((m.face_flags[4 * (size_t) e[2 + 2 * k] + e[3 + 2 * k]] & DFLO_FACE_FLIP) ? 1 : 0);
+            }
          }
       }
       if (row)

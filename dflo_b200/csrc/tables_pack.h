@@ -35,8 +35,22 @@ namespace dflo
                for (int m = 0; m < t.ns; ++m) o.push_back (t.phiface[f][q][m]);
       }
       for (int a = 0; a < n1; ++a) o.push_back (t.gw[a]);
-      if (t.basis == BASIS_QK) // read by the mapped (q1) stage kernel only; the others take exactly stage_table_size doubles
+      if (t.basis == BASIS_QK) // read by the mapped stage kernel only; the others take exactly stage_table_size doubles
+      {
          for (int a = 0; a < n1; ++a) o.push_back (t.gx[a]);
+         // sub-face interpolation (hanging nodes): S[child][q][a] = l_a ((x_q + child) / 2), the 1-D Lagrange basis on the Gauss
+         // nodes at the Gauss points of one half of a face
+         for (int child = 0; child < 2; ++child)
+            for (int q = 0; q < n1; ++q)
+               for (int a = 0; a < n1; ++a)
+               {
+                  const double x = 0.5 * (t.gx[q] + child);
+                  double l = 1.0;
+                  for (int m = 0; m < n1; ++m)
+                     if (m != a) l *= (x - t.gx[m]) / (t.gx[a] - t.gx[m]);
+                  o.push_back (l);
+               }
+      }
       return o;
    }
 

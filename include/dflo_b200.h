@@ -74,8 +74,14 @@ enum
    DFLO_FACE_PERIODIC = 2, /* neighbour reached through a periodic pair: both sides integrate with
                               their own normal (src_mpi/assemble_explicit.cc:186-260); it is a TVB
                               neighbour like any other (src_mpi/claw.cc:417-465) */
-   DFLO_FACE_FLIP = 4      /* periodic face_flip: neighbour's face points run backwards
+   DFLO_FACE_FLIP = 4,     /* periodic face_flip: neighbour's face points run backwards
                               (src_mpi/assemble_explicit.cc:247-250) */
+   /* hanging nodes (one level of refinement across a face, as deal.II keeps it; MeshWorker integrates such a face from the
+    * FINE side on sub-faces): */
+   DFLO_FACE_COARSER = 8,  /* the neighbour is coarser: this face is one half of its face `neighbor_face` ... */
+   DFLO_FACE_CHILD1 = 16,  /* ... the second half along the coarse cell's line (else the first) */
+   DFLO_FACE_HANGING = 32  /* this face has a hanging node: two finer neighbours, listed in dflo_flat_mesh::hanging;
+                              `neighbor` holds the first of them */
 };
 
 /* "mapping" of input.prm (src/claw.cc:165-190): cartesian = MappingCartesian (axis-aligned rectangles, the fast kernels);
@@ -102,6 +108,10 @@ typedef struct
    const double *cell_vertices;   /* [n_cells][4][2] vertices in deal.II's lexicographic order (cell->vertex(0..3)) */
    const uint8_t *neighbor_face;  /* [n_cells][4] the neighbour's local number of the shared face; DFLO_FACE_FLIP in
                                      face_flags when the two cells run along the face in opposite directions */
+   /* faces with a hanging node (needs cell_vertices / neighbor_face; no limiters; unsharded contexts only): */
+   int32_t n_hanging_faces;
+   const int32_t *hanging;        /* [n_hanging_faces][6] coarse cell, its face, then the two fine cells in the order of the
+                                     coarse line: fine cell 0, its face, fine cell 1, its face */
 } dflo_flat_mesh;
 
 /* The subset of Parameters::AllParameters (src/parameters.h:112-414) the hot path reads. */

@@ -24,6 +24,8 @@ typedef struct dflo_mesh dflo_mesh;
  *   "rectangle"          nx ny x0 x1 y0 y1 id_left id_right id_bottom id_top
  *   "rectangle_skew"     nx ny x0 x1 y0 y1 id_left id_right id_bottom id_top amplitude rotate   (general quadrilaterals
  *                        for mapping = q1: interior vertices displaced smoothly; rotate != 0: mixed cell orientations)
+ *   "rectangle_refined"  nx ny x0 x1 y0 y1 id_left id_right id_bottom id_top i0 i1 j0 j1 [rotate]   (cells i0 <= i < i1, j0 <= j < j1 split
+ *                        into four: faces with hanging nodes around the patch)
  *   "compression_corner" nx1 nx2 ny (cells)            (examples/compression_corner/corner.geo: trapezoids, mapping = q1)
  *   "isentropic_vortex"  n_cells_per_side              (examples/isentropic_vortex/grid.geo)
  *   "sod_tube"           nx ny                         (examples/sod_shock_tube/tube.geo)

@@ -234,6 +234,9 @@ namespace
       double x0, y0, hx, hy;
       double vx[4], vy[4]; // vertices, deal.II lexicographic order (A1); MappingQ1 works from these
       int nbr_face[4];   // the neighbour's local number of the shared face (f ^ 1 on lattice meshes)
+      int sub[4];        // hanging nodes: >= 0: the neighbour across face f is COARSER and this face is its child `sub` (0: the half at
+                         // the start of the coarse face's line, 1: the other); -1 otherwise
+      int hang[4];       // >= 0: face f has a hanging node (two finer neighbours): index into oracle_ctx::hanging; -1 otherwise
       int nbr[4];        // neighbour cell or -1 (boundary)
       int bid[4];        // boundary id if at boundary
       int bface[4];      // index into the non-periodic boundary-face list, or -1
@@ -242,6 +245,13 @@ namespace
    };
 
    const double NORMAL[4][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}}; // MappingCartesian, A6
+
+   // a face with a hanging node: the coarse cell's face and the two finer cells behind it, in the order of the coarse line
+   struct Hanging
+   {
+      int coarse, cface;
+      int fine[2], fface[2];
+   };
 }
 
 struct oracle_ctx
@@ -270,6 +280,8 @@ struct oracle_ctx
    int n_rk;
 
    UnitValues dtq;          // QIterated(QTrapez,3): the 4x4 equispaced points of compute_time_step_q (claw.cc:522)
+   UnitValues subface[4][2]; // FESubfaceValues: QGauss<1>(k+1) on child c of face f of the COARSE cell (MeshWorker, hanging nodes)
+   std::vector<Hanging> hanging;
 
    int D () const { return fe.D; }
    bool q1 () const { return prm.mapping == ORACLE_MAPPING_Q1; }
@@ -388,6 +400,8 @@ namespace
          {
             face_map[key (v[FACE_VERT[f][0]], v[FACE_VERT[f][1]])].push_back (std::make_pair (c, f));
             cl.nbr[f] = -1;
+            cl.sub[f] = -1;
+            cl.hang[f] = -1;
             cl.nbr_face[f] = f ^ 1;
             cl.bid[f] = 0;
             cl.bface[f] = -1;
@@ -418,6 +432,45 @@ namespace
          {
             g_error = "non-manifold face";
             return false;
+         }
+      }
+      // hanging nodes (one level of refinement, as deal.II keeps it): an unmatched edge A-B whose mid point M is a vertex with
+      // the two unmatched edges A-M and M-B on the other side
+      {
+         std::map<std::pair<long long, long long>, int> vertex_at;
+         auto vkey = [] (double x, double y) { return std::make_pair ((long long) std::llround (x * 1e9), (long long) std::llround (y * 1e9)); };
+         for (int v = 0; v < nv; ++v) vertex_at[vkey (V[2 * v], V[2 * v + 1])] = v;
+         std::vector<std::pair<Key, std::pair<int, int>>> single;
+         for (auto &kv : face_map)
+            if (kv.second.size () == 1) single.push_back (std::make_pair (kv.first, kv.second[0]));
+         for (auto &e : single)
+         {
+            const int c = e.second.first, f = e.second.second;
+            const int A = C[4 * c + FACE_VERT[f][0]], B = C[4 * c + FACE_VERT[f][1]];
+            auto it = vertex_at.find (vkey (0.5 * (V[2 * A] + V[2 * B]), 0.5 * (V[2 * A + 1] + V[2 * B + 1])));
+            if (it == vertex_at.end ()) continue;
+            const int M = it->second;
+            auto e0 = face_map.find (key (A, M)), e1 = face_map.find (key (M, B));
+            if (e0 == face_map.end () || e1 == face_map.end () || e0->second.size () != 1 || e1->second.size () != 1) continue;
+            Hanging h;
+            h.coarse = c;
+            h.cface = f;
+            const std::pair<int, int> kids[2] = {e0->second[0], e1->second[0]};
+            for (int k = 0; k < 2; ++k)
+            {
+               const int fc = kids[k].first, ff = kids[k].second;
+               h.fine[k] = fc;
+               h.fface[k] = ff;
+               Cell &fcl = o.cells[fc];
+               fcl.nbr[ff] = c;
+               fcl.nbr_face[ff] = f;
+               fcl.sub[ff] = k;
+               // same direction along the line if the fine face starts where its half of the coarse face starts
+               fcl.flip[ff] = C[4 * fc + FACE_VERT[ff][0]] != (k == 0 ? A : M);
+            }
+            o.cells[c].hang[f] = (int) o.hanging.size ();
+            o.cells[c].nbr[f] = h.fine[0]; // "has a neighbour" (cell->neighbor(f) exists and has children)
+            o.hanging.push_back (h);
          }
       }
       // vertex-sharing interior faces = what deal.II's cell->neighbor() knows about
@@ -716,6 +769,46 @@ namespace
       }
    }
 
+   // A face with a hanging node, integrated from the FINE side (MeshWorker::loop: "hanging faces integrated from the fine side
+   // on sub-faces"): FEFaceValues on the fine cell's face f, FESubfaceValues on child `sub` of the coarse
+   // neighbour's face -- the same physical points; assemble_explicit.cc:256-427 does not know the difference.
+   void integrate_subface_term (const oracle_ctx &o, int cno, int f, double *local, double *local_nbr)
+   {
+      const Cell &cl = o.cells[cno];
+      const int ncno = cl.nbr[f], nf = cl.nbr_face[f], child = cl.sub[f];
+      const int D = o.D (), ns = o.fe.ns, nqf = o.face[f].nq;
+      const UnitValues &sv = o.subface[nf][child];
+      std::vector<double> Wplus (nqf * NC), Wminus (nqf * NC), H (nqf * NC);
+      face_values (o, cno, f, Wplus.data ());
+      const double *un = &o.current[(size_t) ncno * D];
+      for (int q = 0; q < nqf; ++q)
+      {
+         const int qn = cl.flip[f] ? nqf - q - 1 : q; // the coarse side's index of this physical point
+         for (int c = 0; c < NC; ++c) Wminus[q * NC + c] = 0.0;
+         for (int i = 0; i < D; ++i) Wminus[q * NC + i / ns] += un[i] * sv.phi[(i % ns) * nqf + qn];
+      }
+      double NRM[2], flen;
+      o.face_geometry (cl, f, NRM, flen);
+      for (int q = 0; q < nqf; ++q)
+         phys_numerical_flux (o.prm.flux_type, NRM, &Wplus[q * NC], &Wminus[q * NC], &o.cell_average[cno * NC],
+                              &o.cell_average[ncno * NC], &H[q * NC]);
+      for (int i = 0; i < D; ++i)
+      {
+         double F_i = 0;
+         const int ci = i / ns;
+         for (int q = 0; q < nqf; ++q) F_i += H[q * NC + ci] * o.face[f].phi[(i % ns) * nqf + q] * face_JxW (o, cl, f, q);
+         local[i] -= F_i;
+      }
+      for (int i = 0; i < D; ++i)
+      {
+         double F_i = 0;
+         const int ci = i / ns;
+         for (int q = 0; q < nqf; ++q)
+            F_i -= H[q * NC + ci] * sv.phi[(i % ns) * nqf + (cl.flip[f] ? nqf - q - 1 : q)] * face_JxW (o, cl, f, q); // JxW of the sub-face = the fine face's
+         local_nbr[i] -= F_i;
+      }
+   }
+
    // is face f of cell c handled by the boundary worker?  (true boundary or periodic: the two
    // periodic partners share no vertices, cell->at_boundary() stays true)
    bool at_boundary (const oracle_ctx &o, int c, int f, const std::vector<char> &shared)
@@ -749,6 +842,13 @@ namespace
          {
             integrate_boundary_term (o, c, f, &L.v[(size_t) (1 + 2 * f) * D]);
             L.has_int[f] = true;
+         }
+         else if (o.cells[c].hang[f] >= 0)
+            ; // the two finer neighbours integrate their halves
+         else if (o.cells[c].sub[f] >= 0) // neighbour is coarser: this (fine) side integrates
+         {
+            integrate_subface_term (o, c, f, &L.v[(size_t) (1 + 2 * f) * D], &L.v[(size_t) (2 + 2 * f) * D]);
+            L.has_int[f] = L.has_ext[f] = true;
          }
          else if (o.cells[c].nbr[f] > c) // face integrated once, from the smaller cell
          {
@@ -1407,6 +1507,25 @@ oracle_ctx *oracle_create (int nv, const double *V, int nc, const int *C, int nb
             y.push_back (gl[b]);
          }
       o->posy.init (fe, x, y, w);
+   }
+   for (int f = 0; f < 4; ++f)
+      for (int child = 0; child < 2; ++child)
+      {
+         std::vector<double> x, y, w;
+         for (int q = 0; q < n1; ++q)
+         {
+            const double t = 0.5 * (fe.gx[q] + child);
+            x.push_back (f == 0 ? 0.0 : f == 1 ? 1.0 : t);
+            y.push_back (f == 2 ? 0.0 : f == 3 ? 1.0 : t);
+            w.push_back (0.5 * fe.gw[q]);
+         }
+         o->subface[f][child].init (fe, x, y, w);
+      }
+   if (!o->hanging.empty () && (prm->limiter_type != ORACLE_LIMITER_NONE || prm->pos_lim || prm->shock_indicator != 0))
+   {
+      g_error = "hanging nodes: no limiters (the limiters' neighbour lists are same-level)";
+      delete o;
+      return nullptr;
    }
    {
       // QIterated<2>(QTrapez<1>(), 3): points i/3, tensor product, x fastest (claw.cc:522)

@@ -300,3 +300,50 @@ def test_q1_vortex_h_convergence_gpu(k, ns, T, cfl, rotate):
         u = r.run_to(T)
         errs.append(_q1_l2(u, k, r.xq, _q1_jxw(v, c, *r.tables), T))
     _check_orders(errs, k, "gpu q1 Q%d rotate %d" % (k, rotate))
+
+
+# ---------------------------------------------------------------------------------------------
+# faces with hanging nodes: the vortex through a once-refined patch whose rim cuts the core
+# ---------------------------------------------------------------------------------------------
+def _refined_args(n):
+    return [n, n, -5, 5, -5, 5, 4, 2, 1, 3, n // 4, n // 2, n // 4, 3 * n // 4]
+
+
+def _rect_l2(u, v, c, gx_gw, xq, T):
+    gx, gw = gx_gw
+    area = (v[c[:, 1], 0] - v[c[:, 0], 0]) * (v[c[:, 2], 1] - v[c[:, 0], 1])
+    w = (gw[None, :] * gw[:, None]).reshape(-1)
+    rho = u.reshape(len(c), 4, -1)[:, 2, :]
+    ex = vortex_exact(xq[..., 0], xq[..., 1], T)[..., 2]
+    return float(np.sqrt((((rho - ex) ** 2) * w[None, :] * area[:, None]).sum()))
+
+
+HANGING_VORTEX = [(1, (16, 32, 64), 0.5, 0.4), (2, (16, 32, 64), 0.5, 0.3), (3, (16, 32, 64), 0.25, 0.15)]
+
+
+@pytest.mark.parametrize("k,ns,T,cfl", HANGING_VORTEX)
+def test_hanging_nodes_vortex_h_convergence_oracle(k, ns, T, cfl):
+    prm = dict(basis="Qk", degree=k, flux="roe", cfl=cfl, compat="mpi")
+    errs = []
+    for n in ns[:2] if k == 3 else ns:
+        mesh = abi.Mesh("rectangle_refined", _refined_args(n))
+        v, c, bl, bi = mesh.primitive()
+        r = _OracleRunner((v, c, bl, bi), PERIODIC_BOX, prm, lambda x, y: vortex_exact(x, y, 0.0))
+        u = r.run_to(T)
+        errs.append(_rect_l2(u, v, c, r.o.tables(), r.o.cell_qpoints(), T))
+    rates = [np.log2(errs[i] / errs[i + 1]) for i in range(len(errs) - 1)]
+    assert rates[-1] >= k + (0.6 if k == 3 else 0.8), (errs, rates)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,ns,T,cfl", HANGING_VORTEX)
+def test_hanging_nodes_vortex_h_convergence_gpu(k, ns, T, cfl):
+    assert gpu_available()
+    prm = dict(basis="Qk", degree=k, flux="roe", cfl=cfl, compat="mpi")
+    errs = []
+    for n in ns:
+        r = _EngineRunner(("rectangle_refined", _refined_args(n)), PERIODIC_BOX, prm, lambda x, y: vortex_exact(x, y, 0.0))
+        v, c, _, _ = r.mesh.primitive()
+        u = r.run_to(T)
+        errs.append(_rect_l2(u, v, c, r.tables, r.xq, T))
+    _check_orders(errs, k, "gpu hanging Q%d" % k)

@@ -472,3 +472,86 @@ def test_local_time_stepping_compression_corner():
     """examples/compression_corner: Q1, KFVS, mapping = q1, time step type = local on the two-block trapezoid mesh."""
     from helpers import compression_corner_case
     compression_corner_case("emu")
+
+
+# ---------------------------------------------------------------------------------------------
+# faces with hanging nodes (SURVEY.md 8(f) row 4, src/refine.cc; MeshWorker sub-face rule, SURVEY A7)
+# ---------------------------------------------------------------------------------------------
+def _refined_case(backend, k, flux, mapping, bc, ic, patch=(2, 5, 1, 4), n=(7, 6), rotate=0, **extra):
+    ids = (4, 2, 1, 3)
+    return Case(("rectangle_refined", [n[0], n[1], -5, 5, -5, 5, *ids, *patch, rotate]), bc, ic, backend=backend, basis="Qk", degree=k, flux=flux,
+                cfl=0.05 if flux == "kep" else 0.3, mapping=mapping, **extra)
+
+
+@pytest.mark.parametrize("mapping", ["cartesian", "q1"])
+@pytest.mark.parametrize("flux", ALL_FLUXES)
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_hanging_nodes_rhs_and_steps(k, flux, mapping):
+    """A patch of cells split into four inside a periodic box: every face on the rim of the patch has a hanging node and
+    is integrated from the fine side on the two halves (FESubfaceValues on the coarse side).  Right-hand side, time step
+    and three steps against the oracle, under both mappings."""
+    c = _refined_case("emu", k, flux, mapping, PERIODIC_BOX, ic_vortex, compat="mpi")
+    assert c.oracle.n_cells == 7 * 6 + 3 * 9
+    _rhs_ok(c)
+    for _ in range(3):
+        _, dt_o, dt_e = c.step()
+        assert abs(dt_o - dt_e) <= 1e-12 * dt_o
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+@pytest.mark.parametrize("k,flux", [(1, "lxf"), (2, "roe"), (3, "hllc")])
+def test_hanging_nodes_mixed_orientations(k, flux):
+    """The same with the vertex order of the cells turned at random: coarse and fine cells meet on arbitrary local faces
+    and run along the shared line in either direction (mapping = q1)."""
+    c = _refined_case("emu", k, flux, "q1", PERIODIC_BOX, ic_vortex, rotate=1, compat="mpi")
+    _rhs_ok(c)
+    for _ in range(3):
+        c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+def test_hanging_nodes_free_stream_conservation_and_boundaries():
+    """Uniform flow through a refined patch that touches the boundary stays uniform; in a periodic box the integral of every
+    conserved variable is kept to round-off (the two sides of a sub-face subtract the same bits); all boundary kinds."""
+    bc = {1: "outflow", 2: "outflow", 3: "outflow", 4: "outflow"}
+    uniform = lambda x, y: np.stack([0.7 + 0 * x, -0.3 + 0 * x, 1.2 + 0 * x, 3.0 + 0 * x], axis=-1)
+    c = _refined_case("emu", 3, "hllc", "cartesian", bc, uniform, patch=(0, 3, 2, 6))
+    r_o, r_e = c.rhs_pair()
+    assert np.abs(r_e).max() < 1e-13 and np.abs(r_o).max() < 1e-13
+    c.close()
+    c = _refined_case("emu", 2, "roe", "cartesian", PERIODIC_BOX, ic_vortex, compat="mpi")
+    v, cells, _, _ = c.mesh.primitive()
+    area = (v[cells[:, 1], 0] - v[cells[:, 0], 0]) * (v[cells[:, 2], 1] - v[cells[:, 0], 1])
+    gx, gw = c.oracle.tables()
+    w = (gw[None, :] * gw[:, None]).reshape(-1)
+    total = lambda u: (u.reshape(len(cells), 4, -1) * w[None, None, :] * area[:, None, None]).sum(axis=(0, 2))
+    t0 = total(c.solution())
+    te, _ = c.engine.advance(3)
+    assert te > 0 and np.abs(total(c.solution()) - t0).max() <= 1e-12 * np.abs(t0).max()
+    c.close()
+    bc = {1: "inflow", 2: "slip", 3: "pressure", 4: "farfield"}
+    c = _refined_case("emu", 2, "hllc", "q1", bc, ic_smooth, patch=(0, 3, 2, 6), gravity=0.7)
+    c.set_boundary(values=(1.0, 0.2, 1.4, 8.8), wiggle=0.05)
+    _rhs_ok(c)
+    for _ in range(2):
+        c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+def test_hanging_nodes_refusals():
+    ids = (4, 2, 1, 3)
+    mesh = ("rectangle_refined", [6, 6, -5, 5, -5, 5, *ids, 2, 4, 2, 4])
+    for kw in (dict(basis="Pk", degree=1), dict(basis="Qk", degree=1, limiter="TVB"), dict(basis="Qk", degree=1, pos_lim=True)):
+        params, pair = abi.make_params(bc={}, flux="lxf", **kw)
+        m = abi.Mesh(mesh[0], mesh[1], lib=emu_lib())
+        flat = m.flatten(params, pair)
+        assert flat.contents.n_hanging_faces == 8
+        with pytest.raises(abi.DfloError):
+            abi.Engine(flat, params, lib=emu_lib(), prefix="dflo_emu_")
+    params, pair = abi.make_params(bc={}, flux="lxf", basis="Qk", degree=1)
+    m = abi.Mesh(mesh[0], mesh[1], lib=emu_lib())
+    with pytest.raises(abi.DfloError):   # sharded contexts: not with hanging nodes
+        abi.Engine(m.flatten(params, pair), params, rank=0, world=2, nccl_id=b"\0" * 128, lib=emu_lib(), prefix="dflo_emu_")

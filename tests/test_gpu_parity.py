@@ -505,3 +505,48 @@ def test_compression_corner_driver_run(tmp_path):
     assert np.any(np.abs(y - ramp) < 1e-9) and np.all(f["point"]["Density"] > 0.5)
     assert f["point"]["Density"].max() > 1.05          # the oblique shock off the ramp is forming
     L.dflo_claw_destroy(h)
+
+
+# ---------------------------------------------------------------------------------------------
+# faces with hanging nodes: sub-face integration in the mapped stage kernel
+# ---------------------------------------------------------------------------------------------
+def _refined_case(k, flux, mapping, bc, ic, patch=(2, 5, 1, 4), n=(7, 6), rotate=0, **extra):
+    ids = (4, 2, 1, 3)
+    return Case(("rectangle_refined", [n[0], n[1], -5, 5, -5, 5, *ids, *patch, rotate]), bc, ic, backend="cuda", basis="Qk", degree=k,
+                flux=flux, cfl=0.05 if flux == "kep" else 0.3, mapping=mapping, **extra)
+
+
+@pytest.mark.parametrize("mapping,rotate", [("cartesian", 0), ("q1", 0), ("q1", 1)])
+@pytest.mark.parametrize("flux", ALL_FLUXES)
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4])
+def test_hanging_nodes_rhs_and_steps(k, flux, mapping, rotate):
+    c = _refined_case(k, flux, mapping, PERIODIC_BOX, ic_vortex, rotate=rotate, compat="mpi")
+    r_o, r_e = c.rhs_pair()
+    assert np.abs(r_o - r_e).max() <= TOL_RHS * max(1.0, np.abs(r_o).max()) * np.sqrt(c.oracle.D)
+    for _ in range(3):
+        _, dt_o, dt_e = c.step()
+        assert abs(dt_o - dt_e) <= 1e-12 * dt_o
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+def test_hanging_nodes_conservation_and_boundaries():
+    c = _refined_case(2, "roe", "cartesian", PERIODIC_BOX, ic_vortex, compat="mpi")
+    v, cells, _, _ = c.mesh.primitive()
+    area = (v[cells[:, 1], 0] - v[cells[:, 0], 0]) * (v[cells[:, 2], 1] - v[cells[:, 0], 1])
+    gx, gw = c.oracle.tables()
+    w = (gw[None, :] * gw[:, None]).reshape(-1)
+    total = lambda u: (u.reshape(len(cells), 4, -1) * w[None, None, :] * area[:, None, None]).sum(axis=(0, 2))
+    t0 = total(c.solution())
+    te, _ = c.engine.advance(5)
+    assert te > 0 and np.abs(total(c.solution()) - t0).max() <= 1e-12 * np.abs(t0).max()
+    c.close()
+    bc = {1: "inflow", 2: "slip", 3: "pressure", 4: "farfield"}
+    c = _refined_case(3, "hllc", "q1", bc, ic_smooth, patch=(0, 3, 2, 6), rotate=1, gravity=0.7)
+    c.set_boundary(values=(1.0, 0.2, 1.4, 8.8), wiggle=0.05)
+    r_o, r_e = c.rhs_pair()
+    assert np.abs(r_o - r_e).max() <= TOL_RHS * max(1.0, np.abs(r_o).max()) * np.sqrt(c.oracle.D)
+    for _ in range(2):
+        c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
