@@ -27,6 +27,7 @@ namespace dflo_b200_adapter
       std::vector<int32_t> neighbor, bface_cell, bface_face, bface_id;
       std::vector<uint8_t> face_flags, neighbor_face;
       std::vector<double> vertices;   // [nc][4][2]: what mapping = q1 works from
+      std::vector<int32_t> hanging;   // [nh][6]: faces with a hanging node (coarse cell, face, fine cell 0, its face, fine cell 1, its face)
       dflo_flat_mesh view () const
       {
          dflo_flat_mesh m = dflo_flat_mesh ();
@@ -41,6 +42,8 @@ namespace dflo_b200_adapter
          m.bface_id = bface_id.data ();
          m.cell_vertices = vertices.data ();
          m.neighbor_face = neighbor_face.data ();
+         m.n_hanging_faces = (int32_t) (hanging.size () / 6);
+         m.hanging = hanging.data ();
          return m;
       }
    };
@@ -48,8 +51,10 @@ namespace dflo_b200_adapter
    // Flatten once: what setup_system() computes cell by cell through deal.II iterators (neighbour arrays
    // src/claw.cc:336-380, cell numbering 294-298) becomes the SoA mesh of include/dflo_b200.h, plus the map from
    // (cell, local dof i) to deal.II's global dof index so that deal.II vectors can be handed over as they are.
-   // Returns DFLO_OK, or DFLO_E_UNSUPPORTED with `why` set for what the library does not cover (hanging nodes; with
-   // cartesian = true also cells that are not axis-aligned rectangles -- pass false for mapping = q1).
+   // Returns DFLO_OK, or DFLO_E_UNSUPPORTED with `why` set for what the library does not cover (with cartesian = true: cells
+   // that are not axis-aligned rectangles -- pass false for mapping = q1).  Faces with hanging nodes (one level, as deal.II
+   // keeps the mesh) go into FlatMeshStorage::hanging; in 2-D deal.II both cells see a line in the same direction, so
+   // no DFLO_FACE_FLIP arises.
    // `cell->user_index()` must already hold the active-cell counter.
    template <class DoFHandlerType>
    int flatten (const DoFHandlerType &dof_handler, unsigned int dofs_per_cell, FlatMeshStorage &out, std::vector<uint32_t> &dof_map,
@@ -62,6 +67,7 @@ namespace dflo_b200_adapter
       out.face_flags.assign (4 * (std::size_t) nc, 0);
       out.neighbor_face.assign (4 * (std::size_t) nc, 0);
       out.vertices.assign (8 * (std::size_t) nc, 0.0);
+      out.hanging.clear ();
       out.bface_cell.clear ();
       out.bface_face.clear ();
       out.bface_id.clear ();
@@ -101,10 +107,34 @@ namespace dflo_b200_adapter
                out.bface_id.push_back ((int32_t) cell->face (f)->boundary_id ());
                continue;
             }
-            if (cell->face (f)->has_children () || cell->neighbor_is_coarser (f))
+            if (cell->face (f)->has_children ())
             {
-               why = "dflo_b200: hanging nodes are not supported";
-               return DFLO_E_UNSUPPORTED;
+               // a hanging node on this face: the two finer cells behind it, in the order of this cell's line (deal.II's
+               // subface numbering).  MeshWorker integrates such a face from the fine side; the library does the same.
+               out.hanging.push_back ((int32_t) c);
+               out.hanging.push_back ((int32_t) f);
+               for (unsigned int k = 0; k < 2; ++k)
+               {
+                  const typename DoFHandlerType::cell_iterator child = cell->neighbor_child_on_subface (f, k);
+                  out.hanging.push_back ((int32_t) child->user_index ());
+                  out.hanging.push_back ((int32_t) cell->neighbor_of_neighbor (f));
+                  if (k == 0)
+                  {
+                     out.neighbor[4 * c + f] = (int32_t) child->user_index ();
+                     out.neighbor_face[4 * c + f] = (uint8_t) cell->neighbor_of_neighbor (f);
+                  }
+               }
+               out.face_flags[4 * c + f] = DFLO_FACE_HANGING;
+               continue;
+            }
+            if (cell->neighbor_is_coarser (f))
+            {
+               // the fine side: (face, subface) of the coarser neighbour this face is a half of
+               const std::pair<unsigned int, unsigned int> fs = cell->neighbor_of_coarser_neighbor (f);
+               out.neighbor[4 * c + f] = (int32_t) cell->neighbor (f)->user_index ();
+               out.neighbor_face[4 * c + f] = (uint8_t) fs.first;
+               out.face_flags[4 * c + f] = DFLO_FACE_COARSER | DFLO_FACE_OWNER | (fs.second ? DFLO_FACE_CHILD1 : 0);
+               continue;
             }
             const typename DoFHandlerType::cell_iterator nb = cell->neighbor (f);
             out.neighbor[4 * c + f] = (int32_t) nb->user_index ();

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace dealii
@@ -121,6 +122,9 @@ namespace dealii
          }
          bool neighbor_is_coarser (unsigned int) const { return false; }
          unsigned int neighbor_of_neighbor (unsigned int f) const { return f ^ 1u; }
+         // refinement: the mock mesh has none -- these exist so that the adapter's hanging-node branch compiles
+         cell_iterator neighbor_child_on_subface (unsigned int f, unsigned int) const { return neighbor (f); }
+         std::pair<unsigned int, unsigned int> neighbor_of_coarser_neighbor (unsigned int f) const { return std::make_pair (f ^ 1u, 0u); }
          cell_iterator neighbor (unsigned int f) const
          {
             const Triangulation<dim> &t = *dh->tria;
