@@ -628,7 +628,6 @@ namespace dflo
             if (p.basis != DFLO_BASIS_QK || p.limiter_type != DFLO_LIMITER_NONE || p.pos_lim)
                return fail (DFLO_E_UNSUPPORTED, "faces with hanging nodes: Qk basis without limiters only");
             if (!mesh.cell_vertices || !mesh.neighbor_face || !mesh.hanging) return fail (DFLO_E_INVALID, "hanging nodes need cell_vertices, neighbor_face and the hanging table");
-            if (world > 1) return fail (DFLO_E_UNSUPPORTED, "faces with hanging nodes are supported on unsharded contexts only");
          }
          if (p.mapping == DFLO_MAPPING_Q1)
          {

@@ -105,27 +105,27 @@ namespace dflo
       g1.clear ();
       g2.clear ();
       std::vector<char> mark (m.n_cells, 0);
-      for (int c = b; c < e; ++c)
+      // all face neighbours of a cell: `neighbor`, plus the second fine cell behind a face with a hanging node
+      std::vector<int> second (m.n_hanging_faces > 0 ? 4 * (size_t) m.n_cells : 0, -1);
+      for (int h = 0; h < m.n_hanging_faces; ++h) second[4 * (size_t) m.hanging[6 * h] + m.hanging[6 * h + 1]] = m.hanging[6 * h + 4];
+      auto visit = [&] (int c, char layer, std::vector<int> &out) {
          for (int f = 0; f < 4; ++f)
-         {
-            const int nb = m.neighbor[4 * (size_t) c + f];
-            if (nb >= 0 && (nb < b || nb >= e) && !mark[nb])
+            for (int k = 0; k < 2; ++k)
             {
-               mark[nb] = 1;
-               g1.push_back (nb);
-            }
-         }
-      if (layers >= 2)
-         for (int c : g1)
-            for (int f = 0; f < 4; ++f)
-            {
-               const int nb = m.neighbor[4 * (size_t) c + f];
+               const int nb = k == 0 ? m.neighbor[4 * (size_t) c + f] : (second.empty () ? -1 : second[4 * (size_t) c + f]);
                if (nb >= 0 && (nb < b || nb >= e) && !mark[nb])
                {
-                  mark[nb] = 2;
-                  g2.push_back (nb);
+                  mark[nb] = layer;
+                  out.push_back (nb);
                }
             }
+      };
+      for (int c = b; c < e; ++c) visit (c, 1, g1);
+      if (layers >= 2)
+      {
+         const std::vector<int> first (g1);
+         for (int c : first) visit (c, 2, g2);
+      }
       std::sort (g1.begin (), g1.end ()); // contiguous ownership => sorted by (owner, id)
       std::sort (g2.begin (), g2.end ());
    }
@@ -506,11 +506,6 @@ namespace dflo
       }
       if (m.n_hanging_faces > 0)
       {
-         if (world > 1)
-         {
-            err = "faces with hanging nodes are supported on unsharded contexts only";
-            return false;
-         }
          std::vector<int> g2l_all (m.n_cells, -1);
          for (int l = 0; l < L.n_local; ++l) g2l_all[L.l2g[l]] = l;
          L.hang_of.assign (4 * (size_t) L.n_local, -1);
@@ -518,14 +513,22 @@ namespace dflo
          {
             const int *e = m.hanging + 6 * (size_t) h;
             const int lc = g2l_all[e[0]];
-            L.hang_of[4 * (size_t) lc + e[1]] = h;
+            if (lc < 0 || lc >= L.n_compute) continue; // the coarse cell is not updated on this rank
+            L.hang_of[4 * (size_t) lc + e[1]] = (int) (L.hang.size () / 6);
             for (int k = 0; k < 2; ++k)
             {
-               L.hang.push_back (g2l_all[e[2 + 2 * k]]);
+               const int lf = g2l_all[e[2 + 2 * k]];
+               if (lf < 0)
+               {
+                  err = "internal: a fine cell behind a hanging node is outside the halo";
+                  return false;
+               }
+               L.hang.push_back (lf);
                L.hang.push_back (e[3 + 2 * k]);
                L.hang.push_back ((m.face_flags[4 * (size_t) e[2 + 2 * k] + e[3 + 2 * k]] & DFLO_FACE_FLIP) ? 1 : 0);
             }
          }
+         if (L.hang.empty ()) L.hang.assign (6, 0);
       }
       if (row)
       {

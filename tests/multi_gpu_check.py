@@ -20,7 +20,7 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))
 
 from dflo_b200 import abi  # noqa: E402
-from helpers import DMR_BC, PERIODIC_BOX, SOD_BC, ic_dmr, ic_sod, ic_sod_moving, ic_sod_moving_wavy, ic_vortex  # noqa: E402
+from helpers import DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, ic_dmr, ic_sod, ic_sod_moving, ic_sod_moving_wavy, ic_step, ic_vortex  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 CASES = [
@@ -38,6 +38,15 @@ CASES = [
     ("sod_Q2_minmax_pos", ("sod_tube", [100, 10]), SOD_BC, ic_sod_moving_wavy,
      dict(basis="Qk", degree=2, flux="hllc", limiter="minmax", char_lim=True, pos_lim=True, beta=2.0, M=0.0, cfl=0.4),
      (0.3, 0.1, 1.0, 2.5), 3, 1e-9),
+    # BASELINE configs[4] at test size: forward step, three lattice blocks, KFVS, TVB + positivity (2-layer halo, stand-alone exchange)
+    ("step_Q3_kfvs_tvb_pos", ("forward_step", [0.05]), STEP_BC, ic_step,
+     dict(basis="Qk", degree=3, flux="kfvs", limiter="TVB", char_lim=True, pos_lim=True, beta=2.0, M=0.0, cfl=0.5),
+     (4.2, 0.0, 1.4, 8.8), 3, 1e-9),
+    # mapping = q1 on skewed quadrilaterals with mixed cell orientations, and a mesh with hanging nodes: the mapped stage kernel
+    ("q1_Q2_hllc_skew", ("rectangle_skew", [24, 24, -5, 5, -5, 5, 4, 2, 1, 3, 0.15, 1]), PERIODIC_BOX, ic_vortex,
+     dict(basis="Qk", degree=2, flux="hllc", cfl=0.3, mapping="q1", compat="mpi"), None, 3, 1e-12),
+    ("hanging_Q3_roe", ("rectangle_refined", [24, 24, -5, 5, -5, 5, 4, 2, 1, 3, 6, 18, 5, 19]), PERIODIC_BOX, ic_vortex,
+     dict(basis="Qk", degree=3, flux="roe", cfl=0.3, compat="mpi"), None, 3, 1e-12),
 ]
 
 

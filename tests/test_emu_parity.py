@@ -551,7 +551,25 @@ def test_hanging_nodes_refusals():
         assert flat.contents.n_hanging_faces == 8
         with pytest.raises(abi.DfloError):
             abi.Engine(flat, params, lib=emu_lib(), prefix="dflo_emu_")
-    params, pair = abi.make_params(bc={}, flux="lxf", basis="Qk", degree=1)
-    m = abi.Mesh(mesh[0], mesh[1], lib=emu_lib())
-    with pytest.raises(abi.DfloError):   # sharded contexts: not with hanging nodes
-        abi.Engine(m.flatten(params, pair), params, rank=0, world=2, nccl_id=b"\0" * 128, lib=emu_lib(), prefix="dflo_emu_")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_hanging_nodes_sharded_matches_single(world):
+    """Cells by id over the ranks with hanging nodes on (and next to) the cuts: a coarse cell's halo holds BOTH fine cells
+    behind its face; bit for bit the single-rank result."""
+    bc = {1: ("periodic", 3), 3: ("periodic", 1), 2: "slip", 4: "farfield"}
+    ids = (4, 2, 1, 3)
+    args = (("rectangle_refined", [7, 6, -5, 5, -5, 5, *ids, 2, 5, 1, 5]), bc, ic_smooth)
+    prm = dict(basis="Qk", degree=2, flux="hllc", cfl=0.3, compat="mpi")
+    one = Case(*args, **prm)
+    many = Case(*args, world=world, **prm)
+    for c in (one, many):
+        c.set_boundary(values=(1.0, 0.2, 1.4, 8.8))
+    assert np.array_equal(one.rhs_pair()[1], many.rhs_pair()[1])
+    for _ in range(2):
+        one.step()
+        many.step()
+    assert np.array_equal(one.solution(), many.solution())
+    assert many.rel_err() <= TOL_STEP_SMOOTH
+    one.close()
+    many.close()
