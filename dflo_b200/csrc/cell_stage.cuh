@@ -1,22 +1,45 @@
-// Stage kernel for the Pk (orthonormal Legendre) basis, one THREAD per cell.
+// Stage kernel for the Pk (orthonormal Legendre) basis: one THREAD per cell, every face solved ONCE per block.
 //
 // Same fused stage as StageKernel / row_stage_kernel -- assemble_system (cell, face and boundary
 // workers, src/assemble_explicit.cc:30-452), M^-1 (claw.cc:228-258), forward-Euler update, SSP-RK
-// combine (claw.cc:694-713, 757-760), cell average (claw.cc:562-597) -- but organised like the
-// limiter cell kernel: a thread keeps the D = 4 (k+1)(k+2)/2 modal coefficients of its cell and the
-// residual in registers and walks through volume points, faces and update on its own; the basis
-// tables are constant-bank operands of fully unrolled FMA chains.  A block of 128 cells is staged
-// with coalesced loads into shared memory (odd row stride: the per-thread walks are free of bank
-// conflicts), neighbours inside the block are read from there, and the updated cells go back
-// through a second shared buffer with coalesced stores that apply the RK combine on the way.  Every face is evaluated from both sides with the same arguments in the same order (the
-// reference's "plus" side first, MeshWorker owner rule of assemble_explicit.cc:440 / both sides for
-// periodic pairs, src_mpi/assemble_explicit.cc:186-260), so the two cells subtract bit-identical
-// fluxes: conservative to round-off without atomics, and a sharded run equals the single-GPU run
-// bit for bit.  Neighbour coefficients come through L1/L2 (x neighbours are the adjacent threads'
-// cells).  The phase-structured tile kernel (kernels.cuh) stays selectable: DFLO_B200_PK=tile.
+// combine (claw.cc:694-713, 757-760), cell average (claw.cc:562-597).  A block of 128 consecutive
+// cells is staged with coalesced loads into shared memory (odd row stride: the per-thread walks are
+// free of bank conflicts) and goes through five barrier-separated phases:
+//
+//   0  stage the block's cells;
+//   1  thread = cell: its LOW faces (0: left, 2: bottom).  The Pk trace on a face is a polynomial of
+//      degree k in the tangential variable, so the two cells are first reduced to k+1 tangential
+//      coefficients per component (the normal direction summed out with L_i(0) / L_i(1)), the k+1
+//      Riemann problems are posed along +e_x / +e_y exactly like the row kernel's (face_flux_axis: the
+//      reference's "plus" side marked, MeshWorker owner rule of assemble_explicit.cc:440), and the
+//      weighted fluxes are projected back on the tangential Legendre modes: k+1 MOMENTS per component.
+//      They go into the cell's own slot of that face and, when the neighbour is staged by the same
+//      block, into the neighbour's slot of its high face;
+//   2  the high faces (1: right, 3: top) nobody solved -- neighbour outside the block, boundary faces,
+//      periodic pairs (both sides integrate their own problem, src_mpi/assemble_explicit.cc:186-260) --
+//      were pushed on a job list in phase 1 and are solved now, one thread per job, by the same code;
+//   3  thread = cell: volume term (structural zeros of the derivative tables skipped), lifting of the
+//      four moment sets, M^-1 = 1/|K|, Euler step, into the cell's own row in place;
+//   4  RK combine with old_solution and coalesced write-back, cell means.
+//
+// Whoever solves a face gets bit-identical arguments in the same order, and each cell adds volume
+// term and faces 0..3 in a fixed order: conservative to round-off without atomics, and a sharded run
+// equals the single-GPU run bit for bit.  The sum-factorised traces and lifts re-associate the
+// reference's dense i x q loops (round-off level differences; the tests state the tolerance).
 #pragma once
 
 #include "kernels.cuh"
+
+// the compute phases as functions of their own: ptxas allocates registers phase by phase (inlined into one body they
+// cost 248 registers, or spills under the cap)
+#ifndef DFLO_PK_NOINLINE
+#define DFLO_PK_NOINLINE 1
+#endif
+#if defined(__CUDACC__) && DFLO_PK_NOINLINE
+#define DFLO_PHASE_FN __device__ __noinline__
+#else
+#define DFLO_PHASE_FN DFLO_DEV
+#endif
 
 namespace dflo
 {
@@ -39,8 +62,27 @@ namespace dflo
       int n_compute;          // cells updated: owned (+ ghost layer 1 when a limiter follows)
       int n_keep;             // cells >= n_keep are redundantly updated ghost cells: only their means are stored
       int mode, compat_mpi;
+      int pf_blocks;          // L2 prefetch distance in blocks (0: none): the cells of block bid + pf_blocks are requested at block start
       double ark, gravity;
    };
+
+   // The cell kernel lets the block solve an interior face once, from the cell that has it as a LOW face (0, 2), and hands the
+   // moments to the neighbour's face F ^ 1: every interior, non-periodic, unflipped face must be seen as F / F ^ 1 by its two
+   // cells, with the same flags.  True for the conforming Cartesian meshes the reference admits for Pk (parameters.cc:536-550).
+   // (Only pairs of updated cells can share a block.)
+   inline bool pk_cell_mesh_ok (const int *nbr, const unsigned char *fflags, int n_compute)
+   {
+      for (int c = 0; c < n_compute; ++c)
+         for (int f = 0; f < 4; ++f)
+         {
+            const int nb = nbr[4 * (size_t) c + f];
+            if (nb < 0 || nb >= n_compute) continue;
+            const int skip = FACE_PERIODIC | FACE_FLIP;
+            if (fflags[4 * (size_t) c + f] & skip) continue;
+            if (nbr[4 * (size_t) nb + (f ^ 1)] != c || (fflags[4 * (size_t) nb + (f ^ 1)] & skip)) return false;
+         }
+      return true;
+   }
 
 #if !defined(__CUDACC__)
    struct double2 // the CPU emulation's stand-in for the CUDA vector type
@@ -53,34 +95,42 @@ namespace dflo
    __constant__ double c_pk_tab[5][PK_TAB_MAX]; // indexed by N1 = k+1
 #endif
 
+
    template <int N1, int FLUX>
    struct PkCellStageKernel
    {
       typedef CellStageArgs Args;
+      static constexpr int K = N1 - 1;
       static constexpr int NQ = N1 * N1;
       static constexpr int NS = n_scalar (BASIS_PK, N1);
       static constexpr int D = 4 * NS;
 #ifndef DFLO_PK_THREADS
 #define DFLO_PK_THREADS 128
 #endif
-#ifndef DFLO_PK_UNROLL_STAGE
-#define DFLO_PK_UNROLL_STAGE 1
-#endif
 #ifndef DFLO_PK_UB
 #define DFLO_PK_UB 12
 #endif
+#ifndef DFLO_PK_QUNROLL
+#define DFLO_PK_QUNROLL 0 // the face loop over the k+1 Riemann problems stays rolled: measured faster (115 vs 117 us, cfg3) at 2/3 of the code
+#endif
 #ifndef DFLO_PK_MIN_BLOCKS
-#define DFLO_PK_MIN_BLOCKS 1
+#define DFLO_PK_MIN_BLOCKS 3
 #endif
       static constexpr int THREADS = DFLO_PK_THREADS;
       static constexpr int CPB = THREADS;      // cells per block
       static constexpr int MIN_BLOCKS = DFLO_PK_MIN_BLOCKS;
-      static constexpr int NPHASE = 3;
+      static constexpr int NPHASE = 5;
       static constexpr int ROW = D + 1;        // odd row stride
-      static constexpr int SMEM_DOUBLES = 2 * CPB * ROW;
+      static constexpr int NM = 4 * N1;        // moments per face: component x tangential mode
+      // shared memory: rows [CPB][ROW] | moments [4 faces][NM][CPB] (cell fastest) | job list [2 CPB] + 2 counters (ints)
+      static constexpr int O_MOM = CPB * ROW, O_JOB = O_MOM + 4 * NM * CPB;
+      static constexpr int SMEM_DOUBLES = O_JOB + CPB + 1;
       static int grid (int n_compute) { return (n_compute + CPB - 1) / CPB; }
       // Pk: phi[NQ*NS] dphix[NQ*NS] dphiy[NQ*NS] phiface[4*N1*NS] gw[N1]
       static constexpr int O_PHI = 0, O_DPX = NQ * NS, O_DPY = 2 * NQ * NS, O_PF = 3 * NQ * NS, O_GW = 3 * NQ * NS + 4 * N1 * NS;
+
+      // mode (i, j) = L_i(x) L_j(y), i + j <= k, in the order of tables.cc / claw.cc:104-114 (j outer, i inner)
+      static DFLO_DEV constexpr int mode (int i, int j) { return j * (K + 1) - j * (j - 1) / 2 + i; }
 
       static DFLO_DEV double T (const double *tb, int i)
       {
@@ -91,105 +141,212 @@ namespace dflo
          return tb[i];
 #endif
       }
+      // 1-D tables read out of the 2-D ones (L_0 = 1 exactly): L_t at Gauss point q; L_i at the end of face F
+      static DFLO_DEV double LG (const double *tb, int t, int q) { return T (tb, O_PHI + q * NS + mode (t, 0)); }
+      static DFLO_DEV double LE (const double *tb, int F, int i) { return T (tb, O_PF + (F * N1) * NS + (F < 2 ? mode (i, 0) : mode (0, i))); }
 
-      // trace at point q of face f: the fma chain of StageKernel::trace, from registers or from memory
-      static DFLO_DEV void trace_own (const double *tb, const double (&u)[4][NS], int f, int q, double W[4])
+      static DFLO_DEV int bump (int *p)
+      {
+#if defined(__CUDA_ARCH__)
+         return atomicAdd (p, 1);
+#else
+         return (*p)++;
+#endif
+      }
+
+      // tangential coefficients of the trace on face F of the cell whose coefficients are at p: a[c][t]
+      template <int F>
+      static DFLO_DEV void face_coefficients (const double *tb, const double *p, double (&a)[4][N1])
       {
 #pragma unroll
          for (int c = 0; c < 4; ++c)
-         {
-            double s = 0.0;
 #pragma unroll
-            for (int m = 0; m < NS; ++m) s = fma (T (tb, O_PF + (f * N1 + q) * NS + m), u[c][m], s);
-            W[c] = s;
+            for (int t = 0; t < N1; ++t)
+            {
+               // normal index n = 0 .. k - t; L_0 = 1
+               double s = p[c * NS + (F < 2 ? mode (0, t) : mode (t, 0))];
+#pragma unroll
+               for (int n = 1; n < N1; ++n)
+                  if (n + t <= K) s = fma (LE (tb, F, n), p[c * NS + (F < 2 ? mode (n, t) : mode (t, n))], s);
+               a[c][t] = s;
+            }
+      }
+
+      // Face F of `cell` seen from that cell: moments b[c][t] = sum_q w_q |face| H_c(q) L_t(g_q) of the numerical flux H
+      // along +e_x (F < 2) / +e_y; interior, periodic and boundary faces (assemble_explicit.cc:127-427)
+      template <int F>
+      static DFLO_DEV void face_moments (const Args &A, const double *tb, int cell, int c0, int ncb, const double *sm, const double *own,
+                                         double (&b)[4][N1])
+      {
+         const int nb = A.nbr[(size_t) cell * 4 + F];
+         const int fl = A.fflags[(size_t) cell * 4 + F];
+         const double nx = (F == 0) ? -1.0 : (F == 1) ? 1.0 : 0.0;
+         const double ny = (F == 2) ? -1.0 : (F == 3) ? 1.0 : 0.0;
+         const double len = A.geom[(size_t) cell * 4 + (F < 2 ? 3 : 2)];
+         double ao[4][N1], an[4][N1];
+         double Ao[4] = {0.0, 0.0, 0.0, 0.0}, An[4] = {0.0, 0.0, 0.0, 0.0};
+         face_coefficients<F> (tb, own, ao);
+         if (flux_uses_averages (FLUX))
+         {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Ao[c] = A.avg[(size_t) cell * 4 + c];
+         }
+         bool plus = true; // this cell is the "plus" side of the flux call
+         if (nb >= 0)
+         {
+            // a neighbour staged by this block is read from its row (two calls: shared / global loads, no generic ones)
+            if ((unsigned) (nb - c0) < (unsigned) ncb)
+               face_coefficients<(F ^ 1)> (tb, sm + (nb - c0) * ROW, an);
+            else
+               face_coefficients<(F ^ 1)> (tb, A.u + (size_t) nb * D, an);
+            if (fl & FACE_FLIP) // the neighbour's face runs backwards: t -> (-1)^t in the symmetric Gauss points
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+#pragma unroll
+                  for (int t = 1; t < N1; t += 2) an[c][t] = -an[c][t];
+            }
+            if (flux_uses_averages (FLUX))
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c) An[c] = A.avg[(size_t) nb * 4 + c];
+            }
+            plus = (fl & (FACE_OWNER | FACE_PERIODIC)) != 0;
+         }
+#pragma unroll
+         for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int t = 0; t < N1; ++t) b[c][t] = 0.0;
+#if DFLO_PK_QUNROLL
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+         for (int q = 0; q < N1; ++q)
+         {
+            double Wo[4], Wn[4], H[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+               double s = ao[c][0];
+#pragma unroll
+               for (int t = 1; t < N1; ++t) s = fma (LG (tb, t, q), ao[c][t], s);
+               Wo[c] = s;
+            }
+            if (nb >= 0)
+            {
+#pragma unroll
+               for (int c = 0; c < 4; ++c)
+               {
+                  double s = an[c][0];
+#pragma unroll
+                  for (int t = 1; t < N1; ++t) s = fma (LG (tb, t, q), an[c][t], s);
+                  Wn[c] = s;
+               }
+            }
+            else
+            {
+               const int bf = -1 - nb;
+               const int kind = A.bkind[bf];
+               double g[4];
+#pragma unroll
+               for (int c = 0; c < 4; ++c) g[c] = A.bc_g[((size_t) bf * N1 + q) * 4 + c];
+               compute_wminus (kind, nx, ny, Wo, g, Wn);
+               if (flux_uses_averages (FLUX))
+               {
+                  if (A.compat_mpi) // src_mpi/assemble_explicit.cc:296-321
+                     compute_wminus (kind, nx, ny, Ao, g, An);
+                  else // src/assemble_explicit.cc:203-204: own average on both sides
+                  {
+#pragma unroll
+                     for (int c = 0; c < 4; ++c) An[c] = Ao[c];
+                  }
+               }
+            }
+            // the axis-specialised Riemann problem of the row kernel (euler.cuh face_flux_axis): states on the
+            // low / high coordinate side of the face, the reference's plus side marked; H = flux along +e_DIR,
+            // the same bits from whichever of the two cells evaluates it
+            constexpr bool low = (F & 1) != 0; // this cell sits on the low side of its faces 1 and 3
+            face_flux_axis<FLUX, F / 2> (low ? plus : !plus, low ? Wo : Wn, low ? Wn : Wo, low ? Ao : An, low ? An : Ao, H);
+            const double wl = T (tb, O_GW + q) * len;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+               const double h = wl * H[c];
+               b[c][0] += h;
+#pragma unroll
+               for (int t = 1; t < N1; ++t) b[c][t] = fma (h, LG (tb, t, q), b[c][t]);
+            }
          }
       }
 
-      // face F of the cell (0 left, 1 right, 2 bottom, 3 top): interior / periodic face or boundary face
-      template <int F>
-      static DFLO_DEV void face_term (const Args &A, const double *tb, int cell, int c0, int ncb, const double *sm, const double (&u)[4][NS],
-                                      double (&r)[4][NS], const double (&Ao)[4], double hx, double hy)
+      // does the block solve face F (1 or 3) of this cell from the neighbour's side in phase 1?
+      static DFLO_DEV bool covered (const Args &A, int cell, int F, int c0, int ncb)
       {
-            const int nb = A.nbr[(size_t) cell * 4 + F];
-            const int fl = A.fflags[(size_t) cell * 4 + F];
-            const double nx = (F == 0) ? -1.0 : (F == 1) ? 1.0 : 0.0;
-            const double ny = (F == 2) ? -1.0 : (F == 3) ? 1.0 : 0.0;
-            const double len = (F < 2) ? hy : hx;
-            double un[4][NS], An[4] = {0.0, 0.0, 0.0, 0.0};
-            if (nb >= 0)
-            {
-               // a neighbour staged by this block is read from its row
-               const double *pn = ((unsigned) (nb - c0) < (unsigned) ncb) ? sm + (nb - c0) * ROW : A.u + (size_t) nb * D;
-#pragma unroll
-               for (int c = 0; c < 4; ++c)
-#pragma unroll
-                  for (int m = 0; m < NS; ++m) un[c][m] = pn[c * NS + m];
-               if (flux_uses_averages (FLUX))
-               {
-#pragma unroll
-                  for (int c = 0; c < 4; ++c) An[c] = A.avg[(size_t) nb * 4 + c];
-               }
-            }
-#pragma unroll
-            for (int q = 0; q < N1; ++q)
-            {
-               double Wo[4], Wn[4], H[4];
-               trace_own (tb, u, F, q, Wo);
-               bool plus = true; // this cell is the "plus" side of the flux call
-               if (nb >= 0)
-               {
-                  if (fl & FACE_FLIP)
-                     trace_own (tb, un, F ^ 1, N1 - 1 - q, Wn);
-                  else
-                     trace_own (tb, un, F ^ 1, q, Wn);
-                  plus = (fl & (FACE_OWNER | FACE_PERIODIC)) != 0;
-               }
-               else
-               {
-                  const int bf = -1 - nb;
-                  const int kind = A.bkind[bf];
-                  double g[4];
-#pragma unroll
-                  for (int c = 0; c < 4; ++c) g[c] = A.bc_g[((size_t) bf * N1 + q) * 4 + c];
-                  compute_wminus (kind, nx, ny, Wo, g, Wn);
-                  if (flux_uses_averages (FLUX))
-                  {
-                     if (A.compat_mpi) // src_mpi/assemble_explicit.cc:296-321
-                        compute_wminus (kind, nx, ny, Ao, g, An);
-                     else // src/assemble_explicit.cc:203-204: own average on both sides
-                     {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) An[c] = Ao[c];
-                     }
-                  }
-               }
-               // the axis-specialised Riemann problem of the row kernel (euler.cuh face_flux_axis): states on the
-               // low / high coordinate side of the face, the reference's plus side marked; H = flux along +e_DIR,
-               // the same bits from whichever of the two cells evaluates it
-               constexpr bool low = (F & 1) != 0; // this cell sits on the low side of its faces 1 and 3
-               face_flux_axis<FLUX, F / 2> (low ? plus : !plus, low ? Wo : Wn, low ? Wn : Wo, low ? Ao : An, low ? An : Ao, H);
-               const double wl = (low ? 1.0 : -1.0) * (T (tb, O_GW + q) * len);
-#pragma unroll
-               for (int c = 0; c < 4; ++c)
-               {
-                  const double h = wl * H[c];
-#pragma unroll
-                  for (int m = 0; m < NS; ++m) r[c][m] = fma (-h, T (tb, O_PF + (F * N1 + q) * NS + m), r[c][m]);
-               }
-            }
-               }
+         const int nb = A.nbr[(size_t) cell * 4 + F];
+         if (nb < 0 || (unsigned) (nb - c0) >= (unsigned) ncb) return false;
+         // the neighbour sees this cell across its face F ^ 1 with the same flags (checked on the host: pk_cell_mesh_ok)
+         return !(A.fflags[(size_t) cell * 4 + F] & (FACE_PERIODIC | FACE_FLIP));
+      }
 
-      // p = 0: stage the block's cells; 1: one thread per cell, result into the second buffer; 2: RK combine,
-      // coalesced write-back, cell averages
+      static DFLO_DEV void store_moments (double *mom, int F, int lc, const double (&b)[4][N1])
+      {
+#pragma unroll
+         for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int t = 0; t < N1; ++t) mom[((F * 4 + c) * N1 + t) * CPB + lc] = b[c][t];
+      }
+
+      template <int F>
+      static DFLO_PHASE_FN void job_face (const Args &A, int c0, int ncb, int lc, const double *sm, double *mom)
+      {
+         double b[4][N1];
+         face_moments<F> (A, A.tab, c0 + lc, c0, ncb, sm, sm + lc * ROW, b);
+         store_moments (mom, F, lc, b);
+      }
+
+      template <int F>
+      static DFLO_PHASE_FN void low_face (const Args &A, int c0, int ncb, int lc, const double *sm, double *mom)
+      {
+         double b[4][N1];
+         face_moments<F> (A, A.tab, c0 + lc, c0, ncb, sm, sm + lc * ROW, b);
+         store_moments (mom, F, lc, b);
+         const int nb = A.nbr[(size_t) (c0 + lc) * 4 + F];
+         // the neighbour's copy; it uses it only if `covered` says so, otherwise a phase-2 job overwrites it
+         if (nb >= 0 && (unsigned) (nb - c0) < (unsigned) ncb && !(A.fflags[(size_t) (c0 + lc) * 4 + F] & (FACE_PERIODIC | FACE_FLIP)))
+            store_moments (mom, F ^ 1, nb - c0, b);
+      }
+
       static DFLO_DEV void phase (int p, const Args &A, double *sm, int tid, int bid)
       {
          const int c0 = bid * CPB;
          const int ncb = (A.n_compute - c0 < CPB) ? A.n_compute - c0 : CPB;
-         double *smB = sm + CPB * ROW;
+         double *mom = sm + O_MOM;
+         int *jobs = reinterpret_cast<int *> (sm + O_JOB), *cnt = jobs + 2 * CPB;
          if (p == 0)
          {
+            if (tid == 0) cnt[0] = cnt[1] = 0;
             const double *src = A.u + (size_t) c0 * D;
-            if (DFLO_PK_UNROLL_STAGE && ncb == CPB) // full block: 16-byte loads, UB of them in flight per thread
+#if defined(__CUDA_ARCH__)
+            // what the later phases read behind dependent addresses, requested now: old_solution of the block into L2 (one
+            // bulk prefetch), the cell's face tables and the time-step scalar towards L1
+            if (tid == 0 && A.mode == MODE_STAGE && A.ark != 0.0)
+               asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u_old + (size_t) c0 * D), "r"((unsigned) (ncb * D * sizeof (double))) : "memory");
+            if (tid == 32 && A.pf_blocks > 0) // a block that runs on this SM soon: its cells into L2
+            {
+               const int pc0 = (bid + A.pf_blocks) * CPB;
+               if (pc0 + CPB <= A.n_compute)
+                  asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.u + (size_t) pc0 * D), "r"((unsigned) (CPB * D * sizeof (double))) : "memory");
+            }
+            if (tid < ncb)
+            {
+               asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.geom + (size_t) (c0 + tid) * 4));
+               if (tid % 8 == 0) asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.nbr + (size_t) (c0 + tid) * 4));
+               if (tid % 32 == 0) asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.fflags + (size_t) (c0 + tid) * 4));
+               if (tid == 0) asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.time));
+            }
+#endif
+            if (ncb == CPB) // full block: 16-byte loads, UB of them in flight per thread
             {
                constexpr int UB = DFLO_PK_UB, NV = D / 2; // D is even: NV double2 per cell, CPB * NV in the block
                const double2 *s2 = reinterpret_cast<const double2 *> (src);
@@ -213,17 +370,54 @@ namespace dflo
             }
             else
                for (int i = tid; i < ncb * D; i += THREADS) sm[(i / D) * ROW + (i % D)] = src[i];
+#if defined(__CUDA_ARCH__)
+            // neighbours outside the block: pull their coefficients towards L1, the face phases read them
+            if (tid < ncb)
+            {
+               const int4 nb4 = *reinterpret_cast<const int4 *> (A.nbr + (size_t) (c0 + tid) * 4);
+               const int nbs[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+#pragma unroll
+               for (int f = 0; f < 4; ++f)
+                  if (nbs[f] >= 0 && (unsigned) (nbs[f] - c0) >= (unsigned) ncb)
+                  {
+                     const char *pn = reinterpret_cast<const char *> (A.u + (size_t) nbs[f] * D);
+#pragma unroll
+                     for (int b = 0; b < D * 8; b += 128) asm volatile ("prefetch.global.L1 [%0];" ::"l"(pn + b));
+                     if ((D * 8) % 128 != 0) asm volatile ("prefetch.global.L1 [%0];" ::"l"(pn + D * 8 - 8));
+                  }
+            }
+#endif
          }
          else if (p == 1)
          {
-            if (tid < ncb) cell_work (A, c0, ncb, tid, sm, smB + tid * ROW);
+            if (tid >= ncb) return;
+            // high faces nobody else solves: F = 1 jobs from the front of the list, F = 3 jobs from its back
+            if (!covered (A, c0 + tid, 1, c0, ncb)) jobs[bump (cnt)] = tid;
+            if (!covered (A, c0 + tid, 3, c0, ncb)) jobs[2 * CPB - 1 - bump (cnt + 1)] = tid;
+            low_face<0> (A, c0, ncb, tid, sm, mom);
+            low_face<2> (A, c0, ncb, tid, sm, mom);
+         }
+         else if (p == 2)
+         {
+            const int n1 = cnt[0], n1r = (n1 + 31) & ~31, n3 = cnt[1]; // warps do not mix the two kinds
+            for (int k = tid; k < n1r + n3; k += THREADS)
+            {
+               if (k < n1)
+                  job_face<1> (A, c0, ncb, jobs[k], sm, mom);
+               else if (k >= n1r)
+                  job_face<3> (A, c0, ncb, jobs[2 * CPB - 1 - (k - n1r)], sm, mom);
+            }
+         }
+         else if (p == 3)
+         {
+            if (tid < ncb) cell_work (A, c0, tid, sm + tid * ROW, mom);
          }
          else
          {
             const bool combine = A.mode == MODE_STAGE && A.ark != 0.0;
             const double *uo = A.u_old + (size_t) c0 * D;
             double *dst = A.out + (size_t) c0 * D;
-            if (DFLO_PK_UNROLL_STAGE && ncb == CPB && combine) // full block: 16-byte accesses, UB old_solution loads in flight
+            if (ncb == CPB && combine) // full block: 16-byte accesses, UB old_solution loads in flight
             {
                constexpr int UB = DFLO_PK_UB, NV = D / 2;
                const double2 *o2 = reinterpret_cast<const double2 *> (uo);
@@ -242,8 +436,8 @@ namespace dflo
                         const int i = 2 * (tid + (k0 + k) * THREADS);
                         const int lc = i / D, kk = i % D; // kk even: both entries belong to the same cell
                         double2 v;
-                        v.x = (1.0 - A.ark) * smB[lc * ROW + kk] + A.ark * w[k].x; // claw.cc:757-760
-                        v.y = (1.0 - A.ark) * smB[lc * ROW + kk + 1] + A.ark * w[k].y;
+                        v.x = (1.0 - A.ark) * sm[lc * ROW + kk] + A.ark * w[k].x; // claw.cc:757-760
+                        v.y = (1.0 - A.ark) * sm[lc * ROW + kk + 1] + A.ark * w[k].y;
                         if (c0 + lc < A.n_keep) d2[tid + (k0 + k) * THREADS] = v;
                         if (kk % NS == 0) A.avg_out[(size_t) (c0 + lc) * 4 + kk / NS] = v.x;
                         if ((kk + 1) % NS == 0) A.avg_out[(size_t) (c0 + lc) * 4 + (kk + 1) / NS] = v.y;
@@ -254,7 +448,7 @@ namespace dflo
                for (int i = tid; i < ncb * D; i += THREADS)
                {
                   const int lc = i / D, k = i % D;
-                  double v = smB[lc * ROW + k];
+                  double v = sm[lc * ROW + k];
                   if (combine) v = (1.0 - A.ark) * v + A.ark * uo[i]; // claw.cc:757-760
                   // cells >= n_keep: redundantly updated ghost cells, only their means are kept
                   if (A.mode == MODE_RHS || c0 + lc < A.n_keep) dst[i] = v;
@@ -263,39 +457,46 @@ namespace dflo
          }
       }
 
-      // residual and Euler update of cell c0 + lc; res = its row of the second buffer
-      static DFLO_DEV void cell_work (const Args &A, int c0, int ncb, int lc, const double *sm, double *res)
+      // r -= (outward flux through face F) tested with the basis: lifting of the moments
+      template <int F>
+      static DFLO_DEV void lift (const double *tb, const double *mom, int lc, double (&r)[4][NS])
+      {
+#pragma unroll
+         for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int t = 0; t < N1; ++t)
+            {
+               const double bt = mom[((F * 4 + c) * N1 + t) * CPB + lc];
+               const double sb = (F & 1) ? -bt : bt; // outward normal = +e on the high faces
+#pragma unroll
+               for (int n = 0; n < N1; ++n)
+                  if (n + t <= K)
+                  {
+                     const int m = F < 2 ? mode (n, t) : mode (t, n);
+                     if (n == 0)
+                        r[c][m] += sb;
+                     else
+                        r[c][m] = fma (sb, LE (tb, F, n), r[c][m]);
+                  }
+            }
+      }
+
+      // volume term, lifting and Euler update of cell c0 + lc; row = its coefficients, replaced by the result
+      static DFLO_PHASE_FN void cell_work (const Args &A, int c0, int lc, double *row, const double *mom)
       {
          const int cell = c0 + lc;
          const double *tb = A.tab;
          const double hx = A.geom[(size_t) cell * 4 + 2], hy = A.geom[(size_t) cell * 4 + 3];
-#if defined(__CUDA_ARCH__)
-         // neighbours outside the block: pull their coefficients towards L1 now, they are read after the volume term
-#pragma unroll
-         for (int f = 0; f < 4; ++f)
-         {
-            const int nb = A.nbr[(size_t) cell * 4 + f];
-            if (nb >= 0 && (unsigned) (nb - c0) >= (unsigned) ncb)
-            {
-               const char *pn = reinterpret_cast<const char *> (A.u + (size_t) nb * D);
-#pragma unroll
-               for (int b = 0; b < D * 8; b += 128) asm volatile ("prefetch.global.L1 [%0];" ::"l"(pn + b));
-               if ((D * 8) % 128 != 0) asm volatile ("prefetch.global.L1 [%0];" ::"l"(pn + D * 8 - 8));
-            }
-         }
-#endif
+         const double dt = A.mode == MODE_RHS ? 0.0 : A.dt_cell ? A.dt_cell[cell] : A.time[1];
          double u[4][NS], r[4][NS];
-         {
-            const double *uc = sm + lc * ROW;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+         for (int c = 0; c < 4; ++c)
 #pragma unroll
-               for (int m = 0; m < NS; ++m)
-               {
-                  u[c][m] = uc[c * NS + m];
-                  r[c][m] = 0.0;
-               }
-         }
+            for (int m = 0; m < NS; ++m)
+            {
+               u[c][m] = row[c * NS + m];
+               r[c][m] = 0.0;
+            }
 
          // ---- cell term, assemble_explicit.cc:30-120: rhs_i += sum_q F(W_q).grad(phi_i) JxW (+ forcing) ----
 #pragma unroll
@@ -305,9 +506,9 @@ namespace dflo
 #pragma unroll
             for (int c = 0; c < 4; ++c)
             {
-               double s = 0.0;
+               double s = u[c][0]; // phi_0 = 1
 #pragma unroll
-               for (int m = 0; m < NS; ++m) s = fma (T (tb, O_PHI + q * NS + m), u[c][m], s);
+               for (int m = 1; m < NS; ++m) s = fma (T (tb, O_PHI + q * NS + m), u[c][m], s);
                W[c] = s;
             }
             flux_matrix (W, Fx, Fy);
@@ -318,7 +519,15 @@ namespace dflo
             {
                const double ax = wx * Fx[c], ay = wy * Fy[c];
 #pragma unroll
-               for (int m = 0; m < NS; ++m) r[c][m] = fma (ax, T (tb, O_DPX + q * NS + m), fma (ay, T (tb, O_DPY + q * NS + m), r[c][m]));
+               for (int j = 0; j < N1; ++j)
+#pragma unroll
+                  for (int i = 0; i < N1; ++i)
+                     if (i + j <= K) // d/dx of L_0(x) L_j(y) and d/dy of L_i(x) L_0(y) vanish
+                     {
+                        const int m = mode (i, j);
+                        if (i > 0) r[c][m] = fma (ax, T (tb, O_DPX + q * NS + m), r[c][m]);
+                        if (j > 0) r[c][m] = fma (ay, T (tb, O_DPY + q * NS + m), r[c][m]);
+                     }
             }
             if (A.gravity != 0.0) // assemble_explicit.cc:78, 108-111
             {
@@ -339,16 +548,10 @@ namespace dflo
          }
 
          // ---- face and boundary terms, assemble_explicit.cc:127-427 ----
-         double Ao[4] = {0.0, 0.0, 0.0, 0.0};
-         if (flux_uses_averages (FLUX))
-         {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) Ao[c] = A.avg[(size_t) cell * 4 + c];
-         }
-         face_term<0> (A, tb, cell, c0, ncb, sm, u, r, Ao, hx, hy);
-         face_term<1> (A, tb, cell, c0, ncb, sm, u, r, Ao, hx, hy);
-         face_term<2> (A, tb, cell, c0, ncb, sm, u, r, Ao, hx, hy);
-         face_term<3> (A, tb, cell, c0, ncb, sm, u, r, Ao, hx, hy);
+         lift<0> (tb, mom, lc, r);
+         lift<1> (tb, mom, lc, r);
+         lift<2> (tb, mom, lc, r);
+         lift<3> (tb, mom, lc, r);
 
          // ---- M^-1 (orthonormal modes: 1/|K|, claw.cc:228-258) and Euler step (claw.cc:694-713); MODE_RHS: the residual ----
          if (A.mode == MODE_RHS)
@@ -356,15 +559,14 @@ namespace dflo
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
-               for (int m = 0; m < NS; ++m) res[c * NS + m] = r[c][m];
+               for (int m = 0; m < NS; ++m) row[c * NS + m] = r[c][m];
             return;
          }
          const double invm = 1.0 / (hx * hy);
-         const double dt = A.dt_cell ? A.dt_cell[cell] : A.time[1];
 #pragma unroll
          for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int m = 0; m < NS; ++m) res[c * NS + m] = u[c][m] + dt * r[c][m] * invm;
+            for (int m = 0; m < NS; ++m) row[c * NS + m] = u[c][m] + dt * r[c][m] * invm;
       }
    };
 }

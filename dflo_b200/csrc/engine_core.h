@@ -564,6 +564,7 @@ namespace dflo
       FaceJob *d_jobs = nullptr;
       TileDesc *d_tiles = nullptr;
       unsigned char *d_fflags = nullptr;
+      bool pk_cell_ok = false; // the mesh admits the thread-per-cell Pk stage kernel (cell_stage.cuh: pk_cell_mesh_ok)
       double *d_ext_force = nullptr; // [n_local][n_q][2], allocated by set_external_force
       int *d_hang_of = nullptr, *d_hang = nullptr; // faces with hanging nodes (LocalMesh::hang_of, hang)
       double *d_dt_cell = nullptr; // [n_local] dt(cell) of time step type = local
@@ -722,6 +723,7 @@ namespace dflo
             d_tiles = upload (td);
          }
          d_fflags = upload (lm.fflags);
+         pk_cell_ok = tab.basis == BASIS_PK && pk_cell_mesh_ok (lm.nbr.data (), lm.fflags.data (), lm.n_compute);
          d_geom = upload (lm.geom);
          d_l2g = upload (lm.l2g);
          if (hanging)
@@ -1177,7 +1179,7 @@ namespace dflo
             launch_mapped_stage (bk, tab.n1, prm.flux_type, m);
             return;
          }
-         if (tab.basis == BASIS_PK && tab.n1 >= 2 && tab.n1 <= 3 && bk.use_pk_cell_kernel ())
+         if (tab.basis == BASIS_PK && tab.n1 >= 2 && tab.n1 <= 3 && bk.use_pk_cell_kernel () && pk_cell_ok)
          {
             CellStageArgs c;
             c.u = a.u;
@@ -1200,6 +1202,7 @@ namespace dflo
             c.compat_mpi = a.compat_mpi;
             c.ark = a.ark;
             c.gravity = a.gravity;
+            c.pf_blocks = bk.stage_prefetch_tiles () > 0 ? bk.n_sms () : 0;
             bk.note_cell_stage ();
             launch_cell_stage (bk, tab.n1, prm.flux_type, c);
             return;

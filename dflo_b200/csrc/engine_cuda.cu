@@ -358,6 +358,7 @@ namespace
       // tile kernel instead), Pk degree 1-2 the thread-per-cell kernel (cell_stage.cuh), mapping = q1 the mapped kernel.
       // What is left for the generic tile kernel (P3, degree 0) runs in its pipelined persistent form (one producer
       // warp streaming tiles through two shared-memory stages) unless DFLO_B200_PERSISTENT=0.
+      int n_sms () const { return n_sm; }
       int stage_prefetch_tiles () const
       {
          static const char *e = std::getenv ("DFLO_B200_PF_TILES");

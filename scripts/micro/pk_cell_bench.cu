@@ -4,7 +4,11 @@
 // compared without rebuilding the library.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I dflo_b200/csrc scripts/micro/pk_cell_bench.cu \
 //        dflo_b200/csrc/tables.cc -o scripts/micro/pk_cell_bench
+#ifdef PK_V1
+#include "cell_stage_v1.cuh"
+#else
 #include "cell_stage.cuh"
+#endif
 #include "tables.h"
 #include "tables_pack.h"
 
@@ -19,9 +23,16 @@ typedef PkCellStageKernel<3, FLUX_HLLC> K;
 __global__ void __launch_bounds__ (K::THREADS, K::MIN_BLOCKS) bench_kernel (const CellStageArgs a)
 {
    extern __shared__ __align__ (16) double smem[];
+#ifdef PK_NOUNROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
    for (int p = 0; p < K::NPHASE; ++p)
    {
+#ifdef PK_PHASE_MASK
+      if (!((PK_PHASE_MASK >> p) & 1)) continue;
+#endif
       K::phase (p, a, smem, threadIdx.x, blockIdx.x);
       if (p + 1 < K::NPHASE) __syncthreads ();
    }
@@ -32,7 +43,9 @@ __global__ void __launch_bounds__ (K::THREADS, K::MIN_BLOCKS) bench_kernel (cons
 int main (int argc, char **argv)
 {
    const int nx = argc > 1 ? atoi (argv[1]) : 1600, ny = argc > 2 ? atoi (argv[2]) : 160, reps = 20;
+   const int TX = argc > 3 ? atoi (argv[3]) : nx, TY = argc > 4 ? atoi (argv[4]) : 1; // cell order: TX x TY tiles (default: row-major)
    const int nc = nx * ny, D = K::D;
+   auto id = [&] (int i, int j) { return ((j / TY) * (nx / TX) + i / TX) * TX * TY + (j % TY) * TX + i % TX; };
    FeTables tab;
    if (!build_tables (BASIS_PK, 2, tab)) return 1;
    std::vector<double> flat = pack_stage_tables (tab);
@@ -43,7 +56,7 @@ int main (int argc, char **argv)
    for (int j = 0; j < ny; ++j)
       for (int i = 0; i < nx; ++i)
       {
-         const int c = j * nx + i;
+         const int c = id (i, j);
          const double x = (i + 0.5) / nx, y = (j + 0.5) / ny;
          const double rho = 1.0 + 0.2 * sin (6.28 * x) * cos (6.28 * y), vx = 0.3, vy = 0.1, p = 1.0 + 0.1 * cos (6.28 * x);
          u[(size_t) c * D + 0 * K::NS] = rho * vx;
@@ -55,10 +68,10 @@ int main (int argc, char **argv)
          geom[4 * c + 1] = (double) j / ny;
          geom[4 * c + 2] = 1.0 / nx;
          geom[4 * c + 3] = 1.0 / ny;
-         nbr[4 * c + 0] = j * nx + (i + nx - 1) % nx;
-         nbr[4 * c + 1] = j * nx + (i + 1) % nx;
-         nbr[4 * c + 2] = ((j + ny - 1) % ny) * nx + i;
-         nbr[4 * c + 3] = ((j + 1) % ny) * nx + i;
+         nbr[4 * c + 0] = id ((i + nx - 1) % nx, j);
+         nbr[4 * c + 1] = id ((i + 1) % nx, j);
+         nbr[4 * c + 2] = id (i, (j + ny - 1) % ny);
+         nbr[4 * c + 3] = id (i, (j + 1) % ny);
          ff[4 * c + 0] = ff[4 * c + 2] = 0;
          ff[4 * c + 1] = ff[4 * c + 3] = FACE_OWNER;
       }
@@ -78,7 +91,7 @@ int main (int argc, char **argv)
    CellStageArgs a;
    a.u = d_u; a.u_old = d_uo; a.out = d_out; a.avg = d_avg; a.avg_out = d_avgo; a.nbr = d_nbr; a.fflags = d_ff; a.geom = d_geom;
    a.bc_g = nullptr; a.bkind = nullptr; a.tab = d_tab; a.time = d_time; a.dt_cell = nullptr; a.ext_force = nullptr;
-   a.n_compute = nc; a.n_keep = nc; a.mode = MODE_STAGE; a.compat_mpi = 0; a.ark = 0.75; a.gravity = 0.0;
+   a.n_compute = nc; a.n_keep = nc; a.mode = MODE_STAGE; a.compat_mpi = 0; a.ark = 0.75; a.gravity = 0.0; a.pf_blocks = argc > 5 ? atoi (argv[5]) : 148;
    const size_t smem = K::SMEM_DOUBLES * sizeof (double);
    CK (cudaFuncSetAttribute (bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
    int occ = 0;
@@ -100,8 +113,10 @@ int main (int argc, char **argv)
    CK (cudaGetLastError ());
    std::vector<double> out ((size_t) nc * D);
    CK (cudaMemcpy (out.data (), d_out, nb, cudaMemcpyDeviceToHost));
-   double cs = 0.0;
-   for (double v : out) cs += v;
-   printf ("cells %d threads %d blocks/SM %d smem %zu: %.1f us per launch, checksum %.15e\n", nc, K::THREADS, occ, smem, 1e3 * total / reps, cs);
+   double cs = 0.0; // order-independent check value: cells visited in lattice order
+   for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i)
+         for (int k = 0; k < D; ++k) cs += out[(size_t) id (i, j) * D + k] * (1.0 + 0.001 * ((i * 7 + j * 13 + k) % 17));
+   printf ("cells %d tiles %dx%d threads %d blocks/SM %d smem %zu: %.1f us per launch, checksum %.15e\n", nc, TX, TY, K::THREADS, occ, smem, 1e3 * total / reps, cs);
    return 0;
 }

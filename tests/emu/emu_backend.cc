@@ -75,6 +75,7 @@ namespace
       bool use_pk_cell_kernel () const { const char *e = std::getenv ("DFLO_EMU_PK"); return e && std::string (e) == "cell"; }
       void note_cell_stage () { ++cell_stage_launches (); }
       int stage_prefetch_tiles () const { return 0; }
+      int n_sms () const { return 1; }
       int debug_flags () const { return 0; }
       bool limiter_block_form () const { static const char *e = std::getenv ("DFLO_EMU_LIMITER"); return e && std::string (e) == "block"; }
       // peer-memory halo exists only on the CUDA backend
