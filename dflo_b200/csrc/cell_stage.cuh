@@ -84,12 +84,6 @@ namespace dflo
       return true;
    }
 
-#if !defined(__CUDACC__)
-   struct double2 // the CPU emulation's stand-in for the CUDA vector type
-   {
-      double x, y;
-   };
-#endif
    constexpr int PK_TAB_MAX = stage_table_size (BASIS_PK, 4);
 #if defined(__CUDACC__)
    __constant__ double c_pk_tab[5][PK_TAB_MAX]; // indexed by N1 = k+1

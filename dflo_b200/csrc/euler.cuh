@@ -755,15 +755,16 @@ namespace dflo
    DFLO_HD void compute_eigen_matrix (const double W[4], EigenMatrices &m)
    {
       const double g1 = GM1;
-      const double rho = W[RHO], E = W[ENE];
-      const double u = W[0] / rho, v = W[1] / rho;
+      const double rho = W[RHO], E = W[ENE], ir = fast_rcp (rho); // reciprocals: see compute_eigen_left
+      const double u = W[0] * ir, v = W[1] * ir;
       const double q2 = u * u + v * v;
       const double p = g1 * (E - 0.5 * rho * q2);
-      const double c2 = GAMMA * p / rho;
-      const double c = sqrt (c2);
-      const double beta = 0.5 / c2;
+      const double c2 = GAMMA * p * ir;
+      const double c = fast_sqrt (c2);
+      const double ic2 = fast_rcp (c2);
+      const double beta = 0.5 * ic2;
       const double phi2 = 0.5 * g1 * q2;
-      const double h = c2 / g1 + 0.5 * q2;
+      const double h = c2 * (1.0 / g1) + 0.5 * q2;
 
       m.Rx[0][0] = 1;        m.Rx[0][1] = 0;   m.Rx[0][2] = 1;         m.Rx[0][3] = 1;
       m.Rx[1][0] = u;        m.Rx[1][1] = 0;   m.Rx[1][2] = u + c;     m.Rx[1][3] = u - c;
@@ -775,12 +776,12 @@ namespace dflo
       m.Ry[2][0] = v;        m.Ry[2][1] = 0;   m.Ry[2][2] = v + c;     m.Ry[2][3] = v - c;
       m.Ry[3][0] = 0.5 * q2; m.Ry[3][1] = u;   m.Ry[3][2] = h + c * v; m.Ry[3][3] = h - c * v;
 
-      m.Lx[0][0] = 1 - phi2 / c2;         m.Lx[0][1] = g1 * u / c2;          m.Lx[0][2] = g1 * v / c2;    m.Lx[0][3] = -g1 / c2;
+      m.Lx[0][0] = 1 - phi2 * ic2;        m.Lx[0][1] = g1 * u * ic2;         m.Lx[0][2] = g1 * v * ic2;   m.Lx[0][3] = -g1 * ic2;
       m.Lx[1][0] = v;                     m.Lx[1][1] = 0;                    m.Lx[1][2] = -1;             m.Lx[1][3] = 0;
       m.Lx[2][0] = beta * (phi2 - c * u); m.Lx[2][1] = beta * (c - g1 * u);  m.Lx[2][2] = -beta * g1 * v; m.Lx[2][3] = beta * g1;
       m.Lx[3][0] = beta * (phi2 + c * u); m.Lx[3][1] = -beta * (c + g1 * u); m.Lx[3][2] = -beta * g1 * v; m.Lx[3][3] = beta * g1;
 
-      m.Ly[0][0] = 1 - phi2 / c2;         m.Ly[0][1] = g1 * u / c2;    m.Ly[0][2] = g1 * v / c2;          m.Ly[0][3] = -g1 / c2;
+      m.Ly[0][0] = 1 - phi2 * ic2;        m.Ly[0][1] = g1 * u * ic2;   m.Ly[0][2] = g1 * v * ic2;         m.Ly[0][3] = -g1 * ic2;
       m.Ly[1][0] = -u;                    m.Ly[1][1] = 1;              m.Ly[1][2] = 0;                    m.Ly[1][3] = 0;
       m.Ly[2][0] = beta * (phi2 - c * v); m.Ly[2][1] = -beta * g1 * u; m.Ly[2][2] = beta * (c - g1 * v);  m.Ly[2][3] = beta * g1;
       m.Ly[3][0] = beta * (phi2 + c * v); m.Ly[3][1] = -beta * g1 * u; m.Ly[3][2] = -beta * (c + g1 * v); m.Ly[3][3] = beta * g1;
@@ -799,21 +800,24 @@ namespace dflo
    DFLO_HD void compute_eigen_left (const double W[4], EigenLeft &m)
    {
       const double g1 = GM1;
-      const double rho = W[RHO], E = W[ENE];
-      const double u = W[0] / rho, v = W[1] / rho;
+      // one reciprocal of the density and one of c^2 instead of the reference's eleven divisions (the device has no
+      // fp64 divider: each IEEE quotient is a ~20-instruction sequence)
+      const double rho = W[RHO], E = W[ENE], ir = fast_rcp (rho);
+      const double u = W[0] * ir, v = W[1] * ir;
       const double q2 = u * u + v * v;
       const double p = g1 * (E - 0.5 * rho * q2);
-      const double c2 = GAMMA * p / rho;
-      const double c = sqrt (c2);
-      const double beta = 0.5 / c2;
+      const double c2 = GAMMA * p * ir;
+      const double c = fast_sqrt (c2);
+      const double ic2 = fast_rcp (c2);
+      const double beta = 0.5 * ic2;
       const double phi2 = 0.5 * g1 * q2;
 
-      m.Lx[0][0] = 1 - phi2 / c2;         m.Lx[0][1] = g1 * u / c2;          m.Lx[0][2] = g1 * v / c2;    m.Lx[0][3] = -g1 / c2;
+      m.Lx[0][0] = 1 - phi2 * ic2;        m.Lx[0][1] = g1 * u * ic2;         m.Lx[0][2] = g1 * v * ic2;   m.Lx[0][3] = -g1 * ic2;
       m.Lx[1][0] = v;                     m.Lx[1][1] = 0;                    m.Lx[1][2] = -1;             m.Lx[1][3] = 0;
       m.Lx[2][0] = beta * (phi2 - c * u); m.Lx[2][1] = beta * (c - g1 * u);  m.Lx[2][2] = -beta * g1 * v; m.Lx[2][3] = beta * g1;
       m.Lx[3][0] = beta * (phi2 + c * u); m.Lx[3][1] = -beta * (c + g1 * u); m.Lx[3][2] = -beta * g1 * v; m.Lx[3][3] = beta * g1;
 
-      m.Ly[0][0] = 1 - phi2 / c2;         m.Ly[0][1] = g1 * u / c2;    m.Ly[0][2] = g1 * v / c2;          m.Ly[0][3] = -g1 / c2;
+      m.Ly[0][0] = 1 - phi2 * ic2;        m.Ly[0][1] = g1 * u * ic2;   m.Ly[0][2] = g1 * v * ic2;         m.Ly[0][3] = -g1 * ic2;
       m.Ly[1][0] = -u;                    m.Ly[1][1] = 1;              m.Ly[1][2] = 0;                    m.Ly[1][3] = 0;
       m.Ly[2][0] = beta * (phi2 - c * v); m.Ly[2][1] = -beta * g1 * u; m.Ly[2][2] = beta * (c - g1 * v);  m.Ly[2][3] = beta * g1;
       m.Ly[3][0] = beta * (phi2 + c * v); m.Ly[3][1] = -beta * g1 * u; m.Ly[3][2] = -beta * (c + g1 * v); m.Ly[3][3] = beta * g1;
@@ -821,13 +825,13 @@ namespace dflo
    DFLO_HD void compute_eigen_right (const double W[4], EigenRight &m)
    {
       const double g1 = GM1;
-      const double rho = W[RHO], E = W[ENE];
-      const double u = W[0] / rho, v = W[1] / rho;
+      const double rho = W[RHO], E = W[ENE], ir = fast_rcp (rho);
+      const double u = W[0] * ir, v = W[1] * ir;
       const double q2 = u * u + v * v;
       const double p = g1 * (E - 0.5 * rho * q2);
-      const double c2 = GAMMA * p / rho;
-      const double c = sqrt (c2);
-      const double h = c2 / g1 + 0.5 * q2;
+      const double c2 = GAMMA * p * ir;
+      const double c = fast_sqrt (c2);
+      const double h = c2 * (1.0 / g1) + 0.5 * q2;
 
       m.Rx[0][0] = 1;        m.Rx[0][1] = 0;   m.Rx[0][2] = 1;         m.Rx[0][3] = 1;
       m.Rx[1][0] = u;        m.Rx[1][1] = 0;   m.Rx[1][2] = u + c;     m.Rx[1][3] = u - c;
@@ -851,15 +855,16 @@ namespace dflo
    DFLO_HD void compute_eigen_stream (const double W[4], EigenStream &m)
    {
       const double g1 = GM1;
-      const double rho = W[RHO], E = W[ENE];
-      const double u = W[0] / rho, v = W[1] / rho;
+      const double rho = W[RHO], E = W[ENE], ir = fast_rcp (rho); // reciprocals: see compute_eigen_left
+      const double u = W[0] * ir, v = W[1] * ir;
       const double q2 = u * u + v * v;
       const double p = g1 * (E - 0.5 * rho * q2);
-      const double c2 = GAMMA * p / rho;
-      const double c = sqrt (c2);
-      const double beta = 0.5 / c2;
+      const double c2 = GAMMA * p * ir;
+      const double c = fast_sqrt (c2);
+      const double ic2 = fast_rcp (c2);
+      const double beta = 0.5 * ic2;
       const double phi2 = 0.5 * g1 * q2;
-      const double h = c2 / g1 + 0.5 * q2;
+      const double h = c2 * (1.0 / g1) + 0.5 * q2;
       const double q = sqrt (q2);
       const double kx = (q > 0.0) ? u / q : 1.0, ky = (q > 0.0) ? v / q : 0.0;
       const double uk = u * kx + v * ky;

@@ -33,6 +33,12 @@
 
 namespace dflo
 {
+#if !defined(__CUDACC__)
+   struct double2 // the CPU emulation's stand-in for the CUDA vector type
+   {
+      double x, y;
+   };
+#endif
    enum { FACE_OWNER = 1, FACE_PERIODIC = 2, FACE_FLIP = 4, JOB_SHARED = 8 };
    enum { MODE_STAGE = 0, MODE_RHS = 1 };
    enum { ERR_NEGATIVE_STATE = 1, ERR_POSLIM_ROOT = 2 };
@@ -1233,7 +1239,48 @@ namespace dflo
          if (p == 0)
          {
             const double *src = A.u + (size_t) c0 * D;
-            for (int i = tid; i < ncb * D; i += THREADS) sm[(i / D) * ROW + (i % D)] = src[i];
+#if defined(__CUDA_ARCH__)
+            // what the cell walk reads behind dependent addresses: towards L1 now
+            if (tid < ncb)
+            {
+               asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.geom + (size_t) (c0 + tid) * 4));
+               asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.avg + (size_t) (c0 + tid) * 4));
+            }
+#endif
+            if (ncb == CPB) // full block: 16-byte loads, all of a round in flight
+            {
+               constexpr int NV = D / 2, UB = NV < 16 ? NV : 16; // D is even: NV double2 per cell, CPB * NV in the block
+               const double2 *s2 = reinterpret_cast<const double2 *> (src);
+#pragma unroll
+               for (int k0 = 0; k0 < NV; k0 += UB)
+               {
+                  double2 v[UB];
+#pragma unroll
+                  for (int k = 0; k < UB; ++k)
+                     if (k0 + k < NV) v[k] = s2[tid + (k0 + k) * THREADS];
+#pragma unroll
+                  for (int k = 0; k < UB; ++k)
+                     if (k0 + k < NV)
+                     {
+                        const int i = 2 * (tid + (k0 + k) * THREADS);
+                        double *d = sm + (i / D) * ROW + (i % D);
+                        d[0] = v[k].x;
+                        d[1] = v[k].y;
+                     }
+               }
+            }
+            else
+               for (int i = tid; i < ncb * D; i += THREADS) sm[(i / D) * ROW + (i % D)] = src[i];
+#if defined(__CUDA_ARCH__)
+            if (tid < ncb && A.tvb) // the neighbours' means
+            {
+               const int4 nb4 = *reinterpret_cast<const int4 *> (A.nbr + (size_t) (c0 + tid) * 4);
+               if (nb4.x >= 0) asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.avg + (size_t) nb4.x * 4));
+               if (nb4.y >= 0) asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.avg + (size_t) nb4.y * 4));
+               if (nb4.z >= 0) asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.avg + (size_t) nb4.z * 4));
+               if (nb4.w >= 0) asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.avg + (size_t) nb4.w * 4));
+            }
+#endif
          }
          else if (tid < ncb)
          {
@@ -1572,12 +1619,12 @@ namespace dflo
                }
                else
                {
-                  const double *pp = LK::t_phipos (tb);
+                  const double *cmax = tb + LK::TAB; // max |phi_m| over the positivity points (pack_limiter_tables)
                   double spread[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
                   for (int m = 1; m < NS; ++m)
                   {
-                     double cm = 0.0;
-                     for (int i = 0; i < 2 * NPOS; ++i) cm = std_max (cm, fabs (pp[i * NS + m]));
+                     const double cm = cmax[m];
 #pragma unroll
                      for (int c = 0; c < 4; ++c) spread[c] += cm * fabs (uc[c * NS + m]);
                   }

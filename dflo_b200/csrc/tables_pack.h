@@ -5,6 +5,8 @@
 
 #include "tables.h"
 
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 namespace dflo
@@ -54,7 +56,7 @@ namespace dflo
       return o;
    }
 
-   // Qk: gw[N1] gx[N1] gdiff[N1] gl_interp[NGLL*N1];  Pk: phipos[2][NPOS][NS]
+   // Qk: gw[N1] gx[N1] gdiff[N1] gl_interp[NGLL*N1];  Pk: phipos[2][NPOS][NS] | cmax[NS]
    inline std::vector<double> pack_limiter_tables (const FeTables &t)
    {
       std::vector<double> o;
@@ -72,6 +74,15 @@ namespace dflo
          for (int s = 0; s < 2; ++s)
             for (int p = 0; p < t.npos; ++p)
                for (int m = 0; m < t.ns; ++m) o.push_back (t.phipos[s][p][m]);
+         // behind the limiter_table_size doubles the block form copies: max |basis function| over the positivity points, per
+         // mode (the rigorous bound of the cell limiter's fast path)
+         for (int m = 0; m < t.ns; ++m)
+         {
+            double cm = 0.0;
+            for (int s = 0; s < 2; ++s)
+               for (int p = 0; p < t.npos; ++p) cm = std::max (cm, std::fabs (t.phipos[s][p][m]));
+            o.push_back (cm);
+         }
       }
       if (o.empty ()) o.push_back (0.0);
       return o;
