@@ -411,7 +411,7 @@ namespace dflo
             const bool combine = A.mode == MODE_STAGE && A.ark != 0.0;
             const double *uo = A.u_old + (size_t) c0 * D;
             double *dst = A.out + (size_t) c0 * D;
-            if (ncb == CPB && combine) // full block: 16-byte accesses, UB old_solution loads in flight
+            if (ncb == CPB && A.mode == MODE_STAGE) // full block: 16-byte accesses, UB old_solution loads in flight
             {
                constexpr int UB = DFLO_PK_UB, NV = D / 2;
                const double2 *o2 = reinterpret_cast<const double2 *> (uo);
@@ -422,7 +422,7 @@ namespace dflo
                   double2 w[UB];
 #pragma unroll
                   for (int k = 0; k < UB; ++k)
-                     if (k0 + k < NV) w[k] = o2[tid + (k0 + k) * THREADS];
+                     if (combine && k0 + k < NV) w[k] = o2[tid + (k0 + k) * THREADS];
 #pragma unroll
                   for (int k = 0; k < UB; ++k)
                      if (k0 + k < NV)
@@ -430,8 +430,13 @@ namespace dflo
                         const int i = 2 * (tid + (k0 + k) * THREADS);
                         const int lc = i / D, kk = i % D; // kk even: both entries belong to the same cell
                         double2 v;
-                        v.x = (1.0 - A.ark) * sm[lc * ROW + kk] + A.ark * w[k].x; // claw.cc:757-760
-                        v.y = (1.0 - A.ark) * sm[lc * ROW + kk + 1] + A.ark * w[k].y;
+                        v.x = sm[lc * ROW + kk];
+                        v.y = sm[lc * ROW + kk + 1];
+                        if (combine) // claw.cc:757-760
+                        {
+                           v.x = (1.0 - A.ark) * v.x + A.ark * w[k].x;
+                           v.y = (1.0 - A.ark) * v.y + A.ark * w[k].y;
+                        }
                         if (c0 + lc < A.n_keep) d2[tid + (k0 + k) * THREADS] = v;
                         if (kk % NS == 0) A.avg_out[(size_t) (c0 + lc) * 4 + kk / NS] = v.x;
                         if ((kk + 1) % NS == 0) A.avg_out[(size_t) (c0 + lc) * 4 + (kk + 1) / NS] = v.y;

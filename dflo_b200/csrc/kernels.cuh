@@ -1225,7 +1225,10 @@ namespace dflo
 #ifndef DFLO_LIM_P2_BLOCKS
 #define DFLO_LIM_P2_BLOCKS 3
 #endif
-      static constexpr int MIN_BLOCKS = (BASIS == BASIS_PK && N1 == 3 && MINMAX == 0) ? DFLO_LIM_P2_BLOCKS : D <= 40 ? 4 : 1;
+#ifndef DFLO_LIM_Q3_BLOCKS
+#define DFLO_LIM_Q3_BLOCKS 3
+#endif
+      static constexpr int MIN_BLOCKS = (BASIS == BASIS_PK && N1 == 3 && MINMAX == 0) ? DFLO_LIM_P2_BLOCKS : D <= 40 ? 4 : D <= 64 ? DFLO_LIM_Q3_BLOCKS : 1;
       static constexpr int NPHASE = 2;
       static constexpr int ROW = D + 1;
       static constexpr int SMEM_DOUBLES = CPB * ROW;
@@ -1246,6 +1249,20 @@ namespace dflo
                asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.geom + (size_t) (c0 + tid) * 4));
                asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.avg + (size_t) (c0 + tid) * 4));
             }
+#endif
+#if defined(__CUDA_ARCH__)
+            // up to Q2 / P3: asynchronous 8-byte copies straight into the padded rows (the odd row stride rules out wider
+            // ones), the whole block in flight at once, no staging registers.  They allocate in L1; with the 66 KB blocks
+            // of Q3 too little of it is left beside the shared memory (measured: 205 us instead of 110 on cfg5), so the
+            // larger cells go through registers
+            if (D <= 40)
+            {
+               const unsigned smb = (unsigned) __cvta_generic_to_shared (sm);
+#pragma unroll 8
+               for (int i = tid; i < ncb * D; i += THREADS)
+                  asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smb + 8u * (unsigned) ((i / D) * ROW + (i % D))), "l"(src + i) : "memory");
+            }
+            else
 #endif
             if (ncb == CPB) // full block: 16-byte loads, all of a round in flight
             {
@@ -1280,6 +1297,7 @@ namespace dflo
                if (nb4.z >= 0) asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.avg + (size_t) nb4.z * 4));
                if (nb4.w >= 0) asm volatile ("prefetch.global.L1 [%0];" ::"l"(A.avg + (size_t) nb4.w * 4));
             }
+            asm volatile ("cp.async.wait_all;" ::: "memory");
 #endif
          }
          else if (tid < ncb)
@@ -1405,6 +1423,16 @@ namespace dflo
          return 1;
       }
 
+      // range of the nodal values for the positivity fast path.  (Tracking only max |value| for the momentum components
+      // would save a quarter of these -- a std_min / std_max pair costs as much as five fp64 multiply-adds -- but the
+      // bound |m| <= (wp - wm) max|m| it leads to is too loose for supersonic flow, where the kinetic energy is most of
+      // E: on cfg5 every cell then fell through to the exact evaluation, 205 us instead of 110.)
+      static DFLO_DEV void track (int c, double u, double (&lo)[4], double (&hi)[4])
+      {
+         lo[c] = std_min (lo[c], u);
+         hi[c] = std_max (hi[c], u);
+      }
+
       // all limiter steps of one cell on its DoFs uc (in place); returns true if they changed
       static DFLO_DEV bool cell_work (const Args &A, int cell, double *uc)
       {
@@ -1445,11 +1473,7 @@ namespace dflo
                         const double u = uc[c * NS + a + N1 * b];
                         sx += (gd[a] * gw[b]) * u;
                         sy += (gw[a] * gd[b]) * u;
-                        if (A.pos_lim)
-                        {
-                           lo[c] = std_min (lo[c], u);
-                           hi[c] = std_max (hi[c], u);
-                        }
+                        if (A.pos_lim) track (c, u, lo, hi);
                      }
                   Dx[c] = dx * (sx / hx);
                   Dy[c] = dx * (sy / hy);
@@ -1548,8 +1572,12 @@ namespace dflo
                         {
                            const double v = av[c] + dr0 * Dxn[c] + dr1 * Dyn[c];
                            uc[c * NS + a + N1 * b] = v;
-                           lo[c] = (a + b == 0) ? v : std_min (lo[c], v);
-                           hi[c] = (a + b == 0) ? v : std_max (hi[c], v);
+                           if (a + b == 0)
+                           {
+                              lo[c] = 1.0e300;
+                              hi[c] = -1.0e300;
+                           }
+                           track (c, v, lo, hi);
                         }
                      }
                }
@@ -1592,9 +1620,7 @@ namespace dflo
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                         {
-                           const double u = uc[c * NS + m];
-                           lo[c] = std_min (lo[c], u);
-                           hi[c] = std_max (hi[c], u);
+                           track (c, uc[c * NS + m], lo, hi);
                         }
                   const double *gli = LK::t_gli (tb);
                   double wp = 1.0, wm = 0.0; // the Gauss direction of a point set is the identity

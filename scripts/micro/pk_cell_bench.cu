@@ -91,7 +91,7 @@ int main (int argc, char **argv)
    CellStageArgs a;
    a.u = d_u; a.u_old = d_uo; a.out = d_out; a.avg = d_avg; a.avg_out = d_avgo; a.nbr = d_nbr; a.fflags = d_ff; a.geom = d_geom;
    a.bc_g = nullptr; a.bkind = nullptr; a.tab = d_tab; a.time = d_time; a.dt_cell = nullptr; a.ext_force = nullptr;
-   a.n_compute = nc; a.n_keep = nc; a.mode = MODE_STAGE; a.compat_mpi = 0; a.ark = 0.75; a.gravity = 0.0; a.pf_blocks = argc > 5 ? atoi (argv[5]) : 148;
+   a.n_compute = nc; a.n_keep = nc; a.mode = MODE_STAGE; a.compat_mpi = 0; a.ark = 0.75; a.gravity = 0.0; a.pf_blocks = argc > 5 ? atoi (argv[5]) : 148; if (argc > 6) a.ark = atof (argv[6]);
    const size_t smem = K::SMEM_DOUBLES * sizeof (double);
    CK (cudaFuncSetAttribute (bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
    int occ = 0;
