@@ -1218,7 +1218,10 @@ namespace dflo
       // block form: CPB cells are staged with coalesced loads into shared memory (odd row stride:
       // the per-thread walks over a cell are then free of bank conflicts), one thread per cell
       // works on its row, changed cells are written back
-      static constexpr int THREADS = D > 64 ? 64 : 128;
+#ifndef DFLO_LIM_Q3_THREADS
+#define DFLO_LIM_Q3_THREADS 64
+#endif
+      static constexpr int THREADS = D > 64 ? 64 : D == 64 ? DFLO_LIM_Q3_THREADS : 128;
       static constexpr int CPB = THREADS;
       // up to Q2 / P3 four blocks fit the shared memory of an SM: hold the compiler to 128 registers for them -- except
       // the P2 TVB + positivity chain (cfg3), which spills 528 bytes at 128 registers: three blocks, 168 registers
@@ -1228,7 +1231,7 @@ namespace dflo
 #ifndef DFLO_LIM_Q3_BLOCKS
 #define DFLO_LIM_Q3_BLOCKS 3
 #endif
-      static constexpr int MIN_BLOCKS = (BASIS == BASIS_PK && N1 == 3 && MINMAX == 0) ? DFLO_LIM_P2_BLOCKS : D <= 40 ? 4 : D <= 64 ? DFLO_LIM_Q3_BLOCKS : 1;
+      static constexpr int MIN_BLOCKS = (BASIS == BASIS_PK && N1 == 3 && MINMAX == 0) ? DFLO_LIM_P2_BLOCKS : D <= 40 ? 4 : D <= 64 ? DFLO_LIM_Q3_BLOCKS * (128 / DFLO_LIM_Q3_THREADS) : 1;
       static constexpr int NPHASE = 2;
       static constexpr int ROW = D + 1;
       static constexpr int SMEM_DOUBLES = CPB * ROW;
