@@ -84,7 +84,12 @@ namespace dflo
       static constexpr int NQ = N1 * N1, D = 4 * NQ;
       static constexpr int CPB = NQ >= 128 ? 1 : 128 / NQ;          // cells per block
       static constexpr int THREADS = (CPB * NQ + 31) / 32 * 32;
-      static constexpr int MIN_BLOCKS = 2;
+#ifndef DFLO_MAPPED_MIN_BLOCKS
+#define DFLO_MAPPED_MIN_BLOCKS 4
+#endif
+      // 128 registers: the sub-face branches of the hanging-node faces had let the allocation grow to 196 (2 blocks, 8 warps
+      // per SM), although most launches never take them
+      static constexpr int MIN_BLOCKS = DFLO_MAPPED_MIN_BLOCKS;
       static constexpr int NPHASE = 4;
       static constexpr int NTAB = N1 * N1 + 3 * N1;
       static constexpr int O_TAB = 0;
@@ -187,22 +192,25 @@ namespace dflo
                const int f = j / (2 * N1), half = (j / N1) & 1, p = j % N1;
                const int fl = A.fflags[(size_t) cell * 4 + f];
                if (half && !(fl & DFLO_FACE_HANGING)) continue;
+               // The branches only gather the two states, the normal and the weight; ONE Riemann solve follows (five inlined
+               // copies of it cost the kernel 84 registers).  swap: the other cell is the one that integrates the face -- its
+               // problem, posed with its normal, is evaluated with the same bits and this cell takes minus the flux.
                double Wp[4], Wm[4], Ap[4], Am[4], H[4];
-               double w;
+               double nx, ny, len;
+               bool swap = false;
+               int pw = p; // Gauss weight of the point
                if (flux_uses_averages (FLUX))
                {
 #pragma unroll
-                  for (int c = 0; c < 4; ++c) Ap[c] = A.avg[(size_t) cell * 4 + c];
+                  for (int c = 0; c < 4; ++c) Ap[c] = Am[c] = A.avg[(size_t) cell * 4 + c];
                }
                if (fl & DFLO_FACE_HANGING)
                {
                   // coarse side of a face with a hanging node: the fine cell behind this half is the one that integrates
-                  // (MeshWorker); its Riemann problem -- its normal, its face points, its JxW -- is evaluated here
-                  // with the same bits, and this cell takes minus the flux
+                  // (MeshWorker); its Riemann problem -- its normal, its face points, its JxW
                   const int *hg = A.hang + 6 * (size_t) A.hang_of[(size_t) cell * 4 + f] + 3 * half;
                   const int fine = hg[0], nf = hg[1];
                   const int pf = hg[2] ? N1 - 1 - p : p; // the fine side's number of this point
-                  double nx, ny, len;
                   q1_face (A.verts + (size_t) fine * 8, nf, nx, ny, len);
                   trace (tb, A.u + (size_t) fine * D, nf, pf, Wm);
                   subtrace (tb, S, uc, f, half, p, Wp);
@@ -211,73 +219,62 @@ namespace dflo
 #pragma unroll
                      for (int c = 0; c < 4; ++c) Am[c] = A.avg[(size_t) fine * 4 + c];
                   }
-                  numerical_flux<FLUX> (nx, ny, Wm, Wp, Am, Ap, H);
-#pragma unroll
-                  for (int c = 0; c < 4; ++c) H[c] = -H[c];
-                  w = gw[pf] * len;
+                  swap = true;
+                  pw = pf;
                }
                else
                {
-               double nx, ny, len;
-               q1_face (v, f, nx, ny, len);
-               trace (tb, uc, f, p, Wp);
-               const int nb = A.nbr[(size_t) cell * 4 + f];
-               if (nb >= 0 && (fl & DFLO_FACE_COARSER))
-               {
-                  // fine side: the neighbour is coarser; its trace on this half of its face, at this cell's points
-                  const int nf = A.nbr_face[(size_t) cell * 4 + f];
-                  const int pc = (fl & DFLO_FACE_FLIP) ? N1 - 1 - p : p;
-                  subtrace (tb, S, A.u + (size_t) nb * D, nf, (fl & DFLO_FACE_CHILD1) ? 1 : 0, pc, Wm);
-                  if (flux_uses_averages (FLUX))
+                  q1_face (v, f, nx, ny, len);
+                  trace (tb, uc, f, p, Wp);
+                  const int nb = A.nbr[(size_t) cell * 4 + f];
+                  if (nb >= 0)
                   {
-#pragma unroll
-                     for (int c = 0; c < 4; ++c) Am[c] = A.avg[(size_t) nb * 4 + c];
-                  }
-                  numerical_flux<FLUX> (nx, ny, Wp, Wm, Ap, Am, H);
-               }
-               else if (nb >= 0)
-               {
-                  const int nf = A.nbr_face[(size_t) cell * 4 + f];
-                  const int pn = (fl & DFLO_FACE_FLIP) ? N1 - 1 - p : p;
-                  trace (tb, A.u + (size_t) nb * D, nf, pn, Wm);
-                  if (flux_uses_averages (FLUX))
-                  {
-#pragma unroll
-                     for (int c = 0; c < 4; ++c) Am[c] = A.avg[(size_t) nb * 4 + c];
-                  }
-                  if (fl & (DFLO_FACE_OWNER | DFLO_FACE_PERIODIC))
-                     numerical_flux<FLUX> (nx, ny, Wp, Wm, Ap, Am, H);
-                  else
-                  {
-                     // the owner's Riemann problem, its normal = -(nx, ny); the flux out of this cell is minus the owner's
-                     numerical_flux<FLUX> (-nx, -ny, Wm, Wp, Am, Ap, H);
-#pragma unroll
-                     for (int c = 0; c < 4; ++c) H[c] = -H[c];
-                  }
-               }
-               else
-               {
-                  // boundary: W- from the boundary condition (assemble_explicit.cc:176-206)
-                  const int bf = -1 - nb;
-                  const int kind = A.bkind[bf];
-                  double g[4];
-#pragma unroll
-                  for (int c = 0; c < 4; ++c) g[c] = A.bc_g[((size_t) bf * N1 + p) * 4 + c];
-                  compute_wminus (kind, nx, ny, Wp, g, Wm);
-                  if (flux_uses_averages (FLUX))
-                  {
-                     if (A.compat_mpi)
-                        compute_wminus (kind, nx, ny, Ap, g, Am);
+                     const int nf = A.nbr_face[(size_t) cell * 4 + f];
+                     const int pn = (fl & DFLO_FACE_FLIP) ? N1 - 1 - p : p;
+                     if (fl & DFLO_FACE_COARSER) // fine side: the neighbour's trace on this half of its face, at this cell's points
+                        subtrace (tb, S, A.u + (size_t) nb * D, nf, (fl & DFLO_FACE_CHILD1) ? 1 : 0, pn, Wm);
                      else
                      {
+                        trace (tb, A.u + (size_t) nb * D, nf, pn, Wm);
+                        if (!(fl & (DFLO_FACE_OWNER | DFLO_FACE_PERIODIC)))
+                        {
+                           // the owner's Riemann problem, its normal = -(nx, ny)
+                           swap = true;
+                           nx = -nx;
+                           ny = -ny;
+                        }
+                     }
+                     if (flux_uses_averages (FLUX))
+                     {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) Am[c] = Ap[c];
+                        for (int c = 0; c < 4; ++c) Am[c] = A.avg[(size_t) nb * 4 + c];
                      }
                   }
-                  numerical_flux<FLUX> (nx, ny, Wp, Wm, Ap, Am, H);
+                  else
+                  {
+                     // boundary: W- from the boundary condition (assemble_explicit.cc:176-206)
+                     const int bf = -1 - nb;
+                     const int kind = A.bkind[bf];
+                     double g[4];
+#pragma unroll
+                     for (int c = 0; c < 4; ++c) g[c] = A.bc_g[((size_t) bf * N1 + p) * 4 + c];
+                     compute_wminus (kind, nx, ny, Wp, g, Wm);
+                     if (flux_uses_averages (FLUX) && A.compat_mpi) compute_wminus (kind, nx, ny, Ap, g, Am); // else: own average on both sides
+                  }
                }
-               w = gw[p] * len; // fe_v.JxW(q) on a straight face
+               {
+                  double P[4], M[4], AP[4], AM[4];
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                  {
+                     P[c] = swap ? Wm[c] : Wp[c];
+                     M[c] = swap ? Wp[c] : Wm[c];
+                     AP[c] = swap ? Am[c] : Ap[c];
+                     AM[c] = swap ? Ap[c] : Am[c];
+                  }
+                  numerical_flux<FLUX> (nx, ny, P, M, AP, AM, H);
                }
+               const double w = (swap ? -1.0 : 1.0) * (gw[pw] * len); // fe_v.JxW(q) on a straight face
                double *h = sH + (((slot * 4 + f) * 2 + half) * N1 + p) * 4;
 #pragma unroll
                for (int c = 0; c < 4; ++c) h[c] = w * H[c];
