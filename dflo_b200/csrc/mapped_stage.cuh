@@ -85,10 +85,11 @@ namespace dflo
       static constexpr int CPB = NQ >= 128 ? 1 : 128 / NQ;          // cells per block
       static constexpr int THREADS = (CPB * NQ + 31) / 32 * 32;
 #ifndef DFLO_MAPPED_MIN_BLOCKS
-#define DFLO_MAPPED_MIN_BLOCKS 4
+#define DFLO_MAPPED_MIN_BLOCKS 6
 #endif
-      // 128 registers: the sub-face branches of the hanging-node faces had let the allocation grow to 196 (2 blocks, 8 warps
-      // per SM), although most launches never take them
+      // 85 registers, 24 warps per SM.  Left alone the allocation had grown to 196 registers with the sub-face branches of the
+      // hanging-node faces (2 blocks, 8 warps per SM), although most launches never take them.  Measured on the 256 x 256 Q3
+      // skewed mesh, ms per step: 2 blocks 0.715, 4 blocks 0.427, 6 blocks 0.374 (a few bytes of spills), 8 blocks 0.398
       static constexpr int MIN_BLOCKS = DFLO_MAPPED_MIN_BLOCKS;
       static constexpr int NPHASE = 4;
       static constexpr int NTAB = N1 * N1 + 3 * N1;
