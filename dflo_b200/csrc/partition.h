@@ -55,7 +55,7 @@ namespace dflo
       std::vector<double> geom;  // [n_local][4] x0 y0 hx hy
       std::vector<double> verts; // [n_local][8] cell vertices (mapping = q1; empty otherwise)
       std::vector<unsigned char> nbr_face; // [n_local][4] the neighbour's local number of the shared face (mapping = q1)
-      // faces with a hanging node (unsharded contexts only): hang_of[cell*4+f] = index or -1; per face
+      // faces with a hanging node: hang_of[cell*4+f] = index or -1; per face
       // { fine cell 0, its face, runs backwards?, fine cell 1, its face, runs backwards? } in local cell numbers
       std::vector<int> hang_of, hang;
       std::vector<int> bf_global, bf_id; // local boundary faces (of the computed cells) -> global bface, boundary id
