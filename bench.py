@@ -327,6 +327,43 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+class near_gpu_cores:
+    """Context manager: bind the calling process to the CPU cores NVML lists as local to GPU `index` (the NUMA node its PCIe
+    root hangs on), so that memory first touched inside -- the pinned staging buffers -- lands there; restores the previous
+    affinity on exit.  Does nothing when NVML or the affinity call is unavailable, or the mask is empty in this cpuset."""
+
+    def __init__(self, index):
+        self.index, self.old = index, None
+
+    def __enter__(self):
+        try:
+            if os.environ.get("DFLO_BENCH_NUMA", "1") == "0":
+                return self
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            if cpus & allowed and (cpus & allowed) != allowed:
+                self.old = allowed
+                os.sched_setaffinity(0, cpus & allowed)
+        except Exception:                                    # noqa: BLE001 -- a placement hint, never an error
+            self.old = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.old is not None:
+            try:
+                os.sched_setaffinity(0, self.old)
+            except OSError:
+                pass
+        return False
+
+
 def e2e_entry(updates_per_step, steps, serial_s, pipe_s, n_ctx, owned_dof):
     serial = updates_per_step * steps / serial_s / 1e6
     what = "set_solution(pinned host) + advance(1 step) + get_solution(pinned host) per step"
@@ -586,7 +623,11 @@ def main():
     eng = abi.Engine(flat, params, device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
     D, n_rk = eng.D, eng.n_rk
     n_dof = nx * ny * D
-    u_host = torch.empty(n_dof, dtype=torch.float64, pin_memory=True)
+    # the pinned host buffer of the e2e leg on the NUMA node of this rank's GPU (first touch with the rank bound to the
+    # cores NVML reports as near the device; the binding is dropped again: the CPU legs use every core)
+    with near_gpu_cores(local_rank):
+        u_host = torch.empty(n_dof, dtype=torch.float64, pin_memory=True)
+        u_host.numpy()[:] = 0.0
     u_host.numpy()[:] = initial_dofs(nx, ny, x0, x1, y0, y1, k)
     u_np = u_host.numpy()
     eng.set_solution(u_np)
@@ -658,7 +699,8 @@ def main():
     if world == 1 and E2E_CTX > 1:
         try:
             engs = [eng] + [abi.Engine(flat, params, device=local_rank) for _ in range(E2E_CTX - 1)]
-            bufs = [u_host] + [torch.empty(n_dof, dtype=torch.float64, pin_memory=True) for _ in range(E2E_CTX - 1)]
+            with near_gpu_cores(local_rank):
+                bufs = [u_host] + [torch.empty(n_dof, dtype=torch.float64, pin_memory=True) for _ in range(E2E_CTX - 1)]
             for b_ in bufs[1:]:
                 b_.copy_(u_host)
             gate, errs, ends = threading.Barrier(E2E_CTX + 1), [], [0.0] * E2E_CTX

@@ -139,6 +139,8 @@ void dflo_emu_halo_put_recv (dflo_emu_ctx *c, int peer, const double *in)
    c->eng.bk.recv_plan.erase (peer);
 }
 int64_t dflo_emu_cell_stage_launches (void) { return EmuBackend::cell_stage_launches (); }
+// the host check that admits the thread-per-cell Pk stage kernel (cell_stage.cuh)
+int dflo_emu_pk_cell_mesh_ok (const int *nbr, const unsigned char *fflags, int n_compute) { return dflo::pk_cell_mesh_ok (nbr, fflags, n_compute) ? 1 : 0; }
 int dflo_emu_n_peers (dflo_emu_ctx *c) { return c->eng.lm.peers.size (); }
 int dflo_emu_peer_rank (dflo_emu_ctx *c, int i) { return c->eng.lm.peers[i].rank; }
 int dflo_emu_n_local (dflo_emu_ctx *c) { return c->eng.lm.n_local; }

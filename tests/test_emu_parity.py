@@ -286,6 +286,33 @@ def test_pk_cell_kernel_rhs_and_step_periodic(pk_cell_kernel, k, flux):
     c.close()
 
 
+def test_pk_cell_kernel_mesh_check():
+    """pk_cell_mesh_ok (cell_stage.cuh): the cell kernel hands the moments of a face to the neighbour's face F ^ 1, so it
+    is only admitted when every interior face is seen as F / F ^ 1 with equal flags by its two (updated) cells; otherwise
+    the engine keeps the tile kernel."""
+    L = emu_lib()
+    i32, u8 = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_ubyte)
+    L.dflo_emu_pk_cell_mesh_ok.argtypes = [i32, u8, ctypes.c_int]
+
+    def ok(nbr, fl, n=None):
+        nbr, fl = np.ascontiguousarray(nbr, dtype=np.int32), np.ascontiguousarray(fl, dtype=np.uint8)
+        return bool(L.dflo_emu_pk_cell_mesh_ok(nbr.ctypes.data_as(i32), fl.ctypes.data_as(u8), len(nbr) if n is None else n))
+
+    # two cells side by side: cell 0's right face (1) is cell 1's left face (0); boundary faces elsewhere
+    nbr = [[-1, 1, -2, -3], [0, -4, -5, -6]]
+    fl = [[0, 1, 0, 0], [0, 0, 0, 0]]
+    assert ok(nbr, fl)
+    # the neighbour sees the face as its face 2 (a rotated cell): not admitted
+    assert not ok([[-1, 1, -2, -3], [-4, -5, 0, -6]], fl)
+    # a flipped or periodic pair is solved from both sides and needs no counterpart
+    for flag in (2, 4):
+        assert ok([[-1, 1, -2, -3], [-4, -5, 0, -6]], [[0, flag, 0, 0], [0, 0, flag, 0]])
+    # flags that differ between the two sides: not admitted
+    assert not ok(nbr, [[0, 1, 0, 0], [4, 0, 0, 0]])
+    # only updated cells matter: with n_compute = 1 the rotated neighbour is a ghost cell outside every block
+    assert ok([[-1, 1, -2, -3], [-4, -5, 0, -6]], fl, n=1)
+
+
 @pytest.mark.parametrize("compat", ["src", "mpi"])
 def test_pk_cell_kernel_boundaries_gravity_external_force(pk_cell_kernel, compat):
     bc = {1: "inflow", 2: "slip", 3: "pressure", 0: "farfield"}
