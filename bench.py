@@ -278,6 +278,30 @@ def cpu_baseline(workload, budget_s=15.0, threads=None):
             "sample_cells": n * n, "sample_steps": steps, "wall_s": dt}
 
 
+def b0_single_thread(workload="cfg1", budget_s=3.0):
+    """the serial CPU port (one thread) on the reference's own CPU-runnable case at its
+    shipped size -- configs[0], 32 x 32 cells."""
+    from oracle import oracle as O
+    desc, basis, k, flux, npg = WORKLOADS[workload]
+    variant = _oracle_variant()
+    p = O.make_params(basis=basis, degree=k, flux=flux, bc=PERIODIC, cfl=0.9, n_threads=1)
+    o = O.Oracle(*O.rect_mesh(npg, npg, -5, 5, -5, 5), p, variant=variant)
+    xq = o.cell_qpoints()
+    o.set_initial_condition(isentropic_vortex(xq[..., 0], xq[..., 1]))
+    o.compute_cell_average()
+    t0 = time.perf_counter()
+    o.run_steps(2)
+    per_step = (time.perf_counter() - t0) / 2
+    steps = max(2, int(budget_s / max(per_step, 1e-6)))
+    t0 = time.perf_counter()
+    o.run_steps(steps)
+    dt = time.perf_counter() - t0
+    return {"value": npg * npg * o.D * o.n_rk * steps / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+            "physics": O.load(variant).phys_impl_name().decode(),
+            "sample": "%d steps of %s at its shipped size (%dx%d cells), %.1f s wall, one thread" % (steps, desc.split(",")[0], npg, npg, dt),
+            "sample_cells": npg * npg, "sample_steps": steps, "wall_s": dt}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -821,6 +845,8 @@ def main():
                 e = config_entry(L, key, args.config_steps, 5, flush, peak, torch)
                 if not args.no_cpu_baseline:
                     e["linf_vs_ref"], e["cpu_baseline"] = parity_leg(key, CONFIGS[key][2], args.parity_steps, threads)
+                    if key == "cfg1":
+                        e["cpu_baseline_1_thread"] = b0_single_thread("cfg1")
                 cfgs.append(e)
             if "q1" in args.next_rows.split(","):
                 cfgs.append(q1_entry(args.config_steps, 5, flush, peak, torch, args.parity_steps, threads, not args.no_cpu_baseline))
