@@ -632,10 +632,11 @@ namespace dflo
          }
          if (p.mapping == DFLO_MAPPING_Q1)
          {
-            // src/parameters.cc:545-549: TVB and Pk need Cartesian grids; the positivity limiter on mapped cells is not covered
+            // src/parameters.cc:545-549: TVB and Pk need Cartesian grids.  The positivity limiter runs on mapped cells as it is:
+            // positivity.cc:46-47 evaluates the solution at GLL x Gauss points of the UNIT cell (FEValues with update_values
+            // only) and scales about cell_average, which compute_cell_average took with the mapped JxW (claw.cc:562-597)
             if (p.basis != DFLO_BASIS_QK) return fail (DFLO_E_UNSUPPORTED, "mapping = q1: Pk basis can only be used with Cartesian grids");
             if (p.limiter_type != DFLO_LIMITER_NONE) return fail (DFLO_E_UNSUPPORTED, "mapping = q1: TVB limiter works on cartesian grids only");
-            if (p.pos_lim) return fail (DFLO_E_UNSUPPORTED, "mapping = q1: the positivity limiter is not supported on mapped cells");
             if (!mesh.cell_vertices || !mesh.neighbor_face) return fail (DFLO_E_INVALID, "mapping = q1 needs cell_vertices and neighbor_face in the flat mesh");
          }
          else

@@ -316,11 +316,6 @@ namespace dflo
             err = "only 'mapping = cartesian' and 'mapping = q1' run on the B200 engine; got " + mapping;
             return false;
          }
-         if (mapping == "q1" && pos_lim)
-         {
-            err = "mapping = q1: the positivity limiter is not supported on mapped cells by the B200 engine";
-            return false;
-         }
          if (time_step_type == "local" && !(cfl > 0.0))
          {
             err = "time step type = local needs a cfl";

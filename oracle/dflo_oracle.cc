@@ -1539,10 +1539,11 @@ oracle_ctx *oracle_create (int nv, const double *V, int nc, const int *C, int nb
          }
       o->dtq.init (fe, x, y, w);
    }
-   if (o->q1 () && (prm->basis != ORACLE_BASIS_QK || prm->limiter_type != ORACLE_LIMITER_NONE || prm->pos_lim))
+   if (o->q1 () && (prm->basis != ORACLE_BASIS_QK || prm->limiter_type != ORACLE_LIMITER_NONE))
    {
-      // parameters.cc:545-549: TVB and Pk need Cartesian grids; the positivity limiter on mapped cells is not restated
-      g_error = "mapping = q1: Qk basis without limiters only";
+      // parameters.cc:545-549: TVB and Pk need Cartesian grids.  The positivity limiter (positivity.cc) works on unit-cell
+      // point values and the mapped cell average, so it needs nothing beyond what apply_positivity_limiter does
+      g_error = "mapping = q1: Qk basis without the TVB limiter only";
       delete o;
       return nullptr;
    }

@@ -104,6 +104,21 @@ def ic_pulse(x, y):
     return np.stack([0 * x, 0 * x, rho, p / 0.4], axis=-1)
 
 
+def ic_pulse_box(x, y):
+    """a hot dense pulse in a cold thin background on the [-5, 5]^2 box"""
+    r2 = (x - 0.7) ** 2 + (y + 0.4) ** 2
+    rho = 0.01 + np.exp(-r2 / 0.5)
+    p = 0.004 + 20 * np.exp(-r2 / 0.5)
+    return np.stack([0 * x, 0 * x, rho, p / 0.4], axis=-1)
+
+
+def ic_disc_box(x, y):
+    """a dense disc with a sharp edge in uniform pressure and velocity: the Qk interpolant undershoots at the GLL points"""
+    r2 = (x - 0.7) ** 2 + (y + 0.4) ** 2
+    rho = np.where(r2 < 1.9, 1.0, 0.05)
+    return np.stack([0.3 * rho, 0 * x, rho, 1.0 / 0.4 + 0.045 * rho], axis=-1)
+
+
 def ic_blast(x, y):
     r2 = (x - 0.45) ** 2 + (y - 0.05) ** 2
     p = np.where(r2 < 0.01, 500.0, 0.01)

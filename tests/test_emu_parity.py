@@ -11,8 +11,8 @@ import numpy as np
 import pytest
 
 from cases import ALL_FLUXES, BASELINE_HORIZON, BASELINE_SMALL, BASES, TOL_RHS, TOL_STEP_SHOCK, TOL_STEP_SMOOTH
-from helpers import (check_horizons, DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, Case, emu_lib, ic_dmr, ic_pulse, ic_smooth, ic_sod, ic_step,
-                     ic_vortex)
+from helpers import (check_horizons, DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, Case, emu_lib, ic_disc_box, ic_dmr, ic_pulse, ic_pulse_box,
+                     ic_smooth, ic_sod, ic_step, ic_vortex)
 
 
 def _rhs_ok(c):
@@ -452,12 +452,46 @@ def test_q1_mapping_refusals():
     ids = (4, 2, 1, 3)
     skew = ("rectangle_skew", [4, 4, -5, 5, -5, 5, *ids, 0.15, 0])
     for kw in (dict(basis="Pk", degree=1, mapping="q1"), dict(basis="Qk", degree=1, mapping="q1", limiter="TVB"),
-               dict(basis="Qk", degree=1, mapping="q1", pos_lim=True), dict(basis="Qk", degree=1, mapping="cartesian")):
+               dict(basis="Qk", degree=1, mapping="cartesian")):
         params, pair = abi.make_params(bc=PERIODIC_BOX, flux="lxf", **kw)
         mesh = abi.Mesh(skew[0], skew[1], lib=emu_lib())
         flat = mesh.flatten(params, pair)
         with pytest.raises(abi.DfloError):
             abi.Engine(flat, params, lib=emu_lib(), prefix="dflo_emu_")
+
+
+@pytest.mark.parametrize("k,ic", [(1, ic_pulse_box), (2, ic_disc_box), (3, ic_disc_box)])
+def test_q1_mapping_positivity_limiter(k, ic):
+    """The positivity limiter on mapped cells (the reference admits it: parameters.cc:536-550 refuses only TVB and Pk off
+    Cartesian grids): positivity.cc evaluates the solution at GLL x Gauss points of the unit cell and scales about the
+    cell average taken with the mapped JxW.  Skewed quadrilaterals with mixed orientations; the limiter must act (both
+    the density and the pressure stage) and its decisions must agree cell by cell."""
+    ids = (4, 2, 1, 3)
+    c = Case(("rectangle_skew", [10, 10, -5, 5, -5, 5, *ids, 0.15, 1]), PERIODIC_BOX, ic, basis="Qk", degree=k, flux="lxf",
+             pos_lim=True, cfl=0.15, mapping="q1", compat="mpi")
+    acted, flips = 0, 0
+    for _ in range(4):
+        flips += c.step()[0]
+        acted |= int(np.bitwise_or.reduce(c.oracle.limited_flags()))
+    assert c.rel_err() <= TOL_STEP_SHOCK and flips == 0
+    assert acted & 2 and acted & 4, "the limiter never acted: the case does not test it"
+    c.close()
+
+
+def test_q1_mapping_positivity_limiter_sharded():
+    """positivity on mapped cells over two ranks (one ghost layer; the limiter is local to a cell): bit for bit the
+    single-rank result"""
+    ids = (4, 2, 1, 3)
+    args = (("rectangle_skew", [10, 10, -5, 5, -5, 5, *ids, 0.15, 1]), PERIODIC_BOX, ic_disc_box)
+    prm = dict(basis="Qk", degree=2, flux="lxf", pos_lim=True, cfl=0.15, mapping="q1", compat="mpi")
+    one, two = Case(*args, **prm), Case(*args, world=2, **prm)
+    for _ in range(3):
+        one.step()
+        two.step()
+    assert np.array_equal(one.solution(), two.solution())
+    assert two.rel_err() <= TOL_STEP_SHOCK
+    one.close()
+    two.close()
 
 
 @pytest.mark.parametrize("world", [2, 3])

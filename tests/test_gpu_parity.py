@@ -6,7 +6,8 @@ import pytest
 
 from cases import ALL_FLUXES, BASELINE_HORIZON, BASELINE_SMALL, BASES, TOL_RHS, TOL_STEP_SHOCK, TOL_STEP_SMOOTH
 from dflo_b200 import abi
-from helpers import (check_horizons, DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, Case, ic_dmr, ic_pulse, ic_smooth, ic_sod, ic_vortex)
+from helpers import (check_horizons, DMR_BC, PERIODIC_BOX, SOD_BC, STEP_BC, Case, ic_disc_box, ic_dmr, ic_pulse, ic_pulse_box, ic_smooth,
+                     ic_sod, ic_vortex)
 
 pytestmark = pytest.mark.gpu
 
@@ -421,8 +422,9 @@ def test_run_loop_output_schedule_and_vtu_files(tmp_path):
 # ---------------------------------------------------------------------------------------------
 def _q1_case(k, flux, rotate, bc, ic, n=8, **extra):
     ids = (4, 2, 1, 3)
+    cfl = extra.pop("cfl", 0.05 if flux == "kep" else 0.3)
     return Case(("rectangle_skew", [n, n, -5, 5, -5, 5, *ids, 0.15, rotate]), bc, ic, backend="cuda", basis="Qk", degree=k, flux=flux,
-                cfl=0.05 if flux == "kep" else 0.3, mapping="q1", **extra)
+                cfl=cfl, mapping="q1", **extra)
 
 
 @pytest.mark.parametrize("rotate", [0, 1])
@@ -447,6 +449,31 @@ def test_q1_mapping_rhs_and_steps_periodic(k, flux, rotate):
         t += dt
     te, _ = c.engine.advance(2, elapsed=c.t)
     assert abs(te - t) <= 1e-12 * t and c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
+@pytest.mark.parametrize("k,ic", [(1, ic_pulse_box), (2, ic_disc_box), (3, ic_disc_box)])
+def test_q1_mapping_positivity_limiter(k, ic):
+    """The positivity limiter on mapped cells (positivity.cc works on unit-cell point values and the mapped cell average;
+    parameters.cc:536-550 refuses only TVB and Pk off Cartesian grids): it must act -- density and pressure stage -- with
+    the oracle's decisions in every cell, through rk_stage and through whole steps on the device."""
+    c = _q1_case(k, "lxf", 1, PERIODIC_BOX, ic, n=10, compat="mpi", pos_lim=True, cfl=0.15)
+    acted, flips = 0, 0
+    for _ in range(4):
+        flips += c.step()[0]
+        acted |= int(np.bitwise_or.reduce(c.oracle.limited_flags()))
+    assert c.rel_err() <= TOL_STEP_SHOCK and flips == 0
+    assert acted & 2 and acted & 4, "the limiter never acted: the case does not test it"
+    o, t = c.oracle, c.t
+    for _ in range(2):
+        dt = o.compute_dt(t)
+        for rk in range(o.n_rk):
+            assert o.rk_stage(rk, dt)[0] == 0
+        o.commit_step()
+        t += dt
+    te, _ = c.engine.advance(2, elapsed=c.t)
+    c.engine.poll_error()
+    assert abs(te - t) <= 1e-12 * t and c.rel_err() <= TOL_STEP_SHOCK
     c.close()
 
 

@@ -183,6 +183,13 @@ def test_prm_rejects_undeclared_keys_and_bad_combinations(lib, tmp_path):
     h = L.dflo_claw_create(str(p).encode(), b"sod_tube 10 2", None, 0)
     assert h, L.dflo_host_last_error()
     L.dflo_claw_destroy(h)
+    # the positivity limiter alone is admitted on mapped cells (parameters.cc:536-550 refuses only TVB and Pk there)
+    p = tmp_path / "q1_positivity.prm"
+    p.write_text(base.replace("set mapping   = cartesian", "set mapping   = q1").replace("set type = TVB", "set type = none")
+                 .replace("set basis     = Pk", "set basis     = Qk"))
+    h = L.dflo_claw_create(str(p).encode(), b"sod_tube 10 2", None, 0)
+    assert h, L.dflo_host_last_error()
+    L.dflo_claw_destroy(h)
     # src/ does not know periodic boundaries (SURVEY 8a forks): compat=src rejects them, compat=mpi accepts
     vort = os.path.join(PRM_DIR, "cfg1_isentropic_vortex_Q1_lxf.prm").encode()
     h = L.dflo_claw_create(vort, b"isentropic_vortex 4", None, abi.COMPAT["mpi"])
