@@ -624,10 +624,11 @@ namespace dflo
          hanging = mesh.n_hanging_faces > 0;
          if (hanging)
          {
-            // the limiters' neighbour lists are same-level (claw.cc:336-380 asserts level or level - 1 but TVB / positivity are
-            // not restated for it); the Qk basis only (as under mapping = q1)
-            if (p.basis != DFLO_BASIS_QK || p.limiter_type != DFLO_LIMITER_NONE || p.pos_lim)
-               return fail (DFLO_E_UNSUPPORTED, "faces with hanging nodes: Qk basis without limiters only");
+            // the TVB / minmax limiters' neighbour lists are same-level (claw.cc:336-380 asserts level or level - 1 but the
+            // limiters are not restated for it); the Qk basis only (as under mapping = q1).  The positivity limiter is local
+            // to a cell and runs as it is
+            if (p.basis != DFLO_BASIS_QK || p.limiter_type != DFLO_LIMITER_NONE)
+               return fail (DFLO_E_UNSUPPORTED, "faces with hanging nodes: Qk basis without the TVB / minmax limiter only");
             if (!mesh.cell_vertices || !mesh.neighbor_face || !mesh.hanging) return fail (DFLO_E_INVALID, "hanging nodes need cell_vertices, neighbor_face and the hanging table");
          }
          if (p.mapping == DFLO_MAPPING_Q1)

@@ -108,7 +108,7 @@ typedef struct
    const double *cell_vertices;   /* [n_cells][4][2] vertices in deal.II's lexicographic order (cell->vertex(0..3)) */
    const uint8_t *neighbor_face;  /* [n_cells][4] the neighbour's local number of the shared face; DFLO_FACE_FLIP in
                                      face_flags when the two cells run along the face in opposite directions */
-   /* faces with a hanging node (needs cell_vertices / neighbor_face; no limiters): */
+   /* faces with a hanging node (needs cell_vertices / neighbor_face; no TVB / minmax limiter): */
    int32_t n_hanging_faces;
    const int32_t *hanging;        /* [n_hanging_faces][6] coarse cell, its face, then the two fine cells in the order of the
                                      coarse line: fine cell 0, its face, fine cell 1, its face */

@@ -1521,9 +1521,10 @@ oracle_ctx *oracle_create (int nv, const double *V, int nc, const int *C, int nb
          }
          o->subface[f][child].init (fe, x, y, w);
       }
-   if (!o->hanging.empty () && (prm->limiter_type != ORACLE_LIMITER_NONE || prm->pos_lim || prm->shock_indicator != 0))
+   if (!o->hanging.empty () && (prm->limiter_type != ORACLE_LIMITER_NONE || prm->shock_indicator != 0))
    {
-      g_error = "hanging nodes: no limiters (the limiters' neighbour lists are same-level)";
+      // the positivity limiter is local to a cell and runs next to hanging nodes as it is
+      g_error = "hanging nodes: no TVB / minmax limiter or shock indicator (their neighbour lists are same-level)";
       delete o;
       return nullptr;
    }

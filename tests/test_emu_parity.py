@@ -605,13 +605,36 @@ def test_hanging_nodes_free_stream_conservation_and_boundaries():
 def test_hanging_nodes_refusals():
     ids = (4, 2, 1, 3)
     mesh = ("rectangle_refined", [6, 6, -5, 5, -5, 5, *ids, 2, 4, 2, 4])
-    for kw in (dict(basis="Pk", degree=1), dict(basis="Qk", degree=1, limiter="TVB"), dict(basis="Qk", degree=1, pos_lim=True)):
+    for kw in (dict(basis="Pk", degree=1), dict(basis="Qk", degree=1, limiter="TVB")):
         params, pair = abi.make_params(bc={}, flux="lxf", **kw)
         m = abi.Mesh(mesh[0], mesh[1], lib=emu_lib())
         flat = m.flatten(params, pair)
         assert flat.contents.n_hanging_faces == 8
         with pytest.raises(abi.DfloError):
             abi.Engine(flat, params, lib=emu_lib(), prefix="dflo_emu_")
+
+
+@pytest.mark.parametrize("mapping,world", [("cartesian", 1), ("q1", 1), ("cartesian", 2)])
+def test_hanging_nodes_positivity_limiter(mapping, world):
+    """The positivity limiter next to hanging nodes (it is local to a cell): a refined patch whose rim cuts the edge of the
+    dense disc, both limiter stages acting, the oracle's decision in every cell; sharded = single bit for bit."""
+    ids = (4, 2, 1, 3)
+    args = (("rectangle_refined", [10, 10, -5, 5, -5, 5, *ids, 4, 8, 3, 7]), PERIODIC_BOX, ic_disc_box)
+    prm = dict(basis="Qk", degree=2, flux="lxf", pos_lim=True, cfl=0.1, mapping=mapping, compat="mpi")
+    c = Case(*args, world=world, **prm)
+    one = Case(*args, **prm) if world > 1 else None
+    acted, flips = 0, 0
+    for _ in range(4):
+        flips += c.step()[0]
+        acted |= int(np.bitwise_or.reduce(c.oracle.limited_flags()))
+        if one:
+            one.step()
+    assert c.rel_err() <= TOL_STEP_SHOCK and flips == 0
+    assert acted & 2 and acted & 4, "the limiter never acted: the case does not test it"
+    if one:
+        assert np.array_equal(one.solution(), c.solution())
+        one.close()
+    c.close()
 
 
 @pytest.mark.parametrize("world", [2, 3])

@@ -539,8 +539,24 @@ def test_compression_corner_driver_run(tmp_path):
 # ---------------------------------------------------------------------------------------------
 def _refined_case(k, flux, mapping, bc, ic, patch=(2, 5, 1, 4), n=(7, 6), rotate=0, **extra):
     ids = (4, 2, 1, 3)
+    cfl = extra.pop("cfl", 0.05 if flux == "kep" else 0.3)
     return Case(("rectangle_refined", [n[0], n[1], -5, 5, -5, 5, *ids, *patch, rotate]), bc, ic, backend="cuda", basis="Qk", degree=k,
-                flux=flux, cfl=0.05 if flux == "kep" else 0.3, mapping=mapping, **extra)
+                flux=flux, cfl=cfl, mapping=mapping, **extra)
+
+
+@pytest.mark.parametrize("k,mapping,rotate", [(1, "cartesian", 0), (2, "cartesian", 0), (3, "cartesian", 0), (1, "q1", 1), (2, "q1", 1)])
+def test_hanging_nodes_positivity_limiter(k, mapping, rotate):
+    """The positivity limiter next to hanging nodes (local to a cell; the refined patch's rim cuts the edge of the dense
+    disc): both limiter stages act with the oracle's decision in every cell."""
+    c = _refined_case(k, "lxf", mapping, PERIODIC_BOX, ic_pulse_box if k == 1 else ic_disc_box, patch=(4, 8, 3, 7), n=(10, 10), rotate=rotate,
+                      compat="mpi", pos_lim=True, cfl=0.1)
+    acted, flips = 0, 0
+    for _ in range(4):
+        flips += c.step()[0]
+        acted |= int(np.bitwise_or.reduce(c.oracle.limited_flags()))
+    assert c.rel_err() <= TOL_STEP_SHOCK and flips == 0
+    assert acted & 4 and (acted & 2 or k == 1), "the limiter never acted: the case does not test it"
+    c.close()
 
 
 @pytest.mark.parametrize("mapping,rotate", [("cartesian", 0), ("q1", 0), ("q1", 1)])
