@@ -1,4 +1,6 @@
-for c in cfg3 cfg4 cfg5; do
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r02j_launches_$c.csv python scripts/bench_configs.py --configs $c --steps 3 > /dev/null 2>&1
-done
-ls -la gpurun_out/r02j_launches_*.csv
+python scripts/bench_configs.py --configs cfg4 --steps 20 2>&1 | grep config | python -c "
+import json,sys
+for l in sys.stdin:
+    d=json.loads(l); print(d['config'], d['ms_per_step'], round(d['mdof_per_s']))"
+DFLO_B200_KTRACE=1 python scripts/bench_configs.py --configs cfg4 --steps 6 2>&1 | grep -E "ktrace.*(BcEval)"
+(timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3)
