@@ -286,6 +286,26 @@ def test_pk_cell_kernel_rhs_and_step_periodic(pk_cell_kernel, k, flux):
     c.close()
 
 
+@pytest.mark.parametrize("k,flux", [(1, "roe"), (2, "hllc"), (2, "kfvs"), (2, "lxf")])
+def test_pk_cell_kernel_several_blocks(pk_cell_kernel, k, flux):
+    """More cells than one block of 128 (and a ragged last block): faces between blocks and periodic pairs go through the
+    job list, faces inside a block are solved once and handed to the neighbour -- periodic box of 196 cells, and the
+    three-block forward-step mesh (252 cells) with every boundary kind."""
+    c = Case(("isentropic_vortex", [14]), PERIODIC_BOX, ic_vortex, basis="Pk", degree=k, flux=flux, cfl=0.5)
+    _rhs_ok(c)
+    c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+    bc = {1: "inflow", 2: "slip", 3: "pressure", 0: "farfield"}
+    c = Case(("forward_step", [0.1]), bc, ic_smooth, basis="Pk", degree=k, flux=flux, cfl=0.5, gravity=0.3)
+    assert c.oracle.n_cells > 128
+    c.set_boundary(values=(0.5, 0.1, 1.2, 3.0), wiggle=0.1)
+    _rhs_ok(c)
+    c.step()
+    assert c.rel_err() <= TOL_STEP_SMOOTH
+    c.close()
+
+
 def test_pk_cell_kernel_mesh_check():
     """pk_cell_mesh_ok (cell_stage.cuh): the cell kernel hands the moments of a face to the neighbour's face F ^ 1, so it
     is only admitted when every interior face is seen as F / F ^ 1 with equal flags by its two (updated) cells; otherwise
