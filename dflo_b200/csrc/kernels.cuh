@@ -1217,21 +1217,24 @@ namespace dflo
       static constexpr int NS = LK::NS, D = LK::D, NGLL = LK::NGLL, NPOS = LK::NPOS;
       // block form: CPB cells are staged with coalesced loads into shared memory (odd row stride:
       // the per-thread walks over a cell are then free of bank conflicts), one thread per cell
-      // works on its row, changed cells are written back
-#ifndef DFLO_LIM_Q3_THREADS
-#define DFLO_LIM_Q3_THREADS 64
+      // works on its row, changed cells are written back.  A block is ONE warp (DFLO_LIM_THREADS = 32): the kernel is a
+      // load phase followed by a long arithmetic phase, and many small blocks interleave the two better than a few large
+      // ones -- measured on the Q3 limiter of cfg5: 128 threads x 3 blocks 113 us, 64 x 6 110 us, 32 x 12 103 us.
+#ifndef DFLO_LIM_THREADS
+#define DFLO_LIM_THREADS 32
 #endif
-      static constexpr int THREADS = D > 64 ? 64 : D == 64 ? DFLO_LIM_Q3_THREADS : 128;
+      static constexpr int THREADS = DFLO_LIM_THREADS;
       static constexpr int CPB = THREADS;
-      // up to Q2 / P3 four blocks fit the shared memory of an SM: hold the compiler to 128 registers for them -- except
-      // the P2 TVB + positivity chain (cfg3), which spills 528 bytes at 128 registers: three blocks, 168 registers
-#ifndef DFLO_LIM_P2_BLOCKS
-#define DFLO_LIM_P2_BLOCKS 3
+      // register budget as resident WARPS per SM: up to Q2 / P3 sixteen (128 registers) -- except the P2 TVB + positivity
+      // chain (cfg3), which spills 528 bytes at 128 registers -- and twelve (168 registers) up to Q3; beyond, what fits
+#ifndef DFLO_LIM_P2_WARPS
+#define DFLO_LIM_P2_WARPS 12
 #endif
-#ifndef DFLO_LIM_Q3_BLOCKS
-#define DFLO_LIM_Q3_BLOCKS 3
+#ifndef DFLO_LIM_Q3_WARPS
+#define DFLO_LIM_Q3_WARPS 12
 #endif
-      static constexpr int MIN_BLOCKS = (BASIS == BASIS_PK && N1 == 3 && MINMAX == 0) ? DFLO_LIM_P2_BLOCKS : D <= 40 ? 4 : D <= 64 ? DFLO_LIM_Q3_BLOCKS * (128 / DFLO_LIM_Q3_THREADS) : 1;
+      static constexpr int WARPS = (BASIS == BASIS_PK && N1 == 3 && MINMAX == 0) ? DFLO_LIM_P2_WARPS : D <= 40 ? 16 : D <= 64 ? DFLO_LIM_Q3_WARPS : 4;
+      static constexpr int MIN_BLOCKS = WARPS * 32 / THREADS;
       static constexpr int NPHASE = 2;
       static constexpr int ROW = D + 1;
       static constexpr int SMEM_DOUBLES = CPB * ROW;
