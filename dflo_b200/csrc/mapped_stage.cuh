@@ -82,7 +82,10 @@ namespace dflo
    {
       typedef MappedStageArgs Args;
       static constexpr int NQ = N1 * N1, D = 4 * NQ;
-      static constexpr int CPB = NQ >= 128 ? 1 : 128 / NQ;          // cells per block
+#ifndef DFLO_MAPPED_BLOCK
+#define DFLO_MAPPED_BLOCK 128 // threads per block; one-warp blocks (32) measured 0.3675 vs 0.374 ms per step on the q1 bench entry: within noise, not taken
+#endif
+      static constexpr int CPB = NQ >= DFLO_MAPPED_BLOCK ? 1 : DFLO_MAPPED_BLOCK / NQ; // cells per block
       static constexpr int THREADS = (CPB * NQ + 31) / 32 * 32;
 #ifndef DFLO_MAPPED_MIN_BLOCKS
 #define DFLO_MAPPED_MIN_BLOCKS 6
@@ -90,7 +93,7 @@ namespace dflo
       // 85 registers, 24 warps per SM.  Left alone the allocation had grown to 196 registers with the sub-face branches of the
       // hanging-node faces (2 blocks, 8 warps per SM), although most launches never take them.  Measured on the 256 x 256 Q3
       // skewed mesh, ms per step: 2 blocks 0.715, 4 blocks 0.427, 6 blocks 0.374 (a few bytes of spills), 8 blocks 0.398
-      static constexpr int MIN_BLOCKS = DFLO_MAPPED_MIN_BLOCKS;
+      static constexpr int MIN_BLOCKS = DFLO_MAPPED_MIN_BLOCKS * 128 / DFLO_MAPPED_BLOCK;
       static constexpr int NPHASE = 4;
       static constexpr int NTAB = N1 * N1 + 3 * N1;
       static constexpr int O_TAB = 0;

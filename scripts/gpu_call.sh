@@ -1,5 +1,2 @@
-python scripts/bench_configs.py --configs cfg3,cfg4,cfg5 --steps 20 2>&1 | grep config | python -c "
-import json,sys
-for l in sys.stdin:
-    d=json.loads(l); print(d['config'], d['ms_per_step'], round(d['mdof_per_s']))"
-(timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -2)
+# scratch: the command of the last ad-hoc GPU call (scripts/gpu_round.sh is the maintained entry)
+(timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -6)
